@@ -1,0 +1,91 @@
+/*
+ * lasr_b200.h -- C ABI of the B200-native LASR render hot path (liblasr_b200.so).
+ *
+ * Drop-in boundary for the reference's pybind module `soft_renderer.cuda.soft_rasterize`
+ * (third_party/softras/soft_renderer/cuda/soft_rasterize_cuda.cpp:59-76, 94-114, 135-138)
+ * and for the dense geometry/loss glue either side of it (nnutils/geom_utils.py:27-71,
+ * nnutils/mesh_net.py:264-267, 304-311, 372-447).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in
+ *     `_host`; all tensors are contiguous, float32 / int32, laid out exactly as the reference's
+ *     tensors are (shapes in the comments);
+ *   - like the reference, the CALLER owns every buffer (soft_rasterize.py:47-62, 88-100); nothing
+ *     is allocated inside; scratch comes from `workspace` (size from *_workspace_bytes);
+ *   - `stream` is a cudaStream_t passed as void* (the reference launches on the legacy default
+ *     stream, .cu:702,717,781; we take the caller's current stream explicitly);
+ *   - every entry point returns 0 on success, non-zero on error (and records a message for
+ *     lasr_b200_last_error()); CUDA launch errors are reported, not printf'ed and swallowed as in
+ *     the reference (.cu:710-712, 741-743, 808-810);
+ *   - enum encodings are the reference's (functional/soft_rasterize.py:22-25):
+ *       func_id_dist  {hard:0, barycentric:1, euclidean:2}
+ *       func_id_rgb   {hard:0, softmax:1}
+ *       func_id_alpha {hard:0, sum:1, prod:2}
+ *       texture_sample_type {surface:0, vertex:1}
+ *   - `dist_eps` is the ALREADY TRANSFORMED value log(1/dist_eps - 1) (soft_rasterize.py:35), as
+ *     in the reference's pybind call.
+ */
+#ifndef LASR_B200_H_
+#define LASR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Library identification / diagnostics. */
+int lasr_b200_abi_version(void);
+const char* lasr_b200_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+uint64_t lasr_b200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Soft rasterizer.
+ * Replaces forward_soft_rasterize / backward_soft_rasterize
+ * (soft_rasterize_cuda.cpp:59-91, 94-132; kernels soft_rasterize_cuda_kernel.cu:245-668).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Scratch needed by one forward or backward call.  Replaces the reference's `faces_info`
+ * [N,F,27] buffer (soft_rasterize.py:47): we keep only a packed per-face pixel window. */
+size_t lasr_b200_raster_workspace_bytes(int batch_size, int num_faces, int image_size);
+
+/* forward_soft_rasterize(faces, textures, faces_info, aggrs_info, soft_colors, image_size, near,
+ *                        far, eps, sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb,
+ *                        func_id_alpha, texture_sample_type, double_side)
+ *   faces        [N,F,9]    in   (x0 y0 z0 x1 y1 z1 x2 y2 z2 per face)
+ *   textures     [N,F,T,3]  in   (T = texture_size: R*R texels for 'surface', 3 for 'vertex')
+ *   aggrs_info   [N,2,S,S]  out  (softmax: sum,max | hard: depth_min, face_index)
+ *   soft_colors  [N,4,S,S]  in/out: RGB planes pre-filled with the background colour by the
+ *                                caller (read at .cu:361,364), overwritten with RGBA
+ *   near_far_dev optional device pointer to {near, far}; when non-NULL it overrides the two
+ *                scalars so LASR's 0-dim CUDA tensors (mesh_net.py:304-311) need no host sync. */
+int lasr_b200_raster_forward(const float* faces, const float* textures, float* aggrs_info,
+                             float* soft_colors, void* workspace, size_t workspace_bytes,
+                             int batch_size, int num_faces, int image_size, int texture_size,
+                             float near_, float far_, const float* near_far_dev, float eps,
+                             float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
+                             int func_id_rgb, int func_id_alpha, int texture_sample_type,
+                             int double_side, void* stream);
+
+/* backward_soft_rasterize(faces, textures, soft_colors, faces_info, aggrs_info, grad_faces,
+ *                         grad_textures, grad_soft_colors, <same scalars>)
+ *   grad_faces    [N,F,9]    out (overwritten; the reference accumulates into a zeroed buffer)
+ *   grad_textures [N,F,T,3]  out (overwritten)
+ * Deterministic: every face's gradient is a private, fixed-order sum (no float atomics, unlike
+ * .cu:606,622,657-666). */
+int lasr_b200_raster_backward(const float* faces, const float* textures, const float* soft_colors,
+                              const float* aggrs_info, float* grad_faces, float* grad_textures,
+                              const float* grad_soft_colors, void* workspace,
+                              size_t workspace_bytes, int batch_size, int num_faces,
+                              int image_size, int texture_size, float near_, float far_,
+                              const float* near_far_dev, float eps, float sigma_val,
+                              int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
+                              int func_id_alpha, int texture_sample_type, int double_side,
+                              void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LASR_B200_H_ */

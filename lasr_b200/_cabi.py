@@ -1,0 +1,125 @@
+"""ctypes binding of liblasr_b200.so -- the C ABI declared in include/lasr_b200.h.
+
+This is the only place Python touches native code.  PyTorch supplies device memory
+(``tensor.data_ptr()``) and the current CUDA stream; no torch type crosses the boundary.
+The library must exist: there is no CPU or eager fallback, a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+from . import _build
+
+_lib = None
+
+_c = ctypes
+_RASTER_SCALARS = [_c.c_int, _c.c_int, _c.c_int, _c.c_int,      # N, F, S, T
+                   _c.c_float, _c.c_float, _c.c_void_p,          # near, far, near_far_dev
+                   _c.c_float, _c.c_float, _c.c_int, _c.c_float, _c.c_float,  # eps, sigma, dist, dist_eps, gamma
+                   _c.c_int, _c.c_int, _c.c_int, _c.c_int,       # rgb, alpha, sample, double_side
+                   _c.c_void_p]                                   # stream
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            raise NativeLibraryMissing(
+                f"{path} not found: build it with `python -m lasr_b200._build` "
+                "(lasr_b200 has no CPU/eager fallback for its CUDA kernels)")
+        L = ctypes.CDLL(path)
+        L.lasr_b200_abi_version.restype = _c.c_int
+        L.lasr_b200_last_error.restype = _c.c_char_p
+        L.lasr_b200_launch_count.restype = _c.c_uint64
+        L.lasr_b200_raster_workspace_bytes.restype = _c.c_size_t
+        L.lasr_b200_raster_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
+        L.lasr_b200_raster_forward.restype = _c.c_int
+        L.lasr_b200_raster_forward.argtypes = [_c.c_void_p] * 5 + [_c.c_size_t] + _RASTER_SCALARS
+        L.lasr_b200_raster_backward.restype = _c.c_int
+        L.lasr_b200_raster_backward.argtypes = [_c.c_void_p] * 8 + [_c.c_size_t] + _RASTER_SCALARS
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = [
+    "lasr_b200_abi_version", "lasr_b200_last_error", "lasr_b200_launch_count",
+    "lasr_b200_raster_workspace_bytes", "lasr_b200_raster_forward", "lasr_b200_raster_backward",
+]
+
+
+def launch_count() -> int:
+    return int(lib().lasr_b200_launch_count())
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {lib().lasr_b200_last_error().decode()}")
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise CudaTensorRequired(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+class CudaTensorRequired(TypeError, RuntimeError):
+    """The reference means to raise TypeError for CPU tensors (functional/soft_rasterize.py:111-112)
+    and in practice raises RuntimeError from CHECK_CUDA (soft_rasterize_cuda.cpp:54,78-82); this is
+    both."""
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def raster_workspace(N: int, F: int, S: int, device) -> torch.Tensor:
+    nbytes = int(lib().lasr_b200_raster_workspace_bytes(N, F, S))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def raster_forward(faces, textures, aggrs_info, soft_colors, workspace, image_size, near, far, near_far_dev, eps,
+                   sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, texture_sample_type,
+                   double_side):
+    for t, nm in ((faces, "faces"), (textures, "textures"), (aggrs_info, "aggrs_info"), (soft_colors, "soft_colors")):
+        _require_cuda_f32(t, nm)
+    N, F = faces.shape[:2]
+    T = textures.shape[2]
+    with torch.cuda.device(faces.device):
+        rc = lib().lasr_b200_raster_forward(
+            faces.data_ptr(), textures.data_ptr(), aggrs_info.data_ptr(), soft_colors.data_ptr(),
+            workspace.data_ptr(), workspace.numel(), N, F, int(image_size), T, float(near), float(far),
+            near_far_dev.data_ptr() if near_far_dev is not None else None, float(eps), float(sigma_val),
+            int(func_id_dist), float(dist_eps), float(gamma_val), int(func_id_rgb), int(func_id_alpha),
+            int(texture_sample_type), int(bool(double_side)), _stream_ptr())
+    _check(rc, "lasr_b200_raster_forward")
+
+
+def raster_backward(faces, textures, soft_colors, aggrs_info, grad_faces, grad_textures, grad_soft_colors, workspace,
+                    image_size, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
+                    func_id_rgb, func_id_alpha, texture_sample_type, double_side):
+    for t, nm in ((faces, "faces"), (textures, "textures"), (soft_colors, "soft_colors"), (aggrs_info, "aggrs_info"),
+                  (grad_faces, "grad_faces"), (grad_textures, "grad_textures"),
+                  (grad_soft_colors, "grad_soft_colors")):
+        _require_cuda_f32(t, nm)
+    N, F = faces.shape[:2]
+    T = textures.shape[2]
+    with torch.cuda.device(faces.device):
+        rc = lib().lasr_b200_raster_backward(
+            faces.data_ptr(), textures.data_ptr(), soft_colors.data_ptr(), aggrs_info.data_ptr(),
+            grad_faces.data_ptr(), grad_textures.data_ptr(), grad_soft_colors.data_ptr(), workspace.data_ptr(),
+            workspace.numel(), N, F, int(image_size), T, float(near), float(far),
+            near_far_dev.data_ptr() if near_far_dev is not None else None, float(eps), float(sigma_val),
+            int(func_id_dist), float(dist_eps), float(gamma_val), int(func_id_rgb), int(func_id_alpha),
+            int(texture_sample_type), int(bool(double_side)), _stream_ptr())
+    _check(rc, "lasr_b200_raster_backward")

@@ -1,0 +1,240 @@
+// raster_common.cuh -- per-face geometry and per-(pixel,face) evaluation shared by the forward
+// (tile-binned, pixel-parallel) and backward (face-parallel) soft-rasterizer kernels.
+//
+// What is computed is the reference's SoftRas model
+// (third_party/softras/soft_renderer/cuda/soft_rasterize_cuda_kernel.cu:24-216, 245-305); how it
+// is computed is ours.  One numerical design rule matters for parity:
+//
+//   The geometric predicates (face_inv / barycentrics / inside-outside / edge selection) are
+//   ill-conditioned for edge-on sliver faces: a 1-ulp change in `det` flips a pixel between
+//   "inside" (D ~ 1) and "outside" (D ~ 0).  To agree with the reference *as compiled by nvcc*
+//   (FMA contraction on), those few expressions are written with explicit round-to-nearest
+//   intrinsics in exactly the association nvcc gives the reference's source
+//   (a*b + c*d -> fma(a, b, c*d); a*b + c*d + e*f -> fma(e, f, fma(a, b, c*d));
+//    a*b - c*d -> fma(a, b, -(c*d)); checked against `cuobjdump -sass` of oracle/_ref).
+//   Everything downstream (sigmoid, depth softmax, colour blend) is well conditioned and free to
+//   use faster formulations.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lasr {
+
+struct RasterArgs {
+  const float* faces;        // [N,F,9]
+  const float* textures;     // [N,F,T,3]
+  float* aggrs_info;         // [N,2,S,S]
+  float* soft_colors;        // [N,4,S,S]
+  const float* grad_soft_colors;  // [N,4,S,S]   (backward)
+  float* grad_faces;         // [N,F,9]          (backward)
+  float* grad_textures;      // [N,F,T,3]        (backward)
+  uint2* face_window;        // [N,F] packed pixel windows (workspace)
+  const float* near_far_dev; // optional {near, far} on device
+  int N, F, S, T, R;
+  float near_, far_, eps, sigma, dist_eps, gamma;
+  int dist, rgb, alpha, sample, double_side;
+};
+
+// ---- reference-shaped sums of products (see header comment) ---------------------------------
+__device__ __forceinline__ float dot2(float a, float b, float c, float d) {
+  return __fmaf_rn(a, b, __fmul_rn(c, d));
+}
+__device__ __forceinline__ float dot3(float a, float b, float c, float d, float e, float f) {
+  return __fmaf_rn(e, f, __fmaf_rn(a, b, __fmul_rn(c, d)));
+}
+__device__ __forceinline__ float cross2(float a, float b, float c, float d) {
+  return __fmaf_rn(a, b, -__fmul_rn(c, d));
+}
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// Pixel-centre coordinate, (2*i + 1 - S) / S evaluated in double and rounded once (.cu:345-346).
+__device__ __forceinline__ float pixel_coord(int i, int S) {
+  return (float)((2.0 * (double)i + 1.0 - (double)S) / (double)S);
+}
+
+// ---- per-face derived quantities (.cu:245-305 + the border box of :32-38) -------------------
+struct FaceGeom {
+  float inv[9];       // inverse of [[x0 x1 x2],[y0 y1 y2],[1 1 1]] (rows give barycentrics)
+  float x[3], y[3], z[3];
+  float a[3][3];      // a[e][j] = sym[e][j] - sym[(e+1)%3][j],  sym = P P^T + 1
+  float lox, hix, loy, hiy;  // bounding box dilated by sqrt(threshold)
+  int obt;            // index of the (first) obtuse corner, -1 if none
+  bool front;
+};
+
+__device__ __forceinline__ void face_setup(const float* __restrict__ fv, float sthr, FaceGeom& g) {
+  const float x0 = fv[0], y0 = fv[1], x1 = fv[3], y1 = fv[4], x2 = fv[6], y2 = fv[7];
+  g.x[0] = x0; g.x[1] = x1; g.x[2] = x2;
+  g.y[0] = y0; g.y[1] = y1; g.y[2] = y2;
+  g.z[0] = fv[2]; g.z[1] = fv[5]; g.z[2] = fv[8];
+  // determinant: x2*(y0-y1) + x0*(y1-y2) + x1*(y2-y0)   (.cu:278-281)
+  float det = __fmaf_rn(x1, __fsub_rn(y2, y0), __fmaf_rn(x2, __fsub_rn(y0, y1), __fmul_rn(x0, __fsub_rn(y1, y2))));
+  det = det > 0.f ? fmaxf(det, 1e-10f) : fminf(det, -1e-10f);  // :282
+  const float adj[9] = {__fsub_rn(y1, y2), __fsub_rn(x2, x1), cross2(x1, y2, x2, y1),
+                        __fsub_rn(y2, y0), __fsub_rn(x0, x2), cross2(x2, y0, x0, y2),
+                        __fsub_rn(y0, y1), __fsub_rn(x1, x0), cross2(x0, y1, x1, y0)};
+#pragma unroll
+  for (int k = 0; k < 9; ++k) g.inv[k] = __fdiv_rn(adj[k], det);  // :284-286 (IEEE division)
+  // sym = F F^T with z -> 1 (:288-294); only row differences are ever used (:81-83,132-134)
+  float sym[3][3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sym[j][k] = __fadd_rn(dot2(g.x[j], g.x[k], g.y[j], g.y[k]), 1.0f);
+#pragma unroll
+  for (int e = 0; e < 3; ++e)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) g.a[e][j] = __fsub_rn(sym[e][j], sym[(e + 1) % 3][j]);
+  // first obtuse corner (:296-304)
+  g.obt = -1;
+#pragma unroll
+  for (int k = 2; k >= 0; --k) {
+    const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+    const float d = dot2(__fsub_rn(g.x[k1], g.x[k]), __fsub_rn(g.x[k2], g.x[k]),
+                         __fsub_rn(g.y[k1], g.y[k]), __fsub_rn(g.y[k2], g.y[k]));
+    if (d < 0.f) g.obt = k;  // descending k so the smallest obtuse k wins, as `break` does
+  }
+  g.front = (y2 - y0) * (x1 - x0) < (y1 - y0) * (x2 - x0);  // :41-44
+  g.hix = __fadd_rn(max3(x0, x1, x2), sthr);
+  g.lox = __fsub_rn(min3(x0, x1, x2), sthr);
+  g.hiy = __fadd_rn(max3(y0, y1, y2), sthr);
+  g.loy = __fsub_rn(min3(y0, y1, y2), sthr);
+}
+
+// Conservative inclusive pixel-index window of coordinates in [lo, hi] (the exact predicate is
+// still applied per pixel; this only has to be a superset).  Empty windows come back lo > hi.
+__device__ __forceinline__ void coord_window(float lo, float hi, int S, int& ilo, int& ihi) {
+  const float a = (lo * (float)S + (float)(S - 1)) * 0.5f;
+  const float b = (hi * (float)S + (float)(S - 1)) * 0.5f;
+  // NaN / inf vertices: the reference's behaviour is undefined (out-of-bounds stack writes in
+  // euclidean_p2f_distance when every comparison is false); we cull such faces.
+  if (!(a >= -1e9f && b <= 1e9f && a <= b + 1.f)) { ilo = 1; ihi = 0; return; }
+  ilo = max(0, (int)floorf(a - 0.0625f));
+  ihi = min(S - 1, (int)ceilf(b + 0.0625f));
+}
+
+// ---- the soft fragment of one (pixel, face) pair --------------------------------------------
+struct Fragment {
+  float w[3];        // barycentrics (unclipped)
+  float t[3];        // euclidean: closest point minus w;  barycentric: w
+  float sign, dx, dy, dis;
+  float frag;        // D in the paper
+};
+
+__device__ __forceinline__ bool pixel_inside(const float* w) {  // .cu:47-50
+  return w[0] <= 1.f && w[0] >= 0.f && w[1] <= 1.f && w[1] >= 0.f && w[2] <= 1.f && w[2] >= 0.f;
+}
+
+// .cu:61-151
+__device__ __forceinline__ void euclid_distance(const FaceGeom& g, float xp, float yp, Fragment& fr) {
+  const float w0 = fr.w[0], w1 = fr.w[1], w2 = fr.w[2];
+  if (w0 > 0.f && w1 > 0.f && w2 > 0.f && w0 < 1.f && w1 < 1.f && w2 < 1.f) {
+    float best = 100000000.f, bx = 0.f, by = 0.f;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      const int b = (e + 1) % 3, c = (e + 2) % 3;
+      const float num = __fsub_rn(dot3(w0, g.a[e][0], w1, g.a[e][1], w2, g.a[e][2]), g.a[e][b]);
+      const float q = __fdiv_rn(num, __fsub_rn(g.a[e][e], g.a[e][b]));
+      float t[3];
+      t[e] = q; t[b] = 1.f - q; t[c] = 0.f;
+      t[0] -= w0; t[1] -= w1; t[2] -= w2;
+      const float dx = dot3(t[0], g.x[0], t[1], g.x[1], t[2], g.x[2]);
+      const float dy = dot3(t[0], g.y[0], t[1], g.y[1], t[2], g.y[2]);
+      const float dd = dot2(dx, dx, dy, dy);
+      if (dd < best) { best = dd; bx = dx; by = dy; fr.t[0] = t[0]; fr.t[1] = t[1]; fr.t[2] = t[2]; }
+    }
+    fr.dx = bx; fr.dy = by; fr.sign = 1.f;
+  } else {
+    int e = 0;
+    if (w1 <= 0.f && w2 <= 0.f) {
+      e = 0;
+      if (g.obt == 0 && dot2(xp - g.x[0], g.x[2] - g.x[0], yp - g.y[0], g.y[2] - g.y[0]) > 0.f) e = 2;
+    } else if (w2 <= 0.f && w0 <= 0.f) {
+      e = 1;
+      if (g.obt == 1 && dot2(xp - g.x[1], g.x[0] - g.x[1], yp - g.y[1], g.y[0] - g.y[1]) > 0.f) e = 0;
+    } else if (w0 <= 0.f && w1 <= 0.f) {
+      e = 2;
+      if (g.obt == 2 && dot2(xp - g.x[2], g.x[1] - g.x[2], yp - g.y[2], g.y[1] - g.y[2]) > 0.f) e = 1;
+    } else if (w0 <= 0.f) {
+      e = 1;
+    } else if (w1 <= 0.f) {
+      e = 2;
+    } else {
+      e = 0;
+    }
+    // pick the row of `a` for edge e without dynamic register indexing
+    const float a0 = e == 0 ? g.a[0][0] : (e == 1 ? g.a[1][0] : g.a[2][0]);
+    const float a1 = e == 0 ? g.a[0][1] : (e == 1 ? g.a[1][1] : g.a[2][1]);
+    const float a2 = e == 0 ? g.a[0][2] : (e == 1 ? g.a[1][2] : g.a[2][2]);
+    const float ae = e == 0 ? a0 : (e == 1 ? a1 : a2);
+    const float ab = e == 0 ? a1 : (e == 1 ? a2 : a0);
+    const float num = __fsub_rn(dot3(w0, a0, w1, a1, w2, a2), ab);
+    const float q = __fdiv_rn(num, __fsub_rn(ae, ab));
+    const float qe = fminf(fmaxf(q, 0.f), 1.f);
+    const float qb = fminf(fmaxf(1.f - q, 0.f), 1.f);
+    // t[e] = qe, t[(e+1)%3] = qb, t[(e+2)%3] = 0, then minus w
+    const float t0 = (e == 0 ? qe : (e == 2 ? qb : 0.f)) - w0;
+    const float t1 = (e == 1 ? qe : (e == 0 ? qb : 0.f)) - w1;
+    const float t2 = (e == 2 ? qe : (e == 1 ? qb : 0.f)) - w2;
+    fr.t[0] = t0; fr.t[1] = t1; fr.t[2] = t2;
+    fr.dx = dot3(t0, g.x[0], t1, g.x[1], t2, g.x[2]);
+    fr.dy = dot3(t0, g.y[0], t1, g.y[1], t2, g.y[2]);
+    fr.sign = -1.f;
+  }
+}
+
+// Returns false when the pair is rejected by the distance stage (.cu:389-404 / :556-572).
+template <bool kFast>
+__device__ __forceinline__ bool soft_fragment(const RasterArgs& A, const FaceGeom& g, float xp, float yp,
+                                              float thr, Fragment& fr) {
+  fr.w[0] = __fadd_rn(__fmaf_rn(xp, g.inv[0], __fmul_rn(yp, g.inv[1])), g.inv[2]);  // :24-29
+  fr.w[1] = __fadd_rn(__fmaf_rn(xp, g.inv[3], __fmul_rn(yp, g.inv[4])), g.inv[5]);
+  fr.w[2] = __fadd_rn(__fmaf_rn(xp, g.inv[6], __fmul_rn(yp, g.inv[7])), g.inv[8]);
+  const int dist = kFast ? 2 : A.dist;
+  fr.sign = 0.f; fr.dx = 0.f; fr.dy = 0.f; fr.dis = 0.f;
+  fr.t[0] = fr.w[0]; fr.t[1] = fr.w[1]; fr.t[2] = fr.w[2];
+  if (dist == 0) {
+    fr.frag = pixel_inside(fr.w) ? 1.f : 0.f;
+    return fr.frag != 0.f;
+  } else if (dist == 1) {  // :154-158
+    const float w0 = fr.w[0], w1 = fr.w[1], w2 = fr.w[2];
+    float d = w0 > w1 ? (w1 > w2 ? w2 : w1) : (w0 > w2 ? w2 : w0);
+    d = d > 0.f ? d * d : -(d * d);
+    fr.dis = d;
+    if (-d >= thr) return false;
+    fr.frag = 1.f / (1.f + expf(-d / A.sigma));
+    return true;
+  } else {
+    euclid_distance(g, xp, yp, fr);
+    fr.dis = dot2(fr.dx, fr.dx, fr.dy, fr.dy);
+    if (fr.sign < 0.f && fr.dis >= thr) return false;
+    fr.frag = 1.f / (1.f + expf(-fr.sign * fr.dis / A.sigma));
+    return true;
+  }
+}
+
+// .cu:53-58
+__device__ __forceinline__ void bary_clip(const float* w, float* wc) {
+  wc[0] = fmaxf(fminf(w[0], 1.f), 0.f);
+  wc[1] = fmaxf(fminf(w[1], 1.f), 0.f);
+  wc[2] = fmaxf(fminf(w[2], 1.f), 0.f);
+  const float s = fmaxf(wc[0] + wc[1] + wc[2], 1e-5f);
+  wc[0] /= s; wc[1] /= s; wc[2] /= s;
+}
+
+// 'surface' texel index of .cu:178-194 (may equal R*R: the reference reads the next face's block)
+__device__ __forceinline__ int surface_texel(const float* wc, int R) {
+  const int wx = (int)(wc[0] * R);
+  const int wy = (int)(wc[1] * R);
+  return ((wc[0] + wc[1]) * R - wx - wy <= 1.f) ? (wy * R + wx) : ((R - 1 - wy) * R + (R - 1 - wx));
+}
+
+// warp butterfly sum (fixed order => deterministic)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace lasr

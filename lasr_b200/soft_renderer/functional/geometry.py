@@ -1,0 +1,144 @@
+"""Dense geometry helpers of SoftRas with the reference's signatures
+(third_party/softras/soft_renderer/functional/{face_vertices,vertex_normals,look_at,look,
+orthogonal,perspective,get_points_from_angles,ambient_lighting,directional_lighting}.py).
+
+Plain PyTorch: these are small, bandwidth-trivial ops; the LASR fast path bypasses most of them
+(see lasr_b200/soft_renderer/renderer.py)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def face_vertices(vertices, faces):
+    """[bs, nv, C] gathered by [bs, nf, 3] -> [bs, nf, 3, C] (face_vertices.py:4-22)."""
+    assert vertices.ndimension() == 3
+    assert faces.ndimension() == 3
+    assert vertices.shape[0] == faces.shape[0]
+    assert vertices.shape[2] == 3
+    assert faces.shape[2] == 3
+    bs, nv = vertices.shape[:2]
+    offs = (torch.arange(bs, device=vertices.device, dtype=torch.int64) * nv)[:, None, None]
+    return vertices.reshape(bs * nv, vertices.shape[2])[faces.long() + offs]
+
+
+def vertex_normals(vertices, faces):
+    """Area-weighted vertex normals, F.normalize eps=1e-6 (vertex_normals.py:4-37)."""
+    assert vertices.ndimension() == 3
+    assert faces.ndimension() == 3
+    assert vertices.shape[0] == faces.shape[0]
+    assert vertices.shape[2] == 3
+    assert faces.shape[2] == 3
+    bs, nv = vertices.shape[:2]
+    offs = (torch.arange(bs, device=vertices.device, dtype=torch.int64) * nv)[:, None, None]
+    idx = (faces.long() + offs).view(-1, 3)
+    flat = vertices.reshape(bs * nv, 3)
+    vf = flat[idx]
+    normals = torch.zeros(bs * nv, 3, device=vertices.device, dtype=vertices.dtype)
+    normals.index_add_(0, idx[:, 1], torch.cross(vf[:, 2] - vf[:, 1], vf[:, 0] - vf[:, 1], dim=1))
+    normals.index_add_(0, idx[:, 2], torch.cross(vf[:, 0] - vf[:, 2], vf[:, 1] - vf[:, 2], dim=1))
+    normals.index_add_(0, idx[:, 0], torch.cross(vf[:, 1] - vf[:, 0], vf[:, 2] - vf[:, 0], dim=1))
+    return F.normalize(normals, eps=1e-6, dim=1).reshape(bs, nv, 3)
+
+
+def _as_batch(x, batch_size, device):
+    if isinstance(x, (list, tuple)):
+        x = torch.tensor(x, dtype=torch.float32, device=device)
+    elif isinstance(x, np.ndarray):
+        x = torch.from_numpy(x).to(device)
+    elif torch.is_tensor(x):
+        x = x.to(device)
+    if x.ndimension() == 1:
+        x = x[None, :].repeat(batch_size, 1)
+    return x
+
+
+def look_at(vertices, eye, at=[0, 0, 0], up=[0, 1, 0]):
+    """look_at.py:6-62 (axes normalised with eps=1e-5)."""
+    if vertices.ndimension() != 3:
+        raise ValueError("vertices Tensor should have 3 dimensions")
+    bs, device = vertices.shape[0], vertices.device
+    eye, at, up = _as_batch(eye, bs, device), _as_batch(at, bs, device), _as_batch(up, bs, device)
+    z_axis = F.normalize(at - eye, eps=1e-5)
+    x_axis = F.normalize(torch.cross(up, z_axis, dim=1), eps=1e-5)
+    y_axis = F.normalize(torch.cross(z_axis, x_axis, dim=1), eps=1e-5)
+    r = torch.stack((x_axis, y_axis, z_axis), dim=1)
+    if vertices.shape != eye.shape:
+        eye = eye[:, None, :]
+    return torch.matmul(vertices - eye, r.transpose(1, 2))
+
+
+def look(vertices, eye, direction=[0, 1, 0], up=None):
+    """look.py: camera at `eye` looking along `direction`."""
+    if vertices.ndimension() != 3:
+        raise ValueError("vertices Tensor should have 3 dimensions")
+    bs, device = vertices.shape[0], vertices.device
+    if up is None:
+        up = torch.tensor([0, 1, 0], dtype=torch.float32, device=device)
+    eye = _as_batch(eye, 1, device) if not torch.is_tensor(eye) or eye.ndimension() == 1 else eye.to(device)
+    direction = _as_batch(direction, 1, device)
+    up = _as_batch(up, 1, device)
+    z_axis = F.normalize(direction, eps=1e-5)
+    x_axis = F.normalize(torch.cross(up, z_axis, dim=1), eps=1e-5)
+    y_axis = F.normalize(torch.cross(z_axis, x_axis, dim=1), eps=1e-5)
+    r = torch.stack((x_axis, y_axis, z_axis), dim=1)
+    if vertices.shape != eye.shape:
+        eye = eye[:, None, :]
+    return torch.matmul(vertices - eye, r.transpose(1, 2))
+
+
+def orthogonal(vertices, scale):
+    """orthogonal.py:4-17 -- x,y scaled, z kept."""
+    if vertices.ndimension() != 3:
+        raise ValueError("vertices Tensor should have 3 dimensions")
+    return torch.stack((vertices[:, :, 0] * scale, vertices[:, :, 1] * scale, vertices[:, :, 2]), dim=2)
+
+
+def perspective(vertices, angle=30.0):
+    """perspective.py -- x,y divided by z*tan(angle)."""
+    if vertices.ndimension() != 3:
+        raise ValueError("vertices Tensor should have 3 dimensions")
+    angle = torch.tensor(angle / 180 * math.pi, dtype=torch.float32, device=vertices.device)[None]
+    width = torch.tan(angle)[:, None]
+    z = vertices[:, :, 2]
+    return torch.stack((vertices[:, :, 0] / z / width, vertices[:, :, 1] / z / width, z), dim=2)
+
+
+def get_points_from_angles(distance, elevation, azimuth, degrees=True):
+    """get_points_from_angles.py -- spherical camera position."""
+    if isinstance(distance, (float, int)):
+        if degrees:
+            elevation, azimuth = math.radians(elevation), math.radians(azimuth)
+        return (distance * math.cos(elevation) * math.sin(azimuth), distance * math.sin(elevation),
+                -distance * math.cos(elevation) * math.cos(azimuth))
+    if degrees:
+        elevation = math.pi / 180.0 * elevation
+        azimuth = math.pi / 180.0 * azimuth
+    return torch.stack([distance * torch.cos(elevation) * torch.sin(azimuth), distance * torch.sin(elevation),
+                        -distance * torch.cos(elevation) * torch.cos(azimuth)]).transpose(1, 0)
+
+
+def _color(c, device):
+    if isinstance(c, (tuple, list)):
+        c = torch.tensor(c, dtype=torch.float32, device=device)
+    elif isinstance(c, np.ndarray):
+        c = torch.from_numpy(c).float().to(device)
+    return c[None, :] if c.ndimension() == 1 else c
+
+
+def ambient_lighting(light, light_intensity=0.5, light_color=(1, 1, 1)):
+    """ambient_lighting.py:7-18 (in place on `light`, as the reference)."""
+    light += light_intensity * _color(light_color, light.device)[:, None, :]
+    return light
+
+
+def directional_lighting(light, normals, light_intensity=0.5, light_color=(1, 1, 1), light_direction=(0, 1, 0)):
+    """directional_lighting.py:7-27."""
+    color = _color(light_color, light.device)
+    direction = _color(light_direction, light.device)
+    cosine = F.relu(torch.sum(normals * direction, dim=2))
+    light += light_intensity * (color[:, None, :] * cosine[:, :, None])
+    return light

@@ -1,0 +1,133 @@
+"""Synthetic inputs for the LASR render hot path.
+
+Procedural meshes (icosphere), the Spot fixture loader and the camera sweep that
+``scripts/render_syn.py:143-173`` of the reference uses to pose Spot.  Pure numpy; used by
+``bench.py``, ``__graft_entry__.smoke()`` and the tests to build *inputs* only.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SPOT_FIXTURE = os.path.join(_REPO, "tests", "golden", "spot_mesh.npz")
+
+
+def icosphere(level: int, radius: float = 1.0):
+    """Unit icosahedron subdivided ``level`` times (level 3 -> 642 V / 1280 F, 4 -> 2562 / 5120,
+    5 -> 10242 / 20480), the mesh family LASR initialises from (``--subdivide``,
+    nnutils/mesh_net.py:63).  Returns (vertices float32 [V,3], faces int32 [F,3])."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+         (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2),
+         (10, 7, 6), (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5),
+         (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    verts = [np.asarray(p, dtype=np.float64) / np.linalg.norm(p) for p in v]
+    faces = [tuple(x) for x in f]
+    for _ in range(level):
+        cache = {}
+
+        def mid(a, b):
+            key = (a, b) if a < b else (b, a)
+            if key not in cache:
+                m = verts[a] + verts[b]
+                verts.append(m / np.linalg.norm(m))
+                cache[key] = len(verts) - 1
+            return cache[key]
+
+        nxt = []
+        for a, b, c in faces:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nxt += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        faces = nxt
+    return (np.asarray(verts) * radius).astype(np.float32), np.asarray(faces, dtype=np.int32)
+
+
+def bumpy_sphere(level: int, radius: float = 0.5, seed: int = 0):
+    """Icosphere with smooth low-frequency lobes, so that the silhouette has concavities and
+    several depth layers overlap (a convex sphere never self-occludes beyond front/back)."""
+    v, f = icosphere(level, 1.0)
+    rng = np.random.RandomState(seed)
+    dirs = rng.randn(6, 3)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    amp = rng.uniform(0.15, 0.45, size=6)
+    r = np.ones(len(v))
+    for d, a in zip(dirs, amp):
+        r += a * np.exp(4.0 * (v @ d - 1.0))
+    return (v * r[:, None] * radius).astype(np.float32), f
+
+
+def load_spot(path: str = SPOT_FIXTURE):
+    """Spot (2930 V / 5856 F), vertices preprocessed as scripts/render_syn.py:72-74
+    (y *= -1; y += 0.1; /= 1.2).  The fixture is produced by tests/golden/make_mesh_fixture.py."""
+    d = np.load(path)
+    v = d["vertices"].astype(np.float32).copy()
+    v[:, 1] *= -1
+    v[:, 1] += 0.1
+    v /= 1.2
+    return v, d["faces"].astype(np.int32)
+
+
+def rodrigues(rvec):
+    """Axis-angle -> rotation matrix (what cv2.Rodrigues returns, render_syn.py:148)."""
+    rvec = np.asarray(rvec, dtype=np.float64)
+    th = np.linalg.norm(rvec)
+    if th < 1e-12:
+        return np.eye(3)
+    k = rvec / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+
+
+def spot_cameras(n_frames: int, seed: int = 0, focal: float = 10.0, depth: float = 10.0):
+    """Per-frame rigid pose of scripts/render_syn.py:143-156: rotation
+    Rodrigues([rx_i, 3*1.57 + 6.28*i/N, 0]) with rx_0 = 0, rx_i ~ U[0,1); translation (0,0,depth);
+    focal 10; principal point 0.  Returns Rmat [N,3,3] such that ``cam = verts @ Rmat + Tmat``
+    (the row-vector convention of nnutils/geom_utils.py:45-71), Tmat [N,1,3], pp [N,2], fl [N,1]."""
+    rng = np.random.RandomState(seed)
+    R = np.zeros((n_frames, 3, 3), dtype=np.float32)
+    for i in range(n_frames):
+        rx = rng.rand()
+        if i == 0:
+            rx = 0.0
+        R[i] = rodrigues([rx, 3 * 1.57 + 6.28 * i / n_frames, 0.0]).T  # render_syn.py:162-164
+    T = np.zeros((n_frames, 1, 3), dtype=np.float32)
+    T[:, 0, 2] = depth
+    pp = np.zeros((n_frames, 2), dtype=np.float32)
+    fl = np.full((n_frames, 1), focal, dtype=np.float32)
+    return R, T, pp, fl
+
+
+def project_frames(verts, Rmat, Tmat, pp, fl):
+    """obj->cam + pinhole of the training path (mesh_net.py:298-302): x,y projected, z kept."""
+    cam = np.matmul(verts[None].astype(np.float32), Rmat) + Tmat
+    out = cam.copy()
+    out[:, :, 0] = pp[:, 0:1] + cam[:, :, 0] * fl / cam[:, :, 2]
+    out[:, :, 1] = pp[:, 1:2] + cam[:, :, 1] * fl / cam[:, :, 2]
+    return out.astype(np.float32), cam.astype(np.float32)
+
+
+def vertex_colors(n_verts: int, seed: int = 0):
+    """sigmoid(N(0,1)) per vertex (third_party/ext_nnutils/mesh_net.py:96,184)."""
+    rng = np.random.RandomState(seed)
+    return (1.0 / (1.0 + np.exp(-rng.randn(n_verts, 3)))).astype(np.float32)
+
+
+def render_inputs(verts, faces, n_frames, seed=0):
+    """Posed, projected, y-flipped vertices [N,V,3] exactly as the rasterizer sees them in LASR
+    (net camera transform is (x, -y, z)), plus near/far by mesh_net.py:304-311."""
+    R, T, pp, fl = spot_cameras(n_frames, seed)
+    px, cam = project_frames(verts, R, T, pp, fl)
+    px[:, :, 1] *= -1
+    z = px[:, :, 2]
+    dmin, dmax = np.float32(z.min()), np.float32(z.max())
+    near = np.float32(dmin - (dmax - dmin) / 2)
+    far = np.float32(dmax + (dmax - dmin) / 2)
+    return px, cam, float(near), float(far)
+
+
+def gather_faces(verts_nv3, faces):
+    """[N,V,C] x [F,3] -> [N,F,3,C] (functional/face_vertices.py with a shared topology)."""
+    return np.ascontiguousarray(verts_nv3[:, faces.astype(np.int64)])

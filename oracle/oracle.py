@@ -1,0 +1,388 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU oracle for the LASR differentiable-render hot path.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl`` legs may import
+this module; nothing under ``lasr_b200/`` does.
+
+Two layers:
+
+* the soft rasterizer -- a ctypes binding of
+  ``oracle/softras_oracle.cpp`` (C++, float and double instantiations), wrapped so that the
+  call reads like the reference's ``SoftRasterizeFunction`` (buffer allocation, enum maps and
+  ``dist_eps -> log(1/eps - 1)`` follow
+  third_party/softras/soft_renderer/functional/soft_rasterize.py:22-53,88-91);
+* numpy restatements of the small dense pieces either side of it (rows S0, G1-G3, R1, R2,
+  L1-L3); each function cites the reference lines it follows.
+
+Parity status: rasterizer pinned against the reference kernels run on a B200
+(tests/golden/softras_ref_*.npz); G1/G2/R2 pinned against the reference's own Python imported
+on CPU (tests/golden/geom_ref.npz); S0 (kornia 0.5.3 quaternion convention, not vendored) and
+L1-L3 (inline code in nnutils/mesh_net.py:372-447, not importable) are **parity unpinned**.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libsoftras_oracle.so")
+_lib = None
+
+DIST_FUNC = {"hard": 0, "barycentric": 1, "euclidean": 2}
+RGB_FUNC = {"hard": 0, "softmax": 1}
+ALPHA_FUNC = {"hard": 0, "sum": 1, "prod": 2}
+SAMPLE_TYPE = {"surface": 0, "vertex": 1}
+
+
+def build(force: bool = False) -> str:
+    """Compile the C++ restatement (g++, OpenMP).  Building the checker is not using it."""
+    src = os.path.join(_HERE, "softras_oracle.cpp")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "oracle"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        _lib.lasr_oracle_max_threads.restype = ctypes.c_int
+    return _lib
+
+
+def set_contract(on: bool = True):
+    """Evaluate the hard-decision sums of products with nvcc's FMA association (default on)."""
+    _load().lasr_oracle_set_contract(ctypes.c_int(1 if on else 0))
+
+
+def max_threads() -> int:
+    return int(_load().lasr_oracle_max_threads())
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class RasterSettings(dict):
+    """The 13 non-tensor arguments of SoftRasterizeFunction.forward (soft_rasterize.py:12-17)."""
+
+    @staticmethod
+    def lasr_training(image_size=256, near=1.0, far=100.0, sigma_val=1e-4, background_color=(0, 0, 0)):
+        # nnutils/mesh_net.py:136-145 (+ :304-311 for near/far, :356 for the white background)
+        return RasterSettings(image_size=image_size, background_color=list(background_color), near=near,
+                              far=far, fill_back=True, eps=1e-3, sigma_val=sigma_val,
+                              dist_func="euclidean", dist_eps=1e-4, gamma_val=1e-2,
+                              aggr_func_rgb="softmax", aggr_func_alpha="prod", texture_type="vertex")
+
+
+_DEFAULTS = dict(image_size=256, background_color=[0, 0, 0], near=1, far=100, fill_back=True, eps=1e-3,
+                 sigma_val=1e-5, dist_func="euclidean", dist_eps=1e-4, gamma_val=1e-4,
+                 aggr_func_rgb="softmax", aggr_func_alpha="prod", texture_type="surface")
+
+
+def _scalars(s):
+    s = {**_DEFAULTS, **s}
+    dist_eps_log = np.log(1.0 / s["dist_eps"] - 1.0)  # soft_rasterize.py:35
+    return s, (
+        ctypes.c_float(float(s["near"])), ctypes.c_float(float(s["far"])), ctypes.c_float(float(s["eps"])),
+        ctypes.c_float(float(s["sigma_val"])), ctypes.c_int(DIST_FUNC[s["dist_func"]]),
+        ctypes.c_float(float(dist_eps_log)), ctypes.c_float(float(s["gamma_val"])),
+        ctypes.c_int(RGB_FUNC[s["aggr_func_rgb"]]), ctypes.c_int(ALPHA_FUNC[s["aggr_func_alpha"]]),
+        ctypes.c_int(SAMPLE_TYPE[s["texture_type"]]), ctypes.c_int(1 if s["fill_back"] else 0))
+
+
+def soft_rasterize_forward(face_vertices, textures, settings=None, dtype=np.float32, accel=True, nthreads=0):
+    """SoftRasterizeFunction.forward (soft_rasterize.py:11-65) on the CPU.
+
+    face_vertices [N,F,3,3] (or [N,F,9]); textures [N,F,T,3].  Returns a dict with
+    soft_colors [N,4,S,S], aggrs_info [N,2,S,S], faces_info [N,F,27], pairs (surviving
+    (pixel,face) pairs) and the saved inputs needed by :func:`soft_rasterize_backward`.
+    """
+    lib = _load()
+    s, sc = _scalars(settings or {})
+    fv = np.ascontiguousarray(np.asarray(face_vertices, dtype=dtype)).reshape(
+        np.shape(face_vertices)[0], np.shape(face_vertices)[1], 9)
+    tex = np.ascontiguousarray(np.asarray(textures, dtype=dtype))
+    N, F = fv.shape[:2]
+    tex = tex.reshape(N, F, -1, 3)
+    T = tex.shape[2]
+    S = int(s["image_size"])
+    faces_info = np.zeros((N, F, 27), dtype=dtype)          # soft_rasterize.py:47
+    aggrs_info = np.zeros((N, 2, S, S), dtype=dtype)        # :48
+    soft_colors = np.ones((N, 4, S, S), dtype=dtype)        # :50-53
+    for k in range(3):
+        soft_colors[:, k] *= dtype(s["background_color"][k])
+    pairs = ctypes.c_longlong(0)
+    fn = lib.lasr_oracle_forward_f32 if dtype == np.float32 else lib.lasr_oracle_forward_f64
+    rc = fn(_ptr(fv), _ptr(tex), _ptr(faces_info), _ptr(aggrs_info), _ptr(soft_colors),
+            ctypes.c_int(N), ctypes.c_int(F), ctypes.c_int(S), ctypes.c_int(T), *sc,
+            ctypes.c_int(1 if accel else 0), ctypes.c_int(nthreads), ctypes.byref(pairs))
+    assert rc == 0
+    return dict(soft_colors=soft_colors, aggrs_info=aggrs_info, faces_info=faces_info, pairs=int(pairs.value),
+                face_vertices=fv, textures=tex, settings=s, dtype=dtype)
+
+
+def soft_rasterize_backward(saved, grad_soft_colors, accel=True, nthreads=0):
+    """SoftRasterizeFunction.backward (soft_rasterize.py:67-102) on the CPU.
+
+    Returns (grad_faces [N,F,9], grad_textures [N,F,T,3]).
+    """
+    lib = _load()
+    dtype = saved["dtype"]
+    s, sc = _scalars(saved["settings"])
+    fv, tex = saved["face_vertices"], saved["textures"]
+    N, F = fv.shape[:2]
+    T = tex.shape[2]
+    S = int(s["image_size"])
+    g = np.ascontiguousarray(np.asarray(grad_soft_colors, dtype=dtype)).reshape(N, 4, S, S)
+    grad_faces = np.zeros_like(fv)          # :88
+    grad_textures = np.zeros_like(tex)      # :89
+    fn = lib.lasr_oracle_backward_f32 if dtype == np.float32 else lib.lasr_oracle_backward_f64
+    rc = fn(_ptr(fv), _ptr(tex), _ptr(saved["soft_colors"]), _ptr(saved["faces_info"]),
+            _ptr(saved["aggrs_info"]), _ptr(grad_faces), _ptr(grad_textures), _ptr(g),
+            ctypes.c_int(N), ctypes.c_int(F), ctypes.c_int(S), ctypes.c_int(T), *sc,
+            ctypes.c_int(1 if accel else 0), ctypes.c_int(nthreads))
+    assert rc == 0
+    return grad_faces, grad_textures
+
+
+# --------------------------------------------------------------------------------------------
+# numpy restatements of the dense glue either side of the rasterizer
+# --------------------------------------------------------------------------------------------
+
+def face_vertices(vertices, faces):
+    """functional/face_vertices.py:4-22 -- gather [N,V,C] by [N,F,3] -> [N,F,3,C]."""
+    vertices = np.asarray(vertices)
+    faces = np.asarray(faces).astype(np.int64)
+    n = vertices.shape[0]
+    return vertices[np.arange(n)[:, None, None], faces]
+
+
+def look_at(vertices, eye, at=(0, 0, 0), up=(0, 1, 0)):
+    """functional/look_at.py:6-62 (F.normalize eps=1e-5)."""
+    v = np.asarray(vertices, dtype=np.float32)
+    n = v.shape[0]
+
+    def norm(x):
+        return x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-5).astype(np.float32)
+
+    def bcast(x):
+        x = np.asarray(x, dtype=np.float32)
+        return np.repeat(x[None], n, 0) if x.ndim == 1 else x
+
+    eye, at, up = bcast(eye), bcast(at), bcast(up)
+    z = norm(at - eye)
+    x = norm(np.cross(up, z))
+    y = norm(np.cross(z, x))
+    r = np.stack([x, y, z], axis=1)  # [n,3,3]
+    return np.matmul(v - eye[:, None, :], np.transpose(r, (0, 2, 1))).astype(np.float32)
+
+
+def orthogonal(vertices, scale=1.0):
+    """functional/orthogonal.py:4-17."""
+    v = np.asarray(vertices, dtype=np.float32).copy()
+    v[:, :, 0] *= np.float32(scale)
+    v[:, :, 1] *= np.float32(scale)
+    return v
+
+
+def vertex_normals(vertices, faces):
+    """functional/vertex_normals.py:4-37 (F.normalize eps=1e-6)."""
+    v = np.asarray(vertices, dtype=np.float32)
+    f = np.asarray(faces).astype(np.int64)
+    n, nv = v.shape[:2]
+    out = np.zeros((n, nv, 3), dtype=np.float32)
+    for b in range(n):
+        vf = v[b][f[b]]  # [F,3,3]
+        np.add.at(out[b], f[b][:, 1], np.cross(vf[:, 2] - vf[:, 1], vf[:, 0] - vf[:, 1]))
+        np.add.at(out[b], f[b][:, 2], np.cross(vf[:, 0] - vf[:, 2], vf[:, 1] - vf[:, 2]))
+        np.add.at(out[b], f[b][:, 0], np.cross(vf[:, 1] - vf[:, 0], vf[:, 2] - vf[:, 0]))
+    return out / np.maximum(np.linalg.norm(out, axis=2, keepdims=True), 1e-6).astype(np.float32)
+
+
+def vertex_lighting(vertices, faces, textures, intensity_ambient=0.5, color_ambient=(1, 1, 1),
+                    intensity_directional=0.5, color_directional=(1, 1, 1), direction=(0, 1, 0)):
+    """lighting.py:50-67 'vertex' branch + functional/{ambient,directional}_lighting.py."""
+    light = np.zeros_like(np.asarray(vertices, dtype=np.float32))
+    light += np.float32(intensity_ambient) * np.asarray(color_ambient, dtype=np.float32)[None, None, :]
+    nrm = vertex_normals(vertices, faces)
+    cosine = np.maximum((nrm * np.asarray(direction, dtype=np.float32)[None, None, :]).sum(2), 0)
+    light += np.float32(intensity_directional) * (
+        np.asarray(color_directional, dtype=np.float32)[None, None, :] * cosine[:, :, None])
+    return np.asarray(textures, dtype=np.float32) * light
+
+
+def obj_to_cam(verts, Rmat, Tmat, nmesh, n_hypo, skin, tocam=True):
+    """nnutils/geom_utils.py:45-71 -- linear-blend skinning, row-vector convention.
+
+    verts [N,V,3]; Rmat [N*nmesh,3,3]; Tmat [N*nmesh,1,3]; skin [N,nmesh-1,V,1] or None.
+    """
+    verts = np.asarray(verts, dtype=np.float32).reshape(-1, np.shape(verts)[1], 3)
+    Rmat = np.asarray(Rmat, dtype=np.float32).reshape(-1, 3, 3)
+    Tmat = np.asarray(Tmat, dtype=np.float32).reshape(-1, 1, 3)
+    bodyR, bodyT = Rmat[::nmesh], Tmat[::nmesh]
+    if nmesh > 1:
+        parts = [np.matmul(verts, Rmat[k + 1::nmesh]) + Tmat[k + 1::nmesh] for k in range(nmesh - 1)]
+        vs = (np.stack(parts, 1) * np.asarray(skin, dtype=np.float32)).sum(1)
+    else:
+        vs = verts
+    if tocam:
+        vs = np.matmul(vs, bodyR) + bodyT
+    return vs.astype(np.float32)
+
+
+def pinhole_cam(verts, pp, fl):
+    """nnutils/geom_utils.py:27-34 -- x,y <- pp + xy*f/z; remaining channels kept."""
+    verts = np.asarray(verts, dtype=np.float32).copy()
+    pp = np.asarray(pp, dtype=np.float32)
+    fl = np.asarray(fl, dtype=np.float32)
+    n_hypo = verts.shape[0] // pp.shape[0]
+    pp = np.repeat(pp[:, None], n_hypo, 1).reshape(-1, 2)
+    fl = fl.reshape(-1, 1)
+    z = verts[:, :, 2].copy()
+    verts[:, :, 1] = pp[:, 1:2] + verts[:, :, 1] * fl / z
+    verts[:, :, 0] = pp[:, 0:1] + verts[:, :, 0] * fl / z
+    return verts
+
+
+def quaternion_to_rotation_matrix(q):
+    """kornia==0.5.3 ``quaternion_to_rotation_matrix`` (lasr.yml:85), XYZW order.
+
+    kornia is not vendored in /root/reference: restated from its published algorithm
+    (normalise, then the standard unit-quaternion matrix).  Convention corroborated in-repo by the
+    identity ``[0,0,0,1]`` (nnutils/mesh_net.py:118,120).  **Parity unpinned.**
+    """
+    q = np.asarray(q, dtype=np.float32)
+    q = q / np.maximum(np.linalg.norm(q, axis=-1, keepdims=True), 1e-12).astype(np.float32)
+    x, y, z, w = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    tx, ty, tz = 2 * x, 2 * y, 2 * z
+    twx, twy, twz = tx * w, ty * w, tz * w
+    txx, txy, txz = tx * x, ty * x, tz * x
+    tyy, tyz, tzz = ty * y, tz * y, tz * z
+    one = np.float32(1)
+    m = np.stack([one - (tyy + tzz), txy - twz, txz + twy,
+                  txy + twz, one - (txx + tzz), tyz - twx,
+                  txz - twy, tyz + twx, one - (txx + tyy)], -1)
+    return m.reshape(q.shape[:-1] + (3, 3)).astype(np.float32)
+
+
+def skin_weights(ctl_ts, ctl_rs, log_ctl, mean_v, n_hypo):
+    """nnutils/mesh_net.py:264-267 -- Gaussian-mixture skinning weights, softmax over bones.
+
+    ctl_ts [H*(B-1),3]; ctl_rs [H*(B-1),4] (XYZW); log_ctl [H*(B-1),3]; mean_v [H,V,3] -> [H,B-1,V,1].
+    """
+    H = n_hypo
+    ctl_ts = np.asarray(ctl_ts, dtype=np.float32).reshape(H, -1, 1, 3)
+    R = quaternion_to_rotation_matrix(ctl_rs).reshape(H, -1, 3, 3)
+    d = ctl_ts - np.asarray(mean_v, dtype=np.float32).reshape(H, 1, -1, 3)
+    d = np.matmul(d, R)
+    d = np.exp(np.asarray(log_ctl, dtype=np.float32)).reshape(H, -1, 1, 3) * d ** 2
+    logits = -10 * d.sum(3)
+    logits = logits - logits.max(1, keepdims=True)
+    e = np.exp(logits)
+    return (e / e.sum(1, keepdims=True))[..., None].astype(np.float32)
+
+
+def near_far(verts_z):
+    """nnutils/mesh_net.py:304-311 -- batch-global depth window."""
+    dmax = np.float32(np.max(verts_z))
+    dmin = np.float32(np.min(verts_z))
+    return np.float32(dmin - (dmax - dmin) / 2), np.float32(dmax + (dmax - dmin) / 2)
+
+
+LASR_EYE_Z = -(1.0 / np.tan(np.radians(30.0)) + 1.0)  # transform.py:37-38 default eye
+
+
+def lasr_render_vertices(verts_px):
+    """The vertex path of render_flow_soft_2 + render_mesh with LASR's renderer settings
+    (nnutils/mesh_net.py:81-82; renderer.py:94-98; transform.py:41-48; look_at.py; orthogonal.py):
+    +eye offset, y flip, look_at(eye) (camera == identity), orthogonal(scale=1)."""
+    v = np.asarray(verts_px, dtype=np.float32)[:, :, :3].copy()
+    eye = np.array([0, 0, LASR_EYE_Z], dtype=np.float32)
+    v = v + eye[None, None]
+    v[:, :, 1] = -1 * v[:, :, 1]
+    return orthogonal(look_at(v, eye), 1.0)
+
+
+# ---- image losses (nnutils/mesh_net.py:372-447; LPIPS term excluded) -- parity unpinned ----
+
+def mask_loss(mask_pred, masks, occ):
+    """mesh_net.py:374-390.  mask_pred [N,H,S,S]; masks, occ [N,S,S] -> (scalar, [N,H])."""
+    mask_pred = np.asarray(mask_pred, dtype=np.float32)
+    sub = (mask_pred - np.asarray(masks, dtype=np.float32)[:, None]) ** 2
+    N, H = sub.shape[:2]
+    out = np.zeros((N, H), dtype=np.float32)
+    for i in range(N):
+        sel = np.asarray(occ)[i] != 0
+        for j in range(H):
+            out[i, j] = sub[i, j][sel].mean(dtype=np.float64)
+    out = 0.5 * out
+    return np.float32(out.mean()), out
+
+
+def flow_loss(flow_rd, bgmask, flow_obs, occ, masks):
+    """mesh_net.py:393-416.  flow_rd [N,H,S,S,2]; bgmask [N,H,S,S]; flow_obs [N,3,S,S]."""
+    flow_rd = np.asarray(flow_rd, dtype=np.float32)
+    occ = np.asarray(occ, dtype=np.float32)
+    N, H = flow_rd.shape[:2]
+    mask = (~np.asarray(bgmask, dtype=bool)) & ((occ != 0) & (np.asarray(masks) > 0))[:, None]
+    diff = flow_rd - np.transpose(np.asarray(flow_obs, dtype=np.float32)[:, None, :2], (0, 1, 3, 4, 2))
+    rd_map = np.sqrt((diff.astype(np.float64) ** 2).sum(-1)).astype(np.float32)
+    wts = np.repeat((1.0 / (1.0 + np.exp(occ.astype(np.float64))))[:, None], H, 1).astype(np.float32)
+    for i in range(N):
+        wts[i] = wts[i] / wts[i][mask[i]].mean(dtype=np.float64)
+    rd_map = rd_map * wts
+    out = np.zeros((N, H), dtype=np.float32)
+    for i in range(N):
+        for j in range(H):
+            out[i, j] = rd_map[i, j][mask[i, j]].mean(dtype=np.float64) if mask[i, j].sum() > 0 else 0
+    out = 0.5 * out
+    return np.float32(out.mean()), out
+
+
+def texture_l1_loss(texture_render, fgmask, imgs, masks, occ, l1tex_wt=1.0):
+    """mesh_net.py:361-363,420-441,444-445 without the 0.005*LPIPS term.
+
+    texture_render [N,H,3,S,S]; fgmask [N,H,S,S]; imgs [N,3,S,S]; masks, occ [N,S,S]."""
+    tr = np.asarray(texture_render, dtype=np.float32)
+    fg = np.asarray(fgmask, dtype=np.float32)
+    m = (np.asarray(masks) > 0).astype(np.float32)[:, None]
+    img_obs = np.asarray(imgs, dtype=np.float32) * m
+    img_white = 1 - m + img_obs
+    img_rnd = tr * fg[:, :, None]
+    N, H = tr.shape[:2]
+    out = np.zeros((N, H), dtype=np.float32)
+    for i in range(N):
+        sel = np.asarray(occ)[i] != 0
+        for j in range(H):
+            a = np.abs(img_obs[i] - img_rnd[i, j]).mean(0)[sel].mean(dtype=np.float64)
+            b = np.abs(img_white[i] - tr[i, j]).mean(0)[sel].mean(dtype=np.float64)
+            out[i, j] = (a + b) * 2 * l1tex_wt
+    out = 0.25 * out
+    return np.float32(out.mean()), out
+
+
+def flow_from_rendered_positions(pos0_px, pos1_px, pp0, pp1, fl0, fl1):
+    """render_flow_soft_2 post-processing, mesh_net.py:88-104.
+
+    pos*_px [n,S,S,3] rendered 3-D positions (channels-last); pp* [n,2]; fl* [n,1].
+    Returns (flow_fw [n,S,S,2], bgmask [n,S,S])."""
+    p0 = np.asarray(pos0_px, dtype=np.float32).copy()
+    p1 = np.asarray(pos1_px, dtype=np.float32).copy()
+    bg = (p0[..., 2] < 1e-9) | (p1[..., 2] < 1e-9)
+    p0[bg] = 10
+    p1[bg] = 10
+    out = []
+    for p, pp, fl in ((p0, pp0, fl0), (p1, pp1, fl1)):
+        pp = np.asarray(pp, dtype=np.float32)
+        fl = np.asarray(fl, dtype=np.float32).reshape(-1, 1)
+        z = p[..., 2].copy()
+        y = pp[:, 1:2, None] + p[..., 1] * fl[:, :1, None] / z
+        x = pp[:, 0:1, None] + p[..., 0] * fl[:, :1, None] / z
+        out.append(np.stack([x, y], -1))
+    return (out[1] - out[0]).astype(np.float32), bg
