@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-LIB_PATH = os.path.join(CSRC, "liblasr_b200.so")
+LIB_PATH = os.environ.get("LASR_B200_LIB") or os.path.join(CSRC, "liblasr_b200.so")  # override: A/B builds
 SOURCES = ["raster.cu"]
 HEADERS = ["raster_common.cuh"]
 

@@ -6,14 +6,15 @@
 // (N*S^2*F iterations, .cu:370,538) and scatters gradients with 18 float atomics per surviving
 // (pixel,face) pair (.cu:620-622,657-666).  Here:
 //
-//   setup     one thread per face: dilated bounding box -> packed pixel window (8 B / face);
+//   setup     one thread per face: derived per-face constants (a 176-byte record), the dilated
+//             bounding box and its packed pixel window (8 B), written once to the workspace;
 //   forward   one CTA per 16x16 pixel tile: (1) the CTA scans the packed windows and compacts the
-//             indices of overlapping faces, in ascending order, into shared memory; (2) derived
-//             per-face constants are computed once per (tile, face) into shared-memory records;
-//             (3) each warp (an 8x4 pixel footprint) culls 32 records at a time against its
-//             footprint with one ballot and evaluates only the survivors.  Faces are visited in
-//             ascending index, the order the reference's per-pixel loop uses, so the online
-//             depth-softmax and the hard z-test see the same sequence;
+//             indices of overlapping faces, in ascending order, into shared memory; (2) each warp
+//             (an 8x4 pixel footprint) then walks that list on its own, culls 32 faces at a time
+//             against its footprint with one ballot and evaluates only the survivors, reading
+//             the face record with warp-uniform 128-bit loads (L1/L2 resident).  Faces are
+//             visited in ascending index, the order the reference's per-pixel loop uses, so the
+//             online depth-softmax and the hard z-test see the same sequence;
 //   backward  one warp per face: the warp sweeps the face's own pixel window, every lane owns a
 //             pixel, the 18 partial derivatives are reduced with a fixed-order warp butterfly and
 //             written once.  No atomics, deterministic, ~2/3 of the lanes do useful work.
@@ -35,64 +36,40 @@ namespace lasr {
 
 constexpr int kTile = 16;           // pixels per tile side
 constexpr int kFwdThreads = 256;    // 8 warps, each an 8x4 pixel footprint
-constexpr int kScanChunk = 2048;    // faces scanned per round (8 warps x 256)
-constexpr int kWarpSeg = kScanChunk / 8;
-constexpr int kRecCap = 128;        // face records staged per sub-batch
-constexpr int kRecWords = 44;       // floats per record (176 B, float4 aligned)
-
-// record layout (float index)
-//  0 lox 1 hix 2 loy 3 hiy | 4..12 inv | 13..15 x | 16..18 y | 19..21 z | 22..30 a[e][j]
-//  31 flags (bits 0-1: obt+1, bit 2: front) | 32 face id | 33..41 vertex-colour texture | 42,43 pad
-constexpr int kRecInv = 4, kRecX = 13, kRecY = 16, kRecZ = 19, kRecA = 22, kRecFlags = 31, kRecFace = 32,
-              kRecTex = 33;
-
-__device__ __forceinline__ void store_record(float* r, const FaceGeom& g, int face, const float* tex9) {
-  r[0] = g.lox; r[1] = g.hix; r[2] = g.loy; r[3] = g.hiy;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) r[kRecInv + k] = g.inv[k];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { r[kRecX + k] = g.x[k]; r[kRecY + k] = g.y[k]; r[kRecZ + k] = g.z[k]; }
-#pragma unroll
-  for (int e = 0; e < 3; ++e)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) r[kRecA + 3 * e + j] = g.a[e][j];
-  r[kRecFlags] = __int_as_float((g.obt + 1) | (g.front ? 4 : 0));
-  r[kRecFace] = __int_as_float(face);
-  if (tex9) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) r[kRecTex + k] = tex9[k];
-  }
-}
-
-__device__ __forceinline__ void load_record(const float* r, FaceGeom& g) {
-  g.lox = r[0]; g.hix = r[1]; g.loy = r[2]; g.hiy = r[3];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) g.inv[k] = r[kRecInv + k];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { g.x[k] = r[kRecX + k]; g.y[k] = r[kRecY + k]; g.z[k] = r[kRecZ + k]; }
-#pragma unroll
-  for (int e = 0; e < 3; ++e)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) g.a[e][j] = r[kRecA + 3 * e + j];
-  const int fl = __float_as_int(r[kRecFlags]);
-  g.obt = (fl & 3) - 1;
-  g.front = (fl & 4) != 0;
-}
+constexpr int kMaxScanChunk = 12288; // faces scanned per round (48 KB of indices); one round if F fits
+#ifndef LASR_FWD_MIN_BLOCKS
+#define LASR_FWD_MIN_BLOCKS 4
+#endif
+#ifndef LASR_BWD_MIN_BLOCKS
+#define LASR_BWD_MIN_BLOCKS 2
+#endif
 
 // ---------------------------------------------------------------------------------------------
-// setup: packed pixel window per face
+// setup: one thread per face -> packed pixel window, dilated border box, full face record;
+// the first S threads also fill the pixel-centre coordinate table.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) raster_setup_kernel(RasterArgs A) {
+__global__ void __launch_bounds__(128) raster_setup_kernel(RasterArgs A, int with_records) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < A.S) A.coords[i] = pixel_coord((int)i, A.S);
   if (i >= (long long)A.N * A.F) return;
   const float* fv = A.faces + i * 9;
   const float sthr = sqrtf(A.dist_eps * A.sigma);
-  const float x0 = fv[0], y0 = fv[1], x1 = fv[3], y1 = fv[4], x2 = fv[6], y2 = fv[7];
+  FaceGeom g;
+  face_setup(fv, sthr, g);
   int xlo, xhi, ylo, yhi;
-  coord_window(min3(x0, x1, x2) - sthr, max3(x0, x1, x2) + sthr, A.S, xlo, xhi);
-  coord_window(min3(y0, y1, y2) - sthr, max3(y0, y1, y2) + sthr, A.S, ylo, yhi);
+  coord_window(g.lox, g.hix, A.S, xlo, xhi);
+  coord_window(g.loy, g.hiy, A.S, ylo, yhi);
   if (xlo > xhi || ylo > yhi) { xlo = 1; xhi = 0; ylo = 1; yhi = 0; }
   A.face_window[i] = make_uint2((uint32_t)xlo | ((uint32_t)xhi << 16), (uint32_t)ylo | ((uint32_t)yhi << 16));
+  if (!with_records) return;
+  A.face_border[i] = make_float4(g.lox, g.hix, g.loy, g.hiy);
+  float tex9[9];
+  const bool vertex_tex = A.sample == 1;
+  if (vertex_tex) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) tex9[k] = A.textures[i * 9 + k];
+  }
+  store_record(A.face_record + i * kRecWords, g, vertex_tex ? tex9 : nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -106,16 +83,20 @@ struct PixelState {
   int face_min;
 };
 
+struct FwdConsts {
+  float thr, near_, far_, inv_range;
+};
+
 template <bool kFast>
-__device__ __forceinline__ void forward_pair(const RasterArgs& A, const float* __restrict__ rec, float xp, float yp,
-                                             float thr, float near_, float far_, int n, PixelState& st) {
+__device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConsts& C, const float* __restrict__ rec,
+                                             float4 bd, int face, int n, float xp, float yp, PixelState& st) {
   // exact border predicate of the reference (.cu:32-38,375)
-  const float4 bd = *reinterpret_cast<const float4*>(rec);  // lox, hix, loy, hiy
   if (xp > bd.y || xp < bd.x || yp > bd.w || yp < bd.z) return;
   FaceGeom g;
-  load_record(rec, g);
+  float tex9[9];
+  load_record(rec, g, tex9);
   Fragment fr;
-  if (!soft_fragment<kFast>(A, g, xp, yp, thr, fr)) return;
+  if (!soft_fragment<kFast>(A, g, xp, yp, C.thr, fr)) return;
   const int alpha_f = kFast ? 2 : A.alpha;
   const int rgb_f = kFast ? 1 : A.rgb;
   const int sample = kFast ? 1 : A.sample;
@@ -125,13 +106,11 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const float* _
   else st.alpha *= 1.f - fr.frag;
   // clipped-barycentric depth (.cu:421-424)
   float wc[3];
-  bary_clip(fr.w, wc);
-  const float zp = 1.f / (wc[0] / g.z[0] + wc[1] / g.z[1] + wc[2] / g.z[2]);
-  if (zp < near_ || zp > far_) return;
+  const float zp = clip_and_depth<kFast>(g, fr.w, wc);
+  if (zp < C.near_ || zp > C.far_) return;
   const bool visible = g.front || (kFast ? true : A.double_side != 0);
-  const int face = __float_as_int(rec[kRecFace]);
   auto sample_tex = [&](int k) -> float {
-    if (sample == 1) return wc[0] * rec[kRecTex + k] + wc[1] * rec[kRecTex + 3 + k] + wc[2] * rec[kRecTex + 6 + k];
+    if (sample == 1) return wc[0] * tex9[k] + wc[1] * tex9[3 + k] + wc[2] * tex9[6 + k];
     const long long base = ((long long)n * A.F + face) * A.T * 3;
     const long long idx = base + (long long)surface_texel(wc, A.R) * 3 + k;
     return idx < (long long)A.N * A.F * A.T * 3 ? A.textures[idx] : 0.f;
@@ -144,13 +123,13 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const float* _
       for (int k = 0; k < 3; ++k) st.col[k] = sample_tex(k);
     }
   } else if (visible) {  // depth softmax, online (.cu:437-451)
-    const float zn = (far_ - zp) / (far_ - near_);
+    const float zn = kFast ? (C.far_ - zp) * C.inv_range : (C.far_ - zp) / (C.far_ - C.near_);
     float rescale = 1.f;
     if (zn > st.smax) {
-      rescale = expf((st.smax - zn) / A.gamma);
+      rescale = kFast ? __expf((st.smax - zn) * A.inv_gamma) : expf((st.smax - zn) / A.gamma);
       st.smax = zn;
     }
-    const float ez = expf((zn - st.smax) / A.gamma) * fr.frag;
+    const float ez = (kFast ? __expf((zn - st.smax) * A.inv_gamma) : expf((zn - st.smax) / A.gamma)) * fr.frag;
     st.ssum = rescale * st.ssum + ez;
 #pragma unroll
     for (int k = 0; k < 3; ++k) st.col[k] = rescale * st.col[k] + ez * sample_tex(k);
@@ -158,10 +137,10 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const float* _
 }
 
 template <bool kFast>
-__global__ void __launch_bounds__(kFwdThreads) raster_forward_kernel(RasterArgs A) {
-  __shared__ __align__(16) float s_rec[kRecCap * kRecWords];
-  __shared__ int s_list[kScanChunk];
+__global__ void __launch_bounds__(kFwdThreads, LASR_FWD_MIN_BLOCKS) raster_forward_kernel(RasterArgs A, int chunk) {
+  extern __shared__ int s_list[];   // [chunk] face indices, 8 per-warp segments of chunk/8
   __shared__ int s_cnt[8];
+  const int wseg = chunk >> 3;
 
   const int S = A.S;
   const int tiles_x = (S + kTile - 1) / kTile;
@@ -169,18 +148,20 @@ __global__ void __launch_bounds__(kFwdThreads) raster_forward_kernel(RasterArgs 
   const int tile_y = blockIdx.x / tiles_x;
   const int n = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int px = tile_x * kTile + (warp & 1) * 8 + (lane & 7);
-  const int py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);  // row from the top
+  const int wx0 = tile_x * kTile + (warp & 1) * 8, wy0 = tile_y * kTile + (warp >> 1) * 4;
+  const int px = wx0 + (lane & 7);
+  const int py = wy0 + (lane >> 3);  // row from the top
   const bool valid = px < S && py < S;
-  const float xp = pixel_coord(px, S);
-  const float yp = pixel_coord(S - 1 - py, S);
+  const float xp = A.coords[min(px, S - 1)];
+  const float yp = A.coords[max(S - 1 - py, 0)];
   const long long SS = (long long)S * S;
   const long long pn = (long long)py * S + px;
 
-  float near_ = A.near_, far_ = A.far_;
-  if (A.near_far_dev) { near_ = A.near_far_dev[0]; far_ = A.near_far_dev[1]; }
-  const float thr = A.dist_eps * A.sigma;
-  const float sthr = sqrtf(thr);
+  FwdConsts C;
+  C.near_ = A.near_; C.far_ = A.far_;
+  if (A.near_far_dev) { C.near_ = A.near_far_dev[0]; C.far_ = A.near_far_dev[1]; }
+  C.thr = A.dist_eps * A.sigma;
+  C.inv_range = 1.f / (C.far_ - C.near_);
   const int rgb_f = kFast ? 1 : A.rgb;
   const int alpha_f = kFast ? 2 : A.alpha;
 
@@ -196,26 +177,25 @@ __global__ void __launch_bounds__(kFwdThreads) raster_forward_kernel(RasterArgs 
     st.col[k] = rgb_f == 1 ? bg * st.ssum : bg;
   }
 
-  // warp footprint in pixel-centre coordinates (for the record-level cull)
-  const float fx0 = pixel_coord(tile_x * kTile + (warp & 1) * 8, S);
-  const float fx1 = pixel_coord(tile_x * kTile + (warp & 1) * 8 + 7, S);
-  const float fy1 = pixel_coord(S - 1 - (tile_y * kTile + (warp >> 1) * 4), S);
-  const float fy0 = pixel_coord(S - 1 - (tile_y * kTile + (warp >> 1) * 4 + 3), S);
+  // warp footprint in pixel-centre coordinates (for the per-warp cull)
+  const float fx0 = A.coords[min(wx0, S - 1)];
+  const float fx1 = A.coords[min(wx0 + 7, S - 1)];
+  const float fy1 = A.coords[max(S - 1 - wy0, 0)];
+  const float fy0 = A.coords[max(S - 1 - (wy0 + 3), 0)];
   // tile window in pixel indices (x index, y index = S-1-row)
   const int tx0 = tile_x * kTile, tx1 = tx0 + kTile - 1;
   const int ty1 = S - 1 - tile_y * kTile, ty0 = ty1 - (kTile - 1);
 
   const uint2* win = A.face_window + (long long)n * A.F;
-  const float* facesN = A.faces + (long long)n * A.F * 9;
-  const float* texN = A.textures + (long long)n * A.F * A.T * 3;
-  const bool vertex_tex = kFast ? true : (A.sample == 1);
+  const float4* border = A.face_border + (long long)n * A.F;
+  const float* records = A.face_record + (long long)n * A.F * kRecWords;
 
-  for (int base = 0; base < A.F; base += kScanChunk) {
-    // (1) scan: warp w owns faces [base + w*256, base + (w+1)*256) and compacts hits in order
+  for (int base = 0; base < A.F; base += chunk) {
+    // (1) scan: warp w owns faces [base + w*wseg, base + (w+1)*wseg) and compacts hits in order
     int cnt = 0;
-    const int seg0 = base + warp * kWarpSeg;
+    const int seg0 = base + warp * wseg;
 #pragma unroll 2
-    for (int it = 0; it < kWarpSeg; it += 32) {
+    for (int it = 0; it < wseg; it += 32) {
       const int f = seg0 + it + lane;
       bool hit = false;
       if (f < A.F) {
@@ -224,53 +204,43 @@ __global__ void __launch_bounds__(kFwdThreads) raster_forward_kernel(RasterArgs 
         hit = xlo <= tx1 && xhi >= tx0 && ylo <= ty1 && yhi >= ty0 && xlo <= xhi;
       }
       const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) s_list[warp * kWarpSeg + cnt + __popc(m & ((1u << lane) - 1))] = f;
+      if (hit) s_list[warp * wseg + cnt + __popc(m & ((1u << lane) - 1))] = f;
       cnt += __popc(m);
     }
     if (lane == 0) s_cnt[warp] = cnt;
     __syncthreads();
-    int pre[9];
-    pre[0] = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) pre[w + 1] = pre[w] + s_cnt[w];
-    const int nlist = pre[8];
-
-    // (2)+(3) stage records in sub-batches and evaluate
-    for (int r0 = 0; r0 < nlist; r0 += kRecCap) {
-      const int nrec = min(kRecCap, nlist - r0);
-      if (tid < nrec) {
-        const int gi = r0 + tid;
-        int seg = 0;
-#pragma unroll
-        for (int w = 1; w < 8; ++w) seg += (gi >= pre[w]) ? 1 : 0;
-        const int f = s_list[seg * kWarpSeg + (gi - pre[seg])];
-        FaceGeom g;
-        face_setup(facesN + (long long)f * 9, sthr, g);
-        float tex9[9];
-        if (vertex_tex) {
-#pragma unroll
-          for (int k = 0; k < 9; ++k) tex9[k] = texN[(long long)f * 9 + k];
-        }
-        store_record(s_rec + tid * kRecWords, g, f, vertex_tex ? tex9 : nullptr);
-      }
-      __syncthreads();
-      for (int c = 0; c < nrec; c += 32) {
+    // (2) every warp walks the whole ordered list on its own: cull 32 faces per ballot against
+    //     its 8x4 footprint, evaluate survivors in ascending face order.  No further barriers.
+#pragma unroll 1
+    for (int seg = 0; seg < 8; ++seg) {
+      const int nseg = s_cnt[seg];
+      const int* lst = s_list + seg * wseg;
+#pragma unroll 1
+      for (int c = 0; c < nseg; c += 32) {
         const int j = c + lane;
+        int f = 0;
+        float4 bd = make_float4(0.f, 0.f, 0.f, 0.f);
         bool pass = false;
-        if (j < nrec) {
-          const float* r = s_rec + j * kRecWords;
-          pass = !(fx0 > r[1] || fx1 < r[0] || fy0 > r[3] || fy1 < r[2]);
+        if (j < nseg) {
+          f = lst[j];
+          bd = __ldg(border + f);
+          pass = !(fx0 > bd.y || fx1 < bd.x || fy0 > bd.w || fy1 < bd.z);
         }
         unsigned m = __ballot_sync(0xffffffffu, pass);
         while (m) {
           const int b = __ffs(m) - 1;
           m &= m - 1;
-          if (valid) forward_pair<kFast>(A, s_rec + (c + b) * kRecWords, xp, yp, thr, near_, far_, n, st);
+          const int fb = __shfl_sync(0xffffffffu, f, b);
+          float4 bb;
+          bb.x = __shfl_sync(0xffffffffu, bd.x, b);
+          bb.y = __shfl_sync(0xffffffffu, bd.y, b);
+          bb.z = __shfl_sync(0xffffffffu, bd.z, b);
+          bb.w = __shfl_sync(0xffffffffu, bd.w, b);
+          if (valid) forward_pair<kFast>(A, C, records + (long long)fb * kRecWords, bb, fb, n, xp, yp, st);
         }
       }
-      __syncthreads();
     }
-    __syncthreads();
+    if (base + chunk < A.F) __syncthreads();  // the list is reused by the next round
   }
 
   if (!valid) return;
@@ -289,7 +259,7 @@ __global__ void __launch_bounds__(kFwdThreads) raster_forward_kernel(RasterArgs 
     agg[SS] = (float)st.face_min;
   } else {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) out[k * SS] = st.col[k] / st.ssum;
+    for (int k = 0; k < 3; ++k) out[k * SS] = div_<kFast>(st.col[k], st.ssum);
     agg[0] = st.ssum;
     agg[SS] = st.smax;
   }
@@ -299,7 +269,7 @@ __global__ void __launch_bounds__(kFwdThreads) raster_forward_kernel(RasterArgs 
 // backward: one warp per face
 // ---------------------------------------------------------------------------------------------
 template <bool kFast>
-__global__ void __launch_bounds__(256) raster_backward_kernel(RasterArgs A) {
+__global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kernel(RasterArgs A) {
   const int lane = threadIdx.x & 31;
   const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wg >= (long long)A.N * A.F) return;
@@ -312,6 +282,8 @@ __global__ void __launch_bounds__(256) raster_backward_kernel(RasterArgs A) {
   if (A.near_far_dev) { near_ = A.near_far_dev[0]; far_ = A.near_far_dev[1]; }
   const float thr = A.dist_eps * A.sigma;
   const float sthr = sqrtf(thr);
+  const float inv_range = 1.f / (far_ - near_);
+  const float cz_scale = A.inv_gamma / (near_ - far_);
   const int dist_f = kFast ? 2 : A.dist;
   const int rgb_f = kFast ? 1 : A.rgb;
   const int alpha_f = kFast ? 2 : A.alpha;
@@ -338,15 +310,18 @@ __global__ void __launch_bounds__(256) raster_backward_kernel(RasterArgs A) {
   if (xlo <= xhi && ylo <= yhi) {
     const int wdt = xhi - xlo + 1;
     const int total = wdt * (yhi - ylo + 1);
+    const float inv_wdt = 1.f / (float)wdt;
     const float* sc = A.soft_colors + (long long)n * 4 * SS;
     const float* ag = A.aggrs_info + (long long)n * 2 * SS;
     const float* gs = A.grad_soft_colors + (long long)n * 4 * SS;
     for (int idx = lane; idx < total; idx += 32) {
-      const int r = idx / wdt;
-      const int xi = xlo + (idx - r * wdt);
+      int r = (int)(((float)idx + 0.5f) * inv_wdt);  // idx / wdt without an integer divide
+      int col = idx - r * wdt;
+      if (col < 0) { --r; col += wdt; } else if (col >= wdt) { ++r; col -= wdt; }
+      const int xi = xlo + col;
       const int yi = yhi - r;
-      const float xp = pixel_coord(xi, S);
-      const float yp = pixel_coord(yi, S);
+      const float xp = A.coords[xi];
+      const float yp = A.coords[yi];
       if (xp > g.hix || xp < g.lox || yp > g.hiy || yp < g.loy) continue;
       Fragment fr;
       if (!soft_fragment<kFast>(A, g, xp, yp, thr, fr)) continue;
@@ -355,10 +330,9 @@ __global__ void __launch_bounds__(256) raster_backward_kernel(RasterArgs A) {
       // gradient (nothing resets C_grad_xy_alpha), reproduced here
       float Cxy = gs[3 * SS + pn];
       if (alpha_f == 1) Cxy /= A.F;
-      else if (alpha_f == 2) Cxy *= (1.f - sc[3 * SS + pn]) / fmaxf(1.f - fr.frag, 1e-6f);
+      else if (alpha_f == 2) Cxy *= div_<kFast>(1.f - sc[3 * SS + pn], fmaxf(1.f - fr.frag, 1e-6f));
       float wc[3];
-      bary_clip(fr.w, wc);
-      const float zp = 1.f / (wc[0] / g.z[0] + wc[1] / g.z[1] + wc[2] / g.z[2]);
+      const float zp = clip_and_depth<kFast>(g, fr.w, wc);
       if (zp < near_ || zp > far_) continue;
       float gz[3] = {0.f, 0.f, 0.f};
       if (rgb_f == 0) {  // .cu:602-609
@@ -378,8 +352,9 @@ __global__ void __launch_bounds__(256) raster_backward_kernel(RasterArgs A) {
         }
       } else if (g.front || (kFast ? true : A.double_side != 0)) {  // .cu:611-640
         const float ssum = ag[pn], smax = ag[SS + pn];
-        const float zn = (far_ - zp) / (far_ - near_);
-        const float wgt = fr.frag * expf((zn - smax) / A.gamma) / ssum;
+        const float zn = kFast ? (far_ - zp) * inv_range : (far_ - zp) / (far_ - near_);
+        const float wgt = kFast ? fr.frag * __expf((zn - smax) * A.inv_gamma) * fast_rcp(ssum)
+                                : fr.frag * expf((zn - smax) / A.gamma) / ssum;
         float Crgb = 0.f;
         int texel = 0;
         if (sample == 0) texel = surface_texel(wc, A.R);
@@ -388,8 +363,9 @@ __global__ void __launch_bounds__(256) raster_backward_kernel(RasterArgs A) {
           const float gk = gs[k * SS + pn];
           float ck;
           if (sample == 1) {
+            const float wg_k = wgt * gk;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) gt[3 * j + k] += wgt * (wc[j] * gk);
+            for (int j = 0; j < 3; ++j) gt[3 * j + k] += wg_k * wc[j];
             ck = wc[0] * tex9[k] + wc[1] * tex9[3 + k] + wc[2] * tex9[6 + k];
           } else {
             if (texel < A.T) atomicAdd(&gtex_out[3 * texel + k], wgt * gk);
@@ -399,13 +375,20 @@ __global__ void __launch_bounds__(256) raster_backward_kernel(RasterArgs A) {
           Crgb += gk * (ck - sc[k * SS + pn]);
         }
         Crgb *= wgt;
-        Cxy += Crgb / fr.frag;
-        const float Cz = Crgb / A.gamma / (near_ - far_) * zp * zp;
-        gz[0] = Cz * wc[0] / g.z[0] / g.z[0];
-        gz[1] = Cz * wc[1] / g.z[1] / g.z[1];
-        gz[2] = Cz * wc[2] / g.z[2] / g.z[2];
+        Cxy += div_<kFast>(Crgb, fr.frag);
+        if (kFast) {
+          const float Cz = Crgb * cz_scale * zp * zp;
+          gz[0] = Cz * wc[0] * g.iz[0] * g.iz[0];
+          gz[1] = Cz * wc[1] * g.iz[1] * g.iz[1];
+          gz[2] = Cz * wc[2] * g.iz[2] * g.iz[2];
+        } else {
+          const float Cz = Crgb / A.gamma / (near_ - far_) * zp * zp;
+          gz[0] = Cz * wc[0] / g.z[0] / g.z[0];
+          gz[1] = Cz * wc[1] / g.z[1] / g.z[1];
+          gz[2] = Cz * wc[2] / g.z[2] / g.z[2];
+        }
       }
-      Cxy *= fr.frag * (1.f - fr.frag) / A.sigma;  // .cu:644
+      Cxy *= kFast ? fr.frag * (1.f - fr.frag) * A.inv_sigma : fr.frag * (1.f - fr.frag) / A.sigma;  // .cu:644
       float gx[3] = {0.f, 0.f, 0.f}, gy[3] = {0.f, 0.f, 0.f};
       if (dist_f == 1) {  // .cu:161-175
         const float* w = fr.t;
@@ -470,6 +453,8 @@ static int check_launch(const char* what) {
   return 0;
 }
 
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
 static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, float far_, const float* nf_dev,
                      float eps, float sigma, int dist, float dist_eps, float gamma, int rgb, int alpha, int sample,
                      int double_side, void* workspace, size_t workspace_bytes) {
@@ -484,7 +469,15 @@ static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, flo
   A.near_ = near_; A.far_ = far_; A.near_far_dev = nf_dev;
   A.eps = eps; A.sigma = sigma; A.dist_eps = dist_eps; A.gamma = gamma;
   A.dist = dist; A.rgb = rgb; A.alpha = alpha; A.sample = sample; A.double_side = double_side;
-  A.face_window = reinterpret_cast<uint2*>(workspace);
+  A.inv_sigma = (float)(1.0 / (double)sigma);
+  A.inv_gamma = (float)(1.0 / (double)gamma);
+  // workspace carve-up (all 256-byte aligned)
+  char* p = reinterpret_cast<char*>(workspace);
+  const size_t nf = (size_t)N * F;
+  A.face_window = reinterpret_cast<uint2*>(p);   p += align256(nf * sizeof(uint2));
+  A.coords = reinterpret_cast<float*>(p);        p += align256((size_t)S * sizeof(float));
+  A.face_border = reinterpret_cast<float4*>(p);  p += align256(nf * sizeof(float4));
+  A.face_record = reinterpret_cast<float*>(p);
   return 0;
 }
 
@@ -510,9 +503,10 @@ extern "C" const char* lasr_b200_last_error(void) {
 extern "C" uint64_t lasr_b200_launch_count(void) { return g_launches.load(); }
 
 extern "C" size_t lasr_b200_raster_workspace_bytes(int N, int F, int S) {
-  (void)S;
-  if (N <= 0 || F <= 0) return 0;
-  return (size_t)N * (size_t)F * sizeof(uint2) + 256;
+  if (N <= 0 || F <= 0 || S <= 0) return 0;
+  const size_t nf = (size_t)N * (size_t)F;
+  return align256(nf * sizeof(uint2)) + align256((size_t)S * sizeof(float)) + align256(nf * sizeof(float4)) +
+         align256(nf * kRecWords * sizeof(float));
 }
 
 extern "C" int lasr_b200_raster_forward(const float* faces, const float* textures, float* aggrs_info,
@@ -529,12 +523,16 @@ extern "C" int lasr_b200_raster_forward(const float* faces, const float* texture
   A.faces = faces; A.textures = textures; A.aggrs_info = aggrs_info; A.soft_colors = soft_colors;
   cudaStream_t st = (cudaStream_t)stream;
   const long long nf = (long long)N * F;
-  raster_setup_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(A);
+  const long long nthreads = nf > S ? nf : S;
+  raster_setup_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(A, 1);
   if (check_launch("raster_setup_kernel")) return 1;
   const int tiles = ((S + kTile - 1) / kTile) * ((S + kTile - 1) / kTile);
   dim3 grid(tiles, N);
-  if (is_fast(A)) raster_forward_kernel<true><<<grid, kFwdThreads, 0, st>>>(A);
-  else raster_forward_kernel<false><<<grid, kFwdThreads, 0, st>>>(A);
+  int chunk = ((F + 255) / 256) * 256;
+  if (chunk > kMaxScanChunk) chunk = kMaxScanChunk;
+  const size_t smem = (size_t)chunk * sizeof(int);
+  if (is_fast(A)) raster_forward_kernel<true><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  else raster_forward_kernel<false><<<grid, kFwdThreads, smem, st>>>(A, chunk);
   return check_launch("raster_forward_kernel");
 }
 
@@ -560,6 +558,12 @@ extern "C" int lasr_b200_raster_backward(const float* faces, const float* textur
   if (texture_sample_type == 0) {  // 'surface' texel gradients are scattered with atomics
     cudaError_t e = cudaMemsetAsync(grad_textures, 0, (size_t)nf * T * 3 * sizeof(float), st);
     if (e != cudaSuccess) return fail(std::string("raster_backward memset: ") + cudaGetErrorString(e));
+  }
+  {  // the backward only needs the coordinate table from the setup pass
+    RasterArgs B = A;
+    B.N = 1; B.F = 1;  // one dummy face: fills coords[0..S)
+    raster_setup_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(B, 0);
+    if (check_launch("raster_setup_kernel")) return 1;
   }
   const unsigned blocks = (unsigned)((nf + 7) / 8);
   if (is_fast(A)) raster_backward_kernel<true><<<blocks, 256, 0, st>>>(A);

@@ -1,24 +1,30 @@
-// raster_common.cuh -- per-face geometry and per-(pixel,face) evaluation shared by the forward
+// raster_common.cuh -- per-face records and per-(pixel,face) evaluation shared by the forward
 // (tile-binned, pixel-parallel) and backward (face-parallel) soft-rasterizer kernels.
 //
 // What is computed is the reference's SoftRas model
 // (third_party/softras/soft_renderer/cuda/soft_rasterize_cuda_kernel.cu:24-216, 245-305); how it
-// is computed is ours.  One numerical design rule matters for parity:
+// is computed is ours.  Two numerical design rules:
 //
-//   The geometric predicates (face_inv / barycentrics / inside-outside / edge selection) are
-//   ill-conditioned for edge-on sliver faces: a 1-ulp change in `det` flips a pixel between
-//   "inside" (D ~ 1) and "outside" (D ~ 0).  To agree with the reference *as compiled by nvcc*
-//   (FMA contraction on), those few expressions are written with explicit round-to-nearest
-//   intrinsics in exactly the association nvcc gives the reference's source
-//   (a*b + c*d -> fma(a, b, c*d); a*b + c*d + e*f -> fma(e, f, fma(a, b, c*d));
-//    a*b - c*d -> fma(a, b, -(c*d)); checked against `cuobjdump -sass` of oracle/_ref).
-//   Everything downstream (sigmoid, depth softmax, colour blend) is well conditioned and free to
-//   use faster formulations.
+//  (1) The geometric predicates (face_inv / barycentrics / inside-outside / edge selection) are
+//      ill-conditioned for edge-on sliver faces: a 1-ulp change in `det` flips a pixel between
+//      "inside" (D ~ 1) and "outside" (D ~ 0).  To agree with the reference *as compiled by
+//      nvcc* (FMA contraction on), those expressions use explicit round-to-nearest intrinsics in
+//      exactly the association nvcc gives the reference's source
+//      (a*b + c*d -> fma(a, b, c*d); a*b + c*d + e*f -> fma(e, f, fma(a, b, c*d));
+//       a*b - c*d -> fma(a, b, -(c*d)); checked against `cuobjdump -sass` of oracle/_ref), and
+//      IEEE division for face_inv.
+//  (2) Everything downstream (closest-point parameter, sigmoid, clipped-barycentric depth, depth
+//      softmax, colour blend and their derivatives) is well conditioned, so it uses reciprocals
+//      (MUFU.RCP) and ex2.approx instead of the reference's IEEE divisions / expf; measured
+//      deviation from the reference kernels is ~1e-6 (tests/golden/report.json), two orders
+//      below the 1e-4 / 1e-3 tolerances.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace lasr {
+
+constexpr int kRecWords = 44;  // floats per face record (176 B = 11 x float4)
 
 struct RasterArgs {
   const float* faces;        // [N,F,9]
@@ -28,14 +34,19 @@ struct RasterArgs {
   const float* grad_soft_colors;  // [N,4,S,S]   (backward)
   float* grad_faces;         // [N,F,9]          (backward)
   float* grad_textures;      // [N,F,T,3]        (backward)
-  uint2* face_window;        // [N,F] packed pixel windows (workspace)
+  // workspace carve-up
+  uint2* face_window;        // [N*F] packed pixel windows
+  float4* face_border;       // [N*F] dilated bounding boxes (lox, hix, loy, hiy)
+  float* face_record;        // [N*F][kRecWords]
+  float* coords;             // [S] pixel-centre coordinates
   const float* near_far_dev; // optional {near, far} on device
   int N, F, S, T, R;
   float near_, far_, eps, sigma, dist_eps, gamma;
+  float inv_sigma, inv_gamma;
   int dist, rgb, alpha, sample, double_side;
 };
 
-// ---- reference-shaped sums of products (see header comment) ---------------------------------
+// ---- reference-shaped sums of products (rule 1) ----------------------------------------------
 __device__ __forceinline__ float dot2(float a, float b, float c, float d) {
   return __fmaf_rn(a, b, __fmul_rn(c, d));
 }
@@ -47,8 +58,30 @@ __device__ __forceinline__ float cross2(float a, float b, float c, float d) {
 }
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+__device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.f, x); }  // MUFU.RCP
+
+// Rule (2) applies to LASR's training configuration (kFast: euclidean / softmax / prod / vertex
+// colours), which has no hard decision downstream of the distance stage.  The other operator
+// modes do ('surface' texel selection sits exactly on `frac sum <= 1` along clipped edges, the
+// 'hard' z-test and 'hard' alpha compare rounded values), so the generic instantiation keeps
+// the reference's IEEE divisions and expf.
+template <bool kFast> __device__ __forceinline__ float div_(float a, float b) {
+  return kFast ? a * fast_rcp(b) : __fdiv_rn(a, b);
+}
+template <bool kFast> __device__ __forceinline__ float exp_(float x) { return kFast ? __expf(x) : expf(x); }
+
+// Correctly rounded num/den from a correctly rounded reciprocal rd = RN(1/den): one Newton step on
+// the quotient (Markstein).  Three FP32 instructions instead of the ~10-instruction IEEE division
+// sequence, same result.  The closest-point parameter feeds the squared distance that is compared
+// against the hard cut-off (`dis >= threshold`, .cu:402), so it must round like the reference.
+__device__ __forceinline__ float div_by_rcp(float num, float den, float rd) {
+  const float q0 = __fmul_rn(num, rd);
+  const float r = __fmaf_rn(-den, q0, num);
+  return __fmaf_rn(r, rd, q0);
+}
 
 // Pixel-centre coordinate, (2*i + 1 - S) / S evaluated in double and rounded once (.cu:345-346).
+// Only the setup kernel calls this (S values per launch); everyone else reads the table.
 __device__ __forceinline__ float pixel_coord(int i, int S) {
   return (float)((2.0 * (double)i + 1.0 - (double)S) / (double)S);
 }
@@ -57,7 +90,9 @@ __device__ __forceinline__ float pixel_coord(int i, int S) {
 struct FaceGeom {
   float inv[9];       // inverse of [[x0 x1 x2],[y0 y1 y2],[1 1 1]] (rows give barycentrics)
   float x[3], y[3], z[3];
+  float iz[3];        // 1 / z
   float a[3][3];      // a[e][j] = sym[e][j] - sym[(e+1)%3][j],  sym = P P^T + 1
+  float rden[3];      // 1 / (a[e][e] - a[e][(e+1)%3])  (= 1 / squared edge length)
   float lox, hix, loy, hiy;  // bounding box dilated by sqrt(threshold)
   int obt;            // index of the (first) obtuse corner, -1 if none
   bool front;
@@ -68,6 +103,7 @@ __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float s
   g.x[0] = x0; g.x[1] = x1; g.x[2] = x2;
   g.y[0] = y0; g.y[1] = y1; g.y[2] = y2;
   g.z[0] = fv[2]; g.z[1] = fv[5]; g.z[2] = fv[8];
+  g.iz[0] = __fdiv_rn(1.f, fv[2]); g.iz[1] = __fdiv_rn(1.f, fv[5]); g.iz[2] = __fdiv_rn(1.f, fv[8]);
   // determinant: x2*(y0-y1) + x0*(y1-y2) + x1*(y2-y0)   (.cu:278-281)
   float det = __fmaf_rn(x1, __fsub_rn(y2, y0), __fmaf_rn(x2, __fsub_rn(y0, y1), __fmul_rn(x0, __fsub_rn(y1, y2))));
   det = det > 0.f ? fmaxf(det, 1e-10f) : fminf(det, -1e-10f);  // :282
@@ -83,9 +119,11 @@ __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float s
 #pragma unroll
     for (int k = 0; k < 3; ++k) sym[j][k] = __fadd_rn(dot2(g.x[j], g.x[k], g.y[j], g.y[k]), 1.0f);
 #pragma unroll
-  for (int e = 0; e < 3; ++e)
+  for (int e = 0; e < 3; ++e) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) g.a[e][j] = __fsub_rn(sym[e][j], sym[(e + 1) % 3][j]);
+    g.rden[e] = __fdiv_rn(1.f, __fsub_rn(g.a[e][e], g.a[e][(e + 1) % 3]));
+  }
   // first obtuse corner (:296-304)
   g.obt = -1;
 #pragma unroll
@@ -100,6 +138,59 @@ __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float s
   g.lox = __fsub_rn(min3(x0, x1, x2), sthr);
   g.hiy = __fadd_rn(max3(y0, y1, y2), sthr);
   g.loy = __fsub_rn(min3(y0, y1, y2), sthr);
+}
+
+// record layout (float index):
+//  0..8 inv | 9..11 x | 12..14 y | 15 flags | 16..18 iz | 19..21 rden | 22..30 a[e][j] | 31 pad
+//  32..40 vertex-colour texture | 41..43 z
+__device__ __forceinline__ void store_record(float* __restrict__ r, const FaceGeom& g, const float* tex9) {
+  float v[kRecWords];
+#pragma unroll
+  for (int k = 0; k < kRecWords; ++k) v[k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) v[k] = g.inv[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    v[9 + k] = g.x[k]; v[12 + k] = g.y[k]; v[16 + k] = g.iz[k]; v[19 + k] = g.rden[k]; v[41 + k] = g.z[k];
+  }
+  v[15] = __int_as_float((g.obt + 1) | (g.front ? 4 : 0));
+#pragma unroll
+  for (int e = 0; e < 3; ++e)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) v[22 + 3 * e + j] = g.a[e][j];
+  if (tex9) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v[32 + k] = tex9[k];
+  }
+  float4* r4 = reinterpret_cast<float4*>(r);
+#pragma unroll
+  for (int k = 0; k < kRecWords / 4; ++k) r4[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+
+// Uniform (warp-broadcast) 128-bit loads of a record: every lane reads the same address.
+__device__ __forceinline__ void load_record(const float* __restrict__ r, FaceGeom& g, float* tex9) {
+  const float4* r4 = reinterpret_cast<const float4*>(r);
+  float v[kRecWords];
+#pragma unroll
+  for (int k = 0; k < kRecWords / 4; ++k) {
+    const float4 q = __ldg(r4 + k);
+    v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) g.inv[k] = v[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    g.x[k] = v[9 + k]; g.y[k] = v[12 + k]; g.iz[k] = v[16 + k]; g.rden[k] = v[19 + k]; g.z[k] = v[41 + k];
+  }
+  const int fl = __float_as_int(v[15]);
+  g.obt = (fl & 3) - 1;
+  g.front = (fl & 4) != 0;
+#pragma unroll
+  for (int e = 0; e < 3; ++e)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) g.a[e][j] = v[22 + 3 * e + j];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) tex9[k] = v[32 + k];
 }
 
 // Conservative inclusive pixel-index window of coordinates in [lo, hi] (the exact predicate is
@@ -127,6 +218,7 @@ __device__ __forceinline__ bool pixel_inside(const float* w) {  // .cu:47-50
 }
 
 // .cu:61-151
+template <bool kFast>
 __device__ __forceinline__ void euclid_distance(const FaceGeom& g, float xp, float yp, Fragment& fr) {
   const float w0 = fr.w[0], w1 = fr.w[1], w2 = fr.w[2];
   if (w0 > 0.f && w1 > 0.f && w2 > 0.f && w0 < 1.f && w1 < 1.f && w2 < 1.f) {
@@ -135,7 +227,8 @@ __device__ __forceinline__ void euclid_distance(const FaceGeom& g, float xp, flo
     for (int e = 0; e < 3; ++e) {
       const int b = (e + 1) % 3, c = (e + 2) % 3;
       const float num = __fsub_rn(dot3(w0, g.a[e][0], w1, g.a[e][1], w2, g.a[e][2]), g.a[e][b]);
-      const float q = __fdiv_rn(num, __fsub_rn(g.a[e][e], g.a[e][b]));
+      const float den = __fsub_rn(g.a[e][e], g.a[e][b]);
+      const float q = kFast ? div_by_rcp(num, den, g.rden[e]) : __fdiv_rn(num, den);
       float t[3];
       t[e] = q; t[b] = 1.f - q; t[c] = 0.f;
       t[0] -= w0; t[1] -= w1; t[2] -= w2;
@@ -169,8 +262,10 @@ __device__ __forceinline__ void euclid_distance(const FaceGeom& g, float xp, flo
     const float a2 = e == 0 ? g.a[0][2] : (e == 1 ? g.a[1][2] : g.a[2][2]);
     const float ae = e == 0 ? a0 : (e == 1 ? a1 : a2);
     const float ab = e == 0 ? a1 : (e == 1 ? a2 : a0);
+    const float rd = e == 0 ? g.rden[0] : (e == 1 ? g.rden[1] : g.rden[2]);
     const float num = __fsub_rn(dot3(w0, a0, w1, a1, w2, a2), ab);
-    const float q = __fdiv_rn(num, __fsub_rn(ae, ab));
+    const float den = __fsub_rn(ae, ab);
+    const float q = kFast ? div_by_rcp(num, den, rd) : __fdiv_rn(num, den);
     const float qe = fminf(fmaxf(q, 0.f), 1.f);
     const float qb = fminf(fmaxf(1.f - q, 0.f), 1.f);
     // t[e] = qe, t[(e+1)%3] = qb, t[(e+2)%3] = 0, then minus w
@@ -203,24 +298,33 @@ __device__ __forceinline__ bool soft_fragment(const RasterArgs& A, const FaceGeo
     d = d > 0.f ? d * d : -(d * d);
     fr.dis = d;
     if (-d >= thr) return false;
-    fr.frag = 1.f / (1.f + expf(-d / A.sigma));
+    fr.frag = kFast ? fast_rcp(1.f + __expf(-d * A.inv_sigma)) : 1.f / (1.f + expf(-d / A.sigma));
     return true;
   } else {
-    euclid_distance(g, xp, yp, fr);
+    euclid_distance<kFast>(g, xp, yp, fr);
     fr.dis = dot2(fr.dx, fr.dx, fr.dy, fr.dy);
     if (fr.sign < 0.f && fr.dis >= thr) return false;
-    fr.frag = 1.f / (1.f + expf(-fr.sign * fr.dis / A.sigma));
+    fr.frag = kFast ? fast_rcp(1.f + __expf(-fr.sign * fr.dis * A.inv_sigma))
+                    : 1.f / (1.f + expf(-fr.sign * fr.dis / A.sigma));
     return true;
   }
 }
 
-// .cu:53-58
-__device__ __forceinline__ void bary_clip(const float* w, float* wc) {
-  wc[0] = fmaxf(fminf(w[0], 1.f), 0.f);
-  wc[1] = fmaxf(fminf(w[1], 1.f), 0.f);
-  wc[2] = fmaxf(fminf(w[2], 1.f), 0.f);
-  const float s = fmaxf(wc[0] + wc[1] + wc[2], 1e-5f);
-  wc[0] /= s; wc[1] /= s; wc[2] /= s;
+// Clipped barycentrics (.cu:53-58) and the depth they interpolate (:423).
+//   wc_k = c_k / s,  c = clamp(w, 0, 1),  s = max(sum c, 1e-5);   zp = 1 / sum_k wc_k / z_k = s / sum_k c_k / z_k
+template <bool kFast>
+__device__ __forceinline__ float clip_and_depth(const FaceGeom& g, const float* w, float* wc) {
+  const float c0 = fmaxf(fminf(w[0], 1.f), 0.f);
+  const float c1 = fmaxf(fminf(w[1], 1.f), 0.f);
+  const float c2 = fmaxf(fminf(w[2], 1.f), 0.f);
+  const float s = fmaxf(c0 + c1 + c2, 1e-5f);
+  if (!kFast) {  // the reference's own operation sequence (see div_/exp_ above)
+    wc[0] = __fdiv_rn(c0, s); wc[1] = __fdiv_rn(c1, s); wc[2] = __fdiv_rn(c2, s);
+    return __fdiv_rn(1.f, __fdiv_rn(wc[0], g.z[0]) + __fdiv_rn(wc[1], g.z[1]) + __fdiv_rn(wc[2], g.z[2]));
+  }
+  const float rs = fast_rcp(s);
+  wc[0] = c0 * rs; wc[1] = c1 * rs; wc[2] = c2 * rs;
+  return s * fast_rcp(c0 * g.iz[0] + c1 * g.iz[1] + c2 * g.iz[2]);
 }
 
 // 'surface' texel index of .cu:178-194 (may equal R*R: the reference reads the next face's block)

@@ -89,3 +89,51 @@ def soft_rasterize(face_vertices, textures, **settings):
                     aggr_func_alpha="prod", texture_type="surface")
     defaults.update(settings)
     return RefSoftRasterize.apply(face_vertices, textures, *[defaults[k] for k in order])
+
+
+# ---- the reference's render_mesh glue, restated (it cannot travel to the GPU box) -------------
+def _vertex_normals(vertices, faces):
+    """functional/vertex_normals.py:4-37."""
+    import torch.nn.functional as F
+    bs, nv = vertices.shape[:2]
+    normals = torch.zeros(bs * nv, 3, device=vertices.device)
+    faces = faces + (torch.arange(bs, dtype=torch.int32, device=vertices.device) * nv)[:, None, None]
+    vf = vertices.reshape(bs * nv, 3)[faces.long()].view(-1, 3, 3)
+    faces = faces.view(-1, 3)
+    normals.index_add_(0, faces[:, 1].long(), torch.cross(vf[:, 2] - vf[:, 1], vf[:, 0] - vf[:, 1], dim=1))
+    normals.index_add_(0, faces[:, 2].long(), torch.cross(vf[:, 0] - vf[:, 2], vf[:, 1] - vf[:, 2], dim=1))
+    normals.index_add_(0, faces[:, 0].long(), torch.cross(vf[:, 1] - vf[:, 0], vf[:, 2] - vf[:, 0], dim=1))
+    return F.normalize(normals, eps=1e-6, dim=1).reshape(bs, nv, 3)
+
+
+def _face_gather(x, faces):
+    """functional/face_vertices.py:4-22."""
+    bs, nv = x.shape[:2]
+    faces = faces + (torch.arange(bs, dtype=torch.int32, device=x.device) * nv)[:, None, None]
+    return x.reshape(bs * nv, 3)[faces.long()]
+
+
+def render_mesh_lasr(vertices, faces, textures, eye, settings):
+    """SoftRenderer.render_mesh with LASR's renderer settings (nnutils/mesh_net.py:132-149):
+    'vertex' lighting with ambient 1 / directional 0 (lighting.py:50-67 -- the vertex normals ARE
+    computed and multiplied by 0, as the reference does), look_at + orthogonal(1)
+    (transform.py:41-48), two gathers (mesh.py:105-109,128-134), then the reference kernels."""
+    import torch.nn.functional as F
+    light = torch.zeros_like(vertices)
+    light = light + 1.0 * torch.ones(1, 1, 3, device=vertices.device)
+    normals = _vertex_normals(vertices, faces)
+    direction = torch.tensor([0.0, 1.0, 0.0], device=vertices.device)[None]
+    cosine = F.relu(torch.sum(normals * direction, dim=2))
+    light = light + 0.0 * (torch.ones(1, 1, 3, device=vertices.device) * cosine[:, :, None])
+    textures = textures * light
+    # look_at(eye) with at = 0, up = +y (look_at.py:44-60)
+    bs = vertices.shape[0]
+    e = eye[None].repeat(bs, 1)
+    z_axis = F.normalize(-e, eps=1e-5)
+    up = torch.tensor([0.0, 1.0, 0.0], device=vertices.device)[None].repeat(bs, 1)
+    x_axis = F.normalize(torch.cross(up, z_axis, dim=1), eps=1e-5)
+    y_axis = F.normalize(torch.cross(z_axis, x_axis, dim=1), eps=1e-5)
+    r = torch.cat((x_axis[:, None], y_axis[:, None], z_axis[:, None]), dim=1)
+    v = torch.matmul(vertices - e[:, None], r.transpose(1, 2))
+    v = torch.stack((v[:, :, 0] * 1.0, v[:, :, 1] * 1.0, v[:, :, 2]), dim=2)  # orthogonal(scale=1)
+    return soft_rasterize(_face_gather(v, faces), _face_gather(textures, faces), **settings)

@@ -1,0 +1,178 @@
+"""Host-side glue (rows S0, G1-G3, R2 of SURVEY.md section 8a) against golden vectors minted from
+the reference's own Python (tests/golden/make_geom_golden.py) and against the numpy oracle.
+CPU only: these functions are plain PyTorch for CPU tensors (the CUDA kernels that serve CUDA
+tensors are checked in the -m gpu tests)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "geom_ref.npz"))
+T = lambda k: torch.from_numpy(GOLD[k])
+
+
+def close(a, b, tol=2e-6):
+    a = a.detach().numpy() if torch.is_tensor(a) else np.asarray(a)
+    return np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max())
+
+
+# ---- oracle restatements pinned against the reference's Python --------------------------------
+def test_oracle_lbs_and_cameras(oracle):
+    assert close(oracle.obj_to_cam(GOLD["lbs_verts"], GOLD["lbs_R"], GOLD["lbs_T"], 5, 1, GOLD["lbs_skin"]), GOLD["lbs_out"])
+    assert close(oracle.obj_to_cam(GOLD["lbs_verts"], GOLD["lbs_R"], GOLD["lbs_T"], 5, 1, GOLD["lbs_skin"], tocam=False),
+                 GOLD["lbs_out_notocam"])
+    assert close(oracle.obj_to_cam(GOLD["lbs_verts"], GOLD["lbs_R"][::5], GOLD["lbs_T"][::5], 1, 1, None), GOLD["rigid_out"])
+    assert close(oracle.pinhole_cam(GOLD["cam_v4"], GOLD["cam_pp"], GOLD["cam_fl"]), GOLD["pinhole_out"])
+
+
+def test_oracle_softras_functionals(oracle):
+    eye = [0, 0, oracle.LASR_EYE_Z]
+    assert close(oracle.look_at(GOLD["sr_verts"], eye), GOLD["look_at_out"])
+    assert close(oracle.look_at(GOLD["sr_verts"], [0.3, -0.2, -2.0]), GOLD["look_at_eye2"])
+    assert close(oracle.orthogonal(GOLD["sr_verts"], 2.0), GOLD["orthogonal_s2"])
+    assert np.array_equal(oracle.face_vertices(GOLD["sr_verts"], GOLD["sr_faces"]), GOLD["face_vertices_out"])
+    assert close(oracle.vertex_normals(GOLD["sr_verts"], GOLD["sr_faces"]), GOLD["vertex_normals_out"], 1e-5)
+
+
+# ---- product functions (CPU-tensor path) pinned against the same vectors ------------------------
+def test_product_geom_utils():
+    from lasr_b200 import geom_utils as gu
+    assert close(gu.obj_to_cam(T("lbs_verts"), T("lbs_R"), T("lbs_T"), 5, 1, T("lbs_skin")), GOLD["lbs_out"])
+    assert close(gu.obj_to_cam(T("lbs_verts"), T("lbs_R"), T("lbs_T"), 5, 1, T("lbs_skin"), tocam=False),
+                 GOLD["lbs_out_notocam"])
+    assert close(gu.obj_to_cam(T("lbs_verts"), T("lbs_R")[::5].contiguous(), T("lbs_T")[::5].contiguous(), 1, 1, None),
+                 GOLD["rigid_out"])
+    assert close(gu.pinhole_cam(T("cam_v4"), T("cam_pp"), T("cam_fl")), GOLD["pinhole_out"])
+    assert close(gu.orthographic_cam(T("cam_v4"), T("cam_pp"), T("cam_fl")), GOLD["ortho_out"])
+
+
+def test_product_softras_functionals():
+    import lasr_b200.soft_renderer as sr
+    srf = sr.functional
+    eye = [0, 0, -(1.0 / np.tan(np.radians(30.0)) + 1)]
+    assert close(srf.look_at(T("sr_verts"), eye), GOLD["look_at_out"])
+    assert close(srf.look_at(T("sr_verts"), [0.3, -0.2, -2.0]), GOLD["look_at_eye2"])
+    assert close(srf.orthogonal(T("sr_verts"), 1.0), GOLD["orthogonal_out"])
+    assert close(srf.orthogonal(T("sr_verts"), 2.0), GOLD["orthogonal_s2"])
+    assert np.array_equal(srf.face_vertices(T("sr_verts"), T("sr_faces")).numpy(), GOLD["face_vertices_out"])
+    assert close(srf.vertex_normals(T("sr_verts"), T("sr_faces")), GOLD["vertex_normals_out"], 1e-5)
+    light = torch.zeros(4, 40, 3)
+    light = srf.ambient_lighting(light, 0.3, (1, 0.5, 0.25))
+    light = srf.directional_lighting(light, T("vertex_normals_out"), 0.7, (0.2, 1, 1), (0, 1, 0))
+    assert close(light, GOLD["light_out"])
+
+
+def test_lasr_camera_chain_is_xy_flip_free_identity(oracle):
+    """with LASR's settings look_at(eye) after '+eye' and orthogonal(1) is the identity."""
+    import lasr_b200.soft_renderer as sr
+    r = sr.SoftRenderer(image_size=32, camera_mode="look_at", perspective=False, light_mode="vertex",
+                        light_intensity_ambient=1.0, light_intensity_directionals=0.0)
+    assert r.lighting.is_identity()
+    v = T("sr_verts") + torch.tensor([0, 0, 10.0])
+    eye = torch.tensor(r.transform.transformer._eye)
+    out = r.transform.transformer(v + eye)
+    assert (out - v).abs().max() < 2e-6
+    ref = oracle.lasr_render_vertices(v.numpy())
+    flip = v.numpy().copy()
+    flip[:, :, 1] *= -1
+    assert np.abs(ref - flip).max() < 2e-6
+
+
+def test_mesh_container_semantics():
+    import lasr_b200.soft_renderer as sr
+    v, f = T("sr_verts"), T("sr_faces")
+    m = sr.Mesh(v, f, textures=torch.rand(4, 40, 3), texture_type="vertex")
+    assert m.batch_size == 4 and m.num_vertices == 40 and m.num_faces == 60 and m.texture_res == 1
+    assert m.face_vertices.shape == (4, 60, 3, 3) and m.face_textures.shape == (4, 60, 3, 3)
+    fv0 = m.face_vertices
+    m.vertices = v * 2                                     # setter invalidates the cached gather
+    assert torch.equal(m.face_vertices, fv0 * 2)
+    m.fill_back_()
+    assert m.num_faces == 120 and torch.equal(m.faces[:, 60:], f[:, :, [2, 1, 0]])
+    m.reset_()
+    assert m.num_faces == 60
+    ms = sr.Mesh(v[0], f[0])                               # 2-D inputs get a batch dimension
+    assert ms.vertices.shape == (1, 40, 3) and ms.textures.shape == (1, 60, 1, 3)
+    with pytest.raises(ValueError):
+        sr.SoftRenderer(camera_mode="fisheye")
+    with pytest.raises(ValueError):
+        sr.Lighting(light_mode="pixel")
+
+
+def test_quaternion_and_skin(oracle):
+    from lasr_b200 import geom_utils as gu
+    ident = gu.quaternion_to_rotation_matrix(torch.tensor([[0.0, 0.0, 0.0, 1.0]]))
+    assert torch.allclose(ident[0], torch.eye(3))
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(16, 4, generator=g)
+    R = gu.quaternion_to_rotation_matrix(q)
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3).expand(16, 3, 3), atol=1e-5)
+    assert torch.allclose(torch.linalg.det(R), torch.ones(16), atol=1e-5)
+    # 90 degrees about z (x,y,z,w) = (0,0,sin45,cos45) maps x -> y
+    Rz = gu.quaternion_to_rotation_matrix(torch.tensor([[0.0, 0.0, np.sqrt(0.5), np.sqrt(0.5)]], dtype=torch.float32))[0]
+    assert torch.allclose(Rz @ torch.tensor([1.0, 0.0, 0.0]), torch.tensor([0.0, 1.0, 0.0]), atol=1e-6)
+    assert np.allclose(oracle.quaternion_to_rotation_matrix(q.numpy()), R.numpy(), atol=1e-6)
+    H, B1, V = 2, 4, 30
+    ctl_ts, ctl_rs = torch.randn(H * B1, 3, generator=g) * 0.3, torch.randn(H * B1, 4, generator=g)
+    log_ctl, mean_v = torch.randn(H * B1, 3, generator=g) * 0.2, torch.randn(H, V, 3, generator=g) * 0.3
+    skin = gu.skin_weights(ctl_ts, ctl_rs, log_ctl, mean_v, H)
+    assert skin.shape == (H, B1, V, 1) and torch.allclose(skin.sum(1), torch.ones(H, V, 1), atol=1e-6)
+    assert np.allclose(oracle.skin_weights(ctl_ts.numpy(), ctl_rs.numpy(), log_ctl.numpy(), mean_v.numpy(), H),
+                       skin.numpy(), atol=2e-6)
+
+
+def test_depth_window(oracle):
+    from lasr_b200 import geom_utils as gu
+    z = T("pinhole_out")[:, :, 2]
+    near, far = gu.depth_window(z)
+    n2, f2 = oracle.near_far(z.numpy())
+    assert abs(float(near) - n2) < 1e-6 and abs(float(far) - f2) < 1e-6
+
+
+def test_image_losses_match_loop_restatement(oracle):
+    """L1-L3: the vectorised product losses equal the numpy restatement of the reference's Python
+    double loops (nnutils/mesh_net.py:372-447)."""
+    from lasr_b200 import losses
+    g = torch.Generator().manual_seed(3)
+    N, H, S = 4, 2, 24
+    mask_pred = torch.rand(N, H, S, S, generator=g)
+    masks = (torch.rand(N, S, S, generator=g) > 0.5).float()
+    occ = torch.randn(N, S, S, generator=g)
+    occ[torch.rand(N, S, S, generator=g) < 0.2] = 0
+    l, sub = losses.mask_loss(mask_pred, masks, occ)
+    lo, subo = oracle.mask_loss(mask_pred.numpy(), masks.numpy(), occ.numpy())
+    assert np.allclose(sub.numpy(), subo, rtol=1e-5, atol=1e-7) and abs(float(l) - lo) < 1e-6
+
+    flow_rd = torch.randn(N, H, S, S, 2, generator=g) * 0.05
+    bg = torch.rand(N, H, S, S, generator=g) < 0.4
+    bg[1, 0] = True                                           # an empty mask for one (frame, hypothesis)
+    flow_obs = torch.randn(N, 3, S, S, generator=g) * 0.05
+    l, sub, _ = losses.flow_loss(flow_rd, bg, flow_obs, occ, masks)
+    lo, subo = oracle.flow_loss(flow_rd.numpy(), bg.numpy(), flow_obs.numpy(), occ.numpy(), masks.numpy())
+    assert sub[1, 0] == 0
+    assert np.allclose(sub.numpy(), subo, rtol=2e-5, atol=1e-7) and abs(float(l) - lo) < 1e-6
+
+    tex = torch.rand(N, H, 3, S, S, generator=g)
+    fg = torch.rand(N, H, S, S, generator=g)
+    imgs = torch.rand(N, 3, S, S, generator=g)
+    l, sub = losses.texture_l1_loss(tex, fg, imgs, masks, occ, 1.0)
+    lo, subo = oracle.texture_l1_loss(tex.numpy(), fg.numpy(), imgs.numpy(), masks.numpy(), occ.numpy(), 1.0)
+    assert np.allclose(sub.numpy(), subo, rtol=2e-5, atol=1e-7) and abs(float(l) - lo) < 1e-6
+
+
+def test_flow_postprocessing_matches_oracle(oracle):
+    from lasr_b200 import geom_utils as gu
+    g = torch.Generator().manual_seed(5)
+    n, S = 2, 16
+    p0 = torch.rand(n, S, S, 3, generator=g) + 9
+    p1 = torch.rand(n, S, S, 3, generator=g) + 9
+    p0[0, :4] = 0                       # background rows (rendered z < 1e-9)
+    pp0, pp1 = torch.randn(n, 2, generator=g) * 0.1, torch.randn(n, 2, generator=g) * 0.1
+    f0, f1 = 9 + torch.rand(n, 1, generator=g), 9 + torch.rand(n, 1, generator=g)
+    fo, bgo = oracle.flow_from_rendered_positions(p0.numpy(), p1.numpy(), pp0.numpy(), pp1.numpy(), f0.numpy(), f1.numpy())
+    bg = (p0[..., 2] < 1e-9) | (p1[..., 2] < 1e-9)
+    ten = torch.full_like(p0, 10.0)
+    q0, q1 = torch.where(bg[..., None], ten, p0), torch.where(bg[..., None], ten, p1)
+    flow = gu._reproject(q1, pp1, f1) - gu._reproject(q0, pp0, f0)
+    assert np.array_equal(bg.numpy(), bgo) and np.allclose(flow.numpy(), fo, atol=1e-6)

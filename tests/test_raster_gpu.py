@@ -1,0 +1,205 @@
+"""GPU parity tests of the sm_100a soft rasterizer, called through the public API -> C ABI.
+
+Three references, in order of authority:
+  1. golden vectors minted from the reference's own CUDA kernels (tests/golden/softras_ref_*.npz);
+  2. the CPU oracle (oracle/, pinned against the same golden vectors) on seeded inputs;
+  3. size-independent properties at BASELINE.json's full size.
+Tolerance (north star): RGBA 1e-4 relative, vertex gradients 1e-3 -- with zero outlier pixels."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import parity
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def srf():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import lasr_b200.soft_renderer as sr
+    return sr.functional
+
+
+def run_ours(srf, c, near_far_tensors=False):
+    dev = torch.device("cuda", 0)
+    fv = torch.from_numpy(c["face_vertices"]).to(dev).requires_grad_(True)
+    tex = torch.from_numpy(c["textures"]).to(dev).requires_grad_(True)
+    s = dict(c["settings"])
+    if near_far_tensors:
+        s["near"] = torch.tensor(s["near"], device=dev)
+        s["far"] = torch.tensor(s["far"], device=dev)
+    img = srf.soft_rasterize(fv, tex, **s)
+    img.backward(torch.from_numpy(c["grad_soft_colors"]).to(dev))
+    torch.cuda.synchronize()
+    return img.detach().cpu().numpy(), fv.grad.cpu().numpy(), tex.grad.cpu().numpy()
+
+
+def run_oracle(oracle, c):
+    oracle.set_contract(True)
+    r = oracle.soft_rasterize_forward(c["face_vertices"], c["textures"], c["settings"], np.float32)
+    gf, gt = oracle.soft_rasterize_backward(r, c["grad_soft_colors"])
+    return r["soft_colors"], gf.reshape(c["face_vertices"].shape), gt.reshape(c["textures"].shape)
+
+
+def assert_parity(tag, ours, ref):
+    ir = parity.image_report(ours[0], ref[0], rel=1e-4)
+    assert ir["n_bad"] == 0, (tag, ir)
+    gfr = parity.grad_report(ours[1], ref[1])
+    gtr = parity.grad_report(ours[2], ref[2])
+    if gfr["scale"] > 1e-20:
+        assert gfr["rel_l2"] < 1e-3 and gfr["max_over_scale"] < 1e-3, (tag, gfr)
+    if gtr["scale"] > 1e-20:
+        assert gtr["rel_l2"] < 1e-3 and gtr["max_over_scale"] < 1e-3, (tag, gtr)
+
+
+@pytest.mark.parametrize("name", sorted(cases.GOLDEN_CASES))
+def test_matches_reference_golden(srf, name):
+    path = os.path.join(GOLD, f"softras_ref_{name}.npz")
+    assert os.path.exists(path), "golden vectors missing"
+    g = np.load(path)
+    ours = run_ours(srf, cases.GOLDEN_CASES[name]())
+    assert_parity(name, ours, (g["soft_colors"], g["grad_faces"], g["grad_textures"]))
+
+
+@pytest.mark.parametrize("name", sorted(cases.GOLDEN_CASES) + sorted(cases.LIVE_CASES))
+def test_matches_oracle(srf, oracle, name):
+    c = (cases.GOLDEN_CASES.get(name) or cases.LIVE_CASES[name])()
+    assert_parity(name, run_ours(srf, c), run_oracle(oracle, c))
+
+
+def _edge_cases():
+    out = {}
+    out["odd_size_s50"] = cases.lasr_case("bumpy2", 2, 50)              # S not a multiple of the tile
+    out["tiny_s8"] = cases.lasr_case("ico1", 1, 8)
+    out["many_faces_one_tile"] = cases.lasr_case("ico3", 1, 16)          # 1280 faces in one 16x16 tile
+    c = cases.lasr_case("ico4", 1, 32)                                   # 5120 faces, > one scan chunk per tile
+    out["5k_faces_s32"] = c
+    c = cases.lasr_case("ico1", 2, 64)
+    c["face_vertices"][:, :, :, 0] += 5.0                                # everything off screen
+    out["all_offscreen"] = c
+    c = cases.lasr_case("ico1", 1, 64)
+    big = np.array([[[-3.0, -3.0, 9.5], [3.0, -3.0, 9.6], [0.0, 3.0, 9.7]]], dtype=np.float32)
+    c["face_vertices"] = np.concatenate([c["face_vertices"], big[None]], 1)   # one face covering the screen
+    c["textures"] = np.concatenate([c["textures"], c["textures"][:, :1]], 1)
+    out["huge_face"] = c
+    c = cases.lasr_case("ico2", 1, 64)
+    c["face_vertices"][0, 5, 1] = c["face_vertices"][0, 5, 0]           # zero-area face (duplicate vertex)
+    c["face_vertices"][0, 9, :, :2] = c["face_vertices"][0, 9, 0, :2]   # all three vertices coincide in 2-D
+    out["degenerate_faces"] = c
+    c = cases.lasr_case("bumpy2", 1, 64)
+    c["settings"]["near"], c["settings"]["far"] = 9.9, 10.1              # depth window cuts the object
+    out["near_far_clip"] = c
+    out["single_face"] = dict(cases.lasr_case("ico0", 1, 32))
+    out["single_face"]["face_vertices"] = out["single_face"]["face_vertices"][:, :1].copy()
+    out["single_face"]["textures"] = out["single_face"]["textures"][:, :1].copy()
+    return out
+
+
+EDGE = _edge_cases()
+
+
+@pytest.mark.parametrize("name", sorted(EDGE))
+def test_edge_cases_match_oracle(srf, oracle, name):
+    assert_parity(name, run_ours(srf, EDGE[name]), run_oracle(oracle, EDGE[name]))
+
+
+def test_near_far_as_device_tensors(srf):
+    c = cases.lasr_case("bumpy2", 2, 64)
+    a = run_ours(srf, c)
+    b = run_ours(srf, c, near_far_tensors=True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_backward_is_deterministic(srf):
+    c = cases.lasr_case("spot", 2, 128)
+    a, b = run_ours(srf, c), run_ours(srf, c)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_full_size_properties(srf):
+    """BASELINE.json configs[1] shape (Spot, 256x256), N=8: properties that need no oracle."""
+    c = cases.lasr_case("spot", 8, 256)
+    img, gf, gt = run_ours(srf, c)
+    assert np.isfinite(img).all() and np.isfinite(gf).all() and np.isfinite(gt).all()
+    a = img[:, 3]
+    assert a.min() >= 0.0 and a.max() <= 1.0
+    assert 0.15 < (a > 0.5).mean() < 0.5                      # the object covers a sensible part of the image
+    bg = a == 0.0                                              # untouched pixels keep the background exactly
+    assert bg.any() and np.all(img[:, :3].transpose(1, 0, 2, 3)[:, bg] == 0.0)
+    # frames are independent: a permuted batch renders the same frames bit for bit
+    perm = np.array([3, 0, 7, 1, 6, 2, 5, 4])
+    cp = dict(c, face_vertices=c["face_vertices"][perm], textures=c["textures"][perm],
+              grad_soft_colors=c["grad_soft_colors"][perm])
+    img2, gf2, gt2 = run_ours(srf, cp)
+    assert np.array_equal(img2, img[perm]) and np.array_equal(gf2, gf[perm]) and np.array_equal(gt2, gt[perm])
+    # backward is linear in the upstream gradient
+    c2 = dict(c, grad_soft_colors=(2.5 * c["grad_soft_colors"]).astype(np.float32))
+    _, gf3, gt3 = run_ours(srf, c2)
+    assert np.allclose(gf3, 2.5 * gf, rtol=1e-4, atol=1e-6 * np.abs(gf).max())
+    assert np.allclose(gt3, 2.5 * gt, rtol=1e-4, atol=1e-6 * np.abs(gt).max())
+    c0 = dict(c, grad_soft_colors=np.zeros_like(c["grad_soft_colors"]))
+    _, gf0, gt0 = run_ours(srf, c0)
+    assert not gf0.any() and not gt0.any()
+    # texture gradient of a constant upstream colour gradient sums to the softmax mass it came from
+    assert np.abs(gt).max() > 0 and np.abs(gf).max() > 0
+
+
+def test_texture_gradient_matches_finite_differences_of_own_forward(srf):
+    """The image is linear in the vertex colours: the texture gradient equals central differences of
+    our own forward (the vertex gradient of SoftRas is approximate by design, see test_oracle_golden)."""
+    dev = torch.device("cuda", 0)
+    c = cases.lasr_case("bumpy2", 1, 64, sigma=1e-3)
+    s = c["settings"]
+    fv = torch.from_numpy(c["face_vertices"]).to(dev)
+    tex0 = torch.from_numpy(c["textures"]).to(dev)
+    G = torch.randn(1, 4, 64, 64, device=dev, generator=torch.Generator(dev).manual_seed(0))
+    tex = tex0.clone().requires_grad_(True)
+    (srf.soft_rasterize(fv, tex, **s) * G).sum().backward()
+    gen = torch.Generator(dev).manual_seed(1)
+    for _ in range(3):
+        d = torch.randn(tex0.shape, device=dev, generator=gen)
+        fd = ((srf.soft_rasterize(fv, tex0 + 0.25 * d, **s).double() * G).sum()
+              - (srf.soft_rasterize(fv, tex0 - 0.25 * d, **s).double() * G).sum()) / 0.5
+        an = (tex.grad.double() * d).sum()
+        assert abs(fd - an) <= 2e-4 * max(abs(float(an)), 1.0), (float(fd), float(an))
+
+
+def test_module_api_render_mesh(srf, oracle):
+    """SoftRenderer.render_mesh with LASR's settings == oracle on the gathered, transformed mesh."""
+    import lasr_b200.soft_renderer as sr
+    from lasr_b200 import synth
+    dev = torch.device("cuda", 0)
+    v, f = synth.bumpy_sphere(2, 0.5)
+    N, S = 2, 64
+    px, cam, near, far = synth.render_inputs(v, f, N)
+    px[:, :, 1] *= -1                       # undo synth's flip: LASR flips inside render_flow_soft_2
+    colors = np.repeat(synth.vertex_colors(len(v))[None], N, 0)
+    r = sr.SoftRenderer(image_size=S, sigma_val=1e-4, gamma_val=1e-2, camera_mode="look_at", perspective=False,
+                        aggr_func_rgb="softmax", light_mode="vertex", light_intensity_ambient=1.0,
+                        light_intensity_directionals=0.0)
+    r.rasterizer.near, r.rasterizer.far = near, far
+    r.rasterizer.background_color = [1, 1, 1]
+    eye = torch.tensor(r.transform.transformer._eye, device=dev)
+    verts = torch.from_numpy(px).to(dev)
+    pre = verts + eye[None, None]
+    pre = torch.cat([pre[:, :, :1], -pre[:, :, 1:2], pre[:, :, 2:]], -1)      # mesh_net.py:82
+    faces = torch.from_numpy(np.repeat(f[None], N, 0)).to(dev)
+    img = r.render_mesh(sr.Mesh(pre, faces, textures=torch.from_numpy(colors).to(dev), texture_type="vertex"))
+    v_ref = oracle.lasr_render_vertices(px)
+    fv = oracle.face_vertices(v_ref, np.repeat(f[None], N, 0))
+    tx = oracle.face_vertices(colors, np.repeat(f[None], N, 0))
+    st = oracle.RasterSettings.lasr_training(S, near, far, 1e-4, (1, 1, 1))
+    ref = oracle.soft_rasterize_forward(fv, tx, st, np.float32)
+    ir = parity.image_report(img.cpu().numpy(), ref["soft_colors"], rel=1e-4)
+    # the +eye / -eye round trip perturbs z by ~1e-6: allow a handful of flips
+    assert ir["frac_bad"] < 1e-3, ir
