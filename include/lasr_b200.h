@@ -85,6 +85,41 @@ int lasr_b200_raster_backward(const float* faces, const float* textures, const f
                               int func_id_alpha, int texture_sample_type, int double_side,
                               void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused linear-blend skinning + body transform + pinhole projection + batch depth window
+ * (SURVEY 8a rows G1, G2, G3).  Replaces, for CUDA tensors,
+ *   obj_to_cam   nnutils/geom_utils.py:45-71     cam = (sum_k w_k (v R_k + T_k)) R_0 + T_0
+ *   pinhole_cam  nnutils/geom_utils.py:27-34     x,y <- pp + xy * f / z
+ *   near/far     nnutils/mesh_net.py:304-311     near = dmin-(dmax-dmin)/2, far = dmax+(dmax-dmin)/2
+ *
+ *   verts [Nv,V,3]  Nv = N, or 1 with verts_shared=1 (one mesh for every frame)
+ *   Rmat  [N*B,3,3], Tmat [N*B,3]      bone 0 of each frame is the body-to-camera transform
+ *   skin  [Ns,B-1,V] Ns = N, or 1 with skin_shared=1; NULL when B == 1
+ *   pp [N,2], fl [N] per-frame principal point / focal length; both NULL = no projection
+ *   cam [N,V,3] out (skinned only when tocam == 0);  px [N,V,4] out = (x, y, z, 1)
+ *   near_far_dev [2] out, optional: depth window of the whole batch, left on the device
+ * ------------------------------------------------------------------------------------------- */
+size_t lasr_b200_lbs_workspace_bytes(int num_frames, int num_vertices, int num_bones);
+
+int lasr_b200_lbs_project_forward(const float* verts, const float* Rmat, const float* Tmat,
+                                  const float* skin, const float* pp, const float* fl, float* cam,
+                                  float* px, float* near_far_dev, void* workspace,
+                                  size_t workspace_bytes, int num_frames, int num_vertices,
+                                  int num_bones, int verts_shared, int skin_shared, int tocam,
+                                  void* stream);
+
+/* Gradients of the above.  grad_cam [N,V,3] and/or grad_px [N,V,4] in (either may be NULL);
+ * grad_verts [N,V,3] and grad_skin [N,B-1,V] are written PER FRAME (callers sum over frames for a
+ * shared mesh / shared weights); grad_R [N*B,3,3], grad_T [N*B,3], grad_pp [N,2], grad_fl [N].
+ * Deterministic (fixed-order block reductions, no float atomics). */
+int lasr_b200_lbs_project_backward(const float* verts, const float* Rmat, const float* Tmat,
+                                   const float* skin, const float* pp, const float* fl,
+                                   const float* grad_cam, const float* grad_px, float* grad_verts,
+                                   float* grad_R, float* grad_T, float* grad_skin, float* grad_pp,
+                                   float* grad_fl, void* workspace, size_t workspace_bytes,
+                                   int num_frames, int num_vertices, int num_bones,
+                                   int verts_shared, int skin_shared, int tocam, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,12 @@ def lib():
         L.lasr_b200_raster_forward.argtypes = [_c.c_void_p] * 5 + [_c.c_size_t] + _RASTER_SCALARS
         L.lasr_b200_raster_backward.restype = _c.c_int
         L.lasr_b200_raster_backward.argtypes = [_c.c_void_p] * 8 + [_c.c_size_t] + _RASTER_SCALARS
+        L.lasr_b200_lbs_workspace_bytes.restype = _c.c_size_t
+        L.lasr_b200_lbs_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
+        L.lasr_b200_lbs_project_forward.restype = _c.c_int
+        L.lasr_b200_lbs_project_forward.argtypes = [_c.c_void_p] * 10 + [_c.c_size_t] + [_c.c_int] * 6 + [_c.c_void_p]
+        L.lasr_b200_lbs_project_backward.restype = _c.c_int
+        L.lasr_b200_lbs_project_backward.argtypes = [_c.c_void_p] * 15 + [_c.c_size_t] + [_c.c_int] * 6 + [_c.c_void_p]
         _lib = L
     return _lib
 
@@ -52,6 +58,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "lasr_b200_abi_version", "lasr_b200_last_error", "lasr_b200_launch_count",
     "lasr_b200_raster_workspace_bytes", "lasr_b200_raster_forward", "lasr_b200_raster_backward",
+    "lasr_b200_lbs_workspace_bytes", "lasr_b200_lbs_project_forward", "lasr_b200_lbs_project_backward",
 ]
 
 
@@ -123,3 +130,41 @@ def raster_backward(faces, textures, soft_colors, aggrs_info, grad_faces, grad_t
             int(func_id_dist), float(dist_eps), float(gamma_val), int(func_id_rgb), int(func_id_alpha),
             int(texture_sample_type), int(bool(double_side)), _stream_ptr())
     _check(rc, "lasr_b200_raster_backward")
+
+
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+def lbs_workspace(N: int, V: int, B: int, device) -> torch.Tensor:
+    return torch.empty(int(lib().lasr_b200_lbs_workspace_bytes(N, V, B)), dtype=torch.uint8, device=device)
+
+
+def lbs_project_forward(verts, Rmat, Tmat, skin, pp, fl, cam, px, near_far, workspace, N, V, B, verts_shared,
+                        skin_shared, tocam):
+    for t, nm in ((verts, "verts"), (Rmat, "Rmat"), (Tmat, "Tmat"), (cam, "cam")):
+        _require_cuda_f32(t, nm)
+    for t, nm in ((skin, "skin"), (pp, "pp"), (fl, "fl"), (px, "px"), (near_far, "near_far")):
+        if t is not None:
+            _require_cuda_f32(t, nm)
+    with torch.cuda.device(verts.device):
+        rc = lib().lasr_b200_lbs_project_forward(_p(verts), _p(Rmat), _p(Tmat), _p(skin), _p(pp), _p(fl), _p(cam),
+                                                 _p(px), _p(near_far), _p(workspace), workspace.numel(), N, V, B,
+                                                 int(verts_shared), int(skin_shared), int(tocam), _stream_ptr())
+    _check(rc, "lasr_b200_lbs_project_forward")
+
+
+def lbs_project_backward(verts, Rmat, Tmat, skin, pp, fl, grad_cam, grad_px, grad_verts, grad_R, grad_T, grad_skin,
+                         grad_pp, grad_fl, workspace, N, V, B, verts_shared, skin_shared, tocam):
+    for t in (verts, Rmat, Tmat, grad_verts, grad_R, grad_T):
+        _require_cuda_f32(t, "lbs tensor")
+    for t in (skin, pp, fl, grad_cam, grad_px, grad_skin, grad_pp, grad_fl):
+        if t is not None:
+            _require_cuda_f32(t, "lbs tensor")
+    with torch.cuda.device(verts.device):
+        rc = lib().lasr_b200_lbs_project_backward(_p(verts), _p(Rmat), _p(Tmat), _p(skin), _p(pp), _p(fl),
+                                                  _p(grad_cam), _p(grad_px), _p(grad_verts), _p(grad_R), _p(grad_T),
+                                                  _p(grad_skin), _p(grad_pp), _p(grad_fl), _p(workspace),
+                                                  workspace.numel(), N, V, B, int(verts_shared), int(skin_shared),
+                                                  int(tocam), _stream_ptr())
+    _check(rc, "lasr_b200_lbs_project_backward")

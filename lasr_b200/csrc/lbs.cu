@@ -1,0 +1,370 @@
+// lbs.cu -- fused linear-blend skinning + rigid body transform + pinhole projection + batch depth
+// window, forward and backward, for sm_100a.
+//
+// Replaces, on CUDA tensors, the reference's dense PyTorch glue
+//   obj_to_cam   nnutils/geom_utils.py:45-71   (B-1 batched matmuls + cat + weighted sum; the
+//                                               [N,B-1,V,3] intermediate is 25x the output)
+//   pinhole_cam  nnutils/geom_utils.py:27-34   (6 clones + 2 in-place slice assigns)
+//   near/far     nnutils/mesh_net.py:304-311   (2 reductions + a device->host sync at the pybind call)
+// with one pass over the vertices: every thread owns one (frame, vertex), the frame's bone
+// transforms sit in shared memory, skinning weights are read coalesced ([B-1, V] rows), and the
+// posed vertex never leaves registers between skinning, the body transform and the projection.
+// Row-vector convention of the reference:  p_k = v R_k + T_k,  vs = sum_k w_k p_k,
+// cam = vs R_0 + T_0,  px = (pp_x + cam_x f / cam_z, pp_y + cam_y f / cam_z, cam_z, 1).
+//
+// Backward is deterministic: per-vertex gradients are written per frame; the per-bone (R, T) and
+// per-frame (pp, f) gradients are block-reduced with fixed-order shuffles into a partials buffer
+// and summed by a second tiny kernel (no float atomics).
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+#include <string>
+
+#include "host_common.h"
+#include "lasr_b200.h"
+
+namespace lasr {
+
+constexpr int kLbsThreads = 256;
+
+struct LbsArgs {
+  const float* verts;   // [Nv, V, 3]   Nv = N or 1 (shared mesh)
+  const float* Rmat;    // [N, B, 3, 3]
+  const float* Tmat;    // [N, B, 3]
+  const float* skin;    // [Ns, B-1, V] Ns = N or 1 (shared weights); may be null when B == 1
+  const float* pp;      // [N, 2] or null (no projection)
+  const float* fl;      // [N]    or null
+  float* cam;           // [N, V, 3] camera-space (or skinned-only when !tocam)
+  float* px;            // [N, V, 4] projected (x, y, z, 1); null when no projection
+  unsigned* zminmax;    // [2] order-preserving encodings of min / max z (null: skip)
+  int N, V, B;
+  int verts_shared, skin_shared, tocam;
+};
+
+// order-preserving float <-> uint encoding for atomicMin/atomicMax
+__device__ __forceinline__ unsigned enc(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void lbs_init_minmax_kernel(unsigned* zminmax) {
+  zminmax[0] = 0xffffffffu;  // min slot starts at +max
+  zminmax[1] = 0u;           // max slot starts at -max
+}
+
+// near = dmin - (dmax - dmin)/2, far = dmax + (dmax - dmin)/2   (mesh_net.py:304-307)
+__global__ void lbs_depth_window_kernel(const unsigned* zminmax, float* near_far) {
+  const float dmin = dec(zminmax[0]), dmax = dec(zminmax[1]);
+  const float half = (dmax - dmin) / 2.f;
+  near_far[0] = dmin - half;
+  near_far[1] = dmax + half;
+}
+
+__global__ void __launch_bounds__(kLbsThreads) lbs_forward_kernel(LbsArgs A) {
+  extern __shared__ float s_rt[];  // [B][12]: R (9, row-major) then T (3)
+  const int n = blockIdx.y;
+  const int v = blockIdx.x * kLbsThreads + threadIdx.x;
+  for (int i = threadIdx.x; i < A.B * 12; i += kLbsThreads) {
+    const int k = i / 12, j = i % 12;
+    s_rt[i] = j < 9 ? A.Rmat[((long long)n * A.B + k) * 9 + j] : A.Tmat[((long long)n * A.B + k) * 3 + (j - 9)];
+  }
+  __syncthreads();
+  float z = 0.f;
+  const bool active = v < A.V;
+  if (active) {
+    const float* vp = A.verts + ((long long)(A.verts_shared ? 0 : n) * A.V + v) * 3;
+    const float x0 = vp[0], y0 = vp[1], z0 = vp[2];
+    float sx = x0, sy = y0, sz = z0;
+    if (A.B > 1) {
+      sx = sy = sz = 0.f;
+      const float* sk = A.skin + (long long)(A.skin_shared ? 0 : n) * (A.B - 1) * A.V + v;
+      for (int k = 1; k < A.B; ++k) {
+        const float* r = s_rt + k * 12;
+        const float w = sk[(long long)(k - 1) * A.V];
+        const float px_ = x0 * r[0] + y0 * r[3] + z0 * r[6] + r[9];
+        const float py_ = x0 * r[1] + y0 * r[4] + z0 * r[7] + r[10];
+        const float pz_ = x0 * r[2] + y0 * r[5] + z0 * r[8] + r[11];
+        sx += w * px_; sy += w * py_; sz += w * pz_;
+      }
+    }
+    float cx = sx, cy = sy, cz = sz;
+    if (A.tocam) {
+      const float* r = s_rt;
+      cx = sx * r[0] + sy * r[3] + sz * r[6] + r[9];
+      cy = sx * r[1] + sy * r[4] + sz * r[7] + r[10];
+      cz = sx * r[2] + sy * r[5] + sz * r[8] + r[11];
+    }
+    float* co = A.cam + ((long long)n * A.V + v) * 3;
+    co[0] = cx; co[1] = cy; co[2] = cz;
+    z = cz;
+    if (A.px) {
+      const float f = A.fl[n];
+      const float fz = f / cz;
+      reinterpret_cast<float4*>(A.px)[(long long)n * A.V + v] =
+          make_float4(A.pp[2 * n] + cx * fz, A.pp[2 * n + 1] + cy * fz, cz, 1.f);
+    }
+  }
+  if (A.zminmax) {
+    float zmin = active ? z : FLT_MAX, zmax = active ? z : -FLT_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
+      zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(A.zminmax, enc(zmin));      // exact: min/max are order independent
+      atomicMax(A.zminmax + 1, enc(zmax));
+    }
+  }
+}
+
+struct LbsBwdArgs {
+  LbsArgs f;
+  const float* grad_cam;  // [N,V,3] or null
+  const float* grad_px;   // [N,V,4] or null
+  float* grad_verts;      // [N,V,3]  (per frame; the caller sums frames for a shared mesh)
+  float* grad_skin;       // [N,B-1,V] (per frame) or null
+  float* partial;         // [N][nblk][B*12 + 3]  block partials of (R,T) per bone and (pp_x, pp_y, f)
+  int nblk;
+};
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-reduce K values per thread into out[0..K) in a fixed order: warp butterflies, then thread j
+// adds the 8 warp sums of value j in warp order.  Must be called by every thread of the block.
+template <int K>
+__device__ __forceinline__ void block_sum_store(const float (&val)[K], float* s_warp, float* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();   // s_warp may still be read by the previous call
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const float w = warp_sum_f(val[j]);
+    if (lane == 0) s_warp[warp * 12 + j] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLbsThreads / 32; ++i) t += s_warp[i * 12 + threadIdx.x];
+    out[threadIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kLbsThreads) lbs_backward_kernel(LbsBwdArgs G) {
+  extern __shared__ float s_rt[];  // [B][12]
+  __shared__ float s_warp[(kLbsThreads / 32) * 12];
+  const LbsArgs& A = G.f;
+  const int n = blockIdx.y;
+  const int v = blockIdx.x * kLbsThreads + threadIdx.x;
+  for (int i = threadIdx.x; i < A.B * 12; i += kLbsThreads) {
+    const int k = i / 12, j = i % 12;
+    s_rt[i] = j < 9 ? A.Rmat[((long long)n * A.B + k) * 9 + j] : A.Tmat[((long long)n * A.B + k) * 3 + (j - 9)];
+  }
+  __syncthreads();
+  const bool active = v < A.V;
+  float x0 = 0.f, y0 = 0.f, z0 = 0.f;
+  float sx = 0.f, sy = 0.f, sz = 0.f;        // skinned (pre-body) position
+  float gcx = 0.f, gcy = 0.f, gcz = 0.f;     // gradient w.r.t. the camera-space position
+  float gppx = 0.f, gppy = 0.f, gfl = 0.f;
+  const float* sk = nullptr;
+  if (active) {
+    const float* vp = A.verts + ((long long)(A.verts_shared ? 0 : n) * A.V + v) * 3;
+    x0 = vp[0]; y0 = vp[1]; z0 = vp[2];
+    sx = x0; sy = y0; sz = z0;
+    if (A.B > 1) {
+      sx = sy = sz = 0.f;
+      sk = A.skin + (long long)(A.skin_shared ? 0 : n) * (A.B - 1) * A.V + v;
+      for (int k = 1; k < A.B; ++k) {
+        const float* r = s_rt + k * 12;
+        const float w = sk[(long long)(k - 1) * A.V];
+        sx += w * (x0 * r[0] + y0 * r[3] + z0 * r[6] + r[9]);
+        sy += w * (x0 * r[1] + y0 * r[4] + z0 * r[7] + r[10]);
+        sz += w * (x0 * r[2] + y0 * r[5] + z0 * r[8] + r[11]);
+      }
+    }
+    if (G.grad_cam) {
+      const float* g = G.grad_cam + ((long long)n * A.V + v) * 3;
+      gcx = g[0]; gcy = g[1]; gcz = g[2];
+    }
+    if (G.grad_px) {
+      const float* r = s_rt;
+      float cx = sx, cy = sy, cz = sz;
+      if (A.tocam) {
+        cx = sx * r[0] + sy * r[3] + sz * r[6] + r[9];
+        cy = sx * r[1] + sy * r[4] + sz * r[7] + r[10];
+        cz = sx * r[2] + sy * r[5] + sz * r[8] + r[11];
+      }
+      const float4 g = reinterpret_cast<const float4*>(G.grad_px)[(long long)n * A.V + v];
+      const float f = A.fl[n];
+      const float iz = 1.f / cz;
+      const float s = (g.x * cx + g.y * cy) * iz;   // (g_x X + g_y Y) / Z
+      gcx += g.x * f * iz;
+      gcy += g.y * f * iz;
+      gcz += g.z - s * f * iz;
+      gfl = s;
+      gppx = g.x; gppy = g.y;
+    }
+  }
+  float* part = G.partial + ((long long)n * G.nblk + blockIdx.x) * (A.B * 12 + 3);
+  // body transform: cam = vs R0 + T0
+  float gsx = gcx, gsy = gcy, gsz = gcz;
+  if (A.tocam) {
+    const float* r = s_rt;
+    gsx = gcx * r[0] + gcy * r[1] + gcz * r[2];   // g_vs = g_cam R0^T
+    gsy = gcx * r[3] + gcy * r[4] + gcz * r[5];
+    gsz = gcx * r[6] + gcy * r[7] + gcz * r[8];
+    const float vs[3] = {sx, sy, sz}, gc[3] = {gcx, gcy, gcz};
+    float acc[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) acc[3 * i + j] = active ? vs[i] * gc[j] : 0.f;   // g_R0 = vs^T g_cam
+#pragma unroll
+    for (int j = 0; j < 3; ++j) acc[9 + j] = active ? gc[j] : 0.f;                  // g_T0
+    block_sum_store(acc, s_warp, part);
+  } else if (threadIdx.x < 12) {
+    part[threadIdx.x] = 0.f;
+  }
+  float gvx = gsx, gvy = gsy, gvz = gsz;   // B == 1: vs = v
+  if (A.B > 1) {
+    gvx = gvy = gvz = 0.f;
+    for (int k = 1; k < A.B; ++k) {
+      const float* r = s_rt + k * 12;
+      float w = 0.f, gw = 0.f;
+      if (active) {
+        w = sk[(long long)(k - 1) * A.V];
+        const float pxk = x0 * r[0] + y0 * r[3] + z0 * r[6] + r[9];
+        const float pyk = x0 * r[1] + y0 * r[4] + z0 * r[7] + r[10];
+        const float pzk = x0 * r[2] + y0 * r[5] + z0 * r[8] + r[11];
+        gw = pxk * gsx + pyk * gsy + pzk * gsz;
+        if (G.grad_skin) G.grad_skin[((long long)n * (A.B - 1) + (k - 1)) * A.V + v] = gw;
+      }
+      const float gp[3] = {w * gsx, w * gsy, w * gsz};   // g_p_k
+      gvx += gp[0] * r[0] + gp[1] * r[1] + gp[2] * r[2];  // g_v += g_p_k R_k^T
+      gvy += gp[0] * r[3] + gp[1] * r[4] + gp[2] * r[5];
+      gvz += gp[0] * r[6] + gp[1] * r[7] + gp[2] * r[8];
+      const float vv[3] = {x0, y0, z0};
+      float acc[12];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[3 * i + j] = vv[i] * gp[j];   // g_R_k = v^T g_p_k  (gp is 0 when inactive)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) acc[9 + j] = gp[j];                   // g_T_k
+      block_sum_store(acc, s_warp, part + k * 12);
+    }
+  }
+  {
+    const float acc[3] = {gppx, gppy, gfl};
+    block_sum_store(acc, s_warp, part + A.B * 12);
+  }
+  if (active) {
+    float* go = G.grad_verts + ((long long)n * A.V + v) * 3;
+    go[0] = gvx; go[1] = gvy; go[2] = gvz;
+  }
+}
+
+// sum the block partials in block order -> grad_R [N,B,9], grad_T [N,B,3], grad_pp [N,2], grad_fl [N]
+__global__ void lbs_reduce_partials_kernel(const float* partial, int nblk, int N, int B, float* grad_R, float* grad_T,
+                                           float* grad_pp, float* grad_fl) {
+  const int per = B * 12 + 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * per) return;
+  const int n = (int)(i / per), j = (int)(i % per);
+  float t = 0.f;
+  for (int b = 0; b < nblk; ++b) t += partial[((long long)n * nblk + b) * per + j];
+  if (j < B * 12) {
+    const int k = j / 12, e = j % 12;
+    if (e < 9) grad_R[((long long)n * B + k) * 9 + e] = t;
+    else grad_T[((long long)n * B + k) * 3 + (e - 9)] = t;
+  } else if (j - B * 12 < 2) {
+    if (grad_pp) grad_pp[2 * n + (j - B * 12)] = t;
+  } else if (grad_fl) {
+    grad_fl[n] = t;
+  }
+}
+
+static int fill_lbs(LbsArgs& A, const float* verts, const float* Rmat, const float* Tmat, const float* skin,
+                    const float* pp, const float* fl, int N, int V, int B, int verts_shared, int skin_shared,
+                    int tocam) {
+  if (N <= 0 || V <= 0 || B <= 0) return lasr_fail("lbs: N, V, B must be positive");
+  if (!verts || !Rmat || !Tmat) return lasr_fail("lbs: null tensor pointer");
+  if (B > 1 && !skin) return lasr_fail("lbs: skin weights required when B > 1");
+  if ((pp == nullptr) != (fl == nullptr)) return lasr_fail("lbs: pp and fl must be given together");
+  if (B * 12 * sizeof(float) > 40000) return lasr_fail("lbs: too many bones for shared memory");
+  A.verts = verts; A.Rmat = Rmat; A.Tmat = Tmat; A.skin = skin; A.pp = pp; A.fl = fl;
+  A.N = N; A.V = V; A.B = B;
+  A.verts_shared = verts_shared; A.skin_shared = skin_shared; A.tocam = tocam;
+  return 0;
+}
+
+}  // namespace lasr
+
+using namespace lasr;
+
+extern "C" size_t lasr_b200_lbs_workspace_bytes(int N, int V, int B) {
+  if (N <= 0 || V <= 0 || B <= 0) return 0;
+  const size_t nblk = (size_t)(V + kLbsThreads - 1) / kLbsThreads;
+  return 256 + (size_t)N * nblk * ((size_t)B * 12 + 3) * sizeof(float);
+}
+
+extern "C" int lasr_b200_lbs_project_forward(const float* verts, const float* Rmat, const float* Tmat,
+                                             const float* skin, const float* pp, const float* fl, float* cam,
+                                             float* px, float* near_far_dev, void* workspace,
+                                             size_t workspace_bytes, int N, int V, int B, int verts_shared,
+                                             int skin_shared, int tocam, void* stream) {
+  LbsArgs A{};
+  if (fill_lbs(A, verts, Rmat, Tmat, skin, pp, fl, N, V, B, verts_shared, skin_shared, tocam)) return 1;
+  if (!cam) return lasr_fail("lbs_project_forward: cam output required");
+  if (pp && !px) return lasr_fail("lbs_project_forward: px output required when projecting");
+  A.cam = cam; A.px = pp ? px : nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (near_far_dev) {
+    if (!workspace || workspace_bytes < 256) return lasr_fail("lbs_project_forward: workspace too small");
+    A.zminmax = reinterpret_cast<unsigned*>(workspace);
+    lbs_init_minmax_kernel<<<1, 1, 0, st>>>(A.zminmax);
+    if (lasr_check_launch("lbs_init_minmax_kernel")) return 1;
+  }
+  dim3 grid((V + kLbsThreads - 1) / kLbsThreads, N);
+  lbs_forward_kernel<<<grid, kLbsThreads, (size_t)B * 12 * sizeof(float), st>>>(A);
+  if (lasr_check_launch("lbs_forward_kernel")) return 1;
+  if (near_far_dev) {
+    lbs_depth_window_kernel<<<1, 1, 0, st>>>(A.zminmax, near_far_dev);
+    if (lasr_check_launch("lbs_depth_window_kernel")) return 1;
+  }
+  return 0;
+}
+
+extern "C" int lasr_b200_lbs_project_backward(const float* verts, const float* Rmat, const float* Tmat,
+                                              const float* skin, const float* pp, const float* fl,
+                                              const float* grad_cam, const float* grad_px, float* grad_verts,
+                                              float* grad_R, float* grad_T, float* grad_skin, float* grad_pp,
+                                              float* grad_fl, void* workspace, size_t workspace_bytes, int N,
+                                              int V, int B, int verts_shared, int skin_shared, int tocam,
+                                              void* stream) {
+  LbsBwdArgs G{};
+  if (fill_lbs(G.f, verts, Rmat, Tmat, skin, pp, fl, N, V, B, verts_shared, skin_shared, tocam)) return 1;
+  if (!grad_verts || !grad_R || !grad_T) return lasr_fail("lbs_project_backward: null gradient output");
+  if (!grad_cam && !grad_px) return lasr_fail("lbs_project_backward: no upstream gradient");
+  if (grad_px && !pp) return lasr_fail("lbs_project_backward: grad_px without a projection");
+  if (!workspace || workspace_bytes < lasr_b200_lbs_workspace_bytes(N, V, B))
+    return lasr_fail("lbs_project_backward: workspace too small");
+  G.grad_cam = grad_cam; G.grad_px = grad_px; G.grad_verts = grad_verts; G.grad_skin = B > 1 ? grad_skin : nullptr;
+  G.nblk = (V + kLbsThreads - 1) / kLbsThreads;
+  G.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(G.nblk, N);
+  lbs_backward_kernel<<<grid, kLbsThreads, (size_t)B * 12 * sizeof(float), st>>>(G);
+  if (lasr_check_launch("lbs_backward_kernel")) return 1;
+  const long long tot = (long long)N * (B * 12 + 3);
+  lbs_reduce_partials_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(G.partial, G.nblk, N, B, grad_R, grad_T,
+                                                                            grad_pp, grad_fl);
+  return lasr_check_launch("lbs_reduce_partials_kernel");
+}

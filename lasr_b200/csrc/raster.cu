@@ -30,6 +30,7 @@
 #include <string>
 
 #include "lasr_b200.h"
+#include "host_common.h"
 #include "raster_common.cuh"
 
 namespace lasr {
@@ -437,21 +438,8 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static std::mutex g_err_mu;
-static std::string g_err;
-static std::atomic<uint64_t> g_launches{0};
-
-static int fail(const std::string& msg) {
-  std::lock_guard<std::mutex> lk(g_err_mu);
-  g_err = msg;
-  return 1;
-}
-static int check_launch(const char* what) {
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(std::string(what) + ": " + cudaGetErrorString(e));
-  return 0;
-}
+static int fail(const std::string& msg) { return lasr_fail(msg); }
+static int check_launch(const char* what) { return lasr_check_launch(what); }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -490,17 +478,6 @@ static bool is_fast(const RasterArgs& A) {
 }  // namespace lasr
 
 using namespace lasr;
-
-extern "C" int lasr_b200_abi_version(void) { return 1; }
-
-extern "C" const char* lasr_b200_last_error(void) {
-  static thread_local std::string copy;
-  std::lock_guard<std::mutex> lk(g_err_mu);
-  copy = g_err;
-  return copy.c_str();
-}
-
-extern "C" uint64_t lasr_b200_launch_count(void) { return g_launches.load(); }
 
 extern "C" size_t lasr_b200_raster_workspace_bytes(int N, int F, int S) {
   if (N <= 0 || F <= 0 || S <= 0) return 0;

@@ -77,7 +77,10 @@ template <bool kFast> __device__ __forceinline__ float exp_(float x) { return kF
 __device__ __forceinline__ float div_by_rcp(float num, float den, float rd) {
   const float q0 = __fmul_rn(num, rd);
   const float r = __fmaf_rn(-den, q0, num);
-  return __fmaf_rn(r, rd, q0);
+  const float q1 = __fmaf_rn(r, rd, q0);
+  // foreshortened (edge-on) edges have den == 0 after rounding -> rd = inf, r = NaN; huge rd can
+  // overflow q0.  Those rare cases take the IEEE division so inf/NaN propagate as in the reference.
+  return (fabsf(rd) < 1e30f && fabsf(q0) < 1e30f) ? q1 : __fdiv_rn(num, den);
 }
 
 // Pixel-centre coordinate, (2*i + 1 - S) / S evaluated in double and rounded once (.cu:345-346).

@@ -1,0 +1,114 @@
+"""GPU parity of the fused LBS + projection kernels against the plain
+PyTorch expressions of lasr_b200.geom_utils on CPU tensors -- which tests/test_host_glue.py pins to
+golden vectors minted from the reference's own nnutils/geom_utils.py -- forward and backward."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "geom_ref.npz"))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda", 0)
+
+
+def rand_rot(n, g):
+    from lasr_b200.geom_utils import quaternion_to_rotation_matrix
+    return quaternion_to_rotation_matrix(torch.randn(n, 4, generator=g))
+
+
+def make_inputs(N, V, B, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    verts = torch.randn(N, V, 3, generator=g) * 0.3
+    R = rand_rot(N * B, g)
+    T = torch.randn(N * B, 1, 3, generator=g) * 0.05
+    T.view(N, B, 1, 3)[:, 0, 0, 2] += 10.0
+    skin = torch.softmax(torch.randn(N, max(B - 1, 1), V, 1, generator=g) * 2, dim=1) if B > 1 else None
+    pp = torch.randn(N, 2, generator=g) * 0.1
+    fl = 8 + torch.rand(N, 1, generator=g) * 4
+    return verts, R, T, skin, pp, fl
+
+
+def close(a, b, tol):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return (a - b).abs().max().item() <= tol * max(1.0, b.abs().max().item())
+
+
+def test_golden_vectors_from_reference(dev):
+    from lasr_b200 import geom_utils as gu
+    T = lambda k: torch.from_numpy(GOLD[k]).to(dev)
+    assert close(gu.obj_to_cam(T("lbs_verts"), T("lbs_R"), T("lbs_T"), 5, 1, T("lbs_skin")), torch.from_numpy(GOLD["lbs_out"]), 2e-6)
+    assert close(gu.obj_to_cam(T("lbs_verts"), T("lbs_R"), T("lbs_T"), 5, 1, T("lbs_skin"), tocam=False),
+                 torch.from_numpy(GOLD["lbs_out_notocam"]), 2e-6)
+    assert close(gu.obj_to_cam(T("lbs_verts"), T("lbs_R")[::5].contiguous(), T("lbs_T")[::5].contiguous(), 1, 1, None),
+                 torch.from_numpy(GOLD["rigid_out"]), 2e-6)
+    assert close(gu.pinhole_cam(T("cam_v4"), T("cam_pp"), T("cam_fl")), torch.from_numpy(GOLD["pinhole_out"]), 2e-6)
+
+
+@pytest.mark.parametrize("N,V,B", [(3, 70, 1), (4, 300, 5), (6, 2930, 26)])
+def test_obj_to_cam_and_pinhole_forward_backward(dev, N, V, B):
+    from lasr_b200 import geom_utils as gu
+    verts, R, T, skin, pp, fl = make_inputs(N, V, B)
+    cpu = [t.clone().requires_grad_(True) if t is not None else None for t in (verts, R, T, skin, pp, fl)]
+    gpu = [t.clone().to(dev).requires_grad_(True) if t is not None else None for t in (verts, R, T, skin, pp, fl)]
+    outs = []
+    for v_, R_, T_, s_, pp_, fl_ in (cpu, gpu):
+        cam = gu.obj_to_cam(v_, R_, T_, B, 1, s_)
+        v4 = torch.cat([cam, torch.ones_like(cam[:, :, :1])], -1)
+        px = gu.pinhole_cam(v4, pp_, fl_)
+        outs.append((cam, px))
+    assert close(outs[1][0], outs[0][0], 2e-6) and close(outs[1][1], outs[0][1], 2e-6)
+    g = torch.Generator().manual_seed(9)
+    gc, gp = torch.randn(N, V, 3, generator=g), torch.randn(N, V, 4, generator=g)
+    (outs[0][0] * gc).sum().add((outs[0][1] * gp).sum()).backward()
+    (outs[1][0] * gc.to(dev)).sum().add((outs[1][1] * gp.to(dev)).sum()).backward()
+    for a, b, nm in zip(gpu, cpu, ("verts", "R", "T", "skin", "pp", "fl")):
+        if a is None:
+            continue
+        assert close(a.grad, b.grad, 5e-5), nm
+
+
+def test_fused_skin_project_shared_mesh_and_weights(dev):
+    """LASR's layout: one mean shape and one set of skinning weights for every frame."""
+    from lasr_b200 import geom_utils as gu
+    from lasr_b200 import native_geom
+    N, V, B = 8, 500, 9
+    verts, R, T, skin, pp, fl = make_inputs(N, V, B, seed=3)
+    v1, s1 = verts[:1].clone(), skin[:1].clone()
+    cpu = [t.clone().requires_grad_(True) for t in (v1, R, T, s1, pp, fl)]
+    cam_ref = gu.obj_to_cam(cpu[0].repeat(N, 1, 1), cpu[1], cpu[2], B, 1, cpu[3].repeat(N, 1, 1, 1))
+    px_ref = gu.pinhole_cam(torch.cat([cam_ref, torch.ones_like(cam_ref[:, :, :1])], -1), cpu[4], cpu[5])
+    gpu = [t.clone().to(dev).requires_grad_(True) for t in (v1, R, T, s1, pp, fl)]
+    cam, px, (near, far) = native_geom.skin_project(gpu[0], gpu[1], gpu[2], B, gpu[3], gpu[4], gpu[5].reshape(-1),
+                                                    depth_window=True)
+    assert close(cam, cam_ref, 2e-6) and close(px, px_ref, 2e-6)
+    n_ref, f_ref = gu.depth_window(px_ref[:, :, 2])
+    assert abs(float(near) - float(n_ref)) < 1e-5 and abs(float(far) - float(f_ref)) < 1e-5
+    g = torch.Generator().manual_seed(4)
+    gc, gp = torch.randn(N, V, 3, generator=g), torch.randn(N, V, 4, generator=g)
+    ((cam_ref * gc).sum() + (px_ref * gp).sum()).backward()
+    ((cam * gc.to(dev)).sum() + (px * gp.to(dev)).sum()).backward()
+    for a, b, nm in zip(gpu, cpu, ("verts", "R", "T", "skin", "pp", "fl")):
+        assert close(a.grad, b.grad, 5e-5), nm
+    # deterministic
+    gpu2 = [t.clone().to(dev).requires_grad_(True) for t in (v1, R, T, s1, pp, fl)]
+    cam2, px2, _ = native_geom.skin_project(gpu2[0], gpu2[1], gpu2[2], B, gpu2[3], gpu2[4], gpu2[5].reshape(-1),
+                                            depth_window=True)
+    ((cam2 * gc.to(dev)).sum() + (px2 * gp.to(dev)).sum()).backward()
+    assert all(torch.equal(a.grad, b.grad) for a, b in zip(gpu, gpu2))
+
+
+def test_hypotheses_repeat_of_principal_point(dev):
+    """pinhole_cam's pp is per frame-pair and repeated over hypotheses (geom_utils.py:28-29)."""
+    from lasr_b200 import geom_utils as gu
+    g = torch.Generator().manual_seed(1)
+    verts = torch.cat([torch.randn(6, 40, 2, generator=g), 9 + torch.rand(6, 40, 1, generator=g), torch.ones(6, 40, 1)], -1)
+    pp, fl = torch.randn(3, 2, generator=g) * 0.1, 9 + torch.rand(6, 1, generator=g)
+    assert close(gu.pinhole_cam(verts.to(dev), pp.to(dev), fl.to(dev)), gu.pinhole_cam(verts, pp, fl), 2e-6)
