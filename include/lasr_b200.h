@@ -48,7 +48,8 @@ uint64_t lasr_b200_launch_count(void);
  * ------------------------------------------------------------------------------------------- */
 
 /* Scratch needed by one forward or backward call.  Replaces the reference's `faces_info`
- * [N,F,27] buffer (soft_rasterize.py:47): we keep only a packed per-face pixel window. */
+ * [N,F,27] buffer (soft_rasterize.py:47): per face a packed pixel window (8 B), the dilated border
+ * box (16 B) and a 176-byte record of derived constants, plus an S-entry pixel-coordinate table. */
 size_t lasr_b200_raster_workspace_bytes(int batch_size, int num_faces, int image_size);
 
 /* forward_soft_rasterize(faces, textures, faces_info, aggrs_info, soft_colors, image_size, near,
@@ -84,6 +85,40 @@ int lasr_b200_raster_backward(const float* faces, const float* textures, const f
                               int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
                               int func_id_alpha, int texture_sample_type, int double_side,
                               void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Indexed ("fused") rasterizer: vertices + shared topology + vertex colours in, image out, gradients
+ * back per vertex.  Replaces the gather -> rasterize -> scatter chain of SoftRenderer.render_mesh for
+ * 'vertex' textures (mesh.py:105-109,128-134 `face_vertices` / `face_textures` = vertices[faces],
+ * functional/face_vertices.py:4-22, and their autograd scatter) so that the [N,F,9] gathered
+ * tensors never exist in HBM.
+ *   verts   [N,V,3]  clip-space vertices (what SoftRasterizer receives as mesh.vertices)
+ *   tri     [F,3]    int32 topology shared by the N frames
+ *   vcolors [N,V,3]  vertex colours
+ *   csr_offsets [V+1], csr_entries [3F] (entry = face*3 + corner, grouped by vertex, ascending):
+ *                    vertex -> corner adjacency used to sum per-face gradients in a fixed order
+ *   grad_verts, grad_vcolors [N,V,3] out (overwritten)
+ * Other arguments as lasr_b200_raster_forward/backward (texture_sample_type is 'vertex').
+ * ------------------------------------------------------------------------------------------- */
+size_t lasr_b200_render_workspace_bytes(int batch_size, int num_faces, int image_size);
+
+int lasr_b200_render_forward(const float* verts, const int32_t* tri, const float* vcolors,
+                             float* aggrs_info, float* soft_colors, void* workspace,
+                             size_t workspace_bytes, int batch_size, int num_vertices, int num_faces,
+                             int image_size, float near_, float far_, const float* near_far_dev,
+                             float eps, float sigma_val, int func_id_dist, float dist_eps,
+                             float gamma_val, int func_id_rgb, int func_id_alpha, int double_side,
+                             void* stream);
+
+int lasr_b200_render_backward(const float* verts, const int32_t* tri, const float* vcolors,
+                              const float* soft_colors, const float* aggrs_info,
+                              const float* grad_soft_colors, const int32_t* csr_offsets,
+                              const int32_t* csr_entries, float* grad_verts, float* grad_vcolors,
+                              void* workspace, size_t workspace_bytes, int batch_size,
+                              int num_vertices, int num_faces, int image_size, float near_,
+                              float far_, const float* near_far_dev, float eps, float sigma_val,
+                              int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
+                              int func_id_alpha, int double_side, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused linear-blend skinning + body transform + pinhole projection + batch depth window

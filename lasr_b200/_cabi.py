@@ -45,6 +45,14 @@ def lib():
         L.lasr_b200_raster_forward.argtypes = [_c.c_void_p] * 5 + [_c.c_size_t] + _RASTER_SCALARS
         L.lasr_b200_raster_backward.restype = _c.c_int
         L.lasr_b200_raster_backward.argtypes = [_c.c_void_p] * 8 + [_c.c_size_t] + _RASTER_SCALARS
+        L.lasr_b200_render_workspace_bytes.restype = _c.c_size_t
+        L.lasr_b200_render_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
+        _render_scalars = [_c.c_int] * 4 + [_c.c_float, _c.c_float, _c.c_void_p, _c.c_float, _c.c_float, _c.c_int,
+                                            _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
+        L.lasr_b200_render_forward.restype = _c.c_int
+        L.lasr_b200_render_forward.argtypes = [_c.c_void_p] * 6 + [_c.c_size_t] + _render_scalars
+        L.lasr_b200_render_backward.restype = _c.c_int
+        L.lasr_b200_render_backward.argtypes = [_c.c_void_p] * 11 + [_c.c_size_t] + _render_scalars
         L.lasr_b200_lbs_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_lbs_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_lbs_project_forward.restype = _c.c_int
@@ -58,6 +66,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "lasr_b200_abi_version", "lasr_b200_last_error", "lasr_b200_launch_count",
     "lasr_b200_raster_workspace_bytes", "lasr_b200_raster_forward", "lasr_b200_raster_backward",
+    "lasr_b200_render_workspace_bytes", "lasr_b200_render_forward", "lasr_b200_render_backward",
     "lasr_b200_lbs_workspace_bytes", "lasr_b200_lbs_project_forward", "lasr_b200_lbs_project_backward",
 ]
 
@@ -168,3 +177,46 @@ def lbs_project_backward(verts, Rmat, Tmat, skin, pp, fl, grad_cam, grad_px, gra
                                                   workspace.numel(), N, V, B, int(verts_shared), int(skin_shared),
                                                   int(tocam), _stream_ptr())
     _check(rc, "lasr_b200_lbs_project_backward")
+
+
+def render_workspace(N: int, F: int, S: int, device) -> torch.Tensor:
+    return torch.empty(int(lib().lasr_b200_render_workspace_bytes(N, F, S)), dtype=torch.uint8, device=device)
+
+
+def _render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
+                        func_id_rgb, func_id_alpha, double_side):
+    return (N, V, F, int(S), float(near), float(far), _p(near_far_dev), float(eps), float(sigma_val),
+            int(func_id_dist), float(dist_eps), float(gamma_val), int(func_id_rgb), int(func_id_alpha),
+            int(bool(double_side)), _stream_ptr())
+
+
+def render_forward(verts, tri, vcolors, aggrs_info, soft_colors, workspace, S, near, far, near_far_dev, eps,
+                   sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side):
+    for t, nm in ((verts, "verts"), (vcolors, "vcolors"), (aggrs_info, "aggrs_info"), (soft_colors, "soft_colors")):
+        _require_cuda_f32(t, nm)
+    if tri.dtype != torch.int32 or not tri.is_cuda or not tri.is_contiguous():
+        raise RuntimeError("tri must be a contiguous CUDA int32 tensor [F,3]")
+    N, V = verts.shape[:2]
+    F = tri.shape[0]
+    with torch.cuda.device(verts.device):
+        rc = lib().lasr_b200_render_forward(
+            _p(verts), _p(tri), _p(vcolors), _p(aggrs_info), _p(soft_colors), _p(workspace), workspace.numel(),
+            *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
+                                 gamma_val, func_id_rgb, func_id_alpha, double_side))
+    _check(rc, "lasr_b200_render_forward")
+
+
+def render_backward(verts, tri, vcolors, soft_colors, aggrs_info, grad_soft_colors, csr_offsets, csr_entries,
+                    grad_verts, grad_vcolors, workspace, S, near, far, near_far_dev, eps, sigma_val, func_id_dist,
+                    dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side):
+    for t in (verts, vcolors, soft_colors, aggrs_info, grad_soft_colors, grad_verts, grad_vcolors):
+        _require_cuda_f32(t, "render tensor")
+    N, V = verts.shape[:2]
+    F = tri.shape[0]
+    with torch.cuda.device(verts.device):
+        rc = lib().lasr_b200_render_backward(
+            _p(verts), _p(tri), _p(vcolors), _p(soft_colors), _p(aggrs_info), _p(grad_soft_colors), _p(csr_offsets),
+            _p(csr_entries), _p(grad_verts), _p(grad_vcolors), _p(workspace), workspace.numel(),
+            *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
+                                 gamma_val, func_id_rgb, func_id_alpha, double_side))
+    _check(rc, "lasr_b200_render_backward")

@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RasterArgs A, int wit
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < A.S) A.coords[i] = pixel_coord((int)i, A.S);
   if (i >= (long long)A.N * A.F) return;
-  const float* fv = A.faces + i * 9;
+  const bool vertex_tex = A.sample == 1;
+  float fv[9], tex9[9];
+  fetch_face(A, (int)(i / A.F), (int)(i % A.F), fv, tex9, vertex_tex && with_records);
   const float sthr = sqrtf(A.dist_eps * A.sigma);
   FaceGeom g;
   face_setup(fv, sthr, g);
@@ -64,12 +66,6 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RasterArgs A, int wit
   A.face_window[i] = make_uint2((uint32_t)xlo | ((uint32_t)xhi << 16), (uint32_t)ylo | ((uint32_t)yhi << 16));
   if (!with_records) return;
   A.face_border[i] = make_float4(g.lox, g.hix, g.loy, g.hiy);
-  float tex9[9];
-  const bool vertex_tex = A.sample == 1;
-  if (vertex_tex) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) tex9[k] = A.textures[i * 9 + k];
-  }
   store_record(A.face_record + i * kRecWords, g, vertex_tex ? tex9 : nullptr);
 }
 
@@ -290,15 +286,10 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
   const int alpha_f = kFast ? 2 : A.alpha;
   const int sample = kFast ? 1 : A.sample;
 
-  const float* fv = A.faces + wg * 9;
+  float fv[9], tex9[9];
+  fetch_face(A, n, f, fv, tex9, sample == 1);
   FaceGeom g;
   face_setup(fv, sthr, g);
-  const float* tex = A.textures + wg * A.T * 3;
-  float tex9[9];
-  if (sample == 1) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) tex9[k] = tex[k];
-  }
   float* gtex_out = A.grad_textures + wg * A.T * 3;
 
   int xlo, xhi, ylo, yhi;
@@ -475,6 +466,30 @@ static bool is_fast(const RasterArgs& A) {
   return A.dist == 2 && A.rgb == 1 && A.alpha == 2 && A.sample == 1 && A.double_side != 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// indexed mode: per-face gradients -> per-vertex gradients through the vertex->corner adjacency
+// (CSR, ascending face order => fixed summation order, no atomics)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vertex_gather_kernel(const float* __restrict__ grad_faces,
+                                                            const float* __restrict__ grad_textures,
+                                                            const int* __restrict__ csr_offsets,
+                                                            const int* __restrict__ csr_entries, float* grad_verts,
+                                                            float* grad_vcolors, int N, int V, int F) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * V) return;
+  const int n = (int)(i / V), v = (int)(i % V);
+  const float* gf = grad_faces + (long long)n * F * 9;
+  const float* gt = grad_textures + (long long)n * F * 9;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  for (int e = csr_offsets[v]; e < csr_offsets[v + 1]; ++e) {
+    const int k = csr_entries[e] * 3;   // entry = face*3 + corner -> offset of that corner's 3 floats
+    a0 += gf[k]; a1 += gf[k + 1]; a2 += gf[k + 2];
+    c0 += gt[k]; c1 += gt[k + 1]; c2 += gt[k + 2];
+  }
+  grad_verts[i * 3] = a0; grad_verts[i * 3 + 1] = a1; grad_verts[i * 3 + 2] = a2;
+  grad_vcolors[i * 3] = c0; grad_vcolors[i * 3 + 1] = c1; grad_vcolors[i * 3 + 2] = c2;
+}
+
 }  // namespace lasr
 
 using namespace lasr;
@@ -546,4 +561,89 @@ extern "C" int lasr_b200_raster_backward(const float* faces, const float* textur
   if (is_fast(A)) raster_backward_kernel<true><<<blocks, 256, 0, st>>>(A);
   else raster_backward_kernel<false><<<blocks, 256, 0, st>>>(A);
   return check_launch("raster_backward_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// indexed ("fused") entry points: vertices + shared topology + vertex colours in, image out;
+// gradients come back per vertex.  No [N,F,9] gathered tensors in HBM on either pass.
+// ---------------------------------------------------------------------------------------------
+extern "C" size_t lasr_b200_render_workspace_bytes(int N, int F, int S) {
+  if (N <= 0 || F <= 0 || S <= 0) return 0;
+  return lasr_b200_raster_workspace_bytes(N, F, S) + 2 * align256((size_t)N * F * 9 * sizeof(float));
+}
+
+static int fill_indexed(RasterArgs& A, const float* verts, const int* tri, const float* vcolors, int V) {
+  if (!verts || !tri || !vcolors || V <= 0) return fail("render: null vertex / topology / colour pointer");
+  if (A.sample != 1) return fail("render: the indexed path takes 'vertex' textures");
+  A.verts = verts; A.tri = tri; A.vcolors = vcolors; A.V = V;
+  return 0;
+}
+
+extern "C" int lasr_b200_render_forward(const float* verts, const int32_t* tri, const float* vcolors,
+                                        float* aggrs_info, float* soft_colors, void* workspace,
+                                        size_t workspace_bytes, int N, int V, int F, int S, float near_, float far_,
+                                        const float* near_far_dev, float eps, float sigma_val, int func_id_dist,
+                                        float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
+                                        int double_side, void* stream) {
+  RasterArgs A{};
+  if (workspace_bytes < lasr_b200_render_workspace_bytes(N, F, S)) return fail("render: workspace too small");
+  if (fill_args(A, N, F, S, 3, near_, far_, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
+                func_id_rgb, func_id_alpha, 1, double_side, workspace, workspace_bytes))
+    return 1;
+  if (fill_indexed(A, verts, tri, vcolors, V)) return 1;
+  if (!aggrs_info || !soft_colors) return fail("render_forward: null tensor pointer");
+  A.aggrs_info = aggrs_info; A.soft_colors = soft_colors;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long nf = (long long)N * F;
+  const long long nthreads = nf > S ? nf : S;
+  raster_setup_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(A, 1);
+  if (check_launch("raster_setup_kernel")) return 1;
+  const int tiles = ((S + kTile - 1) / kTile) * ((S + kTile - 1) / kTile);
+  dim3 grid(tiles, N);
+  int chunk = ((F + 255) / 256) * 256;
+  if (chunk > kMaxScanChunk) chunk = kMaxScanChunk;
+  const size_t smem = (size_t)chunk * sizeof(int);
+  if (is_fast(A)) raster_forward_kernel<true><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  else raster_forward_kernel<false><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  return check_launch("raster_forward_kernel");
+}
+
+extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri, const float* vcolors,
+                                         const float* soft_colors, const float* aggrs_info,
+                                         const float* grad_soft_colors, const int32_t* csr_offsets,
+                                         const int32_t* csr_entries, float* grad_verts, float* grad_vcolors,
+                                         void* workspace, size_t workspace_bytes, int N, int V, int F, int S,
+                                         float near_, float far_, const float* near_far_dev, float eps,
+                                         float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
+                                         int func_id_rgb, int func_id_alpha, int double_side, void* stream) {
+  RasterArgs A{};
+  if (workspace_bytes < lasr_b200_render_workspace_bytes(N, F, S)) return fail("render: workspace too small");
+  if (fill_args(A, N, F, S, 3, near_, far_, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
+                func_id_rgb, func_id_alpha, 1, double_side, workspace, workspace_bytes))
+    return 1;
+  if (fill_indexed(A, verts, tri, vcolors, V)) return 1;
+  if (!soft_colors || !aggrs_info || !grad_soft_colors || !csr_offsets || !csr_entries || !grad_verts || !grad_vcolors)
+    return fail("render_backward: null tensor pointer");
+  A.aggrs_info = const_cast<float*>(aggrs_info);
+  A.soft_colors = const_cast<float*>(soft_colors);
+  A.grad_soft_colors = grad_soft_colors;
+  char* scratch = reinterpret_cast<char*>(workspace) + lasr_b200_raster_workspace_bytes(N, F, S);
+  const long long nf = (long long)N * F;
+  A.grad_faces = reinterpret_cast<float*>(scratch);
+  A.grad_textures = reinterpret_cast<float*>(scratch + align256((size_t)nf * 9 * sizeof(float)));
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    RasterArgs B = A;
+    B.N = 1; B.F = 1;
+    raster_setup_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(B, 0);
+    if (check_launch("raster_setup_kernel")) return 1;
+  }
+  const unsigned blocks = (unsigned)((nf + 7) / 8);
+  if (is_fast(A)) raster_backward_kernel<true><<<blocks, 256, 0, st>>>(A);
+  else raster_backward_kernel<false><<<blocks, 256, 0, st>>>(A);
+  if (check_launch("raster_backward_kernel")) return 1;
+  const long long nv = (long long)N * V;
+  vertex_gather_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(A.grad_faces, A.grad_textures, csr_offsets,
+                                                                      csr_entries, grad_verts, grad_vcolors, N, V, F);
+  return check_launch("vertex_gather_kernel");
 }

@@ -40,11 +40,40 @@ struct RasterArgs {
   float* face_record;        // [N*F][kRecWords]
   float* coords;             // [S] pixel-centre coordinates
   const float* near_far_dev; // optional {near, far} on device
+  // indexed ("fused") input mode: faces/textures are gathered on the fly from per-vertex arrays
+  const float* verts;        // [N,V,3] clip-space vertices   (null: direct mode, use `faces`)
+  const float* vcolors;      // [N,V,3] vertex colours
+  const int* tri;            // [F,3] shared topology
+  int V;
   int N, F, S, T, R;
   float near_, far_, eps, sigma, dist_eps, gamma;
   float inv_sigma, inv_gamma;
   int dist, rgb, alpha, sample, double_side;
 };
+
+// Fetch the 9 vertex floats (and, for 'vertex' textures, the 9 corner colours) of face f of frame
+// n, either from the reference's gathered tensors or straight from per-vertex arrays + topology.
+__device__ __forceinline__ void fetch_face(const RasterArgs& A, int n, int f, float* fv, float* tex9, bool want_tex) {
+  if (A.tri) {
+    const int i0 = A.tri[3 * f], i1 = A.tri[3 * f + 1], i2 = A.tri[3 * f + 2];
+    const float* vb = A.verts + (long long)n * A.V * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { fv[k] = vb[3 * i0 + k]; fv[3 + k] = vb[3 * i1 + k]; fv[6 + k] = vb[3 * i2 + k]; }
+    if (want_tex) {
+      const float* cb = A.vcolors + (long long)n * A.V * 3;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { tex9[k] = cb[3 * i0 + k]; tex9[3 + k] = cb[3 * i1 + k]; tex9[6 + k] = cb[3 * i2 + k]; }
+    }
+  } else {
+    const long long i = (long long)n * A.F + f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) fv[k] = A.faces[i * 9 + k];
+    if (want_tex) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) tex9[k] = A.textures[i * 9 + k];
+    }
+  }
+}
 
 // ---- reference-shaped sums of products (rule 1) ----------------------------------------------
 __device__ __forceinline__ float dot2(float a, float b, float c, float d) {

@@ -1,5 +1,6 @@
 from .geometry import (ambient_lighting, directional_lighting, face_vertices, get_points_from_angles, look, look_at,
                        orthogonal, perspective, vertex_normals)
+from .render_indexed import RenderIndexedFunction, render_indexed, shared_topology, vertex_adjacency
 from .soft_rasterize import SoftRasterizeFunction, soft_rasterize
 
 

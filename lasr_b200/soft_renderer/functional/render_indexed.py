@@ -1,0 +1,100 @@
+"""Indexed ("fused") rasterization: ``soft_rasterize(vertices[faces], textures[faces], ...)`` without
+the two gathers and their autograd scatter -- the kernels fetch vertices / colours through the
+topology themselves and hand back per-vertex gradients (lasr_b200_render_forward/backward).
+
+Semantically identical to ``srf.soft_rasterize(srf.face_vertices(v, f), srf.face_vertices(c, f),
+..., texture_type='vertex')`` (mesh.py:105-109,128-134 + functional/soft_rasterize.py) when every
+frame shares one topology, which is how LASR calls it (faces repeated per frame,
+nnutils/mesh_net.py:77,357)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch.autograd import Function
+
+from ... import _cabi
+from .soft_rasterize import ALPHA_FUNCS, DIST_FUNCS, RGB_FUNCS, _near_far
+
+_topology_cache = {}
+
+
+def shared_topology(faces):
+    """[N,F,3] faces -> ([F,3] int32, csr_offsets [V+1]... built lazily) if all frames share one
+    topology, else None.  The (one-off, synchronising) equality check is cached per tensor."""
+    if faces.dim() == 2:
+        return faces.to(torch.int32).contiguous()
+    key = (faces.data_ptr(), faces._version, tuple(faces.shape), faces.dtype, str(faces.device))
+    hit = _topology_cache.get(key)
+    if hit is None:
+        same = bool((faces == faces[:1]).all()) if faces.shape[0] > 1 else True
+        hit = faces[0].to(torch.int32).contiguous() if same else False
+        if len(_topology_cache) > 64:
+            _topology_cache.clear()
+        _topology_cache[key] = hit
+    return hit if hit is not False else None
+
+
+_csr_cache = {}
+
+
+def vertex_adjacency(tri, num_vertices):
+    """vertex -> (face, corner) adjacency as CSR; entries of a vertex are in ascending face order so
+    the gradient sum has a fixed order.  Cached per topology tensor."""
+    key = (tri.data_ptr(), tri._version, tuple(tri.shape), num_vertices)
+    hit = _csr_cache.get(key)
+    if hit is None:
+        flat = tri.reshape(-1).long()
+        order = torch.argsort(flat, stable=True)
+        counts = torch.bincount(flat, minlength=num_vertices)
+        offsets = torch.zeros(num_vertices + 1, dtype=torch.int32, device=tri.device)
+        offsets[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        hit = (offsets.contiguous(), order.to(torch.int32).contiguous())
+        if len(_csr_cache) > 64:
+            _csr_cache.clear()
+        _csr_cache[key] = hit
+    return hit
+
+
+class RenderIndexedFunction(Function):
+
+    @staticmethod
+    def forward(ctx, vertices, vcolors, tri, image_size, background_color, near, far, fill_back, eps, sigma_val,
+                dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha):
+        if not vertices.is_cuda:
+            raise _cabi.CudaTensorRequired("Rasterize module supports only cuda Tensors")
+        dev = vertices.device
+        N, V = vertices.shape[:2]
+        S = int(image_size)
+        v = vertices.detach().float().contiguous()
+        c = vcolors.detach().float().contiguous()
+        ctx.scal = (eps, sigma_val, DIST_FUNCS[dist_func], float(np.log(1.0 / dist_eps - 1.0)), gamma_val,
+                    RGB_FUNCS[aggr_func_rgb], ALPHA_FUNCS[aggr_func_alpha], bool(fill_back))
+        ctx.near, ctx.far, ctx.nf = _near_far(near, far, dev)
+        ctx.S = S
+        aggrs = torch.empty(N, 2, S, S, dtype=torch.float32, device=dev)
+        img = torch.empty(N, 4, S, S, dtype=torch.float32, device=dev)
+        img[:, :3] = torch.as_tensor(background_color, dtype=torch.float32, device=dev).view(1, 3, 1, 1)
+        ws = _cabi.render_workspace(N, tri.shape[0], S, dev)
+        _cabi.render_forward(v, tri, c, aggrs, img, ws, S, ctx.near, ctx.far, ctx.nf, *ctx.scal)
+        ctx.save_for_backward(v, c, tri, img, aggrs)
+        ctx.shapes = (vertices.shape, vcolors.shape)
+        return img
+
+    @staticmethod
+    def backward(ctx, grad):
+        v, c, tri, img, aggrs = ctx.saved_tensors
+        N, V = v.shape[:2]
+        offsets, entries = vertex_adjacency(tri, V)
+        gv, gc = torch.empty_like(v), torch.empty_like(c)
+        ws = _cabi.render_workspace(N, tri.shape[0], ctx.S, v.device)
+        _cabi.render_backward(v, tri, c, img, aggrs, grad.float().contiguous(), offsets, entries, gv, gc, ws, ctx.S,
+                              ctx.near, ctx.far, ctx.nf, *ctx.scal)
+        vshape, cshape = ctx.shapes
+        return (gv.reshape(vshape), gc.reshape(cshape)) + (None,) * 13
+
+
+def render_indexed(vertices, vcolors, tri, image_size=256, background_color=[0, 0, 0], near=1, far=100,
+                   fill_back=True, eps=1e-3, sigma_val=1e-5, dist_func="euclidean", dist_eps=1e-4, gamma_val=1e-4,
+                   aggr_func_rgb="softmax", aggr_func_alpha="prod"):
+    return RenderIndexedFunction.apply(vertices, vcolors, tri, image_size, background_color, near, far, fill_back,
+                                       eps, sigma_val, dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha)

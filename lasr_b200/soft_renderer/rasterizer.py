@@ -37,6 +37,18 @@ class SoftRasterizer(nn.Module):
 
     def forward(self, mesh, mode=None):
         image_size = self.image_size * (2 if self.anti_aliasing else 1)
+        tri = None
+        if self.texture_type == "vertex" and mesh.vertices.is_cuda and not getattr(mesh, "_fill_back", False):
+            tri = srf.shared_topology(mesh.faces)      # one topology for every frame (LASR's call pattern)
+        if tri is not None:
+            # indexed path: no [N,F,9] gathers, per-vertex gradients straight from the kernels
+            images = srf.render_indexed(mesh.vertices, mesh.textures, tri, image_size, self.background_color,
+                                        self.near, self.far, self.fill_back, self.eps, self.sigma_val,
+                                        self.dist_func, self.dist_eps, self.gamma_val, self.aggr_func_rgb,
+                                        self.aggr_func_alpha)
+            if self.anti_aliasing:
+                images = F.avg_pool2d(images, kernel_size=2, stride=2)
+            return images
         images = srf.soft_rasterize(mesh.face_vertices, mesh.face_textures, image_size, self.background_color,
                                     self.near, self.far, self.fill_back, self.eps, self.sigma_val, self.dist_func,
                                     self.dist_eps, self.gamma_val, self.aggr_func_rgb, self.aggr_func_alpha,

@@ -203,3 +203,63 @@ def test_module_api_render_mesh(srf, oracle):
     ir = parity.image_report(img.cpu().numpy(), ref["soft_colors"], rel=1e-4)
     # the +eye / -eye round trip perturbs z by ~1e-6: allow a handful of flips
     assert ir["frac_bad"] < 1e-3, ir
+
+
+def test_indexed_path_equals_gathered_path(srf):
+    """render_indexed(v, c, tri) == soft_rasterize(v[tri], c[tri]) bit for bit forward, and its
+    per-vertex gradients equal autograd's scatter of the per-face gradients."""
+    from lasr_b200 import synth
+    dev = torch.device("cuda", 0)
+    v, f = synth.load_spot()
+    N, S = 3, 128
+    px, cam, near, far = synth.render_inputs(v, f, N)
+    colors = np.repeat(synth.vertex_colors(len(v))[None], N, 0)
+    s = cases._lasr_settings(S, near, far)
+    G = torch.randn(N, 4, S, S, device=dev, generator=torch.Generator(dev).manual_seed(0))
+    tri = torch.from_numpy(f).to(dev)
+    faces = tri[None].repeat(N, 1, 1)
+
+    va = torch.from_numpy(px).to(dev).requires_grad_(True)
+    ca = torch.from_numpy(colors).to(dev).requires_grad_(True)
+    img_a = srf.soft_rasterize(srf.face_vertices(va, faces), srf.face_vertices(ca, faces), **s)
+    (img_a * G).sum().backward()
+
+    vb = torch.from_numpy(px).to(dev).requires_grad_(True)
+    cb = torch.from_numpy(colors).to(dev).requires_grad_(True)
+    kw = {k: s[k] for k in s if k != "texture_type"}
+    img_b = srf.render_indexed(vb, cb, tri, **kw)
+    (img_b * G).sum().backward()
+    assert torch.equal(img_a, img_b)
+    for a, b in ((va.grad, vb.grad), (ca.grad, cb.grad)):
+        scale = a.abs().max().item()
+        assert (a - b).abs().max().item() <= 2e-6 * scale
+    # deterministic
+    vc = torch.from_numpy(px).to(dev).requires_grad_(True)
+    cc = torch.from_numpy(colors).to(dev).requires_grad_(True)
+    (srf.render_indexed(vc, cc, tri, **kw) * G).sum().backward()
+    assert torch.equal(vb.grad, vc.grad) and torch.equal(cb.grad, cc.grad)
+
+
+def test_rasterizer_module_picks_indexed_path_only_for_shared_topology(srf):
+    import lasr_b200.soft_renderer as sr
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(0)
+    faces = torch.randint(0, 30, (2, 20, 3), generator=g, dtype=torch.int32).to(dev)
+    assert srf.shared_topology(faces) is None                       # per-frame topologies -> gathered path
+    same = faces[:1].repeat(2, 1, 1)
+    assert srf.shared_topology(same) is not None
+    off, ent = srf.vertex_adjacency(same[0].contiguous(), 30)
+    assert off[-1].item() == 60 and ent.numel() == 60
+    flat = same[0].reshape(-1).cpu().numpy()
+    ent, off = ent.cpu().numpy(), off.cpu().numpy()
+    for v in range(30):
+        assert sorted(ent[off[v]:off[v + 1]]) == list(ent[off[v]:off[v + 1]])   # ascending (face, corner)
+        assert all(flat[e] == v for e in ent[off[v]:off[v + 1]])
+    verts = torch.randn(2, 30, 3, generator=g).to(dev) * 0.3 + torch.tensor([0, 0, 10.0], device=dev)
+    r = sr.SoftRasterizer(image_size=32, near=5, far=15, sigma_val=1e-4, gamma_val=1e-2, fill_back=True,
+                          texture_type="vertex")
+    cols = torch.rand(2, 30, 3, generator=g).to(dev)
+    a = r(sr.Mesh(verts, same, textures=cols, texture_type="vertex"))
+    b = srf.soft_rasterize(srf.face_vertices(verts, same), srf.face_vertices(cols, same), 32, [0, 0, 0], 5, 15, True,
+                           1e-3, 1e-4, "euclidean", 1e-4, 1e-2, "softmax", "prod", "vertex")
+    assert torch.equal(a, b)
