@@ -333,11 +333,28 @@ def run_gpu_arm(args, arm_cls):
     h2d = sum(t.numel() * t.element_size() for t in (h_verts, h_colors, h_faces, h_target))
     d2h = sum(t.numel() * t.element_size() for t in (h_loss, h_gv, h_gc))
 
+    host_inputs = [h_verts, h_colors, h_faces, h_target]
+    prefetch = None
+    if arm.name == "ours":
+        # our host pipeline: the H2D copy of step i+1 overlaps the compute of step i (lasr_b200.pipeline);
+        # every step's inputs still cross PCIe inside the timed region.  The reference arm copies the way
+        # LASR does (at the top of the step, on the compute stream).
+        from lasr_b200.pipeline import HostPrefetcher
+        prefetch = HostPrefetcher(device)
+
     def e2e_step():
-        verts = h_verts.to(device, non_blocking=True).requires_grad_(True)
-        colors = h_colors.to(device, non_blocking=True).requires_grad_(True)
-        faces = h_faces.to(device, non_blocking=True)
-        target = h_target.to(device, non_blocking=True)
+        if prefetch is not None:
+            if prefetch.staged == 0:
+                prefetch.stage(host_inputs)
+            d_verts, d_colors, faces, target = prefetch.get()
+            prefetch.stage(host_inputs)                       # next step's inputs, on the copy stream
+            verts = d_verts.detach().requires_grad_(True)
+            colors = d_colors.detach().requires_grad_(True)
+        else:
+            verts = h_verts.to(device, non_blocking=True).requires_grad_(True)
+            colors = h_colors.to(device, non_blocking=True).requires_grad_(True)
+            faces = h_faces.to(device, non_blocking=True)
+            target = h_target.to(device, non_blocking=True)
         img = arm.render(verts, faces, colors)
         loss = 0.5 * (img - target).pow(2).mean()
         loss.backward()
@@ -350,6 +367,8 @@ def run_gpu_arm(args, arm_cls):
         h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
         h_gv.copy_(gv, non_blocking=True)
         h_gc.copy_(gc, non_blocking=True)
+        if prefetch is not None:
+            prefetch.release()
 
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
     for _ in range(max(3, min(args.warmup, 5))):
@@ -390,7 +409,8 @@ def run_gpu_arm(args, arm_cls):
                        "l2": "per-step working set ~195 MB (inputs+outputs+grads) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "api": "SoftRenderer.render_mesh + autograd, L2 image loss, pinned host buffers"},
+                    "api": "SoftRenderer.render_mesh + autograd, L2 image loss, pinned host buffers"
+                           + (", H2D of step i+1 overlapped with step i (HostPrefetcher)" if arm.name == "ours" else "")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "kernels": {"forward_ms": fwd_ms, "backward_ms": bwd_ms,

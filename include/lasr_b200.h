@@ -155,6 +155,34 @@ int lasr_b200_lbs_project_backward(const float* verts, const float* Rmat, const 
                                    int num_frames, int num_vertices, int num_bones,
                                    int verts_shared, int skin_shared, int tocam, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Image losses: one fused masked-reduction pass.  Replaces the Python double
+ * loops of nnutils/mesh_net.py:372-447 (silhouette :374-390, flow :393-416, texture L1 :420-441;
+ * the 0.005*LPIPS term is outside this path).
+ *   mask_pred [N,H,S,S]; flow_rd [N,H,S,S,2] + bgmask [N,H,S,S] uint8 + flow_obs [N,3,S,S] (NULL = no
+ *   flow term); tex [N,H,3,S,S] + fg [N,H,S,S] + imgs [N,3,S,S] (NULL = no texture term);
+ *   masks, occ [N,S,S].
+ *   sums [N,H,7] out, per (frame, hypothesis):
+ *     0: sum_v (mask_pred-mask)^2   1: sum_k s|flow_rd-flow_obs|   2: sum_k s   3: sum_k 1
+ *     4: sum_v mean_c|obs-tex*fg|   5: sum_v mean_c|white-tex|     6: sum_v 1
+ *   with v = occ!=0, k = !bgmask & v & mask>0, s = sigmoid(-occ).
+ * The handful of scalar operations from sums to losses live in lasr_b200/losses.py.
+ * backward: grad_sums [N,H,7] -> per-pixel gradients (any output may be NULL).  Deterministic.
+ * ------------------------------------------------------------------------------------------- */
+size_t lasr_b200_losses_workspace_bytes(int num_frames, int num_hypotheses, int image_size);
+
+int lasr_b200_losses_forward(const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
+                             const float* tex, const float* fg, const float* imgs, const float* masks,
+                             const float* occ, const float* flow_obs, float* sums, void* workspace,
+                             size_t workspace_bytes, int num_frames, int num_hypotheses, int image_size,
+                             void* stream);
+
+int lasr_b200_losses_backward(const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
+                              const float* tex, const float* fg, const float* imgs, const float* masks,
+                              const float* occ, const float* flow_obs, const float* grad_sums,
+                              float* grad_mask_pred, float* grad_flow_rd, float* grad_tex, float* grad_fg,
+                              int num_frames, int num_hypotheses, int image_size, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,12 @@ def lib():
         L.lasr_b200_render_forward.argtypes = [_c.c_void_p] * 6 + [_c.c_size_t] + _render_scalars
         L.lasr_b200_render_backward.restype = _c.c_int
         L.lasr_b200_render_backward.argtypes = [_c.c_void_p] * 11 + [_c.c_size_t] + _render_scalars
+        L.lasr_b200_losses_workspace_bytes.restype = _c.c_size_t
+        L.lasr_b200_losses_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
+        L.lasr_b200_losses_forward.restype = _c.c_int
+        L.lasr_b200_losses_forward.argtypes = [_c.c_void_p] * 11 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
+        L.lasr_b200_losses_backward.restype = _c.c_int
+        L.lasr_b200_losses_backward.argtypes = [_c.c_void_p] * 14 + [_c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
         L.lasr_b200_lbs_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_lbs_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_lbs_project_forward.restype = _c.c_int
@@ -67,6 +73,7 @@ EXPORTED_SYMBOLS = [
     "lasr_b200_abi_version", "lasr_b200_last_error", "lasr_b200_launch_count",
     "lasr_b200_raster_workspace_bytes", "lasr_b200_raster_forward", "lasr_b200_raster_backward",
     "lasr_b200_render_workspace_bytes", "lasr_b200_render_forward", "lasr_b200_render_backward",
+    "lasr_b200_losses_workspace_bytes", "lasr_b200_losses_forward", "lasr_b200_losses_backward",
     "lasr_b200_lbs_workspace_bytes", "lasr_b200_lbs_project_forward", "lasr_b200_lbs_project_backward",
 ]
 
@@ -220,3 +227,21 @@ def render_backward(verts, tri, vcolors, soft_colors, aggrs_info, grad_soft_colo
             *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
                                  gamma_val, func_id_rgb, func_id_alpha, double_side))
     _check(rc, "lasr_b200_render_backward")
+
+
+def losses_forward(mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs, sums, N, H, S):
+    ws = torch.empty(int(lib().lasr_b200_losses_workspace_bytes(N, H, S)), dtype=torch.uint8, device=mask_pred.device)
+    with torch.cuda.device(mask_pred.device):
+        rc = lib().lasr_b200_losses_forward(_p(mask_pred), _p(flow_rd), _p(bgmask), _p(tex), _p(fg), _p(imgs),
+                                            _p(masks), _p(occ), _p(flow_obs), _p(sums), _p(ws), ws.numel(), N, H, S,
+                                            _stream_ptr())
+    _check(rc, "lasr_b200_losses_forward")
+
+
+def losses_backward(mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs, grad_sums, g_mask_pred,
+                    g_flow_rd, g_tex, g_fg, N, H, S):
+    with torch.cuda.device(mask_pred.device):
+        rc = lib().lasr_b200_losses_backward(_p(mask_pred), _p(flow_rd), _p(bgmask), _p(tex), _p(fg), _p(imgs),
+                                             _p(masks), _p(occ), _p(flow_obs), _p(grad_sums), _p(g_mask_pred),
+                                             _p(g_flow_rd), _p(g_tex), _p(g_fg), N, H, S, _stream_ptr())
+    _check(rc, "lasr_b200_losses_backward")

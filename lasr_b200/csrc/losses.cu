@@ -1,0 +1,238 @@
+// losses.cu -- fused masked reductions of LASR's three image losses, sm_100a.
+//
+// The reference computes them inline in LASR.forward (nnutils/mesh_net.py:372-447) with Python
+// double loops over (frame, hypothesis): boolean-mask indexing + .mean() per pair and a host
+// synchronisation per pair (`if mask[i,j].sum()==0`, :412) -- 2bs*H tiny kernels and syncs per loss.
+// Here ONE pass over the images produces, per (frame i, hypothesis j), the six masked sums all three
+// losses are made of; the few scalar operations that turn sums into losses stay in PyTorch on
+// [N,H]-sized tensors (lasr_b200/losses.py), which also gives their autograd for free.  The backward
+// kernel turns the gradients of the sums into per-pixel gradients in one elementwise pass.
+//
+//   v  = occ != 0                      (pixel inside the original frame)
+//   k  = !bgmask & v & (mask > 0)      (flow visibility)
+//   s  = sigmoid(-occ)
+//   obs = img * (mask > 0),  white = 1 - (mask > 0) + obs
+//
+//   sums[i,j,0] = sum v (mask_pred - mask)^2                    -> silhouette loss (:374-390)
+//   sums[i,j,1] = sum k s |flow_rd - flow_obs|_2                -> flow loss       (:393-416)
+//   sums[i,j,2] = sum k s        sums[i,j,3] = sum k
+//   sums[i,j,4] = sum v mean_c |obs_c   - tex_c * fg|           -> texture L1      (:420-441)
+//   sums[i,j,5] = sum v mean_c |white_c - tex_c|
+//   vcount[i]   = sum v
+//
+// Deterministic: fixed-order block reductions into per-block partials, summed in block order.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "host_common.h"
+#include "lasr_b200.h"
+
+namespace lasr {
+
+constexpr int kLossThreads = 256;
+constexpr int kLossPixPerBlock = 4096;   // pixels handled by one block (16 per thread)
+constexpr int kNumSums = 7;              // 6 sums + the valid-pixel count
+
+struct LossArgs {
+  const float* mask_pred;   // [N,H,S,S]
+  const float* flow_rd;     // [N,H,S,S,2]
+  const uint8_t* bgmask;    // [N,H,S,S]
+  const float* tex;         // [N,H,3,S,S]
+  const float* fg;          // [N,H,S,S]
+  const float* imgs;        // [N,3,S,S]
+  const float* masks;       // [N,S,S]
+  const float* occ;         // [N,S,S]
+  const float* flow_obs;    // [N,3,S,S] (channels 0,1 used)
+  int N, H, SS;             // SS = S*S
+  int has_flow, has_tex;
+};
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kLossThreads) losses_forward_kernel(LossArgs A, float* partial, int nblk) {
+  __shared__ float s_w[kLossThreads / 32][kNumSums];
+  const int ij = blockIdx.y;            // frame * H + hypothesis
+  const int i = ij / A.H;
+  const long long SS = A.SS;
+  float acc[kNumSums];
+#pragma unroll
+  for (int q = 0; q < kNumSums; ++q) acc[q] = 0.f;
+  const int p0 = blockIdx.x * kLossPixPerBlock;
+  const int p1 = min(p0 + kLossPixPerBlock, A.SS);
+  for (int p = p0 + threadIdx.x; p < p1; p += kLossThreads) {
+    const float occ = A.occ[i * SS + p];
+    const float m = A.masks[i * SS + p];
+    const bool v = occ != 0.f;
+    const bool fgm = m > 0.f;
+    if (v) {
+      acc[6] += 1.f;
+      const float d = A.mask_pred[ij * SS + p] - m;
+      acc[0] += d * d;
+    }
+    if (A.has_flow) {
+      const bool k = v && fgm && A.bgmask[ij * SS + p] == 0;
+      if (k) {
+        const float2 f = reinterpret_cast<const float2*>(A.flow_rd)[ij * SS + p];
+        const float dx = f.x - A.flow_obs[(i * 3 + 0) * SS + p];
+        const float dy = f.y - A.flow_obs[(i * 3 + 1) * SS + p];
+        const float s = 1.f / (1.f + expf(occ));
+        acc[1] += s * sqrtf(dx * dx + dy * dy);
+        acc[2] += s;
+        acc[3] += 1.f;
+      }
+    }
+    if (A.has_tex && v) {
+      const float fgv = A.fg[ij * SS + p];
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float img = A.imgs[(i * 3 + c) * SS + p];
+        const float obs = fgm ? img : 0.f;
+        const float white = fgm ? img : 1.f;
+        const float t = A.tex[((long long)ij * 3 + c) * SS + p];
+        a += fabsf(obs - t * fgv);
+        b += fabsf(white - t);
+      }
+      acc[4] += a * (1.f / 3.f);
+      acc[5] += b * (1.f / 3.f);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < kNumSums; ++q) {
+    const float w = wsum(acc[q]);
+    if (lane == 0) s_w[warp][q] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumSums) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLossThreads / 32; ++w) t += s_w[w][threadIdx.x];
+    partial[((long long)ij * nblk + blockIdx.x) * kNumSums + threadIdx.x] = t;
+  }
+}
+
+__global__ void losses_reduce_kernel(const float* partial, int nblk, int NH, float* sums) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= NH * kNumSums) return;
+  const int ij = t / kNumSums, q = t % kNumSums;
+  float acc = 0.f;
+  for (int b = 0; b < nblk; ++b) acc += partial[((long long)ij * nblk + b) * kNumSums + q];
+  sums[t] = acc;
+}
+
+// gsums [N,H,7] (gradient of the scalar objective w.r.t. each sum; entry 2,3,6 ignored: those sums
+// do not depend on differentiable inputs) -> per-pixel gradients.
+__global__ void __launch_bounds__(kLossThreads) losses_backward_kernel(LossArgs A, const float* gsums,
+                                                                       float* g_mask_pred, float* g_flow_rd,
+                                                                       float* g_tex, float* g_fg) {
+  const int ij = blockIdx.y;
+  const int i = ij / A.H;
+  const long long SS = A.SS;
+  const int p = blockIdx.x * kLossThreads + threadIdx.x;
+  if (p >= A.SS) return;
+  const float g0 = gsums[ij * kNumSums + 0], g1 = gsums[ij * kNumSums + 1];
+  const float g4 = gsums[ij * kNumSums + 4], g5 = gsums[ij * kNumSums + 5];
+  const float occ = A.occ[i * SS + p];
+  const float m = A.masks[i * SS + p];
+  const bool v = occ != 0.f;
+  const bool fgm = m > 0.f;
+  if (g_mask_pred) g_mask_pred[ij * SS + p] = v ? 2.f * (A.mask_pred[ij * SS + p] - m) * g0 : 0.f;
+  if (A.has_flow && g_flow_rd) {
+    float2 out = make_float2(0.f, 0.f);
+    if (v && fgm && A.bgmask[ij * SS + p] == 0) {
+      const float2 f = reinterpret_cast<const float2*>(A.flow_rd)[ij * SS + p];
+      const float dx = f.x - A.flow_obs[(i * 3 + 0) * SS + p];
+      const float dy = f.y - A.flow_obs[(i * 3 + 1) * SS + p];
+      const float nrm = sqrtf(dx * dx + dy * dy);
+      if (nrm > 0.f) {
+        const float c = g1 / (1.f + expf(occ)) / nrm;
+        out = make_float2(c * dx, c * dy);
+      }
+    }
+    reinterpret_cast<float2*>(g_flow_rd)[ij * SS + p] = out;
+  }
+  if (A.has_tex && g_tex) {
+    const float fgv = A.fg[ij * SS + p];
+    float gfg = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float gt = 0.f;
+      if (v) {
+        const float img = A.imgs[(i * 3 + c) * SS + p];
+        const float obs = fgm ? img : 0.f;
+        const float white = fgm ? img : 1.f;
+        const float t = A.tex[((long long)ij * 3 + c) * SS + p];
+        const float ra = obs - t * fgv, rb = white - t;
+        const float sa = ra > 0.f ? 1.f : (ra < 0.f ? -1.f : 0.f);   // d|x|/dx, 0 at 0 like torch.abs
+        const float sb = rb > 0.f ? 1.f : (rb < 0.f ? -1.f : 0.f);
+        gt = (-sa * fgv * g4 - sb * g5) * (1.f / 3.f);
+        gfg += -sa * t * g4 * (1.f / 3.f);
+      }
+      g_tex[((long long)ij * 3 + c) * SS + p] = gt;
+    }
+    if (g_fg) g_fg[ij * SS + p] = gfg;
+  }
+}
+
+static int fill_loss(LossArgs& A, const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
+                     const float* tex, const float* fg, const float* imgs, const float* masks, const float* occ,
+                     const float* flow_obs, int N, int H, int S) {
+  if (N <= 0 || H <= 0 || S <= 0) return lasr_fail("losses: N, H, S must be positive");
+  if (!mask_pred || !masks || !occ) return lasr_fail("losses: mask_pred, masks, occ are required");
+  A.has_flow = flow_rd != nullptr;
+  A.has_tex = tex != nullptr;
+  if (A.has_flow && (!bgmask || !flow_obs)) return lasr_fail("losses: flow loss needs bgmask and flow_obs");
+  if (A.has_tex && (!fg || !imgs)) return lasr_fail("losses: texture loss needs fg and imgs");
+  A.mask_pred = mask_pred; A.flow_rd = flow_rd; A.bgmask = bgmask; A.tex = tex; A.fg = fg; A.imgs = imgs;
+  A.masks = masks; A.occ = occ; A.flow_obs = flow_obs;
+  A.N = N; A.H = H; A.SS = S * S;
+  return 0;
+}
+
+}  // namespace lasr
+
+using namespace lasr;
+
+extern "C" size_t lasr_b200_losses_workspace_bytes(int N, int H, int S) {
+  if (N <= 0 || H <= 0 || S <= 0) return 0;
+  const size_t nblk = ((size_t)S * S + kLossPixPerBlock - 1) / kLossPixPerBlock;
+  return (size_t)N * H * nblk * kNumSums * sizeof(float) + 256;
+}
+
+extern "C" int lasr_b200_losses_forward(const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
+                                        const float* tex, const float* fg, const float* imgs, const float* masks,
+                                        const float* occ, const float* flow_obs, float* sums, void* workspace,
+                                        size_t workspace_bytes, int N, int H, int S, void* stream) {
+  LossArgs A{};
+  if (fill_loss(A, mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs, N, H, S)) return 1;
+  if (!sums || !workspace || workspace_bytes < lasr_b200_losses_workspace_bytes(N, H, S))
+    return lasr_fail("losses_forward: null output or workspace too small");
+  const int nblk = (A.SS + kLossPixPerBlock - 1) / kLossPixPerBlock;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = reinterpret_cast<float*>(workspace);
+  losses_forward_kernel<<<dim3(nblk, N * H), kLossThreads, 0, st>>>(A, partial, nblk);
+  if (lasr_check_launch("losses_forward_kernel")) return 1;
+  const int tot = N * H * kNumSums;
+  losses_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(partial, nblk, N * H, sums);
+  return lasr_check_launch("losses_reduce_kernel");
+}
+
+extern "C" int lasr_b200_losses_backward(const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
+                                         const float* tex, const float* fg, const float* imgs, const float* masks,
+                                         const float* occ, const float* flow_obs, const float* grad_sums,
+                                         float* grad_mask_pred, float* grad_flow_rd, float* grad_tex, float* grad_fg,
+                                         int N, int H, int S, void* stream) {
+  LossArgs A{};
+  if (fill_loss(A, mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs, N, H, S)) return 1;
+  if (!grad_sums) return lasr_fail("losses_backward: grad_sums required");
+  cudaStream_t st = (cudaStream_t)stream;
+  losses_backward_kernel<<<dim3((A.SS + kLossThreads - 1) / kLossThreads, N * H), kLossThreads, 0, st>>>(
+      A, grad_sums, grad_mask_pred, grad_flow_rd, grad_tex, grad_fg);
+  return lasr_check_launch("losses_backward_kernel");
+}

@@ -410,20 +410,21 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
       for (int k = 0; k < 3; ++k) { gf[3 * k] += gx[k]; gf[3 * k + 1] += gy[k]; gf[3 * k + 2] += gz[k]; }
     }
   }
-  // fixed-order warp reduction, one write per face
+  // fixed-order warp reduction (16 values by recursive halving + 2 butterflies), one write per value
   float* gface_out = A.grad_faces + wg * 9;
+  float v16[16];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const float v = warp_sum(gf[k]);
-    if (lane == k) gface_out[k] = v;
-  }
-  if (sample == 1) {
+  for (int k = 0; k < 9; ++k) v16[k] = gf[k];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const float v = warp_sum(gt[k]);
-      if (lane == k) gtex_out[k] = v;
-    }
+  for (int k = 0; k < 7; ++k) v16[9 + k] = gt[k];
+  warp_sum16(v16, lane);
+  const float t7 = warp_sum(gt[7]), t8 = warp_sum(gt[8]);
+  if ((lane & 1) == 0) {
+    const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    if (idx < 9) gface_out[idx] = v16[0];
+    else if (sample == 1) gtex_out[idx - 9] = v16[0];
   }
+  if (sample == 1 && lane == 0) { gtex_out[7] = t7; gtex_out[8] = t8; }
 }
 
 // ---------------------------------------------------------------------------------------------

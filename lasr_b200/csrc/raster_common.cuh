@@ -87,7 +87,7 @@ __device__ __forceinline__ float cross2(float a, float b, float c, float d) {
 }
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
-__device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.f, x); }  // MUFU.RCP
+__device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.f, x); }
 
 // Rule (2) applies to LASR's training configuration (kFast: euclidean / softmax / prod / vertex
 // colours), which has no hard decision downstream of the distance stage.  The other operator
@@ -126,6 +126,7 @@ struct FaceGeom {
   float a[3][3];      // a[e][j] = sym[e][j] - sym[(e+1)%3][j],  sym = P P^T + 1
   float rden[3];      // 1 / (a[e][e] - a[e][(e+1)%3])  (= 1 / squared edge length)
   float lox, hix, loy, hiy;  // bounding box dilated by sqrt(threshold)
+  float det;          // clamped determinant the rows of inv were divided by
   int obt;            // index of the (first) obtuse corner, -1 if none
   bool front;
 };
@@ -139,6 +140,7 @@ __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float s
   // determinant: x2*(y0-y1) + x0*(y1-y2) + x1*(y2-y0)   (.cu:278-281)
   float det = __fmaf_rn(x1, __fsub_rn(y2, y0), __fmaf_rn(x2, __fsub_rn(y0, y1), __fmul_rn(x0, __fsub_rn(y1, y2))));
   det = det > 0.f ? fmaxf(det, 1e-10f) : fminf(det, -1e-10f);  // :282
+  g.det = det;
   const float adj[9] = {__fsub_rn(y1, y2), __fsub_rn(x2, x1), cross2(x1, y2, x2, y1),
                         __fsub_rn(y2, y0), __fsub_rn(x0, x2), cross2(x2, y0, x0, y2),
                         __fsub_rn(y0, y1), __fsub_rn(x1, x0), cross2(x0, y1, x1, y0)};
@@ -364,6 +366,27 @@ __device__ __forceinline__ int surface_texel(const float* wc, int R) {
   const int wx = (int)(wc[0] * R);
   const int wy = (int)(wc[1] * R);
   return ((wc[0] + wc[1]) * R - wx - wy <= 1.f) ? (wy * R + wx) : ((R - 1 - wy) * R + (R - 1 - wx));
+}
+
+// Sum 16 per-lane values over the warp with 16 shuffles instead of 80 (recursive halving: at each
+// stage a lane keeps half of its values and ships the other half to its partner).  On return lane L
+// holds in v[0] the warp total of value  idx = 8*bit4(L) + 4*bit3(L) + 2*bit2(L) + bit1(L).
+// Fixed combination order => deterministic.
+__device__ __forceinline__ void warp_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int stage = 0; stage < 4; ++stage) {
+    const int o = 16 >> stage;         // 16, 8, 4, 2
+    const int half = 8 >> stage;       // values kept after this stage: 8, 4, 2, 1
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float a = v[i], b = v[i + half];
+      const float keep = upper ? b : a;
+      const float send = upper ? a : b;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
 // warp butterfly sum (fixed order => deterministic)

@@ -10,6 +10,49 @@ The 0.005*LPIPS term of the texture loss (:442-443) is a convnet and outside thi
 from __future__ import annotations
 
 import torch
+from torch.autograd import Function
+
+
+class _LossSums(Function):
+    """[N,H,7] masked sums of lasr_b200/csrc/losses.cu (see the layout there); differentiable w.r.t.
+    mask_pred, flow_rd, texture_render and fgmask."""
+
+    @staticmethod
+    def forward(ctx, mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs):
+        from . import _cabi
+        N, H, S = mask_pred.shape[0], mask_pred.shape[1], mask_pred.shape[-1]
+        c = lambda t: None if t is None else t.detach().float().contiguous()
+        mp, fr, tx, fgc, im, mk, oc, fo = (c(t) for t in (mask_pred, flow_rd, tex, fg, imgs, masks, occ, flow_obs))
+        bg = None if bgmask is None else bgmask.detach().to(torch.uint8).contiguous()
+        sums = torch.empty(N, H, 7, dtype=torch.float32, device=mask_pred.device)
+        _cabi.losses_forward(mp, fr, bg, tx, fgc, im, mk, oc, fo, sums, N, H, S)
+        ctx.save_for_backward(*[t for t in (mp, fr, bg, tx, fgc, im, mk, oc, fo) if t is not None])
+        ctx.present = [t is not None for t in (mp, fr, bg, tx, fgc, im, mk, oc, fo)]
+        ctx.dims = (N, H, S)
+        return sums
+
+    @staticmethod
+    def backward(ctx, gsums):
+        from . import _cabi
+        it = iter(ctx.saved_tensors)
+        mp, fr, bg, tx, fgc, im, mk, oc, fo = [next(it) if p else None for p in ctx.present]
+        N, H, S = ctx.dims
+        need = ctx.needs_input_grad
+        g_mp = torch.empty_like(mp) if need[0] else None
+        g_fr = torch.empty_like(fr) if (fr is not None and need[1]) else None
+        g_tx = torch.empty_like(tx) if (tx is not None and (need[3] or need[4])) else None
+        g_fg = torch.empty_like(fgc) if (tx is not None and need[4]) else None
+        _cabi.losses_backward(mp, fr, bg, tx, fgc, im, mk, oc, fo, gsums.float().contiguous(), g_mp, g_fr, g_tx, g_fg,
+                              N, H, S)
+        return g_mp, g_fr, None, (g_tx if need[3] else None), g_fg, None, None, None, None
+
+
+def _native(t):
+    return t.is_cuda
+
+
+def _sums(mask_pred, masks, occ, flow_rd=None, bgmask=None, flow_obs=None, tex=None, fg=None, imgs=None):
+    return _LossSums.apply(mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs)
 
 
 def _masked_mean(x, m, dims):
@@ -22,6 +65,10 @@ def mask_loss(mask_pred, masks, occ):
     """Silhouette loss (mesh_net.py:374-390).
     mask_pred [N,H,S,S] rendered alpha; masks [N,S,S]; occ [N,S,S] (0 = pixel outside the frame).
     Returns (scalar, per-(frame,hypothesis) [N,H])."""
+    if _native(mask_pred):
+        q = _sums(mask_pred, masks, occ)
+        sub = 0.5 * q[..., 0] / q[..., 6]
+        return sub.mean(), sub
     valid = (occ != 0)[:, None]
     sub = 0.5 * _masked_mean((mask_pred - masks[:, None]).pow(2), valid.expand_as(mask_pred), (2, 3))
     return sub.mean(), sub
@@ -33,6 +80,12 @@ def flow_loss(flow_rd, bgmask, flow_obs, occ, masks):
     Returns (scalar, per-(frame,hypothesis) [N,H], visibility mask [N,H,S,S])."""
     N, H = flow_rd.shape[:2]
     mask = (~bgmask) & ((occ != 0) & (masks > 0))[:, None]
+    if _native(flow_rd):
+        q = _sums(torch.zeros_like(bgmask, dtype=torch.float32), masks, occ, flow_rd, bgmask, flow_obs)
+        A, B, C = q[..., 1], q[..., 2], q[..., 3]
+        wmean = B.sum(1, keepdim=True) / C.sum(1, keepdim=True)      # per frame, over all hypotheses (:406-407)
+        sub = 0.5 * torch.where(C == 0, torch.zeros_like(A), A / wmean / C.clamp(min=1))
+        return sub.mean(), sub, mask
     diff = flow_rd - flow_obs[:, None, :2].permute(0, 1, 3, 4, 2)
     rd_map = torch.norm(diff, 2, -1)
     w = (-occ).sigmoid()[:, None].expand(N, H, -1, -1)
@@ -47,6 +100,10 @@ def flow_loss(flow_rd, bgmask, flow_obs, occ, masks):
 def texture_l1_loss(texture_render, fgmask, imgs, masks, occ, l1tex_wt=1.0):
     """Texture L1 terms (mesh_net.py:361-363, 420-441, 444-445) without the LPIPS term.
     texture_render [N,H,3,S,S]; fgmask [N,H,S,S]; imgs [N,3,S,S]; masks, occ [N,S,S]."""
+    if _native(texture_render):
+        q = _sums(fgmask, masks, occ, tex=texture_render, fg=fgmask, imgs=imgs)
+        sub = 0.25 * ((q[..., 4] + q[..., 5]) / q[..., 6] * 2 * l1tex_wt)
+        return sub.mean(), sub
     m = (masks > 0).float()[:, None]
     img_obs = imgs * m
     img_white = 1 - m + img_obs
@@ -57,3 +114,16 @@ def texture_l1_loss(texture_render, fgmask, imgs, masks, occ, l1tex_wt=1.0):
     sub = _masked_mean(a, valid.expand_as(a), (2, 3)) + _masked_mean(b, valid.expand_as(b), (2, 3))
     sub = 0.25 * (sub * 2 * l1tex_wt)
     return sub.mean(), sub
+
+
+def image_losses(mask_pred, masks, occ, flow_rd, bgmask, flow_obs, texture_render, fgmask, imgs, l1tex_wt=1.0):
+    """All three losses from ONE fused pass (CUDA tensors): returns (mask_loss, flow_loss, texture_loss,
+    per-(frame,hypothesis) dict).  Values equal mask_loss / flow_loss / texture_l1_loss."""
+    q = _sums(mask_pred, masks, occ, flow_rd, bgmask, flow_obs, texture_render, fgmask, imgs)
+    V = q[..., 6]
+    m_sub = 0.5 * q[..., 0] / V
+    A, B, C = q[..., 1], q[..., 2], q[..., 3]
+    wmean = B.sum(1, keepdim=True) / C.sum(1, keepdim=True)
+    f_sub = 0.5 * torch.where(C == 0, torch.zeros_like(A), A / wmean / C.clamp(min=1))
+    t_sub = 0.25 * ((q[..., 4] + q[..., 5]) / V * 2 * l1tex_wt)
+    return m_sub.mean(), f_sub.mean(), t_sub.mean(), dict(mask=m_sub, flow=f_sub, texture=t_sub)

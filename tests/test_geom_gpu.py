@@ -112,3 +112,38 @@ def test_hypotheses_repeat_of_principal_point(dev):
     verts = torch.cat([torch.randn(6, 40, 2, generator=g), 9 + torch.rand(6, 40, 1, generator=g), torch.ones(6, 40, 1)], -1)
     pp, fl = torch.randn(3, 2, generator=g) * 0.1, 9 + torch.rand(6, 1, generator=g)
     assert close(gu.pinhole_cam(verts.to(dev), pp.to(dev), fl.to(dev)), gu.pinhole_cam(verts, pp, fl), 2e-6)
+
+
+def test_fused_image_losses_match_cpu_expressions(dev):
+    """L1-L3 on CUDA (one fused masked-reduction kernel + its backward) == the PyTorch expressions on
+    CPU tensors, which tests/test_host_glue.py ties to the loop-for-loop restatement of the reference."""
+    from lasr_b200 import losses
+    g = torch.Generator().manual_seed(11)
+    N, H, S = 5, 2, 96
+    mk = lambda *sh: torch.rand(*sh, generator=g)
+    mask_pred, fg, tex = mk(N, H, S, S), mk(N, H, S, S), mk(N, H, 3, S, S)
+    flow_rd = torch.randn(N, H, S, S, 2, generator=g) * 0.05
+    masks = (mk(N, S, S) > 0.5).float()
+    occ = torch.randn(N, S, S, generator=g)
+    occ[mk(N, S, S) < 0.2] = 0
+    bg = mk(N, H, S, S) < 0.4
+    bg[1, 0] = True
+    flow_obs, imgs = torch.randn(N, 3, S, S, generator=g) * 0.05, mk(N, 3, S, S)
+
+    def run(d):
+        t = lambda x: x.clone().to(d)
+        mp, fr, tx, fgx = (t(x).requires_grad_(True) for x in (mask_pred, flow_rd, tex, fg))
+        lm, sm = losses.mask_loss(mp, t(masks), t(occ))
+        lf, sf, _ = losses.flow_loss(fr, t(bg), t(flow_obs), t(occ), t(masks))
+        lt, stx = losses.texture_l1_loss(tx, fgx, t(imgs), t(masks), t(occ), 0.7)
+        (lm + 2 * lf + 3 * lt).backward()
+        return [x.detach().cpu() for x in (lm, lf, lt, sm, sf, stx, mp.grad, fr.grad, tx.grad, fgx.grad)]
+
+    a, b = run(torch.device("cpu")), run(dev)
+    for x, y in zip(a, b):
+        assert torch.allclose(x, y, rtol=2e-4, atol=1e-7), (x.flatten()[:4], y.flatten()[:4])
+    # the single fused call gives the same three numbers
+    t = lambda x: x.clone().to(dev)
+    lm, lf, lt, _ = losses.image_losses(t(mask_pred), t(masks), t(occ), t(flow_rd), t(bg), t(flow_obs), t(tex), t(fg),
+                                        t(imgs), 0.7)
+    assert torch.allclose(torch.stack([lm, lf, lt]).cpu(), torch.stack(a[:3]), rtol=2e-4)
