@@ -1,0 +1,113 @@
+"""The render hot path of ``LASR.forward`` (nnutils/mesh_net.py:255-447) as one call.
+
+Pose in, three image losses out, with every stage served by this package:
+skinning weights (S0) -> fused LBS + camera + projection + depth window (G1-G3) -> forward /
+backward flow renders and the texture render through the indexed soft rasterizer (R1-R4) ->
+fused silhouette / flow / texture-L1 losses (L1-L3).  It is what a maintainer would call from
+``LASR.forward`` in place of lines 255-447, and what the tests use to check the whole chain against
+an oracle-backed CPU composition.  Tensor layout follows the reference: a batch holds ``bs`` frame
+pairs as [first frames; second frames] (2*bs items), each with ``H`` hypotheses and ``B`` bones.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import geom_utils as gu
+from . import losses as L
+from . import soft_renderer as sr
+
+
+@dataclass
+class HotPathOptions:
+    img_size: int = 256
+    n_hypo: int = 1
+    n_bones: int = 1
+    sigval: float = 1e-4
+    l1tex_wt: float = 1.0
+    opt_tex: bool = True
+
+
+class RenderHotPath(torch.nn.Module):
+    """Holds the three SoftRenderers LASR builds for this region (mesh_net.py:136-145)."""
+
+    def __init__(self, opts: HotPathOptions):
+        super().__init__()
+        self.opts = opts
+        mk = lambda: sr.SoftRenderer(image_size=opts.img_size, sigma_val=opts.sigval, gamma_val=1e-2,
+                                     camera_mode="look_at", perspective=False, aggr_func_rgb="softmax",
+                                     light_mode="vertex", light_intensity_ambient=1.0,
+                                     light_intensity_directionals=0.0)
+        self.renderer_softflf, self.renderer_softflb, self.renderer_softtex = mk(), mk(), mk()
+
+    def forward(self, pred_v, tex, faces, Rmat, Tmat, ppoint, scale, batch, bones=None):
+        """pred_v [2bs*H,V,3]; tex [2bs*H,V,3]; faces [2bs,F,3] int32; Rmat [2bs*H*B,3,3] (already
+        transposed as mesh_net.py:259); Tmat [2bs*H*B,3]; ppoint [2bs,2]; scale [2bs*H,1];
+        batch = dict(masks [2bs,S,S], imgs [2bs,3,S,S], flow [2bs,3,S,S], occ [2bs,S,S]);
+        bones = dict(ctl_ts, ctl_rs, log_ctl, rest_ts) when B > 1.
+        Returns dict(total, mask_loss, flow_loss, texture_loss, + renders)."""
+        o = self.opts
+        H, B, S = o.n_hypo, o.n_bones, o.img_size
+        n2 = ppoint.shape[0]          # 2 * bs
+        bs = n2 // 2
+        skin = None
+        if B > 1:                      # mesh_net.py:261-281
+            skin = gu.skin_weights(bones["ctl_ts"], bones["ctl_rs"], bones["log_ctl"],
+                                   pred_v.view(n2, H, -1, 3)[0].detach(), H)
+            skin = skin.repeat(n2, 1, 1, 1)
+            rest_ts = bones["rest_ts"][:, None, :, None].repeat(n2, 1, 1, 1).view(-1, B - 1, 3, 1)
+            R4 = Rmat.view(-1, B, 3, 3)
+            T4 = Tmat.view(-1, B, 3, 1)
+            T_parts = -R4[:, 1:].matmul(rest_ts) + T4[:, 1:] + rest_ts
+            Tmat = torch.cat([T4[:, :1], T_parts], 1).view(-1, 3)
+            Rmat = torch.cat([R4[:, :1], R4[:, 1:].permute(0, 1, 3, 2)], 1).view(-1, 3, 3)
+        # 1) LBS + camera (mesh_net.py:298-311)
+        cam = gu.obj_to_cam(pred_v, Rmat, Tmat[:, None, :], B, H, skin)
+        verts_fl = torch.cat([cam, torch.ones_like(cam[:, :, :1])], dim=-1)
+        verts_pos0 = verts_fl.view(n2, H, -1, 4)[:bs].reshape(bs * H, -1, 4)
+        verts_pos1 = verts_fl.view(n2, H, -1, 4)[bs:].reshape(bs * H, -1, 4)
+        verts_px = gu.pinhole_cam(verts_fl, ppoint, scale)
+        near, far = gu.depth_window(verts_px[:, :, 2])
+        for r in (self.renderer_softflf, self.renderer_softflb, self.renderer_softtex):
+            r.rasterizer.near, r.rasterizer.far = near, far
+            r.rasterizer.sigma_val = o.sigval
+        # 2) flow renders (mesh_net.py:318-335)
+        px4 = verts_px.view(n2, H, -1, 4)
+        rep = lambda t, lo, hi: t[:, None][lo:hi].repeat(1, H, 1).view(-1, t.shape[-1])
+        flow_fw, bg_fw, fg_fw = gu.render_flow_soft_2(
+            self.renderer_softflf, px4[:bs].reshape(bs * H, -1, 4), faces[:bs], verts_pos0, verts_pos1,
+            rep(ppoint, 0, bs), rep(ppoint, bs, n2), scale.view(n2, H, 1)[:bs].reshape(-1, 1),
+            scale.view(n2, H, 1)[bs:].reshape(-1, 1))
+        flow_bw, bg_bw, fg_bw = gu.render_flow_soft_2(
+            self.renderer_softflb, px4[bs:].reshape(bs * H, -1, 4), faces[bs:], verts_pos1, verts_pos0,
+            rep(ppoint, bs, n2), rep(ppoint, 0, bs), scale.view(n2, H, 1)[bs:].reshape(-1, 1),
+            scale.view(n2, H, 1)[:bs].reshape(-1, 1))
+        bgmask = torch.cat([bg_fw, bg_bw], 0)
+        flow_rd = torch.cat([flow_fw, flow_bw], 0)
+        # 3) texture / silhouette render (mesh_net.py:348-363)
+        offset = gu._eye_offset(self.renderer_softtex, verts_px.device)
+        pre = verts_px[:, :, :3] + offset
+        pre = torch.cat([pre[:, :, :1], -pre[:, :, 1:2], pre[:, :, 2:]], dim=-1)
+        self.renderer_softtex.rasterizer.background_color = [1, 1, 1]
+        faces_h = faces[:, None].repeat(1, H, 1, 1).view(-1, faces.shape[1], 3)
+        texture_render = self.renderer_softtex.render_mesh(sr.Mesh(pre, faces_h, textures=tex, texture_type="vertex"))
+        mask_pred = texture_render[:, -1]
+        rgb = texture_render[:, :3]
+        # 4) losses (mesh_net.py:372-447, LPIPS term excluded)
+        mp = mask_pred.view(n2, H, S, S)
+        fr = flow_rd.view(n2, H, S, S, 2)
+        bgm = bgmask.view(n2, H, S, S)
+        tr = rgb.reshape(n2, H, 3, S, S)
+        if mp.is_cuda and o.opt_tex:
+            mask_loss, flow_loss, texture_loss, sub = L.image_losses(mp, batch["masks"], batch["occ"], fr, bgm,
+                                                                     batch["flow"], tr, mp, batch["imgs"], o.l1tex_wt)
+        else:
+            mask_loss, _ = L.mask_loss(mp, batch["masks"], batch["occ"])
+            flow_loss, _, _ = L.flow_loss(fr, bgm, batch["flow"], batch["occ"], batch["masks"])
+            texture_loss = (L.texture_l1_loss(tr, mp, batch["imgs"], batch["masks"], batch["occ"], o.l1tex_wt)[0]
+                            if o.opt_tex else mask_loss * 0)
+        total = mask_loss + flow_loss + (texture_loss if o.opt_tex else 0)
+        return dict(total=total, mask_loss=mask_loss, flow_loss=flow_loss, texture_loss=texture_loss,
+                    mask_pred=mask_pred, texture_render=rgb, flow_rd=flow_rd, bgmask=bgmask, verts_px=verts_px,
+                    near=near, far=far)

@@ -1,0 +1,110 @@
+"""Whole-chain integration: lasr_b200.hotpath.RenderHotPath (S0 -> G1-G3 -> R1-R4 -> L1-L3) on the GPU
+against the same chain on CPU tensors with the CPU ORACLE as the rasterizer (forward and backward),
+i.e. reference-pinned pieces composed end to end.  Losses and every gradient must agree."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class OracleRasterize(torch.autograd.Function):
+    """srf.soft_rasterize for CPU tensors, computed by oracle/ (tests only)."""
+
+    @staticmethod
+    def forward(ctx, fv, tex, settings):
+        from oracle import oracle as O
+        O.set_contract(True)
+        s = {k: (float(v) if torch.is_tensor(v) else v) for k, v in settings.items()}
+        r = O.soft_rasterize_forward(fv.detach().numpy(), tex.detach().numpy(), s, np.float32)
+        ctx.r, ctx.shapes = r, (fv.shape, tex.shape)
+        return torch.from_numpy(r["soft_colors"])
+
+    @staticmethod
+    def backward(ctx, g):
+        from oracle import oracle as O
+        gf, gt = O.soft_rasterize_backward(ctx.r, g.contiguous().numpy())
+        return torch.from_numpy(gf).reshape(ctx.shapes[0]), torch.from_numpy(gt).reshape(ctx.shapes[1]), None
+
+
+def oracle_soft_rasterize(face_vertices, textures, image_size=256, background_color=[0, 0, 0], near=1, far=100,
+                          fill_back=True, eps=1e-3, sigma_val=1e-5, dist_func="euclidean", dist_eps=1e-4,
+                          gamma_val=1e-4, aggr_func_rgb="softmax", aggr_func_alpha="prod", texture_type="surface"):
+    s = dict(image_size=image_size, background_color=list(background_color), near=near, far=far, fill_back=fill_back,
+             eps=eps, sigma_val=sigma_val, dist_func=dist_func, dist_eps=dist_eps, gamma_val=gamma_val,
+             aggr_func_rgb=aggr_func_rgb, aggr_func_alpha=aggr_func_alpha, texture_type=texture_type)
+    return OracleRasterize.apply(face_vertices, textures, s)
+
+
+def scenario(H, B, S, bs=2, seed=0):
+    from lasr_b200 import synth
+    from lasr_b200.geom_utils import quaternion_to_rotation_matrix
+    g = torch.Generator().manual_seed(seed)
+    v, f = synth.bumpy_sphere(2, 0.4)
+    V = len(v)
+    n2 = 2 * bs
+    N = n2 * H
+    pred_v = torch.from_numpy(v)[None].repeat(N, 1, 1)
+    tex = torch.sigmoid(torch.randn(1, V, 3, generator=g)).repeat(N, 1, 1)
+    faces = torch.from_numpy(f)[None].repeat(n2, 1, 1)
+    q = torch.randn(N * B, 4, generator=g) * 0.15
+    q[:, 3] = 1.0
+    q.view(N, B, 4)[:, 0, :3] = torch.randn(N, 3, generator=g)          # free body rotation
+    Rmat = quaternion_to_rotation_matrix(q).permute(0, 2, 1).contiguous()  # mesh_net.py:259
+    Tmat = torch.randn(N * B, 3, generator=g) * 0.03
+    Tmat.view(N, B, 3)[:, 0, 2] += 10.0
+    ppoint = torch.randn(n2, 2, generator=g) * 0.05
+    scale = 9.5 + torch.rand(N, 1, generator=g)
+    bones = None
+    if B > 1:
+        idx = torch.randperm(V, generator=g)[:H * (B - 1)]
+        ctl = torch.from_numpy(v)[idx]
+        bones = dict(ctl_ts=ctl.clone(), rest_ts=ctl.clone() + 0.01,
+                     ctl_rs=torch.tensor([[0.0, 0.0, 0.0, 1.0]]).repeat(H * (B - 1), 1) + torch.randn(H * (B - 1), 4, generator=g) * 0.05,
+                     log_ctl=torch.ones(H * (B - 1), 3))
+    occ = torch.randn(n2, S, S, generator=g)
+    occ[torch.rand(n2, S, S, generator=g) < 0.15] = 0
+    batch = dict(masks=(torch.rand(n2, S, S, generator=g) > 0.4).float(), imgs=torch.rand(n2, 3, S, S, generator=g),
+                 flow=torch.randn(n2, 3, S, S, generator=g) * 0.05, occ=occ)
+    return pred_v, tex, faces, Rmat, Tmat, ppoint, scale, batch, bones
+
+
+@pytest.mark.parametrize("H,B", [(1, 1), (2, 3)])
+def test_hot_path_matches_oracle_backed_cpu_chain(monkeypatch, H, B):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from lasr_b200 import hotpath
+    import lasr_b200.soft_renderer.rasterizer as rast
+    S = 48
+    opts = hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B, sigval=1e-4, l1tex_wt=1.0)
+    pred_v, tex, faces, Rmat, Tmat, ppoint, scale, batch, bones = scenario(H, B, S)
+
+    def run(dev):
+        t = lambda x: x.clone().to(dev)
+        leaves = dict(pred_v=t(pred_v), tex=t(tex), Rmat=t(Rmat), Tmat=t(Tmat), ppoint=t(ppoint), scale=t(scale))
+        bn = None
+        if bones is not None:
+            bn = {k: t(v) for k, v in bones.items()}
+            leaves.update({f"bone_{k}": bn[k] for k in bn})
+        for x in leaves.values():
+            x.requires_grad_(True)
+        m = hotpath.RenderHotPath(opts)
+        out = m(leaves["pred_v"], leaves["tex"], t(faces), leaves["Rmat"], leaves["Tmat"], leaves["ppoint"],
+                leaves["scale"], {k: t(v) for k, v in batch.items()}, bn)
+        out["total"].backward()
+        return ({k: out[k].detach().cpu() for k in ("total", "mask_loss", "flow_loss", "texture_loss", "mask_pred")},
+                {k: (x.grad.detach().cpu() if x.grad is not None else None) for k, x in leaves.items()})
+
+    gpu_out, gpu_grads = run(torch.device("cuda", 0))
+    monkeypatch.setattr(rast.srf, "soft_rasterize", oracle_soft_rasterize)
+    cpu_out, cpu_grads = run(torch.device("cpu"))
+
+    for k in ("total", "mask_loss", "flow_loss", "texture_loss"):
+        assert abs(float(gpu_out[k]) - float(cpu_out[k])) <= 2e-4 * max(1e-3, abs(float(cpu_out[k]))), k
+    assert (gpu_out["mask_pred"] - cpu_out["mask_pred"]).abs().max() < 1e-4
+    for k, g in cpu_grads.items():
+        if g is None:
+            assert gpu_grads[k] is None or float(gpu_grads[k].abs().max()) == 0.0
+            continue
+        rel = (gpu_grads[k] - g).norm() / g.norm().clamp(min=1e-20)
+        assert rel < 2e-3, (k, float(rel))
