@@ -224,7 +224,7 @@ class OursArm:
         if timed:
             e[1].record()
         self.cabi.raster_backward(self.fv, self.tex, self.img, self.aggrs, self.gf, self.gt, self.grad, self.ws,
-                                  *self.scal)
+                                  *self.scal, setup_done=True)
         if timed:
             e[2].record()
             self.pending.append(e)

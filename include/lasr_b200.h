@@ -84,7 +84,10 @@ int lasr_b200_raster_backward(const float* faces, const float* textures, const f
                               const float* near_far_dev, float eps, float sigma_val,
                               int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
                               int func_id_alpha, int texture_sample_type, int double_side,
-                              void* stream);
+                              int setup_done, void* stream);
+/* setup_done = 1: `workspace` is the one the matching lasr_b200_raster_forward call filled for the SAME
+ * inputs (the reference likewise hands its forward's `faces_info` to the backward,
+ * soft_rasterize.py:64,71); the per-face records are then read back instead of recomputed. */
 
 /* ---------------------------------------------------------------------------------------------
  * Indexed ("fused") rasterizer: vertices + shared topology + vertex colours in, image out, gradients
@@ -118,7 +121,7 @@ int lasr_b200_render_backward(const float* verts, const int32_t* tri, const floa
                               int num_vertices, int num_faces, int image_size, float near_,
                               float far_, const float* near_far_dev, float eps, float sigma_val,
                               int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
-                              int func_id_alpha, int double_side, void* stream);
+                              int func_id_alpha, int double_side, int setup_done, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused linear-blend skinning + body transform + pinhole projection + batch depth window

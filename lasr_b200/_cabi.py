@@ -19,8 +19,7 @@ _c = ctypes
 _RASTER_SCALARS = [_c.c_int, _c.c_int, _c.c_int, _c.c_int,      # N, F, S, T
                    _c.c_float, _c.c_float, _c.c_void_p,          # near, far, near_far_dev
                    _c.c_float, _c.c_float, _c.c_int, _c.c_float, _c.c_float,  # eps, sigma, dist, dist_eps, gamma
-                   _c.c_int, _c.c_int, _c.c_int, _c.c_int,       # rgb, alpha, sample, double_side
-                   _c.c_void_p]                                   # stream
+                   _c.c_int, _c.c_int, _c.c_int, _c.c_int]       # rgb, alpha, sample, double_side
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -42,17 +41,18 @@ def lib():
         L.lasr_b200_raster_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_raster_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_raster_forward.restype = _c.c_int
-        L.lasr_b200_raster_forward.argtypes = [_c.c_void_p] * 5 + [_c.c_size_t] + _RASTER_SCALARS
+        L.lasr_b200_raster_forward.argtypes = [_c.c_void_p] * 5 + [_c.c_size_t] + _RASTER_SCALARS + [_c.c_void_p]
         L.lasr_b200_raster_backward.restype = _c.c_int
-        L.lasr_b200_raster_backward.argtypes = [_c.c_void_p] * 8 + [_c.c_size_t] + _RASTER_SCALARS
+        L.lasr_b200_raster_backward.argtypes = [_c.c_void_p] * 8 + [_c.c_size_t] + _RASTER_SCALARS + [_c.c_int, _c.c_void_p]
         L.lasr_b200_render_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_render_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         _render_scalars = [_c.c_int] * 4 + [_c.c_float, _c.c_float, _c.c_void_p, _c.c_float, _c.c_float, _c.c_int,
-                                            _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
+                                            _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_render_forward.restype = _c.c_int
-        L.lasr_b200_render_forward.argtypes = [_c.c_void_p] * 6 + [_c.c_size_t] + _render_scalars
+        L.lasr_b200_render_forward.argtypes = [_c.c_void_p] * 6 + [_c.c_size_t] + _render_scalars + [_c.c_void_p]
         L.lasr_b200_render_backward.restype = _c.c_int
-        L.lasr_b200_render_backward.argtypes = [_c.c_void_p] * 11 + [_c.c_size_t] + _render_scalars
+        L.lasr_b200_render_backward.argtypes = ([_c.c_void_p] * 11 + [_c.c_size_t] + _render_scalars
+                                                + [_c.c_int, _c.c_void_p])
         L.lasr_b200_losses_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_losses_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_losses_forward.restype = _c.c_int
@@ -130,7 +130,7 @@ def raster_forward(faces, textures, aggrs_info, soft_colors, workspace, image_si
 
 def raster_backward(faces, textures, soft_colors, aggrs_info, grad_faces, grad_textures, grad_soft_colors, workspace,
                     image_size, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
-                    func_id_rgb, func_id_alpha, texture_sample_type, double_side):
+                    func_id_rgb, func_id_alpha, texture_sample_type, double_side, setup_done=False):
     for t, nm in ((faces, "faces"), (textures, "textures"), (soft_colors, "soft_colors"), (aggrs_info, "aggrs_info"),
                   (grad_faces, "grad_faces"), (grad_textures, "grad_textures"),
                   (grad_soft_colors, "grad_soft_colors")):
@@ -144,7 +144,7 @@ def raster_backward(faces, textures, soft_colors, aggrs_info, grad_faces, grad_t
             workspace.numel(), N, F, int(image_size), T, float(near), float(far),
             near_far_dev.data_ptr() if near_far_dev is not None else None, float(eps), float(sigma_val),
             int(func_id_dist), float(dist_eps), float(gamma_val), int(func_id_rgb), int(func_id_alpha),
-            int(texture_sample_type), int(bool(double_side)), _stream_ptr())
+            int(texture_sample_type), int(bool(double_side)), int(bool(setup_done)), _stream_ptr())
     _check(rc, "lasr_b200_raster_backward")
 
 
@@ -194,7 +194,7 @@ def _render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, fun
                         func_id_rgb, func_id_alpha, double_side):
     return (N, V, F, int(S), float(near), float(far), _p(near_far_dev), float(eps), float(sigma_val),
             int(func_id_dist), float(dist_eps), float(gamma_val), int(func_id_rgb), int(func_id_alpha),
-            int(bool(double_side)), _stream_ptr())
+            int(bool(double_side)))
 
 
 def render_forward(verts, tri, vcolors, aggrs_info, soft_colors, workspace, S, near, far, near_far_dev, eps,
@@ -209,13 +209,13 @@ def render_forward(verts, tri, vcolors, aggrs_info, soft_colors, workspace, S, n
         rc = lib().lasr_b200_render_forward(
             _p(verts), _p(tri), _p(vcolors), _p(aggrs_info), _p(soft_colors), _p(workspace), workspace.numel(),
             *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
-                                 gamma_val, func_id_rgb, func_id_alpha, double_side))
+                                 gamma_val, func_id_rgb, func_id_alpha, double_side), _stream_ptr())
     _check(rc, "lasr_b200_render_forward")
 
 
 def render_backward(verts, tri, vcolors, soft_colors, aggrs_info, grad_soft_colors, csr_offsets, csr_entries,
                     grad_verts, grad_vcolors, workspace, S, near, far, near_far_dev, eps, sigma_val, func_id_dist,
-                    dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side):
+                    dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side, setup_done=False):
     for t in (verts, vcolors, soft_colors, aggrs_info, grad_soft_colors, grad_verts, grad_vcolors):
         _require_cuda_f32(t, "render tensor")
     N, V = verts.shape[:2]
@@ -225,7 +225,8 @@ def render_backward(verts, tri, vcolors, soft_colors, aggrs_info, grad_soft_colo
             _p(verts), _p(tri), _p(vcolors), _p(soft_colors), _p(aggrs_info), _p(grad_soft_colors), _p(csr_offsets),
             _p(csr_entries), _p(grad_verts), _p(grad_vcolors), _p(workspace), workspace.numel(),
             *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
-                                 gamma_val, func_id_rgb, func_id_alpha, double_side))
+                                 gamma_val, func_id_rgb, func_id_alpha, double_side), int(bool(setup_done)),
+            _stream_ptr())
     _check(rc, "lasr_b200_render_backward")
 
 

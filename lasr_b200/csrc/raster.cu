@@ -63,6 +63,10 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RasterArgs A, int wit
   coord_window(g.lox, g.hix, A.S, xlo, xhi);
   coord_window(g.loy, g.hiy, A.S, ylo, yhi);
   if (xlo > xhi || ylo > yhi) { xlo = 1; xhi = 0; ylo = 1; yhi = 0; }
+  else if (with_records) {   // union of the frame's face windows: lets empty tiles skip their scan
+    int* fw = A.frame_window + 4 * (i / A.F);
+    atomicMin(fw + 0, xlo); atomicMin(fw + 1, -xhi); atomicMin(fw + 2, ylo); atomicMin(fw + 3, -yhi);
+  }
   A.face_window[i] = make_uint2((uint32_t)xlo | ((uint32_t)xhi << 16), (uint32_t)ylo | ((uint32_t)yhi << 16));
   if (!with_records) return;
   A.face_border[i] = make_float4(g.lox, g.hix, g.loy, g.hiy);
@@ -187,7 +191,10 @@ __global__ void __launch_bounds__(kFwdThreads, LASR_FWD_MIN_BLOCKS) raster_forwa
   const float4* border = A.face_border + (long long)n * A.F;
   const float* records = A.face_record + (long long)n * A.F * kRecWords;
 
-  for (int base = 0; base < A.F; base += chunk) {
+  // tiles that no face window of this frame reaches skip the scan and go straight to the epilogue
+  const int4 fwin = *reinterpret_cast<const int4*>(A.frame_window + 4 * n);
+  const bool tile_live = tx1 >= fwin.x && tx0 <= -fwin.y && ty1 >= fwin.z && ty0 <= -fwin.w;
+  for (int base = 0; tile_live && base < A.F; base += chunk) {
     // (1) scan: warp w owns faces [base + w*wseg, base + (w+1)*wseg) and compacts hits in order
     int cnt = 0;
     const int seg0 = base + warp * wseg;
@@ -286,10 +293,17 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
   const int alpha_f = kFast ? 2 : A.alpha;
   const int sample = kFast ? 1 : A.sample;
 
-  float fv[9], tex9[9];
-  fetch_face(A, n, f, fv, tex9, sample == 1);
+  float tex9[9];
   FaceGeom g;
-  face_setup(fv, sthr, g);
+  if (A.records_valid) {   // the forward's per-face record (the reference hands faces_info to its backward too)
+    load_record(A.face_record + wg * kRecWords, g, tex9);
+    const float4 bd = __ldg(A.face_border + wg);
+    g.lox = bd.x; g.hix = bd.y; g.loy = bd.z; g.hiy = bd.w;
+  } else {
+    float fv[9];
+    fetch_face(A, n, f, fv, tex9, sample == 1);
+    face_setup(fv, sthr, g);
+  }
   float* gtex_out = A.grad_textures + wg * A.T * 3;
 
   int xlo, xhi, ylo, yhi;
@@ -456,6 +470,7 @@ static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, flo
   const size_t nf = (size_t)N * F;
   A.face_window = reinterpret_cast<uint2*>(p);   p += align256(nf * sizeof(uint2));
   A.coords = reinterpret_cast<float*>(p);        p += align256((size_t)S * sizeof(float));
+  A.frame_window = reinterpret_cast<int*>(p);    p += align256((size_t)N * 4 * sizeof(int));
   A.face_border = reinterpret_cast<float4*>(p);  p += align256(nf * sizeof(float4));
   A.face_record = reinterpret_cast<float*>(p);
   return 0;
@@ -498,7 +513,8 @@ using namespace lasr;
 extern "C" size_t lasr_b200_raster_workspace_bytes(int N, int F, int S) {
   if (N <= 0 || F <= 0 || S <= 0) return 0;
   const size_t nf = (size_t)N * (size_t)F;
-  return align256(nf * sizeof(uint2)) + align256((size_t)S * sizeof(float)) + align256(nf * sizeof(float4)) +
+  return align256(nf * sizeof(uint2)) + align256((size_t)S * sizeof(float)) + align256((size_t)N * 4 * sizeof(int)) +
+         align256(nf * sizeof(float4)) +
          align256(nf * kRecWords * sizeof(float));
 }
 
@@ -517,6 +533,8 @@ extern "C" int lasr_b200_raster_forward(const float* faces, const float* texture
   cudaStream_t st = (cudaStream_t)stream;
   const long long nf = (long long)N * F;
   const long long nthreads = nf > S ? nf : S;
+  if (cudaMemsetAsync(A.frame_window, 0x7f, (size_t)N * 4 * sizeof(int), st) != cudaSuccess)
+    return fail("render_forward: memset failed");
   raster_setup_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(A, 1);
   if (check_launch("raster_setup_kernel")) return 1;
   const int tiles = ((S + kTile - 1) / kTile) * ((S + kTile - 1) / kTile);
@@ -535,11 +553,12 @@ extern "C" int lasr_b200_raster_backward(const float* faces, const float* textur
                                          int N, int F, int S, int T, float near_, float far_,
                                          const float* near_far_dev, float eps, float sigma_val, int func_id_dist,
                                          float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
-                                         int texture_sample_type, int double_side, void* stream) {
+                                         int texture_sample_type, int double_side, int setup_done, void* stream) {
   RasterArgs A{};
   if (fill_args(A, N, F, S, T, near_, far_, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
                 func_id_rgb, func_id_alpha, texture_sample_type, double_side, workspace, workspace_bytes))
     return 1;
+  A.records_valid = setup_done;
   if (!faces || !textures || !aggrs_info || !soft_colors || !grad_faces || !grad_textures || !grad_soft_colors)
     return fail("raster_backward: null tensor pointer");
   A.faces = faces; A.textures = textures;
@@ -552,7 +571,7 @@ extern "C" int lasr_b200_raster_backward(const float* faces, const float* textur
     cudaError_t e = cudaMemsetAsync(grad_textures, 0, (size_t)nf * T * 3 * sizeof(float), st);
     if (e != cudaSuccess) return fail(std::string("raster_backward memset: ") + cudaGetErrorString(e));
   }
-  {  // the backward only needs the coordinate table from the setup pass
+  if (!setup_done) {  // only the coordinate table is needed from the setup pass
     RasterArgs B = A;
     B.N = 1; B.F = 1;  // one dummy face: fills coords[0..S)
     raster_setup_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(B, 0);
@@ -597,6 +616,8 @@ extern "C" int lasr_b200_render_forward(const float* verts, const int32_t* tri, 
   cudaStream_t st = (cudaStream_t)stream;
   const long long nf = (long long)N * F;
   const long long nthreads = nf > S ? nf : S;
+  if (cudaMemsetAsync(A.frame_window, 0x7f, (size_t)N * 4 * sizeof(int), st) != cudaSuccess)
+    return fail("render_forward: memset failed");
   raster_setup_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(A, 1);
   if (check_launch("raster_setup_kernel")) return 1;
   const int tiles = ((S + kTile - 1) / kTile) * ((S + kTile - 1) / kTile);
@@ -616,12 +637,14 @@ extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri,
                                          void* workspace, size_t workspace_bytes, int N, int V, int F, int S,
                                          float near_, float far_, const float* near_far_dev, float eps,
                                          float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
-                                         int func_id_rgb, int func_id_alpha, int double_side, void* stream) {
+                                         int func_id_rgb, int func_id_alpha, int double_side, int setup_done,
+                                         void* stream) {
   RasterArgs A{};
   if (workspace_bytes < lasr_b200_render_workspace_bytes(N, F, S)) return fail("render: workspace too small");
   if (fill_args(A, N, F, S, 3, near_, far_, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
                 func_id_rgb, func_id_alpha, 1, double_side, workspace, workspace_bytes))
     return 1;
+  A.records_valid = setup_done;
   if (fill_indexed(A, verts, tri, vcolors, V)) return 1;
   if (!soft_colors || !aggrs_info || !grad_soft_colors || !csr_offsets || !csr_entries || !grad_verts || !grad_vcolors)
     return fail("render_backward: null tensor pointer");
@@ -633,7 +656,7 @@ extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri,
   A.grad_faces = reinterpret_cast<float*>(scratch);
   A.grad_textures = reinterpret_cast<float*>(scratch + align256((size_t)nf * 9 * sizeof(float)));
   cudaStream_t st = (cudaStream_t)stream;
-  {
+  if (!setup_done) {
     RasterArgs B = A;
     B.N = 1; B.F = 1;
     raster_setup_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(B, 0);

@@ -39,6 +39,8 @@ struct RasterArgs {
   float4* face_border;       // [N*F] dilated bounding boxes (lox, hix, loy, hiy)
   float* face_record;        // [N*F][kRecWords]
   float* coords;             // [S] pixel-centre coordinates
+  int records_valid;         // backward: workspace already holds the forward's setup of the same inputs
+  int* frame_window;         // [N][4] (x_lo, -x_hi, y_lo, -y_hi) of the union of face windows (atomicMin)
   const float* near_far_dev; // optional {near, far} on device
   // indexed ("fused") input mode: faces/textures are gathered on the fly from per-vertex arrays
   const float* verts;        // [N,V,3] clip-space vertices   (null: direct mode, use `faces`)

@@ -76,19 +76,18 @@ class RenderIndexedFunction(Function):
         img[:, :3] = torch.as_tensor(background_color, dtype=torch.float32, device=dev).view(1, 3, 1, 1)
         ws = _cabi.render_workspace(N, tri.shape[0], S, dev)
         _cabi.render_forward(v, tri, c, aggrs, img, ws, S, ctx.near, ctx.far, ctx.nf, *ctx.scal)
-        ctx.save_for_backward(v, c, tri, img, aggrs)
+        ctx.save_for_backward(v, c, tri, img, aggrs, ws)
         ctx.shapes = (vertices.shape, vcolors.shape)
         return img
 
     @staticmethod
     def backward(ctx, grad):
-        v, c, tri, img, aggrs = ctx.saved_tensors
+        v, c, tri, img, aggrs, ws = ctx.saved_tensors
         N, V = v.shape[:2]
         offsets, entries = vertex_adjacency(tri, V)
         gv, gc = torch.empty_like(v), torch.empty_like(c)
-        ws = _cabi.render_workspace(N, tri.shape[0], ctx.S, v.device)
         _cabi.render_backward(v, tri, c, img, aggrs, grad.float().contiguous(), offsets, entries, gv, gc, ws, ctx.S,
-                              ctx.near, ctx.far, ctx.nf, *ctx.scal)
+                              ctx.near, ctx.far, ctx.nf, *ctx.scal, setup_done=True)
         vshape, cshape = ctx.shapes
         return (gv.reshape(vshape), gc.reshape(cshape)) + (None,) * 13
 

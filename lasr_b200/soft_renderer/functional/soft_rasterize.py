@@ -69,22 +69,21 @@ class SoftRasterizeFunction(Function):
         _cabi.raster_forward(fv, tex, aggrs_info, soft_colors, workspace, S, ctx.near, ctx.far, ctx.near_far_dev,
                              eps, sigma_val, ctx.func_dist_type, ctx.dist_eps, gamma_val, ctx.func_rgb_type,
                              ctx.func_alpha_type, ctx.texture_type, ctx.fill_back)
-        ctx.save_for_backward(fv, tex, soft_colors, aggrs_info)
+        ctx.save_for_backward(fv, tex, soft_colors, aggrs_info, workspace)   # workspace plays the reference's faces_info
         return soft_colors
 
     @staticmethod
     def backward(ctx, grad_soft_colors):
-        fv, tex, soft_colors, aggrs_info = ctx.saved_tensors
+        fv, tex, soft_colors, aggrs_info, workspace = ctx.saved_tensors
         nb, nf = fv.shape[:2]
         S = ctx.image_size
         grad_faces = torch.empty_like(fv)
         grad_textures = torch.empty_like(tex)
         g = grad_soft_colors.to(torch.float32).contiguous()
-        workspace = _cabi.raster_workspace(nb, nf, S, fv.device)
         _cabi.raster_backward(fv, tex, soft_colors, aggrs_info, grad_faces, grad_textures, g, workspace, S,
                               ctx.near, ctx.far, ctx.near_far_dev, ctx.eps, ctx.sigma_val, ctx.func_dist_type,
                               ctx.dist_eps, ctx.gamma_val, ctx.func_rgb_type, ctx.func_alpha_type, ctx.texture_type,
-                              ctx.fill_back)
+                              ctx.fill_back, setup_done=True)
         fshape, tshape = ctx.in_shapes
         return (grad_faces.reshape(fshape), grad_textures.reshape(tshape)) + (None,) * 13
 

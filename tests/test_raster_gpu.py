@@ -263,3 +263,28 @@ def test_rasterizer_module_picks_indexed_path_only_for_shared_topology(srf):
     b = srf.soft_rasterize(srf.face_vertices(verts, same), srf.face_vertices(cols, same), 32, [0, 0, 0], 5, 15, True,
                            1e-3, 1e-4, "euclidean", 1e-4, 1e-2, "softmax", "prod", "vertex")
     assert torch.equal(a, b)
+
+
+def test_backward_with_reused_setup_equals_fresh_setup(srf):
+    """setup_done=1 (read the forward's per-face records) and setup_done=0 (recompute) are the same."""
+    from lasr_b200 import _cabi
+    dev = torch.device("cuda", 0)
+    c = cases.lasr_case("spot", 2, 128)
+    s = c["settings"]
+    N, F = c["face_vertices"].shape[:2]
+    S = s["image_size"]
+    fv = torch.from_numpy(c["face_vertices"]).to(dev).reshape(N, F, 9).contiguous()
+    tex = torch.from_numpy(c["textures"]).to(dev).contiguous()
+    g = torch.from_numpy(c["grad_soft_colors"]).to(dev)
+    img = torch.zeros(N, 4, S, S, device=dev)
+    agg = torch.empty(N, 2, S, S, device=dev)
+    ws = _cabi.raster_workspace(N, F, S, dev)
+    scal = (S, s["near"], s["far"], None, s["eps"], s["sigma_val"], 2, float(np.log(1 / s["dist_eps"] - 1)),
+            s["gamma_val"], 1, 2, 1, True)
+    _cabi.raster_forward(fv, tex, agg, img, ws, *scal)
+    outs = []
+    for reuse, w in ((True, ws), (False, _cabi.raster_workspace(N, F, S, dev))):
+        gf, gt = torch.empty_like(fv), torch.empty_like(tex)
+        _cabi.raster_backward(fv, tex, img, agg, gf, gt, g, w, *scal, setup_done=reuse)
+        outs.append((gf, gt))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
