@@ -101,10 +101,9 @@ __global__ void __launch_bounds__(kLbsThreads) lbs_forward_kernel(LbsArgs A) {
     co[0] = cx; co[1] = cy; co[2] = cz;
     z = cz;
     if (A.px) {
-      const float f = A.fl[n];
-      const float fz = f / cz;
+      const float f = A.fl[n];   // same operation order as the reference: pp + (x * f) / z  (geom_utils.py:32-33)
       reinterpret_cast<float4*>(A.px)[(long long)n * A.V + v] =
-          make_float4(A.pp[2 * n] + cx * fz, A.pp[2 * n + 1] + cy * fz, cz, 1.f);
+          make_float4(A.pp[2 * n] + __fdiv_rn(cx * f, cz), A.pp[2 * n + 1] + __fdiv_rn(cy * f, cz), cz, 1.f);
     }
   }
   if (A.zminmax) {

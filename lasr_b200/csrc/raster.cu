@@ -63,12 +63,26 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RasterArgs A, int wit
   coord_window(g.lox, g.hix, A.S, xlo, xhi);
   coord_window(g.loy, g.hiy, A.S, ylo, yhi);
   if (xlo > xhi || ylo > yhi) { xlo = 1; xhi = 0; ylo = 1; yhi = 0; }
-  else if (with_records) {   // union of the frame's face windows: lets empty tiles skip their scan
-    int* fw = A.frame_window + 4 * (i / A.F);
-    atomicMin(fw + 0, xlo); atomicMin(fw + 1, -xhi); atomicMin(fw + 2, ylo); atomicMin(fw + 3, -yhi);
-  }
   A.face_window[i] = make_uint2((uint32_t)xlo | ((uint32_t)xhi << 16), (uint32_t)ylo | ((uint32_t)yhi << 16));
   if (!with_records) return;
+  {  // union of the frame's face windows (lets empty tiles skip their scan): one atomic per warp, not per face
+    const int frame = (int)(i / A.F);
+    const bool live = xlo <= xhi;
+    const unsigned act = __activemask();
+    const int f0 = __shfl_sync(act, frame, __ffs(act) - 1);
+    const bool uniform = __all_sync(act, frame == f0);
+    int a = live ? xlo : 0x7f7f7f7f, b = live ? -xhi : 0x7f7f7f7f, c = live ? ylo : 0x7f7f7f7f, d = live ? -yhi : 0x7f7f7f7f;
+    int* fw = A.frame_window + 4 * frame;
+    if (uniform) {
+      a = __reduce_min_sync(act, a); b = __reduce_min_sync(act, b);
+      c = __reduce_min_sync(act, c); d = __reduce_min_sync(act, d);
+      if ((threadIdx.x & 31) == __ffs(act) - 1 && a != 0x7f7f7f7f) {
+        atomicMin(fw + 0, a); atomicMin(fw + 1, b); atomicMin(fw + 2, c); atomicMin(fw + 3, d);
+      }
+    } else if (live) {
+      atomicMin(fw + 0, a); atomicMin(fw + 1, b); atomicMin(fw + 2, c); atomicMin(fw + 3, d);
+    }
+  }
   A.face_border[i] = make_float4(g.lox, g.hix, g.loy, g.hiy);
   store_record(A.face_record + i * kRecWords, g, vertex_tex ? tex9 : nullptr);
 }

@@ -61,7 +61,7 @@ def scenario(H, B, S, bs=2, seed=0):
         ctl = torch.from_numpy(v)[idx]
         bones = dict(ctl_ts=ctl.clone(), rest_ts=ctl.clone() + 0.01,
                      ctl_rs=torch.tensor([[0.0, 0.0, 0.0, 1.0]]).repeat(H * (B - 1), 1) + torch.randn(H * (B - 1), 4, generator=g) * 0.05,
-                     log_ctl=torch.ones(H * (B - 1), 3))
+                     log_ctl=1.0 + torch.randn(H * (B - 1), 3, generator=g) * 0.5)   # anisotropic: rotation matters
     occ = torch.randn(n2, S, S, generator=g)
     occ[torch.rand(n2, S, S, generator=g) < 0.15] = 0
     batch = dict(masks=(torch.rand(n2, S, S, generator=g) > 0.4).float(), imgs=torch.rand(n2, 3, S, S, generator=g),
@@ -104,10 +104,10 @@ def test_hot_path_matches_oracle_backed_cpu_chain(monkeypatch, H, B):
     # the two chains feed the rasterizer vertices that differ in the last bit (cuBLAS-free LBS kernel vs
     # torch CPU matmul); edge-on sliver faces turn that into isolated pixel flips, so: counted outliers
     d = (gpu_out["mask_pred"] - cpu_out["mask_pred"]).abs()
-    assert (d > 1e-4).float().mean() < 2e-3 and d.max() < 0.5, (float((d > 1e-4).float().mean()), float(d.max()))
+    assert (d > 2e-3).float().mean() < 2e-3 and d.max() < 0.5, (float((d > 2e-3).float().mean()), float(d.max()))
     for k, g in cpu_grads.items():
         if g is None:
             assert gpu_grads[k] is None or float(gpu_grads[k].abs().max()) == 0.0
             continue
-        rel = (gpu_grads[k] - g).norm() / g.norm().clamp(min=1e-20)
-        assert rel < 2e-2, (k, float(rel))
+        err = (gpu_grads[k] - g).norm()
+        assert err <= 2e-2 * g.norm() + 1e-7, (k, float(err), float(g.norm()))
