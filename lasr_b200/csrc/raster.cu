@@ -44,6 +44,9 @@ constexpr int kMaxScanChunk = 12288; // faces scanned per round (48 KB of indice
 #ifndef LASR_BWD_MIN_BLOCKS
 #define LASR_BWD_MIN_BLOCKS 2
 #endif
+#ifndef LASR_BWD_THREADS
+#define LASR_BWD_THREADS 128
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // setup: one thread per face -> packed pixel window, dilated border box, full face record;
@@ -591,9 +594,10 @@ extern "C" int lasr_b200_raster_backward(const float* faces, const float* textur
     raster_setup_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(B, 0);
     if (check_launch("raster_setup_kernel")) return 1;
   }
-  const unsigned blocks = (unsigned)((nf + 7) / 8);
-  if (is_fast(A)) raster_backward_kernel<true><<<blocks, 256, 0, st>>>(A);
-  else raster_backward_kernel<false><<<blocks, 256, 0, st>>>(A);
+  constexpr int kWarpsPerBlock = LASR_BWD_THREADS / 32;
+  const unsigned blocks = (unsigned)((nf + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  if (is_fast(A)) raster_backward_kernel<true><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+  else raster_backward_kernel<false><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
   return check_launch("raster_backward_kernel");
 }
 
@@ -676,9 +680,10 @@ extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri,
     raster_setup_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(B, 0);
     if (check_launch("raster_setup_kernel")) return 1;
   }
-  const unsigned blocks = (unsigned)((nf + 7) / 8);
-  if (is_fast(A)) raster_backward_kernel<true><<<blocks, 256, 0, st>>>(A);
-  else raster_backward_kernel<false><<<blocks, 256, 0, st>>>(A);
+  constexpr int kWarpsPerBlock = LASR_BWD_THREADS / 32;
+  const unsigned blocks = (unsigned)((nf + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  if (is_fast(A)) raster_backward_kernel<true><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+  else raster_backward_kernel<false><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
   if (check_launch("raster_backward_kernel")) return 1;
   const long long nv = (long long)N * V;
   vertex_gather_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(A.grad_faces, A.grad_textures, csr_offsets,
