@@ -136,9 +136,12 @@ def measured_traffic(kernel_name):
     return None, None
 
 
-def build_workload(n_frames, S, seed):
+def build_workload(n_frames, S, seed, mesh="spot"):
     from lasr_b200 import synth
-    v, f = synth.load_spot()
+    if mesh == "spot":
+        v, f = synth.load_spot()
+    else:                       # ico4 = 2562 V / 5120 F, ico5 = 10242 V / 20480 F (BASELINE configs B, D)
+        v, f = synth.icosphere(int(mesh[3:]), 0.5)
     px, cam, near, far = synth.render_inputs(v, f, n_frames, seed)
     colors = np.repeat(synth.vertex_colors(len(v), 0)[None], n_frames, 0)
     settings = dict(image_size=S, background_color=[0, 0, 0], near=near, far=far, fill_back=True, eps=1e-3,
@@ -293,7 +296,7 @@ def run_gpu_arm(args, arm_cls):
         torch.cuda.set_device(0)
     device = torch.device("cuda", local if world > 1 else 0)
     S = args.image_size
-    wl = build_workload(args.frames, S, seed=rank)
+    wl = build_workload(args.frames, S, seed=rank, mesh=args.mesh)
     arm = arm_cls(wl, S, device)
     N, F = arm.N, arm.F
 
@@ -403,8 +406,10 @@ def run_gpu_arm(args, arm_cls):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": arm.name,
-            "config": {"workload": "BASELINE.json configs[1]: Spot 2930V/5856F, 256x256, 64 frames per GPU, "
-                                   "euclidean/prod/softmax/vertex, sigma 1e-4, gamma 1e-2",
+            "config": {"workload": ("BASELINE.json configs[1]: Spot 2930V/5856F, 256x256, 64 frames per GPU, "
+                                    "euclidean/prod/softmax/vertex, sigma 1e-4, gamma 1e-2")
+                       if (args.mesh == "spot" and S == 256 and N == 64) else
+                       f"non-headline shape: {args.mesh} {wl['verts'].shape[0]}V/{F}F, {S}x{S}, {N} frames per GPU, LASR settings",
                        "frames_per_gpu": N, "faces": F, "image_size": S, "parallelism": f"frame-shard x{world}",
                        "l2": "per-step working set ~195 MB (inputs+outputs+grads) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
@@ -438,7 +443,7 @@ def run_cpu_arm(args):
     if rank != 0:
         return
     S = args.image_size
-    wl = build_workload(args.frames, S, seed=0)
+    wl = build_workload(args.frames, S, seed=0, mesh=args.mesh)
     vals = []
     for i in range(args.warmup + args.steps):
         cb = cpu_baseline(wl, S, budget_s=max(1.0, args.cpu_budget / 2))
@@ -466,6 +471,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU")
     ap.add_argument("--image-size", type=int, default=S_DEFAULT)
+    ap.add_argument("--mesh", default="spot", choices=["spot", "ico4", "ico5"],
+                    help="non-default meshes are for the extra BASELINE.md shapes, not the headline line")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -85,4 +85,6 @@ LIVE_CASES = {
     "lasr_spot_s256_n2": lambda: lasr_case("spot", 2, 256),
     "lasr_spot_s256_n2_sig1e-5": lambda: lasr_case("spot", 2, 256, sigma=1e-5),
     "lasr_ico4_s256_n2": lambda: lasr_case("ico4", 2, 256),
+    "lasr_ico5_s512_n1": lambda: lasr_case("ico5", 1, 512),          # BASELINE config D shape (20480 faces, 512^2)
+    "lasr_ico3_s256_n2_white": lambda: lasr_case("ico3", 2, 256, bg=(1, 1, 1)),   # the shape LASR trains at
 }
