@@ -37,7 +37,7 @@ namespace lasr {
 
 constexpr int kTile = 16;           // pixels per tile side
 constexpr int kFwdThreads = 256;    // 8 warps, each an 8x4 pixel footprint
-constexpr int kMaxScanChunk = 12288; // faces scanned per round (48 KB of indices); one round if F fits
+constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indices, under the 48 KB default limit with the static smem); one round if F fits
 #ifndef LASR_FWD_MIN_BLOCKS
 #define LASR_FWD_MIN_BLOCKS 4
 #endif
