@@ -283,6 +283,69 @@ class ReferenceArm(OursArm):
         return self.ref.render_mesh_lasr(verts + self.eye[None, None], faces, colors, self.eye, self.wl["settings"])
 
 
+def extras_microbench(device, peak_gbs, iters=20):
+    """The two HBM-bound helper kernels of the path, timed alone with CUDA events (config E shape for the
+    LBS: Spot, 64 frames, 26 bones; config A shape for the losses) against their algorithmic bytes."""
+    import torch
+    from lasr_b200 import native_geom, losses, synth
+    from lasr_b200.geom_utils import quaternion_to_rotation_matrix
+    out = {}
+    g = torch.Generator().manual_seed(0)
+    v, _ = synth.load_spot()
+    N, V, B, S, H = 64, len(v), 26, 256, 1
+    verts = torch.from_numpy(v)[None].to(device).requires_grad_(True)
+    R = quaternion_to_rotation_matrix(torch.randn(N * B, 4, generator=g)).to(device).requires_grad_(True)
+    T = (torch.randn(N * B, 3, generator=g) * 0.02)
+    T.view(N, B, 3)[:, 0, 2] += 10
+    T = T.to(device).requires_grad_(True)
+    skin = torch.softmax(torch.randn(1, B - 1, V, 1, generator=g), 1).to(device).requires_grad_(True)
+    pp = torch.zeros(N, 2, device=device, requires_grad=True)
+    fl = torch.full((N,), 10.0, device=device, requires_grad=True)
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    with torch.no_grad():
+        t_f = timeit(lambda: native_geom.skin_project(verts, R, T, B, skin, pp, fl, depth_window=True))
+    cam, px, _ = native_geom.skin_project(verts, R, T, B, skin, pp, fl, depth_window=True)
+    gc, gp = torch.randn_like(cam), torch.randn_like(px)
+    t_fb = timeit(lambda: torch.autograd.grad([cam, px], [verts, R, T, skin, pp, fl], [gc, gp], retain_graph=True))
+    lbs_fwd_bytes = V * 12 + (B - 1) * V * 4 + N * (B * 48 + 12) + N * V * 28       # shared mesh+skin in, cam+px out
+    lbs_bwd_bytes = V * 12 + (B - 1) * V * 4 + N * B * 48 + N * V * 28 + N * V * 12 + N * (B - 1) * V * 4
+    out["lbs_project"] = {"shape": f"N={N} V={V} B={B} (shared mesh + weights)", "forward_ms": t_f, "backward_ms": t_fb,
+                          "forward_GBps": lbs_fwd_bytes / t_f / 1e6, "backward_GBps": lbs_bwd_bytes / t_fb / 1e6,
+                          "forward_frac_of_hbm_peak": lbs_fwd_bytes / t_f / 1e6 / peak_gbs,
+                          "backward_frac_of_hbm_peak": lbs_bwd_bytes / t_fb / 1e6 / peak_gbs,
+                          "note": "backward includes the per-frame -> shared reductions done by torch.sum"}
+    mk = lambda *sh: torch.rand(*sh, generator=g).to(device)
+    mp, fg, tex = mk(N, H, S, S).requires_grad_(True), mk(N, H, S, S).requires_grad_(True), mk(N, H, 3, S, S).requires_grad_(True)
+    fr = (torch.randn(N, H, S, S, 2, generator=g) * 0.05).to(device).requires_grad_(True)
+    masks, occ = (mk(N, S, S) > 0.5).float(), torch.randn(N, S, S, generator=g).to(device)
+    bg, fo, imgs = mk(N, H, S, S) < 0.4, mk(N, 3, S, S), mk(N, 3, S, S)
+    with torch.no_grad():
+        t_lf = timeit(lambda: losses.image_losses(mp, masks, occ, fr, bg, fo, tex, fg, imgs))
+    lm, lf, lt, _ = losses.image_losses(mp, masks, occ, fr, bg, fo, tex, fg, imgs)
+    t_lb = timeit(lambda: torch.autograd.grad(lm + lf + lt, [mp, fr, tex, fg], retain_graph=True))
+    px_n = N * H * S * S
+    loss_fwd_bytes = px_n * (4 + 8 + 1 + 12 + 4) + N * S * S * (12 + 4 + 4 + 8)
+    loss_bwd_bytes = loss_fwd_bytes + px_n * (4 + 8 + 12 + 4)
+    out["image_losses"] = {"shape": f"N={N} H={H} S={S}", "forward_ms": t_lf, "backward_ms": t_lb,
+                           "forward_GBps": loss_fwd_bytes / t_lf / 1e6, "backward_GBps": loss_bwd_bytes / t_lb / 1e6,
+                           "forward_frac_of_hbm_peak": loss_fwd_bytes / t_lf / 1e6 / peak_gbs,
+                           "backward_frac_of_hbm_peak": loss_bwd_bytes / t_lb / 1e6 / peak_gbs,
+                           "note": "includes the [N,H]-sized PyTorch arithmetic from sums to losses and its autograd"}
+    return out
+
+
 def run_gpu_arm(args, arm_cls):
     import torch
     rank, world, local = dist_env()
@@ -429,6 +492,8 @@ def run_gpu_arm(args, arm_cls):
                                  "section 4); measured DRAM traffic is below the algorithmic bytes because the images the "
                                  "forward just wrote are still L2-resident"},
         }
+        if world == 1 and arm.name == "ours" and args.extras:
+            out["extras"] = extras_microbench(device, peak)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(wl, S, args.cpu_budget)
         print(json.dumps(out), flush=True)
@@ -476,6 +541,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="also time the LBS/projection and image-loss kernels alone")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
