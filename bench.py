@@ -408,29 +408,39 @@ def run_gpu_arm(args, arm_cls):
         from lasr_b200.pipeline import HostPrefetcher
         prefetch = HostPrefetcher(device)
 
+    def compute(verts_buf, colors_buf, faces, target):
+        verts = verts_buf.detach().requires_grad_(True)
+        colors = colors_buf.detach().requires_grad_(True)
+        img = arm.render(verts, faces, colors)
+        loss = 0.5 * (img - target).pow(2).mean()
+        loss.backward()
+        # the mesh is shared by the frames: sum per-frame gradients
+        return loss.detach().reshape(1), verts.grad.sum(0), colors.grad.sum(0)
+
+    graphs = {}
+
     def e2e_step():
         if prefetch is not None:
             if prefetch.staged == 0:
                 prefetch.stage(host_inputs)
-            d_verts, d_colors, faces, target = prefetch.get()
+            bufs = prefetch.get()
             prefetch.stage(host_inputs)                       # next step's inputs, on the copy stream
-            verts = d_verts.detach().requires_grad_(True)
-            colors = d_colors.detach().requires_grad_(True)
+            if args.no_graph:
+                loss, gv, gc = compute(*bufs)
+            else:                                             # one CUDA graph per staging slot (static addresses)
+                key = bufs[0].data_ptr()
+                if key not in graphs:
+                    from lasr_b200.pipeline import GraphedStep
+                    graphs[key] = GraphedStep(compute, bufs)
+                loss, gv, gc = graphs[key]()
         else:
-            verts = h_verts.to(device, non_blocking=True).requires_grad_(True)
-            colors = h_colors.to(device, non_blocking=True).requires_grad_(True)
-            faces = h_faces.to(device, non_blocking=True)
-            target = h_target.to(device, non_blocking=True)
-        img = arm.render(verts, faces, colors)
-        loss = 0.5 * (img - target).pow(2).mean()
-        loss.backward()
-        gv = verts.grad.sum(0)      # the mesh is shared by the frames: sum per-frame gradients
-        gc = colors.grad.sum(0)
+            loss, gv, gc = compute(h_verts.to(device, non_blocking=True), h_colors.to(device, non_blocking=True),
+                                   h_faces.to(device, non_blocking=True), h_target.to(device, non_blocking=True))
         if dist is not None:        # one flat bucket, one all-reduce
             flat = torch.cat([gv.reshape(-1), gc.reshape(-1)])
             dist.all_reduce(flat)
             gv, gc = flat[:gv.numel()].view_as(gv), flat[gv.numel():].view_as(gc)
-        h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        h_loss.copy_(loss, non_blocking=True)
         h_gv.copy_(gv, non_blocking=True)
         h_gc.copy_(gc, non_blocking=True)
         if prefetch is not None:
@@ -478,7 +488,8 @@ def run_gpu_arm(args, arm_cls):
             "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "api": "SoftRenderer.render_mesh + autograd, L2 image loss, pinned host buffers"
-                           + (", H2D of step i+1 overlapped with step i (HostPrefetcher)" if arm.name == "ours" else "")},
+                           + (", H2D of step i+1 overlapped with step i (HostPrefetcher)" if arm.name == "ours" else "")
+                           + (", step replayed as a CUDA graph (GraphedStep)" if (arm.name == "ours" and not args.no_graph) else "")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "kernels": {"forward_ms": fwd_ms, "backward_ms": bwd_ms,
@@ -541,6 +552,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="e2e: launch kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--extras", action="store_true", help="also time the LBS/projection and image-loss kernels alone")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

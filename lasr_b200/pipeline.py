@@ -51,3 +51,31 @@ class HostPrefetcher:
         slot["free"].record(torch.cuda.current_stream(self.device))
         self.tail = (self.tail + 1) % self.depth
         self.staged -= 1
+
+
+class GraphedStep:
+    """A whole render step (forward, loss, backward, gradient reduction) captured once into a CUDA graph
+    and replayed, so the ~40 kernel launches of a step cost one launch.  Shapes are static in LASR's
+    optimisation loop (fixed batch, mesh and image size), which is exactly the case CUDA graphs serve.
+
+    ``fn(*static_inputs)`` must do everything on the current stream, allocate only through PyTorch, read
+    its inputs from the given device tensors (the same storage at every replay) and return a tuple of
+    tensors; ``GraphedStep(...)()`` replays and returns those (static) output tensors."""
+
+    def __init__(self, fn, static_inputs, warmup: int = 3):
+        self.static_inputs = list(static_inputs)
+        dev = self.static_inputs[0].device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                     # warm-up off the capture stream (PyTorch's recipe)
+            for _ in range(warmup):
+                fn(*self.static_inputs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = fn(*self.static_inputs)
+
+    def __call__(self):
+        self.graph.replay()
+        return self.outputs

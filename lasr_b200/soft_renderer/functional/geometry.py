@@ -44,9 +44,23 @@ def vertex_normals(vertices, faces):
     return F.normalize(normals, eps=1e-6, dim=1).reshape(bs, nv, 3)
 
 
+_const_cache = {}
+
+
+def _const(values, device):
+    """Small constant vectors (eye / at / up / colours given as Python lists) are uploaded once per
+    (value, device) and reused: no host->device copy inside the step, so it can be CUDA-graph captured."""
+    key = (tuple(float(v) for v in values), str(device))
+    t = _const_cache.get(key)
+    if t is None:
+        t = torch.tensor(list(key[0]), dtype=torch.float32, device=device)
+        _const_cache[key] = t
+    return t
+
+
 def _as_batch(x, batch_size, device):
     if isinstance(x, (list, tuple)):
-        x = torch.tensor(x, dtype=torch.float32, device=device)
+        x = _const(x, device)
     elif isinstance(x, np.ndarray):
         x = torch.from_numpy(x).to(device)
     elif torch.is_tensor(x):
@@ -123,7 +137,7 @@ def get_points_from_angles(distance, elevation, azimuth, degrees=True):
 
 def _color(c, device):
     if isinstance(c, (tuple, list)):
-        c = torch.tensor(c, dtype=torch.float32, device=device)
+        c = _const(c, device)
     elif isinstance(c, np.ndarray):
         c = torch.from_numpy(c).float().to(device)
     return c[None, :] if c.ndimension() == 1 else c

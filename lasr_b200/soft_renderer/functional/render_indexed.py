@@ -73,7 +73,8 @@ class RenderIndexedFunction(Function):
         ctx.S = S
         aggrs = torch.empty(N, 2, S, S, dtype=torch.float32, device=dev)
         img = torch.empty(N, 4, S, S, dtype=torch.float32, device=dev)
-        img[:, :3] = torch.as_tensor(background_color, dtype=torch.float32, device=dev).view(1, 3, 1, 1)
+        for k in range(3):
+            img[:, k].fill_(float(background_color[k]))       # fills, not an H2D copy: CUDA-graph safe
         ws = _cabi.render_workspace(N, tri.shape[0], S, dev)
         _cabi.render_forward(v, tri, c, aggrs, img, ws, S, ctx.near, ctx.far, ctx.nf, *ctx.scal)
         ctx.save_for_backward(v, c, tri, img, aggrs, ws)

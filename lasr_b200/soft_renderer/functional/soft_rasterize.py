@@ -63,8 +63,8 @@ class SoftRasterizeFunction(Function):
         S = ctx.image_size
         aggrs_info = torch.empty(nb, 2, S, S, dtype=torch.float32, device=device)
         soft_colors = torch.empty(nb, 4, S, S, dtype=torch.float32, device=device)
-        bg = torch.as_tensor(background_color, dtype=torch.float32, device=device).reshape(3)
-        soft_colors[:, :3] = bg.view(1, 3, 1, 1)      # the kernel reads the background from here
+        for k in range(3):                            # the kernel reads the background from here
+            soft_colors[:, k].fill_(float(background_color[k]))   # (fills, not an H2D copy: CUDA-graph safe)
         workspace = _cabi.raster_workspace(nb, nf, S, device)
         _cabi.raster_forward(fv, tex, aggrs_info, soft_colors, workspace, S, ctx.near, ctx.far, ctx.near_far_dev,
                              eps, sigma_val, ctx.func_dist_type, ctx.dist_eps, gamma_val, ctx.func_rgb_type,
