@@ -186,6 +186,15 @@ int lasr_b200_losses_backward(const float* mask_pred, const float* flow_rd, cons
                               float* grad_mask_pred, float* grad_flow_rd, float* grad_tex, float* grad_fg,
                               int num_frames, int num_hypotheses, int image_size, void* stream);
 
+/* sums [N,H,7] -> sub [3][N*H] (per-pair mask / flow / texture losses) and out3 [3] (their means), the
+ * scalar arithmetic of mesh_net.py:388-390, 404-416, 440-445 in one tiny kernel; and its adjoint:
+ * grad_out3 [3] (+ optional grad_sub [3][N*H]) -> grad_sums [N,H,7] for lasr_b200_losses_backward. */
+int lasr_b200_losses_finalize(const float* sums, float* sub, float* out3, int num_frames, int num_hypotheses,
+                              float l1tex_wt, void* stream);
+int lasr_b200_losses_coefficients(const float* sums, const float* grad_out3, const float* grad_sub,
+                                  float* grad_sums, int num_frames, int num_hypotheses, float l1tex_wt,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

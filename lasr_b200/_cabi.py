@@ -59,6 +59,10 @@ def lib():
         L.lasr_b200_losses_forward.argtypes = [_c.c_void_p] * 11 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
         L.lasr_b200_losses_backward.restype = _c.c_int
         L.lasr_b200_losses_backward.argtypes = [_c.c_void_p] * 14 + [_c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
+        L.lasr_b200_losses_finalize.restype = _c.c_int
+        L.lasr_b200_losses_finalize.argtypes = [_c.c_void_p] * 3 + [_c.c_int, _c.c_int, _c.c_float, _c.c_void_p]
+        L.lasr_b200_losses_coefficients.restype = _c.c_int
+        L.lasr_b200_losses_coefficients.argtypes = [_c.c_void_p] * 4 + [_c.c_int, _c.c_int, _c.c_float, _c.c_void_p]
         L.lasr_b200_lbs_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_lbs_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_lbs_project_forward.restype = _c.c_int
@@ -74,6 +78,7 @@ EXPORTED_SYMBOLS = [
     "lasr_b200_raster_workspace_bytes", "lasr_b200_raster_forward", "lasr_b200_raster_backward",
     "lasr_b200_render_workspace_bytes", "lasr_b200_render_forward", "lasr_b200_render_backward",
     "lasr_b200_losses_workspace_bytes", "lasr_b200_losses_forward", "lasr_b200_losses_backward",
+    "lasr_b200_losses_finalize", "lasr_b200_losses_coefficients",
     "lasr_b200_lbs_workspace_bytes", "lasr_b200_lbs_project_forward", "lasr_b200_lbs_project_backward",
 ]
 
@@ -246,3 +251,16 @@ def losses_backward(mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_
                                              _p(masks), _p(occ), _p(flow_obs), _p(grad_sums), _p(g_mask_pred),
                                              _p(g_flow_rd), _p(g_tex), _p(g_fg), N, H, S, _stream_ptr())
     _check(rc, "lasr_b200_losses_backward")
+
+
+def losses_finalize(sums, sub, out3, N, H, l1tex_wt):
+    with torch.cuda.device(sums.device):
+        rc = lib().lasr_b200_losses_finalize(_p(sums), _p(sub), _p(out3), N, H, float(l1tex_wt), _stream_ptr())
+    _check(rc, "lasr_b200_losses_finalize")
+
+
+def losses_coefficients(sums, g3, gsub, gsums, N, H, l1tex_wt):
+    with torch.cuda.device(sums.device):
+        rc = lib().lasr_b200_losses_coefficients(_p(sums), _p(g3), _p(gsub), _p(gsums), N, H, float(l1tex_wt),
+                                                 _stream_ptr())
+    _check(rc, "lasr_b200_losses_coefficients")

@@ -4,9 +4,10 @@
 // double loops over (frame, hypothesis): boolean-mask indexing + .mean() per pair and a host
 // synchronisation per pair (`if mask[i,j].sum()==0`, :412) -- 2bs*H tiny kernels and syncs per loss.
 // Here ONE pass over the images produces, per (frame i, hypothesis j), the six masked sums all three
-// losses are made of; the few scalar operations that turn sums into losses stay in PyTorch on
-// [N,H]-sized tensors (lasr_b200/losses.py), which also gives their autograd for free.  The backward
-// kernel turns the gradients of the sums into per-pixel gradients in one elementwise pass.
+// losses are made of; a one-block kernel turns sums into the per-pair losses and their means
+// (losses_finalize_kernel) and its adjoint turns upstream gradients into gradients of the sums
+// (losses_coef_kernel); the backward kernel then produces per-pixel gradients in one elementwise pass.
+// (lasr_b200/losses.py also offers the three losses separately with the scalar step in PyTorch.)
 //
 //   v  = occ != 0                      (pixel inside the original frame)
 //   k  = !bgmask & v & (mask > 0)      (flow visibility)
@@ -180,6 +181,67 @@ __global__ void __launch_bounds__(kLossThreads) losses_backward_kernel(LossArgs 
   }
 }
 
+// sums [N,H,7] -> per-(frame,hypothesis) losses sub[3][N*H] (mask, flow, texture) and their means
+// out3[3], following nnutils/mesh_net.py:388-390, 404-416, 440-445.  One block; fixed-order reduction.
+__global__ void __launch_bounds__(256) losses_finalize_kernel(const float* sums, int N, int H, float l1tex_wt,
+                                                              float* sub, float* out3) {
+  __shared__ float s_b[64], s_c[64];   // per-frame partial sums of B and C are recomputed per thread; smem for means
+  __shared__ float s_red[3][256 / 32];
+  const int NH = N * H;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int t = threadIdx.x; t < NH; t += blockDim.x) {
+    const int i = t / H;
+    const float* q = sums + (long long)t * kNumSums;
+    const float V = q[6];
+    float Bs = 0.f, Cs = 0.f;
+    for (int j = 0; j < H; ++j) { Bs += sums[((long long)i * H + j) * kNumSums + 2]; Cs += sums[((long long)i * H + j) * kNumSums + 3]; }
+    const float m = 0.5f * q[0] / V;
+    const float wmean = Bs / Cs;
+    const float f = q[3] == 0.f ? 0.f : 0.5f * q[1] / wmean / q[3];
+    const float x = 0.25f * ((q[4] + q[5]) / V * 2.f * l1tex_wt);
+    sub[t] = m; sub[NH + t] = f; sub[2 * NH + t] = x;
+    acc[0] += m; acc[1] += f; acc[2] += x;
+  }
+  (void)s_b; (void)s_c;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float w = wsum(acc[k]);
+    if (lane == 0) s_red[k][warp] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[threadIdx.x][w];
+    out3[threadIdx.x] = t / (float)NH;
+  }
+}
+
+// upstream gradients of the three means (g3[3]) and of the per-pair losses (gsub[3][N*H], may be null)
+// -> gradient of every sum (only sums 0, 1, 4, 5 carry gradient to the images)
+__global__ void losses_coef_kernel(const float* sums, const float* g3, const float* gsub, int N, int H,
+                                   float l1tex_wt, float* gsums) {
+  const int NH = N * H;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= NH) return;
+  const int i = t / H;
+  const float* q = sums + (long long)t * kNumSums;
+  const float V = q[6];
+  float Bs = 0.f, Cs = 0.f;
+  for (int j = 0; j < H; ++j) { Bs += sums[((long long)i * H + j) * kNumSums + 2]; Cs += sums[((long long)i * H + j) * kNumSums + 3]; }
+  const float inv = 1.f / (float)NH;
+  const float gm = g3[0] * inv + (gsub ? gsub[t] : 0.f);
+  const float gf = g3[1] * inv + (gsub ? gsub[NH + t] : 0.f);
+  const float gx = g3[2] * inv + (gsub ? gsub[2 * NH + t] : 0.f);
+  float* o = gsums + (long long)t * kNumSums;
+  o[0] = gm * 0.5f / V;
+  o[1] = q[3] == 0.f ? 0.f : gf * 0.5f / (Bs / Cs) / q[3];
+  o[2] = 0.f; o[3] = 0.f;
+  o[4] = gx * 0.5f * l1tex_wt / V;
+  o[5] = o[4];
+  o[6] = 0.f;
+}
+
 static int fill_loss(LossArgs& A, const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
                      const float* tex, const float* fg, const float* imgs, const float* masks, const float* occ,
                      const float* flow_obs, int N, int H, int S) {
@@ -235,4 +297,20 @@ extern "C" int lasr_b200_losses_backward(const float* mask_pred, const float* fl
   losses_backward_kernel<<<dim3((A.SS + kLossThreads - 1) / kLossThreads, N * H), kLossThreads, 0, st>>>(
       A, grad_sums, grad_mask_pred, grad_flow_rd, grad_tex, grad_fg);
   return lasr_check_launch("losses_backward_kernel");
+}
+
+extern "C" int lasr_b200_losses_finalize(const float* sums, float* sub, float* out3, int N, int H, float l1tex_wt,
+                                         void* stream) {
+  if (!sums || !sub || !out3 || N <= 0 || H <= 0) return lasr_fail("losses_finalize: bad arguments");
+  losses_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums, N, H, l1tex_wt, sub, out3);
+  return lasr_check_launch("losses_finalize_kernel");
+}
+
+extern "C" int lasr_b200_losses_coefficients(const float* sums, const float* grad_out3, const float* grad_sub,
+                                             float* grad_sums, int N, int H, float l1tex_wt, void* stream) {
+  if (!sums || !grad_out3 || !grad_sums || N <= 0 || H <= 0) return lasr_fail("losses_coefficients: bad arguments");
+  const int NH = N * H;
+  losses_coef_kernel<<<(NH + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, grad_out3, grad_sub, N, H, l1tex_wt,
+                                                                         grad_sums);
+  return lasr_check_launch("losses_coef_kernel");
 }

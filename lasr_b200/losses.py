@@ -47,6 +47,46 @@ class _LossSums(Function):
         return g_mp, g_fr, None, (g_tx if need[3] else None), g_fg, None, None, None, None
 
 
+class _FusedImageLosses(Function):
+    """All three losses in four launches forward (sums, reduce, finalize) and three backward
+    (coefficients, per-pixel gradients): no [N,H]-sized PyTorch arithmetic, no autograd graph of tiny ops."""
+
+    @staticmethod
+    def forward(ctx, mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs, l1tex_wt):
+        from . import _cabi
+        N, H, S = mask_pred.shape[0], mask_pred.shape[1], mask_pred.shape[-1]
+        c = lambda t: t.detach().float().contiguous()
+        mp, fr, tx, fgc, im, mk, oc, fo = (c(t) for t in (mask_pred, flow_rd, tex, fg, imgs, masks, occ, flow_obs))
+        bg = bgmask.detach().to(torch.uint8).contiguous()
+        dev = mask_pred.device
+        sums = torch.empty(N, H, 7, dtype=torch.float32, device=dev)
+        _cabi.losses_forward(mp, fr, bg, tx, fgc, im, mk, oc, fo, sums, N, H, S)
+        sub = torch.empty(3, N, H, dtype=torch.float32, device=dev)
+        out3 = torch.empty(3, dtype=torch.float32, device=dev)
+        _cabi.losses_finalize(sums, sub, out3, N, H, l1tex_wt)
+        ctx.save_for_backward(mp, fr, bg, tx, fgc, im, mk, oc, fo, sums)
+        ctx.dims = (N, H, S, float(l1tex_wt))
+        return out3, sub
+
+    @staticmethod
+    def backward(ctx, g_out3, g_sub):
+        from . import _cabi
+        mp, fr, bg, tx, fgc, im, mk, oc, fo, sums = ctx.saved_tensors
+        N, H, S, wt = ctx.dims
+        dev = mp.device
+        g3 = torch.zeros(3, device=dev) if g_out3 is None else g_out3.float().contiguous()
+        gsub = None if g_sub is None else g_sub.float().contiguous()
+        gsums = torch.empty_like(sums)
+        _cabi.losses_coefficients(sums, g3, gsub, gsums, N, H, wt)
+        need = ctx.needs_input_grad
+        g_mp = torch.empty_like(mp) if need[0] else None
+        g_fr = torch.empty_like(fr) if need[1] else None
+        g_tx = torch.empty_like(tx) if (need[3] or need[4]) else None
+        g_fg = torch.empty_like(fgc) if need[4] else None
+        _cabi.losses_backward(mp, fr, bg, tx, fgc, im, mk, oc, fo, gsums, g_mp, g_fr, g_tx, g_fg, N, H, S)
+        return g_mp, g_fr, None, (g_tx if need[3] else None), g_fg, None, None, None, None, None
+
+
 def _native(t):
     return t.is_cuda
 
@@ -118,12 +158,9 @@ def texture_l1_loss(texture_render, fgmask, imgs, masks, occ, l1tex_wt=1.0):
 
 def image_losses(mask_pred, masks, occ, flow_rd, bgmask, flow_obs, texture_render, fgmask, imgs, l1tex_wt=1.0):
     """All three losses from ONE fused pass (CUDA tensors): returns (mask_loss, flow_loss, texture_loss,
-    per-(frame,hypothesis) dict).  Values equal mask_loss / flow_loss / texture_l1_loss."""
-    q = _sums(mask_pred, masks, occ, flow_rd, bgmask, flow_obs, texture_render, fgmask, imgs)
-    V = q[..., 6]
-    m_sub = 0.5 * q[..., 0] / V
-    A, B, C = q[..., 1], q[..., 2], q[..., 3]
-    wmean = B.sum(1, keepdim=True) / C.sum(1, keepdim=True)
-    f_sub = 0.5 * torch.where(C == 0, torch.zeros_like(A), A / wmean / C.clamp(min=1))
-    t_sub = 0.25 * ((q[..., 4] + q[..., 5]) / V * 2 * l1tex_wt)
-    return m_sub.mean(), f_sub.mean(), t_sub.mean(), dict(mask=m_sub, flow=f_sub, texture=t_sub)
+    per-(frame,hypothesis) dict).  Values equal mask_loss / flow_loss / texture_l1_loss.  If the
+    silhouette and the texture foreground mask are the same tensor (LASR: both are the rendered alpha,
+    mesh_net.py:358-359) their gradients are summed by autograd as usual."""
+    out3, sub = _FusedImageLosses.apply(mask_pred, flow_rd, bgmask, texture_render, fgmask, imgs, masks, occ,
+                                        flow_obs, l1tex_wt)
+    return out3[0], out3[1], out3[2], dict(mask=sub[0], flow=sub[1], texture=sub[2])
