@@ -185,7 +185,6 @@ __global__ void __launch_bounds__(kLossThreads) losses_backward_kernel(LossArgs 
 // out3[3], following nnutils/mesh_net.py:388-390, 404-416, 440-445.  One block; fixed-order reduction.
 __global__ void __launch_bounds__(256) losses_finalize_kernel(const float* sums, int N, int H, float l1tex_wt,
                                                               float* sub, float* out3) {
-  __shared__ float s_b[64], s_c[64];   // per-frame partial sums of B and C are recomputed per thread; smem for means
   __shared__ float s_red[3][256 / 32];
   const int NH = N * H;
   float acc[3] = {0.f, 0.f, 0.f};
@@ -202,7 +201,6 @@ __global__ void __launch_bounds__(256) losses_finalize_kernel(const float* sums,
     sub[t] = m; sub[NH + t] = f; sub[2 * NH + t] = x;
     acc[0] += m; acc[1] += f; acc[2] += x;
   }
-  (void)s_b; (void)s_c;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {

@@ -35,8 +35,13 @@
 
 namespace lasr {
 
-constexpr int kTile = 16;           // pixels per tile side
-constexpr int kFwdThreads = 256;    // 8 warps, each an 8x4 pixel footprint
+#ifndef LASR_TILE_H
+#define LASR_TILE_H 16
+#endif
+constexpr int kTileW = 16;                      // tile width in pixels (two 8x4 warp footprints)
+constexpr int kTileH = LASR_TILE_H;             // tile height in pixels (multiple of 4)
+constexpr int kFwdWarps = 2 * (kTileH / 4);     // each warp owns an 8x4 pixel footprint
+constexpr int kFwdThreads = 32 * kFwdWarps;
 constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indices, under the 48 KB default limit with the static smem); one round if F fits
 #ifndef LASR_FWD_MIN_BLOCKS
 #define LASR_FWD_MIN_BLOCKS 4
@@ -157,16 +162,16 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConst
 template <bool kFast>
 __global__ void __launch_bounds__(kFwdThreads, LASR_FWD_MIN_BLOCKS) raster_forward_kernel(RasterArgs A, int chunk) {
   extern __shared__ int s_list[];   // [chunk] face indices, 8 per-warp segments of chunk/8
-  __shared__ int s_cnt[8];
-  const int wseg = chunk >> 3;
+  __shared__ int s_cnt[kFwdWarps];
+  const int wseg = chunk / kFwdWarps;
 
   const int S = A.S;
-  const int tiles_x = (S + kTile - 1) / kTile;
+  const int tiles_x = (S + kTileW - 1) / kTileW;
   const int tile_x = blockIdx.x % tiles_x;
   const int tile_y = blockIdx.x / tiles_x;
   const int n = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wx0 = tile_x * kTile + (warp & 1) * 8, wy0 = tile_y * kTile + (warp >> 1) * 4;
+  const int wx0 = tile_x * kTileW + (warp & 1) * 8, wy0 = tile_y * kTileH + (warp >> 1) * 4;
   const int px = wx0 + (lane & 7);
   const int py = wy0 + (lane >> 3);  // row from the top
   const bool valid = px < S && py < S;
@@ -201,8 +206,8 @@ __global__ void __launch_bounds__(kFwdThreads, LASR_FWD_MIN_BLOCKS) raster_forwa
   const float fy1 = A.coords[max(S - 1 - wy0, 0)];
   const float fy0 = A.coords[max(S - 1 - (wy0 + 3), 0)];
   // tile window in pixel indices (x index, y index = S-1-row)
-  const int tx0 = tile_x * kTile, tx1 = tx0 + kTile - 1;
-  const int ty1 = S - 1 - tile_y * kTile, ty0 = ty1 - (kTile - 1);
+  const int tx0 = tile_x * kTileW, tx1 = tx0 + kTileW - 1;
+  const int ty1 = S - 1 - tile_y * kTileH, ty0 = ty1 - (kTileH - 1);
 
   const uint2* win = A.face_window + (long long)n * A.F;
   const float4* border = A.face_border + (long long)n * A.F;
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(kFwdThreads, LASR_FWD_MIN_BLOCKS) raster_forwa
     // (2) every warp walks the whole ordered list on its own: cull 32 faces per ballot against
     //     its 8x4 footprint, evaluate survivors in ascending face order.  No further barriers.
 #pragma unroll 1
-    for (int seg = 0; seg < 8; ++seg) {
+    for (int seg = 0; seg < kFwdWarps; ++seg) {
       const int nseg = s_cnt[seg];
       const int* lst = s_list + seg * wseg;
 #pragma unroll 1
@@ -554,10 +559,10 @@ extern "C" int lasr_b200_raster_forward(const float* faces, const float* texture
     return fail("render_forward: memset failed");
   raster_setup_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(A, 1);
   if (check_launch("raster_setup_kernel")) return 1;
-  const int tiles = ((S + kTile - 1) / kTile) * ((S + kTile - 1) / kTile);
+  const int tiles = ((S + kTileW - 1) / kTileW) * ((S + kTileH - 1) / kTileH);
   dim3 grid(tiles, N);
-  int chunk = ((F + 255) / 256) * 256;
-  if (chunk > kMaxScanChunk) chunk = kMaxScanChunk;
+  int chunk = ((F + kFwdThreads - 1) / kFwdThreads) * kFwdThreads;   // a multiple of 32 faces per warp
+  if (chunk > kMaxScanChunk) chunk = (kMaxScanChunk / kFwdThreads) * kFwdThreads;
   const size_t smem = (size_t)chunk * sizeof(int);
   if (is_fast(A)) raster_forward_kernel<true><<<grid, kFwdThreads, smem, st>>>(A, chunk);
   else raster_forward_kernel<false><<<grid, kFwdThreads, smem, st>>>(A, chunk);
@@ -638,10 +643,10 @@ extern "C" int lasr_b200_render_forward(const float* verts, const int32_t* tri, 
     return fail("render_forward: memset failed");
   raster_setup_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(A, 1);
   if (check_launch("raster_setup_kernel")) return 1;
-  const int tiles = ((S + kTile - 1) / kTile) * ((S + kTile - 1) / kTile);
+  const int tiles = ((S + kTileW - 1) / kTileW) * ((S + kTileH - 1) / kTileH);
   dim3 grid(tiles, N);
-  int chunk = ((F + 255) / 256) * 256;
-  if (chunk > kMaxScanChunk) chunk = kMaxScanChunk;
+  int chunk = ((F + kFwdThreads - 1) / kFwdThreads) * kFwdThreads;   // a multiple of 32 faces per warp
+  if (chunk > kMaxScanChunk) chunk = (kMaxScanChunk / kFwdThreads) * kFwdThreads;
   const size_t smem = (size_t)chunk * sizeof(int);
   if (is_fast(A)) raster_forward_kernel<true><<<grid, kFwdThreads, smem, st>>>(A, chunk);
   else raster_forward_kernel<false><<<grid, kFwdThreads, smem, st>>>(A, chunk);
