@@ -140,7 +140,7 @@ def build_workload(n_frames, S, seed, mesh="spot"):
     from lasr_b200 import synth
     if mesh == "spot":
         v, f = synth.load_spot()
-    else:                       # ico4 = 2562 V / 5120 F, ico5 = 10242 V / 20480 F (BASELINE configs B, D)
+    else:   # ico3 = 642 V / 1280 F (what LASR trains at), ico4 = 2562 / 5120, ico5 = 10242 / 20480 (BASELINE B, D)
         v, f = synth.icosphere(int(mesh[3:]), 0.5)
     px, cam, near, far = synth.render_inputs(v, f, n_frames, seed)
     colors = np.repeat(synth.vertex_colors(len(v), 0)[None], n_frames, 0)
@@ -548,7 +548,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU")
     ap.add_argument("--image-size", type=int, default=S_DEFAULT)
-    ap.add_argument("--mesh", default="spot", choices=["spot", "ico4", "ico5"],
+    ap.add_argument("--mesh", default="spot", choices=["spot", "ico3", "ico4", "ico5"],
                     help="non-default meshes are for the extra BASELINE.md shapes, not the headline line")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")

@@ -5,9 +5,9 @@ TAG=${1:-r1}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 python -m pytest tests -q -m gpu > $OUT/pytest_gpu.log 2>&1; tail -3 $OUT/pytest_gpu.log
-python bench.py --steps 50 --warmup 5 > $OUT/bench_ours.json 2> $OUT/bench_ours.err
+python bench.py --steps 50 --warmup 5 --extras > $OUT/bench_ours.json 2> $OUT/bench_ours.err
 python bench.py --impl reference --steps 10 --warmup 3 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
-for cfg in "ico4 256 64" "ico5 512 32"; do set -- $cfg
+for cfg in "ico3 256 64" "ico4 256 64" "ico5 512 32"; do set -- $cfg
   python bench.py --mesh $1 --image-size $2 --frames $3 --steps 20 --warmup 3 --no-cpu-baseline --e2e-steps 5 > $OUT/bench_ours_$1_$2.json 2>> $OUT/bench_ours.err
   python bench.py --impl reference --mesh $1 --image-size $2 --frames $3 --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 3 > $OUT/bench_ref_$1_$2.json 2>> $OUT/bench_ref.err
 done

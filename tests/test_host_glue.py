@@ -176,3 +176,107 @@ def test_flow_postprocessing_matches_oracle(oracle):
     q0, q1 = torch.where(bg[..., None], ten, p0), torch.where(bg[..., None], ten, p1)
     flow = gu._reproject(q1, pp1, f1) - gu._reproject(q0, pp0, f0)
     assert np.array_equal(bg.numpy(), bgo) and np.allclose(flow.numpy(), fo, atol=1e-6)
+
+
+def test_install_as_soft_renderer_exposes_what_lasr_uses():
+    """nnutils/mesh_net.py:47,132-149,306-316,354-356 and nnutils/geom_utils.py:24 import and poke these."""
+    import importlib
+    import sys
+    import lasr_b200
+    saved = {k: sys.modules.get(k) for k in ("soft_renderer", "soft_renderer.functional")}
+    try:
+        lasr_b200.install_as_soft_renderer()
+        sr = importlib.import_module("soft_renderer")
+        r = sr.SoftRenderer(image_size=32, sigma_val=1e-4, gamma_val=1e-2, camera_mode="look_at", perspective=False,
+                            aggr_func_rgb="softmax", light_mode="vertex", light_intensity_ambient=1.0,
+                            light_intensity_directionals=0.0)
+        r.rasterizer.near, r.rasterizer.far = 1.0, 2.0
+        r.rasterizer.sigma_val = 1e-5
+        r.rasterizer.background_color = [1, 1, 1]
+        assert len(r.transform.transformer._eye) == 3 and abs(r.transform.transformer._eye[2] + 2.7320508) < 1e-6
+        r.set_sigma(1e-4); r.set_gamma(1e-3); r.set_texture_mode("vertex")
+        assert r.rasterizer.sigma_val == 1e-4 and r.rasterizer.gamma_val == 1e-3 and r.lighting.light_mode == "vertex"
+        assert hasattr(sr, "Mesh") and hasattr(sr.functional, "soft_rasterize") and hasattr(sr.functional, "face_vertices")
+        with pytest.raises(NotImplementedError):
+            sr.functional.load_obj("x.obj")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+class _OracleRasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fv, tex, settings):
+        from oracle import oracle as O
+        s = {k: (float(v) if torch.is_tensor(v) else v) for k, v in settings.items()}
+        r = O.soft_rasterize_forward(fv.detach().numpy(), tex.detach().numpy(), s, np.float32)
+        ctx.r, ctx.shapes = r, (fv.shape, tex.shape)
+        return torch.from_numpy(r["soft_colors"])
+
+    @staticmethod
+    def backward(ctx, g):
+        from oracle import oracle as O
+        gf, gt = O.soft_rasterize_backward(ctx.r, g.contiguous().numpy())
+        return torch.from_numpy(gf).reshape(ctx.shapes[0]), torch.from_numpy(gt).reshape(ctx.shapes[1]), None
+
+
+def test_hot_path_region_runs_on_cpu_with_oracle_rasterizer(monkeypatch):
+    """The whole mesh_net.py:255-447 region (skin -> LBS -> projection -> 3 renders -> 3 losses) on CPU
+    tensors with the oracle as the rasterizer: finite losses, gradients reach every input, and the
+    losses equal the loop-for-loop restatement applied to the same renders."""
+    from lasr_b200 import hotpath, synth
+    from lasr_b200.geom_utils import quaternion_to_rotation_matrix
+    import lasr_b200.soft_renderer.rasterizer as rast
+    from oracle import oracle as O
+
+    def fake(face_vertices, textures, image_size=256, background_color=[0, 0, 0], near=1, far=100, fill_back=True,
+             eps=1e-3, sigma_val=1e-5, dist_func="euclidean", dist_eps=1e-4, gamma_val=1e-4, aggr_func_rgb="softmax",
+             aggr_func_alpha="prod", texture_type="surface"):
+        return _OracleRasterize.apply(face_vertices, textures, dict(
+            image_size=image_size, background_color=list(background_color), near=near, far=far, fill_back=fill_back,
+            eps=eps, sigma_val=sigma_val, dist_func=dist_func, dist_eps=dist_eps, gamma_val=gamma_val,
+            aggr_func_rgb=aggr_func_rgb, aggr_func_alpha=aggr_func_alpha, texture_type=texture_type))
+
+    monkeypatch.setattr(rast.srf, "soft_rasterize", fake)
+    g = torch.Generator().manual_seed(0)
+    H, B, S, bs = 1, 3, 24, 1
+    v, f = synth.icosphere(1, 0.4)
+    N = 2 * bs * H
+    pred_v = torch.from_numpy(v)[None].repeat(N, 1, 1).requires_grad_(True)
+    tex = torch.sigmoid(torch.randn(N, len(v), 3, generator=g)).requires_grad_(True)
+    faces = torch.from_numpy(f)[None].repeat(2 * bs, 1, 1)
+    q = torch.randn(N * B, 4, generator=g) * 0.1
+    q[:, 3] = 1
+    Rmat = quaternion_to_rotation_matrix(q).permute(0, 2, 1).contiguous().requires_grad_(True)
+    Tm = torch.randn(N * B, 3, generator=g) * 0.02
+    Tm.view(N, B, 3)[:, 0, 2] += 10
+    Tmat = Tm.requires_grad_(True)
+    ppoint = (torch.randn(2 * bs, 2, generator=g) * 0.05).requires_grad_(True)
+    scale = (9.5 + torch.rand(N, 1, generator=g)).requires_grad_(True)
+    ctl = torch.from_numpy(v)[:H * (B - 1)].clone()
+    bones = dict(ctl_ts=ctl.clone().requires_grad_(True), rest_ts=(ctl + 0.01).requires_grad_(True),
+                 ctl_rs=torch.tensor([[0.0, 0.0, 0.0, 1.0]]).repeat(H * (B - 1), 1).requires_grad_(True),
+                 log_ctl=(1 + torch.randn(H * (B - 1), 3, generator=g) * 0.3).requires_grad_(True))
+    occ = torch.randn(2 * bs, S, S, generator=g)
+    batch = dict(masks=(torch.rand(2 * bs, S, S, generator=g) > 0.4).float(), imgs=torch.rand(2 * bs, 3, S, S, generator=g),
+                 flow=torch.randn(2 * bs, 3, S, S, generator=g) * 0.05, occ=occ)
+    m = hotpath.RenderHotPath(hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B))
+    out = m(pred_v, tex, faces, Rmat, Tmat, ppoint, scale, batch, bones)
+    out["total"].backward()
+    assert all(torch.isfinite(out[k]) for k in ("total", "mask_loss", "flow_loss", "texture_loss"))
+    for name, t in dict(pred_v=pred_v, tex=tex, Rmat=Rmat, Tmat=Tmat, ppoint=ppoint, scale=scale, **bones).items():
+        assert t.grad is not None and torch.isfinite(t.grad).all(), name
+    assert pred_v.grad.abs().max() > 0 and tex.grad.abs().max() > 0 and Rmat.grad.abs().max() > 0
+    n2 = 2 * bs
+    lo, _ = O.mask_loss(out["mask_pred"].detach().view(n2, H, S, S).numpy(), batch["masks"].numpy(), occ.numpy())
+    assert abs(float(out["mask_loss"]) - lo) < 1e-6
+    lo, _ = O.flow_loss(out["flow_rd"].detach().view(n2, H, S, S, 2).numpy(), out["bgmask"].view(n2, H, S, S).numpy(),
+                        batch["flow"].numpy(), occ.numpy(), batch["masks"].numpy())
+    assert abs(float(out["flow_loss"]) - lo) < 1e-6
+    lo, _ = O.texture_l1_loss(out["texture_render"].detach().reshape(n2, H, 3, S, S).numpy(),
+                              out["mask_pred"].detach().view(n2, H, S, S).numpy(), batch["imgs"].numpy(),
+                              batch["masks"].numpy(), occ.numpy(), 1.0)
+    assert abs(float(out["texture_loss"]) - lo) < 1e-6

@@ -288,3 +288,31 @@ def test_backward_with_reused_setup_equals_fresh_setup(srf):
         _cabi.raster_backward(fv, tex, img, agg, gf, gt, g, w, *scal, setup_done=reuse)
         outs.append((gf, gt))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_anti_aliasing_and_forward_entry_point(srf, oracle):
+    """SoftRasterizer(anti_aliasing=True) renders at 2x and average-pools (rasterizer.py:43,52-53);
+    SoftRenderer.forward(vertices, faces, textures) builds the Mesh itself (renderer.py:99-101)."""
+    import lasr_b200.soft_renderer as sr
+    import torch.nn.functional as F
+    from lasr_b200 import synth
+    dev = torch.device("cuda", 0)
+    v, f = synth.bumpy_sphere(1, 0.5)
+    px, cam, near, far = synth.render_inputs(v, f, 2)
+    verts = torch.from_numpy(px).to(dev)
+    faces = torch.from_numpy(np.repeat(f[None], 2, 0)).to(dev)
+    cols = torch.from_numpy(np.repeat(synth.vertex_colors(len(v))[None], 2, 0)).to(dev)
+    r = sr.SoftRasterizer(image_size=32, near=near, far=far, anti_aliasing=True, fill_back=True, sigma_val=1e-4,
+                          gamma_val=1e-2, texture_type="vertex")
+    img = r(sr.Mesh(verts, faces, textures=cols, texture_type="vertex"))
+    st = oracle.RasterSettings.lasr_training(64, near, far, 1e-4)
+    ref = oracle.soft_rasterize_forward(synth.gather_faces(px, f), synth.gather_faces(cols.cpu().numpy(), f), st, np.float32)
+    ref_img = F.avg_pool2d(torch.from_numpy(ref["soft_colors"]), 2, 2).numpy()
+    assert img.shape == (2, 4, 32, 32) and parity.image_report(img.cpu().numpy(), ref_img)["n_bad"] == 0
+    rr = sr.SoftRenderer(image_size=32, near=near, far=far, sigma_val=1e-4, gamma_val=1e-2, camera_mode="look_at",
+                         perspective=False, light_mode="vertex", light_intensity_ambient=1.0,
+                         light_intensity_directionals=0.0)
+    eye = torch.tensor(rr.transform.transformer._eye, device=dev)
+    a = rr(verts + eye, faces, cols, texture_type="vertex")
+    b = rr.render_mesh(sr.Mesh(verts + eye, faces, textures=cols, texture_type="vertex"))
+    assert torch.equal(a, b) and a.shape == (2, 4, 32, 32)
