@@ -292,15 +292,18 @@ __global__ void __launch_bounds__(kFwdThreads, LASR_FWD_MIN_BLOCKS) raster_forwa
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward: one warp per face
+// backward: one warp per face; faces whose pixel window is huge are deferred to a second launch of
+// the same code with one CTA per face (kBig), so a few screen-filling triangles cannot serialise the
+// kernel behind a single warp.  Either way a face's gradient is a private fixed-order sum.
 // ---------------------------------------------------------------------------------------------
-template <bool kFast>
+constexpr int kBigFacePixels = 4096;   // window area above which a face goes to the CTA-per-face pass
+constexpr int kBigListCap = 16384;     // deferred faces the workspace can list (the rest run inline)
+
+template <bool kFast, bool kBig>
 __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kernel(RasterArgs A) {
+  __shared__ float s_part[8][18];
   const int lane = threadIdx.x & 31;
-  const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (wg >= (long long)A.N * A.F) return;
-  const int n = (int)(wg / A.F);
-  const int f = (int)(wg % A.F);
+  const int nwarps = blockDim.x >> 5;
   const int S = A.S;
   const long long SS = (long long)S * S;
 
@@ -314,6 +317,16 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
   const int rgb_f = kFast ? 1 : A.rgb;
   const int alpha_f = kFast ? 2 : A.alpha;
   const int sample = kFast ? 1 : A.sample;
+
+  const int n_items = kBig ? min(A.big_list[0], kBigListCap) : 1;
+  for (int item = kBig ? blockIdx.x : 0; item < n_items; item += kBig ? gridDim.x : 1) {
+  const long long wg = kBig ? (long long)A.big_list[1 + item]
+                            : (long long)blockIdx.x * nwarps + (threadIdx.x >> 5);
+  if (!kBig && wg >= (long long)A.N * A.F) return;
+  const int n = (int)(wg / A.F);
+  const int f = (int)(wg % A.F);
+  const int gtid = kBig ? threadIdx.x : lane;        // index within the group sweeping this face
+  const int gsize = kBig ? blockDim.x : 32;
 
   float tex9[9];
   FaceGeom g;
@@ -331,6 +344,15 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
   int xlo, xhi, ylo, yhi;
   coord_window(g.lox, g.hix, S, xlo, xhi);
   coord_window(g.loy, g.hiy, S, ylo, yhi);
+  if (!kBig && xlo <= xhi && ylo <= yhi && (xhi - xlo + 1) * (yhi - ylo + 1) > kBigFacePixels) {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(A.big_list, 1);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot < kBigListCap) {           // deferred: the CTA-per-face pass writes this face's outputs
+      if (lane == 0) A.big_list[1 + slot] = (int)wg;
+      return;
+    }
+  }
   float gf[9], gt[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) { gf[k] = 0.f; gt[k] = 0.f; }
@@ -342,7 +364,7 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
     const float* sc = A.soft_colors + (long long)n * 4 * SS;
     const float* ag = A.aggrs_info + (long long)n * 2 * SS;
     const float* gs = A.grad_soft_colors + (long long)n * 4 * SS;
-    for (int idx = lane; idx < total; idx += 32) {
+    for (int idx = gtid; idx < total; idx += gsize) {
       int r = (int)(((float)idx + 0.5f) * inv_wdt);  // idx / wdt without an integer divide
       int col = idx - r * wdt;
       if (col < 0) { --r; col += wdt; } else if (col >= wdt) { ++r; col -= wdt; }
@@ -446,7 +468,7 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
       for (int k = 0; k < 3; ++k) { gf[3 * k] += gx[k]; gf[3 * k + 1] += gy[k]; gf[3 * k + 2] += gz[k]; }
     }
   }
-  // fixed-order warp reduction (16 values by recursive halving + 2 butterflies), one write per value
+  // fixed-order reduction (16 values by recursive halving + 2 butterflies), one write per value
   float* gface_out = A.grad_faces + wg * 9;
   float v16[16];
 #pragma unroll
@@ -455,12 +477,27 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
   for (int k = 0; k < 7; ++k) v16[9 + k] = gt[k];
   warp_sum16(v16, lane);
   const float t7 = warp_sum(gt[7]), t8 = warp_sum(gt[8]);
-  if ((lane & 1) == 0) {
-    const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-    if (idx < 9) gface_out[idx] = v16[0];
-    else if (sample == 1) gtex_out[idx - 9] = v16[0];
+  const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+  if (!kBig) {
+    if ((lane & 1) == 0) {
+      if (vidx < 9) gface_out[vidx] = v16[0];
+      else if (sample == 1) gtex_out[vidx - 9] = v16[0];
+    }
+    if (sample == 1 && lane == 0) { gtex_out[7] = t7; gtex_out[8] = t8; }
+  } else {   // CTA per face: combine the warps' totals in warp order
+    const int warp = threadIdx.x >> 5;
+    if ((lane & 1) == 0) s_part[warp][vidx] = v16[0];
+    if (lane == 0) { s_part[warp][16] = t7; s_part[warp][17] = t8; }
+    __syncthreads();
+    if (threadIdx.x < 18) {
+      float t = 0.f;
+      for (int w = 0; w < nwarps; ++w) t += s_part[w][threadIdx.x];
+      if (threadIdx.x < 9) gface_out[threadIdx.x] = t;
+      else if (sample == 1) gtex_out[threadIdx.x - 9] = t;
+    }
+    __syncthreads();
   }
-  if (sample == 1 && lane == 0) { gtex_out[7] = t7; gtex_out[8] = t8; }
+  }  // item loop
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -493,9 +530,26 @@ static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, flo
   A.face_window = reinterpret_cast<uint2*>(p);   p += align256(nf * sizeof(uint2));
   A.coords = reinterpret_cast<float*>(p);        p += align256((size_t)S * sizeof(float));
   A.frame_window = reinterpret_cast<int*>(p);    p += align256((size_t)N * 4 * sizeof(int));
+  A.big_list = reinterpret_cast<int*>(p);        p += align256((size_t)(kBigListCap + 1) * sizeof(int));
   A.face_border = reinterpret_cast<float4*>(p);  p += align256(nf * sizeof(float4));
   A.face_record = reinterpret_cast<float*>(p);
   return 0;
+}
+
+static bool is_fast(const RasterArgs& A);
+
+// main pass (one warp per face, huge faces deferred) + CTA-per-face pass over the deferred list
+static int launch_backward(const RasterArgs& A, long long nf, cudaStream_t st) {
+  if (cudaMemsetAsync(A.big_list, 0, sizeof(int), st) != cudaSuccess) return fail("raster_backward: memset failed");
+  constexpr int kWarpsPerBlock = LASR_BWD_THREADS / 32;
+  const unsigned blocks = (unsigned)((nf + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  if (is_fast(A)) raster_backward_kernel<true, false><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+  else raster_backward_kernel<false, false><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+  if (check_launch("raster_backward_kernel")) return 1;
+  const unsigned big_blocks = 592;   // 4 per SM; each loops over the (usually empty) deferred list
+  if (is_fast(A)) raster_backward_kernel<true, true><<<big_blocks, 256, 0, st>>>(A);
+  else raster_backward_kernel<false, true><<<big_blocks, 256, 0, st>>>(A);
+  return check_launch("raster_backward_kernel<big>");
 }
 
 static bool is_fast(const RasterArgs& A) {
@@ -536,6 +590,7 @@ extern "C" size_t lasr_b200_raster_workspace_bytes(int N, int F, int S) {
   if (N <= 0 || F <= 0 || S <= 0) return 0;
   const size_t nf = (size_t)N * (size_t)F;
   return align256(nf * sizeof(uint2)) + align256((size_t)S * sizeof(float)) + align256((size_t)N * 4 * sizeof(int)) +
+         align256((size_t)(kBigListCap + 1) * sizeof(int)) +
          align256(nf * sizeof(float4)) +
          align256(nf * kRecWords * sizeof(float));
 }
@@ -599,11 +654,7 @@ extern "C" int lasr_b200_raster_backward(const float* faces, const float* textur
     raster_setup_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(B, 0);
     if (check_launch("raster_setup_kernel")) return 1;
   }
-  constexpr int kWarpsPerBlock = LASR_BWD_THREADS / 32;
-  const unsigned blocks = (unsigned)((nf + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  if (is_fast(A)) raster_backward_kernel<true><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
-  else raster_backward_kernel<false><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
-  return check_launch("raster_backward_kernel");
+  return launch_backward(A, nf, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -685,11 +736,7 @@ extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri,
     raster_setup_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(B, 0);
     if (check_launch("raster_setup_kernel")) return 1;
   }
-  constexpr int kWarpsPerBlock = LASR_BWD_THREADS / 32;
-  const unsigned blocks = (unsigned)((nf + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  if (is_fast(A)) raster_backward_kernel<true><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
-  else raster_backward_kernel<false><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
-  if (check_launch("raster_backward_kernel")) return 1;
+  if (launch_backward(A, nf, st)) return 1;
   const long long nv = (long long)N * V;
   vertex_gather_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(A.grad_faces, A.grad_textures, csr_offsets,
                                                                       csr_entries, grad_verts, grad_vcolors, N, V, F);

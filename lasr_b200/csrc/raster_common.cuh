@@ -40,6 +40,7 @@ struct RasterArgs {
   float* face_record;        // [N*F][kRecWords]
   float* coords;             // [S] pixel-centre coordinates
   int records_valid;         // backward: workspace already holds the forward's setup of the same inputs
+  int* big_list;             // [1 + cap]: count, then flat (frame*F + face) ids of faces deferred to the CTA-per-face pass
   int* frame_window;         // [N][4] (x_lo, -x_hi, y_lo, -y_hi) of the union of face windows (atomicMin)
   const float* near_far_dev; // optional {near, far} on device
   // indexed ("fused") input mode: faces/textures are gathered on the fly from per-vertex arrays

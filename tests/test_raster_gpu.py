@@ -90,6 +90,13 @@ def _edge_cases():
     c["face_vertices"] = np.concatenate([c["face_vertices"], big[None]], 1)   # one face covering the screen
     c["textures"] = np.concatenate([c["textures"], c["textures"][:, :1]], 1)
     out["huge_face"] = c
+    c = cases.lasr_case("ico2", 2, 128)
+    z = float(c["face_vertices"][..., 2].mean())
+    big = np.array([[[-2.0, -2.0, z + 0.05], [2.0, -2.0, z + 0.1], [0.0, 2.5, z + 0.15]],
+                    [[-0.9, 0.8, z - 0.1], [0.9, 0.7, z - 0.05], [0.1, -0.95, z]]], dtype=np.float32)
+    c["face_vertices"] = np.concatenate([c["face_vertices"], np.repeat(big[None], 2, 0)], 1)
+    c["textures"] = np.concatenate([c["textures"], c["textures"][:, :2]], 1)
+    out["huge_faces_deferred_pass"] = c                                  # windows > 4096 px -> CTA-per-face backward
     c = cases.lasr_case("ico2", 1, 64)
     c["face_vertices"][0, 5, 1] = c["face_vertices"][0, 5, 0]           # zero-area face (duplicate vertex)
     c["face_vertices"][0, 9, :, :2] = c["face_vertices"][0, 9, 0, :2]   # all three vertices coincide in 2-D
