@@ -121,6 +121,23 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def profiled_issue_stats(kernel_name):
+    """Issue-slot utilisation / lane efficiency of the kernel from the committed ncu capture (the binding
+    resource on this path; the HBM fraction is low by nature)."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json")), reverse=True):
+        try:
+            k = json.load(open(path))["kernels"]
+        except Exception:
+            continue
+        for name, v in k.items():
+            if name.startswith(kernel_name):
+                return {"issue_slots_busy_pct": v.get("issue_active_pct"), "active_lanes_per_instruction": v.get("threads_per_inst"),
+                        "warp_instructions": v.get("warp_instructions"), "registers": v.get("registers"),
+                        "achieved_occupancy_pct": v.get("achieved_occupancy_pct"), "source": os.path.relpath(path, ROOT)}
+    return None
+
+
 def measured_traffic(kernel_name):
     """dram__bytes_read+write per launch of the dominant kernel, from the committed ncu capture of this
     same command/config (profiles/traffic_r*.json; newest round wins).  None if no capture matches."""
@@ -500,6 +517,7 @@ def run_gpu_arm(args, arm_cls):
                          "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bwd_bytes,
+                         "binding_resource": profiled_issue_stats("raster_backward_kernel") if arm.name == "ours" else None,
                          "note": "FP32-issue bound after binning (ncu: issue slots ~65% busy, DRAM <5% of peak; DESIGN.md "
                                  "section 4); measured DRAM traffic is below the algorithmic bytes because the images the "
                                  "forward just wrote are still L2-resident"},

@@ -118,7 +118,11 @@ def depth_window(verts_z):
 # R1: flow rendering (nnutils/mesh_net.py:75-104, nnutils/geom_utils.py:73-95)
 # ----------------------------------------------------------------------------------------------
 def _eye_offset(renderer_soft, device):
-    return torch.as_tensor(renderer_soft.transform.transformer._eye, dtype=torch.float32, device=device)[None, None]
+    eye = renderer_soft.transform.transformer._eye
+    if torch.is_tensor(eye):
+        return eye.to(device=device, dtype=torch.float32).reshape(1, 1, 3)
+    from .soft_renderer.functional.geometry import _const      # uploaded once per (value, device): graph-capturable
+    return _const(eye, device)[None, None]
 
 
 def _reproject(pos_px, pp, fl):
@@ -128,7 +132,8 @@ def _reproject(pos_px, pp, fl):
     return torch.stack([x, y], dim=-1)
 
 
-def render_flow_soft_2(renderer_soft, verts, faces, verts_pos0, verts_pos1, pp0, pp1, proj_cam0, proj_cam1):
+def render_flow_soft_2(renderer_soft, verts, faces, verts_pos0, verts_pos1, pp0, pp1, proj_cam0, proj_cam1,
+                       shared_faces=None):
     """Render the 3-D positions of two frames as vertex 'colours' through the soft rasterizer and
     re-project them with each frame's intrinsics to get optical flow (mesh_net.py:75-104).
     Returns (flow_fw [n,S,S,2], bgmask [n,S,S] bool, fgmask [n,S,S])."""
@@ -140,7 +145,7 @@ def render_flow_soft_2(renderer_soft, verts, faces, verts_pos0, verts_pos1, pp0,
     nb = verts.shape[0]
     px = renderer_soft.render_mesh(sr.Mesh(torch.cat([pre, pre], 0), torch.cat([faces, faces], 0),
                                            textures=torch.cat([verts_pos0[:, :, :3], verts_pos1[:, :, :3]], 0),
-                                           texture_type="vertex"))
+                                           texture_type="vertex", shared_faces=shared_faces))
     fgmask = px[:nb, -1]
     px = px[:, :3]
     pos0 = px[:nb].permute(0, 2, 3, 1)

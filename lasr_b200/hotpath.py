@@ -41,7 +41,7 @@ class RenderHotPath(torch.nn.Module):
                                      light_intensity_directionals=0.0)
         self.renderer_softflf, self.renderer_softflb, self.renderer_softtex = mk(), mk(), mk()
 
-    def forward(self, pred_v, tex, faces, Rmat, Tmat, ppoint, scale, batch, bones=None):
+    def forward(self, pred_v, tex, faces, Rmat, Tmat, ppoint, scale, batch, bones=None, shared_faces=None):
         """pred_v [2bs*H,V,3]; tex [2bs*H,V,3]; faces [2bs,F,3] int32; Rmat [2bs*H*B,3,3] (already
         transposed as mesh_net.py:259); Tmat [2bs*H*B,3]; ppoint [2bs,2]; scale [2bs*H,1];
         batch = dict(masks [2bs,S,S], imgs [2bs,3,S,S], flow [2bs,3,S,S], occ [2bs,S,S]);
@@ -49,6 +49,10 @@ class RenderHotPath(torch.nn.Module):
         Returns dict(total, mask_loss, flow_loss, texture_loss, + renders)."""
         o = self.opts
         H, B, S = o.n_hypo, o.n_bones, o.img_size
+        if shared_faces is None and faces.is_cuda:
+            # LASR renders one mesh: every frame carries the same topology (ext_nnutils/mesh_net.py:171-185).
+            # Verified once per faces tensor (cached); pass shared_faces= to skip even that.
+            shared_faces = sr.functional.shared_topology(faces)
         n2 = ppoint.shape[0]          # 2 * bs
         bs = n2 // 2
         skin = None
@@ -78,11 +82,11 @@ class RenderHotPath(torch.nn.Module):
         flow_fw, bg_fw, fg_fw = gu.render_flow_soft_2(
             self.renderer_softflf, px4[:bs].reshape(bs * H, -1, 4), faces[:bs], verts_pos0, verts_pos1,
             rep(ppoint, 0, bs), rep(ppoint, bs, n2), scale.view(n2, H, 1)[:bs].reshape(-1, 1),
-            scale.view(n2, H, 1)[bs:].reshape(-1, 1))
+            scale.view(n2, H, 1)[bs:].reshape(-1, 1), shared_faces=shared_faces)
         flow_bw, bg_bw, fg_bw = gu.render_flow_soft_2(
             self.renderer_softflb, px4[bs:].reshape(bs * H, -1, 4), faces[bs:], verts_pos1, verts_pos0,
             rep(ppoint, bs, n2), rep(ppoint, 0, bs), scale.view(n2, H, 1)[bs:].reshape(-1, 1),
-            scale.view(n2, H, 1)[:bs].reshape(-1, 1))
+            scale.view(n2, H, 1)[:bs].reshape(-1, 1), shared_faces=shared_faces)
         bgmask = torch.cat([bg_fw, bg_bw], 0)
         flow_rd = torch.cat([flow_fw, flow_bw], 0)
         # 3) texture / silhouette render (mesh_net.py:348-363)
@@ -91,7 +95,8 @@ class RenderHotPath(torch.nn.Module):
         pre = torch.cat([pre[:, :, :1], -pre[:, :, 1:2], pre[:, :, 2:]], dim=-1)
         self.renderer_softtex.rasterizer.background_color = [1, 1, 1]
         faces_h = faces[:, None].repeat(1, H, 1, 1).view(-1, faces.shape[1], 3)
-        texture_render = self.renderer_softtex.render_mesh(sr.Mesh(pre, faces_h, textures=tex, texture_type="vertex"))
+        texture_render = self.renderer_softtex.render_mesh(sr.Mesh(pre, faces_h, textures=tex, texture_type="vertex",
+                                                                   shared_faces=shared_faces))
         mask_pred = texture_render[:, -1]
         rgb = texture_render[:, :3]
         # 4) losses (mesh_net.py:372-447, LPIPS term excluded)

@@ -12,7 +12,10 @@ from . import functional as srf
 
 
 class Mesh(object):
-    def __init__(self, vertices, faces, textures=None, texture_res=1, texture_type="surface"):
+    def __init__(self, vertices, faces, textures=None, texture_res=1, texture_type="surface", shared_faces=None):
+        # shared_faces (extension): an int32 [F,3] topology the caller guarantees every frame uses; lets the
+        # rasterizer take the indexed path without comparing the frames' face tensors (a device sync).
+        self.shared_faces = shared_faces
         if isinstance(vertices, np.ndarray):
             vertices = torch.from_numpy(vertices).float().cuda()
         if isinstance(faces, np.ndarray):
@@ -63,6 +66,7 @@ class Mesh(object):
 
     @faces.setter
     def faces(self, faces):
+        self.shared_faces = None
         self._faces = faces
         self.num_faces = faces.shape[1]
         self._invalidate()

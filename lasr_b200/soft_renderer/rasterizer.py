@@ -39,7 +39,9 @@ class SoftRasterizer(nn.Module):
         image_size = self.image_size * (2 if self.anti_aliasing else 1)
         tri = None
         if self.texture_type == "vertex" and mesh.vertices.is_cuda and not getattr(mesh, "_fill_back", False):
-            tri = srf.shared_topology(mesh.faces)      # one topology for every frame (LASR's call pattern)
+            tri = getattr(mesh, "shared_faces", None)   # caller-guaranteed shared topology (no check needed)
+            if tri is None:
+                tri = srf.shared_topology(mesh.faces)  # one topology for every frame (LASR's call pattern)
         if tri is not None:
             # indexed path: no [N,F,9] gathers, per-vertex gradients straight from the kernels
             images = srf.render_indexed(mesh.vertices, mesh.textures, tri, image_size, self.background_color,

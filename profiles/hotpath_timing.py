@@ -1,0 +1,63 @@
+"""Throughput of the whole render hot path (lasr_b200.hotpath.RenderHotPath: skin -> LBS -> projection ->
+flow fw/bw renders + texture render -> three losses, forward + backward) on one GPU.
+usage: python profiles/hotpath_timing.py [bones] [pairs] [graph]"""
+import os, sys, time
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+from lasr_b200 import hotpath, synth
+from lasr_b200.geom_utils import quaternion_to_rotation_matrix
+from lasr_b200.pipeline import GraphedStep
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 26
+bs = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+use_graph = (sys.argv[3] == "graph") if len(sys.argv) > 3 else False
+H, S = 1, 256
+dev = torch.device("cuda", 0)
+g = torch.Generator().manual_seed(0)
+v, f = synth.load_spot()
+V, n2 = len(v), 2 * bs
+N = n2 * H
+Rb, Tb, pp, fl = synth.spot_cameras(N)
+pred_v = torch.from_numpy(v)[None].repeat(N, 1, 1).to(dev)
+tex = torch.from_numpy(synth.vertex_colors(V))[None].repeat(N, 1, 1).to(dev)
+faces = torch.from_numpy(f)[None].repeat(n2, 1, 1).to(dev)
+q = torch.randn(N * B, 4, generator=g) * 0.05
+q[:, 3] = 1
+R = quaternion_to_rotation_matrix(q).view(N, B, 3, 3)
+R[:, 0] = torch.from_numpy(Rb)
+Rmat = R.view(-1, 3, 3).permute(0, 2, 1).permute(0, 2, 1).contiguous().to(dev)
+T = torch.randn(N * B, 3, generator=g) * 0.01
+T.view(N, B, 3)[:, 0] = torch.from_numpy(Tb[:, 0])
+Tmat = T.to(dev)
+ppoint = torch.zeros(n2, 2, device=dev)
+scale = torch.full((N, 1), 10.0, device=dev)
+bones = None
+if B > 1:
+    idx = torch.randperm(V, generator=g)[:H * (B - 1)]
+    ctl = torch.from_numpy(v)[idx].to(dev)
+    bones = dict(ctl_ts=ctl.clone(), rest_ts=ctl.clone(), ctl_rs=torch.tensor([[0., 0, 0, 1]], device=dev).repeat(H * (B - 1), 1),
+                 log_ctl=torch.ones(H * (B - 1), 3, device=dev))
+batch = dict(masks=(torch.rand(n2, S, S, generator=g) > 0.5).float().to(dev), imgs=torch.rand(n2, 3, S, S, generator=g).to(dev),
+             flow=(torch.randn(n2, 3, S, S, generator=g) * 0.02).to(dev), occ=torch.randn(n2, S, S, generator=g).to(dev))
+leaves = [pred_v, tex, Rmat, Tmat, ppoint, scale] + (list(bones.values()) if bones else [])
+m = hotpath.RenderHotPath(hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B)).to(dev)
+
+def step(*xs):
+    xs = [x.detach().requires_grad_(True) for x in xs]
+    bn = dict(zip(bones.keys(), xs[6:])) if bones else None
+    out = m(xs[0], xs[1], faces, xs[2], xs[3], xs[4], xs[5], batch, bn)
+    out["total"].backward()
+    return (out["total"].detach(),) + tuple(x.grad for x in xs)
+
+run = GraphedStep(step, leaves) if use_graph else (lambda: step(*leaves))
+for _ in range(3):
+    run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+K = 15
+t0 = time.perf_counter(); e0.record()
+for _ in range(K):
+    outs = run()
+e1.record(); torch.cuda.synchronize()
+ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / K
+print(f"hotpath B={B} pairs={bs} frames={N} graph={use_graph}: {ms:.3f} ms/step -> {N/ms*1e3:.0f} frames/s  loss={float(outs[0]):.5f}")
