@@ -195,6 +195,22 @@ int lasr_b200_losses_coefficients(const float* sums, const float* grad_out3, con
                                   float* grad_sums, int num_frames, int num_hypotheses, float l1tex_wt,
                                   void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Flow epilogue: the post-processing of render_flow_soft_2,
+ * nnutils/mesh_net.py:88-104, in one pass.  px [2n,4,S,S] is the rasterizer's output for the stacked
+ * batch (first n: frame-0 positions, last n: frame-1 positions); pp0/pp1 [n,2], f0/f1 [n].
+ * flow [n,S,S,2] and bgmask [n,S,S] (uint8) out.  backward: grad_flow -> grad_px [2n,4,S,S] (only the
+ * frame-1 half carries gradient, p0 is detached and background pixels are cut, :102-103), grad_pp1,
+ * grad_f1 (pp0 / f0 get none).
+ * ------------------------------------------------------------------------------------------- */
+size_t lasr_b200_flow_epilogue_workspace_bytes(int num_frames, int image_size);
+int lasr_b200_flow_epilogue_forward(const float* px, const float* pp0, const float* pp1, const float* f0,
+                                    const float* f1, float* flow, uint8_t* bgmask, int num_frames,
+                                    int image_size, void* stream);
+int lasr_b200_flow_epilogue_backward(const float* px, const float* f1, const float* grad_flow, float* grad_px,
+                                     float* grad_pp1, float* grad_f1, void* workspace, size_t workspace_bytes,
+                                     int num_frames, int image_size, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

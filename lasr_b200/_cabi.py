@@ -63,6 +63,12 @@ def lib():
         L.lasr_b200_losses_finalize.argtypes = [_c.c_void_p] * 3 + [_c.c_int, _c.c_int, _c.c_float, _c.c_void_p]
         L.lasr_b200_losses_coefficients.restype = _c.c_int
         L.lasr_b200_losses_coefficients.argtypes = [_c.c_void_p] * 4 + [_c.c_int, _c.c_int, _c.c_float, _c.c_void_p]
+        L.lasr_b200_flow_epilogue_workspace_bytes.restype = _c.c_size_t
+        L.lasr_b200_flow_epilogue_workspace_bytes.argtypes = [_c.c_int, _c.c_int]
+        L.lasr_b200_flow_epilogue_forward.restype = _c.c_int
+        L.lasr_b200_flow_epilogue_forward.argtypes = [_c.c_void_p] * 7 + [_c.c_int, _c.c_int, _c.c_void_p]
+        L.lasr_b200_flow_epilogue_backward.restype = _c.c_int
+        L.lasr_b200_flow_epilogue_backward.argtypes = [_c.c_void_p] * 7 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_void_p]
         L.lasr_b200_lbs_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_lbs_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_lbs_project_forward.restype = _c.c_int
@@ -79,6 +85,7 @@ EXPORTED_SYMBOLS = [
     "lasr_b200_render_workspace_bytes", "lasr_b200_render_forward", "lasr_b200_render_backward",
     "lasr_b200_losses_workspace_bytes", "lasr_b200_losses_forward", "lasr_b200_losses_backward",
     "lasr_b200_losses_finalize", "lasr_b200_losses_coefficients",
+    "lasr_b200_flow_epilogue_workspace_bytes", "lasr_b200_flow_epilogue_forward", "lasr_b200_flow_epilogue_backward",
     "lasr_b200_lbs_workspace_bytes", "lasr_b200_lbs_project_forward", "lasr_b200_lbs_project_backward",
 ]
 
@@ -264,3 +271,18 @@ def losses_coefficients(sums, g3, gsub, gsums, N, H, l1tex_wt):
         rc = lib().lasr_b200_losses_coefficients(_p(sums), _p(g3), _p(gsub), _p(gsums), N, H, float(l1tex_wt),
                                                  _stream_ptr())
     _check(rc, "lasr_b200_losses_coefficients")
+
+
+def flow_epilogue_forward(px, pp0, pp1, f0, f1, flow, bgmask, n, S):
+    with torch.cuda.device(px.device):
+        rc = lib().lasr_b200_flow_epilogue_forward(_p(px), _p(pp0), _p(pp1), _p(f0), _p(f1), _p(flow), _p(bgmask), n, S,
+                                                   _stream_ptr())
+    _check(rc, "lasr_b200_flow_epilogue_forward")
+
+
+def flow_epilogue_backward(px, f1, grad_flow, grad_px, grad_pp1, grad_f1, n, S):
+    ws = torch.empty(int(lib().lasr_b200_flow_epilogue_workspace_bytes(n, S)), dtype=torch.uint8, device=px.device)
+    with torch.cuda.device(px.device):
+        rc = lib().lasr_b200_flow_epilogue_backward(_p(px), _p(f1), _p(grad_flow), _p(grad_px), _p(grad_pp1), _p(grad_f1),
+                                                    _p(ws), ws.numel(), n, S, _stream_ptr())
+    _check(rc, "lasr_b200_flow_epilogue_backward")

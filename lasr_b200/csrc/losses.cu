@@ -240,6 +240,85 @@ __global__ void losses_coef_kernel(const float* sums, const float* g3, const flo
   o[6] = 0.f;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Flow epilogue of render_flow_soft_2 (nnutils/mesh_net.py:88-104): the rasterizer rendered the 3-D
+// positions of frame 0 and frame 1 as colours (planar [2n,4,S,S]: first n = frame-0 positions, last
+// n = frame-1 positions); re-project both with their intrinsics and subtract.
+//   bg   = pos0.z < 1e-9 | pos1.z < 1e-9           (both set to 10 there, as the reference does)
+//   flow = (pp1 + pos1.xy * f1 / pos1.z) - (pp0 + pos0.xy * f0 / pos0.z)      [n,S,S,2]
+// Gradient flows to frame-1 positions only, and not at background pixels (`p0.detach()`, :102-103).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) flow_epilogue_forward_kernel(const float* __restrict__ px, const float* pp0,
+                                                                    const float* pp1, const float* f0, const float* f1,
+                                                                    float* flow, uint8_t* bgmask, int n, int SS) {
+  const int i = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= SS) return;
+  const float* a = px + (long long)i * 4 * SS + p;         // frame-0 positions
+  const float* b = px + (long long)(n + i) * 4 * SS + p;   // frame-1 positions
+  float x0 = a[0], y0 = a[SS], z0 = a[2 * (long long)SS];
+  float x1 = b[0], y1 = b[SS], z1 = b[2 * (long long)SS];
+  const bool bg = z0 < 1e-9f || z1 < 1e-9f;
+  if (bg) { x0 = y0 = z0 = 10.f; x1 = y1 = z1 = 10.f; }
+  const float u0 = pp0[2 * i] + x0 * f0[i] / z0, v0 = pp0[2 * i + 1] + y0 * f0[i] / z0;
+  const float u1 = pp1[2 * i] + x1 * f1[i] / z1, v1 = pp1[2 * i + 1] + y1 * f1[i] / z1;
+  reinterpret_cast<float2*>(flow)[(long long)i * SS + p] = make_float2(u1 - u0, v1 - v0);
+  bgmask[(long long)i * SS + p] = bg ? 1 : 0;
+}
+
+// grad_flow [n,S,S,2] -> grad_px [2n,4,S,S] (zero except xyz of the frame-1 half at foreground pixels),
+// plus per-frame partial sums for pp1 (x,y) and f1: partial [n][nblk][3]
+__global__ void __launch_bounds__(256) flow_epilogue_backward_kernel(const float* __restrict__ px, const float* f1,
+                                                                     const float* __restrict__ gflow, float* gpx,
+                                                                     float* partial, int n, int SS, int nblk) {
+  __shared__ float s_w[8][3];
+  const int i = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc[3] = {0.f, 0.f, 0.f};
+  if (p < SS) {
+    const float* a = px + (long long)i * 4 * SS + p;
+    const float* b = px + (long long)(n + i) * 4 * SS + p;
+    const float z0 = a[2 * (long long)SS];
+    const float x1 = b[0], y1 = b[SS], z1 = b[2 * (long long)SS];
+    const bool bg = z0 < 1e-9f || z1 < 1e-9f;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (!bg) {
+      const float2 g = reinterpret_cast<const float2*>(gflow)[(long long)i * SS + p];
+      const float f = f1[i], iz = 1.f / z1;
+      gx = g.x * f * iz;
+      gy = g.y * f * iz;
+      gz = -(g.x * x1 + g.y * y1) * f * iz * iz;
+      acc[0] = g.x; acc[1] = g.y; acc[2] = (g.x * x1 + g.y * y1) * iz;
+    }
+    float* o0 = gpx + (long long)i * 4 * SS + p;
+    float* o1 = gpx + (long long)(n + i) * 4 * SS + p;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o0[c * (long long)SS] = 0.f;
+    o1[0] = gx; o1[SS] = gy; o1[2 * (long long)SS] = gz; o1[3 * (long long)SS] = 0.f;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float w = wsum(acc[k]);
+    if (lane == 0) s_w[warp][k] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_w[w][threadIdx.x];
+    partial[((long long)i * nblk + blockIdx.x) * 3 + threadIdx.x] = t;
+  }
+}
+
+__global__ void flow_epilogue_reduce_kernel(const float* partial, int n, int nblk, float* gpp1, float* gf1) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * 3) return;
+  const int i = t / 3, k = t % 3;
+  float acc = 0.f;
+  for (int b = 0; b < nblk; ++b) acc += partial[((long long)i * nblk + b) * 3 + k];
+  if (k < 2) gpp1[2 * i + k] = acc; else gf1[i] = acc;
+}
+
 static int fill_loss(LossArgs& A, const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
                      const float* tex, const float* fg, const float* imgs, const float* masks, const float* occ,
                      const float* flow_obs, int N, int H, int S) {
@@ -311,4 +390,36 @@ extern "C" int lasr_b200_losses_coefficients(const float* sums, const float* gra
   losses_coef_kernel<<<(NH + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, grad_out3, grad_sub, N, H, l1tex_wt,
                                                                          grad_sums);
   return lasr_check_launch("losses_coef_kernel");
+}
+
+extern "C" size_t lasr_b200_flow_epilogue_workspace_bytes(int n, int S) {
+  if (n <= 0 || S <= 0) return 0;
+  return (size_t)n * (((size_t)S * S + 255) / 256) * 3 * sizeof(float) + 256;
+}
+
+extern "C" int lasr_b200_flow_epilogue_forward(const float* px, const float* pp0, const float* pp1, const float* f0,
+                                               const float* f1, float* flow, uint8_t* bgmask, int n, int S,
+                                               void* stream) {
+  if (!px || !pp0 || !pp1 || !f0 || !f1 || !flow || !bgmask || n <= 0 || S <= 0)
+    return lasr_fail("flow_epilogue_forward: bad arguments");
+  const int SS = S * S;
+  flow_epilogue_forward_kernel<<<dim3((SS + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(px, pp0, pp1, f0, f1, flow,
+                                                                                             bgmask, n, SS);
+  return lasr_check_launch("flow_epilogue_forward_kernel");
+}
+
+extern "C" int lasr_b200_flow_epilogue_backward(const float* px, const float* f1, const float* grad_flow,
+                                                float* grad_px, float* grad_pp1, float* grad_f1, void* workspace,
+                                                size_t workspace_bytes, int n, int S, void* stream) {
+  if (!px || !f1 || !grad_flow || !grad_px || !grad_pp1 || !grad_f1 || n <= 0 || S <= 0)
+    return lasr_fail("flow_epilogue_backward: bad arguments");
+  if (!workspace || workspace_bytes < lasr_b200_flow_epilogue_workspace_bytes(n, S))
+    return lasr_fail("flow_epilogue_backward: workspace too small");
+  const int SS = S * S, nblk = (SS + 255) / 256;
+  float* partial = reinterpret_cast<float*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  flow_epilogue_backward_kernel<<<dim3(nblk, n), 256, 0, st>>>(px, f1, grad_flow, grad_px, partial, n, SS, nblk);
+  if (lasr_check_launch("flow_epilogue_backward_kernel")) return 1;
+  flow_epilogue_reduce_kernel<<<(n * 3 + 127) / 128, 128, 0, st>>>(partial, n, nblk, grad_pp1, grad_f1);
+  return lasr_check_launch("flow_epilogue_reduce_kernel");
 }

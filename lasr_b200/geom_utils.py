@@ -132,6 +132,39 @@ def _reproject(pos_px, pp, fl):
     return torch.stack([x, y], dim=-1)
 
 
+class _FlowEpilogue(torch.autograd.Function):
+    """mesh_net.py:88-104 on CUDA tensors in one kernel (lasr_b200_flow_epilogue_forward/backward)."""
+
+    @staticmethod
+    def forward(ctx, px, pp0, pp1, f0, f1):
+        from . import _cabi
+        n2, _, S, _ = px.shape
+        n = n2 // 2
+        pxc = px.detach().float().contiguous()
+        c = lambda t, sh: t.detach().float().reshape(sh).contiguous()
+        pp0c, pp1c, f0c, f1c = c(pp0, (n, 2)), c(pp1, (n, 2)), c(f0, (n,)), c(f1, (n,))
+        flow = torch.empty(n, S, S, 2, dtype=torch.float32, device=px.device)
+        bg = torch.empty(n, S, S, dtype=torch.uint8, device=px.device)
+        _cabi.flow_epilogue_forward(pxc, pp0c, pp1c, f0c, f1c, flow, bg, n, S)
+        ctx.save_for_backward(pxc, f1c)
+        ctx.shapes = (pp1.shape, f1.shape)
+        bgb = bg.bool()
+        ctx.mark_non_differentiable(bgb)
+        return flow, bgb
+
+    @staticmethod
+    def backward(ctx, gflow, _gbg):
+        from . import _cabi
+        pxc, f1c = ctx.saved_tensors
+        n2, _, S, _ = pxc.shape
+        n = n2 // 2
+        gpx = torch.empty_like(pxc)
+        gpp1 = torch.empty(n, 2, dtype=torch.float32, device=pxc.device)
+        gf1 = torch.empty(n, dtype=torch.float32, device=pxc.device)
+        _cabi.flow_epilogue_backward(pxc, f1c, gflow.float().contiguous(), gpx, gpp1, gf1, n, S)
+        return gpx, None, gpp1.reshape(ctx.shapes[0]), None, gf1.reshape(ctx.shapes[1])
+
+
 def render_flow_soft_2(renderer_soft, verts, faces, verts_pos0, verts_pos1, pp0, pp1, proj_cam0, proj_cam1,
                        shared_faces=None):
     """Render the 3-D positions of two frames as vertex 'colours' through the soft rasterizer and
@@ -147,6 +180,9 @@ def render_flow_soft_2(renderer_soft, verts, faces, verts_pos0, verts_pos1, pp0,
                                            textures=torch.cat([verts_pos0[:, :, :3], verts_pos1[:, :, :3]], 0),
                                            texture_type="vertex", shared_faces=shared_faces))
     fgmask = px[:nb, -1]
+    if px.is_cuda:
+        flow_fw, bgmask = _FlowEpilogue.apply(px, pp0, pp1, proj_cam0[:, :1], proj_cam1[:, :1])
+        return flow_fw, bgmask, fgmask
     px = px[:, :3]
     pos0 = px[:nb].permute(0, 2, 3, 1)
     pos1 = px[nb:].permute(0, 2, 3, 1)
