@@ -5,6 +5,7 @@ TAG=${1:-r1}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 python -m pytest tests -q -m gpu > $OUT/pytest_gpu.log 2>&1; tail -3 $OUT/pytest_gpu.log
+python tests/golden/make_softras_golden.py $OUT/golden --report-only > $OUT/golden_report.log 2>&1; tail -2 $OUT/golden_report.log
 python bench.py --steps 50 --warmup 5 --extras > $OUT/bench_ours.json 2> $OUT/bench_ours.err
 python bench.py --impl reference --steps 10 --warmup 3 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
 for cfg in "ico3 256 64" "ico4 256 64" "ico5 512 32"; do set -- $cfg

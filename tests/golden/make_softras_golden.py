@@ -79,7 +79,9 @@ def three_way(name, c, report):
 
 
 def main():
-    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    report_only = "--report-only" in sys.argv      # re-measure the gaps without re-minting the vectors
+    out = args[0] if args else os.path.join(ROOT, "gpurun_out", "golden")
     os.makedirs(out, exist_ok=True)
     report = {}
     for name, ctor in cases.GOLDEN_CASES.items():
@@ -87,6 +89,8 @@ def main():
         ref_img, ref_gf, ref_gt = three_way(name, c, report)
         h = hashlib.sha256(c["face_vertices"].tobytes() + c["textures"].tobytes()
                            + c["grad_soft_colors"].tobytes()).hexdigest()
+        if report_only:
+            continue
         np.savez_compressed(os.path.join(out, f"softras_ref_{name}.npz"), soft_colors=ref_img,
                             grad_faces=ref_gf, grad_textures=ref_gt, inputs_sha256=np.array(h),
                             settings=np.array(json.dumps(c["settings"])))
