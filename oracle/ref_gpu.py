@@ -137,3 +137,126 @@ def render_mesh_lasr(vertices, faces, textures, eye, settings):
     v = torch.matmul(vertices - e[:, None], r.transpose(1, 2))
     v = torch.stack((v[:, :, 0] * 1.0, v[:, :, 1] * 1.0, v[:, :, 2]), dim=2)  # orthogonal(scale=1)
     return soft_rasterize(_face_gather(v, faces), _face_gather(textures, faces), **settings)
+
+
+# ---- the whole hot-path region of LASR.forward, reference style -------------------------------
+def _ref_obj_to_cam(verts, Rmat, Tmat, nmesh, skin):
+    """nnutils/geom_utils.py:45-71 as the reference executes it: one matmul per bone, cat, weighted sum."""
+    verts, Rmat, Tmat = verts.clone(), Rmat.clone(), Tmat.clone()
+    bodyR, bodyT = Rmat[::nmesh].clone(), Tmat[::nmesh].clone()
+    if nmesh > 1:
+        parts = []
+        for k in range(nmesh - 1):
+            parts.append((verts.matmul(Rmat[k + 1::nmesh].clone()) + Tmat[k + 1::nmesh].clone())[:, None])
+        vs = (torch.cat(parts, 1) * skin).sum(1)
+    else:
+        vs = verts
+    return vs.clone().matmul(bodyR) + bodyT
+
+
+def _ref_pinhole(verts, pp, fl):
+    """nnutils/geom_utils.py:27-34 (clones + in-place slice assigns)."""
+    n_hypo = verts.shape[0] // pp.shape[0]
+    pp = pp.clone()[:, None].repeat(1, n_hypo, 1).view(-1, 2)
+    fl = fl.clone()[:, None].view(-1, 1)
+    verts = verts.clone()
+    verts[:, :, 1] = pp[:, 1:2] + verts[:, :, 1].clone() * fl / verts[:, :, 2].clone()
+    verts[:, :, 0] = pp[:, 0:1] + verts[:, :, 0].clone() * fl / verts[:, :, 2].clone()
+    return verts
+
+
+def _ref_render_flow(verts, faces, pos0, pos1, pp0, pp1, f0, f1, eye, settings):
+    """nnutils/mesh_net.py:75-104 with the reference kernels."""
+    n_hypo = verts.shape[0] // faces.shape[0]
+    faces = faces[:, None].repeat(1, n_hypo, 1, 1).view(-1, faces.shape[1], 3)
+    pos0, pos1 = pos0.clone(), pos1.clone()
+    pre = verts[:, :, :3] + eye[None, None]
+    pre[:, :, 1] = -1 * pre[:, :, 1]
+    nb = verts.shape[0]
+    px = render_mesh_lasr(torch.cat([pre, pre], 0), torch.cat([faces, faces], 0),
+                          torch.cat([pos0[:, :, :3], pos1[:, :, :3]], 0), eye, settings).clone()
+    fg = px[:nb, -1]
+    px = px[:, :3]
+    p0 = px[:nb].permute(0, 2, 3, 1)
+    p1 = px[nb:].permute(0, 2, 3, 1)
+    bg = (p0[:, :, :, 2] < 1e-9) | (p1[:, :, :, 2] < 1e-9)
+    p0[bg] = 10
+    p1[bg] = 10
+    p0[:, :, :, 1] = pp0[:, 1:2, None] + p0[:, :, :, 1].clone() * f0[:, :1, None] / p0[:, :, :, 2].clone()
+    p0[:, :, :, 0] = pp0[:, 0:1, None] + p0[:, :, :, 0].clone() * f0[:, :1, None] / p0[:, :, :, 2].clone()
+    p1[:, :, :, 1] = pp1[:, 1:2, None] + p1[:, :, :, 1].clone() * f1[:, :1, None] / p1[:, :, :, 2].clone()
+    p1[:, :, :, 0] = pp1[:, 0:1, None] + p1[:, :, :, 0].clone() * f1[:, :1, None] / p1[:, :, :, 2].clone()
+    flow = (p1 - p0.detach())[:, :, :, :2]
+    flow[bg] = flow[bg].detach()
+    return flow, bg, fg
+
+
+def lasr_region_reference(pred_v, tex, faces, Rmat, Tmat, ppoint, scale, batch, n_hypo, n_bones, S, skin, eye,
+                          sigval=1e-4, l1tex_wt=1.0):
+    """Restatement of nnutils/mesh_net.py:298-447 (LBS -> projection -> near/far with the host sync ->
+    flow fw / bw renders -> texture render -> mask / flow / texture-L1 losses in Python double loops)
+    on the reference's own kernels.  Skin weights and the rest-pose bone transforms are taken as inputs.
+    Bench / comparison infrastructure only."""
+    H, B = n_hypo, n_bones
+    n2 = ppoint.shape[0]
+    bs = n2 // 2
+    vfl = _ref_obj_to_cam(pred_v, Rmat, Tmat[:, None, :], B, skin)
+    vfl = torch.cat([vfl, torch.ones_like(vfl[:, :, 0:1])], dim=-1)
+    pos0 = vfl.view(n2, H, -1, 4)[:bs].clone().view(bs * H, -1, 4)
+    pos1 = vfl.view(n2, H, -1, 4)[bs:].clone().view(bs * H, -1, 4)
+    vpx = _ref_pinhole(vfl, ppoint, scale)
+    dmax, dmin = vpx[:, :, -2].max(), vpx[:, :, -2].min()
+    near, far = float(dmin - (dmax - dmin) / 2), float(dmax + (dmax - dmin) / 2)   # pybind `float` coercion = sync
+    st = dict(image_size=S, background_color=[0, 0, 0], near=near, far=far, fill_back=True, eps=1e-3, sigma_val=sigval,
+              dist_func="euclidean", dist_eps=1e-4, gamma_val=1e-2, aggr_func_rgb="softmax", aggr_func_alpha="prod",
+              texture_type="vertex")
+    v4 = vpx.view(n2, H, -1, 4)
+    rp = lambda t, lo, hi: t[:, None][lo:hi].repeat(1, H, 1).view(-1, 2)
+    sc = scale.view(n2, H, 1)
+    ffw, bgf, _ = _ref_render_flow(v4[:bs].reshape(bs * H, -1, 4), faces[:bs], pos0, pos1, rp(ppoint, 0, bs),
+                                   rp(ppoint, bs, n2), sc[:bs].reshape(-1, 1), sc[bs:].reshape(-1, 1), eye, st)
+    fbw, bgb, _ = _ref_render_flow(v4[bs:].reshape(bs * H, -1, 4), faces[bs:], pos1, pos0, rp(ppoint, bs, n2),
+                                   rp(ppoint, 0, bs), sc[bs:].reshape(-1, 1), sc[:bs].reshape(-1, 1), eye, st)
+    bgmask = torch.cat([bgf, bgb], 0)
+    flow_rd = torch.cat([ffw, fbw], 0)
+    pre = vpx[:, :, :3] + eye[None, None]
+    pre[:, :, 1] = -1 * pre[:, :, 1]
+    rend = render_mesh_lasr(pre, faces[:, None].repeat(1, H, 1, 1).view(-1, faces.shape[1], 3), tex, eye,
+                            dict(st, background_color=[1, 1, 1])).clone()
+    mask_pred_all, rgb = rend[:, -1], rend[:, :3]
+    masks, occ, imgs, flow = batch["masks"], batch["occ"], batch["imgs"], batch["flow"]
+    img_obs = imgs * (masks > 0).float()[:, None]
+    img_rnd = rgb * mask_pred_all[:, None]
+    img_white = 1 - (masks > 0).float()[:, None] + img_obs
+    # 1) mask loss (:374-390)
+    mask_pred = mask_pred_all.view(n2, -1, S, S)
+    msub = (mask_pred - masks[:, None]).pow(2)
+    tmp = torch.zeros(n2, H, device=pred_v.device)
+    for i in range(n2):
+        for j in range(H):
+            tmp[i, j] = msub[i, j][occ[i] != 0].mean()
+    mask_loss = (0.5 * tmp).mean()
+    # 2) flow loss (:393-416)
+    frd = flow_rd.view(n2, -1, S, S, 2)
+    mask = (~bgmask).view(n2, -1, S, S) & ((occ != 0)[:, None] & (masks > 0)[:, None]).repeat(1, H, 1, 1)
+    fmap = torch.norm((frd - flow[:, None, :2].permute(0, 1, 3, 4, 2)), 2, -1)
+    w = (-occ).sigmoid()[:, None].repeat(1, H, 1, 1)
+    for i in range(n2):
+        w[i] = w[i] / w[i][mask[i]].mean()
+    fmap = fmap * w
+    tmp = torch.zeros(n2, H, device=pred_v.device)
+    for i in range(n2):
+        for j in range(H):
+            tmp[i, j] = fmap[i, j][mask[i, j]].mean()
+            if mask[i, j].sum() == 0:
+                tmp[i, j] = 0
+    flow_loss = (0.5 * tmp).mean()
+    # 3) texture L1 (:420-441, LPIPS term excluded)
+    tmp = torch.zeros(n2, H, device=pred_v.device)
+    for i in range(n2):
+        for j in range(H):
+            tmp[i, j] += (img_obs[i] - img_rnd.view(n2, -1, 3, S, S)[i, j]).abs().mean(0)[occ[i] != 0].mean()
+            tmp[i, j] += (img_white[i] - rgb.view(n2, -1, 3, S, S)[i, j]).abs().mean(0)[occ[i] != 0].mean()
+            tmp[i, j] *= 2 * l1tex_wt
+    tex_loss = (0.25 * tmp).mean()
+    return mask_loss + flow_loss + tex_loss, mask_loss, flow_loss, tex_loss
