@@ -97,13 +97,19 @@ int lasr_b200_raster_backward(const float* faces, const float* textures, const f
  * tensors never exist in HBM.
  *   verts   [N,V,3]  clip-space vertices (what SoftRasterizer receives as mesh.vertices)
  *   tri     [F,3]    int32 topology shared by the N frames
- *   vcolors [N,V,3]  vertex colours
+ *   vcolors [K,N,V,3] vertex colours: num_sets = K (1, 2 or 3) colour sets interpolated in ONE geometry
+ *                    pass (K > 1 needs LASR's configuration: euclidean / softmax / prod / fill_back).
+ *                    LASR renders the same posed mesh three times per frame with different vertex
+ *                    attributes -- forward flow, backward flow, texture (nnutils/mesh_net.py:318-363);
+ *                    with K sets those share the per-pixel distance / depth-softmax work.
+ *   soft_colors / grad_soft_colors [N,3K+1,S,S]: planes 3s..3s+2 = set s, plane 3K = alpha (K = 1 is
+ *                    the reference's RGBA layout); soft_colors arrives pre-filled with the backgrounds
  *   csr_offsets [V+1], csr_entries [3F] (entry = face*3 + corner, grouped by vertex, ascending):
  *                    vertex -> corner adjacency used to sum per-face gradients in a fixed order
- *   grad_verts, grad_vcolors [N,V,3] out (overwritten)
+ *   grad_verts [N,V,3], grad_vcolors [K,N,V,3] out (overwritten)
  * Other arguments as lasr_b200_raster_forward/backward (texture_sample_type is 'vertex').
  * ------------------------------------------------------------------------------------------- */
-size_t lasr_b200_render_workspace_bytes(int batch_size, int num_faces, int image_size);
+size_t lasr_b200_render_workspace_bytes(int batch_size, int num_faces, int image_size, int num_sets);
 
 int lasr_b200_render_forward(const float* verts, const int32_t* tri, const float* vcolors,
                              float* aggrs_info, float* soft_colors, void* workspace,
@@ -111,7 +117,7 @@ int lasr_b200_render_forward(const float* verts, const int32_t* tri, const float
                              int image_size, float near_, float far_, const float* near_far_dev,
                              float eps, float sigma_val, int func_id_dist, float dist_eps,
                              float gamma_val, int func_id_rgb, int func_id_alpha, int double_side,
-                             void* stream);
+                             int num_sets, void* stream);
 
 int lasr_b200_render_backward(const float* verts, const int32_t* tri, const float* vcolors,
                               const float* soft_colors, const float* aggrs_info,
@@ -121,7 +127,8 @@ int lasr_b200_render_backward(const float* verts, const int32_t* tri, const floa
                               int num_vertices, int num_faces, int image_size, float near_,
                               float far_, const float* near_far_dev, float eps, float sigma_val,
                               int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
-                              int func_id_alpha, int double_side, int setup_done, void* stream);
+                              int func_id_alpha, int double_side, int num_sets, int setup_done,
+                              void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused linear-blend skinning + body transform + pinhole projection + batch depth window
@@ -210,6 +217,34 @@ int lasr_b200_flow_epilogue_forward(const float* px, const float* pp0, const flo
 int lasr_b200_flow_epilogue_backward(const float* px, const float* f1, const float* grad_flow, float* grad_px,
                                      float* grad_pp1, float* grad_f1, void* workspace, size_t workspace_bytes,
                                      int num_frames, int image_size, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused image head of the three-set render (SURVEY 8a rows R1 epilogue + L1-L3 in one pass).
+ * `image` [N*H,10,S,S] is the output of lasr_b200_render_forward with num_sets = 3 and colour sets
+ * (own camera-space positions, the paired frame's positions, texture): planes 0-2 / 3-5 / 6-8 and the
+ * silhouette in plane 9.  Per frame it re-projects both position sets with the frame's own and its
+ * pair's intrinsics (render_flow_soft_2's post-processing, nnutils/mesh_net.py:88-104; the forward AND
+ * the backward flow, :318-335, in one call because frame i of the first half pairs with i+bs and vice
+ * versa) and accumulates the seven masked sums of lasr_b200_losses_forward (mesh_net.py:372-447).
+ *   pp_own, pp_pair [N*H,2]; f_own, f_pair [N*H]; imgs, masks, occ, flow_obs as lasr_b200_losses_forward
+ *   sums [N,H,7] out; flow_rd [N*H,S,S,2] and bgmask [N*H,S,S] (uint8) optional outputs (both or none)
+ * backward: grad_sums [N,H,7] (from lasr_b200_losses_coefficients) -> grad_image [N*H,10,S,S] (all
+ * planes written), grad_pp_pair [N*H,2], grad_f_pair [N*H].  Deterministic.
+ * ------------------------------------------------------------------------------------------- */
+size_t lasr_b200_head_workspace_bytes(int N, int H, int image_size);
+
+int lasr_b200_head_forward(const float* image, const float* pp_own, const float* pp_pair,
+                           const float* f_own, const float* f_pair, const float* imgs,
+                           const float* masks, const float* occ, const float* flow_obs, float* sums,
+                           float* flow_rd, uint8_t* bgmask, void* workspace, size_t workspace_bytes,
+                           int N, int H, int image_size, void* stream);
+
+int lasr_b200_head_backward(const float* image, const float* pp_own, const float* pp_pair,
+                            const float* f_own, const float* f_pair, const float* imgs,
+                            const float* masks, const float* occ, const float* flow_obs,
+                            const float* grad_sums, float* grad_image, float* grad_pp_pair,
+                            float* grad_f_pair, void* workspace, size_t workspace_bytes, int N, int H,
+                            int image_size, void* stream);
 
 #ifdef __cplusplus
 }

@@ -45,14 +45,20 @@ def lib():
         L.lasr_b200_raster_backward.restype = _c.c_int
         L.lasr_b200_raster_backward.argtypes = [_c.c_void_p] * 8 + [_c.c_size_t] + _RASTER_SCALARS + [_c.c_int, _c.c_void_p]
         L.lasr_b200_render_workspace_bytes.restype = _c.c_size_t
-        L.lasr_b200_render_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
+        L.lasr_b200_render_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int, _c.c_int]
         _render_scalars = [_c.c_int] * 4 + [_c.c_float, _c.c_float, _c.c_void_p, _c.c_float, _c.c_float, _c.c_int,
-                                            _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_int]
+                                            _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_render_forward.restype = _c.c_int
         L.lasr_b200_render_forward.argtypes = [_c.c_void_p] * 6 + [_c.c_size_t] + _render_scalars + [_c.c_void_p]
         L.lasr_b200_render_backward.restype = _c.c_int
         L.lasr_b200_render_backward.argtypes = ([_c.c_void_p] * 11 + [_c.c_size_t] + _render_scalars
                                                 + [_c.c_int, _c.c_void_p])
+        L.lasr_b200_head_workspace_bytes.restype = _c.c_size_t
+        L.lasr_b200_head_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
+        L.lasr_b200_head_forward.restype = _c.c_int
+        L.lasr_b200_head_forward.argtypes = [_c.c_void_p] * 13 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
+        L.lasr_b200_head_backward.restype = _c.c_int
+        L.lasr_b200_head_backward.argtypes = [_c.c_void_p] * 14 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
         L.lasr_b200_losses_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_losses_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_losses_forward.restype = _c.c_int
@@ -87,6 +93,7 @@ EXPORTED_SYMBOLS = [
     "lasr_b200_losses_finalize", "lasr_b200_losses_coefficients",
     "lasr_b200_flow_epilogue_workspace_bytes", "lasr_b200_flow_epilogue_forward", "lasr_b200_flow_epilogue_backward",
     "lasr_b200_lbs_workspace_bytes", "lasr_b200_lbs_project_forward", "lasr_b200_lbs_project_backward",
+    "lasr_b200_head_workspace_bytes", "lasr_b200_head_forward", "lasr_b200_head_backward",
 ]
 
 
@@ -198,15 +205,27 @@ def lbs_project_backward(verts, Rmat, Tmat, skin, pp, fl, grad_cam, grad_px, gra
     _check(rc, "lasr_b200_lbs_project_backward")
 
 
-def render_workspace(N: int, F: int, S: int, device) -> torch.Tensor:
-    return torch.empty(int(lib().lasr_b200_render_workspace_bytes(N, F, S)), dtype=torch.uint8, device=device)
+def render_workspace(N: int, F: int, S: int, device, num_sets: int = 1) -> torch.Tensor:
+    nbytes = int(lib().lasr_b200_render_workspace_bytes(N, F, S, num_sets))
+    if nbytes == 0:
+        raise RuntimeError("render: bad sizes (num_sets must be 1, 2 or 3)")
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
 def _render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
-                        func_id_rgb, func_id_alpha, double_side):
+                        func_id_rgb, func_id_alpha, double_side, num_sets):
     return (N, V, F, int(S), float(near), float(far), _p(near_far_dev), float(eps), float(sigma_val),
             int(func_id_dist), float(dist_eps), float(gamma_val), int(func_id_rgb), int(func_id_alpha),
-            int(bool(double_side)))
+            int(bool(double_side)), int(num_sets))
+
+
+def _num_sets(verts, vcolors):
+    """vcolors [N,V,3] -> 1; [K,N,V,3] -> K."""
+    if vcolors.dim() == verts.dim():
+        return 1
+    if vcolors.dim() != verts.dim() + 1 or tuple(vcolors.shape[1:]) != tuple(verts.shape):
+        raise RuntimeError("vcolors must be [N,V,3] or [K,N,V,3]")
+    return int(vcolors.shape[0])
 
 
 def render_forward(verts, tri, vcolors, aggrs_info, soft_colors, workspace, S, near, far, near_far_dev, eps,
@@ -217,11 +236,14 @@ def render_forward(verts, tri, vcolors, aggrs_info, soft_colors, workspace, S, n
         raise RuntimeError("tri must be a contiguous CUDA int32 tensor [F,3]")
     N, V = verts.shape[:2]
     F = tri.shape[0]
+    K = _num_sets(verts, vcolors)
+    if tuple(soft_colors.shape[:2]) != (N, 3 * K + 1):
+        raise RuntimeError("soft_colors must be [N,3K+1,S,S]")
     with torch.cuda.device(verts.device):
         rc = lib().lasr_b200_render_forward(
             _p(verts), _p(tri), _p(vcolors), _p(aggrs_info), _p(soft_colors), _p(workspace), workspace.numel(),
             *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
-                                 gamma_val, func_id_rgb, func_id_alpha, double_side), _stream_ptr())
+                                 gamma_val, func_id_rgb, func_id_alpha, double_side, K), _stream_ptr())
     _check(rc, "lasr_b200_render_forward")
 
 
@@ -232,12 +254,15 @@ def render_backward(verts, tri, vcolors, soft_colors, aggrs_info, grad_soft_colo
         _require_cuda_f32(t, "render tensor")
     N, V = verts.shape[:2]
     F = tri.shape[0]
+    K = _num_sets(verts, vcolors)
+    if grad_vcolors.shape != vcolors.shape or grad_soft_colors.shape != soft_colors.shape:
+        raise RuntimeError("render_backward: gradient shapes must match vcolors / soft_colors")
     with torch.cuda.device(verts.device):
         rc = lib().lasr_b200_render_backward(
             _p(verts), _p(tri), _p(vcolors), _p(soft_colors), _p(aggrs_info), _p(grad_soft_colors), _p(csr_offsets),
             _p(csr_entries), _p(grad_verts), _p(grad_vcolors), _p(workspace), workspace.numel(),
             *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
-                                 gamma_val, func_id_rgb, func_id_alpha, double_side), int(bool(setup_done)),
+                                 gamma_val, func_id_rgb, func_id_alpha, double_side, K), int(bool(setup_done)),
             _stream_ptr())
     _check(rc, "lasr_b200_render_backward")
 
@@ -271,6 +296,32 @@ def losses_coefficients(sums, g3, gsub, gsums, N, H, l1tex_wt):
         rc = lib().lasr_b200_losses_coefficients(_p(sums), _p(g3), _p(gsub), _p(gsums), N, H, float(l1tex_wt),
                                                  _stream_ptr())
     _check(rc, "lasr_b200_losses_coefficients")
+
+
+def head_forward(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, sums, flow_rd, bgmask, N, H, S):
+    for t in (image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, sums):
+        _require_cuda_f32(t, "head tensor")
+    if tuple(image.shape) != (N * H, 10, S, S):
+        raise RuntimeError("head: image must be [N*H,10,S,S] (three colour sets + silhouette)")
+    ws = torch.empty(int(lib().lasr_b200_head_workspace_bytes(N, H, S)), dtype=torch.uint8, device=image.device)
+    with torch.cuda.device(image.device):
+        rc = lib().lasr_b200_head_forward(_p(image), _p(pp_own), _p(pp_pair), _p(f_own), _p(f_pair), _p(imgs),
+                                          _p(masks), _p(occ), _p(flow_obs), _p(sums), _p(flow_rd), _p(bgmask), _p(ws),
+                                          ws.numel(), N, H, S, _stream_ptr())
+    _check(rc, "lasr_b200_head_forward")
+
+
+def head_backward(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, grad_sums, grad_image,
+                  grad_pp_pair, grad_f_pair, N, H, S):
+    for t in (image, grad_sums, grad_image, grad_pp_pair, grad_f_pair):
+        _require_cuda_f32(t, "head tensor")
+    ws = torch.empty(int(lib().lasr_b200_head_workspace_bytes(N, H, S)), dtype=torch.uint8, device=image.device)
+    with torch.cuda.device(image.device):
+        rc = lib().lasr_b200_head_backward(_p(image), _p(pp_own), _p(pp_pair), _p(f_own), _p(f_pair), _p(imgs),
+                                           _p(masks), _p(occ), _p(flow_obs), _p(grad_sums), _p(grad_image),
+                                           _p(grad_pp_pair), _p(grad_f_pair), _p(ws), ws.numel(), N, H, S,
+                                           _stream_ptr())
+    _check(rc, "lasr_b200_head_backward")
 
 
 def flow_epilogue_forward(px, pp0, pp1, f0, f1, flow, bgmask, n, S):

@@ -319,6 +319,200 @@ __global__ void flow_epilogue_reduce_kernel(const float* partial, int n, int nbl
   if (k < 2) gpp1[2 * i + k] = acc; else gf1[i] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused image head for the three-set render (lasr_b200_render_forward with num_sets = 3): the image
+// [N*H,10,S,S] holds, per frame, the camera-space position of the frame's own pose (planes 0-2), of
+// its pair's pose (3-5), the texture (6-8) and the silhouette (9).  One pass does the work of the flow
+// epilogue above for BOTH flow directions (frame i of the first half pairs with i+bs and vice versa;
+// the caller passes per-frame own / pair intrinsics) and of losses_forward_kernel, without the
+// flow / bgmask / texture / mask intermediates in HBM; its adjoint writes the whole image gradient.
+// Arithmetic is that of flow_epilogue_* and losses_* above, expression for expression.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHeadPlanes = 10;
+
+struct HeadArgs {
+  const float* image;      // [N*H,10,S,S]
+  const float* pp_own;     // [N*H,2]
+  const float* pp_pair;    // [N*H,2]
+  const float* f_own;      // [N*H]
+  const float* f_pair;     // [N*H]
+  const float* imgs;       // [N,3,S,S]
+  const float* masks;      // [N,S,S]
+  const float* occ;        // [N,S,S]
+  const float* flow_obs;   // [N,3,S,S]
+  int N, H, SS;
+};
+
+struct HeadFlow { float fx, fy, x1, y1, z1; bool bg; };
+
+__device__ __forceinline__ HeadFlow head_flow(const HeadArgs& A, const float* img, int ij, int p) {
+  const long long SS = A.SS;
+  float x0 = img[p], y0 = img[SS + p], z0 = img[2 * SS + p];
+  float x1 = img[3 * SS + p], y1 = img[4 * SS + p], z1 = img[5 * SS + p];
+  HeadFlow r;
+  r.bg = z0 < 1e-9f || z1 < 1e-9f;
+  if (r.bg) { x0 = y0 = z0 = 10.f; x1 = y1 = z1 = 10.f; }
+  const float f0 = A.f_own[ij], f1 = A.f_pair[ij];
+  const float u0 = A.pp_own[2 * ij] + x0 * f0 / z0, v0 = A.pp_own[2 * ij + 1] + y0 * f0 / z0;
+  const float u1 = A.pp_pair[2 * ij] + x1 * f1 / z1, v1 = A.pp_pair[2 * ij + 1] + y1 * f1 / z1;
+  r.fx = u1 - u0; r.fy = v1 - v0; r.x1 = x1; r.y1 = y1; r.z1 = z1;
+  return r;
+}
+
+__global__ void __launch_bounds__(kLossThreads) head_forward_kernel(HeadArgs A, float* partial, int nblk,
+                                                                    float* flow_out, uint8_t* bg_out) {
+  __shared__ float s_w[kLossThreads / 32][kNumSums];
+  const int ij = blockIdx.y;
+  const int i = ij / A.H;
+  const long long SS = A.SS;
+  const float* img = A.image + (long long)ij * kHeadPlanes * SS;
+  float acc[kNumSums];
+#pragma unroll
+  for (int q = 0; q < kNumSums; ++q) acc[q] = 0.f;
+  const int p0 = blockIdx.x * kLossPixPerBlock;
+  const int p1 = min(p0 + kLossPixPerBlock, A.SS);
+  for (int p = p0 + threadIdx.x; p < p1; p += kLossThreads) {
+    const float occ = A.occ[i * SS + p];
+    const float m = A.masks[i * SS + p];
+    const bool v = occ != 0.f;
+    const bool fgm = m > 0.f;
+    const float alpha = img[9 * SS + p];
+    if (v) {
+      acc[6] += 1.f;
+      const float d = alpha - m;
+      acc[0] += d * d;
+    }
+    if ((v && fgm) || flow_out) {
+      const HeadFlow fl = head_flow(A, img, ij, p);
+      if (flow_out) {
+        reinterpret_cast<float2*>(flow_out)[ij * SS + p] = make_float2(fl.fx, fl.fy);
+        bg_out[ij * SS + p] = fl.bg ? 1 : 0;
+      }
+      if (v && fgm && !fl.bg) {
+        const float dx = fl.fx - A.flow_obs[(i * 3 + 0) * SS + p];
+        const float dy = fl.fy - A.flow_obs[(i * 3 + 1) * SS + p];
+        const float s = 1.f / (1.f + expf(occ));
+        acc[1] += s * sqrtf(dx * dx + dy * dy);
+        acc[2] += s;
+        acc[3] += 1.f;
+      }
+    }
+    if (v) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float im = A.imgs[(i * 3 + c) * SS + p];
+        const float obs = fgm ? im : 0.f;
+        const float white = fgm ? im : 1.f;
+        const float t = img[(6 + c) * SS + p];
+        a += fabsf(obs - t * alpha);
+        b += fabsf(white - t);
+      }
+      acc[4] += a * (1.f / 3.f);
+      acc[5] += b * (1.f / 3.f);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < kNumSums; ++q) {
+    const float w = wsum(acc[q]);
+    if (lane == 0) s_w[warp][q] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumSums) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLossThreads / 32; ++w) t += s_w[w][threadIdx.x];
+    partial[((long long)ij * nblk + blockIdx.x) * kNumSums + threadIdx.x] = t;
+  }
+}
+
+// gsums [N,H,7] -> grad_image [N*H,10,S,S] (every plane written) + per-block partials of the pair
+// intrinsics' gradients: partial [N*H][nblk][3] = (d pp_pair.x, d pp_pair.y, d f_pair)
+__global__ void __launch_bounds__(256) head_backward_kernel(HeadArgs A, const float* gsums, float* gimage,
+                                                            float* partial, int nblk) {
+  __shared__ float s_w[8][3];
+  const int ij = blockIdx.y;
+  const int i = ij / A.H;
+  const long long SS = A.SS;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc[3] = {0.f, 0.f, 0.f};
+  if (p < A.SS) {
+    const float* img = A.image + (long long)ij * kHeadPlanes * SS;
+    float* go = gimage + (long long)ij * kHeadPlanes * SS + p;
+    const float g0 = gsums[ij * kNumSums + 0], g1 = gsums[ij * kNumSums + 1];
+    const float g4 = gsums[ij * kNumSums + 4], g5 = gsums[ij * kNumSums + 5];
+    const float occ = A.occ[i * SS + p];
+    const float m = A.masks[i * SS + p];
+    const bool v = occ != 0.f;
+    const bool fgm = m > 0.f;
+    const float alpha = img[9 * SS + p];
+    float galpha = v ? 2.f * (alpha - m) * g0 : 0.f;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (v && fgm) {
+      const HeadFlow fl = head_flow(A, img, ij, p);
+      if (!fl.bg) {
+        const float dx = fl.fx - A.flow_obs[(i * 3 + 0) * SS + p];
+        const float dy = fl.fy - A.flow_obs[(i * 3 + 1) * SS + p];
+        const float nrm = sqrtf(dx * dx + dy * dy);
+        if (nrm > 0.f) {
+          const float c = g1 / (1.f + expf(occ)) / nrm;
+          const float ox = c * dx, oy = c * dy;
+          const float f = A.f_pair[ij], iz = 1.f / fl.z1;
+          gx = ox * f * iz;
+          gy = oy * f * iz;
+          gz = -(ox * fl.x1 + oy * fl.y1) * f * iz * iz;
+          acc[0] = ox; acc[1] = oy; acc[2] = (ox * fl.x1 + oy * fl.y1) * iz;
+        }
+      }
+    }
+    go[0] = 0.f; go[SS] = 0.f; go[2 * SS] = 0.f;
+    go[3 * SS] = gx; go[4 * SS] = gy; go[5 * SS] = gz;
+    float gfg = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float gt = 0.f;
+      if (v) {
+        const float im = A.imgs[(i * 3 + c) * SS + p];
+        const float obs = fgm ? im : 0.f;
+        const float white = fgm ? im : 1.f;
+        const float t = img[(6 + c) * SS + p];
+        const float ra = obs - t * alpha, rb = white - t;
+        const float sa = ra > 0.f ? 1.f : (ra < 0.f ? -1.f : 0.f);
+        const float sb = rb > 0.f ? 1.f : (rb < 0.f ? -1.f : 0.f);
+        gt = (-sa * alpha * g4 - sb * g5) * (1.f / 3.f);
+        gfg += -sa * t * g4 * (1.f / 3.f);
+      }
+      go[(6 + c) * SS] = gt;
+    }
+    go[9 * SS] = galpha + gfg;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float w = wsum(acc[k]);
+    if (lane == 0) s_w[warp][k] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_w[w][threadIdx.x];
+    partial[((long long)ij * nblk + blockIdx.x) * 3 + threadIdx.x] = t;
+  }
+}
+
+static int fill_head(HeadArgs& A, const float* image, const float* pp_own, const float* pp_pair, const float* f_own,
+                     const float* f_pair, const float* imgs, const float* masks, const float* occ,
+                     const float* flow_obs, int N, int H, int S) {
+  if (N <= 0 || H <= 0 || S <= 0) return lasr_fail("head: N, H, S must be positive");
+  if (!image || !pp_own || !pp_pair || !f_own || !f_pair || !imgs || !masks || !occ || !flow_obs)
+    return lasr_fail("head: null tensor pointer");
+  A.image = image; A.pp_own = pp_own; A.pp_pair = pp_pair; A.f_own = f_own; A.f_pair = f_pair;
+  A.imgs = imgs; A.masks = masks; A.occ = occ; A.flow_obs = flow_obs;
+  A.N = N; A.H = H; A.SS = S * S;
+  return 0;
+}
+
 static int fill_loss(LossArgs& A, const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
                      const float* tex, const float* fg, const float* imgs, const float* masks, const float* occ,
                      const float* flow_obs, int N, int H, int S) {
@@ -421,5 +615,53 @@ extern "C" int lasr_b200_flow_epilogue_backward(const float* px, const float* f1
   flow_epilogue_backward_kernel<<<dim3(nblk, n), 256, 0, st>>>(px, f1, grad_flow, grad_px, partial, n, SS, nblk);
   if (lasr_check_launch("flow_epilogue_backward_kernel")) return 1;
   flow_epilogue_reduce_kernel<<<(n * 3 + 127) / 128, 128, 0, st>>>(partial, n, nblk, grad_pp1, grad_f1);
+  return lasr_check_launch("flow_epilogue_reduce_kernel");
+}
+
+extern "C" size_t lasr_b200_head_workspace_bytes(int N, int H, int S) {
+  if (N <= 0 || H <= 0 || S <= 0) return 0;
+  const size_t SS = (size_t)S * S;
+  const size_t a = (size_t)N * H * ((SS + kLossPixPerBlock - 1) / kLossPixPerBlock) * kNumSums * sizeof(float);
+  const size_t b = (size_t)N * H * ((SS + 255) / 256) * 3 * sizeof(float);
+  return (a > b ? a : b) + 256;
+}
+
+extern "C" int lasr_b200_head_forward(const float* image, const float* pp_own, const float* pp_pair,
+                                      const float* f_own, const float* f_pair, const float* imgs,
+                                      const float* masks, const float* occ, const float* flow_obs, float* sums,
+                                      float* flow_rd, uint8_t* bgmask, void* workspace, size_t workspace_bytes, int N,
+                                      int H, int S, void* stream) {
+  HeadArgs A{};
+  if (fill_head(A, image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, N, H, S)) return 1;
+  if (!sums || !workspace || workspace_bytes < lasr_b200_head_workspace_bytes(N, H, S))
+    return lasr_fail("head_forward: null output or workspace too small");
+  if ((flow_rd == nullptr) != (bgmask == nullptr)) return lasr_fail("head_forward: flow_rd and bgmask go together");
+  const int nblk = (A.SS + kLossPixPerBlock - 1) / kLossPixPerBlock;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = reinterpret_cast<float*>(workspace);
+  head_forward_kernel<<<dim3(nblk, N * H), kLossThreads, 0, st>>>(A, partial, nblk, flow_rd, bgmask);
+  if (lasr_check_launch("head_forward_kernel")) return 1;
+  const int tot = N * H * kNumSums;
+  losses_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(partial, nblk, N * H, sums);
+  return lasr_check_launch("losses_reduce_kernel");
+}
+
+extern "C" int lasr_b200_head_backward(const float* image, const float* pp_own, const float* pp_pair,
+                                       const float* f_own, const float* f_pair, const float* imgs,
+                                       const float* masks, const float* occ, const float* flow_obs,
+                                       const float* grad_sums, float* grad_image, float* grad_pp_pair,
+                                       float* grad_f_pair, void* workspace, size_t workspace_bytes, int N, int H,
+                                       int S, void* stream) {
+  HeadArgs A{};
+  if (fill_head(A, image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, N, H, S)) return 1;
+  if (!grad_sums || !grad_image || !grad_pp_pair || !grad_f_pair) return lasr_fail("head_backward: null pointer");
+  if (!workspace || workspace_bytes < lasr_b200_head_workspace_bytes(N, H, S))
+    return lasr_fail("head_backward: workspace too small");
+  const int nblk = (A.SS + 255) / 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = reinterpret_cast<float*>(workspace);
+  head_backward_kernel<<<dim3(nblk, N * H), 256, 0, st>>>(A, grad_sums, grad_image, partial, nblk);
+  if (lasr_check_launch("head_backward_kernel")) return 1;
+  flow_epilogue_reduce_kernel<<<(N * H * 3 + 127) / 128, 128, 0, st>>>(partial, N * H, nblk, grad_pp_pair, grad_f_pair);
   return lasr_check_launch("flow_epilogue_reduce_kernel");
 }

@@ -49,6 +49,12 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #ifndef LASR_BWD_MIN_BLOCKS
 #define LASR_BWD_MIN_BLOCKS 2
 #endif
+#ifndef LASR_FWD_MIN_BLOCKS_MULTI   // several colour sets per pass carry more live state per pixel
+#define LASR_FWD_MIN_BLOCKS_MULTI 3
+#endif
+#ifndef LASR_BWD_MIN_BLOCKS_MULTI
+#define LASR_BWD_MIN_BLOCKS_MULTI 1
+#endif
 #ifndef LASR_BWD_THREADS
 #define LASR_BWD_THREADS 128
 #endif
@@ -62,7 +68,7 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RasterArgs A, int wit
   if (i < A.S) A.coords[i] = pixel_coord((int)i, A.S);
   if (i >= (long long)A.N * A.F) return;
   const bool vertex_tex = A.sample == 1;
-  float fv[9], tex9[9];
+  float fv[9], tex9[9 * kMaxSets];
   fetch_face(A, (int)(i / A.F), (int)(i % A.F), fv, tex9, vertex_tex && with_records);
   const float sthr = sqrtf(A.dist_eps * A.sigma);
   FaceGeom g;
@@ -92,16 +98,19 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RasterArgs A, int wit
     }
   }
   A.face_border[i] = make_float4(g.lox, g.hix, g.loy, g.hiy);
-  store_record(A.face_record + i * kRecWords, g, vertex_tex ? tex9 : nullptr);
+  if (A.K == 1) store_record<1>(A.face_record + i * rec_words(1), g, vertex_tex ? tex9 : nullptr);
+  else if (A.K == 2) store_record<2>(A.face_record + i * rec_words(2), g, tex9);
+  else store_record<3>(A.face_record + i * rec_words(3), g, tex9);
 }
 
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+template <int K>
 struct PixelState {
   float alpha;             // running product / sum / flag
   float ssum, smax;        // online softmax state
-  float col[3];
+  float col[3 * K];        // K colour sets share the geometry work of one pass
   float depth_min;         // hard rgb
   int face_min;
 };
@@ -110,14 +119,14 @@ struct FwdConsts {
   float thr, near_, far_, inv_range;
 };
 
-template <bool kFast>
+template <bool kFast, int K>
 __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConsts& C, const float* __restrict__ rec,
-                                             float4 bd, int face, int n, float xp, float yp, PixelState& st) {
+                                             float4 bd, int face, int n, float xp, float yp, PixelState<K>& st) {
   // exact border predicate of the reference (.cu:32-38,375)
   if (xp > bd.y || xp < bd.x || yp > bd.w || yp < bd.z) return;
   FaceGeom g;
-  float tex9[9];
-  load_record(rec, g, tex9);
+  float tex9[9 * K];
+  load_record<K>(rec, g, tex9);
   Fragment fr;
   if (!soft_fragment<kFast>(A, g, xp, yp, C.thr, fr)) return;
   const int alpha_f = kFast ? 2 : A.alpha;
@@ -132,8 +141,11 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConst
   const float zp = clip_and_depth<kFast>(g, fr.w, wc);
   if (zp < C.near_ || zp > C.far_) return;
   const bool visible = g.front || (kFast ? true : A.double_side != 0);
-  auto sample_tex = [&](int k) -> float {
-    if (sample == 1) return wc[0] * tex9[k] + wc[1] * tex9[3 + k] + wc[2] * tex9[6 + k];
+  auto sample_tex = [&](int k) -> float {   // k = 3*set + channel
+    if (sample == 1) {
+      const float* t = tex9 + 9 * (k / 3);
+      return wc[0] * t[k % 3] + wc[1] * t[3 + k % 3] + wc[2] * t[6 + k % 3];
+    }
     const long long base = ((long long)n * A.F + face) * A.T * 3;
     const long long idx = base + (long long)surface_texel(wc, A.R) * 3 + k;
     return idx < (long long)A.N * A.F * A.T * 3 ? A.textures[idx] : 0.f;
@@ -155,12 +167,14 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConst
     const float ez = (kFast ? __expf((zn - st.smax) * A.inv_gamma) : expf((zn - st.smax) / A.gamma)) * fr.frag;
     st.ssum = rescale * st.ssum + ez;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) st.col[k] = rescale * st.col[k] + ez * sample_tex(k);
+    for (int k = 0; k < 3 * K; ++k) st.col[k] = rescale * st.col[k] + ez * sample_tex(k);
   }
 }
 
-template <bool kFast>
-__global__ void __launch_bounds__(kFwdThreads, LASR_FWD_MIN_BLOCKS) raster_forward_kernel(RasterArgs A, int chunk) {
+template <bool kFast, int K>
+__global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LASR_FWD_MIN_BLOCKS_MULTI) raster_forward_kernel(RasterArgs A, int chunk) {
+  constexpr int kRecWords = rec_words(K);
+  constexpr int P = 3 * K + 1;      // image planes per frame: K colour sets, then alpha
   extern __shared__ int s_list[];   // [chunk] face indices, 8 per-warp segments of chunk/8
   __shared__ int s_cnt[kFwdWarps];
   const int wseg = chunk / kFwdWarps;
@@ -188,15 +202,15 @@ __global__ void __launch_bounds__(kFwdThreads, LASR_FWD_MIN_BLOCKS) raster_forwa
   const int rgb_f = kFast ? 1 : A.rgb;
   const int alpha_f = kFast ? 2 : A.alpha;
 
-  PixelState st;
+  PixelState<K> st;
   st.alpha = alpha_f == 2 ? 1.f : 0.f;
   st.ssum = expf(A.eps / A.gamma);
   st.smax = A.eps;
   st.depth_min = 10000000.f;
   st.face_min = -1;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const float bg = valid ? A.soft_colors[((long long)n * 4 + k) * SS + pn] : 0.f;
+  for (int k = 0; k < 3 * K; ++k) {
+    const float bg = valid ? A.soft_colors[((long long)n * P + k) * SS + pn] : 0.f;
     st.col[k] = rgb_f == 1 ? bg * st.ssum : bg;
   }
 
@@ -262,7 +276,7 @@ __global__ void __launch_bounds__(kFwdThreads, LASR_FWD_MIN_BLOCKS) raster_forwa
           bb.y = __shfl_sync(0xffffffffu, bd.y, b);
           bb.z = __shfl_sync(0xffffffffu, bd.z, b);
           bb.w = __shfl_sync(0xffffffffu, bd.w, b);
-          if (valid) forward_pair<kFast>(A, C, records + (long long)fb * kRecWords, bb, fb, n, xp, yp, st);
+          if (valid) forward_pair<kFast, K>(A, C, records + (long long)fb * kRecWords, bb, fb, n, xp, yp, st);
         }
       }
     }
@@ -271,11 +285,11 @@ __global__ void __launch_bounds__(kFwdThreads, LASR_FWD_MIN_BLOCKS) raster_forwa
 
   if (!valid) return;
   // finalize (.cu:457-482)
-  float* out = A.soft_colors + (long long)n * 4 * SS + pn;
+  float* out = A.soft_colors + (long long)n * P * SS + pn;
   float* agg = A.aggrs_info + (long long)n * 2 * SS + pn;
-  if (alpha_f == 0) out[3 * SS] = st.alpha;
-  else if (alpha_f == 1) out[3 * SS] = st.alpha / A.F;
-  else out[3 * SS] = 1.f - st.alpha;
+  if (alpha_f == 0) out[(P - 1) * SS] = st.alpha;
+  else if (alpha_f == 1) out[(P - 1) * SS] = st.alpha / A.F;
+  else out[(P - 1) * SS] = 1.f - st.alpha;
   if (rgb_f == 0) {
     if (st.face_min != -1) {
 #pragma unroll
@@ -285,7 +299,7 @@ __global__ void __launch_bounds__(kFwdThreads, LASR_FWD_MIN_BLOCKS) raster_forwa
     agg[SS] = (float)st.face_min;
   } else {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) out[k * SS] = div_<kFast>(st.col[k], st.ssum);
+    for (int k = 0; k < 3 * K; ++k) out[k * SS] = div_<kFast>(st.col[k], st.ssum);
     agg[0] = st.ssum;
     agg[SS] = st.smax;
   }
@@ -299,9 +313,12 @@ __global__ void __launch_bounds__(kFwdThreads, LASR_FWD_MIN_BLOCKS) raster_forwa
 constexpr int kBigFacePixels = 4096;   // window area above which a face goes to the CTA-per-face pass
 constexpr int kBigListCap = 16384;     // deferred faces the workspace can list (the rest run inline)
 
-template <bool kFast, bool kBig>
-__global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kernel(RasterArgs A) {
-  __shared__ float s_part[8][18];
+template <bool kFast, bool kBig, int K>
+__global__ void __launch_bounds__(256, K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_MIN_BLOCKS_MULTI) raster_backward_kernel(RasterArgs A) {
+  constexpr int kRecWords = rec_words(K);
+  constexpr int P = 3 * K + 1;          // image planes per frame
+  constexpr int NV = 9 + 9 * K;         // gradient values per face: 9 position + 9 per colour set
+  __shared__ float s_part[8][NV];
   const int lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   const int S = A.S;
@@ -328,10 +345,10 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
   const int gtid = kBig ? threadIdx.x : lane;        // index within the group sweeping this face
   const int gsize = kBig ? blockDim.x : 32;
 
-  float tex9[9];
+  float tex9[9 * K];
   FaceGeom g;
   if (A.records_valid) {   // the forward's per-face record (the reference hands faces_info to its backward too)
-    load_record(A.face_record + wg * kRecWords, g, tex9);
+    load_record<K>(A.face_record + wg * kRecWords, g, tex9);
     const float4 bd = __ldg(A.face_border + wg);
     g.lox = bd.x; g.hix = bd.y; g.loy = bd.z; g.hiy = bd.w;
   } else {
@@ -339,7 +356,7 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
     fetch_face(A, n, f, fv, tex9, sample == 1);
     face_setup(fv, sthr, g);
   }
-  float* gtex_out = A.grad_textures + wg * A.T * 3;
+  float* gtex_out = A.grad_textures + wg * (K == 1 ? A.T * 3 : 9 * K);
 
   int xlo, xhi, ylo, yhi;
   coord_window(g.lox, g.hix, S, xlo, xhi);
@@ -353,17 +370,19 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
       return;
     }
   }
-  float gf[9], gt[9];
+  float gf[9], gt[9 * K];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) { gf[k] = 0.f; gt[k] = 0.f; }
+  for (int k = 0; k < 9; ++k) gf[k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9 * K; ++k) gt[k] = 0.f;
 
   if (xlo <= xhi && ylo <= yhi) {
     const int wdt = xhi - xlo + 1;
     const int total = wdt * (yhi - ylo + 1);
     const float inv_wdt = 1.f / (float)wdt;
-    const float* sc = A.soft_colors + (long long)n * 4 * SS;
+    const float* sc = A.soft_colors + (long long)n * P * SS;
     const float* ag = A.aggrs_info + (long long)n * 2 * SS;
-    const float* gs = A.grad_soft_colors + (long long)n * 4 * SS;
+    const float* gs = A.grad_soft_colors + (long long)n * P * SS;
     for (int idx = gtid; idx < total; idx += gsize) {
       int r = (int)(((float)idx + 0.5f) * inv_wdt);  // idx / wdt without an integer divide
       int col = idx - r * wdt;
@@ -378,9 +397,9 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
       const long long pn = (long long)(S - 1 - yi) * S + xi;
       // alpha term (.cu:582-593); for 'hard' alpha the reference still adds the raw upstream
       // gradient (nothing resets C_grad_xy_alpha), reproduced here
-      float Cxy = gs[3 * SS + pn];
+      float Cxy = gs[(P - 1) * SS + pn];
       if (alpha_f == 1) Cxy /= A.F;
-      else if (alpha_f == 2) Cxy *= div_<kFast>(1.f - sc[3 * SS + pn], fmaxf(1.f - fr.frag, 1e-6f));
+      else if (alpha_f == 2) Cxy *= div_<kFast>(1.f - sc[(P - 1) * SS + pn], fmaxf(1.f - fr.frag, 1e-6f));
       float wc[3];
       const float zp = clip_and_depth<kFast>(g, fr.w, wc);
       if (zp < near_ || zp > far_) continue;
@@ -409,14 +428,16 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
         int texel = 0;
         if (sample == 0) texel = surface_texel(wc, A.R);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < 3 * K; ++k) {   // k = 3*set + channel
           const float gk = gs[k * SS + pn];
           float ck;
           if (sample == 1) {
             const float wg_k = wgt * gk;
+            float* gts = gt + 9 * (k / 3);
+            const float* ts = tex9 + 9 * (k / 3);
 #pragma unroll
-            for (int j = 0; j < 3; ++j) gt[3 * j + k] += wg_k * wc[j];
-            ck = wc[0] * tex9[k] + wc[1] * tex9[3 + k] + wc[2] * tex9[6 + k];
+            for (int j = 0; j < 3; ++j) gts[3 * j + k % 3] += wg_k * wc[j];
+            ck = wc[0] * ts[k % 3] + wc[1] * ts[3 + k % 3] + wc[2] * ts[6 + k % 3];
           } else {
             if (texel < A.T) atomicAdd(&gtex_out[3 * texel + k], wgt * gk);
             const long long ti = wg * A.T * 3 + (long long)texel * 3 + k;
@@ -478,6 +499,49 @@ __global__ void __launch_bounds__(256, LASR_BWD_MIN_BLOCKS) raster_backward_kern
   warp_sum16(v16, lane);
   const float t7 = warp_sum(gt[7]), t8 = warp_sum(gt[8]);
   const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+  if (K > 1) {   // several colour sets: the same recursive-halving sum, 16 values at a time
+    constexpr int G = (NV + 15) / 16;
+    float tot[G];
+#pragma unroll
+    for (int b = 0; b < G; ++b) {
+      float w16[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int q = 16 * b + k;
+        w16[k] = q < 9 ? gf[q < 9 ? q : 0] : (q < NV ? gt[q < NV && q >= 9 ? q - 9 : 0] : 0.f);
+      }
+      warp_sum16(w16, lane);
+      tot[b] = w16[0];
+    }
+    if (!kBig) {
+      if ((lane & 1) == 0) {
+#pragma unroll
+        for (int b = 0; b < G; ++b) {
+          const int q = 16 * b + vidx;
+          if (q < 9) gface_out[q] = tot[b];
+          else if (q < NV) gtex_out[q - 9] = tot[b];
+        }
+      }
+    } else {
+      const int warp = threadIdx.x >> 5;
+      if ((lane & 1) == 0) {
+#pragma unroll
+        for (int b = 0; b < G; ++b) {
+          const int q = 16 * b + vidx;
+          if (q < NV) s_part[warp][q] = tot[b];
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < NV) {
+        float t = 0.f;
+        for (int w = 0; w < nwarps; ++w) t += s_part[w][threadIdx.x];
+        if (threadIdx.x < 9) gface_out[threadIdx.x] = t;
+        else gtex_out[threadIdx.x - 9] = t;
+      }
+      __syncthreads();
+    }
+    continue;
+  }
   if (!kBig) {
     if ((lane & 1) == 0) {
       if (vidx < 9) gface_out[vidx] = v16[0];
@@ -508,16 +572,28 @@ static int check_launch(const char* what) { return lasr_check_launch(what); }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+static size_t raster_ws_bytes(int N, int F, int S, int K) {
+  if (N <= 0 || F <= 0 || S <= 0 || K < 1 || K > kMaxSets) return 0;
+  const size_t nf = (size_t)N * (size_t)F;
+  return align256(nf * sizeof(uint2)) + align256((size_t)S * sizeof(float)) + align256((size_t)N * 4 * sizeof(int)) +
+         align256((size_t)(kBigListCap + 1) * sizeof(int)) +
+         align256(nf * sizeof(float4)) +
+         align256(nf * rec_words(K) * sizeof(float));
+}
+
 static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, float far_, const float* nf_dev,
                      float eps, float sigma, int dist, float dist_eps, float gamma, int rgb, int alpha, int sample,
-                     int double_side, void* workspace, size_t workspace_bytes) {
+                     int double_side, void* workspace, size_t workspace_bytes, int K = 1) {
   if (N <= 0 || F <= 0 || S <= 0 || T <= 0) return fail("raster: batch_size, num_faces, image_size, texture_size must be positive");
   if (S > 32768) return fail("raster: image_size > 32768 unsupported");
   if (dist < 0 || dist > 2 || rgb < 0 || rgb > 1 || alpha < 0 || alpha > 2 || sample < 0 || sample > 1)
     return fail("raster: bad func id");
   if (sample == 1 && T != 3) return fail("raster: 'vertex' textures must be [N,F,3,3]");
-  if (!workspace || workspace_bytes < lasr_b200_raster_workspace_bytes(N, F, S)) return fail("raster: workspace too small");
-  A.N = N; A.F = F; A.S = S; A.T = T;
+  if (K < 1 || K > kMaxSets) return fail("render: num_sets must be 1, 2 or 3");
+  if (!workspace || workspace_bytes < raster_ws_bytes(N, F, S, K)) return fail("raster: workspace too small");
+  if (K > 1 && !(dist == 2 && rgb == 1 && alpha == 2 && sample == 1 && double_side != 0))
+    return fail("render: several colour sets need euclidean / softmax / prod / vertex / fill_back (LASR's configuration)");
+  A.N = N; A.F = F; A.S = S; A.T = T; A.K = K;
   A.R = (int)sqrt((double)T);  // .cu:696
   A.near_ = near_; A.far_ = far_; A.near_far_dev = nf_dev;
   A.eps = eps; A.sigma = sigma; A.dist_eps = dist_eps; A.gamma = gamma;
@@ -543,12 +619,16 @@ static int launch_backward(const RasterArgs& A, long long nf, cudaStream_t st) {
   if (cudaMemsetAsync(A.big_list, 0, sizeof(int), st) != cudaSuccess) return fail("raster_backward: memset failed");
   constexpr int kWarpsPerBlock = LASR_BWD_THREADS / 32;
   const unsigned blocks = (unsigned)((nf + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  if (is_fast(A)) raster_backward_kernel<true, false><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
-  else raster_backward_kernel<false, false><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+  if (A.K == 3) raster_backward_kernel<true, false, 3><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+  else if (A.K == 2) raster_backward_kernel<true, false, 2><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+  else if (is_fast(A)) raster_backward_kernel<true, false, 1><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+  else raster_backward_kernel<false, false, 1><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
   if (check_launch("raster_backward_kernel")) return 1;
   const unsigned big_blocks = 592;   // 4 per SM; each loops over the (usually empty) deferred list
-  if (is_fast(A)) raster_backward_kernel<true, true><<<big_blocks, 256, 0, st>>>(A);
-  else raster_backward_kernel<false, true><<<big_blocks, 256, 0, st>>>(A);
+  if (A.K == 3) raster_backward_kernel<true, true, 3><<<big_blocks, 256, 0, st>>>(A);
+  else if (A.K == 2) raster_backward_kernel<true, true, 2><<<big_blocks, 256, 0, st>>>(A);
+  else if (is_fast(A)) raster_backward_kernel<true, true, 1><<<big_blocks, 256, 0, st>>>(A);
+  else raster_backward_kernel<false, true, 1><<<big_blocks, 256, 0, st>>>(A);
   return check_launch("raster_backward_kernel<big>");
 }
 
@@ -566,34 +646,39 @@ __global__ void __launch_bounds__(256) vertex_gather_kernel(const float* __restr
                                                             const float* __restrict__ grad_textures,
                                                             const int* __restrict__ csr_offsets,
                                                             const int* __restrict__ csr_entries, float* grad_verts,
-                                                            float* grad_vcolors, int N, int V, int F) {
+                                                            float* grad_vcolors, int N, int V, int F, int K) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * V) return;
   const int n = (int)(i / V), v = (int)(i % V);
   const float* gf = grad_faces + (long long)n * F * 9;
-  const float* gt = grad_textures + (long long)n * F * 9;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  const float* gt = grad_textures + (long long)n * F * 9 * K;   // per face: K sets x 3 corners x rgb
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  float c[3 * kMaxSets];
+#pragma unroll
+  for (int q = 0; q < 3 * kMaxSets; ++q) c[q] = 0.f;
   for (int e = csr_offsets[v]; e < csr_offsets[v + 1]; ++e) {
-    const int k = csr_entries[e] * 3;   // entry = face*3 + corner -> offset of that corner's 3 floats
+    const int ent = csr_entries[e];     // entry = face*3 + corner
+    const int k = ent * 3;              // offset of that corner's 3 position gradients
     a0 += gf[k]; a1 += gf[k + 1]; a2 += gf[k + 2];
-    c0 += gt[k]; c1 += gt[k + 1]; c2 += gt[k + 2];
+    const float* gc = gt + (long long)(ent / 3) * 9 * K + (ent % 3) * 3;
+#pragma unroll
+    for (int s = 0; s < kMaxSets; ++s)
+      if (s < K) { c[3 * s] += gc[9 * s]; c[3 * s + 1] += gc[9 * s + 1]; c[3 * s + 2] += gc[9 * s + 2]; }
   }
   grad_verts[i * 3] = a0; grad_verts[i * 3 + 1] = a1; grad_verts[i * 3 + 2] = a2;
-  grad_vcolors[i * 3] = c0; grad_vcolors[i * 3 + 1] = c1; grad_vcolors[i * 3 + 2] = c2;
+#pragma unroll
+  for (int s = 0; s < kMaxSets; ++s)
+    if (s < K) {
+      float* o = grad_vcolors + ((long long)s * N * V + i) * 3;
+      o[0] = c[3 * s]; o[1] = c[3 * s + 1]; o[2] = c[3 * s + 2];
+    }
 }
 
 }  // namespace lasr
 
 using namespace lasr;
 
-extern "C" size_t lasr_b200_raster_workspace_bytes(int N, int F, int S) {
-  if (N <= 0 || F <= 0 || S <= 0) return 0;
-  const size_t nf = (size_t)N * (size_t)F;
-  return align256(nf * sizeof(uint2)) + align256((size_t)S * sizeof(float)) + align256((size_t)N * 4 * sizeof(int)) +
-         align256((size_t)(kBigListCap + 1) * sizeof(int)) +
-         align256(nf * sizeof(float4)) +
-         align256(nf * kRecWords * sizeof(float));
-}
+extern "C" size_t lasr_b200_raster_workspace_bytes(int N, int F, int S) { return raster_ws_bytes(N, F, S, 1); }
 
 extern "C" int lasr_b200_raster_forward(const float* faces, const float* textures, float* aggrs_info,
                                         float* soft_colors, void* workspace, size_t workspace_bytes, int N, int F,
@@ -619,8 +704,10 @@ extern "C" int lasr_b200_raster_forward(const float* faces, const float* texture
   int chunk = ((F + kFwdThreads - 1) / kFwdThreads) * kFwdThreads;   // a multiple of 32 faces per warp
   if (chunk > kMaxScanChunk) chunk = (kMaxScanChunk / kFwdThreads) * kFwdThreads;
   const size_t smem = (size_t)chunk * sizeof(int);
-  if (is_fast(A)) raster_forward_kernel<true><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-  else raster_forward_kernel<false><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  if (A.K == 3) raster_forward_kernel<true, 3><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  else if (A.K == 2) raster_forward_kernel<true, 2><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  else if (is_fast(A)) raster_forward_kernel<true, 1><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  else raster_forward_kernel<false, 1><<<grid, kFwdThreads, smem, st>>>(A, chunk);
   return check_launch("raster_forward_kernel");
 }
 
@@ -661,9 +748,10 @@ extern "C" int lasr_b200_raster_backward(const float* faces, const float* textur
 // indexed ("fused") entry points: vertices + shared topology + vertex colours in, image out;
 // gradients come back per vertex.  No [N,F,9] gathered tensors in HBM on either pass.
 // ---------------------------------------------------------------------------------------------
-extern "C" size_t lasr_b200_render_workspace_bytes(int N, int F, int S) {
-  if (N <= 0 || F <= 0 || S <= 0) return 0;
-  return lasr_b200_raster_workspace_bytes(N, F, S) + 2 * align256((size_t)N * F * 9 * sizeof(float));
+extern "C" size_t lasr_b200_render_workspace_bytes(int N, int F, int S, int num_sets) {
+  if (N <= 0 || F <= 0 || S <= 0 || num_sets < 1 || num_sets > kMaxSets) return 0;
+  return raster_ws_bytes(N, F, S, num_sets) + align256((size_t)N * F * 9 * sizeof(float)) +
+         align256((size_t)N * F * 9 * num_sets * sizeof(float));
 }
 
 static int fill_indexed(RasterArgs& A, const float* verts, const int* tri, const float* vcolors, int V) {
@@ -678,11 +766,12 @@ extern "C" int lasr_b200_render_forward(const float* verts, const int32_t* tri, 
                                         size_t workspace_bytes, int N, int V, int F, int S, float near_, float far_,
                                         const float* near_far_dev, float eps, float sigma_val, int func_id_dist,
                                         float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
-                                        int double_side, void* stream) {
+                                        int double_side, int num_sets, void* stream) {
   RasterArgs A{};
-  if (workspace_bytes < lasr_b200_render_workspace_bytes(N, F, S)) return fail("render: workspace too small");
+  if (num_sets < 1 || num_sets > kMaxSets) return fail("render: num_sets must be 1, 2 or 3");
+  if (workspace_bytes < lasr_b200_render_workspace_bytes(N, F, S, num_sets)) return fail("render: workspace too small");
   if (fill_args(A, N, F, S, 3, near_, far_, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
-                func_id_rgb, func_id_alpha, 1, double_side, workspace, workspace_bytes))
+                func_id_rgb, func_id_alpha, 1, double_side, workspace, workspace_bytes, num_sets))
     return 1;
   if (fill_indexed(A, verts, tri, vcolors, V)) return 1;
   if (!aggrs_info || !soft_colors) return fail("render_forward: null tensor pointer");
@@ -699,8 +788,10 @@ extern "C" int lasr_b200_render_forward(const float* verts, const int32_t* tri, 
   int chunk = ((F + kFwdThreads - 1) / kFwdThreads) * kFwdThreads;   // a multiple of 32 faces per warp
   if (chunk > kMaxScanChunk) chunk = (kMaxScanChunk / kFwdThreads) * kFwdThreads;
   const size_t smem = (size_t)chunk * sizeof(int);
-  if (is_fast(A)) raster_forward_kernel<true><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-  else raster_forward_kernel<false><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  if (A.K == 3) raster_forward_kernel<true, 3><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  else if (A.K == 2) raster_forward_kernel<true, 2><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  else if (is_fast(A)) raster_forward_kernel<true, 1><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  else raster_forward_kernel<false, 1><<<grid, kFwdThreads, smem, st>>>(A, chunk);
   return check_launch("raster_forward_kernel");
 }
 
@@ -711,12 +802,13 @@ extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri,
                                          void* workspace, size_t workspace_bytes, int N, int V, int F, int S,
                                          float near_, float far_, const float* near_far_dev, float eps,
                                          float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
-                                         int func_id_rgb, int func_id_alpha, int double_side, int setup_done,
-                                         void* stream) {
+                                         int func_id_rgb, int func_id_alpha, int double_side, int num_sets,
+                                         int setup_done, void* stream) {
   RasterArgs A{};
-  if (workspace_bytes < lasr_b200_render_workspace_bytes(N, F, S)) return fail("render: workspace too small");
+  if (num_sets < 1 || num_sets > kMaxSets) return fail("render: num_sets must be 1, 2 or 3");
+  if (workspace_bytes < lasr_b200_render_workspace_bytes(N, F, S, num_sets)) return fail("render: workspace too small");
   if (fill_args(A, N, F, S, 3, near_, far_, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
-                func_id_rgb, func_id_alpha, 1, double_side, workspace, workspace_bytes))
+                func_id_rgb, func_id_alpha, 1, double_side, workspace, workspace_bytes, num_sets))
     return 1;
   A.records_valid = setup_done;
   if (fill_indexed(A, verts, tri, vcolors, V)) return 1;
@@ -725,7 +817,7 @@ extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri,
   A.aggrs_info = const_cast<float*>(aggrs_info);
   A.soft_colors = const_cast<float*>(soft_colors);
   A.grad_soft_colors = grad_soft_colors;
-  char* scratch = reinterpret_cast<char*>(workspace) + lasr_b200_raster_workspace_bytes(N, F, S);
+  char* scratch = reinterpret_cast<char*>(workspace) + raster_ws_bytes(N, F, S, num_sets);
   const long long nf = (long long)N * F;
   A.grad_faces = reinterpret_cast<float*>(scratch);
   A.grad_textures = reinterpret_cast<float*>(scratch + align256((size_t)nf * 9 * sizeof(float)));
@@ -739,6 +831,7 @@ extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri,
   if (launch_backward(A, nf, st)) return 1;
   const long long nv = (long long)N * V;
   vertex_gather_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(A.grad_faces, A.grad_textures, csr_offsets,
-                                                                      csr_entries, grad_verts, grad_vcolors, N, V, F);
+                                                                      csr_entries, grad_verts, grad_vcolors, N, V, F,
+                                                                      num_sets);
   return check_launch("vertex_gather_kernel");
 }

@@ -24,7 +24,10 @@
 
 namespace lasr {
 
-constexpr int kRecWords = 44;  // floats per face record (176 B = 11 x float4)
+constexpr int kMaxSets = 3;    // colour sets interpolated in one geometry pass (indexed path)
+// floats per face record: 32 of geometry, then 9 per colour set (+ z for the reference-faithful
+// generic path, which is single-set), rounded to float4s: 44 / 52 / 60 for 1 / 2 / 3 sets
+__host__ __device__ constexpr int rec_words(int K) { return K == 1 ? 44 : ((32 + 9 * K + 3) / 4) * 4; }
 
 struct RasterArgs {
   const float* faces;        // [N,F,9]
@@ -37,7 +40,7 @@ struct RasterArgs {
   // workspace carve-up
   uint2* face_window;        // [N*F] packed pixel windows
   float4* face_border;       // [N*F] dilated bounding boxes (lox, hix, loy, hiy)
-  float* face_record;        // [N*F][kRecWords]
+  float* face_record;        // [N*F][rec_words(K)]
   float* coords;             // [S] pixel-centre coordinates
   int records_valid;         // backward: workspace already holds the forward's setup of the same inputs
   int* big_list;             // [1 + cap]: count, then flat (frame*F + face) ids of faces deferred to the CTA-per-face pass
@@ -45,7 +48,8 @@ struct RasterArgs {
   const float* near_far_dev; // optional {near, far} on device
   // indexed ("fused") input mode: faces/textures are gathered on the fly from per-vertex arrays
   const float* verts;        // [N,V,3] clip-space vertices   (null: direct mode, use `faces`)
-  const float* vcolors;      // [N,V,3] vertex colours
+  const float* vcolors;      // [K][N,V,3] vertex colours, K colour sets sharing one geometry pass
+  int K;                     // number of colour sets (1 on the reference-signature paths); images have 3K+1 planes
   const int* tri;            // [F,3] shared topology
   int V;
   int N, F, S, T, R;
@@ -56,6 +60,7 @@ struct RasterArgs {
 
 // Fetch the 9 vertex floats (and, for 'vertex' textures, the 9 corner colours) of face f of frame
 // n, either from the reference's gathered tensors or straight from per-vertex arrays + topology.
+// (tex9 receives 9 floats per colour set, A.K sets, when want_tex.)
 __device__ __forceinline__ void fetch_face(const RasterArgs& A, int n, int f, float* fv, float* tex9, bool want_tex) {
   if (A.tri) {
     const int i0 = A.tri[3 * f], i1 = A.tri[3 * f + 1], i2 = A.tri[3 * f + 2];
@@ -63,9 +68,16 @@ __device__ __forceinline__ void fetch_face(const RasterArgs& A, int n, int f, fl
 #pragma unroll
     for (int k = 0; k < 3; ++k) { fv[k] = vb[3 * i0 + k]; fv[3 + k] = vb[3 * i1 + k]; fv[6 + k] = vb[3 * i2 + k]; }
     if (want_tex) {
-      const float* cb = A.vcolors + (long long)n * A.V * 3;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { tex9[k] = cb[3 * i0 + k]; tex9[3 + k] = cb[3 * i1 + k]; tex9[6 + k] = cb[3 * i2 + k]; }
+      for (int s = 0; s < kMaxSets; ++s) {
+        if (s < A.K) {
+          const float* cb = A.vcolors + ((long long)s * A.N + n) * A.V * 3;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            tex9[9 * s + k] = cb[3 * i0 + k]; tex9[9 * s + 3 + k] = cb[3 * i1 + k]; tex9[9 * s + 6 + k] = cb[3 * i2 + k];
+          }
+        }
+      }
     }
   } else {
     const long long i = (long long)n * A.F + f;
@@ -180,7 +192,9 @@ __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float s
 // record layout (float index):
 //  0..8 inv | 9..11 x | 12..14 y | 15 flags | 16..18 iz | 19..21 rden | 22..30 a[e][j] | 31 pad
 //  32..40 vertex-colour texture | 41..43 z
+template <int K>
 __device__ __forceinline__ void store_record(float* __restrict__ r, const FaceGeom& g, const float* tex9) {
+  constexpr int kRecWords = rec_words(K);
   float v[kRecWords];
 #pragma unroll
   for (int k = 0; k < kRecWords; ++k) v[k] = 0.f;
@@ -188,7 +202,8 @@ __device__ __forceinline__ void store_record(float* __restrict__ r, const FaceGe
   for (int k = 0; k < 9; ++k) v[k] = g.inv[k];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    v[9 + k] = g.x[k]; v[12 + k] = g.y[k]; v[16 + k] = g.iz[k]; v[19 + k] = g.rden[k]; v[41 + k] = g.z[k];
+    v[9 + k] = g.x[k]; v[12 + k] = g.y[k]; v[16 + k] = g.iz[k]; v[19 + k] = g.rden[k];
+    if (K == 1) v[41 + k] = g.z[k];
   }
   v[15] = __int_as_float((g.obt + 1) | (g.front ? 4 : 0));
 #pragma unroll
@@ -197,7 +212,7 @@ __device__ __forceinline__ void store_record(float* __restrict__ r, const FaceGe
     for (int j = 0; j < 3; ++j) v[22 + 3 * e + j] = g.a[e][j];
   if (tex9) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) v[32 + k] = tex9[k];
+    for (int k = 0; k < 9 * K; ++k) v[32 + k] = tex9[k];
   }
   float4* r4 = reinterpret_cast<float4*>(r);
 #pragma unroll
@@ -205,7 +220,9 @@ __device__ __forceinline__ void store_record(float* __restrict__ r, const FaceGe
 }
 
 // Uniform (warp-broadcast) 128-bit loads of a record: every lane reads the same address.
+template <int K>
 __device__ __forceinline__ void load_record(const float* __restrict__ r, FaceGeom& g, float* tex9) {
+  constexpr int kRecWords = rec_words(K);
   const float4* r4 = reinterpret_cast<const float4*>(r);
   float v[kRecWords];
 #pragma unroll
@@ -217,7 +234,8 @@ __device__ __forceinline__ void load_record(const float* __restrict__ r, FaceGeo
   for (int k = 0; k < 9; ++k) g.inv[k] = v[k];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    g.x[k] = v[9 + k]; g.y[k] = v[12 + k]; g.iz[k] = v[16 + k]; g.rden[k] = v[19 + k]; g.z[k] = v[41 + k];
+    g.x[k] = v[9 + k]; g.y[k] = v[12 + k]; g.iz[k] = v[16 + k]; g.rden[k] = v[19 + k];
+    g.z[k] = K == 1 ? v[41 + k] : 0.f;
   }
   const int fl = __float_as_int(v[15]);
   g.obt = (fl & 3) - 1;
@@ -227,7 +245,7 @@ __device__ __forceinline__ void load_record(const float* __restrict__ r, FaceGeo
 #pragma unroll
     for (int j = 0; j < 3; ++j) g.a[e][j] = v[22 + 3 * e + j];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) tex9[k] = v[32 + k];
+  for (int k = 0; k < 9 * K; ++k) tex9[k] = v[32 + k];
 }
 
 // Conservative inclusive pixel-index window of coordinates in [lo, hi] (the exact predicate is

@@ -27,6 +27,8 @@ class HotPathOptions:
     sigval: float = 1e-4
     l1tex_wt: float = 1.0
     opt_tex: bool = True
+    fused: bool = True          # CUDA only: one three-set render + fused image head instead of three renders
+    report_flow: bool = True    # fused path: also materialise flow_rd / bgmask (reporting; costs one write)
 
 
 class RenderHotPath(torch.nn.Module):
@@ -76,6 +78,8 @@ class RenderHotPath(torch.nn.Module):
         for r in (self.renderer_softflf, self.renderer_softflb, self.renderer_softtex):
             r.rasterizer.near, r.rasterizer.far = near, far
             r.rasterizer.sigma_val = o.sigval
+        if o.fused and verts_px.is_cuda and o.opt_tex:
+            return self._forward_fused(verts_fl, verts_px, tex, faces, ppoint, scale, batch, shared_faces, near, far)
         # 2) flow renders (mesh_net.py:318-335)
         px4 = verts_px.view(n2, H, -1, 4)
         rep = lambda t, lo, hi: t[:, None][lo:hi].repeat(1, H, 1).view(-1, t.shape[-1])
@@ -116,3 +120,38 @@ class RenderHotPath(torch.nn.Module):
         return dict(total=total, mask_loss=mask_loss, flow_loss=flow_loss, texture_loss=texture_loss,
                     mask_pred=mask_pred, texture_render=rgb, flow_rd=flow_rd, bgmask=bgmask, verts_px=verts_px,
                     near=near, far=far)
+
+    def _forward_fused(self, verts_fl, verts_px, tex, faces, ppoint, scale, batch, shared_faces, near, far):
+        """Steps 2-4 of ``forward`` with the mesh rasterized ONCE per frame.  The reference renders every
+        posed frame three times with the same geometry and renderer settings but different vertex
+        attributes -- flow (own + paired camera-space positions, mesh_net.py:77-87, 318-335) and texture
+        (:348-363); here the three attribute sets ride one geometry pass (render_indexed with
+        [3,N,V,3] colours) and one fused head turns the 10-plane image into the three losses.  Same
+        values as the three-render path; the vertex gradient is the sum the reference's autograd forms."""
+        o = self.opts
+        H, S = o.n_hypo, o.img_size
+        n2 = ppoint.shape[0]
+        bs = n2 // 2
+        nh = n2 * H
+        r = self.renderer_softtex
+        offset = gu._eye_offset(r, verts_px.device)
+        pre = verts_px[:, :, :3] + offset
+        pre = torch.cat([pre[:, :, :1], -pre[:, :, 1:2], pre[:, :, 2:]], dim=-1)
+        own = verts_fl[:, :, :3]
+        pair = torch.roll(own.view(n2, H, -1, 3), bs, 0).reshape(nh, -1, 3)     # frame i <-> i +- bs
+        sets = torch.stack([own, pair, tex.reshape(nh, -1, 3).to(own.dtype)], 0)
+        faces_h = faces[:, None].repeat(1, H, 1, 1).view(-1, faces.shape[1], 3)
+        r.rasterizer.background_color = [0, 0, 0, 0, 0, 0, 1, 1, 1]
+        image = r.render_mesh(sr.Mesh(pre, faces_h, textures=sets, texture_type="vertex", shared_faces=shared_faces))
+        r.rasterizer.background_color = [1, 1, 1]
+        pp_own = ppoint[:, None].repeat(1, H, 1).view(nh, 2)
+        pp_pair = torch.roll(ppoint, bs, 0)[:, None].repeat(1, H, 1).view(nh, 2)
+        f_own = scale.view(n2, H, -1)[:, :, 0].reshape(nh)
+        f_pair = torch.roll(scale.view(n2, H, -1)[:, :, 0], bs, 0).reshape(nh)
+        mask_loss, flow_loss, texture_loss, sub, flow_rd, bgmask = L.fused_head(
+            image, pp_own, pp_pair, f_own, f_pair, batch["imgs"], batch["masks"], batch["occ"], batch["flow"], n2, H,
+            o.l1tex_wt, want_flow=o.report_flow)
+        total = mask_loss + flow_loss + texture_loss
+        return dict(total=total, mask_loss=mask_loss, flow_loss=flow_loss, texture_loss=texture_loss,
+                    mask_pred=image[:, 9], texture_render=image[:, 6:9], flow_rd=flow_rd, bgmask=bgmask,
+                    verts_px=verts_px, near=near, far=far)

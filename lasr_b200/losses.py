@@ -87,6 +87,68 @@ class _FusedImageLosses(Function):
         return g_mp, g_fr, None, (g_tx if need[3] else None), g_fg, None, None, None, None, None
 
 
+class _FusedHead(Function):
+    """Flow re-projection (both directions) + all three losses straight from the three-set render
+    [N*H,10,S,S] (lasr_b200_head_forward/backward): the flow, background-mask, texture and silhouette
+    intermediates of mesh_net.py:88-104 / 372-447 never exist as separate tensors, and the backward
+    writes the image gradient in one pass."""
+
+    @staticmethod
+    def forward(ctx, image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, l1tex_wt, N, H, want_flow):
+        from . import _cabi
+        S = image.shape[-1]
+        dev = image.device
+        c = lambda t, sh: t.detach().float().reshape(sh).contiguous()
+        img = image.detach().float().contiguous()
+        po, pq = c(pp_own, (N * H, 2)), c(pp_pair, (N * H, 2))
+        fo, fq = c(f_own, (N * H,)), c(f_pair, (N * H,))
+        im, mk, oc, fl = (t.detach().float().contiguous() for t in (imgs, masks, occ, flow_obs))
+        sums = torch.empty(N, H, 7, dtype=torch.float32, device=dev)
+        flow_rd = bg = None
+        if want_flow:
+            flow_rd = torch.empty(N * H, S, S, 2, dtype=torch.float32, device=dev)
+            bg = torch.empty(N * H, S, S, dtype=torch.uint8, device=dev)
+        _cabi.head_forward(img, po, pq, fo, fq, im, mk, oc, fl, sums, flow_rd, bg, N, H, S)
+        sub = torch.empty(3, N, H, dtype=torch.float32, device=dev)
+        out3 = torch.empty(3, dtype=torch.float32, device=dev)
+        _cabi.losses_finalize(sums, sub, out3, N, H, l1tex_wt)
+        ctx.save_for_backward(img, po, pq, fo, fq, im, mk, oc, fl, sums)
+        ctx.dims = (N, H, S, float(l1tex_wt))
+        ctx.shapes = (pp_pair.shape, f_pair.shape)
+        if want_flow:
+            bgb = bg.bool()
+            ctx.mark_non_differentiable(flow_rd, bgb)
+            return out3, sub, flow_rd, bgb
+        return out3, sub, None, None
+
+    @staticmethod
+    def backward(ctx, g_out3, g_sub, _gflow, _gbg):
+        from . import _cabi
+        img, po, pq, fo, fq, im, mk, oc, fl, sums = ctx.saved_tensors
+        N, H, S, wt = ctx.dims
+        dev = img.device
+        g3 = torch.zeros(3, device=dev) if g_out3 is None else g_out3.float().contiguous()
+        gsub = None if g_sub is None else g_sub.float().contiguous()
+        gsums = torch.empty_like(sums)
+        _cabi.losses_coefficients(sums, g3, gsub, gsums, N, H, wt)
+        gimg = torch.empty_like(img)
+        gpp = torch.empty(N * H, 2, dtype=torch.float32, device=dev)
+        gf = torch.empty(N * H, dtype=torch.float32, device=dev)
+        _cabi.head_backward(img, po, pq, fo, fq, im, mk, oc, fl, gsums, gimg, gpp, gf, N, H, S)
+        return (gimg, None, gpp.reshape(ctx.shapes[0]), None, gf.reshape(ctx.shapes[1]), None, None, None, None,
+                None, None, None, None)
+
+
+def fused_head(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, n_frames, n_hypo, l1tex_wt=1.0,
+               want_flow=True):
+    """image [N*H,10,S,S] from the three-set render -> (mask_loss, flow_loss, texture_loss, per-pair dict,
+    flow_rd [N*H,S,S,2] | None, bgmask [N*H,S,S] bool | None).  The flow outputs are for reporting only
+    (not differentiable: their gradient path is inside the losses)."""
+    out3, sub, flow_rd, bg = _FusedHead.apply(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs,
+                                              l1tex_wt, n_frames, n_hypo, want_flow)
+    return out3[0], out3[1], out3[2], dict(mask=sub[0], flow=sub[1], texture=sub[2]), flow_rd, bg
+
+
 def _native(t):
     return t.is_cuda
 

@@ -71,11 +71,15 @@ class RenderIndexedFunction(Function):
                     RGB_FUNCS[aggr_func_rgb], ALPHA_FUNCS[aggr_func_alpha], bool(fill_back))
         ctx.near, ctx.far, ctx.nf = _near_far(near, far, dev)
         ctx.S = S
+        K = 1 if c.dim() == 3 else int(c.shape[0])
+        bg = [float(x) for x in np.asarray(background_color, dtype=np.float64).reshape(-1)]
+        if len(bg) != 3 * K:
+            raise ValueError("background_color needs 3 values per colour set")
         aggrs = torch.empty(N, 2, S, S, dtype=torch.float32, device=dev)
-        img = torch.empty(N, 4, S, S, dtype=torch.float32, device=dev)
-        for k in range(3):
-            img[:, k].fill_(float(background_color[k]))       # fills, not an H2D copy: CUDA-graph safe
-        ws = _cabi.render_workspace(N, tri.shape[0], S, dev)
+        img = torch.empty(N, 3 * K + 1, S, S, dtype=torch.float32, device=dev)
+        for k in range(3 * K):
+            img[:, k].fill_(bg[k])       # fills, not an H2D copy: CUDA-graph safe
+        ws = _cabi.render_workspace(N, tri.shape[0], S, dev, K)
         _cabi.render_forward(v, tri, c, aggrs, img, ws, S, ctx.near, ctx.far, ctx.nf, *ctx.scal)
         ctx.save_for_backward(v, c, tri, img, aggrs, ws)
         ctx.shapes = (vertices.shape, vcolors.shape)
@@ -96,5 +100,9 @@ class RenderIndexedFunction(Function):
 def render_indexed(vertices, vcolors, tri, image_size=256, background_color=[0, 0, 0], near=1, far=100,
                    fill_back=True, eps=1e-3, sigma_val=1e-5, dist_func="euclidean", dist_eps=1e-4, gamma_val=1e-4,
                    aggr_func_rgb="softmax", aggr_func_alpha="prod"):
+    """vcolors [N,V,3] -> image [N,4,S,S] (RGBA, the reference's layout).  vcolors [K,N,V,3] with
+    K = 2 or 3 renders K colour sets over ONE geometry pass -> image [N,3K+1,S,S] (set s in planes
+    3s..3s+2, alpha last); background_color then holds K rgb triples.  Per set the result equals a
+    separate render of that set; the vertex gradient is the sum over the sets."""
     return RenderIndexedFunction.apply(vertices, vcolors, tri, image_size, background_color, near, far, fill_back,
                                        eps, sigma_val, dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha)

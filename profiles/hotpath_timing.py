@@ -41,7 +41,10 @@ if B > 1:
 batch = dict(masks=(torch.rand(n2, S, S, generator=g) > 0.5).float().to(dev), imgs=torch.rand(n2, 3, S, S, generator=g).to(dev),
              flow=(torch.randn(n2, 3, S, S, generator=g) * 0.02).to(dev), occ=torch.randn(n2, S, S, generator=g).to(dev))
 leaves = [pred_v, tex, Rmat, Tmat, ppoint, scale] + (list(bones.values()) if bones else [])
-m = hotpath.RenderHotPath(hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B)).to(dev)
+fused = os.environ.get("FUSED", "1") != "0"            # one three-set render + fused head (default) vs three renders
+report_flow = os.environ.get("REPORT_FLOW", "1") != "0"
+m = hotpath.RenderHotPath(hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B, fused=fused,
+                                                 report_flow=report_flow)).to(dev)
 
 def step(*xs):
     xs = [x.detach().requires_grad_(True) for x in xs]

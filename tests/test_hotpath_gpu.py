@@ -69,14 +69,17 @@ def scenario(H, B, S, bs=2, seed=0):
     return pred_v, tex, faces, Rmat, Tmat, ppoint, scale, batch, bones
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("H,B", [(1, 1), (2, 3)])
-def test_hot_path_matches_oracle_backed_cpu_chain(monkeypatch, H, B):
+def test_hot_path_matches_oracle_backed_cpu_chain(monkeypatch, H, B, fused):
+    """fused=True: one three-set render + fused head on the GPU; fused=False: the reference's three
+    renders.  The CPU chain is always the reference's structure (three oracle renders)."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from lasr_b200 import hotpath
     import lasr_b200.soft_renderer.rasterizer as rast
     S = 48
-    opts = hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B, sigval=1e-4, l1tex_wt=1.0)
+    opts = hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B, sigval=1e-4, l1tex_wt=1.0, fused=fused)
     pred_v, tex, faces, Rmat, Tmat, ppoint, scale, batch, bones = scenario(H, B, S)
 
     def run(dev):
@@ -111,3 +114,103 @@ def test_hot_path_matches_oracle_backed_cpu_chain(monkeypatch, H, B):
             continue
         err = (gpu_grads[k] - g).norm()
         assert err <= 2e-2 * g.norm() + 1e-7, (k, float(err), float(g.norm()))
+
+
+@pytest.mark.parametrize("H,B", [(1, 1), (2, 3)])
+def test_fused_hot_path_equals_three_render_hot_path(H, B):
+    """Same device, same inputs: rasterizing once with three attribute sets + the fused head must give the
+    losses, images and gradients of the three separate renders (only float summation order differs)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from lasr_b200 import hotpath
+    S = 64
+    pred_v, tex, faces, Rmat, Tmat, ppoint, scale, batch, bones = scenario(H, B, S, seed=3)
+    dev = torch.device("cuda", 0)
+
+    def run(fused):
+        t = lambda x: x.clone().to(dev)
+        leaves = dict(pred_v=t(pred_v), tex=t(tex), Rmat=t(Rmat), Tmat=t(Tmat), ppoint=t(ppoint), scale=t(scale))
+        bn = None
+        if bones is not None:
+            bn = {k: t(v) for k, v in bones.items()}
+            leaves.update({f"bone_{k}": bn[k] for k in bn})
+        for x in leaves.values():
+            x.requires_grad_(True)
+        m = hotpath.RenderHotPath(hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B, sigval=1e-4, fused=fused))
+        out = m(leaves["pred_v"], leaves["tex"], t(faces), leaves["Rmat"], leaves["Tmat"], leaves["ppoint"],
+                leaves["scale"], {k: t(v) for k, v in batch.items()}, bn)
+        out["total"].backward()
+        keys = ("total", "mask_loss", "flow_loss", "texture_loss", "mask_pred", "texture_render", "flow_rd", "bgmask")
+        return ({k: out[k].detach().cpu() for k in keys},
+                {k: (x.grad.detach().cpu() if x.grad is not None else None) for k, x in leaves.items()})
+
+    a_out, a_grads = run(True)
+    b_out, b_grads = run(False)
+    for k in ("total", "mask_loss", "flow_loss", "texture_loss"):
+        assert abs(float(a_out[k]) - float(b_out[k])) <= 1e-5 * max(1e-3, abs(float(b_out[k]))), k
+    assert torch.equal(a_out["bgmask"].reshape(-1), b_out["bgmask"].reshape(-1))
+    for k in ("mask_pred", "texture_render", "flow_rd"):
+        d = (a_out[k].reshape(-1) - b_out[k].reshape(-1)).abs().max()
+        assert float(d) <= 1e-5, (k, float(d))
+    for k, g in b_grads.items():
+        if g is None:
+            assert a_grads[k] is None or float(a_grads[k].abs().max()) == 0.0
+            continue
+        err = (a_grads[k] - g).norm()
+        assert err <= 1e-4 * g.norm() + 1e-8, (k, float(err), float(g.norm()))
+
+
+def test_fused_head_equals_epilogue_plus_losses():
+    """lasr_b200_head_* against the unfused kernels it replaces (flow epilogue + fused image losses)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from lasr_b200 import geom_utils as gu, losses as L
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(5)
+    N, H, S = 4, 2, 40
+    NH = N * H
+    img = torch.rand(NH, 10, S, S, generator=g)
+    img[:, 2] = 8 + 2 * img[:, 2]
+    img[:, 5] = 8 + 2 * img[:, 5]
+    hole = torch.rand(NH, S, S, generator=g) < 0.3          # background: both depth planes 0
+    img[:, 2][hole] = 0
+    img[:, 5][hole] = 0
+    occ = torch.randn(N, S, S, generator=g)
+    occ[torch.rand(N, S, S, generator=g) < 0.2] = 0
+    obs = dict(masks=(torch.rand(N, S, S, generator=g) > 0.4).float(), imgs=torch.rand(N, 3, S, S, generator=g),
+               flow=torch.randn(N, 3, S, S, generator=g) * 0.05, occ=occ)
+    obs = {k: v.to(dev) for k, v in obs.items()}
+    pp_o, pp_p = torch.randn(NH, 2, generator=g) * 0.05, torch.randn(NH, 2, generator=g) * 0.05
+    f_o, f_p = 9 + torch.rand(NH, generator=g), 9 + torch.rand(NH, generator=g)
+
+    def leaves():
+        out = [x.clone().to(dev).requires_grad_(True) for x in (img, pp_o, pp_p, f_o, f_p)]
+        return out
+
+    a = leaves()
+    ml, fl, tl, sub, flow_a, bg_a = L.fused_head(a[0], a[1], a[2], a[3], a[4], obs["imgs"], obs["masks"], obs["occ"],
+                                                 obs["flow"], N, H, 0.7)
+    (ml + 2 * fl + 3 * tl + (sub["flow"] * torch.arange(NH, device=dev).view(N, H)).sum() * 1e-2).backward()
+
+    b = leaves()
+    zeros = torch.zeros(NH, 1, S, S, device=dev)
+    px = torch.cat([torch.cat([b[0][:, 0:3], zeros], 1), torch.cat([b[0][:, 3:6], zeros], 1)], 0)
+    flow_b, bg_b = gu._FlowEpilogue.apply(px, b[1], b[2], b[3][:, None], b[4][:, None])
+    mp = b[0][:, 9].view(N, H, S, S)
+    ml2, fl2, tl2, sub2 = L.image_losses(mp, obs["masks"], obs["occ"], flow_b.view(N, H, S, S, 2),
+                                         bg_b.view(N, H, S, S), obs["flow"], b[0][:, 6:9].reshape(N, H, 3, S, S), mp,
+                                         obs["imgs"], 0.7)
+    (ml2 + 2 * fl2 + 3 * tl2 + (sub2["flow"] * torch.arange(NH, device=dev).view(N, H)).sum() * 1e-2).backward()
+
+    assert torch.equal(bg_a, bg_b) and torch.equal(flow_a, flow_b)
+    for x, y in ((ml, ml2), (fl, fl2), (tl, tl2)):
+        assert abs(float(x) - float(y)) <= 1e-6 * abs(float(y)) + 1e-9
+    for k in sub:
+        assert torch.allclose(sub[k], sub2[k], rtol=1e-6, atol=1e-9)
+    names = ("image", "pp_own", "pp_pair", "f_own", "f_pair")
+    for nm, x, y in zip(names, a, b):
+        if y.grad is None:
+            assert x.grad is None or float(x.grad.abs().max()) == 0.0, nm
+            continue
+        assert x.grad is not None, nm
+        assert torch.allclose(x.grad, y.grad, rtol=1e-5, atol=1e-9), (nm, float((x.grad - y.grad).abs().max()))

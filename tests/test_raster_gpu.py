@@ -323,3 +323,65 @@ def test_anti_aliasing_and_forward_entry_point(srf, oracle):
     a = rr(verts + eye, faces, cols, texture_type="vertex")
     b = rr.render_mesh(sr.Mesh(verts + eye, faces, textures=cols, texture_type="vertex"))
     assert torch.equal(a, b) and a.shape == (2, 4, 32, 32)
+
+
+@pytest.mark.parametrize("K", [2, 3])
+def test_colour_sets_in_one_pass_equal_separate_renders(srf, K):
+    """render_indexed with [K,N,V,3] colours (one geometry pass) == K separate renders: identical planes,
+    identical alpha, per-set colour gradients, and a vertex gradient equal to the sum over the sets."""
+    from lasr_b200 import synth
+    v, f = synth.bumpy_sphere(3, 0.35)
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(K)
+    N, S = 3, 96
+    V = len(v)
+    verts = torch.from_numpy(v)[None].repeat(N, 1, 1) * 0.8
+    verts = verts + torch.randn(N, 1, 3, generator=g) * 0.05
+    verts[:, :, 2] += 5.0
+    tri = torch.from_numpy(f).int().to(dev)
+    cols = torch.rand(K, N, V, 3, generator=g)
+    bgs = [[0.0, 0.0, 0.0], [1.0, 0.5, 0.25], [1.0, 1.0, 1.0]][:K]
+    kw = dict(image_size=S, near=1.0, far=20.0, fill_back=True, sigma_val=1e-4, gamma_val=1e-2,
+              dist_func="euclidean", aggr_func_rgb="softmax", aggr_func_alpha="prod")
+    gout = torch.randn(N, 3 * K + 1, S, S, generator=g).to(dev)
+
+    va = verts.clone().to(dev).requires_grad_(True)
+    ca = cols.clone().to(dev).requires_grad_(True)
+    img = srf.render_indexed(va, ca, tri, background_color=[c for b in bgs for c in b], **kw)
+    assert img.shape == (N, 3 * K + 1, S, S)
+    (img * gout).sum().backward()
+
+    gv_sum = torch.zeros_like(va)
+    for s in range(K):
+        vb = verts.clone().to(dev).requires_grad_(True)
+        cb = cols[s].clone().to(dev).requires_grad_(True)
+        one = srf.render_indexed(vb, cb, tri, background_color=bgs[s], **kw)
+        assert torch.equal(one[:, :3], img[:, 3 * s:3 * s + 3]), s
+        assert torch.equal(one[:, 3], img[:, 3 * K]), s
+        go = torch.cat([gout[:, 3 * s:3 * s + 3], gout[:, 3 * K:] if s == 0 else torch.zeros_like(gout[:, :1])], 1)
+        (one * go).sum().backward()
+        assert torch.allclose(cb.grad, ca.grad[s], rtol=1e-5, atol=1e-7), s
+        gv_sum += vb.grad
+    err = (va.grad - gv_sum).norm()
+    assert err <= 2e-5 * gv_sum.norm(), (float(err), float(gv_sum.norm()))
+    # deterministic
+    va2 = verts.clone().to(dev).requires_grad_(True)
+    ca2 = cols.clone().to(dev).requires_grad_(True)
+    (srf.render_indexed(va2, ca2, tri, background_color=[c for b in bgs for c in b], **kw) * gout).sum().backward()
+    assert torch.equal(va2.grad, va.grad) and torch.equal(ca2.grad, ca.grad)
+
+
+def test_colour_sets_reject_other_configurations(srf):
+    from lasr_b200 import synth
+    v, f = synth.icosphere(1)
+    dev = torch.device("cuda", 0)
+    verts = torch.from_numpy(v)[None].to(dev) * 0.5
+    tri = torch.from_numpy(f).int().to(dev)
+    cols = torch.rand(2, 1, len(v), 3, device=dev)
+    with pytest.raises(RuntimeError):
+        srf.render_indexed(verts, cols, tri, image_size=32, background_color=[0] * 6, aggr_func_rgb="hard")
+    with pytest.raises(ValueError):
+        srf.render_indexed(verts, cols, tri, image_size=32, background_color=[0] * 3)
+    with pytest.raises(RuntimeError):
+        srf.render_indexed(verts, torch.rand(4, 1, len(v), 3, device=dev), tri, image_size=32,
+                           background_color=[0] * 12)
