@@ -107,6 +107,10 @@ int lasr_b200_raster_backward(const float* faces, const float* textures, const f
  *   csr_offsets [V+1], csr_entries [3F] (entry = face*3 + corner, grouped by vertex, ascending):
  *                    vertex -> corner adjacency used to sum per-face gradients in a fixed order
  *   grad_verts [N,V,3], grad_vcolors [K,N,V,3] out (overwritten)
+ *   detached_sets (backward): 0, or 1 with K >= 2 -- colour set 0 is rendered for reading only, as if
+ *                    its planes were `.detach()`ed: planes 0-2 of grad_soft_colors are not read and
+ *                    grad_vcolors[0] is zero (LASR re-projects the frame's own positions only under
+ *                    .detach(), nnutils/mesh_net.py:102-103)
  * Other arguments as lasr_b200_raster_forward/backward (texture_sample_type is 'vertex').
  * ------------------------------------------------------------------------------------------- */
 size_t lasr_b200_render_workspace_bytes(int batch_size, int num_faces, int image_size, int num_sets);
@@ -127,8 +131,8 @@ int lasr_b200_render_backward(const float* verts, const int32_t* tri, const floa
                               int num_vertices, int num_faces, int image_size, float near_,
                               float far_, const float* near_far_dev, float eps, float sigma_val,
                               int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
-                              int func_id_alpha, int double_side, int num_sets, int setup_done,
-                              void* stream);
+                              int func_id_alpha, int double_side, int num_sets, int detached_sets,
+                              int setup_done, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused linear-blend skinning + body transform + pinhole projection + batch depth window

@@ -52,7 +52,7 @@ def lib():
         L.lasr_b200_render_forward.argtypes = [_c.c_void_p] * 6 + [_c.c_size_t] + _render_scalars + [_c.c_void_p]
         L.lasr_b200_render_backward.restype = _c.c_int
         L.lasr_b200_render_backward.argtypes = ([_c.c_void_p] * 11 + [_c.c_size_t] + _render_scalars
-                                                + [_c.c_int, _c.c_void_p])
+                                                + [_c.c_int, _c.c_int, _c.c_void_p])
         L.lasr_b200_head_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_head_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_head_forward.restype = _c.c_int
@@ -249,7 +249,7 @@ def render_forward(verts, tri, vcolors, aggrs_info, soft_colors, workspace, S, n
 
 def render_backward(verts, tri, vcolors, soft_colors, aggrs_info, grad_soft_colors, csr_offsets, csr_entries,
                     grad_verts, grad_vcolors, workspace, S, near, far, near_far_dev, eps, sigma_val, func_id_dist,
-                    dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side, setup_done=False):
+                    dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side, setup_done=False, detached_sets=0):
     for t in (verts, vcolors, soft_colors, aggrs_info, grad_soft_colors, grad_verts, grad_vcolors):
         _require_cuda_f32(t, "render tensor")
     N, V = verts.shape[:2]
@@ -262,8 +262,8 @@ def render_backward(verts, tri, vcolors, soft_colors, aggrs_info, grad_soft_colo
             _p(verts), _p(tri), _p(vcolors), _p(soft_colors), _p(aggrs_info), _p(grad_soft_colors), _p(csr_offsets),
             _p(csr_entries), _p(grad_verts), _p(grad_vcolors), _p(workspace), workspace.numel(),
             *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
-                                 gamma_val, func_id_rgb, func_id_alpha, double_side, K), int(bool(setup_done)),
-            _stream_ptr())
+                                 gamma_val, func_id_rgb, func_id_alpha, double_side, K), int(detached_sets),
+            int(bool(setup_done)), _stream_ptr())
     _check(rc, "lasr_b200_render_backward")
 
 

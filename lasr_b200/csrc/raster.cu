@@ -53,7 +53,7 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #define LASR_FWD_MIN_BLOCKS_MULTI 3
 #endif
 #ifndef LASR_BWD_MIN_BLOCKS_MULTI
-#define LASR_BWD_MIN_BLOCKS_MULTI 1
+#define LASR_BWD_MIN_BLOCKS_MULTI 2
 #endif
 #ifndef LASR_BWD_THREADS
 #define LASR_BWD_THREADS 128
@@ -313,11 +313,15 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
 constexpr int kBigFacePixels = 4096;   // window area above which a face goes to the CTA-per-face pass
 constexpr int kBigListCap = 16384;     // deferred faces the workspace can list (the rest run inline)
 
-template <bool kFast, bool kBig, int K>
+// KF: colour sets [0,KF) are detached -- their image-gradient planes are not read and they get no
+// colour gradient (LASR's flow render uses the frame's own positions only under .detach(),
+// nnutils/mesh_net.py:102); sets [KF,K) are live.
+template <bool kFast, bool kBig, int K, int KF>
 __global__ void __launch_bounds__(256, K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_MIN_BLOCKS_MULTI) raster_backward_kernel(RasterArgs A) {
   constexpr int kRecWords = rec_words(K);
   constexpr int P = 3 * K + 1;          // image planes per frame
-  constexpr int NV = 9 + 9 * K;         // gradient values per face: 9 position + 9 per colour set
+  constexpr int KL = K - KF;            // live colour sets
+  constexpr int NV = 9 + 9 * KL;        // gradient values per face: 9 position + 9 per live colour set
   __shared__ float s_part[8][NV];
   const int lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(256, K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_M
     fetch_face(A, n, f, fv, tex9, sample == 1);
     face_setup(fv, sthr, g);
   }
-  float* gtex_out = A.grad_textures + wg * (K == 1 ? A.T * 3 : 9 * K);
+  float* gtex_out = A.grad_textures + wg * (K == 1 ? A.T * 3 : 9 * K) + 9 * KF;
 
   int xlo, xhi, ylo, yhi;
   coord_window(g.lox, g.hix, S, xlo, xhi);
@@ -370,11 +374,11 @@ __global__ void __launch_bounds__(256, K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_M
       return;
     }
   }
-  float gf[9], gt[9 * K];
+  float gf[9], gt[9 * KL];
 #pragma unroll
   for (int k = 0; k < 9; ++k) gf[k] = 0.f;
 #pragma unroll
-  for (int k = 0; k < 9 * K; ++k) gt[k] = 0.f;
+  for (int k = 0; k < 9 * KL; ++k) gt[k] = 0.f;
 
   if (xlo <= xhi && ylo <= yhi) {
     const int wdt = xhi - xlo + 1;
@@ -428,12 +432,12 @@ __global__ void __launch_bounds__(256, K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_M
         int texel = 0;
         if (sample == 0) texel = surface_texel(wc, A.R);
 #pragma unroll
-        for (int k = 0; k < 3 * K; ++k) {   // k = 3*set + channel
+        for (int k = 3 * KF; k < 3 * K; ++k) {   // k = 3*set + channel, live sets only
           const float gk = gs[k * SS + pn];
           float ck;
           if (sample == 1) {
             const float wg_k = wgt * gk;
-            float* gts = gt + 9 * (k / 3);
+            float* gts = gt + 9 * (k / 3 - KF);
             const float* ts = tex9 + 9 * (k / 3);
 #pragma unroll
             for (int j = 0; j < 3; ++j) gts[3 * j + k % 3] += wg_k * wc[j];
@@ -619,16 +623,21 @@ static int launch_backward(const RasterArgs& A, long long nf, cudaStream_t st) {
   if (cudaMemsetAsync(A.big_list, 0, sizeof(int), st) != cudaSuccess) return fail("raster_backward: memset failed");
   constexpr int kWarpsPerBlock = LASR_BWD_THREADS / 32;
   const unsigned blocks = (unsigned)((nf + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  if (A.K == 3) raster_backward_kernel<true, false, 3><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
-  else if (A.K == 2) raster_backward_kernel<true, false, 2><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
-  else if (is_fast(A)) raster_backward_kernel<true, false, 1><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
-  else raster_backward_kernel<false, false, 1><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+  const int kf = A.first_live_set;
+  if (A.K == 3 && kf == 1) raster_backward_kernel<true, false, 3, 1><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+  else if (A.K == 3) raster_backward_kernel<true, false, 3, 0><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+  else if (A.K == 2 && kf == 1) raster_backward_kernel<true, false, 2, 1><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+  else if (A.K == 2) raster_backward_kernel<true, false, 2, 0><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+  else if (is_fast(A)) raster_backward_kernel<true, false, 1, 0><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+  else raster_backward_kernel<false, false, 1, 0><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
   if (check_launch("raster_backward_kernel")) return 1;
   const unsigned big_blocks = 592;   // 4 per SM; each loops over the (usually empty) deferred list
-  if (A.K == 3) raster_backward_kernel<true, true, 3><<<big_blocks, 256, 0, st>>>(A);
-  else if (A.K == 2) raster_backward_kernel<true, true, 2><<<big_blocks, 256, 0, st>>>(A);
-  else if (is_fast(A)) raster_backward_kernel<true, true, 1><<<big_blocks, 256, 0, st>>>(A);
-  else raster_backward_kernel<false, true, 1><<<big_blocks, 256, 0, st>>>(A);
+  if (A.K == 3 && kf == 1) raster_backward_kernel<true, true, 3, 1><<<big_blocks, 256, 0, st>>>(A);
+  else if (A.K == 3) raster_backward_kernel<true, true, 3, 0><<<big_blocks, 256, 0, st>>>(A);
+  else if (A.K == 2 && kf == 1) raster_backward_kernel<true, true, 2, 1><<<big_blocks, 256, 0, st>>>(A);
+  else if (A.K == 2) raster_backward_kernel<true, true, 2, 0><<<big_blocks, 256, 0, st>>>(A);
+  else if (is_fast(A)) raster_backward_kernel<true, true, 1, 0><<<big_blocks, 256, 0, st>>>(A);
+  else raster_backward_kernel<false, true, 1, 0><<<big_blocks, 256, 0, st>>>(A);
   return check_launch("raster_backward_kernel<big>");
 }
 
@@ -646,7 +655,8 @@ __global__ void __launch_bounds__(256) vertex_gather_kernel(const float* __restr
                                                             const float* __restrict__ grad_textures,
                                                             const int* __restrict__ csr_offsets,
                                                             const int* __restrict__ csr_entries, float* grad_verts,
-                                                            float* grad_vcolors, int N, int V, int F, int K) {
+                                                            float* grad_vcolors, int N, int V, int F, int K,
+                                                            int first_live) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * V) return;
   const int n = (int)(i / V), v = (int)(i % V);
@@ -663,7 +673,7 @@ __global__ void __launch_bounds__(256) vertex_gather_kernel(const float* __restr
     const float* gc = gt + (long long)(ent / 3) * 9 * K + (ent % 3) * 3;
 #pragma unroll
     for (int s = 0; s < kMaxSets; ++s)
-      if (s < K) { c[3 * s] += gc[9 * s]; c[3 * s + 1] += gc[9 * s + 1]; c[3 * s + 2] += gc[9 * s + 2]; }
+      if (s >= first_live && s < K) { c[3 * s] += gc[9 * s]; c[3 * s + 1] += gc[9 * s + 1]; c[3 * s + 2] += gc[9 * s + 2]; }
   }
   grad_verts[i * 3] = a0; grad_verts[i * 3 + 1] = a1; grad_verts[i * 3 + 2] = a2;
 #pragma unroll
@@ -803,14 +813,17 @@ extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri,
                                          float near_, float far_, const float* near_far_dev, float eps,
                                          float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
                                          int func_id_rgb, int func_id_alpha, int double_side, int num_sets,
-                                         int setup_done, void* stream) {
+                                         int detached_sets, int setup_done, void* stream) {
   RasterArgs A{};
   if (num_sets < 1 || num_sets > kMaxSets) return fail("render: num_sets must be 1, 2 or 3");
+  if (detached_sets < 0 || detached_sets > 1 || detached_sets >= num_sets)
+    return fail("render_backward: detached_sets must be 0, or 1 with num_sets >= 2");
   if (workspace_bytes < lasr_b200_render_workspace_bytes(N, F, S, num_sets)) return fail("render: workspace too small");
   if (fill_args(A, N, F, S, 3, near_, far_, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
                 func_id_rgb, func_id_alpha, 1, double_side, workspace, workspace_bytes, num_sets))
     return 1;
   A.records_valid = setup_done;
+  A.first_live_set = detached_sets;
   if (fill_indexed(A, verts, tri, vcolors, V)) return 1;
   if (!soft_colors || !aggrs_info || !grad_soft_colors || !csr_offsets || !csr_entries || !grad_verts || !grad_vcolors)
     return fail("render_backward: null tensor pointer");
@@ -832,6 +845,6 @@ extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri,
   const long long nv = (long long)N * V;
   vertex_gather_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(A.grad_faces, A.grad_textures, csr_offsets,
                                                                       csr_entries, grad_verts, grad_vcolors, N, V, F,
-                                                                      num_sets);
+                                                                      num_sets, detached_sets);
   return check_launch("vertex_gather_kernel");
 }

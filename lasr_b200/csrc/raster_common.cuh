@@ -50,6 +50,7 @@ struct RasterArgs {
   const float* verts;        // [N,V,3] clip-space vertices   (null: direct mode, use `faces`)
   const float* vcolors;      // [K][N,V,3] vertex colours, K colour sets sharing one geometry pass
   int K;                     // number of colour sets (1 on the reference-signature paths); images have 3K+1 planes
+  int first_live_set;        // backward: colour sets below this index are detached (no gradient read / written)
   const int* tri;            // [F,3] shared topology
   int V;
   int N, F, S, T, R;

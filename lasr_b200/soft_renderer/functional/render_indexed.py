@@ -59,7 +59,7 @@ class RenderIndexedFunction(Function):
 
     @staticmethod
     def forward(ctx, vertices, vcolors, tri, image_size, background_color, near, far, fill_back, eps, sigma_val,
-                dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha):
+                dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha, detached_sets=0):
         if not vertices.is_cuda:
             raise _cabi.CudaTensorRequired("Rasterize module supports only cuda Tensors")
         dev = vertices.device
@@ -72,6 +72,9 @@ class RenderIndexedFunction(Function):
         ctx.near, ctx.far, ctx.nf = _near_far(near, far, dev)
         ctx.S = S
         K = 1 if c.dim() == 3 else int(c.shape[0])
+        if detached_sets not in (0, 1) or detached_sets >= K:
+            raise ValueError("detached_sets must be 0, or 1 with at least two colour sets")
+        ctx.detached = int(detached_sets)
         bg = [float(x) for x in np.asarray(background_color, dtype=np.float64).reshape(-1)]
         if len(bg) != 3 * K:
             raise ValueError("background_color needs 3 values per colour set")
@@ -92,17 +95,19 @@ class RenderIndexedFunction(Function):
         offsets, entries = vertex_adjacency(tri, V)
         gv, gc = torch.empty_like(v), torch.empty_like(c)
         _cabi.render_backward(v, tri, c, img, aggrs, grad.float().contiguous(), offsets, entries, gv, gc, ws, ctx.S,
-                              ctx.near, ctx.far, ctx.nf, *ctx.scal, setup_done=True)
+                              ctx.near, ctx.far, ctx.nf, *ctx.scal, setup_done=True, detached_sets=ctx.detached)
         vshape, cshape = ctx.shapes
-        return (gv.reshape(vshape), gc.reshape(cshape)) + (None,) * 13
+        return (gv.reshape(vshape), gc.reshape(cshape)) + (None,) * 14
 
 
 def render_indexed(vertices, vcolors, tri, image_size=256, background_color=[0, 0, 0], near=1, far=100,
                    fill_back=True, eps=1e-3, sigma_val=1e-5, dist_func="euclidean", dist_eps=1e-4, gamma_val=1e-4,
-                   aggr_func_rgb="softmax", aggr_func_alpha="prod"):
+                   aggr_func_rgb="softmax", aggr_func_alpha="prod", detached_sets=0):
     """vcolors [N,V,3] -> image [N,4,S,S] (RGBA, the reference's layout).  vcolors [K,N,V,3] with
     K = 2 or 3 renders K colour sets over ONE geometry pass -> image [N,3K+1,S,S] (set s in planes
     3s..3s+2, alpha last); background_color then holds K rgb triples.  Per set the result equals a
-    separate render of that set; the vertex gradient is the sum over the sets."""
+    separate render of that set; the vertex gradient is the sum over the sets.  detached_sets=1 declares
+    set 0 an output for reading only (as if its planes were ``.detach()``ed): the backward skips it."""
     return RenderIndexedFunction.apply(vertices, vcolors, tri, image_size, background_color, near, far, fill_back,
-                                       eps, sigma_val, dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha)
+                                       eps, sigma_val, dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha,
+                                       detached_sets)

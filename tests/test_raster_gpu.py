@@ -364,6 +364,20 @@ def test_colour_sets_in_one_pass_equal_separate_renders(srf, K):
         gv_sum += vb.grad
     err = (va.grad - gv_sum).norm()
     assert err <= 2e-5 * gv_sum.norm(), (float(err), float(gv_sum.norm()))
+    # detached_sets=1: set 0 is an output for reading only == zero upstream gradient on its planes
+    gz = gout.clone()
+    gz[:, :3] = 0
+    outs = []
+    for det in (0, 1):
+        vd = verts.clone().to(dev).requires_grad_(True)
+        cd = cols.clone().to(dev).requires_grad_(True)
+        im = srf.render_indexed(vd, cd, tri, background_color=[c for b in bgs for c in b], detached_sets=det, **kw)
+        assert torch.equal(im, img)
+        (im * (gz if det == 0 else gout)).sum().backward()      # det=1 must ignore planes 0-2 of gout
+        outs.append((vd.grad, cd.grad))
+    assert float(outs[1][1][0].abs().max()) == 0.0
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-8)
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-8)
     # deterministic
     va2 = verts.clone().to(dev).requires_grad_(True)
     ca2 = cols.clone().to(dev).requires_grad_(True)
