@@ -106,6 +106,8 @@ int lasr_b200_raster_backward(const float* faces, const float* textures, const f
  *                    the reference's RGBA layout); soft_colors arrives pre-filled with the backgrounds
  *   csr_offsets [V+1], csr_entries [3F] (entry = face*3 + corner, grouped by vertex, ascending):
  *                    vertex -> corner adjacency used to sum per-face gradients in a fixed order
+ *   background      HOST array of 3K floats (rgb per set), or NULL when soft_colors arrives pre-filled
+ *                    with the background the way the reference's op expects it (soft_rasterize.py:50-53)
  *   grad_verts [N,V,3], grad_vcolors [K,N,V,3] out (overwritten)
  *   detached_sets (backward): 0, or 1 with K >= 2 -- colour set 0 is rendered for reading only, as if
  *                    its planes were `.detach()`ed: planes 0-2 of grad_soft_colors are not read and
@@ -121,7 +123,7 @@ int lasr_b200_render_forward(const float* verts, const int32_t* tri, const float
                              int image_size, float near_, float far_, const float* near_far_dev,
                              float eps, float sigma_val, int func_id_dist, float dist_eps,
                              float gamma_val, int func_id_rgb, int func_id_alpha, int double_side,
-                             int num_sets, void* stream);
+                             int num_sets, const float* background, void* stream);
 
 int lasr_b200_render_backward(const float* verts, const int32_t* tri, const float* vcolors,
                               const float* soft_colors, const float* aggrs_info,
@@ -249,6 +251,27 @@ int lasr_b200_head_backward(const float* image, const float* pp_own, const float
                             const float* grad_sums, float* grad_image, float* grad_pp_pair,
                             float* grad_f_pair, void* workspace, size_t workspace_bytes, int N, int H,
                             int image_size, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Skinning weights, nnutils/mesh_net.py:264-267:
+ *   skin[h,b,v] = softmax_b( -10 * sum_d exp(log_ctl[h,b,d]) * ((ctl_ts[h,b] - verts[h,v]) . R(ctl_rs[h,b]))_d^2 )
+ * with R = kornia's quaternion_to_rotation_matrix (XYZW, normalised first).
+ *   ctl_ts, log_ctl [H*Bp,3]; ctl_rs [H*Bp,4]; verts [H,V,3] (the caller's detached mean shape)
+ *   skin [H,Bp,V] out -- the reference's [H,B-1,V,1] without the trailing 1; Bp = B-1 part bones, <= 128
+ * backward: grad_skin [H,Bp,V] -> grad_ctl_ts, grad_log_ctl [H*Bp,3], grad_ctl_rs [H*Bp,4] (overwritten).
+ * Deterministic (fixed-order partial sums).
+ * ------------------------------------------------------------------------------------------- */
+size_t lasr_b200_skin_workspace_bytes(int n_hypo, int n_part_bones, int num_vertices);
+
+int lasr_b200_skin_weights_forward(const float* ctl_ts, const float* ctl_rs, const float* log_ctl,
+                                   const float* verts, float* skin, int n_hypo, int n_part_bones,
+                                   int num_vertices, void* stream);
+
+int lasr_b200_skin_weights_backward(const float* ctl_ts, const float* ctl_rs, const float* log_ctl,
+                                    const float* verts, const float* skin, const float* grad_skin,
+                                    float* grad_ctl_ts, float* grad_ctl_rs, float* grad_log_ctl,
+                                    void* workspace, size_t workspace_bytes, int n_hypo,
+                                    int n_part_bones, int num_vertices, void* stream);
 
 #ifdef __cplusplus
 }

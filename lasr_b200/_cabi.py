@@ -49,10 +49,18 @@ def lib():
         _render_scalars = [_c.c_int] * 4 + [_c.c_float, _c.c_float, _c.c_void_p, _c.c_float, _c.c_float, _c.c_int,
                                             _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_render_forward.restype = _c.c_int
-        L.lasr_b200_render_forward.argtypes = [_c.c_void_p] * 6 + [_c.c_size_t] + _render_scalars + [_c.c_void_p]
+        L.lasr_b200_render_forward.argtypes = ([_c.c_void_p] * 6 + [_c.c_size_t] + _render_scalars
+                                               + [_c.POINTER(_c.c_float), _c.c_void_p])
         L.lasr_b200_render_backward.restype = _c.c_int
         L.lasr_b200_render_backward.argtypes = ([_c.c_void_p] * 11 + [_c.c_size_t] + _render_scalars
                                                 + [_c.c_int, _c.c_int, _c.c_void_p])
+        L.lasr_b200_skin_workspace_bytes.restype = _c.c_size_t
+        L.lasr_b200_skin_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
+        L.lasr_b200_skin_weights_forward.restype = _c.c_int
+        L.lasr_b200_skin_weights_forward.argtypes = [_c.c_void_p] * 5 + [_c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
+        L.lasr_b200_skin_weights_backward.restype = _c.c_int
+        L.lasr_b200_skin_weights_backward.argtypes = ([_c.c_void_p] * 10 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int,
+                                                                            _c.c_void_p])
         L.lasr_b200_head_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_head_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_head_forward.restype = _c.c_int
@@ -94,6 +102,7 @@ EXPORTED_SYMBOLS = [
     "lasr_b200_flow_epilogue_workspace_bytes", "lasr_b200_flow_epilogue_forward", "lasr_b200_flow_epilogue_backward",
     "lasr_b200_lbs_workspace_bytes", "lasr_b200_lbs_project_forward", "lasr_b200_lbs_project_backward",
     "lasr_b200_head_workspace_bytes", "lasr_b200_head_forward", "lasr_b200_head_backward",
+    "lasr_b200_skin_workspace_bytes", "lasr_b200_skin_weights_forward", "lasr_b200_skin_weights_backward",
 ]
 
 
@@ -229,7 +238,9 @@ def _num_sets(verts, vcolors):
 
 
 def render_forward(verts, tri, vcolors, aggrs_info, soft_colors, workspace, S, near, far, near_far_dev, eps,
-                   sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side):
+                   sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side,
+                   background=None):
+    """background: 3K floats (then soft_colors need not be pre-filled) or None (pre-filled image)."""
     for t, nm in ((verts, "verts"), (vcolors, "vcolors"), (aggrs_info, "aggrs_info"), (soft_colors, "soft_colors")):
         _require_cuda_f32(t, nm)
     if tri.dtype != torch.int32 or not tri.is_cuda or not tri.is_contiguous():
@@ -239,11 +250,16 @@ def render_forward(verts, tri, vcolors, aggrs_info, soft_colors, workspace, S, n
     K = _num_sets(verts, vcolors)
     if tuple(soft_colors.shape[:2]) != (N, 3 * K + 1):
         raise RuntimeError("soft_colors must be [N,3K+1,S,S]")
+    bg_arr = None
+    if background is not None:
+        if len(background) != 3 * K:
+            raise RuntimeError("background needs 3 floats per colour set")
+        bg_arr = (_c.c_float * (3 * K))(*[float(x) for x in background])
     with torch.cuda.device(verts.device):
         rc = lib().lasr_b200_render_forward(
             _p(verts), _p(tri), _p(vcolors), _p(aggrs_info), _p(soft_colors), _p(workspace), workspace.numel(),
             *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
-                                 gamma_val, func_id_rgb, func_id_alpha, double_side, K), _stream_ptr())
+                                 gamma_val, func_id_rgb, func_id_alpha, double_side, K), bg_arr, _stream_ptr())
     _check(rc, "lasr_b200_render_forward")
 
 
@@ -296,6 +312,26 @@ def losses_coefficients(sums, g3, gsub, gsums, N, H, l1tex_wt):
         rc = lib().lasr_b200_losses_coefficients(_p(sums), _p(g3), _p(gsub), _p(gsums), N, H, float(l1tex_wt),
                                                  _stream_ptr())
     _check(rc, "lasr_b200_losses_coefficients")
+
+
+def skin_weights_forward(ctl_ts, ctl_rs, log_ctl, verts, skin, H, Bp, V):
+    for t in (ctl_ts, ctl_rs, log_ctl, verts, skin):
+        _require_cuda_f32(t, "skin tensor")
+    with torch.cuda.device(verts.device):
+        rc = lib().lasr_b200_skin_weights_forward(_p(ctl_ts), _p(ctl_rs), _p(log_ctl), _p(verts), _p(skin), H, Bp, V,
+                                                  _stream_ptr())
+    _check(rc, "lasr_b200_skin_weights_forward")
+
+
+def skin_weights_backward(ctl_ts, ctl_rs, log_ctl, verts, skin, grad_skin, g_ts, g_rs, g_log, H, Bp, V):
+    for t in (ctl_ts, ctl_rs, log_ctl, verts, skin, grad_skin, g_ts, g_rs, g_log):
+        _require_cuda_f32(t, "skin tensor")
+    ws = torch.empty(int(lib().lasr_b200_skin_workspace_bytes(H, Bp, V)), dtype=torch.uint8, device=verts.device)
+    with torch.cuda.device(verts.device):
+        rc = lib().lasr_b200_skin_weights_backward(_p(ctl_ts), _p(ctl_rs), _p(log_ctl), _p(verts), _p(skin),
+                                                   _p(grad_skin), _p(g_ts), _p(g_rs), _p(g_log), _p(ws), ws.numel(),
+                                                   H, Bp, V, _stream_ptr())
+    _check(rc, "lasr_b200_skin_weights_backward")
 
 
 def head_forward(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, sums, flow_rd, bgmask, N, H, S):

@@ -329,6 +329,7 @@ __global__ void flow_epilogue_reduce_kernel(const float* partial, int n, int nbl
 // Arithmetic is that of flow_epilogue_* and losses_* above, expression for expression.
 // ---------------------------------------------------------------------------------------------
 constexpr int kHeadPlanes = 10;
+constexpr int kHeadPixPerBlock = 1024;   // 4 pixels per thread: enough blocks in flight to cover the 17 loads per pixel
 
 struct HeadArgs {
   const float* image;      // [N*H,10,S,S]
@@ -369,8 +370,8 @@ __global__ void __launch_bounds__(kLossThreads) head_forward_kernel(HeadArgs A, 
   float acc[kNumSums];
 #pragma unroll
   for (int q = 0; q < kNumSums; ++q) acc[q] = 0.f;
-  const int p0 = blockIdx.x * kLossPixPerBlock;
-  const int p1 = min(p0 + kLossPixPerBlock, A.SS);
+  const int p0 = blockIdx.x * kHeadPixPerBlock;
+  const int p1 = min(p0 + kHeadPixPerBlock, A.SS);
   for (int p = p0 + threadIdx.x; p < p1; p += kLossThreads) {
     const float occ = A.occ[i * SS + p];
     const float m = A.masks[i * SS + p];
@@ -621,7 +622,7 @@ extern "C" int lasr_b200_flow_epilogue_backward(const float* px, const float* f1
 extern "C" size_t lasr_b200_head_workspace_bytes(int N, int H, int S) {
   if (N <= 0 || H <= 0 || S <= 0) return 0;
   const size_t SS = (size_t)S * S;
-  const size_t a = (size_t)N * H * ((SS + kLossPixPerBlock - 1) / kLossPixPerBlock) * kNumSums * sizeof(float);
+  const size_t a = (size_t)N * H * ((SS + kHeadPixPerBlock - 1) / kHeadPixPerBlock) * kNumSums * sizeof(float);
   const size_t b = (size_t)N * H * ((SS + 255) / 256) * 3 * sizeof(float);
   return (a > b ? a : b) + 256;
 }
@@ -636,7 +637,7 @@ extern "C" int lasr_b200_head_forward(const float* image, const float* pp_own, c
   if (!sums || !workspace || workspace_bytes < lasr_b200_head_workspace_bytes(N, H, S))
     return lasr_fail("head_forward: null output or workspace too small");
   if ((flow_rd == nullptr) != (bgmask == nullptr)) return lasr_fail("head_forward: flow_rd and bgmask go together");
-  const int nblk = (A.SS + kLossPixPerBlock - 1) / kLossPixPerBlock;
+  const int nblk = (A.SS + kHeadPixPerBlock - 1) / kHeadPixPerBlock;
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = reinterpret_cast<float*>(workspace);
   head_forward_kernel<<<dim3(nblk, N * H), kLossThreads, 0, st>>>(A, partial, nblk, flow_rd, bgmask);

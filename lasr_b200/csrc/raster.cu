@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
   st.face_min = -1;
 #pragma unroll
   for (int k = 0; k < 3 * K; ++k) {
-    const float bg = valid ? A.soft_colors[((long long)n * P + k) * SS + pn] : 0.f;
+    const float bg = A.bg_in_args ? A.bg[k] : (valid ? A.soft_colors[((long long)n * P + k) * SS + pn] : 0.f);
     st.col[k] = rgb_f == 1 ? bg * st.ssum : bg;
   }
 
@@ -776,7 +776,7 @@ extern "C" int lasr_b200_render_forward(const float* verts, const int32_t* tri, 
                                         size_t workspace_bytes, int N, int V, int F, int S, float near_, float far_,
                                         const float* near_far_dev, float eps, float sigma_val, int func_id_dist,
                                         float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
-                                        int double_side, int num_sets, void* stream) {
+                                        int double_side, int num_sets, const float* background, void* stream) {
   RasterArgs A{};
   if (num_sets < 1 || num_sets > kMaxSets) return fail("render: num_sets must be 1, 2 or 3");
   if (workspace_bytes < lasr_b200_render_workspace_bytes(N, F, S, num_sets)) return fail("render: workspace too small");
@@ -786,6 +786,10 @@ extern "C" int lasr_b200_render_forward(const float* verts, const int32_t* tri, 
   if (fill_indexed(A, verts, tri, vcolors, V)) return 1;
   if (!aggrs_info || !soft_colors) return fail("render_forward: null tensor pointer");
   A.aggrs_info = aggrs_info; A.soft_colors = soft_colors;
+  if (background) {   // host array of 3*num_sets floats: no pre-fill pass over the image, no read of it here
+    A.bg_in_args = 1;
+    for (int k = 0; k < 3 * num_sets; ++k) A.bg[k] = background[k];
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const long long nf = (long long)N * F;
   const long long nthreads = nf > S ? nf : S;

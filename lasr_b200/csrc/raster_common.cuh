@@ -51,6 +51,8 @@ struct RasterArgs {
   const float* vcolors;      // [K][N,V,3] vertex colours, K colour sets sharing one geometry pass
   int K;                     // number of colour sets (1 on the reference-signature paths); images have 3K+1 planes
   int first_live_set;        // backward: colour sets below this index are detached (no gradient read / written)
+  int bg_in_args;            // forward: background colours come from bg[] instead of a pre-filled soft_colors
+  float bg[3 * kMaxSets];
   const int* tri;            // [F,3] shared topology
   int V;
   int N, F, S, T, R;

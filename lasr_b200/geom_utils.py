@@ -42,6 +42,9 @@ def skin_weights(ctl_ts, ctl_rs, log_ctl, mean_v, n_hypo):
     ctl_ts [H*(B-1),3], ctl_rs [H*(B-1),4] (XYZW), log_ctl [H*(B-1),3], mean_v [H,V,3] (detached by
     the caller, as the reference does) -> skin [H,B-1,V,1]."""
     H = n_hypo
+    if _use_native(mean_v):
+        from . import native_geom
+        return native_geom.SkinWeightsFunction.apply(ctl_ts, ctl_rs, log_ctl, mean_v, H)
     dis = ctl_ts.view(H, -1, 1, 3) - mean_v.view(H, 1, -1, 3)
     dis = dis.matmul(quaternion_to_rotation_matrix(ctl_rs).view(H, -1, 3, 3))
     dis = log_ctl.exp().view(H, -1, 1, 3) * dis.pow(2)

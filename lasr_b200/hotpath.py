@@ -61,13 +61,24 @@ class RenderHotPath(torch.nn.Module):
         if B > 1:                      # mesh_net.py:261-281
             skin = gu.skin_weights(bones["ctl_ts"], bones["ctl_rs"], bones["log_ctl"],
                                    pred_v.view(n2, H, -1, 3)[0].detach(), H)
-            skin = skin.repeat(n2, 1, 1, 1)
+            fused_route = o.fused and pred_v.is_cuda and o.opt_tex
+            if not (fused_route and H == 1):       # the fused LBS kernel reads one shared [1,B-1,V] table
+                skin = skin.repeat(n2, 1, 1, 1)
             rest_ts = bones["rest_ts"][:, None, :, None].repeat(n2, 1, 1, 1).view(-1, B - 1, 3, 1)
             R4 = Rmat.view(-1, B, 3, 3)
             T4 = Tmat.view(-1, B, 3, 1)
             T_parts = -R4[:, 1:].matmul(rest_ts) + T4[:, 1:] + rest_ts
             Tmat = torch.cat([T4[:, :1], T_parts], 1).view(-1, 3)
             Rmat = torch.cat([R4[:, :1], R4[:, 1:].permute(0, 1, 3, 2)], 1).view(-1, 3, 3)
+        if o.fused and pred_v.is_cuda and o.opt_tex:
+            # 1') LBS + camera + projection + depth window in ONE kernel (lasr_b200_lbs_project_forward)
+            from . import native_geom
+            pp_rep = ppoint[:, None].repeat(1, H, 1).view(n2 * H, 2)
+            cam, px3, (near, far) = native_geom.skin_project(pred_v, Rmat, Tmat, B, skin, pp_rep, scale.view(-1),
+                                                             tocam=True, depth_window=True)
+            self.renderer_softtex.rasterizer.near, self.renderer_softtex.rasterizer.far = near, far
+            self.renderer_softtex.rasterizer.sigma_val = o.sigval
+            return self._forward_fused(cam, px3, tex, faces, ppoint, scale, batch, shared_faces, near, far)
         # 1) LBS + camera (mesh_net.py:298-311)
         cam = gu.obj_to_cam(pred_v, Rmat, Tmat[:, None, :], B, H, skin)
         verts_fl = torch.cat([cam, torch.ones_like(cam[:, :, :1])], dim=-1)
@@ -78,8 +89,6 @@ class RenderHotPath(torch.nn.Module):
         for r in (self.renderer_softflf, self.renderer_softflb, self.renderer_softtex):
             r.rasterizer.near, r.rasterizer.far = near, far
             r.rasterizer.sigma_val = o.sigval
-        if o.fused and verts_px.is_cuda and o.opt_tex:
-            return self._forward_fused(verts_fl, verts_px, tex, faces, ppoint, scale, batch, shared_faces, near, far)
         # 2) flow renders (mesh_net.py:318-335)
         px4 = verts_px.view(n2, H, -1, 4)
         rep = lambda t, lo, hi: t[:, None][lo:hi].repeat(1, H, 1).view(-1, t.shape[-1])
@@ -121,7 +130,7 @@ class RenderHotPath(torch.nn.Module):
                     mask_pred=mask_pred, texture_render=rgb, flow_rd=flow_rd, bgmask=bgmask, verts_px=verts_px,
                     near=near, far=far)
 
-    def _forward_fused(self, verts_fl, verts_px, tex, faces, ppoint, scale, batch, shared_faces, near, far):
+    def _forward_fused(self, cam, verts_px, tex, faces, ppoint, scale, batch, shared_faces, near, far):
         """Steps 2-4 of ``forward`` with the mesh rasterized ONCE per frame.  The reference renders every
         posed frame three times with the same geometry and renderer settings but different vertex
         attributes -- flow (own + paired camera-space positions, mesh_net.py:77-87, 318-335) and texture
@@ -134,10 +143,10 @@ class RenderHotPath(torch.nn.Module):
         bs = n2 // 2
         nh = n2 * H
         r = self.renderer_softtex
+        from .soft_renderer.functional.geometry import _const
         offset = gu._eye_offset(r, verts_px.device)
-        pre = verts_px[:, :, :3] + offset
-        pre = torch.cat([pre[:, :, :1], -pre[:, :, 1:2], pre[:, :, 2:]], dim=-1)
-        own = verts_fl[:, :, :3]
+        pre = (verts_px[:, :, :3] + offset) * _const([1.0, -1.0, 1.0], verts_px.device)   # y flip (:83), exact
+        own = cam                                            # camera-space positions [n2*H,V,3]
         pair = torch.roll(own.view(n2, H, -1, 3), bs, 0).reshape(nh, -1, 3)     # frame i <-> i +- bs
         sets = torch.stack([own, pair, tex.reshape(nh, -1, 3).to(own.dtype)], 0)
         faces_h = faces[:, None].repeat(1, H, 1, 1).view(-1, faces.shape[1], 3)

@@ -79,6 +79,33 @@ class SkinProjectFunction(Function):
                 None, None, None)
 
 
+class SkinWeightsFunction(Function):
+    """nnutils/mesh_net.py:264-267 on CUDA tensors (lasr_b200_skin_weights_forward/backward).
+    (ctl_ts [H*Bp,3], ctl_rs [H*Bp,4], log_ctl [H*Bp,3], mean_v [H,V,3]) -> skin [H,Bp,V,1]; mean_v gets no
+    gradient (the reference detaches it, :266)."""
+
+    @staticmethod
+    def forward(ctx, ctl_ts, ctl_rs, log_ctl, mean_v, H):
+        c = lambda t, sh: t.detach().float().reshape(sh).contiguous()
+        Bp = ctl_ts.numel() // (3 * H)
+        V = mean_v.numel() // (3 * H)
+        ts, rs, lg, mv = c(ctl_ts, (H * Bp, 3)), c(ctl_rs, (H * Bp, 4)), c(log_ctl, (H * Bp, 3)), c(mean_v, (H, V, 3))
+        skin = torch.empty(H, Bp, V, dtype=torch.float32, device=mean_v.device)
+        _cabi.skin_weights_forward(ts, rs, lg, mv, skin, H, Bp, V)
+        ctx.save_for_backward(ts, rs, lg, mv, skin)
+        ctx.meta = (H, Bp, V, ctl_ts.shape, ctl_rs.shape, log_ctl.shape)
+        return skin[:, :, :, None]
+
+    @staticmethod
+    def backward(ctx, g):
+        ts, rs, lg, mv, skin = ctx.saved_tensors
+        H, Bp, V, s_ts, s_rs, s_lg = ctx.meta
+        g = g.float().reshape(H, Bp, V).contiguous()
+        g_ts, g_rs, g_lg = torch.empty_like(ts), torch.empty_like(rs), torch.empty_like(lg)
+        _cabi.skin_weights_backward(ts, rs, lg, mv, skin, g, g_ts, g_rs, g_lg, H, Bp, V)
+        return g_ts.reshape(s_ts), g_rs.reshape(s_rs), g_lg.reshape(s_lg), None, None
+
+
 def skin_project(verts, Rmat, Tmat, nmesh, skin=None, pp=None, fl=None, tocam=True, depth_window=False):
     """Fused G1+G2+G3.  verts [N or 1,V,3]; Rmat [N*nmesh,3,3]; Tmat [N*nmesh,(1,)3];
     skin [N or 1,nmesh-1,V(,1)]; pp [N,2] and fl [N(,1)] per FRAME (already repeated over hypotheses).

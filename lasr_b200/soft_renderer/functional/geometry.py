@@ -75,6 +75,15 @@ def look_at(vertices, eye, at=[0, 0, 0], up=[0, 1, 0]):
     if vertices.ndimension() != 3:
         raise ValueError("vertices Tensor should have 3 dimensions")
     bs, device = vertices.shape[0], vertices.device
+    key = None
+    if all(isinstance(t, (list, tuple)) for t in (eye, at, up)):
+        # a camera given as Python constants (LASR: renderer.transform.transformer._eye) has a constant
+        # basis: build it once per (camera, batch size, device) with the very same ops, then reuse
+        key = (tuple(map(float, eye)), tuple(map(float, at)), tuple(map(float, up)), bs, str(device))
+        hit = _look_at_cache.get(key)
+        if hit is not None:
+            eye_b, rt = hit
+            return torch.matmul(vertices - eye_b, rt)
     eye, at, up = _as_batch(eye, bs, device), _as_batch(at, bs, device), _as_batch(up, bs, device)
     z_axis = F.normalize(at - eye, eps=1e-5)
     x_axis = F.normalize(torch.cross(up, z_axis, dim=1), eps=1e-5)
@@ -82,7 +91,14 @@ def look_at(vertices, eye, at=[0, 0, 0], up=[0, 1, 0]):
     r = torch.stack((x_axis, y_axis, z_axis), dim=1)
     if vertices.shape != eye.shape:
         eye = eye[:, None, :]
+    if key is not None and not (vertices.is_cuda and torch.cuda.is_current_stream_capturing()):
+        if len(_look_at_cache) > 32:
+            _look_at_cache.clear()
+        _look_at_cache[key] = (eye.contiguous(), r.transpose(1, 2).contiguous())
     return torch.matmul(vertices - eye, r.transpose(1, 2))
+
+
+_look_at_cache = {}
 
 
 def look(vertices, eye, direction=[0, 1, 0], up=None):
@@ -108,6 +124,8 @@ def orthogonal(vertices, scale):
     """orthogonal.py:4-17 -- x,y scaled, z kept."""
     if vertices.ndimension() != 3:
         raise ValueError("vertices Tensor should have 3 dimensions")
+    if isinstance(scale, (int, float)) and scale == 1 and vertices.shape[2] == 3:
+        return vertices          # x*1 is exact: value-identical to the stack below (LASR: viewing_scale=1)
     return torch.stack((vertices[:, :, 0] * scale, vertices[:, :, 1] * scale, vertices[:, :, 2]), dim=2)
 
 

@@ -80,10 +80,9 @@ class RenderIndexedFunction(Function):
             raise ValueError("background_color needs 3 values per colour set")
         aggrs = torch.empty(N, 2, S, S, dtype=torch.float32, device=dev)
         img = torch.empty(N, 3 * K + 1, S, S, dtype=torch.float32, device=dev)
-        for k in range(3 * K):
-            img[:, k].fill_(bg[k])       # fills, not an H2D copy: CUDA-graph safe
         ws = _cabi.render_workspace(N, tri.shape[0], S, dev, K)
-        _cabi.render_forward(v, tri, c, aggrs, img, ws, S, ctx.near, ctx.far, ctx.nf, *ctx.scal)
+        # background colours travel as kernel arguments: no fill pass over the image (CUDA-graph safe)
+        _cabi.render_forward(v, tri, c, aggrs, img, ws, S, ctx.near, ctx.far, ctx.nf, *ctx.scal, background=bg)
         ctx.save_for_backward(v, c, tri, img, aggrs, ws)
         ctx.shapes = (vertices.shape, vcolors.shape)
         return img

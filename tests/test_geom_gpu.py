@@ -147,3 +147,37 @@ def test_fused_image_losses_match_cpu_expressions(dev):
     lm, lf, lt, _ = losses.image_losses(t(mask_pred), t(masks), t(occ), t(flow_rd), t(bg), t(flow_obs), t(tex), t(fg),
                                         t(imgs), 0.7)
     assert torch.allclose(torch.stack([lm, lf, lt]).cpu(), torch.stack(a[:3]), rtol=2e-4)
+
+
+@pytest.mark.parametrize("H,Bp,V", [(1, 25, 2930), (2, 7, 642), (1, 1, 100)])
+def test_native_skin_weights_match_the_reference_expression(H, Bp, V):
+    """S0 kernel (lasr_b200_skin_weights_*) vs the reference's expression (nnutils/mesh_net.py:264-267) run as
+    plain PyTorch in float64 on the CPU: weights and the gradients of all three bone parameters."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from lasr_b200 import geom_utils as gu
+    g = torch.Generator().manual_seed(H * 100 + Bp)
+    mean_v = torch.randn(H, V, 3, generator=g) * 0.3
+    idx = torch.randint(0, V, (H, Bp), generator=g)
+    ctl_ts = torch.stack([mean_v[h, idx[h]] for h in range(H)]).reshape(H * Bp, 3) + 0.01
+    ctl_rs = torch.tensor([[0.0, 0.0, 0.0, 1.0]]).repeat(H * Bp, 1) + torch.randn(H * Bp, 4, generator=g) * 0.2
+    ctl_rs = ctl_rs * (0.5 + torch.rand(H * Bp, 1, generator=g))          # not unit length
+    log_ctl = 1.0 + torch.randn(H * Bp, 3, generator=g) * 0.5
+    gout = torch.randn(H, Bp, V, 1, generator=g)
+
+    def run(dev, dt):
+        leaves = [x.clone().to(dev, dt).requires_grad_(True) for x in (ctl_ts, ctl_rs, log_ctl)]
+        skin = gu.skin_weights(leaves[0], leaves[1], leaves[2], mean_v.to(dev, dt), H)
+        (skin * gout.to(dev, dt)).sum().backward()
+        return skin.detach().cpu().double(), [x.grad.cpu().double() for x in leaves]
+
+    s_gpu, g_gpu = run(torch.device("cuda", 0), torch.float32)
+    s_ref, g_ref = run(torch.device("cpu"), torch.float64)
+    assert s_gpu.shape == (H, Bp, V, 1)
+    assert float((s_gpu - s_ref).abs().max()) < 2e-6
+    assert float((s_gpu.sum(1) - 1).abs().max()) < 1e-5
+    for a, b, nm in zip(g_gpu, g_ref, ("ctl_ts", "ctl_rs", "log_ctl")):
+        assert (a - b).norm() <= 2e-5 * b.norm() + 1e-7, (nm, float((a - b).norm()), float(b.norm()))
+    # deterministic
+    s2, g2 = run(torch.device("cuda", 0), torch.float32)
+    assert torch.equal(s2, s_gpu) and all(torch.equal(x, y) for x, y in zip(g2, g_gpu))

@@ -204,9 +204,9 @@ def test_fused_head_equals_epilogue_plus_losses():
 
     assert torch.equal(bg_a, bg_b) and torch.equal(flow_a, flow_b)
     for x, y in ((ml, ml2), (fl, fl2), (tl, tl2)):
-        assert abs(float(x) - float(y)) <= 1e-6 * abs(float(y)) + 1e-9
+        assert abs(float(x) - float(y)) <= 1e-5 * abs(float(y)) + 1e-9
     for k in sub:
-        assert torch.allclose(sub[k], sub2[k], rtol=1e-6, atol=1e-9)
+        assert torch.allclose(sub[k], sub2[k], rtol=1e-5, atol=1e-9)
     names = ("image", "pp_own", "pp_pair", "f_own", "f_pair")
     for nm, x, y in zip(names, a, b):
         if y.grad is None:
