@@ -361,7 +361,44 @@ def extras_microbench(device, peak_gbs, iters=20):
                            "forward_frac_of_hbm_peak": loss_fwd_bytes / t_lf / 1e6 / peak_gbs,
                            "backward_frac_of_hbm_peak": loss_bwd_bytes / t_lb / 1e6 / peak_gbs,
                            "note": "sums + reduce + finalize kernels forward; coefficient + per-pixel kernels backward"}
+    out["hot_path"] = hot_path_microbench(device)
     return out
+
+
+def hot_path_microbench(device, iters=15):
+    """The whole render region of LASR.forward (mesh_net.py:255-447: skin weights -> LBS -> projection ->
+    flow fw/bw + texture renders -> three losses, forward + backward) at config E's shape (Spot, 64 frames,
+    26 bones, 256^2), as one CUDA graph: `fused` = one three-set render + fused head, `three_renders` = the
+    reference's structure (three SoftRas passes per frame) on the same kernels."""
+    import torch
+    from lasr_b200 import hotpath, synth
+    from lasr_b200.pipeline import GraphedStep
+    n_pairs, B, S = 32, 26, 256
+    inp, leaves = synth.hot_path_inputs(n_pairs, B, S, device)
+    res = {"shape": f"Spot, {2 * n_pairs} frames, {B} bones, {S}^2, CUDA graph, CUDA-event timed"}
+    for name, fused in (("fused", True), ("three_renders", False)):
+        m = hotpath.RenderHotPath(hotpath.HotPathOptions(img_size=S, n_hypo=1, n_bones=B, fused=fused)).to(device)
+
+        def step(*xs):
+            xs = [x.detach().requires_grad_(True) for x in xs]
+            bn = dict(zip(inp["bones"].keys(), xs[6:]))
+            o = m(xs[0], xs[1], inp["faces"], xs[2], xs[3], xs[4], xs[5], inp["batch"], bn)
+            o["total"].backward()
+            return (o["total"].detach(),) + tuple(x.grad for x in xs)
+
+        run = GraphedStep(step, leaves)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            outs = run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        res[name] = {"ms_per_step": ms, "frames_per_s": 2 * n_pairs / ms * 1e3, "loss": float(outs[0])}
+    return res
 
 
 def run_gpu_arm(args, arm_cls):

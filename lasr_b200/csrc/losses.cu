@@ -360,6 +360,53 @@ __device__ __forceinline__ HeadFlow head_flow(const HeadArgs& A, const float* im
   return r;
 }
 
+// per-pixel body of the forward head: planes x[0..9], observations, accumulators
+__device__ __forceinline__ void head_pixel(const HeadArgs& A, int ij, const float* x, float occ, float m,
+                                           const float* im3, float fobs_x, float fobs_y, float* acc, bool want_flow,
+                                           float2* flow, uint8_t* bgo) {
+  const bool v = occ != 0.f;
+  const bool fgm = m > 0.f;
+  const float alpha = x[9];
+  if (v) {
+    acc[6] += 1.f;
+    const float d = alpha - m;
+    acc[0] += d * d;
+  }
+  if ((v && fgm) || want_flow) {
+    float x0 = x[0], y0 = x[1], z0 = x[2], x1 = x[3], y1 = x[4], z1 = x[5];
+    const bool bg = z0 < 1e-9f || z1 < 1e-9f;
+    if (bg) { x0 = y0 = z0 = 10.f; x1 = y1 = z1 = 10.f; }
+    const float f0 = A.f_own[ij], f1 = A.f_pair[ij];
+    const float u0 = A.pp_own[2 * ij] + x0 * f0 / z0, v0 = A.pp_own[2 * ij + 1] + y0 * f0 / z0;
+    const float u1 = A.pp_pair[2 * ij] + x1 * f1 / z1, v1 = A.pp_pair[2 * ij + 1] + y1 * f1 / z1;
+    const float fx = u1 - u0, fy = v1 - v0;
+    if (want_flow) { *flow = make_float2(fx, fy); *bgo = bg ? 1 : 0; }
+    if (v && fgm && !bg) {
+      const float dx = fx - fobs_x, dy = fy - fobs_y;
+      const float s = 1.f / (1.f + expf(occ));
+      acc[1] += s * sqrtf(dx * dx + dy * dy);
+      acc[2] += s;
+      acc[3] += 1.f;
+    }
+  }
+  if (v) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float obs = fgm ? im3[c] : 0.f;
+      const float white = fgm ? im3[c] : 1.f;
+      const float t = x[6 + c];
+      a += fabsf(obs - t * alpha);
+      b += fabsf(white - t);
+    }
+    acc[4] += a * (1.f / 3.f);
+    acc[5] += b * (1.f / 3.f);
+  }
+}
+
+// kVec = 4: each thread takes 4 consecutive pixels with 128-bit loads (needs S*S % 4 == 0): 17 independent
+// float4 loads in flight per thread instead of 17 dependent-latency scalar rounds
+template <int kVec>
 __global__ void __launch_bounds__(kLossThreads) head_forward_kernel(HeadArgs A, float* partial, int nblk,
                                                                     float* flow_out, uint8_t* bg_out) {
   __shared__ float s_w[kLossThreads / 32][kNumSums];
@@ -372,45 +419,40 @@ __global__ void __launch_bounds__(kLossThreads) head_forward_kernel(HeadArgs A, 
   for (int q = 0; q < kNumSums; ++q) acc[q] = 0.f;
   const int p0 = blockIdx.x * kHeadPixPerBlock;
   const int p1 = min(p0 + kHeadPixPerBlock, A.SS);
-  for (int p = p0 + threadIdx.x; p < p1; p += kLossThreads) {
-    const float occ = A.occ[i * SS + p];
-    const float m = A.masks[i * SS + p];
-    const bool v = occ != 0.f;
-    const bool fgm = m > 0.f;
-    const float alpha = img[9 * SS + p];
-    if (v) {
-      acc[6] += 1.f;
-      const float d = alpha - m;
-      acc[0] += d * d;
-    }
-    if ((v && fgm) || flow_out) {
-      const HeadFlow fl = head_flow(A, img, ij, p);
-      if (flow_out) {
-        reinterpret_cast<float2*>(flow_out)[ij * SS + p] = make_float2(fl.fx, fl.fy);
-        bg_out[ij * SS + p] = fl.bg ? 1 : 0;
-      }
-      if (v && fgm && !fl.bg) {
-        const float dx = fl.fx - A.flow_obs[(i * 3 + 0) * SS + p];
-        const float dy = fl.fy - A.flow_obs[(i * 3 + 1) * SS + p];
-        const float s = 1.f / (1.f + expf(occ));
-        acc[1] += s * sqrtf(dx * dx + dy * dy);
-        acc[2] += s;
-        acc[3] += 1.f;
-      }
-    }
-    if (v) {
-      float a = 0.f, b = 0.f;
+  for (int p = p0 + threadIdx.x * kVec; p < p1; p += kLossThreads * kVec) {
+    float x[kHeadPlanes][kVec], occ[kVec], m[kVec], im[3][kVec], fo[2][kVec];
+    if (kVec == 4) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float im = A.imgs[(i * 3 + c) * SS + p];
-        const float obs = fgm ? im : 0.f;
-        const float white = fgm ? im : 1.f;
-        const float t = img[(6 + c) * SS + p];
-        a += fabsf(obs - t * alpha);
-        b += fabsf(white - t);
+      for (int c = 0; c < kHeadPlanes; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(img + c * SS + p);
+        x[c][0] = t.x; x[c][1] = t.y; x[c][2] = t.z; x[c][kVec - 1] = t.w;
       }
-      acc[4] += a * (1.f / 3.f);
-      acc[5] += b * (1.f / 3.f);
+      auto ld4 = [&](const float* base, float* o) {
+        const float4 t = *reinterpret_cast<const float4*>(base + p);
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[kVec - 1] = t.w;
+      };
+      ld4(A.occ + i * SS, occ); ld4(A.masks + i * SS, m);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ld4(A.imgs + (i * 3 + c) * SS, im[c]);
+      ld4(A.flow_obs + (i * 3 + 0) * SS, fo[0]); ld4(A.flow_obs + (i * 3 + 1) * SS, fo[1]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < kHeadPlanes; ++c) x[c][0] = img[c * SS + p];
+      occ[0] = A.occ[i * SS + p]; m[0] = A.masks[i * SS + p];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) im[c][0] = A.imgs[(i * 3 + c) * SS + p];
+      fo[0][0] = A.flow_obs[(i * 3 + 0) * SS + p]; fo[1][0] = A.flow_obs[(i * 3 + 1) * SS + p];
+    }
+#pragma unroll
+    for (int e = 0; e < kVec; ++e) {
+      float xe[kHeadPlanes], im3[3];
+#pragma unroll
+      for (int c = 0; c < kHeadPlanes; ++c) xe[c] = x[c][e];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) im3[c] = im[c][e];
+      head_pixel(A, ij, xe, occ[e], m[e], im3, fo[0][e], fo[1][e], acc, flow_out != nullptr,
+                 flow_out ? reinterpret_cast<float2*>(flow_out) + ij * SS + p + e : nullptr,
+                 bg_out ? bg_out + ij * SS + p + e : nullptr);
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -640,7 +682,8 @@ extern "C" int lasr_b200_head_forward(const float* image, const float* pp_own, c
   const int nblk = (A.SS + kHeadPixPerBlock - 1) / kHeadPixPerBlock;
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = reinterpret_cast<float*>(workspace);
-  head_forward_kernel<<<dim3(nblk, N * H), kLossThreads, 0, st>>>(A, partial, nblk, flow_rd, bgmask);
+  if (A.SS % 4 == 0) head_forward_kernel<4><<<dim3(nblk, N * H), kLossThreads, 0, st>>>(A, partial, nblk, flow_rd, bgmask);
+  else head_forward_kernel<1><<<dim3(nblk, N * H), kLossThreads, 0, st>>>(A, partial, nblk, flow_rd, bgmask);
   if (lasr_check_launch("head_forward_kernel")) return 1;
   const int tot = N * H * kNumSums;
   losses_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(partial, nblk, N * H, sums);

@@ -131,3 +131,44 @@ def render_inputs(verts, faces, n_frames, seed=0):
 def gather_faces(verts_nv3, faces):
     """[N,V,C] x [F,3] -> [N,F,3,C] (functional/face_vertices.py with a shared topology)."""
     return np.ascontiguousarray(verts_nv3[:, faces.astype(np.int64)])
+
+
+def hot_path_inputs(n_pairs: int, n_bones: int, image_size: int, device, n_hypo: int = 1, seed: int = 0):
+    """Synthetic inputs of the whole render hot path (lasr_b200.hotpath.RenderHotPath) at SURVEY 8(d)'s
+    config-E shape: the Spot mesh, ``2*n_pairs`` frames on the render_syn.py camera orbit, ``n_bones``
+    bones (1 body + parts with small random articulations, rest pose at sampled vertices), random
+    observations.  Returns (args tuple for RenderHotPath.forward, list of differentiable leaves)."""
+    import torch
+    from .geom_utils import quaternion_to_rotation_matrix
+    g = torch.Generator().manual_seed(seed)
+    v, f = load_spot()
+    V, n2, H, B, S = len(v), 2 * n_pairs, n_hypo, n_bones, image_size
+    N = n2 * H
+    Rb, Tb, _, _ = spot_cameras(N)
+    pred_v = torch.from_numpy(v)[None].repeat(N, 1, 1).to(device)
+    tex = torch.from_numpy(vertex_colors(V))[None].repeat(N, 1, 1).to(device)
+    faces = torch.from_numpy(f)[None].repeat(n2, 1, 1).to(device)
+    q = torch.randn(N * B, 4, generator=g) * 0.05
+    q[:, 3] = 1
+    R = quaternion_to_rotation_matrix(q).view(N, B, 3, 3)
+    R[:, 0] = torch.from_numpy(Rb)
+    Rmat = R.view(-1, 3, 3).contiguous().to(device)
+    T = torch.randn(N * B, 3, generator=g) * 0.01
+    T.view(N, B, 3)[:, 0] = torch.from_numpy(Tb[:, 0])
+    Tmat = T.to(device)
+    ppoint = torch.zeros(n2, 2, device=device)
+    scale = torch.full((N, 1), 10.0, device=device)
+    bones = None
+    if B > 1:
+        idx = torch.randperm(V, generator=g)[:H * (B - 1)]
+        ctl = torch.from_numpy(v)[idx].to(device)
+        bones = dict(ctl_ts=ctl.clone(), rest_ts=ctl.clone(),
+                     ctl_rs=torch.tensor([[0., 0, 0, 1]], device=device).repeat(H * (B - 1), 1),
+                     log_ctl=torch.ones(H * (B - 1), 3, device=device))
+    batch = dict(masks=(torch.rand(n2, S, S, generator=g) > 0.5).float().to(device),
+                 imgs=torch.rand(n2, 3, S, S, generator=g).to(device),
+                 flow=(torch.randn(n2, 3, S, S, generator=g) * 0.02).to(device),
+                 occ=torch.randn(n2, S, S, generator=g).to(device))
+    leaves = [pred_v, tex, Rmat, Tmat, ppoint, scale] + (list(bones.values()) if bones else [])
+    return dict(pred_v=pred_v, tex=tex, faces=faces, Rmat=Rmat, Tmat=Tmat, ppoint=ppoint, scale=scale, batch=batch,
+                bones=bones), leaves

@@ -14,33 +14,10 @@ use_graph = (sys.argv[3] == "graph") if len(sys.argv) > 3 else False
 use_ref = (sys.argv[3] == "reference") if len(sys.argv) > 3 else False
 H, S = 1, 256
 dev = torch.device("cuda", 0)
-g = torch.Generator().manual_seed(0)
-v, f = synth.load_spot()
-V, n2 = len(v), 2 * bs
+inp, leaves = synth.hot_path_inputs(bs, B, S, dev, n_hypo=H)
+faces, batch, bones = inp["faces"], inp["batch"], inp["bones"]
+n2 = 2 * bs
 N = n2 * H
-Rb, Tb, pp, fl = synth.spot_cameras(N)
-pred_v = torch.from_numpy(v)[None].repeat(N, 1, 1).to(dev)
-tex = torch.from_numpy(synth.vertex_colors(V))[None].repeat(N, 1, 1).to(dev)
-faces = torch.from_numpy(f)[None].repeat(n2, 1, 1).to(dev)
-q = torch.randn(N * B, 4, generator=g) * 0.05
-q[:, 3] = 1
-R = quaternion_to_rotation_matrix(q).view(N, B, 3, 3)
-R[:, 0] = torch.from_numpy(Rb)
-Rmat = R.view(-1, 3, 3).permute(0, 2, 1).permute(0, 2, 1).contiguous().to(dev)
-T = torch.randn(N * B, 3, generator=g) * 0.01
-T.view(N, B, 3)[:, 0] = torch.from_numpy(Tb[:, 0])
-Tmat = T.to(dev)
-ppoint = torch.zeros(n2, 2, device=dev)
-scale = torch.full((N, 1), 10.0, device=dev)
-bones = None
-if B > 1:
-    idx = torch.randperm(V, generator=g)[:H * (B - 1)]
-    ctl = torch.from_numpy(v)[idx].to(dev)
-    bones = dict(ctl_ts=ctl.clone(), rest_ts=ctl.clone(), ctl_rs=torch.tensor([[0., 0, 0, 1]], device=dev).repeat(H * (B - 1), 1),
-                 log_ctl=torch.ones(H * (B - 1), 3, device=dev))
-batch = dict(masks=(torch.rand(n2, S, S, generator=g) > 0.5).float().to(dev), imgs=torch.rand(n2, 3, S, S, generator=g).to(dev),
-             flow=(torch.randn(n2, 3, S, S, generator=g) * 0.02).to(dev), occ=torch.randn(n2, S, S, generator=g).to(dev))
-leaves = [pred_v, tex, Rmat, Tmat, ppoint, scale] + (list(bones.values()) if bones else [])
 fused = os.environ.get("FUSED", "1") != "0"            # one three-set render + fused head (default) vs three renders
 report_flow = os.environ.get("REPORT_FLOW", "1") != "0"
 m = hotpath.RenderHotPath(hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B, fused=fused,
