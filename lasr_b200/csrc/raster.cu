@@ -42,6 +42,10 @@ constexpr int kTileW = 16;                      // tile width in pixels (two 8x4
 constexpr int kTileH = LASR_TILE_H;             // tile height in pixels (multiple of 4)
 constexpr int kFwdWarps = 2 * (kTileH / 4);     // each warp owns an 8x4 pixel footprint
 constexpr int kFwdThreads = 32 * kFwdWarps;
+#ifndef LASR_SCAN_UNROLL            // window loads kept in flight per thread in the tile scan
+#define LASR_SCAN_UNROLL 2
+#endif
+constexpr int kScanUnroll = LASR_SCAN_UNROLL;
 constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indices, under the 48 KB default limit with the static smem); one round if F fits
 #ifndef LASR_FWD_MIN_BLOCKS
 #define LASR_FWD_MIN_BLOCKS 4
@@ -54,6 +58,9 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #endif
 #ifndef LASR_BWD_MIN_BLOCKS_MULTI
 #define LASR_BWD_MIN_BLOCKS_MULTI 2
+#endif
+#ifndef LASR_PREFETCH_REC           // warm L1 with a face's record when it passes the warp cull
+#define LASR_PREFETCH_REC 1
 #endif
 #ifndef LASR_BWD_THREADS
 #define LASR_BWD_THREADS 128
@@ -234,7 +241,7 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
     // (1) scan: warp w owns faces [base + w*wseg, base + (w+1)*wseg) and compacts hits in order
     int cnt = 0;
     const int seg0 = base + warp * wseg;
-#pragma unroll 2
+#pragma unroll kScanUnroll
     for (int it = 0; it < wseg; it += 32) {
       const int f = seg0 + it + lane;
       bool hit = false;
@@ -265,6 +272,14 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
           f = lst[j];
           bd = __ldg(border + f);
           pass = !(fx0 > bd.y || fx1 < bd.x || fy0 > bd.w || fy1 < bd.z);
+#if LASR_PREFETCH_REC
+          if (pass) {
+            const char* rp = reinterpret_cast<const char*>(records + (long long)f * kRecWords);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rp));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + 128));
+            if (kRecWords * 4 > 208) asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + kRecWords * 4 - 16));
+          }
+#endif
         }
         unsigned m = __ballot_sync(0xffffffffu, pass);
         while (m) {
@@ -396,9 +411,9 @@ __global__ void __launch_bounds__(256, K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_M
       const float xp = A.coords[xi];
       const float yp = A.coords[yi];
       if (xp > g.hix || xp < g.lox || yp > g.hiy || yp < g.loy) continue;
+      const long long pn = (long long)(S - 1 - yi) * S + xi;
       Fragment fr;
       if (!soft_fragment<kFast>(A, g, xp, yp, thr, fr)) continue;
-      const long long pn = (long long)(S - 1 - yi) * S + xi;
       // alpha term (.cu:582-593); for 'hard' alpha the reference still adds the raw upstream
       // gradient (nothing resets C_grad_xy_alpha), reproduced here
       float Cxy = gs[(P - 1) * SS + pn];
@@ -409,7 +424,7 @@ __global__ void __launch_bounds__(256, K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_M
       if (zp < near_ || zp > far_) continue;
       float gz[3] = {0.f, 0.f, 0.f};
       if (rgb_f == 0) {  // .cu:602-609
-        if ((float)f == ag[SS + pn]) {
+        if ((float)f == ag[SS + pn]) {   // (hard rgb: generic path only)
           if (sample == 1) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
