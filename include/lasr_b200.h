@@ -273,6 +273,44 @@ int lasr_b200_skin_weights_backward(const float* ctl_ts, const float* ctl_rs, co
                                     void* workspace, size_t workspace_bytes, int n_hypo,
                                     int n_part_bones, int num_vertices, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Mesh regularisers on the sparse topology.  The reference evaluates them through
+ * dense V x V matrices; these take a CSR vertex adjacency / an edge list built once per topology.
+ *   nbr_offsets [V+1], nbr [E2]: unique neighbours of every vertex, ascending (E2 = directed edges =
+ *                    non-zeros of the reference's adjacency matrix)
+ *   LaplacianLoss (third_party/ext_nnutils/loss_utils.py:34-65):  lap = L x with L = I - D^-1 A (rows of
+ *                    isolated vertices zero), loss[n] = sum lap^2.   x, lap, grad_x [N,V,3]; loss [N]
+ *   ARAPLoss (nnutils/loss_utils.py:29-64):  loss[n] = mean over directed edges (a,b) of
+ *                    | |x_b-x_a|^2 - |dx_b-dx_a|^2 |
+ *   FlattenLoss (third_party/ext_nnutils/loss_utils.py:67-152):  edges [E,4] = (v0, v1, v2, v3): an edge
+ *                    and the opposite vertices of its two faces; loss[n] = sum_e (cos(dihedral)+1)^2;
+ *                    inc_offsets [V+1], inc [4E] (entry = edge*4 + slot, grouped by vertex, ascending):
+ *                    vertex -> edge-corner incidence used to sum the per-edge gradients in a fixed order
+ * Every gradient is formed in gather form: no atomics, deterministic.
+ * ------------------------------------------------------------------------------------------- */
+size_t lasr_b200_meshreg_workspace_bytes(int N, int num_vertices, int num_edges);
+
+int lasr_b200_laplacian_forward(const float* x, const int32_t* nbr_offsets, const int32_t* nbr, float* lap,
+                                float* loss, void* workspace, size_t workspace_bytes, int N,
+                                int num_vertices, void* stream);
+int lasr_b200_laplacian_backward(const float* lap, const float* grad_loss, const int32_t* nbr_offsets,
+                                 const int32_t* nbr, float* grad_x, int N, int num_vertices, void* stream);
+
+int lasr_b200_arap_forward(const float* dx, const float* x, const int32_t* nbr_offsets, const int32_t* nbr,
+                           float* loss, void* workspace, size_t workspace_bytes, int N, int num_vertices,
+                           int num_directed_edges, void* stream);
+int lasr_b200_arap_backward(const float* dx, const float* x, const float* grad_loss,
+                            const int32_t* nbr_offsets, const int32_t* nbr, float* grad_dx, float* grad_x,
+                            int N, int num_vertices, int num_directed_edges, void* stream);
+
+int lasr_b200_flatten_forward(const float* x, const int32_t* edges, float* loss, void* workspace,
+                              size_t workspace_bytes, int N, int num_vertices, int num_edges, float eps,
+                              void* stream);
+int lasr_b200_flatten_backward(const float* x, const int32_t* edges, const float* grad_loss,
+                               const int32_t* inc_offsets, const int32_t* inc, float* grad_x,
+                               void* workspace, size_t workspace_bytes, int N, int num_vertices,
+                               int num_edges, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

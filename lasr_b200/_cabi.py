@@ -54,6 +54,17 @@ def lib():
         L.lasr_b200_render_backward.restype = _c.c_int
         L.lasr_b200_render_backward.argtypes = ([_c.c_void_p] * 11 + [_c.c_size_t] + _render_scalars
                                                 + [_c.c_int, _c.c_int, _c.c_void_p])
+        L.lasr_b200_meshreg_workspace_bytes.restype = _c.c_size_t
+        L.lasr_b200_meshreg_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
+        vp, ci = _c.c_void_p, _c.c_int
+        for name, args in (("laplacian_forward", [vp] * 6 + [_c.c_size_t, ci, ci, vp]),
+                           ("laplacian_backward", [vp] * 5 + [ci, ci, vp]),
+                           ("arap_forward", [vp] * 6 + [_c.c_size_t, ci, ci, ci, vp]),
+                           ("arap_backward", [vp] * 7 + [ci, ci, ci, vp]),
+                           ("flatten_forward", [vp] * 4 + [_c.c_size_t, ci, ci, ci, _c.c_float, vp]),
+                           ("flatten_backward", [vp] * 7 + [_c.c_size_t, ci, ci, ci, _c.c_float, vp])):
+            fn = getattr(L, "lasr_b200_" + name)
+            fn.restype, fn.argtypes = ci, args
         L.lasr_b200_skin_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_skin_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_skin_weights_forward.restype = _c.c_int
@@ -103,6 +114,8 @@ EXPORTED_SYMBOLS = [
     "lasr_b200_lbs_workspace_bytes", "lasr_b200_lbs_project_forward", "lasr_b200_lbs_project_backward",
     "lasr_b200_head_workspace_bytes", "lasr_b200_head_forward", "lasr_b200_head_backward",
     "lasr_b200_skin_workspace_bytes", "lasr_b200_skin_weights_forward", "lasr_b200_skin_weights_backward",
+    "lasr_b200_meshreg_workspace_bytes", "lasr_b200_laplacian_forward", "lasr_b200_laplacian_backward",
+    "lasr_b200_arap_forward", "lasr_b200_arap_backward", "lasr_b200_flatten_forward", "lasr_b200_flatten_backward",
 ]
 
 
@@ -312,6 +325,28 @@ def losses_coefficients(sums, g3, gsub, gsums, N, H, l1tex_wt):
         rc = lib().lasr_b200_losses_coefficients(_p(sums), _p(g3), _p(gsub), _p(gsums), N, H, float(l1tex_wt),
                                                  _stream_ptr())
     _check(rc, "lasr_b200_losses_coefficients")
+
+
+def meshreg_workspace(N, V, E, device):
+    return torch.empty(int(lib().lasr_b200_meshreg_workspace_bytes(N, V, E)), dtype=torch.uint8, device=device)
+
+
+def meshreg_call(name, *args):
+    """lasr_b200_<name>(*args, stream): tensors become device pointers, numbers pass through."""
+    dev = next(a.device for a in args if torch.is_tensor(a))
+    conv = []
+    for a in args:
+        if torch.is_tensor(a):
+            if not a.is_cuda or not a.is_contiguous():
+                raise CudaTensorRequired(f"lasr_b200_{name}: tensors must be contiguous CUDA tensors")
+            if a.dtype not in (torch.float32, torch.int32, torch.uint8):
+                raise RuntimeError(f"lasr_b200_{name}: unsupported dtype {a.dtype}")
+            conv.append(_p(a))
+        else:
+            conv.append(a)
+    with torch.cuda.device(dev):
+        rc = getattr(lib(), "lasr_b200_" + name)(*conv, _stream_ptr())
+    _check(rc, "lasr_b200_" + name)
 
 
 def skin_weights_forward(ctl_ts, ctl_rs, log_ctl, verts, skin, H, Bp, V):
