@@ -32,12 +32,13 @@ def _run(mods, tag, device, dtype):
     return out
 
 
-def _check(out, tag, rtol):
+def _check(out, tag, rtol, flatten_grad_rtol=None):
     for name, (loss, gx, gdx) in out.items():
         ref = GOLD[f"{tag}_{name}"]
         assert np.abs(loss - ref).max() <= rtol * np.abs(ref).max(), (name, loss, ref)
         rg = GOLD[f"{tag}_{name}_gx"]
-        assert np.linalg.norm(gx - rg) <= rtol * np.linalg.norm(rg), (name, "grad_x")
+        tol = flatten_grad_rtol if (name == "flatten" and flatten_grad_rtol) else rtol
+        assert np.linalg.norm(gx - rg) <= tol * np.linalg.norm(rg), (name, "grad_x", np.linalg.norm(gx - rg) / np.linalg.norm(rg))
         if gdx is not None:
             rd = GOLD[f"{tag}_arap_gdx"]
             assert np.linalg.norm(gdx - rd) <= rtol * np.linalg.norm(rd), (name, "grad_dx")
@@ -93,7 +94,9 @@ def test_average_flag_and_shapes():
 def test_kernels_match_reference_python(tag):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    _check(_run(_mods(tag, "cuda"), tag, "cuda", torch.float32), tag, 2e-5)
+    # the flatten gradient is ill-conditioned on the near-regular ico2 sphere: the reference's own expression
+    # evaluated by PyTorch in fp32 is 1.2e-4 away from its fp64 value there (4e-7 on ico1), hence 5e-4
+    _check(_run(_mods(tag, "cuda"), tag, "cuda", torch.float32), tag, 2e-5, flatten_grad_rtol=5e-4)
 
 
 @pytest.mark.gpu
