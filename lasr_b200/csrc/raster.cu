@@ -59,9 +59,6 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #ifndef LASR_BWD_MIN_BLOCKS_MULTI
 #define LASR_BWD_MIN_BLOCKS_MULTI 2
 #endif
-#ifndef LASR_TRI_CULL               // cull (warp footprint, face) pairs against the dilated TRIANGLE, not only its bbox
-#define LASR_TRI_CULL 1
-#endif
 #ifndef LASR_PREFETCH_REC           // warm L1 with a face's record when it passes the warp cull
 #define LASR_PREFETCH_REC 1
 #endif
@@ -108,25 +105,6 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RasterArgs A, int wit
     }
   }
   A.face_border[i] = make_float4(g.lox, g.hix, g.loy, g.hiy);
-  {  // edge functions pushed outwards by the influence radius: a pixel block on which one of them is negative
-     // everywhere is farther than the radius from the edge's line, hence from the triangle (which lies on the
-     // inner side of all three lines), hence rejected by the distance stage for every pixel (.cu:402).
-     // Radius = 1.25 x sqrt(threshold): the reference's computed distance may undershoot the geometric one
-     // by a few per cent.  Thin / degenerate faces (height below half the radius, clamped determinant,
-     // non-finite inverse) keep the bounding-box test only: their edge functions are ill-conditioned.
-    const float m = 1.25f * sthr;
-    float4 ef[3];
-    bool safe = fabsf(g.det) > 1e-9f && A.dist != 1;   // 'barycentric' distances are not Euclidean: bbox test only
-#pragma unroll
-    for (int e = 0; e < 3; ++e) {
-      const float gx = g.inv[3 * e], gy = g.inv[3 * e + 1], gc = g.inv[3 * e + 2];
-      const float gn = sqrtf(gx * gx + gy * gy);
-      safe = safe && isfinite(gx) && isfinite(gy) && isfinite(gc) && gn > 0.f && gn * (0.5f * sthr) < 1.f;
-      ef[e] = make_float4(gx, gy, gc + m * gn, 0.f);
-    }
-#pragma unroll
-    for (int e = 0; e < 3; ++e) A.face_edges[3 * i + e] = safe ? ef[e] : make_float4(0.f, 0.f, 1.f, 0.f);
-  }
   if (A.K == 1) store_record<1>(A.face_record + i * rec_words(1), g, vertex_tex ? tex9 : nullptr);
   else if (A.K == 2) store_record<2>(A.face_record + i * rec_words(2), g, tex9);
   else store_record<3>(A.face_record + i * rec_words(3), g, tex9);
@@ -254,7 +232,6 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
 
   const uint2* win = A.face_window + (long long)n * A.F;
   const float4* border = A.face_border + (long long)n * A.F;
-  const float4* edges = A.face_edges + (long long)n * A.F * 3;
   const float* records = A.face_record + (long long)n * A.F * kRecWords;
 
   // tiles that no face window of this frame reaches skip the scan and go straight to the epilogue
@@ -295,16 +272,6 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
           f = lst[j];
           bd = __ldg(border + f);
           pass = !(fx0 > bd.y || fx1 < bd.x || fy0 > bd.w || fy1 < bd.z);
-#if LASR_TRI_CULL
-          if (pass) {
-#pragma unroll
-            for (int e = 0; e < 3; ++e) {
-              const float4 q = __ldg(edges + 3 * f + e);
-              const float wmax = q.x * (q.x > 0.f ? fx1 : fx0) + q.y * (q.y > 0.f ? fy1 : fy0) + q.z;
-              pass = pass && !(wmax < 0.f);
-            }
-          }
-#endif
 #if LASR_PREFETCH_REC
           if (pass) {
             const char* rp = reinterpret_cast<const char*>(records + (long long)f * kRecWords);
@@ -629,7 +596,7 @@ static size_t raster_ws_bytes(int N, int F, int S, int K) {
   const size_t nf = (size_t)N * (size_t)F;
   return align256(nf * sizeof(uint2)) + align256((size_t)S * sizeof(float)) + align256((size_t)N * 4 * sizeof(int)) +
          align256((size_t)(kBigListCap + 1) * sizeof(int)) +
-         align256(nf * sizeof(float4)) + align256(nf * 3 * sizeof(float4)) +
+         align256(nf * sizeof(float4)) +
          align256(nf * rec_words(K) * sizeof(float));
 }
 
@@ -660,7 +627,6 @@ static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, flo
   A.frame_window = reinterpret_cast<int*>(p);    p += align256((size_t)N * 4 * sizeof(int));
   A.big_list = reinterpret_cast<int*>(p);        p += align256((size_t)(kBigListCap + 1) * sizeof(int));
   A.face_border = reinterpret_cast<float4*>(p);  p += align256(nf * sizeof(float4));
-  A.face_edges = reinterpret_cast<float4*>(p);   p += align256(nf * 3 * sizeof(float4));
   A.face_record = reinterpret_cast<float*>(p);
   return 0;
 }

@@ -40,7 +40,6 @@ struct RasterArgs {
   // workspace carve-up
   uint2* face_window;        // [N*F] packed pixel windows
   float4* face_border;       // [N*F] dilated bounding boxes (lox, hix, loy, hiy)
-  float4* face_edges;        // [N*F][3] outward-offset edge functions (gx, gy, gc', -) for the warp-level cull
   float* face_record;        // [N*F][rec_words(K)]
   float* coords;             // [S] pixel-centre coordinates
   int records_valid;         // backward: workspace already holds the forward's setup of the same inputs
