@@ -15,43 +15,51 @@ from torch.autograd import Function
 from ... import _cabi
 from .soft_rasterize import ALPHA_FUNCS, DIST_FUNCS, RGB_FUNCS, _near_far
 
+import weakref
+
+# Caches are keyed by the identity of the tensor OBJECT (id + a weak reference that must still resolve to the
+# same object) and its in-place version counter -- not by data_ptr, which the allocator may hand to a
+# different tensor of the same shape later.
 _topology_cache = {}
+_csr_cache = {}
+
+
+def _cache_get(cache, t, extra=()):
+    hit = cache.get(id(t))
+    if hit is not None and hit[0]() is t and hit[1] == (t._version,) + tuple(extra):
+        return hit[2]
+    return None
+
+
+def _cache_put(cache, t, value, extra=()):
+    key = id(t)
+    cache[key] = (weakref.ref(t, lambda _r, k=key, c=cache: c.pop(k, None)), (t._version,) + tuple(extra), value)
+    return value
 
 
 def shared_topology(faces):
-    """[N,F,3] faces -> ([F,3] int32, csr_offsets [V+1]... built lazily) if all frames share one
-    topology, else None.  The (one-off, synchronising) equality check is cached per tensor."""
+    """[N,F,3] faces -> [F,3] int32 if all frames share one topology, else None.  The (one-off,
+    synchronising) equality check is cached per tensor object."""
     if faces.dim() == 2:
-        return faces.to(torch.int32).contiguous()
-    key = (faces.data_ptr(), faces._version, tuple(faces.shape), faces.dtype, str(faces.device))
-    hit = _topology_cache.get(key)
+        return faces if (faces.dtype == torch.int32 and faces.is_contiguous()) else faces.to(torch.int32).contiguous()
+    hit = _cache_get(_topology_cache, faces)
     if hit is None:
         same = bool((faces == faces[:1]).all()) if faces.shape[0] > 1 else True
-        hit = faces[0].to(torch.int32).contiguous() if same else False
-        if len(_topology_cache) > 64:
-            _topology_cache.clear()
-        _topology_cache[key] = hit
+        hit = _cache_put(_topology_cache, faces, faces[0].to(torch.int32).contiguous() if same else False)
     return hit if hit is not False else None
-
-
-_csr_cache = {}
 
 
 def vertex_adjacency(tri, num_vertices):
     """vertex -> (face, corner) adjacency as CSR; entries of a vertex are in ascending face order so
-    the gradient sum has a fixed order.  Cached per topology tensor."""
-    key = (tri.data_ptr(), tri._version, tuple(tri.shape), num_vertices)
-    hit = _csr_cache.get(key)
+    the gradient sum has a fixed order.  Cached per topology tensor object."""
+    hit = _cache_get(_csr_cache, tri, (num_vertices,))
     if hit is None:
         flat = tri.reshape(-1).long()
         order = torch.argsort(flat, stable=True)
         counts = torch.bincount(flat, minlength=num_vertices)
         offsets = torch.zeros(num_vertices + 1, dtype=torch.int32, device=tri.device)
         offsets[1:] = torch.cumsum(counts, 0).to(torch.int32)
-        hit = (offsets.contiguous(), order.to(torch.int32).contiguous())
-        if len(_csr_cache) > 64:
-            _csr_cache.clear()
-        _csr_cache[key] = hit
+        hit = _cache_put(_csr_cache, tri, (offsets.contiguous(), order.to(torch.int32).contiguous()), (num_vertices,))
     return hit
 
 
@@ -83,15 +91,17 @@ class RenderIndexedFunction(Function):
         ws = _cabi.render_workspace(N, tri.shape[0], S, dev, K)
         # background colours travel as kernel arguments: no fill pass over the image (CUDA-graph safe)
         _cabi.render_forward(v, tri, c, aggrs, img, ws, S, ctx.near, ctx.far, ctx.nf, *ctx.scal, background=bg)
-        ctx.save_for_backward(v, c, tri, img, aggrs, ws)
+        # the adjacency is looked up here, where `tri` is the caller's (cached) tensor object; the backward
+        # only sees re-wrapped saved tensors
+        offsets, entries = vertex_adjacency(tri, V)
+        ctx.save_for_backward(v, c, tri, img, aggrs, ws, offsets, entries)
         ctx.shapes = (vertices.shape, vcolors.shape)
         return img
 
     @staticmethod
     def backward(ctx, grad):
-        v, c, tri, img, aggrs, ws = ctx.saved_tensors
+        v, c, tri, img, aggrs, ws, offsets, entries = ctx.saved_tensors
         N, V = v.shape[:2]
-        offsets, entries = vertex_adjacency(tri, V)
         gv, gc = torch.empty_like(v), torch.empty_like(c)
         _cabi.render_backward(v, tri, c, img, aggrs, grad.float().contiguous(), offsets, entries, gv, gc, ws, ctx.S,
                               ctx.near, ctx.far, ctx.nf, *ctx.scal, setup_done=True, detached_sets=ctx.detached)
