@@ -311,6 +311,46 @@ int lasr_b200_flatten_backward(const float* x, const int32_t* edges, const float
                                void* workspace, size_t workspace_bytes, int N, int num_vertices,
                                int num_edges, float eps, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Chamfer3D nearest neighbours.
+ * Replaces the pybind module `chamfer_3D` (third_party/chamfer3D/chamfer_cuda.cpp:9-32; kernels
+ * chamfer3D.cu:12-196) behind chamfer_3DFunction (third_party/chamfer3D/dist_chamfer_3D.py:27-63);
+ * LASR's call site: nnutils/mesh_net.py:474-478, scripts/eval_mesh.py:168.
+ *   forward(xyz1, xyz2, dist1, dist2, idx1, idx2):
+ *     xyz1 [B,n,3], xyz2 [B,m,3] in;  dist1 [B,n] = min_k |xyz1_j - xyz2_k|^2 (SQUARED distance),
+ *     idx1 [B,n] int32 = the lowest k attaining it;  dist2 [B,m], idx2 [B,m] the same with the roles swapped.
+ *   backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2):
+ *     gradxyz1 [B,n,3], gradxyz2 [B,m,3] are fully OVERWRITTEN (the reference accumulates into
+ *     caller-zeroed buffers, dist_chamfer_3D.py:54-58; same values).  The matched-target terms are
+ *     scattered with float atomics, as in the reference (chamfer3D.cu:169-174).
+ * ------------------------------------------------------------------------------------------- */
+int lasr_b200_chamfer_forward(const float* xyz1, const float* xyz2, float* dist1, float* dist2,
+                              int32_t* idx1, int32_t* idx2, int batch_size, int n, int m, void* stream);
+int lasr_b200_chamfer_backward(const float* xyz1, const float* xyz2, const float* grad_dist1,
+                               const float* grad_dist2, const int32_t* idx1, const int32_t* idx2,
+                               float* grad_xyz1, float* grad_xyz2, int batch_size, int n, int m,
+                               void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Texture atlas kernels of the SoftRas extension family.
+ * Replace the pybind modules `soft_renderer.cuda.load_textures` (load_textures_cuda.cpp:19-36, kernel
+ * load_textures_cuda_kernel.cu:8-66; caller functional/load_obj.py:100) and
+ * `soft_renderer.cuda.create_texture_image` (create_texture_image_cuda.cpp:17-34, kernel
+ * create_texture_image_cuda_kernel.cu:10-73; caller functional/save_obj.py:27).
+ *   load_textures(image, faces, textures, is_update):
+ *     image [H,W,3] (already flipped, 0..1), faces [F,3,2] texture coordinates, is_update [F] int32,
+ *     textures [F,R*R,3] in/out: faces with is_update != 0 are resampled bilinearly, the rest kept.
+ *   create_texture_image(vertices_all, textures, image, eps):
+ *     faces [F,3,2] texture coordinates in ATLAS PIXELS, textures [F,R*R,3], image [H,W,3] out
+ *     (cells of faces >= F are left untouched), tile_width = int(sqrt(F-1))+1, cell = W / tile_width.
+ * ------------------------------------------------------------------------------------------- */
+int lasr_b200_load_textures(const float* image, const float* faces, const int32_t* is_update,
+                            float* textures, int num_faces, int texture_res, int image_height,
+                            int image_width, void* stream);
+int lasr_b200_create_texture_image(const float* faces, const float* textures, float* image,
+                                   int num_faces, int texture_res_in, int image_height, int image_width,
+                                   float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

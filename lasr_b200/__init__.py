@@ -12,4 +12,8 @@ def install_as_soft_renderer():
     from . import soft_renderer as _sr
     _sys.modules["soft_renderer"] = _sr
     _sys.modules["soft_renderer.functional"] = _sr.functional
+    # the brute-force nearest-neighbour extension LASR imports next to it (nnutils/train_utils.py:43)
+    from . import chamfer3D as _ch
+    _sys.modules["chamfer3D"] = _ch
+    _sys.modules["chamfer3D.dist_chamfer_3D"] = _ch.dist_chamfer_3D
     return _sr

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.environ.get("LASR_B200_LIB") or os.path.join(CSRC, "liblasr_b200.so")  # override: A/B builds
-SOURCES = ["host_common.cu", "raster.cu", "lbs.cu", "losses.cu", "skin.cu", "meshreg.cu"]
+SOURCES = ["host_common.cu", "raster.cu", "lbs.cu", "losses.cu", "skin.cu", "meshreg.cu", "chamfer.cu", "texture_io.cu"]
 HEADERS = ["raster_common.cuh", "host_common.h"]
 
 
@@ -24,18 +24,30 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, defines=()) -> str:
+    """Compile every source to an object in parallel (one nvcc each), then link the shared library."""
     if not force and not _stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-           "-Xcompiler", "-fPIC", "--shared", "-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH]
+    objdir = os.path.join(CSRC, "build", os.path.basename(LIB_PATH) + ".obj")
+    os.makedirs(objdir, exist_ok=True)
+    common = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC] + [f"-D{d}" for d in defines]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    subprocess.check_call(cmd)
+        common += ["-Xptxas", "-v"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        subprocess.check_call(common + ["-c", os.path.join(CSRC, src), "-o", obj])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    subprocess.check_call([nvcc, "--shared", "-o", LIB_PATH] + objs)
     return LIB_PATH
 
 
 if __name__ == "__main__":
-    print(build_library(force=True, verbose=True))
+    import sys
+    print(build_library(force=True, verbose="-v" in sys.argv, defines=[a[2:] for a in sys.argv[1:] if a.startswith("-D")]))

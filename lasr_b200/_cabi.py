@@ -62,7 +62,11 @@ def lib():
                            ("arap_forward", [vp] * 6 + [_c.c_size_t, ci, ci, ci, vp]),
                            ("arap_backward", [vp] * 7 + [ci, ci, ci, vp]),
                            ("flatten_forward", [vp] * 4 + [_c.c_size_t, ci, ci, ci, _c.c_float, vp]),
-                           ("flatten_backward", [vp] * 7 + [_c.c_size_t, ci, ci, ci, _c.c_float, vp])):
+                           ("flatten_backward", [vp] * 7 + [_c.c_size_t, ci, ci, ci, _c.c_float, vp]),
+                           ("chamfer_forward", [vp] * 6 + [ci, ci, ci, vp]),
+                           ("chamfer_backward", [vp] * 8 + [ci, ci, ci, vp]),
+                           ("load_textures", [vp] * 4 + [ci, ci, ci, ci, vp]),
+                           ("create_texture_image", [vp] * 3 + [ci, ci, ci, ci, _c.c_float, vp])):
             fn = getattr(L, "lasr_b200_" + name)
             fn.restype, fn.argtypes = ci, args
         L.lasr_b200_skin_workspace_bytes.restype = _c.c_size_t
@@ -116,6 +120,8 @@ EXPORTED_SYMBOLS = [
     "lasr_b200_skin_workspace_bytes", "lasr_b200_skin_weights_forward", "lasr_b200_skin_weights_backward",
     "lasr_b200_meshreg_workspace_bytes", "lasr_b200_laplacian_forward", "lasr_b200_laplacian_backward",
     "lasr_b200_arap_forward", "lasr_b200_arap_backward", "lasr_b200_flatten_forward", "lasr_b200_flatten_backward",
+    "lasr_b200_chamfer_forward", "lasr_b200_chamfer_backward",
+    "lasr_b200_load_textures", "lasr_b200_create_texture_image",
 ]
 
 
@@ -329,6 +335,10 @@ def losses_coefficients(sums, g3, gsub, gsums, N, H, l1tex_wt):
 
 def meshreg_workspace(N, V, E, device):
     return torch.empty(int(lib().lasr_b200_meshreg_workspace_bytes(N, V, E)), dtype=torch.uint8, device=device)
+
+
+def native_call(name, *args):
+    return meshreg_call(name, *args)
 
 
 def meshreg_call(name, *args):

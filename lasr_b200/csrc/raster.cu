@@ -168,10 +168,10 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConst
     const float zn = kFast ? (C.far_ - zp) * C.inv_range : (C.far_ - zp) / (C.far_ - C.near_);
     float rescale = 1.f;
     if (zn > st.smax) {
-      rescale = kFast ? __expf((st.smax - zn) * A.inv_gamma) : expf((st.smax - zn) / A.gamma);
+      rescale = kFast ? fast_exp((st.smax - zn) * A.inv_gamma) : expf((st.smax - zn) / A.gamma);
       st.smax = zn;
     }
-    const float ez = (kFast ? __expf((zn - st.smax) * A.inv_gamma) : expf((zn - st.smax) / A.gamma)) * fr.frag;
+    const float ez = (kFast ? fast_exp((zn - st.smax) * A.inv_gamma) : expf((zn - st.smax) / A.gamma)) * fr.frag;
     st.ssum = rescale * st.ssum + ez;
 #pragma unroll
     for (int k = 0; k < 3 * K; ++k) st.col[k] = rescale * st.col[k] + ez * sample_tex(k);
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(256, K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_M
       } else if (g.front || (kFast ? true : A.double_side != 0)) {  // .cu:611-640
         const float ssum = ag[pn], smax = ag[SS + pn];
         const float zn = kFast ? (far_ - zp) * inv_range : (far_ - zp) / (far_ - near_);
-        const float wgt = kFast ? fr.frag * __expf((zn - smax) * A.inv_gamma) * fast_rcp(ssum)
+        const float wgt = kFast ? fr.frag * fast_exp((zn - smax) * A.inv_gamma) * fast_rcp(ssum)
                                 : fr.frag * expf((zn - smax) / A.gamma) / ssum;
         float Crgb = 0.f;
         int texel = 0;

@@ -24,6 +24,16 @@
 
 namespace lasr {
 
+#ifndef LASR_NOISE_C1
+#define LASR_NOISE_C1 8.f
+#endif
+#ifndef LASR_NOISE_C2
+#define LASR_NOISE_C2 8.f
+#endif
+#ifndef LASR_NOISE_K
+#define LASR_NOISE_K 4.f
+#endif
+
 constexpr int kMaxSets = 3;    // colour sets interpolated in one geometry pass (indexed path)
 // floats per face record: 32 of geometry, then 9 per colour set (+ z for the reference-faithful
 // generic path, which is single-set), rounded to float4s: 44 / 52 / 60 for 1 / 2 / 3 sets
@@ -105,7 +115,32 @@ __device__ __forceinline__ float cross2(float a, float b, float c, float d) {
 }
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
-__device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.f, x); }
+// MUFU.RCP / MUFU.EX2 without the denormal-range scaling nvcc wraps around __fdividef / __expf when it
+// compiles without -ftz (FSETP + FMUL 2^24 + FSEL ... : five instructions for one reciprocal).  Every
+// operand on the kFast path is far from the denormal range (1 + e^x, sums of weights >= 1e-5, softmax sums
+// >= e^{eps/gamma}), and an underflowing e^x flushing to 0 instead of 1e-40 is below anything the images
+// or gradients resolve.  Non-volatile asm: the compiler may schedule, hoist and CSE it.
+#ifndef LASR_FTZ_MUFU
+#define LASR_FTZ_MUFU 1
+#endif
+__device__ __forceinline__ float fast_rcp(float x) {
+#if LASR_FTZ_MUFU && defined(__CUDA_ARCH__)
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  return __fdividef(1.f, x);
+#endif
+}
+__device__ __forceinline__ float fast_exp(float x) {
+#if LASR_FTZ_MUFU && defined(__CUDA_ARCH__)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+#else
+  return __expf(x);
+#endif
+}
 
 // Rule (2) applies to LASR's training configuration (kFast: euclidean / softmax / prod / vertex
 // colours), which has no hard decision downstream of the distance stage.  The other operator
@@ -115,7 +150,7 @@ __device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.f, x); 
 template <bool kFast> __device__ __forceinline__ float div_(float a, float b) {
   return kFast ? a * fast_rcp(b) : __fdiv_rn(a, b);
 }
-template <bool kFast> __device__ __forceinline__ float exp_(float x) { return kFast ? __expf(x) : expf(x); }
+template <bool kFast> __device__ __forceinline__ float exp_(float x) { return kFast ? fast_exp(x) : expf(x); }
 
 // Correctly rounded num/den from a correctly rounded reciprocal rd = RN(1/den): one Newton step on
 // the quotient (Markstein).  Three FP32 instructions instead of the ~10-instruction IEEE division
@@ -145,6 +180,7 @@ struct FaceGeom {
   float rden[3];      // 1 / (a[e][e] - a[e][(e+1)%3])  (= 1 / squared edge length)
   float lox, hix, loy, hiy;  // bounding box dilated by sqrt(threshold)
   float det;          // clamped determinant the rows of inv were divided by
+  float kappa;        // edge-prediction trust threshold (see euclid_distance): (s_mid - s_lo)^2 > kappa * s_mid
   int obt;            // index of the (first) obtuse corner, -1 if none
   bool front;
 };
@@ -186,6 +222,21 @@ __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float s
     if (d < 0.f) g.obt = k;  // descending k so the smallest obtuse k wins, as `break` does
   }
   g.front = (y2 - y0) * (x1 - x0) < (y1 - y0) * (x2 - x0);  // :41-44
+  {
+    // Rounding-noise amplitude (in NDC) of the distances the reference's float pipeline computes for
+    // this face: barycentric noise 2^-24 * |inv row| carried onto the vertices, plus the along-edge
+    // wobble of the foot point, ~2^-24 * |sym| / |shortest edge|.  The edge *prediction* for inside
+    // pixels is trusted only when the two nearest edges are separated by kNoiseK such amplitudes:
+    //   d_mid - d_lo > K eta   <=   (s_mid - s_lo)^2 * det^2 > 4 K^2 eta^2 * s_mid      (d_e^2 = s_e det^2)
+    float m = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) m = fmaxf(m, fabsf(g.inv[3 * k]) + fabsf(g.inv[3 * k + 1]) + fabsf(g.inv[3 * k + 2]));
+    const float xm = fmaxf(1.f, fmaxf(max3(fabsf(x0), fabsf(x1), fabsf(x2)), max3(fabsf(y0), fabsf(y1), fabsf(y2))));
+    const float emin2 = min3(__fsub_rn(g.a[0][0], g.a[0][1]), __fsub_rn(g.a[1][1], g.a[1][2]), __fsub_rn(g.a[2][2], g.a[2][0]));
+    const float eta = 5.96e-8f * (LASR_NOISE_C1 * m * xm + LASR_NOISE_C2 * xm * xm * rsqrtf(fmaxf(emin2, 1e-30f)));
+    const float ke = 2.f * LASR_NOISE_K * eta / det;
+    g.kappa = ke * ke;   // inf / NaN for degenerate faces: the prediction is then never trusted
+  }
   g.hix = __fadd_rn(max3(x0, x1, x2), sthr);
   g.lox = __fsub_rn(min3(x0, x1, x2), sthr);
   g.hiy = __fadd_rn(max3(y0, y1, y2), sthr);
@@ -193,7 +244,7 @@ __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float s
 }
 
 // record layout (float index):
-//  0..8 inv | 9..11 x | 12..14 y | 15 flags | 16..18 iz | 19..21 rden | 22..30 a[e][j] | 31 pad
+//  0..8 inv | 9..11 x | 12..14 y | 15 flags | 16..18 iz | 19..21 rden | 22..30 a[e][j] | 31 kappa
 //  32..40 vertex-colour texture | 41..43 z
 template <int K>
 __device__ __forceinline__ void store_record(float* __restrict__ r, const FaceGeom& g, const float* tex9) {
@@ -209,6 +260,7 @@ __device__ __forceinline__ void store_record(float* __restrict__ r, const FaceGe
     if (K == 1) v[41 + k] = g.z[k];
   }
   v[15] = __int_as_float((g.obt + 1) | (g.front ? 4 : 0));
+  v[31] = g.kappa;
 #pragma unroll
   for (int e = 0; e < 3; ++e)
 #pragma unroll
@@ -240,6 +292,7 @@ __device__ __forceinline__ void load_record(const float* __restrict__ r, FaceGeo
     g.x[k] = v[9 + k]; g.y[k] = v[12 + k]; g.iz[k] = v[16 + k]; g.rden[k] = v[19 + k];
     g.z[k] = K == 1 ? v[41 + k] : 0.f;
   }
+  g.kappa = v[31];
   const int fl = __float_as_int(v[15]);
   g.obt = (fl & 3) - 1;
   g.front = (fl & 4) != 0;
@@ -276,19 +329,48 @@ __device__ __forceinline__ bool pixel_inside(const float* w) {  // .cu:47-50
 }
 
 // .cu:61-151
+//
+// The reference evaluates all three edges for a pixel strictly inside the face and keeps the
+// nearest (first minimum), and one edge -- chosen from the signs of w -- for a pixel outside.  A
+// warp that holds both kinds of pixel would execute both code paths, the three-edge one with two or
+// three live lanes.  Here (kFast, LASR_FAST_INSIDE) an inside pixel *predicts* the winning edge
+// from  dist(p, line e)^2 = w_opp(e)^2 * det^2 / |edge e|^2  (det^2 is common to the three, so
+// w_opp^2 * rden[e] ranks them) and then runs the same single-edge evaluation as an outside pixel,
+// with the reference's own rounding; when the two best candidates are within 1e-3 of each other
+// (or anything is NaN) the lane falls back to the three-edge loop, so the edge -- and with it every
+// bit of (t, dx, dy, dis) -- is the one the reference's loop selects.
+#ifndef LASR_FAST_INSIDE
+#define LASR_FAST_INSIDE 1
+#endif
 template <bool kFast>
 __device__ __forceinline__ void euclid_distance(const FaceGeom& g, float xp, float yp, Fragment& fr) {
   const float w0 = fr.w[0], w1 = fr.w[1], w2 = fr.w[2];
-  if (w0 > 0.f && w1 > 0.f && w2 > 0.f && w0 < 1.f && w1 < 1.f && w2 < 1.f) {
+  const bool inside = w0 > 0.f && w1 > 0.f && w2 > 0.f && w0 < 1.f && w1 < 1.f && w2 < 1.f;
+  int e = 0;
+  bool all_edges = inside;
+  if (kFast && LASR_FAST_INSIDE) {
+    const float s0 = w2 * w2 * g.rden[0], s1 = w0 * w0 * g.rden[1], s2 = w1 * w1 * g.rden[2];
+    const float lo = fminf(fminf(s0, s1), s2);
+    const float mid = fmaxf(fminf(s0, s1), fminf(fmaxf(s0, s1), s2));   // second smallest
+    e = s0 == lo ? 0 : (s1 == lo ? 1 : 2);
+    const float gap = mid - lo;
+    // near tie relative to the face's rounding noise, or NaN/inf from a degenerate edge -> all edges
+    all_edges = inside && !(gap > 1e-3f * mid && gap * gap > g.kappa * mid);
+  }
+#ifdef LASR_HOST_STATS   // tests/host_harness only
+  if (inside) ++lasr_host_inside_pairs;
+  if (all_edges) ++lasr_host_all_edges_pairs;
+#endif
+  if (all_edges) {
     float best = 100000000.f, bx = 0.f, by = 0.f;
 #pragma unroll
-    for (int e = 0; e < 3; ++e) {
-      const int b = (e + 1) % 3, c = (e + 2) % 3;
-      const float num = __fsub_rn(dot3(w0, g.a[e][0], w1, g.a[e][1], w2, g.a[e][2]), g.a[e][b]);
-      const float den = __fsub_rn(g.a[e][e], g.a[e][b]);
-      const float q = kFast ? div_by_rcp(num, den, g.rden[e]) : __fdiv_rn(num, den);
+    for (int e3 = 0; e3 < 3; ++e3) {
+      const int b = (e3 + 1) % 3, c = (e3 + 2) % 3;
+      const float num = __fsub_rn(dot3(w0, g.a[e3][0], w1, g.a[e3][1], w2, g.a[e3][2]), g.a[e3][b]);
+      const float den = __fsub_rn(g.a[e3][e3], g.a[e3][b]);
+      const float q = kFast ? div_by_rcp(num, den, g.rden[e3]) : __fdiv_rn(num, den);
       float t[3];
-      t[e] = q; t[b] = 1.f - q; t[c] = 0.f;
+      t[e3] = q; t[b] = 1.f - q; t[c] = 0.f;
       t[0] -= w0; t[1] -= w1; t[2] -= w2;
       const float dx = dot3(t[0], g.x[0], t[1], g.x[1], t[2], g.x[2]);
       const float dy = dot3(t[0], g.y[0], t[1], g.y[1], t[2], g.y[2]);
@@ -296,8 +378,9 @@ __device__ __forceinline__ void euclid_distance(const FaceGeom& g, float xp, flo
       if (dd < best) { best = dd; bx = dx; by = dy; fr.t[0] = t[0]; fr.t[1] = t[1]; fr.t[2] = t[2]; }
     }
     fr.dx = bx; fr.dy = by; fr.sign = 1.f;
-  } else {
-    int e = 0;
+    return;
+  }
+  if (!inside) {
     if (w1 <= 0.f && w2 <= 0.f) {
       e = 0;
       if (g.obt == 0 && dot2(xp - g.x[0], g.x[2] - g.x[0], yp - g.y[0], g.y[2] - g.y[0]) > 0.f) e = 2;
@@ -314,27 +397,29 @@ __device__ __forceinline__ void euclid_distance(const FaceGeom& g, float xp, flo
     } else {
       e = 0;
     }
-    // pick the row of `a` for edge e without dynamic register indexing
-    const float a0 = e == 0 ? g.a[0][0] : (e == 1 ? g.a[1][0] : g.a[2][0]);
-    const float a1 = e == 0 ? g.a[0][1] : (e == 1 ? g.a[1][1] : g.a[2][1]);
-    const float a2 = e == 0 ? g.a[0][2] : (e == 1 ? g.a[1][2] : g.a[2][2]);
-    const float ae = e == 0 ? a0 : (e == 1 ? a1 : a2);
-    const float ab = e == 0 ? a1 : (e == 1 ? a2 : a0);
-    const float rd = e == 0 ? g.rden[0] : (e == 1 ? g.rden[1] : g.rden[2]);
-    const float num = __fsub_rn(dot3(w0, a0, w1, a1, w2, a2), ab);
-    const float den = __fsub_rn(ae, ab);
-    const float q = kFast ? div_by_rcp(num, den, rd) : __fdiv_rn(num, den);
-    const float qe = fminf(fmaxf(q, 0.f), 1.f);
-    const float qb = fminf(fmaxf(1.f - q, 0.f), 1.f);
-    // t[e] = qe, t[(e+1)%3] = qb, t[(e+2)%3] = 0, then minus w
-    const float t0 = (e == 0 ? qe : (e == 2 ? qb : 0.f)) - w0;
-    const float t1 = (e == 1 ? qe : (e == 0 ? qb : 0.f)) - w1;
-    const float t2 = (e == 2 ? qe : (e == 1 ? qb : 0.f)) - w2;
-    fr.t[0] = t0; fr.t[1] = t1; fr.t[2] = t2;
-    fr.dx = dot3(t0, g.x[0], t1, g.x[1], t2, g.x[2]);
-    fr.dy = dot3(t0, g.y[0], t1, g.y[1], t2, g.y[2]);
-    fr.sign = -1.f;
   }
+  // pick the row of `a` for edge e without dynamic register indexing
+  const float a0 = e == 0 ? g.a[0][0] : (e == 1 ? g.a[1][0] : g.a[2][0]);
+  const float a1 = e == 0 ? g.a[0][1] : (e == 1 ? g.a[1][1] : g.a[2][1]);
+  const float a2 = e == 0 ? g.a[0][2] : (e == 1 ? g.a[1][2] : g.a[2][2]);
+  const float ae = e == 0 ? a0 : (e == 1 ? a1 : a2);
+  const float ab = e == 0 ? a1 : (e == 1 ? a2 : a0);
+  const float rd = e == 0 ? g.rden[0] : (e == 1 ? g.rden[1] : g.rden[2]);
+  const float num = __fsub_rn(dot3(w0, a0, w1, a1, w2, a2), ab);
+  const float den = __fsub_rn(ae, ab);
+  const float q = kFast ? div_by_rcp(num, den, rd) : __fdiv_rn(num, den);
+  // inside: the foot of the perpendicular on the edge's line, unclamped (.cu:81-87); outside: clamped
+  // to the segment (.cu:136-139)
+  const float qe = inside ? q : fminf(fmaxf(q, 0.f), 1.f);
+  const float qb = inside ? 1.f - q : fminf(fmaxf(1.f - q, 0.f), 1.f);
+  // t[e] = qe, t[(e+1)%3] = qb, t[(e+2)%3] = 0, then minus w
+  const float t0 = (e == 0 ? qe : (e == 2 ? qb : 0.f)) - w0;
+  const float t1 = (e == 1 ? qe : (e == 0 ? qb : 0.f)) - w1;
+  const float t2 = (e == 2 ? qe : (e == 1 ? qb : 0.f)) - w2;
+  fr.t[0] = t0; fr.t[1] = t1; fr.t[2] = t2;
+  fr.dx = dot3(t0, g.x[0], t1, g.x[1], t2, g.x[2]);
+  fr.dy = dot3(t0, g.y[0], t1, g.y[1], t2, g.y[2]);
+  fr.sign = inside ? 1.f : -1.f;
 }
 
 // Returns false when the pair is rejected by the distance stage (.cu:389-404 / :556-572).
@@ -356,13 +441,13 @@ __device__ __forceinline__ bool soft_fragment(const RasterArgs& A, const FaceGeo
     d = d > 0.f ? d * d : -(d * d);
     fr.dis = d;
     if (-d >= thr) return false;
-    fr.frag = kFast ? fast_rcp(1.f + __expf(-d * A.inv_sigma)) : 1.f / (1.f + expf(-d / A.sigma));
+    fr.frag = kFast ? fast_rcp(1.f + fast_exp(-d * A.inv_sigma)) : 1.f / (1.f + expf(-d / A.sigma));
     return true;
   } else {
     euclid_distance<kFast>(g, xp, yp, fr);
     fr.dis = dot2(fr.dx, fr.dx, fr.dy, fr.dy);
     if (fr.sign < 0.f && fr.dis >= thr) return false;
-    fr.frag = kFast ? fast_rcp(1.f + __expf(-fr.sign * fr.dis * A.inv_sigma))
+    fr.frag = kFast ? fast_rcp(1.f + fast_exp(-fr.sign * fr.dis * A.inv_sigma))
                     : 1.f / (1.f + expf(-fr.sign * fr.dis / A.sigma));
     return true;
   }

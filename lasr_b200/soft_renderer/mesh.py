@@ -132,12 +132,25 @@ class Mesh(object):
 
     @classmethod
     def from_obj(cls, filename_obj, normalization=False, load_texture=False, texture_res=1, texture_type="surface"):
-        srf.load_obj(filename_obj)  # raises NotImplementedError: out of the hot path
+        """Create a Mesh from a Wavefront .obj file (mesh.py:148-164 of the reference)."""
+        if load_texture:
+            vertices, faces, textures = srf.load_obj(filename_obj, normalization=normalization,
+                                                     texture_res=texture_res, load_texture=True,
+                                                     texture_type=texture_type)
+        else:
+            vertices, faces = srf.load_obj(filename_obj, normalization=normalization, texture_res=texture_res,
+                                           load_texture=False)
+            textures = None
+        return cls(vertices, faces, textures, texture_res, texture_type)
 
     def save_obj(self, filename_obj, save_texture=False, texture_res_out=16):
         if self.batch_size != 1:
             raise ValueError("Could not save when batch size >= 1")
-        srf.save_obj(filename_obj)
+        if save_texture:
+            srf.save_obj(filename_obj, self.vertices[0], self.faces[0], textures=self.textures[0],
+                         texture_res=texture_res_out, texture_type=self.texture_type)
+        else:
+            srf.save_obj(filename_obj, self.vertices[0], self.faces[0], textures=None)
 
     def voxelize(self, voxel_size=32):
         srf.voxelization(None)

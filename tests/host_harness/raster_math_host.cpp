@@ -1,0 +1,70 @@
+// TEST INFRASTRUCTURE.  Compiles lasr_b200/csrc/raster_common.cuh for the HOST (g++) so that the
+// per-(pixel, face) arithmetic of the CUDA kernels -- record setup, barycentrics, the euclidean
+// distance stage with its edge selection -- can be exercised on a machine without a GPU and compared
+// with the C++ oracle bit for bit.  The device intrinsics are mapped to their IEEE host equivalents
+// (explicit fma / mul / add, so -ffp-contract=off keeps the association the kernels spell out).
+// Build: see tests/test_kernel_math_host.py.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include <cuda_runtime.h>   // vector types only; nothing is launched
+
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fdividef(float a, float b) { return a / b; }
+#define __expf(x) expf(x)
+static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
+#define LASR_HOST_STATS 1
+static long long lasr_host_inside_pairs = 0, lasr_host_all_edges_pairs = 0;
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline float __shfl_xor_sync(unsigned, float v, int) { return v; }
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+namespace lasr {
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+}
+
+#include "raster_common.cuh"
+
+using namespace lasr;
+
+// For n (face, pixel) pairs: face_setup -> store_record -> load_record (the kernels' round trip) ->
+// soft_fragment<kFast=true> with LASR's distance mode.  out[n][10] = accepted, w0,w1,w2, t0,t1,t2, dx, dy,
+// dis (accepted == 0: rejected by the distance stage); out_frag[n] = D.
+extern "C" void lasr_host_soft_fragment(const float* faces9, const float* px, const float* py, int n, float sigma,
+                                        float dist_eps, float* out, float* out_frag) {
+  RasterArgs A{};
+  A.dist = 2; A.sigma = sigma; A.dist_eps = dist_eps; A.inv_sigma = (float)(1.0 / (double)sigma);
+  const float thr = dist_eps * sigma;
+  const float sthr = sqrtf(thr);
+  for (int i = 0; i < n; ++i) {
+    FaceGeom g0, g;
+    face_setup(faces9 + 9 * i, sthr, g0);
+    alignas(16) float rec[rec_words(1)];
+    float tex9[9] = {0};
+    store_record<1>(rec, g0, tex9);
+    load_record<1>(rec, g, tex9);
+    Fragment fr;
+    const bool ok = soft_fragment<true>(A, g, px[i], py[i], thr, fr);
+    float* o = out + 10 * i;
+    o[0] = ok ? 1.f : 0.f;
+    o[1] = fr.w[0]; o[2] = fr.w[1]; o[3] = fr.w[2];
+    o[4] = fr.t[0]; o[5] = fr.t[1]; o[6] = fr.t[2];
+    o[7] = fr.dx; o[8] = fr.dy; o[9] = fr.dis;
+    out_frag[i] = ok ? fr.frag : 0.f;
+  }
+}
+
+extern "C" void lasr_host_stats(long long* inside, long long* all_edges, int reset) {
+  *inside = lasr_host_inside_pairs; *all_edges = lasr_host_all_edges_pairs;
+  if (reset) { lasr_host_inside_pairs = 0; lasr_host_all_edges_pairs = 0; }
+}
+
+extern "C" int lasr_host_fast_inside(void) { return LASR_FAST_INSIDE; }

@@ -198,7 +198,7 @@ def test_install_as_soft_renderer_exposes_what_lasr_uses():
         assert r.rasterizer.sigma_val == 1e-4 and r.rasterizer.gamma_val == 1e-3 and r.lighting.light_mode == "vertex"
         assert hasattr(sr, "Mesh") and hasattr(sr.functional, "soft_rasterize") and hasattr(sr.functional, "face_vertices")
         with pytest.raises(NotImplementedError):
-            sr.functional.load_obj("x.obj")
+            sr.functional.voxelization(None)
     finally:
         for k, v in saved.items():
             if v is None:

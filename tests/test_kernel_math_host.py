@@ -1,0 +1,105 @@
+"""Host build of the CUDA kernels' per-(pixel, face) arithmetic (tests/host_harness): the predicted-edge shortcut
+for pixels inside a face (raster_common.cuh: euclid_distance, LASR_FAST_INSIDE) must select the very edge the
+reference's three-edge loop selects -- every bit of (w, t, dx, dy, dis, D) equal -- on real meshes and on
+pathological triangle soups, with the fallback to the full loop staying rare on real meshes.  No GPU needed."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases  # noqa: E402
+
+DIST_EPS = float(np.float32(np.log(1 / 1e-4 - 1)))
+
+
+@pytest.fixture(scope="module")
+def libs(tmp_path_factory):
+    d = tmp_path_factory.mktemp("host_harness")
+    out = {}
+    for v in (0, 1):
+        so = str(d / f"raster_math_host_{v}.so")
+        subprocess.check_call([os.path.join(ROOT, "tests", "host_harness", "build.sh"), so, f"-DLASR_FAST_INSIDE={v}"])
+        out[v] = ctypes.CDLL(so)
+        assert out[v].lasr_host_fast_inside() == v
+    return out
+
+
+def _run(L, f9, px, py, sigma):
+    n = len(px)
+    out = np.zeros((n, 10), np.float32); fr = np.zeros(n, np.float32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    L.lasr_host_soft_fragment(P(f9), P(px), P(py), ctypes.c_int(n), ctypes.c_float(sigma), ctypes.c_float(DIST_EPS), P(out), P(fr))
+    return out, fr
+
+
+def _pairs(fv, S, sigma, rng, cap=400000):
+    """All grid pixels inside every face's dilated bounding box (sub-sampled for huge faces)."""
+    r = np.sqrt(DIST_EPS * sigma)
+    coords = ((2 * np.arange(S) + 1 - S) / S).astype(np.float32)
+    F, X, Y = [], [], []
+    for f in fv:
+        xs, ys = f[[0, 3, 6]], f[[1, 4, 7]]
+        cx = coords[(coords >= xs.min() - r) & (coords <= xs.max() + r)]
+        cy = coords[(coords >= ys.min() - r) & (coords <= ys.max() + r)]
+        if len(cx) == 0 or len(cy) == 0:
+            continue
+        if len(cx) * len(cy) > 2500:
+            cx, cy = rng.choice(cx, 50), rng.choice(cy, 50)
+        gx, gy = np.meshgrid(cx, cy)
+        F.append(np.repeat(f[None], gx.size, 0)); X.append(gx.ravel()); Y.append(gy.ravel())
+    F = np.concatenate(F).astype(np.float32); X = np.concatenate(X).astype(np.float32); Y = np.concatenate(Y).astype(np.float32)
+    if len(X) > cap:
+        s = rng.choice(len(X), cap, replace=False)
+        F, X, Y = F[s], X[s], Y[s]
+    return np.ascontiguousarray(F), np.ascontiguousarray(X), np.ascontiguousarray(Y)
+
+
+def _soup(rng, n, kind):
+    p = rng.uniform(-0.8, 0.8, (n, 3, 2)).astype(np.float32)
+    if kind == "sliver":
+        p[:, 2] = p[:, 0] + (p[:, 1] - p[:, 0]) * rng.uniform(0, 1, (n, 1)).astype(np.float32) + rng.normal(0, 1e-5, (n, 2)).astype(np.float32)
+    if kind == "needle":
+        p[:, 1] = p[:, 0] + rng.normal(0, 1e-4, (n, 2)).astype(np.float32)
+    if kind == "tiny":
+        p[:, 1:] = p[:, :1] + rng.normal(0, 2e-3, (n, 2, 2)).astype(np.float32)
+    if kind == "degenerate":
+        p[:, 2] = p[:, 1]
+    if kind == "iso":      # grid-aligned isosceles triangles: exact ties at pixel centres
+        S = 64
+        c = ((2 * rng.randint(8, 56, (n, 2)) + 1 - S) / S).astype(np.float32)
+        h = (rng.randint(1, 8, (n,)) * 2 / S).astype(np.float32)
+        p[:, 0] = c + np.stack([-h, -h], 1); p[:, 1] = c + np.stack([h, -h], 1); p[:, 2] = c + np.stack([0 * h, h], 1)
+    z = rng.uniform(5, 15, (n, 3, 1)).astype(np.float32)
+    return np.concatenate([p, z], 2).reshape(n, 9)
+
+
+def _check(libs, F, X, Y, sigma, tag):
+    a, fa = _run(libs[0], F, X, Y, sigma)
+    libs[1].lasr_host_stats(ctypes.byref(ctypes.c_longlong()), ctypes.byref(ctypes.c_longlong()), 1)
+    b, fb = _run(libs[1], F, X, Y, sigma)
+    inside, slow = ctypes.c_longlong(), ctypes.c_longlong()
+    libs[1].lasr_host_stats(ctypes.byref(inside), ctypes.byref(slow), 1)
+    same = (a.view(np.uint32) == b.view(np.uint32)).all(1) & (fa.view(np.uint32) == fb.view(np.uint32))
+    assert same.all(), f"{tag}: {int((~same).sum())} of {len(X)} pairs differ"
+    return inside.value, slow.value
+
+
+@pytest.mark.parametrize("mesh,S", [("spot", 256), ("ico2", 64), ("bumpy2", 96)])
+@pytest.mark.parametrize("sigma", [1e-4, 1e-5])
+def test_predicted_edge_is_bit_identical_on_meshes(libs, mesh, S, sigma):
+    c = cases.lasr_case(mesh, 2, S, sigma=sigma)
+    F, X, Y = _pairs(c["face_vertices"].reshape(-1, 9), S, sigma, np.random.RandomState(0))
+    inside, slow = _check(libs, F, X, Y, sigma, mesh)
+    assert inside > 1000 and slow < 0.15 * inside      # the shortcut is taken for the vast majority of inside pixels
+
+
+@pytest.mark.parametrize("kind", ["random", "sliver", "needle", "tiny", "degenerate", "iso"])
+def test_predicted_edge_is_bit_identical_on_pathological_soups(libs, kind):
+    rng = np.random.RandomState(3)
+    F, X, Y = _pairs(_soup(rng, 1500, kind), 64, 1e-4, rng)
+    _check(libs, F, X, Y, 1e-4, kind)
