@@ -65,6 +65,18 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #ifndef LASR_BWD_THREADS
 #define LASR_BWD_THREADS 128
 #endif
+#ifndef LASR_FTZ_MUFU_FWD           // bare FTZ MUFU reciprocal / ex2 in the forward (faster) ...
+#define LASR_FTZ_MUFU_FWD 1
+#endif
+#ifndef LASR_FTZ_MUFU_BWD           // ... but not in the backward (measured slower)
+#define LASR_FTZ_MUFU_BWD 0
+#endif
+#ifndef LASR_BWD_PREFETCH           // prefetch a pixel's planes to L1 before the fragment math
+#define LASR_BWD_PREFETCH 0
+#endif
+#ifndef LASR_BWD_INDEX32            // 32-bit per-frame plane offsets in the backward's pixel loop
+#define LASR_BWD_INDEX32 1
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // setup: one thread per face -> packed pixel window, dilated border box, full face record;
@@ -129,13 +141,14 @@ struct FwdConsts {
 template <bool kFast, int K>
 __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConsts& C, const float* __restrict__ rec,
                                              float4 bd, int face, int n, float xp, float yp, PixelState<K>& st) {
+  constexpr int kMode = kFast ? (LASR_FTZ_MUFU_FWD ? 2 : 1) : 0;   // arithmetic mode, see raster_common.cuh
   // exact border predicate of the reference (.cu:32-38,375)
   if (xp > bd.y || xp < bd.x || yp > bd.w || yp < bd.z) return;
   FaceGeom g;
   float tex9[9 * K];
   load_record<K>(rec, g, tex9);
   Fragment fr;
-  if (!soft_fragment<kFast>(A, g, xp, yp, C.thr, fr)) return;
+  if (!soft_fragment<kMode>(A, g, xp, yp, C.thr, fr)) return;
   const int alpha_f = kFast ? 2 : A.alpha;
   const int rgb_f = kFast ? 1 : A.rgb;
   const int sample = kFast ? 1 : A.sample;
@@ -145,7 +158,7 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConst
   else st.alpha *= 1.f - fr.frag;
   // clipped-barycentric depth (.cu:421-424)
   float wc[3];
-  const float zp = clip_and_depth<kFast>(g, fr.w, wc);
+  const float zp = clip_and_depth<kMode>(g, fr.w, wc);
   if (zp < C.near_ || zp > C.far_) return;
   const bool visible = g.front || (kFast ? true : A.double_side != 0);
   auto sample_tex = [&](int k) -> float {   // k = 3*set + channel
@@ -168,10 +181,10 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConst
     const float zn = kFast ? (C.far_ - zp) * C.inv_range : (C.far_ - zp) / (C.far_ - C.near_);
     float rescale = 1.f;
     if (zn > st.smax) {
-      rescale = kFast ? fast_exp((st.smax - zn) * A.inv_gamma) : expf((st.smax - zn) / A.gamma);
+      rescale = kFast ? fast_exp<kMode>((st.smax - zn) * A.inv_gamma) : expf((st.smax - zn) / A.gamma);
       st.smax = zn;
     }
-    const float ez = (kFast ? fast_exp((zn - st.smax) * A.inv_gamma) : expf((zn - st.smax) / A.gamma)) * fr.frag;
+    const float ez = (kFast ? fast_exp<kMode>((zn - st.smax) * A.inv_gamma) : expf((zn - st.smax) / A.gamma)) * fr.frag;
     st.ssum = rescale * st.ssum + ez;
 #pragma unroll
     for (int k = 0; k < 3 * K; ++k) st.col[k] = rescale * st.col[k] + ez * sample_tex(k);
@@ -180,6 +193,7 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConst
 
 template <bool kFast, int K>
 __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LASR_FWD_MIN_BLOCKS_MULTI) raster_forward_kernel(RasterArgs A, int chunk) {
+  constexpr int kMode = kFast ? (LASR_FTZ_MUFU_FWD ? 2 : 1) : 0;
   constexpr int kRecWords = rec_words(K);
   constexpr int P = 3 * K + 1;      // image planes per frame: K colour sets, then alpha
   extern __shared__ int s_list[];   // [chunk] face indices, 8 per-warp segments of chunk/8
@@ -314,7 +328,7 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
     agg[SS] = (float)st.face_min;
   } else {
 #pragma unroll
-    for (int k = 0; k < 3 * K; ++k) out[k * SS] = div_<kFast>(st.col[k], st.ssum);
+    for (int k = 0; k < 3 * K; ++k) out[k * SS] = div_<kMode>(st.col[k], st.ssum);
     agg[0] = st.ssum;
     agg[SS] = st.smax;
   }
@@ -331,8 +345,12 @@ constexpr int kBigListCap = 16384;     // deferred faces the workspace can list 
 // KF: colour sets [0,KF) are detached -- their image-gradient planes are not read and they get no
 // colour gradient (LASR's flow render uses the frame's own positions only under .detach(),
 // nnutils/mesh_net.py:102); sets [KF,K) are live.
+template <bool k32> struct PlaneIndex { typedef long long type; };
+template <> struct PlaneIndex<true> { typedef unsigned type; };
+
 template <bool kFast, bool kBig, int K, int KF>
 __global__ void __launch_bounds__(256, K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_MIN_BLOCKS_MULTI) raster_backward_kernel(RasterArgs A) {
+  constexpr int kMode = kFast ? (LASR_FTZ_MUFU_BWD ? 2 : 1) : 0;   // arithmetic mode, see raster_common.cuh
   constexpr int kRecWords = rec_words(K);
   constexpr int P = 3 * K + 1;          // image planes per frame
   constexpr int KL = K - KF;            // live colour sets
@@ -402,6 +420,15 @@ __global__ void __launch_bounds__(256, K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_M
     const float* sc = A.soft_colors + (long long)n * P * SS;
     const float* ag = A.aggrs_info + (long long)n * 2 * SS;
     const float* gs = A.grad_soft_colors + (long long)n * P * SS;
+    // Single colour set: per-frame plane offsets as 32-bit values (fill_args bounds P*S*S) on opaque 64-bit
+    // bases -> one IMAD.WIDE per load instead of an IADD3/IADD3.X/LEA/LEA.HI.X chain (the ten plane loads of
+    // a pixel were ~40 integer instructions per sweep; backward 1.208 -> 1.168 ms on config A).  With several
+    // colour sets the 64-bit form schedules better (measured: 2.06 vs 2.12 ms at K = 3), so it is kept there.
+    constexpr bool kIdx32 = LASR_BWD_INDEX32 != 0 && K == 1;
+    typedef typename PlaneIndex<kIdx32>::type index_t;
+    const index_t SSx = (index_t)S * (index_t)S;
+    if (kIdx32) asm volatile("" : "+l"(sc), "+l"(ag), "+l"(gs));
+#define PLANE(k) ((index_t)(k) * SSx + pn)
     for (int idx = gtid; idx < total; idx += gsize) {
       int r = (int)(((float)idx + 0.5f) * inv_wdt);  // idx / wdt without an integer divide
       int col = idx - r * wdt;
@@ -411,44 +438,55 @@ __global__ void __launch_bounds__(256, K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_M
       const float xp = A.coords[xi];
       const float yp = A.coords[yi];
       if (xp > g.hix || xp < g.lox || yp > g.hiy || yp < g.loy) continue;
-      const long long pn = (long long)(S - 1 - yi) * S + xi;
+      const index_t pn = (index_t)(S - 1 - yi) * (index_t)S + (index_t)xi;
+#if LASR_BWD_PREFETCH
+      // the pixel's image / gradient planes are needed ~150 instructions from now: start them towards L1
+      if (kFast) {
+#pragma unroll
+        for (int k = 3 * KF; k < P; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(gs + PLANE(k)));
+#pragma unroll
+        for (int k = 3 * KF; k < P; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc + PLANE(k)));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(ag + PLANE(0)));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(ag + PLANE(1)));
+      }
+#endif
       Fragment fr;
-      if (!soft_fragment<kFast>(A, g, xp, yp, thr, fr)) continue;
+      if (!soft_fragment<kMode>(A, g, xp, yp, thr, fr)) continue;
       // alpha term (.cu:582-593); for 'hard' alpha the reference still adds the raw upstream
       // gradient (nothing resets C_grad_xy_alpha), reproduced here
-      float Cxy = gs[(P - 1) * SS + pn];
+      float Cxy = gs[PLANE(P - 1)];
       if (alpha_f == 1) Cxy /= A.F;
-      else if (alpha_f == 2) Cxy *= div_<kFast>(1.f - sc[(P - 1) * SS + pn], fmaxf(1.f - fr.frag, 1e-6f));
+      else if (alpha_f == 2) Cxy *= div_<kMode>(1.f - sc[PLANE(P - 1)], fmaxf(1.f - fr.frag, 1e-6f));
       float wc[3];
-      const float zp = clip_and_depth<kFast>(g, fr.w, wc);
+      const float zp = clip_and_depth<kMode>(g, fr.w, wc);
       if (zp < near_ || zp > far_) continue;
       float gz[3] = {0.f, 0.f, 0.f};
       if (rgb_f == 0) {  // .cu:602-609
-        if ((float)f == ag[SS + pn]) {   // (hard rgb: generic path only)
+        if ((float)f == ag[PLANE(1)]) {   // (hard rgb: generic path only)
           if (sample == 1) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-              const float gk = gs[k * SS + pn];
+              const float gk = gs[PLANE(k)];
 #pragma unroll
               for (int j = 0; j < 3; ++j) gt[3 * j + k] += wc[j] * gk;
             }
           } else {
             const int texel = surface_texel(wc, A.R);
             if (texel < A.T)
-              for (int k = 0; k < 3; ++k) atomicAdd(&gtex_out[3 * texel + k], gs[k * SS + pn]);
+              for (int k = 0; k < 3; ++k) atomicAdd(&gtex_out[3 * texel + k], gs[PLANE(k)]);
           }
         }
       } else if (g.front || (kFast ? true : A.double_side != 0)) {  // .cu:611-640
-        const float ssum = ag[pn], smax = ag[SS + pn];
+        const float ssum = ag[PLANE(0)], smax = ag[PLANE(1)];
         const float zn = kFast ? (far_ - zp) * inv_range : (far_ - zp) / (far_ - near_);
-        const float wgt = kFast ? fr.frag * fast_exp((zn - smax) * A.inv_gamma) * fast_rcp(ssum)
+        const float wgt = kFast ? fr.frag * fast_exp<kMode>((zn - smax) * A.inv_gamma) * fast_rcp<kMode>(ssum)
                                 : fr.frag * expf((zn - smax) / A.gamma) / ssum;
         float Crgb = 0.f;
         int texel = 0;
         if (sample == 0) texel = surface_texel(wc, A.R);
 #pragma unroll
         for (int k = 3 * KF; k < 3 * K; ++k) {   // k = 3*set + channel, live sets only
-          const float gk = gs[k * SS + pn];
+          const float gk = gs[PLANE(k)];
           float ck;
           if (sample == 1) {
             const float wg_k = wgt * gk;
@@ -462,10 +500,10 @@ __global__ void __launch_bounds__(256, K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_M
             const long long ti = wg * A.T * 3 + (long long)texel * 3 + k;
             ck = ti < (long long)A.N * A.F * A.T * 3 ? A.textures[ti] : 0.f;
           }
-          Crgb += gk * (ck - sc[k * SS + pn]);
+          Crgb += gk * (ck - sc[PLANE(k)]);
         }
         Crgb *= wgt;
-        Cxy += div_<kFast>(Crgb, fr.frag);
+        Cxy += div_<kMode>(Crgb, fr.frag);
         if (kFast) {
           const float Cz = Crgb * cz_scale * zp * zp;
           gz[0] = Cz * wc[0] * g.iz[0] * g.iz[0];
@@ -604,7 +642,7 @@ static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, flo
                      float eps, float sigma, int dist, float dist_eps, float gamma, int rgb, int alpha, int sample,
                      int double_side, void* workspace, size_t workspace_bytes, int K = 1) {
   if (N <= 0 || F <= 0 || S <= 0 || T <= 0) return fail("raster: batch_size, num_faces, image_size, texture_size must be positive");
-  if (S > 32768) return fail("raster: image_size > 32768 unsupported");
+  if (S > 8192) return fail("raster: image_size > 8192 unsupported (per-frame plane offsets are 32-bit)");
   if (dist < 0 || dist > 2 || rgb < 0 || rgb > 1 || alpha < 0 || alpha > 2 || sample < 0 || sample > 1)
     return fail("raster: bad func id");
   if (sample == 1 && T != 3) return fail("raster: 'vertex' textures must be [N,F,3,3]");

@@ -120,26 +120,31 @@ __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(
 // operand on the kFast path is far from the denormal range (1 + e^x, sums of weights >= 1e-5, softmax sums
 // >= e^{eps/gamma}), and an underflowing e^x flushing to 0 instead of 1e-40 is below anything the images
 // or gradients resolve.  Non-volatile asm: the compiler may schedule, hoist and CSE it.
-#ifndef LASR_FTZ_MUFU
-#define LASR_FTZ_MUFU 1
+//
+// The arithmetic mode of the per-pair functions is a template int: 0 = generic (the reference's IEEE
+// divisions and expf), 1 = fast (reciprocals / ex2 through __fdividef / __expf), 2 = fast with the bare
+// FTZ MUFU forms.  Measured on B200 (profiles/RESULTS.md): mode 2 is 4-7 % faster than mode 1 in the forward
+// kernel and 13 % SLOWER in the backward (same instruction savings, worse schedule at 4 warps per
+// scheduler), so each kernel picks its own.
+template <int kMode> __device__ __forceinline__ float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  if (kMode == 2) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+  }
 #endif
-__device__ __forceinline__ float fast_rcp(float x) {
-#if LASR_FTZ_MUFU && defined(__CUDA_ARCH__)
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-#else
   return __fdividef(1.f, x);
-#endif
 }
-__device__ __forceinline__ float fast_exp(float x) {
-#if LASR_FTZ_MUFU && defined(__CUDA_ARCH__)
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
-  return y;
-#else
-  return __expf(x);
+template <int kMode> __device__ __forceinline__ float fast_exp(float x) {
+#if defined(__CUDA_ARCH__)
+  if (kMode == 2) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+  }
 #endif
+  return __expf(x);
 }
 
 // Rule (2) applies to LASR's training configuration (kFast: euclidean / softmax / prod / vertex
@@ -147,10 +152,10 @@ __device__ __forceinline__ float fast_exp(float x) {
 // modes do ('surface' texel selection sits exactly on `frac sum <= 1` along clipped edges, the
 // 'hard' z-test and 'hard' alpha compare rounded values), so the generic instantiation keeps
 // the reference's IEEE divisions and expf.
-template <bool kFast> __device__ __forceinline__ float div_(float a, float b) {
-  return kFast ? a * fast_rcp(b) : __fdiv_rn(a, b);
+template <int kFast> __device__ __forceinline__ float div_(float a, float b) {
+  return kFast ? a * fast_rcp<kFast>(b) : __fdiv_rn(a, b);
 }
-template <bool kFast> __device__ __forceinline__ float exp_(float x) { return kFast ? fast_exp(x) : expf(x); }
+template <int kFast> __device__ __forceinline__ float exp_(float x) { return kFast ? fast_exp<kFast>(x) : expf(x); }
 
 // Correctly rounded num/den from a correctly rounded reciprocal rd = RN(1/den): one Newton step on
 // the quotient (Markstein).  Three FP32 instructions instead of the ~10-instruction IEEE division
@@ -342,13 +347,13 @@ __device__ __forceinline__ bool pixel_inside(const float* w) {  // .cu:47-50
 #ifndef LASR_FAST_INSIDE
 #define LASR_FAST_INSIDE 1
 #endif
-template <bool kFast>
+template <int kFast>
 __device__ __forceinline__ void euclid_distance(const FaceGeom& g, float xp, float yp, Fragment& fr) {
   const float w0 = fr.w[0], w1 = fr.w[1], w2 = fr.w[2];
   const bool inside = w0 > 0.f && w1 > 0.f && w2 > 0.f && w0 < 1.f && w1 < 1.f && w2 < 1.f;
   int e = 0;
   bool all_edges = inside;
-  if (kFast && LASR_FAST_INSIDE) {
+  if (kFast != 0 && LASR_FAST_INSIDE) {
     const float s0 = w2 * w2 * g.rden[0], s1 = w0 * w0 * g.rden[1], s2 = w1 * w1 * g.rden[2];
     const float lo = fminf(fminf(s0, s1), s2);
     const float mid = fmaxf(fminf(s0, s1), fminf(fmaxf(s0, s1), s2));   // second smallest
@@ -423,7 +428,7 @@ __device__ __forceinline__ void euclid_distance(const FaceGeom& g, float xp, flo
 }
 
 // Returns false when the pair is rejected by the distance stage (.cu:389-404 / :556-572).
-template <bool kFast>
+template <int kFast>
 __device__ __forceinline__ bool soft_fragment(const RasterArgs& A, const FaceGeom& g, float xp, float yp,
                                               float thr, Fragment& fr) {
   fr.w[0] = __fadd_rn(__fmaf_rn(xp, g.inv[0], __fmul_rn(yp, g.inv[1])), g.inv[2]);  // :24-29
@@ -441,13 +446,13 @@ __device__ __forceinline__ bool soft_fragment(const RasterArgs& A, const FaceGeo
     d = d > 0.f ? d * d : -(d * d);
     fr.dis = d;
     if (-d >= thr) return false;
-    fr.frag = kFast ? fast_rcp(1.f + fast_exp(-d * A.inv_sigma)) : 1.f / (1.f + expf(-d / A.sigma));
+    fr.frag = kFast ? fast_rcp<kFast>(1.f + fast_exp<kFast>(-d * A.inv_sigma)) : 1.f / (1.f + expf(-d / A.sigma));
     return true;
   } else {
     euclid_distance<kFast>(g, xp, yp, fr);
     fr.dis = dot2(fr.dx, fr.dx, fr.dy, fr.dy);
     if (fr.sign < 0.f && fr.dis >= thr) return false;
-    fr.frag = kFast ? fast_rcp(1.f + fast_exp(-fr.sign * fr.dis * A.inv_sigma))
+    fr.frag = kFast ? fast_rcp<kFast>(1.f + fast_exp<kFast>(-fr.sign * fr.dis * A.inv_sigma))
                     : 1.f / (1.f + expf(-fr.sign * fr.dis / A.sigma));
     return true;
   }
@@ -455,7 +460,7 @@ __device__ __forceinline__ bool soft_fragment(const RasterArgs& A, const FaceGeo
 
 // Clipped barycentrics (.cu:53-58) and the depth they interpolate (:423).
 //   wc_k = c_k / s,  c = clamp(w, 0, 1),  s = max(sum c, 1e-5);   zp = 1 / sum_k wc_k / z_k = s / sum_k c_k / z_k
-template <bool kFast>
+template <int kFast>
 __device__ __forceinline__ float clip_and_depth(const FaceGeom& g, const float* w, float* wc) {
   const float c0 = fmaxf(fminf(w[0], 1.f), 0.f);
   const float c1 = fmaxf(fminf(w[1], 1.f), 0.f);
@@ -465,9 +470,9 @@ __device__ __forceinline__ float clip_and_depth(const FaceGeom& g, const float* 
     wc[0] = __fdiv_rn(c0, s); wc[1] = __fdiv_rn(c1, s); wc[2] = __fdiv_rn(c2, s);
     return __fdiv_rn(1.f, __fdiv_rn(wc[0], g.z[0]) + __fdiv_rn(wc[1], g.z[1]) + __fdiv_rn(wc[2], g.z[2]));
   }
-  const float rs = fast_rcp(s);
+  const float rs = fast_rcp<kFast>(s);
   wc[0] = c0 * rs; wc[1] = c1 * rs; wc[2] = c2 * rs;
-  return s * fast_rcp(c0 * g.iz[0] + c1 * g.iz[1] + c2 * g.iz[2]);
+  return s * fast_rcp<kFast>(c0 * g.iz[0] + c1 * g.iz[1] + c2 * g.iz[2]);
 }
 
 // 'surface' texel index of .cu:178-194 (may equal R*R: the reference reads the next face's block)

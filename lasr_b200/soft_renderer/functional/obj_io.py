@@ -136,7 +136,10 @@ def create_texture_image(textures, texture_res=16):
     image = torch.ones(tile_height * texture_res, tile_width * texture_res, 3, dtype=torch.float32, device=dev)
     n = torch.arange(num_faces)
     column = (n % tile_width).float()
-    row = (n / tile_width).float()                # true division, as in the reference (save_obj.py:17)
+    # Deliberate deviation: the reference writes `face_nums / tile_width` (save_obj.py:17), which was floor division
+    # on the torch it was written for but is TRUE division on LASR's pinned torch 1.7.1 -- the triangles then
+    # straddle the cells of other faces and the exported atlas does not reload.  The cell row is an integer.
+    row = torch.div(n, tile_width, rounding_mode="floor").float()
     vertices = torch.zeros((num_faces, 3, 2), dtype=torch.float32)
     vertices[:, 0, 0] = column * texture_res + texture_res / 2
     vertices[:, 0, 1] = row * texture_res + 1

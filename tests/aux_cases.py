@@ -45,7 +45,7 @@ def atlas_vertices(num_faces, res):
     tile_width = int((num_faces - 1.) ** 0.5) + 1
     n = np.arange(num_faces)
     column = (n % tile_width).astype(np.float32)
-    row = (n / tile_width).astype(np.float32)
+    row = (n // tile_width).astype(np.float32)
     v = np.zeros((num_faces, 3, 2), np.float32)
     v[:, 0, 0] = column * res + res / 2
     v[:, 0, 1] = row * res + 1

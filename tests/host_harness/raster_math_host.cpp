@@ -52,7 +52,7 @@ extern "C" void lasr_host_soft_fragment(const float* faces9, const float* px, co
     store_record<1>(rec, g0, tex9);
     load_record<1>(rec, g, tex9);
     Fragment fr;
-    const bool ok = soft_fragment<true>(A, g, px[i], py[i], thr, fr);
+    const bool ok = soft_fragment<1>(A, g, px[i], py[i], thr, fr);
     float* o = out + 10 * i;
     o[0] = ok ? 1.f : 0.f;
     o[1] = fr.w[0]; o[2] = fr.w[1]; o[3] = fr.w[2];
