@@ -351,6 +351,26 @@ int lasr_b200_create_texture_image(const float* faces, const float* textures, fl
                                    int num_faces, int texture_res_in, int image_height, int image_width,
                                    float eps, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Dataloader -> device staging.
+ * Replaces the per-item preprocessing of BaseDataset.__getitem__ (dataloader/vidbase.py:52-193) between file
+ * decode and collate -- complement-colour background, mask-box crop (cv2.remap at integer offsets), cv2.resize
+ * to img_size, flow re-normalisation between the two crops, focal scale and principal-point offsets -- for
+ * `num_pairs` dataset items at once.  A pair is frame 0 and its partner frame n.
+ *   in   frames_bgr [P,2,H,W,3] u8 (cv2.imread order), masks [P,2,H,W] u8, flows [P,2,H,W,3] f32 (readPFM:
+ *        u, v, valid; slot 0 holds the flow 0->n, slot 1 the flow n->0), occs [P,2,H,W] f32
+ *   out  img [P,2,3,S,S] RGB 0..1 (elem 'img' / 'imgn'), mask [P,2,S,S] 0/1 ('mask'), flow [P,2,3,S,S]
+ *        ('flow' / 'flown'), occ [P,2,S,S] ('occ' / 'occn'), cam_focal [P,2] (cam[0] = 1/alp), pps [P,2,2],
+ *        boxes [P,2,4] int32 = (center x, center y, half size, mask pixel count); a frame whose mask is empty
+ *        has count 0 and its pair's outputs are left untouched (the reference raises there).
+ * ------------------------------------------------------------------------------------------- */
+size_t lasr_b200_stage_workspace_bytes(int num_pairs);
+int lasr_b200_stage_pairs(const uint8_t* frames_bgr, const uint8_t* masks, const float* flows,
+                          const float* occs, float* img, float* mask_out, float* flow_out,
+                          float* occ_out, float* cam_focal, float* pps, int32_t* boxes,
+                          void* workspace, size_t workspace_bytes, int num_pairs, int height,
+                          int width, int image_size, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

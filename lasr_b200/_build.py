@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.environ.get("LASR_B200_LIB") or os.path.join(CSRC, "liblasr_b200.so")  # override: A/B builds
-SOURCES = ["host_common.cu", "raster.cu", "lbs.cu", "losses.cu", "skin.cu", "meshreg.cu", "chamfer.cu", "texture_io.cu"]
+SOURCES = ["host_common.cu", "raster.cu", "lbs.cu", "losses.cu", "skin.cu", "meshreg.cu", "chamfer.cu", "texture_io.cu", "staging.cu"]
 HEADERS = ["raster_common.cuh", "host_common.h"]
 
 

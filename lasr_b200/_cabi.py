@@ -66,9 +66,12 @@ def lib():
                            ("chamfer_forward", [vp] * 6 + [ci, ci, ci, vp]),
                            ("chamfer_backward", [vp] * 8 + [ci, ci, ci, vp]),
                            ("load_textures", [vp] * 4 + [ci, ci, ci, ci, vp]),
-                           ("create_texture_image", [vp] * 3 + [ci, ci, ci, ci, _c.c_float, vp])):
+                           ("create_texture_image", [vp] * 3 + [ci, ci, ci, ci, _c.c_float, vp]),
+                           ("stage_pairs", [vp] * 12 + [_c.c_size_t, ci, ci, ci, ci, vp])):
             fn = getattr(L, "lasr_b200_" + name)
             fn.restype, fn.argtypes = ci, args
+        L.lasr_b200_stage_workspace_bytes.restype = _c.c_size_t
+        L.lasr_b200_stage_workspace_bytes.argtypes = [ci]
         L.lasr_b200_skin_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_skin_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_skin_weights_forward.restype = _c.c_int
@@ -122,6 +125,7 @@ EXPORTED_SYMBOLS = [
     "lasr_b200_arap_forward", "lasr_b200_arap_backward", "lasr_b200_flatten_forward", "lasr_b200_flatten_backward",
     "lasr_b200_chamfer_forward", "lasr_b200_chamfer_backward",
     "lasr_b200_load_textures", "lasr_b200_create_texture_image",
+    "lasr_b200_stage_workspace_bytes", "lasr_b200_stage_pairs",
 ]
 
 

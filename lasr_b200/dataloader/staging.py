@@ -1,0 +1,87 @@
+"""Batch staging on the device: decoded frame pairs in, the tensors of the reference's collated batch out.
+
+``stage_pairs`` is the functional form (CUDA tensors in, dict of CUDA tensors out, keys and shapes of the
+reference's ``elem`` after ``default_collate``: dataloader/vidbase.py:193-229).  ``DeviceStager`` adds the host
+side of it: pinned staging buffers, the H2D copies on a side stream, and an event the consumer stream waits on,
+so batch i+1 is uploaded and preprocessed while step i renders.
+
+No CPU fallback: the kernels live in ``csrc/staging.cu`` behind ``lasr_b200_stage_pairs``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _cabi
+
+
+def stage_pairs(frames_bgr, masks, flows, occs, img_size):
+    """frames_bgr [P,2,H,W,3] uint8, masks [P,2,H,W] uint8, flows [P,2,H,W,3] float32, occs [P,2,H,W] float32
+    (CUDA, contiguous; slot 0 = frame 0 with the flow 0->n, slot 1 = frame n with the flow n->0).
+    Returns the collated batch: img / imgn [P,3,S,S], mask [P,2,S,S], flow / flown [P,3,S,S], occ / occn [P,S,S],
+    cam / camn [P,7], pps [P,2,2] (float32, CUDA) and 'boxes' [P,2,4] int32 (cx, cy, L, mask pixels)."""
+    if frames_bgr.dim() != 5 or frames_bgr.shape[1] != 2 or frames_bgr.shape[4] != 3:
+        raise RuntimeError("stage_pairs: frames_bgr must be [P,2,H,W,3]")
+    P, _, H, W, _ = frames_bgr.shape
+    if tuple(masks.shape) != (P, 2, H, W) or tuple(flows.shape) != (P, 2, H, W, 3) or tuple(occs.shape) != (P, 2, H, W):
+        raise RuntimeError("stage_pairs: masks / flows / occs do not match frames_bgr")
+    if frames_bgr.dtype != torch.uint8 or masks.dtype != torch.uint8:
+        raise RuntimeError("stage_pairs: frames and masks must be uint8 (as decoded)")
+    dev, S = frames_bgr.device, int(img_size)
+    f32 = dict(dtype=torch.float32, device=dev)
+    img = torch.empty(P, 2, 3, S, S, **f32); mask = torch.empty(P, 2, S, S, **f32)
+    flow = torch.empty(P, 2, 3, S, S, **f32); occ = torch.empty(P, 2, S, S, **f32)
+    focal = torch.zeros(P, 2, **f32); pps = torch.zeros(P, 2, 2, **f32)
+    boxes = torch.zeros(P, 2, 4, dtype=torch.int32, device=dev)
+    ws = torch.empty(int(_cabi.lib().lasr_b200_stage_workspace_bytes(P)), dtype=torch.uint8, device=dev)
+    _cabi.native_call("stage_pairs", frames_bgr.contiguous(), masks.contiguous(), flows.contiguous().float(),
+                      occs.contiguous().float(), img, mask, flow, occ, focal, pps, boxes, ws, ws.numel(), P, H, W, S)
+    cam = torch.zeros(P, 2, 7, **f32)              # [1/alp, 0, 0, 1, 0, 0, 0]   (vidbase.py:167-183)
+    cam[:, :, 0] = focal
+    cam[:, :, 3] = 1.0
+    return {"img": img[:, 0], "imgn": img[:, 1], "mask": mask, "flow": flow[:, 0], "flown": flow[:, 1],
+            "occ": occ[:, 0], "occn": occ[:, 1], "cam": cam[:, 0], "camn": cam[:, 1], "pps": pps, "boxes": boxes}
+
+
+def check_boxes(boxes):
+    """The reference raises inside numpy when a mask is empty (``xid.max()`` of an empty array, vidbase.py:98);
+    here the condition is detected from the staged pixel counts (one small D2H read)."""
+    if bool((boxes[..., 3] == 0).any()):
+        raise ValueError("stage_pairs: a frame has an empty mask (the reference's crop box is undefined)")
+
+
+class DeviceStager:
+    """Pinned host buffers + side-stream upload + device preprocessing for batches of `pairs` items of HxW frames."""
+
+    def __init__(self, pairs, height, width, img_size, device="cuda"):
+        self.P, self.H, self.W, self.S = int(pairs), int(height), int(width), int(img_size)
+        self.device = torch.device(device)
+        shp = (self.P, 2, self.H, self.W)
+        self._host = {"frames_bgr": torch.empty(shp + (3,), dtype=torch.uint8).pin_memory(),
+                      "masks": torch.empty(shp, dtype=torch.uint8).pin_memory(),
+                      "flows": torch.empty(shp + (3,), dtype=torch.float32).pin_memory(),
+                      "occs": torch.empty(shp, dtype=torch.float32).pin_memory()}
+        self._dev = {k: torch.empty_like(v, device=self.device) for k, v in self._host.items()}
+        self._stream = torch.cuda.Stream(device=self.device)
+        self._done = torch.cuda.Event()
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self._host.values())
+
+    def submit(self, raw):
+        """raw: dict of numpy / CPU tensors with the keys of ``collate_raw``.  Starts upload + staging on the side
+        stream and returns immediately; ``result()`` makes the current stream wait for it."""
+        for k, buf in self._host.items():
+            buf.copy_(torch.as_tensor(np.ascontiguousarray(raw[k])) if not torch.is_tensor(raw[k]) else raw[k])
+        self._stream.wait_stream(torch.cuda.current_stream(self.device))     # buffers of the previous batch are free
+        with torch.cuda.stream(self._stream):
+            for k, buf in self._host.items():
+                self._dev[k].copy_(buf, non_blocking=True)
+            self._out = stage_pairs(self._dev["frames_bgr"], self._dev["masks"], self._dev["flows"], self._dev["occs"],
+                                    self.S)
+            self._done.record(self._stream)
+        return self
+
+    def result(self):
+        torch.cuda.current_stream(self.device).wait_event(self._done)
+        for v in self._out.values():
+            v.record_stream(torch.cuda.current_stream(self.device))
+        return self._out
