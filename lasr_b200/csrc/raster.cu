@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -41,6 +42,22 @@ namespace lasr {
 constexpr int kTileW = 16;                      // tile width in pixels (two 8x4 warp footprints)
 constexpr int kTileH = LASR_TILE_H;             // tile height in pixels (multiple of 4)
 constexpr int kFwdWarps = 2 * (kTileH / 4);     // each warp owns an 8x4 pixel footprint
+#ifndef LASR_FWD_LPT                // dispatch forward tiles heaviest-first (longest-processing-time order)
+#define LASR_FWD_LPT 1
+#endif
+#ifndef LASR_BINNING                // two-level binning: 64x64-pixel bins built once per frame, tiles scan their bin
+#define LASR_BINNING 0
+#endif
+constexpr int kBin = 64;            // bin edge in pixels; a multiple of both tile edges
+static_assert(kBin % kTileW == 0 && kBin % kTileH == 0, "tiles must nest in bins");
+#ifndef LASR_DYN_TILE_W             // tile of the footprint-claiming forward variant (0: disabled)
+#define LASR_DYN_TILE_W 0
+#endif
+#ifndef LASR_DYN_TILE_H
+#define LASR_DYN_TILE_H 16
+#endif
+constexpr int kDynTileW = LASR_DYN_TILE_W > 0 ? LASR_DYN_TILE_W : 16;
+constexpr int kDynTileH = LASR_DYN_TILE_H;
 constexpr int kFwdThreads = 32 * kFwdWarps;
 #ifndef LASR_SCAN_UNROLL            // window loads kept in flight per thread in the tile scan
 #define LASR_SCAN_UNROLL 2
@@ -50,14 +67,14 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #ifndef LASR_FWD_MIN_BLOCKS
 #define LASR_FWD_MIN_BLOCKS 4
 #endif
-#ifndef LASR_BWD_MIN_BLOCKS
-#define LASR_BWD_MIN_BLOCKS 2
+#ifndef LASR_BWD_MIN_BLOCKS          // resident CTAs of LASR_BWD_THREADS threads the register budget must allow
+#define LASR_BWD_MIN_BLOCKS 4
 #endif
 #ifndef LASR_FWD_MIN_BLOCKS_MULTI   // several colour sets per pass carry more live state per pixel
 #define LASR_FWD_MIN_BLOCKS_MULTI 3
 #endif
 #ifndef LASR_BWD_MIN_BLOCKS_MULTI
-#define LASR_BWD_MIN_BLOCKS_MULTI 2
+#define LASR_BWD_MIN_BLOCKS_MULTI 4
 #endif
 #ifndef LASR_PREFETCH_REC           // warm L1 with a face's record when it passes the warp cull
 #define LASR_PREFETCH_REC 1
@@ -116,6 +133,14 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RasterArgs A, int wit
       atomicMin(fw + 0, a); atomicMin(fw + 1, b); atomicMin(fw + 2, c); atomicMin(fw + 3, d);
     }
   }
+  if (A.tile_count && xlo <= xhi) {   // work estimate per forward tile: faces whose window reaches it
+    const int tiles_x = (A.S + kTileW - 1) / kTileW, tiles_y = (A.S + kTileH - 1) / kTileH;
+    int* tc = A.tile_count + (long long)(i / A.F) * tiles_x * tiles_y;
+    const int tx0 = xlo / kTileW, tx1 = xhi / kTileW;
+    const int ty0 = (A.S - 1 - yhi) / kTileH, ty1 = (A.S - 1 - ylo) / kTileH;   // rows from the top
+    for (int ty = ty0; ty <= ty1; ++ty)
+      for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(tc + ty * tiles_x + tx, 1);
+  }
   A.face_border[i] = make_float4(g.lox, g.hix, g.loy, g.hiy);
   if (A.K == 1) store_record<1>(A.face_record + i * rec_words(1), g, vertex_tex ? tex9 : nullptr);
   else if (A.K == 2) store_record<2>(A.face_record + i * rec_words(2), g, tex9);
@@ -123,8 +148,108 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RasterArgs A, int wit
 }
 
 // ---------------------------------------------------------------------------------------------
+// binning: one CTA per (64x64-pixel bin, frame) compacts, in ascending face order, the faces whose pixel
+// window reaches the bin, together with the window clipped to the bin.  A 16x16 tile then scans the few
+// hundred entries of its bin instead of all F windows (16 bins x F reads per frame instead of 256 tiles x F:
+// the tile scan was 8 % of the forward's instructions and 11 % of its stall samples).  Two passes over the
+// windows (count, then write at the warp's offset) keep the order without atomics.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) raster_bin_kernel(RasterArgs A) {
+  __shared__ int s_cnt[8];
+  const int n = blockIdx.y, bin = blockIdx.x;
+  const int bx = bin % A.bins_x, by = bin / A.bins_x;            // by counts row blocks from the top
+  const int S = A.S, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x0 = bx * kBin, x1 = x0 + kBin - 1;                   // x index range
+  const int y1 = S - 1 - by * kBin, y0 = y1 - (kBin - 1);         // y index range (index = S-1-row), may start < 0
+  const int bins = A.bins_x * ((S + kBin - 1) / kBin);
+  int* count = A.bin_count + (long long)n * bins + bin;
+  const int4 fwin = *reinterpret_cast<const int4*>(A.frame_window + 4 * n);
+  if (!(x1 >= fwin.x && x0 <= -fwin.y && y1 >= fwin.z && y0 <= -fwin.w)) {   // no face reaches this bin
+    if (threadIdx.x == 0) *count = 0;
+    return;
+  }
+  const uint2* win = A.face_window + (long long)n * A.F;
+  uint2* out = A.bin_entries + ((long long)n * bins + bin) * A.F;
+  const int per_warp = ((A.F + 8 * 32 - 1) / (8 * 32)) * 32;      // faces per warp, a multiple of 32
+  const int f0 = warp * per_warp;
+  int offset = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    int cnt = 0;
+    for (int it = 0; it < per_warp; it += 32) {
+      const int f = f0 + it + lane;
+      bool hit = false;
+      uint2 wv = make_uint2(0, 0);
+      if (f < A.F) {
+        wv = win[f];
+        const int xlo = wv.x & 0xffff, xhi = wv.x >> 16, ylo = wv.y & 0xffff, yhi = wv.y >> 16;
+        hit = xlo <= x1 && xhi >= x0 && ylo <= y1 && yhi >= y0 && xlo <= xhi;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (pass == 1 && hit) {
+        const int xlo = wv.x & 0xffff, xhi = wv.x >> 16, ylo = wv.y & 0xffff, yhi = wv.y >> 16;
+        const unsigned packed = (unsigned)max(xlo - x0, 0) | ((unsigned)min(xhi - x0, kBin - 1) << 8) |
+                                ((unsigned)max(ylo - y0, 0) << 16) | ((unsigned)min(yhi - y0, kBin - 1) << 24);
+        out[offset + cnt + __popc(m & ((1u << lane) - 1))] = make_uint2((unsigned)f, packed);
+      }
+      cnt += __popc(m);
+    }
+    if (pass == 0) {
+      if (lane == 0) s_cnt[warp] = cnt;
+      __syncthreads();
+      int total = 0;
+      for (int w = 0; w < 8; ++w) { if (w == warp) offset = total; total += s_cnt[w]; }
+      if (threadIdx.x == 0) *count = total;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dispatch order of the forward's CTAs: (frame, tile) items sorted by their face count, heaviest first
+// (counting sort, one CTA).  CTAs are started in block-index order and a tile on the object lives for tens of
+// microseconds, so with frame-major order the SMs idled through a long tail (ncu: active 81 % of the launch);
+// longest-first dispatch is the classic remedy.  Only the ORDER of independent tiles changes -- ties between
+// equal counts are broken by atomics, which cannot affect any output.
+// ---------------------------------------------------------------------------------------------
+constexpr int kOrderBuckets = 1024;
+__global__ void __launch_bounds__(1024) raster_order_kernel(const int* __restrict__ count, int* __restrict__ order,
+                                                            int items) {
+  __shared__ int s_hist[kOrderBuckets];
+  for (int b = threadIdx.x; b < kOrderBuckets; b += blockDim.x) s_hist[b] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < items; i += blockDim.x) atomicAdd(&s_hist[min(count[i], kOrderBuckets - 1)], 1);
+  __syncthreads();
+  if (threadIdx.x < 32) {   // exclusive prefix over buckets in DESCENDING count order, one warp
+    int carry = 0;
+    for (int base = kOrderBuckets - 32; base >= 0; base -= 32) {
+      const int b = base + 31 - (int)threadIdx.x;           // lane 0 takes the largest count of this group
+      const int h = s_hist[b];
+      int incl = h;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)threadIdx.x >= o) incl += v;
+      }
+      s_hist[b] = carry + incl - h;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < items; i += blockDim.x)
+    order[atomicAdd(&s_hist[min(count[i], kOrderBuckets - 1)], 1)] = i;
+}
+
+// ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+#ifndef LASR_FWD_CENTRE_OUT
+#define LASR_FWD_CENTRE_OUT 1
+#endif
+// r-th element of the sequence c, c+1, c-1, c+2, ... over [0, n), c = (n-1)/2: the middle first, the ends last
+__device__ __forceinline__ int centre_out(int r, int n) {
+  const int c = (n - 1) >> 1, k = (r + 1) >> 1;
+  return (r & 1) ? c + k : c - k;
+}
+
 template <int K>
 struct PixelState {
   float alpha;             // running product / sum / flag
@@ -191,29 +316,51 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConst
   }
 }
 
-template <bool kFast, int K>
+// kDyn = false: one CTA per 16 x kTileH tile, warp w owns footprint w for the whole kernel; the face list may be
+//               built in several rounds (F > kMaxScanChunk), the per-pixel state living in registers across them.
+// kDyn = true:  one CTA per kDynTileW x kDynTileH tile holding kDynFp > 8 footprints; the list is built once
+//               (F <= kMaxScanChunk) and the warps CLAIM footprints from a shared counter until none is left.
+//               The footprints of a tile differ widely in work (silhouette edge vs. interior vs. background):
+//               with static ownership a CTA keeps its registers until its slowest warp is done (ncu: 37 %
+//               achieved occupancy of 50 % theoretical); claiming evens that out and halves the scans per pixel.
+template <bool kFast, int K, bool kDyn>
 __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LASR_FWD_MIN_BLOCKS_MULTI) raster_forward_kernel(RasterArgs A, int chunk) {
   constexpr int kMode = kFast ? (LASR_FTZ_MUFU_FWD ? 2 : 1) : 0;
   constexpr int kRecWords = rec_words(K);
   constexpr int P = 3 * K + 1;      // image planes per frame: K colour sets, then alpha
+  constexpr int kTW = kDyn ? kDynTileW : kTileW, kTH = kDyn ? kDynTileH : kTileH;
+  constexpr int kFpX = kTW / 8, kNumFp = kFpX * (kTH / 4);
   extern __shared__ int s_list[];   // [chunk] face indices, 8 per-warp segments of chunk/8
   __shared__ int s_cnt[kFwdWarps];
+  __shared__ int s_next;
   const int wseg = chunk / kFwdWarps;
 
   const int S = A.S;
-  const int tiles_x = (S + kTileW - 1) / kTileW;
-  const int tile_x = blockIdx.x % tiles_x;
-  const int tile_y = blockIdx.x / tiles_x;
-  const int n = blockIdx.y;
+  const int tiles_x = (S + kTW - 1) / kTW, tiles_y = (S + kTH - 1) / kTH;
+  int n, tile_x, tile_y;
+  if (A.tile_order && !kDyn) {   // heaviest tiles first (raster_order_kernel)
+    const int item = A.tile_order[blockIdx.x];
+    n = item / (tiles_x * tiles_y);
+    tile_x = (item % (tiles_x * tiles_y)) % tiles_x;
+    tile_y = (item % (tiles_x * tiles_y)) / tiles_x;
+  } else {
+#if LASR_FWD_CENTRE_OUT
+  // CTAs are dispatched in block-index order and live long (tens of microseconds for a tile on the object), so
+  // whatever is dispatched last decides how long the other SMs idle at the end of the launch (ncu: SMs active
+  // 81 % of the kernel with frame-major order).  Order: frame fastest, tiles from the image centre outwards --
+  // the last CTAs of the grid are then the border tiles of all frames, which are mostly background.
+  n = blockIdx.x % A.N;
+  const int rank = blockIdx.x / A.N;
+  tile_x = centre_out(rank % tiles_x, tiles_x);
+  tile_y = centre_out(rank / tiles_x, tiles_y);
+#else
+  n = blockIdx.x / (tiles_x * tiles_y);
+  tile_x = (blockIdx.x % (tiles_x * tiles_y)) % tiles_x;
+  tile_y = (blockIdx.x % (tiles_x * tiles_y)) / tiles_x;
+#endif
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wx0 = tile_x * kTileW + (warp & 1) * 8, wy0 = tile_y * kTileH + (warp >> 1) * 4;
-  const int px = wx0 + (lane & 7);
-  const int py = wy0 + (lane >> 3);  // row from the top
-  const bool valid = px < S && py < S;
-  const float xp = A.coords[min(px, S - 1)];
-  const float yp = A.coords[max(S - 1 - py, 0)];
   const long long SS = (long long)S * S;
-  const long long pn = (long long)py * S + px;
 
   FwdConsts C;
   C.near_ = A.near_; C.far_ = A.far_;
@@ -223,26 +370,9 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
   const int rgb_f = kFast ? 1 : A.rgb;
   const int alpha_f = kFast ? 2 : A.alpha;
 
-  PixelState<K> st;
-  st.alpha = alpha_f == 2 ? 1.f : 0.f;
-  st.ssum = expf(A.eps / A.gamma);
-  st.smax = A.eps;
-  st.depth_min = 10000000.f;
-  st.face_min = -1;
-#pragma unroll
-  for (int k = 0; k < 3 * K; ++k) {
-    const float bg = A.bg_in_args ? A.bg[k] : (valid ? A.soft_colors[((long long)n * P + k) * SS + pn] : 0.f);
-    st.col[k] = rgb_f == 1 ? bg * st.ssum : bg;
-  }
-
-  // warp footprint in pixel-centre coordinates (for the per-warp cull)
-  const float fx0 = A.coords[min(wx0, S - 1)];
-  const float fx1 = A.coords[min(wx0 + 7, S - 1)];
-  const float fy1 = A.coords[max(S - 1 - wy0, 0)];
-  const float fy0 = A.coords[max(S - 1 - (wy0 + 3), 0)];
   // tile window in pixel indices (x index, y index = S-1-row)
-  const int tx0 = tile_x * kTileW, tx1 = tx0 + kTileW - 1;
-  const int ty1 = S - 1 - tile_y * kTileH, ty0 = ty1 - (kTileH - 1);
+  const int tx0 = tile_x * kTW, tx1 = tx0 + kTW - 1;
+  const int ty1 = S - 1 - tile_y * kTH, ty0 = ty1 - (kTH - 1);
 
   const uint2* win = A.face_window + (long long)n * A.F;
   const float4* border = A.face_border + (long long)n * A.F;
@@ -251,27 +381,84 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
   // tiles that no face window of this frame reaches skip the scan and go straight to the epilogue
   const int4 fwin = *reinterpret_cast<const int4*>(A.frame_window + 4 * n);
   const bool tile_live = tx1 >= fwin.x && tx0 <= -fwin.y && ty1 >= fwin.z && ty0 <= -fwin.w;
-  for (int base = 0; tile_live && base < A.F; base += chunk) {
-    // (1) scan: warp w owns faces [base + w*wseg, base + (w+1)*wseg) and compacts hits in order
+  if (kDyn && tid == 0) s_next = kFwdWarps;
+
+  // (1) scan: warp w owns candidates [base + w*wseg, base + (w+1)*wseg) and compacts hits in order.  The
+  //     candidates are the entries of the tile's 64x64 bin (ascending face id, window relative to the bin) or,
+  //     without binning, all F face windows.
+  const bool binned = A.bins_x > 0;
+  const int bins = binned ? A.bins_x * ((S + kBin - 1) / kBin) : 0;
+  const int bin = binned ? (tile_y * kTH / kBin) * A.bins_x + tile_x * kTW / kBin : 0;
+  const uint2* bin_list = binned ? A.bin_entries + ((long long)n * bins + bin) * A.F : nullptr;
+  const int n_cand = binned ? A.bin_count[(long long)n * bins + bin] : A.F;
+  // tile window relative to the bin origin (x index, y index = S-1-row)
+  const int bx0 = (tile_x * kTW / kBin) * kBin, by0 = S - 1 - (tile_y * kTH / kBin) * kBin - (kBin - 1);
+  const int rx0 = tx0 - bx0, rx1 = tx1 - bx0, ry0 = ty0 - by0, ry1 = ty1 - by0;
+  auto scan = [&](int base) {
     int cnt = 0;
     const int seg0 = base + warp * wseg;
 #pragma unroll kScanUnroll
     for (int it = 0; it < wseg; it += 32) {
-      const int f = seg0 + it + lane;
+      const int j = seg0 + it + lane;
       bool hit = false;
-      if (f < A.F) {
-        const uint2 wv = win[f];
-        const int xlo = wv.x & 0xffff, xhi = wv.x >> 16, ylo = wv.y & 0xffff, yhi = wv.y >> 16;
-        hit = xlo <= tx1 && xhi >= tx0 && ylo <= ty1 && yhi >= ty0 && xlo <= xhi;
+      int f = j;
+      if (j < n_cand) {
+        if (binned) {
+          const uint2 e = bin_list[j];
+          f = (int)e.x;
+          const int xlo = e.y & 255, xhi = (e.y >> 8) & 255, ylo = (e.y >> 16) & 255, yhi = e.y >> 24;
+          hit = xlo <= rx1 && xhi >= rx0 && ylo <= ry1 && yhi >= ry0;
+        } else {
+          const uint2 wv = win[j];
+          const int xlo = wv.x & 0xffff, xhi = wv.x >> 16, ylo = wv.y & 0xffff, yhi = wv.y >> 16;
+          hit = xlo <= tx1 && xhi >= tx0 && ylo <= ty1 && yhi >= ty0 && xlo <= xhi;
+        }
       }
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (hit) s_list[warp * wseg + cnt + __popc(m & ((1u << lane) - 1))] = f;
       cnt += __popc(m);
     }
     if (lane == 0) s_cnt[warp] = cnt;
-    __syncthreads();
-    // (2) every warp walks the whole ordered list on its own: cull 32 faces per ballot against
-    //     its 8x4 footprint, evaluate survivors in ascending face order.  No further barriers.
+  };
+
+  // one 8x4 footprint: lane = pixel
+  struct Footprint {
+    int px, py;
+    bool valid;
+    float xp, yp, fx0, fx1, fy0, fy1;
+    long long pn;
+  };
+  auto place = [&](int fp) {
+    Footprint q;
+    const int wx0 = tile_x * kTW + (fp % kFpX) * 8, wy0 = tile_y * kTH + (fp / kFpX) * 4;
+    q.px = wx0 + (lane & 7);
+    q.py = wy0 + (lane >> 3);  // row from the top
+    q.valid = q.px < S && q.py < S;
+    q.xp = A.coords[min(q.px, S - 1)];
+    q.yp = A.coords[max(S - 1 - q.py, 0)];
+    q.pn = (long long)q.py * S + q.px;
+    // footprint in pixel-centre coordinates (for the per-warp cull)
+    q.fx0 = A.coords[min(wx0, S - 1)];
+    q.fx1 = A.coords[min(wx0 + 7, S - 1)];
+    q.fy1 = A.coords[max(S - 1 - wy0, 0)];
+    q.fy0 = A.coords[max(S - 1 - (wy0 + 3), 0)];
+    return q;
+  };
+  auto init_state = [&](const Footprint& q, PixelState<K>& st) {
+    st.alpha = alpha_f == 2 ? 1.f : 0.f;
+    st.ssum = expf(A.eps / A.gamma);
+    st.smax = A.eps;
+    st.depth_min = 10000000.f;
+    st.face_min = -1;
+#pragma unroll
+    for (int k = 0; k < 3 * K; ++k) {
+      const float bg = A.bg_in_args ? A.bg[k] : (q.valid ? A.soft_colors[((long long)n * P + k) * SS + q.pn] : 0.f);
+      st.col[k] = rgb_f == 1 ? bg * st.ssum : bg;
+    }
+  };
+  // (2) a warp walks the whole ordered list on its own: cull 32 faces per ballot against its 8x4 footprint,
+  //     evaluate survivors in ascending face order.  No barriers.
+  auto walk = [&](const Footprint& q, PixelState<K>& st) {
 #pragma unroll 1
     for (int seg = 0; seg < kFwdWarps; ++seg) {
       const int nseg = s_cnt[seg];
@@ -285,7 +472,7 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
         if (j < nseg) {
           f = lst[j];
           bd = __ldg(border + f);
-          pass = !(fx0 > bd.y || fx1 < bd.x || fy0 > bd.w || fy1 < bd.z);
+          pass = !(q.fx0 > bd.y || q.fx1 < bd.x || q.fy0 > bd.w || q.fy1 < bd.z);
 #if LASR_PREFETCH_REC
           if (pass) {
             const char* rp = reinterpret_cast<const char*>(records + (long long)f * kRecWords);
@@ -305,32 +492,61 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
           bb.y = __shfl_sync(0xffffffffu, bd.y, b);
           bb.z = __shfl_sync(0xffffffffu, bd.z, b);
           bb.w = __shfl_sync(0xffffffffu, bd.w, b);
-          if (valid) forward_pair<kFast, K>(A, C, records + (long long)fb * kRecWords, bb, fb, n, xp, yp, st);
+          if (q.valid) forward_pair<kFast, K>(A, C, records + (long long)fb * kRecWords, bb, fb, n, q.xp, q.yp, st);
         }
       }
     }
-    if (base + chunk < A.F) __syncthreads();  // the list is reused by the next round
-  }
-
-  if (!valid) return;
+  };
   // finalize (.cu:457-482)
-  float* out = A.soft_colors + (long long)n * P * SS + pn;
-  float* agg = A.aggrs_info + (long long)n * 2 * SS + pn;
-  if (alpha_f == 0) out[(P - 1) * SS] = st.alpha;
-  else if (alpha_f == 1) out[(P - 1) * SS] = st.alpha / A.F;
-  else out[(P - 1) * SS] = 1.f - st.alpha;
-  if (rgb_f == 0) {
-    if (st.face_min != -1) {
+  auto finish = [&](const Footprint& q, const PixelState<K>& st) {
+    if (!q.valid) return;
+    float* out = A.soft_colors + (long long)n * P * SS + q.pn;
+    float* agg = A.aggrs_info + (long long)n * 2 * SS + q.pn;
+    if (alpha_f == 0) out[(P - 1) * SS] = st.alpha;
+    else if (alpha_f == 1) out[(P - 1) * SS] = st.alpha / A.F;
+    else out[(P - 1) * SS] = 1.f - st.alpha;
+    if (rgb_f == 0) {
+      if (st.face_min != -1) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) out[k * SS] = st.col[k];
+        for (int k = 0; k < 3; ++k) out[k * SS] = st.col[k];
+      }
+      agg[0] = st.depth_min;
+      agg[SS] = (float)st.face_min;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3 * K; ++k) out[k * SS] = div_<kMode>(st.col[k], st.ssum);
+      agg[0] = st.ssum;
+      agg[SS] = st.smax;
     }
-    agg[0] = st.depth_min;
-    agg[SS] = (float)st.face_min;
+  };
+
+  if (!kDyn) {
+    const Footprint q = place(warp);
+    PixelState<K> st;
+    init_state(q, st);
+    for (int base = 0; tile_live && base < n_cand; base += chunk) {
+      scan(base);
+      __syncthreads();
+      walk(q, st);
+      if (base + chunk < n_cand) __syncthreads();  // the list is reused by the next round
+    }
+    finish(q, st);
   } else {
-#pragma unroll
-    for (int k = 0; k < 3 * K; ++k) out[k * SS] = div_<kMode>(st.col[k], st.ssum);
-    agg[0] = st.ssum;
-    agg[SS] = st.smax;
+    if (tile_live) scan(0);
+    else if (lane == 0) s_cnt[warp] = 0;
+    __syncthreads();
+    int fp = warp;
+    while (fp < kNumFp) {
+      const Footprint q = place(fp);
+      if (__any_sync(0xffffffffu, q.valid)) {
+        PixelState<K> st;
+        init_state(q, st);
+        walk(q, st);
+        finish(q, st);
+      }
+      if (lane == 0) fp = atomicAdd(&s_next, 1);
+      fp = __shfl_sync(0xffffffffu, fp, 0);
+    }
   }
 }
 
@@ -349,7 +565,7 @@ template <bool k32> struct PlaneIndex { typedef long long type; };
 template <> struct PlaneIndex<true> { typedef unsigned type; };
 
 template <bool kFast, bool kBig, int K, int KF>
-__global__ void __launch_bounds__(256, K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_MIN_BLOCKS_MULTI) raster_backward_kernel(RasterArgs A) {
+__global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_MIN_BLOCKS_MULTI)) raster_backward_kernel(RasterArgs A) {
   constexpr int kMode = kFast ? (LASR_FTZ_MUFU_BWD ? 2 : 1) : 0;   // arithmetic mode, see raster_common.cuh
   constexpr int kRecWords = rec_words(K);
   constexpr int P = 3 * K + 1;          // image planes per frame
@@ -629,11 +845,26 @@ static int check_launch(const char* what) { return lasr_check_launch(what); }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// Heaviest-first dispatch costs a memset, ~3 atomics per face in the setup kernel and a one-CTA sort
+// (~25 us together); it pays once the forward runs for more than a few hundred microseconds (Spot, 64 frames:
+// 1.21 -> 1.05 ms; ico3, 64 frames: 0.36 -> 0.39 ms).  LASR_B200_FWD_LPT=0/1 in the environment forces it.
+static bool use_lpt(int N, int F) {
+  static const int forced = [] { const char* e = getenv("LASR_B200_FWD_LPT"); return e ? atoi(e) : -1; }();
+  if (!LASR_FWD_LPT) return false;
+  if (forced >= 0) return forced != 0;
+  return (long long)N * F >= 150000;
+}
+
+static size_t num_tiles(int S) { return (size_t)((S + kTileW - 1) / kTileW) * (size_t)((S + kTileH - 1) / kTileH); }
+static size_t num_bins(int S) { const size_t b = (size_t)((S + kBin - 1) / kBin); return b * b; }
+
 static size_t raster_ws_bytes(int N, int F, int S, int K) {
   if (N <= 0 || F <= 0 || S <= 0 || K < 1 || K > kMaxSets) return 0;
   const size_t nf = (size_t)N * (size_t)F;
   return align256(nf * sizeof(uint2)) + align256((size_t)S * sizeof(float)) + align256((size_t)N * 4 * sizeof(int)) +
          align256((size_t)(kBigListCap + 1) * sizeof(int)) +
+         (LASR_FWD_LPT ? 2 * align256((size_t)N * num_tiles(S) * sizeof(int)) : 0) +
+         (LASR_BINNING ? align256((size_t)N * num_bins(S) * sizeof(int)) + align256(nf * num_bins(S) * sizeof(uint2)) : 0) +
          align256(nf * sizeof(float4)) +
          align256(nf * rec_words(K) * sizeof(float));
 }
@@ -664,12 +895,56 @@ static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, flo
   A.coords = reinterpret_cast<float*>(p);        p += align256((size_t)S * sizeof(float));
   A.frame_window = reinterpret_cast<int*>(p);    p += align256((size_t)N * 4 * sizeof(int));
   A.big_list = reinterpret_cast<int*>(p);        p += align256((size_t)(kBigListCap + 1) * sizeof(int));
+  if (LASR_FWD_LPT) {   // space is always reserved (the workspace size must not depend on the environment)
+    int* tc = reinterpret_cast<int*>(p);         p += align256((size_t)N * num_tiles(S) * sizeof(int));
+    int* to = reinterpret_cast<int*>(p);         p += align256((size_t)N * num_tiles(S) * sizeof(int));
+    if (use_lpt(N, F)) { A.tile_count = tc; A.tile_order = to; }
+  }
+  if (LASR_BINNING) {
+    A.bin_count = reinterpret_cast<int*>(p);     p += align256((size_t)N * num_bins(S) * sizeof(int));
+    A.bin_entries = reinterpret_cast<uint2*>(p); p += align256(nf * num_bins(S) * sizeof(uint2));
+    A.bins_x = (S + kBin - 1) / kBin;
+  }
   A.face_border = reinterpret_cast<float4*>(p);  p += align256(nf * sizeof(float4));
   A.face_record = reinterpret_cast<float*>(p);
   return 0;
 }
 
 static bool is_fast(const RasterArgs& A);
+
+// forward launch: the footprint-claiming variant whenever the face list fits one scan round
+static int launch_forward(const RasterArgs& A, cudaStream_t st) {
+  const int S = A.S, F = A.F, N = A.N;
+  if (A.tile_order) {
+    raster_order_kernel<<<1, 1024, 0, st>>>(A.tile_count, A.tile_order, (int)(num_tiles(S) * N));
+    if (check_launch("raster_order_kernel")) return 1;
+  }
+  if (A.bins_x > 0) {
+    dim3 bgrid((unsigned)num_bins(S), N);
+    raster_bin_kernel<<<bgrid, 256, 0, st>>>(A);
+    if (check_launch("raster_bin_kernel")) return 1;
+  }
+  int chunk = ((F + kFwdThreads - 1) / kFwdThreads) * kFwdThreads;   // a multiple of 32 faces per warp
+  const bool dyn = LASR_DYN_TILE_W > 0 && chunk <= kMaxScanChunk && A.bins_x == 0;
+  if (chunk > kMaxScanChunk) chunk = (kMaxScanChunk / kFwdThreads) * kFwdThreads;
+  const size_t smem = (size_t)chunk * sizeof(int);
+  if (dyn) {
+    const int tiles = ((S + kDynTileW - 1) / kDynTileW) * ((S + kDynTileH - 1) / kDynTileH);
+    dim3 grid((unsigned)((long long)tiles * N));
+    if (A.K == 3) raster_forward_kernel<true, 3, true><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+    else if (A.K == 2) raster_forward_kernel<true, 2, true><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+    else if (is_fast(A)) raster_forward_kernel<true, 1, true><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+    else raster_forward_kernel<false, 1, true><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  } else {
+    const int tiles = ((S + kTileW - 1) / kTileW) * ((S + kTileH - 1) / kTileH);
+    dim3 grid((unsigned)((long long)tiles * N));
+    if (A.K == 3) raster_forward_kernel<true, 3, false><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+    else if (A.K == 2) raster_forward_kernel<true, 2, false><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+    else if (is_fast(A)) raster_forward_kernel<true, 1, false><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+    else raster_forward_kernel<false, 1, false><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  }
+  return check_launch("raster_forward_kernel");
+}
 
 // main pass (one warp per face, huge faces deferred) + CTA-per-face pass over the deferred list
 static int launch_backward(const RasterArgs& A, long long nf, cudaStream_t st) {
@@ -758,20 +1033,12 @@ extern "C" int lasr_b200_raster_forward(const float* faces, const float* texture
   cudaStream_t st = (cudaStream_t)stream;
   const long long nf = (long long)N * F;
   const long long nthreads = nf > S ? nf : S;
-  if (cudaMemsetAsync(A.frame_window, 0x7f, (size_t)N * 4 * sizeof(int), st) != cudaSuccess)
+  if (cudaMemsetAsync(A.frame_window, 0x7f, (size_t)N * 4 * sizeof(int), st) != cudaSuccess ||
+      (A.tile_count && cudaMemsetAsync(A.tile_count, 0, (size_t)N * num_tiles(S) * sizeof(int), st) != cudaSuccess))
     return fail("render_forward: memset failed");
   raster_setup_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(A, 1);
   if (check_launch("raster_setup_kernel")) return 1;
-  const int tiles = ((S + kTileW - 1) / kTileW) * ((S + kTileH - 1) / kTileH);
-  dim3 grid(tiles, N);
-  int chunk = ((F + kFwdThreads - 1) / kFwdThreads) * kFwdThreads;   // a multiple of 32 faces per warp
-  if (chunk > kMaxScanChunk) chunk = (kMaxScanChunk / kFwdThreads) * kFwdThreads;
-  const size_t smem = (size_t)chunk * sizeof(int);
-  if (A.K == 3) raster_forward_kernel<true, 3><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-  else if (A.K == 2) raster_forward_kernel<true, 2><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-  else if (is_fast(A)) raster_forward_kernel<true, 1><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-  else raster_forward_kernel<false, 1><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-  return check_launch("raster_forward_kernel");
+  return launch_forward(A, st);
 }
 
 extern "C" int lasr_b200_raster_backward(const float* faces, const float* textures, const float* soft_colors,
@@ -846,20 +1113,12 @@ extern "C" int lasr_b200_render_forward(const float* verts, const int32_t* tri, 
   cudaStream_t st = (cudaStream_t)stream;
   const long long nf = (long long)N * F;
   const long long nthreads = nf > S ? nf : S;
-  if (cudaMemsetAsync(A.frame_window, 0x7f, (size_t)N * 4 * sizeof(int), st) != cudaSuccess)
+  if (cudaMemsetAsync(A.frame_window, 0x7f, (size_t)N * 4 * sizeof(int), st) != cudaSuccess ||
+      (A.tile_count && cudaMemsetAsync(A.tile_count, 0, (size_t)N * num_tiles(S) * sizeof(int), st) != cudaSuccess))
     return fail("render_forward: memset failed");
   raster_setup_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(A, 1);
   if (check_launch("raster_setup_kernel")) return 1;
-  const int tiles = ((S + kTileW - 1) / kTileW) * ((S + kTileH - 1) / kTileH);
-  dim3 grid(tiles, N);
-  int chunk = ((F + kFwdThreads - 1) / kFwdThreads) * kFwdThreads;   // a multiple of 32 faces per warp
-  if (chunk > kMaxScanChunk) chunk = (kMaxScanChunk / kFwdThreads) * kFwdThreads;
-  const size_t smem = (size_t)chunk * sizeof(int);
-  if (A.K == 3) raster_forward_kernel<true, 3><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-  else if (A.K == 2) raster_forward_kernel<true, 2><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-  else if (is_fast(A)) raster_forward_kernel<true, 1><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-  else raster_forward_kernel<false, 1><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-  return check_launch("raster_forward_kernel");
+  return launch_forward(A, st);
 }
 
 extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri, const float* vcolors,

@@ -7,6 +7,7 @@ Three references, in order of authority:
 Tolerance (north star): RGBA 1e-4 relative, vertex gradients 1e-3 -- with zero outlier pixels."""
 import glob
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -18,6 +19,7 @@ import parity
 pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -399,3 +401,28 @@ def test_colour_sets_reject_other_configurations(srf):
     with pytest.raises(RuntimeError):
         srf.render_indexed(verts, torch.rand(4, 1, len(v), 3, device=dev), tri, image_size=32,
                            background_color=[0] * 12)
+
+
+def test_dispatch_order_does_not_change_a_single_value(tmp_path):
+    """The forward starts its tiles heaviest-first once the launch is big enough (raster_order_kernel) and from the
+    image centre outwards otherwise; both only permute independent CTAs.  Force each through the environment in a
+    fresh process and compare images and gradients bit for bit."""
+    import subprocess
+    script = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
+        "import cases\n"
+        "import lasr_b200.soft_renderer as sr\n"
+        "c = cases.lasr_case('spot', 3, 128)\n"
+        "fv = torch.from_numpy(c['face_vertices']).cuda().requires_grad_(True)\n"
+        "tex = torch.from_numpy(c['textures']).cuda().requires_grad_(True)\n"
+        "img = sr.functional.soft_rasterize(fv, tex, **c['settings'])\n"
+        "img.backward(torch.from_numpy(c['grad_soft_colors']).cuda())\n"
+        "np.savez(sys.argv[1], img=img.detach().cpu().numpy(), gf=fv.grad.cpu().numpy(), gt=tex.grad.cpu().numpy())\n")
+    outs = []
+    for mode in ("0", "1"):
+        out = str(tmp_path / f"lpt{mode}.npz")
+        subprocess.check_call([sys.executable, "-c", script, out], env=dict(os.environ, LASR_B200_FWD_LPT=mode))
+        outs.append(np.load(out))
+    for k in ("img", "gf", "gt"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
