@@ -362,6 +362,27 @@ def extras_microbench(device, peak_gbs, iters=20):
                            "backward_frac_of_hbm_peak": loss_bwd_bytes / t_lb / 1e6 / peak_gbs,
                            "note": "sums + reduce + finalize kernels forward; coefficient + per-pixel kernels backward"}
     out["hot_path"] = hot_path_microbench(device)
+    # dataloader -> device staging: 16 pairs of 480x854 frames -> 256^2, inputs resident
+    from lasr_b200.dataloader.staging import stage_pairs
+    P, Hh, Ww = 16, 480, 854
+    frs = torch.randint(0, 256, (P, 2, Hh, Ww, 3), generator=g, dtype=torch.uint8).to(device)
+    yy, xx = torch.meshgrid(torch.arange(Hh), torch.arange(Ww), indexing="ij")
+    mks = torch.stack([torch.stack([((((xx - 300 - 20 * p - 9 * q) / 140.0) ** 2 + ((yy - 230) / 120.0) ** 2) < 1).to(torch.uint8) * 255
+                                    for q in range(2)]) for p in range(P)]).to(device)
+    fls, ocs = torch.randn(P, 2, Hh, Ww, 3, generator=g).to(device), (torch.rand(P, 2, Hh, Ww, generator=g) * 20).to(device)
+    t_st = timeit(lambda: stage_pairs(frs, mks, fls, ocs, S))
+    bx = stage_pairs(frs, mks, fls, ocs, S)["boxes"].cpu().numpy().reshape(-1, 4)
+    crop_px = sum(min(2 * int(b[2]), Ww) * min(2 * int(b[2]), Hh) for b in bx)
+    st_bytes = 2 * P * Hh * Ww + 3 * int(bx[:, 3].sum()) + crop_px * 20 + 2 * P * S * S * 32
+    out["staging"] = {"shape": f"{P} pairs of {Hh}x{Ww} -> {S}^2", "ms": t_st, "GBps": st_bytes / t_st / 1e6,
+                      "frac_of_hbm_peak": st_bytes / t_st / 1e6 / peak_gbs,
+                      "bytes": "masks + masked frame bytes + crop windows x 20 B + outputs x 32 B (compulsory traffic)"}
+    from lasr_b200.chamfer3D import dist_chamfer_3D as C
+    cham = C.chamfer_3DDist()
+    pts = torch.from_numpy(v)[None].to(device)
+    t_ch = timeit(lambda: cham(pts, pts * torch.tensor([-1.0, 1.0, 1.0], device=device)))
+    out["chamfer"] = {"shape": f"B=1 n=m={V} (nnutils/mesh_net.py:474-477)", "ms": t_ch,
+                      "pairs_per_s": 2.0 * V * V / t_ch * 1e3, "note": "launch / host bound at this size"}
     return out
 
 

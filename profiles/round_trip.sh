@@ -21,6 +21,8 @@ python profiles/hotpath_timing.py 1 32 graph >> $OUT/hotpath.log 2>&1
 grep hotpath $OUT/hotpath.log
 python profiles/multi_set_timing.py > $OUT/multi_set.log 2>&1; cat $OUT/multi_set.log
 python profiles/regularizer_timing.py 64 > $OUT/regularizers.log 2>&1; cat $OUT/regularizers.log
+python profiles/staging_timing.py 16 20 2>&1 | grep staging | tee $OUT/staging.log
+python profiles/aux_timing.py 2>&1 | grep chamfer | tee $OUT/chamfer.log
 # profiler passes (numbers printed under ncu are never bench values)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 3 > $OUT/ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"raster_forward|raster_backward" -s 6 -c 2 -o $OUT/raster python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 3 > $OUT/ncu_full.log 2>&1
