@@ -45,19 +45,6 @@ constexpr int kFwdWarps = 2 * (kTileH / 4);     // each warp owns an 8x4 pixel f
 #ifndef LASR_FWD_LPT                // dispatch forward tiles heaviest-first (longest-processing-time order)
 #define LASR_FWD_LPT 1
 #endif
-#ifndef LASR_BINNING                // two-level binning: 64x64-pixel bins built once per frame, tiles scan their bin
-#define LASR_BINNING 0
-#endif
-constexpr int kBin = 64;            // bin edge in pixels; a multiple of both tile edges
-static_assert(kBin % kTileW == 0 && kBin % kTileH == 0, "tiles must nest in bins");
-#ifndef LASR_DYN_TILE_W             // tile of the footprint-claiming forward variant (0: disabled)
-#define LASR_DYN_TILE_W 0
-#endif
-#ifndef LASR_DYN_TILE_H
-#define LASR_DYN_TILE_H 16
-#endif
-constexpr int kDynTileW = LASR_DYN_TILE_W > 0 ? LASR_DYN_TILE_W : 16;
-constexpr int kDynTileH = LASR_DYN_TILE_H;
 constexpr int kFwdThreads = 32 * kFwdWarps;
 #ifndef LASR_SCAN_UNROLL            // window loads kept in flight per thread in the tile scan
 #define LASR_SCAN_UNROLL 2
@@ -87,9 +74,6 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #endif
 #ifndef LASR_FTZ_MUFU_BWD           // ... but not in the backward (measured slower)
 #define LASR_FTZ_MUFU_BWD 0
-#endif
-#ifndef LASR_BWD_PREFETCH           // prefetch a pixel's planes to L1 before the fragment math
-#define LASR_BWD_PREFETCH 0
 #endif
 #ifndef LASR_BWD_INDEX32            // 32-bit per-frame plane offsets in the backward's pixel loop
 #define LASR_BWD_INDEX32 1
@@ -145,62 +129,6 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RasterArgs A, int wit
   if (A.K == 1) store_record<1>(A.face_record + i * rec_words(1), g, vertex_tex ? tex9 : nullptr);
   else if (A.K == 2) store_record<2>(A.face_record + i * rec_words(2), g, tex9);
   else store_record<3>(A.face_record + i * rec_words(3), g, tex9);
-}
-
-// ---------------------------------------------------------------------------------------------
-// binning: one CTA per (64x64-pixel bin, frame) compacts, in ascending face order, the faces whose pixel
-// window reaches the bin, together with the window clipped to the bin.  A 16x16 tile then scans the few
-// hundred entries of its bin instead of all F windows (16 bins x F reads per frame instead of 256 tiles x F:
-// the tile scan was 8 % of the forward's instructions and 11 % of its stall samples).  Two passes over the
-// windows (count, then write at the warp's offset) keep the order without atomics.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) raster_bin_kernel(RasterArgs A) {
-  __shared__ int s_cnt[8];
-  const int n = blockIdx.y, bin = blockIdx.x;
-  const int bx = bin % A.bins_x, by = bin / A.bins_x;            // by counts row blocks from the top
-  const int S = A.S, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int x0 = bx * kBin, x1 = x0 + kBin - 1;                   // x index range
-  const int y1 = S - 1 - by * kBin, y0 = y1 - (kBin - 1);         // y index range (index = S-1-row), may start < 0
-  const int bins = A.bins_x * ((S + kBin - 1) / kBin);
-  int* count = A.bin_count + (long long)n * bins + bin;
-  const int4 fwin = *reinterpret_cast<const int4*>(A.frame_window + 4 * n);
-  if (!(x1 >= fwin.x && x0 <= -fwin.y && y1 >= fwin.z && y0 <= -fwin.w)) {   // no face reaches this bin
-    if (threadIdx.x == 0) *count = 0;
-    return;
-  }
-  const uint2* win = A.face_window + (long long)n * A.F;
-  uint2* out = A.bin_entries + ((long long)n * bins + bin) * A.F;
-  const int per_warp = ((A.F + 8 * 32 - 1) / (8 * 32)) * 32;      // faces per warp, a multiple of 32
-  const int f0 = warp * per_warp;
-  int offset = 0;
-  for (int pass = 0; pass < 2; ++pass) {
-    int cnt = 0;
-    for (int it = 0; it < per_warp; it += 32) {
-      const int f = f0 + it + lane;
-      bool hit = false;
-      uint2 wv = make_uint2(0, 0);
-      if (f < A.F) {
-        wv = win[f];
-        const int xlo = wv.x & 0xffff, xhi = wv.x >> 16, ylo = wv.y & 0xffff, yhi = wv.y >> 16;
-        hit = xlo <= x1 && xhi >= x0 && ylo <= y1 && yhi >= y0 && xlo <= xhi;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (pass == 1 && hit) {
-        const int xlo = wv.x & 0xffff, xhi = wv.x >> 16, ylo = wv.y & 0xffff, yhi = wv.y >> 16;
-        const unsigned packed = (unsigned)max(xlo - x0, 0) | ((unsigned)min(xhi - x0, kBin - 1) << 8) |
-                                ((unsigned)max(ylo - y0, 0) << 16) | ((unsigned)min(yhi - y0, kBin - 1) << 24);
-        out[offset + cnt + __popc(m & ((1u << lane) - 1))] = make_uint2((unsigned)f, packed);
-      }
-      cnt += __popc(m);
-    }
-    if (pass == 0) {
-      if (lane == 0) s_cnt[warp] = cnt;
-      __syncthreads();
-      int total = 0;
-      for (int w = 0; w < 8; ++w) { if (w == warp) offset = total; total += s_cnt[w]; }
-      if (threadIdx.x == 0) *count = total;
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -316,29 +244,23 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConst
   }
 }
 
-// kDyn = false: one CTA per 16 x kTileH tile, warp w owns footprint w for the whole kernel; the face list may be
-//               built in several rounds (F > kMaxScanChunk), the per-pixel state living in registers across them.
-// kDyn = true:  one CTA per kDynTileW x kDynTileH tile holding kDynFp > 8 footprints; the list is built once
-//               (F <= kMaxScanChunk) and the warps CLAIM footprints from a shared counter until none is left.
-//               The footprints of a tile differ widely in work (silhouette edge vs. interior vs. background):
-//               with static ownership a CTA keeps its registers until its slowest warp is done (ncu: 37 %
-//               achieved occupancy of 50 % theoretical); claiming evens that out and halves the scans per pixel.
-template <bool kFast, int K, bool kDyn>
+// One CTA per 16 x kTileH tile, warp w owns footprint w for the whole kernel; the face list may be built in several
+// rounds (F > kMaxScanChunk), the per-pixel state living in registers across them.
+template <bool kFast, int K>
 __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LASR_FWD_MIN_BLOCKS_MULTI) raster_forward_kernel(RasterArgs A, int chunk) {
   constexpr int kMode = kFast ? (LASR_FTZ_MUFU_FWD ? 2 : 1) : 0;
   constexpr int kRecWords = rec_words(K);
   constexpr int P = 3 * K + 1;      // image planes per frame: K colour sets, then alpha
-  constexpr int kTW = kDyn ? kDynTileW : kTileW, kTH = kDyn ? kDynTileH : kTileH;
-  constexpr int kFpX = kTW / 8, kNumFp = kFpX * (kTH / 4);
+  constexpr int kTW = kTileW, kTH = kTileH;
+  constexpr int kFpX = kTW / 8;
   extern __shared__ int s_list[];   // [chunk] face indices, 8 per-warp segments of chunk/8
   __shared__ int s_cnt[kFwdWarps];
-  __shared__ int s_next;
   const int wseg = chunk / kFwdWarps;
 
   const int S = A.S;
   const int tiles_x = (S + kTW - 1) / kTW, tiles_y = (S + kTH - 1) / kTH;
   int n, tile_x, tile_y;
-  if (A.tile_order && !kDyn) {   // heaviest tiles first (raster_order_kernel)
+  if (A.tile_order) {   // heaviest tiles first (raster_order_kernel)
     const int item = A.tile_order[blockIdx.x];
     n = item / (tiles_x * tiles_y);
     tile_x = (item % (tiles_x * tiles_y)) % tiles_x;
@@ -381,38 +303,19 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
   // tiles that no face window of this frame reaches skip the scan and go straight to the epilogue
   const int4 fwin = *reinterpret_cast<const int4*>(A.frame_window + 4 * n);
   const bool tile_live = tx1 >= fwin.x && tx0 <= -fwin.y && ty1 >= fwin.z && ty0 <= -fwin.w;
-  if (kDyn && tid == 0) s_next = kFwdWarps;
 
-  // (1) scan: warp w owns candidates [base + w*wseg, base + (w+1)*wseg) and compacts hits in order.  The
-  //     candidates are the entries of the tile's 64x64 bin (ascending face id, window relative to the bin) or,
-  //     without binning, all F face windows.
-  const bool binned = A.bins_x > 0;
-  const int bins = binned ? A.bins_x * ((S + kBin - 1) / kBin) : 0;
-  const int bin = binned ? (tile_y * kTH / kBin) * A.bins_x + tile_x * kTW / kBin : 0;
-  const uint2* bin_list = binned ? A.bin_entries + ((long long)n * bins + bin) * A.F : nullptr;
-  const int n_cand = binned ? A.bin_count[(long long)n * bins + bin] : A.F;
-  // tile window relative to the bin origin (x index, y index = S-1-row)
-  const int bx0 = (tile_x * kTW / kBin) * kBin, by0 = S - 1 - (tile_y * kTH / kBin) * kBin - (kBin - 1);
-  const int rx0 = tx0 - bx0, rx1 = tx1 - bx0, ry0 = ty0 - by0, ry1 = ty1 - by0;
+  // (1) scan: warp w owns faces [base + w*wseg, base + (w+1)*wseg) and compacts hits in order
   auto scan = [&](int base) {
     int cnt = 0;
     const int seg0 = base + warp * wseg;
 #pragma unroll kScanUnroll
     for (int it = 0; it < wseg; it += 32) {
-      const int j = seg0 + it + lane;
+      const int f = seg0 + it + lane;
       bool hit = false;
-      int f = j;
-      if (j < n_cand) {
-        if (binned) {
-          const uint2 e = bin_list[j];
-          f = (int)e.x;
-          const int xlo = e.y & 255, xhi = (e.y >> 8) & 255, ylo = (e.y >> 16) & 255, yhi = e.y >> 24;
-          hit = xlo <= rx1 && xhi >= rx0 && ylo <= ry1 && yhi >= ry0;
-        } else {
-          const uint2 wv = win[j];
-          const int xlo = wv.x & 0xffff, xhi = wv.x >> 16, ylo = wv.y & 0xffff, yhi = wv.y >> 16;
-          hit = xlo <= tx1 && xhi >= tx0 && ylo <= ty1 && yhi >= ty0 && xlo <= xhi;
-        }
+      if (f < A.F) {
+        const uint2 wv = win[f];
+        const int xlo = wv.x & 0xffff, xhi = wv.x >> 16, ylo = wv.y & 0xffff, yhi = wv.y >> 16;
+        hit = xlo <= tx1 && xhi >= tx0 && ylo <= ty1 && yhi >= ty0 && xlo <= xhi;
       }
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (hit) s_list[warp * wseg + cnt + __popc(m & ((1u << lane) - 1))] = f;
@@ -520,34 +423,16 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
     }
   };
 
-  if (!kDyn) {
-    const Footprint q = place(warp);
-    PixelState<K> st;
-    init_state(q, st);
-    for (int base = 0; tile_live && base < n_cand; base += chunk) {
-      scan(base);
-      __syncthreads();
-      walk(q, st);
-      if (base + chunk < n_cand) __syncthreads();  // the list is reused by the next round
-    }
-    finish(q, st);
-  } else {
-    if (tile_live) scan(0);
-    else if (lane == 0) s_cnt[warp] = 0;
+  const Footprint q = place(warp);
+  PixelState<K> st;
+  init_state(q, st);
+  for (int base = 0; tile_live && base < A.F; base += chunk) {
+    scan(base);
     __syncthreads();
-    int fp = warp;
-    while (fp < kNumFp) {
-      const Footprint q = place(fp);
-      if (__any_sync(0xffffffffu, q.valid)) {
-        PixelState<K> st;
-        init_state(q, st);
-        walk(q, st);
-        finish(q, st);
-      }
-      if (lane == 0) fp = atomicAdd(&s_next, 1);
-      fp = __shfl_sync(0xffffffffu, fp, 0);
-    }
+    walk(q, st);
+    if (base + chunk < A.F) __syncthreads();  // the list is reused by the next round
   }
+  finish(q, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -655,17 +540,6 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
       const float yp = A.coords[yi];
       if (xp > g.hix || xp < g.lox || yp > g.hiy || yp < g.loy) continue;
       const index_t pn = (index_t)(S - 1 - yi) * (index_t)S + (index_t)xi;
-#if LASR_BWD_PREFETCH
-      // the pixel's image / gradient planes are needed ~150 instructions from now: start them towards L1
-      if (kFast) {
-#pragma unroll
-        for (int k = 3 * KF; k < P; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(gs + PLANE(k)));
-#pragma unroll
-        for (int k = 3 * KF; k < P; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc + PLANE(k)));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(ag + PLANE(0)));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(ag + PLANE(1)));
-      }
-#endif
       Fragment fr;
       if (!soft_fragment<kMode>(A, g, xp, yp, thr, fr)) continue;
       // alpha term (.cu:582-593); for 'hard' alpha the reference still adds the raw upstream
@@ -856,7 +730,6 @@ static bool use_lpt(int N, int F) {
 }
 
 static size_t num_tiles(int S) { return (size_t)((S + kTileW - 1) / kTileW) * (size_t)((S + kTileH - 1) / kTileH); }
-static size_t num_bins(int S) { const size_t b = (size_t)((S + kBin - 1) / kBin); return b * b; }
 
 static size_t raster_ws_bytes(int N, int F, int S, int K) {
   if (N <= 0 || F <= 0 || S <= 0 || K < 1 || K > kMaxSets) return 0;
@@ -864,7 +737,6 @@ static size_t raster_ws_bytes(int N, int F, int S, int K) {
   return align256(nf * sizeof(uint2)) + align256((size_t)S * sizeof(float)) + align256((size_t)N * 4 * sizeof(int)) +
          align256((size_t)(kBigListCap + 1) * sizeof(int)) +
          (LASR_FWD_LPT ? 2 * align256((size_t)N * num_tiles(S) * sizeof(int)) : 0) +
-         (LASR_BINNING ? align256((size_t)N * num_bins(S) * sizeof(int)) + align256(nf * num_bins(S) * sizeof(uint2)) : 0) +
          align256(nf * sizeof(float4)) +
          align256(nf * rec_words(K) * sizeof(float));
 }
@@ -900,11 +772,6 @@ static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, flo
     int* to = reinterpret_cast<int*>(p);         p += align256((size_t)N * num_tiles(S) * sizeof(int));
     if (use_lpt(N, F)) { A.tile_count = tc; A.tile_order = to; }
   }
-  if (LASR_BINNING) {
-    A.bin_count = reinterpret_cast<int*>(p);     p += align256((size_t)N * num_bins(S) * sizeof(int));
-    A.bin_entries = reinterpret_cast<uint2*>(p); p += align256(nf * num_bins(S) * sizeof(uint2));
-    A.bins_x = (S + kBin - 1) / kBin;
-  }
   A.face_border = reinterpret_cast<float4*>(p);  p += align256(nf * sizeof(float4));
   A.face_record = reinterpret_cast<float*>(p);
   return 0;
@@ -915,34 +782,19 @@ static bool is_fast(const RasterArgs& A);
 // forward launch: the footprint-claiming variant whenever the face list fits one scan round
 static int launch_forward(const RasterArgs& A, cudaStream_t st) {
   const int S = A.S, F = A.F, N = A.N;
+  const int tiles = (int)num_tiles(S);
   if (A.tile_order) {
-    raster_order_kernel<<<1, 1024, 0, st>>>(A.tile_count, A.tile_order, (int)(num_tiles(S) * N));
+    raster_order_kernel<<<1, 1024, 0, st>>>(A.tile_count, A.tile_order, tiles * N);
     if (check_launch("raster_order_kernel")) return 1;
   }
-  if (A.bins_x > 0) {
-    dim3 bgrid((unsigned)num_bins(S), N);
-    raster_bin_kernel<<<bgrid, 256, 0, st>>>(A);
-    if (check_launch("raster_bin_kernel")) return 1;
-  }
   int chunk = ((F + kFwdThreads - 1) / kFwdThreads) * kFwdThreads;   // a multiple of 32 faces per warp
-  const bool dyn = LASR_DYN_TILE_W > 0 && chunk <= kMaxScanChunk && A.bins_x == 0;
   if (chunk > kMaxScanChunk) chunk = (kMaxScanChunk / kFwdThreads) * kFwdThreads;
   const size_t smem = (size_t)chunk * sizeof(int);
-  if (dyn) {
-    const int tiles = ((S + kDynTileW - 1) / kDynTileW) * ((S + kDynTileH - 1) / kDynTileH);
-    dim3 grid((unsigned)((long long)tiles * N));
-    if (A.K == 3) raster_forward_kernel<true, 3, true><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-    else if (A.K == 2) raster_forward_kernel<true, 2, true><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-    else if (is_fast(A)) raster_forward_kernel<true, 1, true><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-    else raster_forward_kernel<false, 1, true><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-  } else {
-    const int tiles = ((S + kTileW - 1) / kTileW) * ((S + kTileH - 1) / kTileH);
-    dim3 grid((unsigned)((long long)tiles * N));
-    if (A.K == 3) raster_forward_kernel<true, 3, false><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-    else if (A.K == 2) raster_forward_kernel<true, 2, false><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-    else if (is_fast(A)) raster_forward_kernel<true, 1, false><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-    else raster_forward_kernel<false, 1, false><<<grid, kFwdThreads, smem, st>>>(A, chunk);
-  }
+  const unsigned grid = (unsigned)((long long)tiles * N);
+  if (A.K == 3) raster_forward_kernel<true, 3><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  else if (A.K == 2) raster_forward_kernel<true, 2><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  else if (is_fast(A)) raster_forward_kernel<true, 1><<<grid, kFwdThreads, smem, st>>>(A, chunk);
+  else raster_forward_kernel<false, 1><<<grid, kFwdThreads, smem, st>>>(A, chunk);
   return check_launch("raster_forward_kernel");
 }
 

@@ -57,9 +57,6 @@ struct RasterArgs {
   int* frame_window;         // [N][4] (x_lo, -x_hi, y_lo, -y_hi) of the union of face windows (atomicMin)
   int* tile_count;           // [N][tiles] faces whose window reaches each forward tile (work estimate)
   int* tile_order;           // [N*tiles] (frame * tiles + tile), heaviest first: the forward's dispatch order
-  uint2* bin_entries;        // [N][bins][F] (face id, window clipped to the 64x64 bin, 4 x 8 bits), ascending face id
-  int* bin_count;            // [N][bins]
-  int bins_x;                // bins per image row (0: binning disabled, tiles scan all faces)
   const float* near_far_dev; // optional {near, far} on device
   // indexed ("fused") input mode: faces/textures are gathered on the fly from per-vertex arrays
   const float* verts;        // [N,V,3] clip-space vertices   (null: direct mode, use `faces`)

@@ -64,11 +64,14 @@ class DeviceStager:
         self._dev = {k: torch.empty_like(v, device=self.device) for k, v in self._host.items()}
         self._stream = torch.cuda.Stream(device=self.device)
         self._done = torch.cuda.Event()
+        self._pending = False
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self._host.values())
 
     def submit(self, raw):
         """raw: dict of numpy / CPU tensors with the keys of ``collate_raw``.  Starts upload + staging on the side
         stream and returns immediately; ``result()`` makes the current stream wait for it."""
+        if self._pending:          # the previous upload may still be reading the pinned buffers
+            self._done.synchronize()
         for k, buf in self._host.items():
             buf.copy_(torch.as_tensor(np.ascontiguousarray(raw[k])) if not torch.is_tensor(raw[k]) else raw[k])
         self._stream.wait_stream(torch.cuda.current_stream(self.device))     # buffers of the previous batch are free
@@ -78,6 +81,7 @@ class DeviceStager:
             self._out = stage_pairs(self._dev["frames_bgr"], self._dev["masks"], self._dev["flows"], self._dev["occs"],
                                     self.S)
             self._done.record(self._stream)
+        self._pending = True
         return self
 
     def result(self):
