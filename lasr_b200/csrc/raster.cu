@@ -142,9 +142,19 @@ constexpr int kOrderBuckets = 1024;
 __global__ void __launch_bounds__(1024) raster_order_kernel(const int* __restrict__ count, int* __restrict__ order,
                                                             int items) {
   __shared__ int s_hist[kOrderBuckets];
+  __shared__ int s_zero;                        // background tiles (count 0, half of all items): one ballot-aggregated
+                                                // atomic per warp instead of thousands on the same bucket
+  const int lane = threadIdx.x & 31;
   for (int b = threadIdx.x; b < kOrderBuckets; b += blockDim.x) s_hist[b] = 0;
+  if (threadIdx.x == 0) s_zero = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < items; i += blockDim.x) atomicAdd(&s_hist[min(count[i], kOrderBuckets - 1)], 1);
+  const int padded = (items + 31) & ~31;        // whole warps stay in the loop together (ballot)
+  for (int i = threadIdx.x; i < padded; i += blockDim.x) {
+    const int c = i < items ? count[i] : -1;
+    const unsigned z = __ballot_sync(0xffffffffu, c == 0);
+    if (c > 0) atomicAdd(&s_hist[min(c, kOrderBuckets - 1)], 1);
+    else if (z && lane == __ffs(z) - 1) atomicAdd(&s_zero, __popc(z));
+  }
   __syncthreads();
   if (threadIdx.x < 32) {   // exclusive prefix over buckets in DESCENDING count order, one warp
     int carry = 0;
@@ -160,10 +170,22 @@ __global__ void __launch_bounds__(1024) raster_order_kernel(const int* __restric
       s_hist[b] = carry + incl - h;
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (threadIdx.x == 0) s_zero = carry;       // the empty tiles follow all the others
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < items; i += blockDim.x)
-    order[atomicAdd(&s_hist[min(count[i], kOrderBuckets - 1)], 1)] = i;
+  for (int i = threadIdx.x; i < padded; i += blockDim.x) {
+    const int c = i < items ? count[i] : -1;
+    const unsigned z = __ballot_sync(0xffffffffu, c == 0);
+    if (c > 0) {
+      order[atomicAdd(&s_hist[min(c, kOrderBuckets - 1)], 1)] = i;
+    } else if (c == 0) {                        // exactly the lanes of z
+      const int leader = __ffs(z) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&s_zero, __popc(z));
+      base = __shfl_sync(z, base, leader);
+      order[base + __popc(z & ((1u << lane) - 1))] = i;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
