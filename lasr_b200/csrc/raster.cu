@@ -60,8 +60,11 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #ifndef LASR_FWD_MIN_BLOCKS_MULTI   // several colour sets per pass carry more live state per pixel
 #define LASR_FWD_MIN_BLOCKS_MULTI 3
 #endif
-#ifndef LASR_BWD_MIN_BLOCKS_MULTI   // 168 registers: the multi-set backward spills at 128 (K = 3: 2.05 -> 1.95 ms)
-#define LASR_BWD_MIN_BLOCKS_MULTI 3
+#ifndef LASR_BWD_MIN_BLOCKS_MULTI   // three live colour sets (36 accumulators): 168 registers instead of spilling at 128
+#define LASR_BWD_MIN_BLOCKS_MULTI 3  // (K = 3 backward 2.05 -> 1.95 ms)
+#endif
+#ifndef LASR_BWD_MIN_BLOCKS_LIVE2   // two live sets (LASR's hot path: K = 3 with the frame's own positions detached):
+#define LASR_BWD_MIN_BLOCKS_LIVE2 4 // 128 registers and a few spilled words beat 168 registers at 12 warps per SM
 #endif
 #ifndef LASR_PREFETCH_REC           // warm L1 with a face's record when it passes the warp cull
 #define LASR_PREFETCH_REC 1
@@ -74,6 +77,9 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #endif
 #ifndef LASR_FTZ_MUFU_BWD           // ... but not in the backward (measured slower)
 #define LASR_FTZ_MUFU_BWD 0
+#endif
+#ifndef LASR_BWD_INDEX32_MULTI      // ... and in the multi-set backward
+#define LASR_BWD_INDEX32_MULTI 0
 #endif
 #ifndef LASR_BWD_INDEX32            // 32-bit per-frame plane offsets in the backward's pixel loop
 #define LASR_BWD_INDEX32 1
@@ -472,7 +478,7 @@ template <bool k32> struct PlaneIndex { typedef long long type; };
 template <> struct PlaneIndex<true> { typedef unsigned type; };
 
 template <bool kFast, bool kBig, int K, int KF>
-__global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K == 1 ? LASR_BWD_MIN_BLOCKS : LASR_BWD_MIN_BLOCKS_MULTI)) raster_backward_kernel(RasterArgs A) {
+__global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K == 1 ? LASR_BWD_MIN_BLOCKS : (K - KF >= 3 ? LASR_BWD_MIN_BLOCKS_MULTI : LASR_BWD_MIN_BLOCKS_LIVE2))) raster_backward_kernel(RasterArgs A) {
   constexpr int kMode = kFast ? (LASR_FTZ_MUFU_BWD ? 2 : 1) : 0;   // arithmetic mode, see raster_common.cuh
   constexpr int kRecWords = rec_words(K);
   constexpr int P = 3 * K + 1;          // image planes per frame
@@ -547,7 +553,7 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
     // bases -> one IMAD.WIDE per load instead of an IADD3/IADD3.X/LEA/LEA.HI.X chain (the ten plane loads of
     // a pixel were ~40 integer instructions per sweep; backward 1.208 -> 1.168 ms on config A).  With several
     // colour sets the 64-bit form schedules better (measured: 2.06 vs 2.12 ms at K = 3), so it is kept there.
-    constexpr bool kIdx32 = LASR_BWD_INDEX32 != 0 && K == 1;
+    constexpr bool kIdx32 = K == 1 ? LASR_BWD_INDEX32 != 0 : LASR_BWD_INDEX32_MULTI != 0;
     typedef typename PlaneIndex<kIdx32>::type index_t;
     const index_t SSx = (index_t)S * (index_t)S;
     if (kIdx32) asm volatile("" : "+l"(sc), "+l"(ag), "+l"(gs));
