@@ -51,37 +51,47 @@ def check_boxes(boxes):
 
 
 class DeviceStager:
-    """Pinned host buffers + side-stream upload + device preprocessing for batches of `pairs` items of HxW frames."""
+    """Pinned host buffers + side-stream upload + device preprocessing for batches of `pairs` items of HxW frames.
+
+    Two pinned slots alternate, so the host can fill slot i+1 while the copy engine is still reading slot i; a slot is
+    refilled only after the upload that last used it has completed (its event)."""
 
     def __init__(self, pairs, height, width, img_size, device="cuda"):
         self.P, self.H, self.W, self.S = int(pairs), int(height), int(width), int(img_size)
         self.device = torch.device(device)
         shp = (self.P, 2, self.H, self.W)
-        self._host = {"frames_bgr": torch.empty(shp + (3,), dtype=torch.uint8).pin_memory(),
+        mk = lambda: {"frames_bgr": torch.empty(shp + (3,), dtype=torch.uint8).pin_memory(),
                       "masks": torch.empty(shp, dtype=torch.uint8).pin_memory(),
                       "flows": torch.empty(shp + (3,), dtype=torch.float32).pin_memory(),
                       "occs": torch.empty(shp, dtype=torch.float32).pin_memory()}
-        self._dev = {k: torch.empty_like(v, device=self.device) for k, v in self._host.items()}
+        self._host = [mk(), mk()]
+        self._uploaded = [None, None]            # event recorded after the H2D copies of each slot
+        self._slot = 0
+        self._dev = {k: torch.empty_like(v, device=self.device) for k, v in self._host[0].items()}
         self._stream = torch.cuda.Stream(device=self.device)
         self._done = torch.cuda.Event()
-        self._pending = False
-        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self._host.values())
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self._host[0].values())
 
     def submit(self, raw):
         """raw: dict of numpy / CPU tensors with the keys of ``collate_raw``.  Starts upload + staging on the side
         stream and returns immediately; ``result()`` makes the current stream wait for it."""
-        if self._pending:          # the previous upload may still be reading the pinned buffers
-            self._done.synchronize()
-        for k, buf in self._host.items():
+        slot = self._slot
+        self._slot ^= 1
+        if self._uploaded[slot] is not None:       # the copy engine may still be reading this slot
+            self._uploaded[slot].synchronize()
+        host = self._host[slot]
+        for k, buf in host.items():
             buf.copy_(torch.as_tensor(np.ascontiguousarray(raw[k])) if not torch.is_tensor(raw[k]) else raw[k])
-        self._stream.wait_stream(torch.cuda.current_stream(self.device))     # buffers of the previous batch are free
+        self._stream.wait_stream(torch.cuda.current_stream(self.device))     # consumers of the previous outputs
         with torch.cuda.stream(self._stream):
-            for k, buf in self._host.items():
+            for k, buf in host.items():
                 self._dev[k].copy_(buf, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._stream)
+            self._uploaded[slot] = ev
             self._out = stage_pairs(self._dev["frames_bgr"], self._dev["masks"], self._dev["flows"], self._dev["occs"],
                                     self.S)
             self._done.record(self._stream)
-        self._pending = True
         return self
 
     def result(self):
