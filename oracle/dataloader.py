@@ -14,7 +14,8 @@ cv2's resize arithmetic is restated from its documented algorithm: ``scale = 1 /
 ``fx = float((dx + 0.5) * scale - 0.5)``, ``sx = floor(fx)``, ``fx -= sx``, clamped at both ends with weight 0,
 float32 weights, horizontal pass then vertical; nearest: ``sx = min(floor(dx * scale), src - 1)``.
 
-Parity status: pinned against the reference's own code run in the build container on a synthetic video
+Parity status: pinned against the reference's own code run in the build container on two synthetic videos -- one with
+the object inside the frame, one at the frame corner so that the crop's constant border is exercised
 (tests/golden/dataloader_ref.npz, tests/golden/make_dataloader_golden.py).
 """
 from __future__ import annotations
@@ -106,10 +107,12 @@ def preprocess_pair(bgr0, mask0, flow0, occ0, bgr1, mask1, flow1, occ1, S):
     return res
 
 
-def pair_inputs(g, item):
-    """Decoded inputs of dataset item `item` from the golden file's frame stacks (vidbase.py:53-94)."""
-    i0 = int(g["baselist"][item]); fwd = int(g["directlist"][item]) == 1
+def pair_inputs(g, item, pre=""):
+    """Decoded inputs of dataset item `item` of golden video `pre` ("" or "b_") from the golden file's frame
+    stacks (vidbase.py:53-94)."""
+    i0 = int(g[pre + "baselist"][item]); fwd = int(g[pre + "directlist"][item]) == 1
     i1 = i0 + 1 if fwd else i0 - 1
-    f0, o0 = (g["flow_fw"][i0], g["occ_fw"][i0]) if fwd else (g["flow_bw"][i0], g["occ_bw"][i0])
-    f1, o1 = (g["flow_bw"][i1], g["occ_bw"][i1]) if fwd else (g["flow_fw"][i1], g["occ_fw"][i1])
-    return (g["frames_bgr"][i0], g["masks"][i0], f0, o0, g["frames_bgr"][i1], g["masks"][i1], f1, o1)
+    G = lambda k: g[pre + k]
+    f0, o0 = (G("flow_fw")[i0], G("occ_fw")[i0]) if fwd else (G("flow_bw")[i0], G("occ_bw")[i0])
+    f1, o1 = (G("flow_bw")[i1], G("occ_bw")[i1]) if fwd else (G("flow_fw")[i1], G("occ_fw")[i1])
+    return (G("frames_bgr")[i0], G("masks")[i0], f0, o0, G("frames_bgr")[i1], G("masks")[i1], f1, o1)

@@ -36,15 +36,15 @@ def smooth(rng, shape, sigma):
     return cv2.GaussianBlur(rng.normal(size=shape).astype(np.float32), (0, 0), sigma)
 
 
-def synth_video(tmp, n_frames=3, H=96, W=136, seed=0):
+def synth_video(tmp, n_frames=3, H=96, W=136, seed=0, centre=(52, 40), step=(9, 4), axes=(24.0, 17.0)):
     import cv2
     rng = np.random.RandomState(seed)
     lists = dict(img=[], mask=[], fw=[], bw=[], cam=[])
     yy, xx = np.mgrid[0:H, 0:W]
     for t in range(n_frames):
         img = np.clip(127 + 60 * smooth(rng, (H, W, 3), 3.0) * 4, 0, 255).astype(np.uint8)
-        cx, cy = 52 + 9 * t, 40 + 4 * t
-        mask = ((((xx - cx) / (24.0 + 2 * t)) ** 2 + ((yy - cy) / (17.0 + t)) ** 2) < 1).astype(np.uint8) * 255
+        cx, cy = centre[0] + step[0] * t, centre[1] + step[1] * t
+        mask = ((((xx - cx) / (axes[0] + 2 * t)) ** 2 + ((yy - cy) / (axes[1] + t)) ** 2) < 1).astype(np.uint8) * 255
         p = dict(img=f"{tmp}/img-{t:05d}.png", mask=f"{tmp}/mask-{t:05d}.png", fw=f"{tmp}/flo-fw-{t:05d}.pfm",
                  bw=f"{tmp}/flo-bw-{t:05d}.pfm", cam=f"{tmp}/cam-{t:05d}.txt")
         cv2.imwrite(p["img"], img); cv2.imwrite(p["mask"], mask)
@@ -71,27 +71,31 @@ def main():
     from dataloader import vidbase
 
     out = {}
-    with tempfile.TemporaryDirectory() as tmp:
-        L = synth_video(tmp)
-        ds = vidbase.BaseDataset(types.SimpleNamespace(img_size=64))
-        ds.imglist, ds.masklist, ds.flowfwlist, ds.flowbwlist, ds.camlist = L["img"], L["mask"], L["fw"], L["bw"], L["cam"]
-        ds.dframe, ds.can_frame = 1, 0
-        ds.baselist = [0, 1, 1, 2]                  # forward pairs then backward pairs, as dataloader/vid.py builds them
-        ds.directlist = [1, 1, 0, 0]
-        ds.num_imgs = len(ds.baselist)
-        items = (0, 1, 3)
-        out["items"] = np.asarray(items); out["img_size"] = np.asarray(64)
-        out["baselist"] = np.asarray(ds.baselist); out["directlist"] = np.asarray(ds.directlist)
-        # decoded inputs, exactly as the reference decodes them
-        out["frames_bgr"] = np.stack([cv2.imread(p) for p in L["img"]])
-        out["masks"] = np.stack([cv2.imread(p, 0) for p in L["mask"]])
-        for d in ("fw", "bw"):
-            out[f"flow_{d}"] = np.stack([np.ascontiguousarray(readPFM(p)[0]) for p in L[d]])
-            out[f"occ_{d}"] = np.stack([np.ascontiguousarray(readPFM(p.replace("flo-", "occ-"))[0]) for p in L[d]])
-        for i in items:
-            elem = ds[i]
-            for k in ("img", "imgn", "mask", "flow", "flown", "occ", "occn", "cam", "camn", "pps", "shape", "id0", "id1"):
-                out[f"item{i}/{k}"] = np.asarray(elem[k])
+    # video "" : object well inside the frame; video "b_": object at the frame corner, so the square crop reaches
+    # outside the image and cv2.remap's constant border (complement colour / zeros) is exercised
+    videos = {"": dict(seed=0), "b_": dict(seed=1, H=80, W=120, centre=(22, 14), step=(-3, 2), axes=(26.0, 15.0))}
+    for pre, kw in videos.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            L = synth_video(tmp, **kw)
+            ds = vidbase.BaseDataset(types.SimpleNamespace(img_size=64))
+            ds.imglist, ds.masklist, ds.flowfwlist, ds.flowbwlist, ds.camlist = L["img"], L["mask"], L["fw"], L["bw"], L["cam"]
+            ds.dframe, ds.can_frame = 1, 0
+            ds.baselist = [0, 1, 1, 2]                  # forward pairs then backward pairs, as dataloader/vid.py builds them
+            ds.directlist = [1, 1, 0, 0]
+            ds.num_imgs = len(ds.baselist)
+            items = (0, 1, 3)
+            out[pre + "items"] = np.asarray(items); out[pre + "img_size"] = np.asarray(64)
+            out[pre + "baselist"] = np.asarray(ds.baselist); out[pre + "directlist"] = np.asarray(ds.directlist)
+            # decoded inputs, exactly as the reference decodes them
+            out[pre + "frames_bgr"] = np.stack([cv2.imread(p) for p in L["img"]])
+            out[pre + "masks"] = np.stack([cv2.imread(p, 0) for p in L["mask"]])
+            for d in ("fw", "bw"):
+                out[pre + f"flow_{d}"] = np.stack([np.ascontiguousarray(readPFM(p)[0]) for p in L[d]])
+                out[pre + f"occ_{d}"] = np.stack([np.ascontiguousarray(readPFM(p.replace("flo-", "occ-"))[0]) for p in L[d]])
+            for i in items:
+                elem = ds[i]
+                for k in ("img", "imgn", "mask", "flow", "flown", "occ", "occn", "cam", "camn", "pps", "shape", "id0", "id1"):
+                    out[pre + f"item{i}/{k}"] = np.asarray(elem[k])
     path = os.path.join(ROOT, "tests", "golden", "dataloader_ref.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

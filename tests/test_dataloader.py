@@ -18,6 +18,7 @@ from oracle import dataloader as OD  # noqa: E402
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "dataloader_ref.npz"))
 KEYS = ("img", "imgn", "mask", "flow", "flown", "occ", "occn", "cam", "camn", "pps")
 S = int(GOLD["img_size"])
+VIDEOS = ("", "b_")      # object inside the frame / at the frame corner (the crop reaches outside: constant border)
 
 
 def write_pfm(path, data):
@@ -30,16 +31,19 @@ def write_pfm(path, data):
 
 
 # ------------------------------------------------------------------------------------------------ CPU
-def test_oracle_reproduces_the_reference_dataloader():
-    for it in GOLD["items"]:
-        r = OD.preprocess_pair(*OD.pair_inputs(GOLD, int(it)), S)
+@pytest.mark.parametrize("pre", VIDEOS)
+def test_oracle_reproduces_the_reference_dataloader(pre):
+    if pre == "b_":
+        assert (GOLD["b_item0/pps"] < 0).any()          # the crop does leave the frame in this video
+    for it in GOLD[pre + "items"]:
+        r = OD.preprocess_pair(*OD.pair_inputs(GOLD, int(it), pre), S)
         for k in KEYS:
-            ref = GOLD[f"item{it}/{k}"]
+            ref = GOLD[f"{pre}item{it}/{k}"]
             assert r[k].shape == ref.shape, (it, k)
             if k in ("img", "imgn"):          # float64 image path: summation order of the masked mean
-                np.testing.assert_allclose(r[k], ref, rtol=0, atol=1e-15, err_msg=f"{it}/{k}")
+                np.testing.assert_allclose(r[k], ref, rtol=0, atol=1e-15, err_msg=f"{pre}{it}/{k}")
             else:                             # float32 flow / occlusion, masks, crop boxes: bit-exact
-                assert np.array_equal(r[k], ref), (it, k)
+                assert np.array_equal(r[k], ref), (pre, it, k)
 
 
 def test_oracle_resize_taps_are_cv2s():
@@ -101,25 +105,26 @@ def test_raw_dataset_decodes_what_the_reference_decodes(tmp_path):
     assert tuple(batch["frames_bgr"].shape) == (3, 2) + GOLD["frames_bgr"].shape[1:] and batch["flows"].dtype == torch.float32
 
 
-def _raw_batch(items):
-    ins = [OD.pair_inputs(GOLD, int(i)) for i in items]
+def _raw_batch(items, pre=""):
+    ins = [OD.pair_inputs(GOLD, int(i), pre) for i in items]
     st = lambda a, b: np.stack([np.stack([x[a], x[b]]) for x in ins])
     return st(0, 4), st(1, 5), st(2, 6).astype(np.float32), st(3, 7).astype(np.float32)
 
 
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
-def test_staging_kernels_match_the_reference_dataloader():
+@pytest.mark.parametrize("pre", VIDEOS)
+def test_staging_kernels_match_the_reference_dataloader(pre):
     from lasr_b200.dataloader import stage_pairs
     dev = torch.device("cuda", 0)
-    items = [int(i) for i in GOLD["items"]]
-    fr, mk, fl, oc = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in _raw_batch(items))
+    items = [int(i) for i in GOLD[pre + "items"]]
+    fr, mk, fl, oc = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in _raw_batch(items, pre))
     out = stage_pairs(fr, mk, fl, oc, S)
     torch.cuda.synchronize()
     for p, it in enumerate(items):
         for k in KEYS:
             got = out[k][p].cpu().numpy().astype(np.float64)
-            ref = GOLD[f"item{it}/{k}"].astype(np.float64)
+            ref = GOLD[f"{pre}item{it}/{k}"].astype(np.float64)
             assert got.shape == ref.shape, (it, k)
             if k in ("mask", "pps", "cam", "camn"):
                 np.testing.assert_allclose(got, ref, rtol=1e-7, atol=0, err_msg=f"{it}/{k}")      # exact up to f32 storage
@@ -129,7 +134,7 @@ def test_staging_kernels_match_the_reference_dataloader():
             else:                                                                                   # float32 pipeline vs float64 / float32
                 np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2e-6, err_msg=f"{it}/{k}")
         b = out["boxes"][p].cpu().numpy()
-        for slot, m in enumerate((OD.pair_inputs(GOLD, it)[1], OD.pair_inputs(GOLD, it)[5])):
+        for slot, m in enumerate((OD.pair_inputs(GOLD, it, pre)[1], OD.pair_inputs(GOLD, it, pre)[5])):
             assert tuple(b[slot][:3]) == OD.crop_box(m) and b[slot][3] == int((m > 0).sum())
 
 
