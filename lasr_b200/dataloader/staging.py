@@ -99,3 +99,75 @@ class DeviceStager:
         for v in self._out.values():
             v.record_stream(torch.cuda.current_stream(self.device))
         return self._out
+
+
+def pair_frame_indices(im0, direction, dframe=1):
+    """(frame 0, frame n, flow of frame 0 is the forward flow?) for one dataset item, as the reference picks them
+    (dataloader/vidbase.py:53-55, 85-90): direction 1 pairs im0 with im0 + dframe and reads flow-forward[im0] /
+    flow-backward[im0 + dframe]; direction 0 pairs it with im0 - dframe and reads flow-backward[im0] /
+    flow-forward[im0 - dframe]."""
+    forward = int(direction) == 1
+    return int(im0), int(im0) + (dframe if forward else -dframe), forward
+
+
+class ResidentVideo:
+    """A whole decoded video kept in HBM and staged there.
+
+    LASR optimises one video of a few dozen frames for thousands of steps; decoded, an 80-frame 480p video with its
+    flow and occlusion maps is ~0.65 GB -- it is uploaded ONCE.  The per-item preprocessing is deterministic (the
+    reference's dataloader has no augmentation), so every (frame, direction) item is staged once, in chunks, on first
+    use, and a batch is an ``index_select`` over the staged items: no PCIe traffic and no preprocessing per step.
+
+    frames_bgr [T,H,W,3] uint8, masks [T,H,W] uint8, flow_fw / flow_bw [T,H,W,3] float32, occ_fw / occ_bw [T,H,W]
+    float32 (numpy or tensors; flow_fw[t] is the flow t -> t + dframe, flow_bw[t] the flow t -> t - dframe)."""
+
+    def __init__(self, frames_bgr, masks, flow_fw, occ_fw, flow_bw, occ_bw, img_size, dframe=1, device="cuda", chunk=16):
+        dev = torch.device(device)
+        up = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a) if not torch.is_tensor(a) else a).to(dev, dt).contiguous()
+        self.frames, self.masks = up(frames_bgr, torch.uint8), up(masks, torch.uint8)
+        self.flow = {True: up(flow_fw, torch.float32), False: up(flow_bw, torch.float32)}
+        self.occ = {True: up(occ_fw, torch.float32), False: up(occ_bw, torch.float32)}
+        self.T, self.S, self.dframe, self.chunk, self.device = int(self.frames.shape[0]), int(img_size), int(dframe), int(chunk), dev
+        self._staged = None          # dict of tensors over all 2*T (frame, direction) slots, filled on first use
+        self._valid = None
+
+    def _slot(self, im0, direction):
+        return 2 * int(im0) + (1 if int(direction) == 1 else 0)
+
+    def _stage_all(self):
+        items = [(t, d) for t in range(self.T) for d in (0, 1)]
+        ok = [0 <= pair_frame_indices(t, d, self.dframe)[1] < self.T for t, d in items]
+        out = None
+        todo = [it for it, v in zip(items, ok) if v]
+        for s in range(0, len(todo), self.chunk):
+            part = todo[s:s + self.chunk]
+            sel = [pair_frame_indices(t, d, self.dframe) for t, d in part]
+            i0 = torch.tensor([a for a, _, _ in sel], device=self.device)
+            i1 = torch.tensor([b for _, b, _ in sel], device=self.device)
+            fwd = torch.tensor([f for _, _, f in sel], device=self.device)
+            f4, f3 = fwd[:, None, None, None], fwd[:, None, None]
+            fr = torch.stack([self.frames[i0], self.frames[i1]], 1)
+            mk = torch.stack([self.masks[i0], self.masks[i1]], 1)
+            # frame 0 carries the flow towards its partner, the partner the flow back (vidbase.py:85-90)
+            fl = torch.stack([torch.where(f4, self.flow[True][i0], self.flow[False][i0]),
+                              torch.where(f4, self.flow[False][i1], self.flow[True][i1])], 1)
+            oc = torch.stack([torch.where(f3, self.occ[True][i0], self.occ[False][i0]),
+                              torch.where(f3, self.occ[False][i1], self.occ[True][i1])], 1)
+            res = stage_pairs(fr, mk, fl, oc, self.S)
+            check_boxes(res["boxes"])
+            if out is None:
+                out = {k: torch.zeros((2 * self.T,) + tuple(v.shape[1:]), dtype=v.dtype, device=self.device) for k, v in res.items()}
+            slots = torch.tensor([self._slot(t, d) for t, d in part], device=self.device)
+            for k, v in res.items():
+                out[k][slots] = v
+        self._staged = out
+        self._valid = torch.tensor(ok, device=self.device)
+
+    def stage(self, base_frames, directions):
+        """The collated batch (keys / shapes of ``stage_pairs``) for items (base frame, direction)."""
+        if self._staged is None:
+            self._stage_all()
+        slots = torch.tensor([self._slot(t, d) for t, d in zip(base_frames, directions)], device=self.device)
+        if not bool(self._valid[slots].all()):
+            raise IndexError("ResidentVideo.stage: an item pairs a frame with one outside the video")
+        return {k: v.index_select(0, slots) for k, v in self._staged.items()}

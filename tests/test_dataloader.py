@@ -105,6 +105,15 @@ def test_raw_dataset_decodes_what_the_reference_decodes(tmp_path):
     assert tuple(batch["frames_bgr"].shape) == (3, 2) + GOLD["frames_bgr"].shape[1:] and batch["flows"].dtype == torch.float32
 
 
+def test_pair_selection_follows_the_reference():
+    from lasr_b200.dataloader import pair_frame_indices
+    for pre in VIDEOS:
+        for it in GOLD[pre + "items"]:
+            i0, i1, fwd = pair_frame_indices(GOLD[pre + "baselist"][it], GOLD[pre + "directlist"][it], 1)
+            assert i0 == int(GOLD[f"{pre}item{it}/id0"]) and i1 == int(GOLD[f"{pre}item{it}/id1"])
+            assert fwd == (int(GOLD[pre + "directlist"][it]) == 1)
+
+
 def _raw_batch(items, pre=""):
     ins = [OD.pair_inputs(GOLD, int(i), pre) for i in items]
     st = lambda a, b: np.stack([np.stack([x[a], x[b]]) for x in ins])
@@ -187,3 +196,29 @@ def test_staging_properties_at_davis_size_and_through_the_stager():
         check_boxes(stage_pairs(fr.to(dev), mk2.to(dev), fl.to(dev), oc.to(dev), S2)["boxes"])
     with pytest.raises((TypeError, RuntimeError)):
         stage_pairs(fr, mk, fl, oc, S2)            # CPU tensors are refused loudly
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pre", VIDEOS)
+def test_resident_video_stages_once_and_serves_batches(pre):
+    """The whole video in HBM, every (frame, direction) item staged on first use, batches by index_select: the items the
+    reference's dataset returns, in any order and repeatedly."""
+    from lasr_b200.dataloader import ResidentVideo, stage_pairs
+    G = lambda k: GOLD[pre + k]
+    rv = ResidentVideo(G("frames_bgr"), G("masks"), G("flow_fw"), G("occ_fw"), G("flow_bw"), G("occ_bw"), S, chunk=3)
+    items = [int(i) for i in G("items")]
+    base = [int(G("baselist")[i]) for i in items]; dirs = [int(G("directlist")[i]) for i in items]
+    out = rv.stage(base, dirs)
+    for p, it in enumerate(items):
+        for k in KEYS:
+            got = out[k][p].cpu().numpy().astype(np.float64); ref = GOLD[f"{pre}item{it}/{k}"].astype(np.float64)
+            np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2e-6, err_msg=f"{pre}{it}/{k}")
+    again = rv.stage(base[::-1], dirs[::-1])                       # served from the staged items, any order
+    for k in KEYS:
+        assert torch.equal(again[k], out[k].flip(0)), k
+    dev = torch.device("cuda", 0)
+    direct = stage_pairs(*(torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in _raw_batch(items, pre)), S)
+    for k in KEYS:
+        assert torch.equal(out[k], direct[k]), k                   # identical to staging the same pairs directly
+    with pytest.raises(IndexError):
+        rv.stage([0], [0])                                         # frame 0 has no predecessor
