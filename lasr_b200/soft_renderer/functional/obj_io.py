@@ -54,8 +54,10 @@ def _uv_index(field):
     return int(field.split("/")[1]) if ("/" in field and "//" not in field) else 0
 
 
-def load_textures(filename_obj, filename_mtl, texture_res):
-    """'surface' textures [F, texture_res**2, 3] sampled from the materials' images (load_obj.py:28-101)."""
+def parse_obj_uv(filename_obj):
+    """Host-side parse of the texture side of an OBJ (load_obj.py:29-67): per-corner texture coordinates
+    [F,3,2] float32 (polygons fan-triangulated; corners without a `vt` index take the LAST `vt`, the reference's
+    `vertices[0 - 1]`) and the material name of every triangle."""
     uv, corner_uv, face_material = [], [], []
     material = ""
     for t in _tokens(filename_obj):
@@ -70,7 +72,30 @@ def load_textures(filename_obj, filename_mtl, texture_res):
             material = t[1]
     uv = np.asarray(uv, np.float32).reshape(-1, 2)
     faces = uv[np.asarray(corner_uv, np.int32).reshape(-1, 3) - 1]           # [F,3,2]
-    faces = torch.from_numpy(np.ascontiguousarray(faces)).cuda()
+    return np.ascontiguousarray(faces), face_material
+
+
+def parse_obj(filename_obj):
+    """Host-side parse of the geometry of an OBJ (load_obj.py:113-137, 147-153): vertices [V,3] float32, per-vertex
+    colours [V,3] (the optional `v x y z r g b` form; empty rows otherwise), faces [F,3] int32 0-based with polygons
+    fan-triangulated, and the `mtllib` file name (None if absent)."""
+    verts, colours, tris, mtllib = [], [], [], None
+    for t in _tokens(filename_obj):
+        if t[0] == "v":
+            verts.append([float(v) for v in t[1:4]])
+            colours.append([float(v) for v in t[4:7]])
+        elif t[0] == "f":
+            idx = [int(v.split("/")[0]) for v in t[1:]]
+            tris.extend((idx[0], idx[i + 1], idx[i + 2]) for i in range(len(idx) - 2))
+        elif t[0] == "mtllib":
+            mtllib = t[1]
+    return (np.asarray(verts, np.float32).reshape(-1, 3), colours, np.asarray(tris, np.int32).reshape(-1, 3) - 1, mtllib)
+
+
+def load_textures(filename_obj, filename_mtl, texture_res):
+    """'surface' textures [F, texture_res**2, 3] sampled from the materials' images (load_obj.py:28-101)."""
+    faces, face_material = parse_obj_uv(filename_obj)
+    faces = torch.from_numpy(faces).cuda()
     faces[1 < faces] = faces[1 < faces] % 1                                    # wrap (load_obj.py:70)
 
     colors, texture_filenames = load_mtl(filename_mtl)
@@ -97,18 +122,9 @@ def load_obj(filename_obj, normalization=False, load_texture=False, texture_res=
     """Vertices [V,3] float32, faces [F,3] int32 (0-based, polygons fan-triangulated) and optionally textures, all
     CUDA tensors (load_obj.py:104-167)."""
     assert texture_type in ["surface", "vertex"]
-    verts, colours, tris, mtllib = [], [], [], None
-    for t in _tokens(filename_obj):
-        if t[0] == "v":
-            verts.append([float(v) for v in t[1:4]])
-            colours.append([float(v) for v in t[4:7]])
-        elif t[0] == "f":
-            idx = [int(v.split("/")[0]) for v in t[1:]]
-            tris.extend((idx[0], idx[i + 1], idx[i + 2]) for i in range(len(idx) - 2))
-        elif t[0] == "mtllib":
-            mtllib = t[1]
-    vertices = torch.from_numpy(np.asarray(verts, np.float32).reshape(-1, 3)).cuda()
-    faces = torch.from_numpy(np.asarray(tris, np.int32).reshape(-1, 3)).cuda() - 1
+    verts, colours, tris, mtllib = parse_obj(filename_obj)
+    vertices = torch.from_numpy(verts).cuda()
+    faces = torch.from_numpy(tris).cuda()
 
     textures = None
     if load_texture and texture_type == "surface":

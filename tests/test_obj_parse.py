@@ -1,0 +1,116 @@
+"""OBJ / MTL parsing of soft_renderer.functional.obj_io on the host (no GPU): hand-computed expectations on a small
+polygon soup, and -- where the reference tree exists (the build container) -- the reference's own load_obj /
+load_textures (third_party/softras/soft_renderer/functional/load_obj.py) run on the same files, with its CUDA
+resampling kernel replaced by a stub that records the arguments it would have been called with."""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from lasr_b200.soft_renderer.functional import obj_io
+
+REF = "/root/reference/third_party/softras/soft_renderer/functional/load_obj.py"
+SPOT = "/root/reference/database/misc/spot/spot_triangulated.obj"
+
+OBJ = """# a quad, a triangle with normals only, a pentagon, two materials
+mtllib soup.mtl
+v 0 0 0 1.0 0.5 0.25
+v 1 0 0 0.1 0.2 0.3
+v 1 1 0 0 0 0
+v 0 1 0 1 1 1
+v 0.5 1.5 0.5 0.2 0.4 0.6
+vt 0.0 0.0
+vt 1.0 0.0
+vt 1.0 1.0
+vt 0.0 1.0
+vt 0.5 1.5
+usemtl red
+f 1/1 2/2 3/3 4/4
+usemtl tex
+f 1//1 2//1 3//1
+f 1/1/1 2/2/1 3/3/1 5/5/1 4/4/1
+"""
+MTL = "newmtl red\nKd 1.0 0.0 0.0\nnewmtl tex\nKd 0.5 0.5 0.5\nmap_Kd tex.png\n"
+
+
+@pytest.fixture()
+def soup(tmp_path):
+    (tmp_path / "soup.obj").write_text(OBJ)
+    (tmp_path / "soup.mtl").write_text(MTL)
+    return str(tmp_path / "soup.obj")
+
+
+def test_geometry_and_uv_parsing(soup):
+    v, colours, f, mtllib = obj_io.parse_obj(soup)
+    assert v.shape == (5, 3) and v.dtype == np.float32 and mtllib == "soup.mtl"
+    # quad -> 2 triangles, triangle -> 1, pentagon -> 3 (fans around the first corner), 0-based
+    assert f.tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 2], [0, 1, 2], [0, 2, 4], [0, 4, 3]] and f.dtype == np.int32
+    assert np.allclose(np.asarray(colours, np.float32)[0], [1.0, 0.5, 0.25])
+    uv, mats = obj_io.parse_obj_uv(soup)
+    assert uv.shape == (6, 3, 2) and mats == ["red", "red", "tex", "tex", "tex", "tex"]
+    assert np.array_equal(uv[0], [[0, 0], [1, 0], [1, 1]]) and np.array_equal(uv[1], [[0, 0], [1, 1], [0, 1]])
+    assert np.array_equal(uv[2], [[0.5, 1.5]] * 3)          # `v//vn` corners: index 0 - 1 = the last vt, as the reference
+    colors, files = obj_io.load_mtl(soup[:-4] + ".mtl")
+    assert files == {"tex": "tex.png"} and np.allclose(colors["red"], [1, 0, 0])
+
+
+def _reference_loader(captured):
+    """The reference's load_obj module with skimage / the CUDA extension stubbed and `.cuda()` made the identity."""
+    from PIL import Image
+    sk = types.ModuleType("skimage"); skio = types.ModuleType("skimage.io")
+    skio.imread = lambda p: np.asarray(Image.open(p))
+    sk.io = skio
+    ext = types.ModuleType("soft_renderer.cuda.load_textures")
+
+    def load_textures(image, faces, textures, is_update):
+        captured.append((image.clone(), faces.clone(), textures.clone(), is_update.clone()))
+        return textures
+    ext.load_textures = load_textures
+    mods = {"skimage": sk, "skimage.io": skio, "soft_renderer": types.ModuleType("soft_renderer"),
+            "soft_renderer.cuda": types.ModuleType("soft_renderer.cuda"), "soft_renderer.cuda.load_textures": ext}
+    saved = {k: sys.modules.get(k) for k in mods}
+    sys.modules.update(mods)
+    try:
+        spec = importlib.util.spec_from_file_location("ref_load_obj", REF)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return m
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("which", ["soup", "spot"])
+def test_parsers_agree_with_the_reference_loader(soup, which, monkeypatch, tmp_path):
+    from PIL import Image
+    path = soup if which == "soup" else SPOT
+    if which == "soup":
+        Image.fromarray((np.random.RandomState(0).rand(8, 8, 3) * 255).astype(np.uint8)).save(str(tmp_path / "tex.png"))
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    captured = []
+    ref = _reference_loader(captured)
+    rv, rf, rt = ref.load_obj(path, load_texture=True, texture_res=2, texture_type="surface")
+    v, _, f, mtllib = obj_io.parse_obj(path)
+    assert np.array_equal(v, rv.numpy()) and np.array_equal(f, rf.numpy())
+    uv, mats = obj_io.parse_obj_uv(path)
+    uv = torch.from_numpy(uv); uv[1 < uv] = uv[1 < uv] % 1
+    assert len(captured) == 1
+    image, faces, textures_in, is_update = captured[0]
+    assert torch.equal(uv, faces)                                   # the kernel's `faces` argument
+    _, files = obj_io.load_mtl(os.path.join(os.path.dirname(path), mtllib))
+    (name, fname), = files.items()
+    assert np.array_equal((np.asarray(mats) == name).astype(np.int32), is_update.numpy())
+    ours_img = np.ascontiguousarray((obj_io._read_image(os.path.join(os.path.dirname(path), fname)).astype(np.float32) / 255.)[::-1][:, :, :3])
+    assert np.array_equal(ours_img, image.numpy())                  # the kernel's `image` argument (flipped, 0..1)
+    if which == "soup":                                             # material colours painted before the resampling
+        assert torch.equal(textures_in[0], torch.tensor([1.0, 0.0, 0.0]).expand(4, 3))
+    vv, ff = ref.load_obj(path, normalization=True)
+    monkeypatch.undo()
