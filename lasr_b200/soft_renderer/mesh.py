@@ -132,25 +132,23 @@ class Mesh(object):
 
     @classmethod
     def from_obj(cls, filename_obj, normalization=False, load_texture=False, texture_res=1, texture_type="surface"):
-        """Create a Mesh from a Wavefront .obj file (mesh.py:148-164 of the reference)."""
-        if load_texture:
-            vertices, faces, textures = srf.load_obj(filename_obj, normalization=normalization,
-                                                     texture_res=texture_res, load_texture=True,
-                                                     texture_type=texture_type)
-        else:
-            vertices, faces = srf.load_obj(filename_obj, normalization=normalization, texture_res=texture_res,
-                                           load_texture=False)
-            textures = None
+        """A Mesh from a Wavefront .obj file; with ``load_texture`` also its 'surface' texture atlas (sampled by
+        ``lasr_b200_load_textures``) or its per-vertex colours (reference: mesh.py:148-164)."""
+        loaded = srf.load_obj(filename_obj, normalization=normalization, texture_res=texture_res,
+                              load_texture=bool(load_texture),
+                              **({"texture_type": texture_type} if load_texture else {}))
+        vertices, faces = loaded[0], loaded[1]
+        textures = loaded[2] if load_texture else None
         return cls(vertices, faces, textures, texture_res, texture_type)
 
     def save_obj(self, filename_obj, save_texture=False, texture_res_out=16):
+        """Write the (single) mesh of this container; ``save_texture`` adds the .mtl and the .png atlas painted by
+        ``lasr_b200_create_texture_image`` (reference: mesh.py:166-174)."""
         if self.batch_size != 1:
             raise ValueError("Could not save when batch size >= 1")
-        if save_texture:
-            srf.save_obj(filename_obj, self.vertices[0], self.faces[0], textures=self.textures[0],
-                         texture_res=texture_res_out, texture_type=self.texture_type)
-        else:
-            srf.save_obj(filename_obj, self.vertices[0], self.faces[0], textures=None)
+        extra = dict(textures=self.textures[0], texture_res=texture_res_out, texture_type=self.texture_type) \
+            if save_texture else dict(textures=None)
+        srf.save_obj(filename_obj, self.vertices[0], self.faces[0], **extra)
 
     def voxelize(self, voxel_size=32):
         srf.voxelization(None)
