@@ -7,7 +7,9 @@
 // (pixel,face) pair (.cu:620-622,657-666).  Here:
 //
 //   setup     one thread per face: derived per-face constants (a 176-byte record), the dilated
-//             bounding box and its packed pixel window (8 B), written once to the workspace;
+//             bounding box and its packed pixel window (8 B), written once to the workspace; for
+//             large launches also a per-tile face count, from which a one-CTA counting sort lists
+//             the (frame, tile) items heaviest first -- the order the forward's CTAs start in;
 //   forward   one CTA per 16x16 pixel tile: (1) the CTA scans the packed windows and compacts the
 //             indices of overlapping faces, in ascending order, into shared memory; (2) each warp
 //             (an 8x4 pixel footprint) then walks that list on its own, culls 32 faces at a time
@@ -807,7 +809,7 @@ static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, flo
 
 static bool is_fast(const RasterArgs& A);
 
-// forward launch: the footprint-claiming variant whenever the face list fits one scan round
+// forward launch: dispatch order first (if this launch uses it), then one CTA per (frame, tile)
 static int launch_forward(const RasterArgs& A, cudaStream_t st) {
   const int S = A.S, F = A.F, N = A.N;
   const int tiles = (int)num_tiles(S);
