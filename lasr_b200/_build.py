@@ -44,7 +44,7 @@ def build_library(force: bool = False, verbose: bool = False, defines=()) -> str
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
-    subprocess.check_call([nvcc, "--shared", "-Wno-deprecated-gpu-targets", "-o", LIB_PATH] + objs)
+    subprocess.check_call([nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs)
     return LIB_PATH
 
 
