@@ -484,6 +484,68 @@ __device__ __forceinline__ int surface_texel(const float* wc, int R) {
   return ((wc[0] + wc[1]) * R - wx - wy <= 1.f) ? (wy * R + wx) : ((R - 1 - wy) * R + (R - 1 - wx));
 }
 
+// ---- row spans of the dilated triangle (backward, LASR_BWD_SPANS; not enabled by default) -----------------
+// A pair can only be accepted if the pixel is inside the face or closer than sqrt(threshold) to it, i.e. inside the
+// triangle dilated by a disc -- a convex set whose intersection with a pixel row is ONE interval, ~30 % smaller in
+// total than the dilated bounding box the backward sweeps (profiles/analysis_backward_sweeps.py).  Everything here
+// only has to be a SUPERSET of what the exact per-pixel tests accept: the tests themselves stay in the loop.
+//
+// Rounding-noise amplitude (NDC) of the distances the reference's float pipeline computes for this face (the same
+// estimate face_setup turns into kappa): the dilation radius is widened by a few of these, and faces whose noise is
+// not small against the radius -- slivers, degenerate faces, whose "inside" set is noise -- keep the full window.
+__device__ __forceinline__ float face_noise_eta(const FaceGeom& g) {
+  float m = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) m = fmaxf(m, fabsf(g.inv[3 * k]) + fabsf(g.inv[3 * k + 1]) + fabsf(g.inv[3 * k + 2]));
+  const float xm = fmaxf(1.f, fmaxf(max3(fabsf(g.x[0]), fabsf(g.x[1]), fabsf(g.x[2])),
+                                    max3(fabsf(g.y[0]), fabsf(g.y[1]), fabsf(g.y[2]))));
+  const float emin2 = min3(g.a[0][0] - g.a[0][1], g.a[1][1] - g.a[1][2], g.a[2][2] - g.a[2][0]);
+  return 5.96e-8f * (LASR_NOISE_C1 * m * xm + LASR_NOISE_C2 * xm * xm * rsqrtf(fmaxf(emin2, 1e-30f)));
+}
+
+#ifndef LASR_SPAN_MAX_NOISE
+#define LASR_SPAN_MAX_NOISE 0.05f
+#endif
+// Inclusive pixel-index interval of the pixel centres inside [lo, hi] (centre i sits at (2i + 1 - S) / S), widened by
+// 1/64 pixel for the float rounding of this conversion -- tighter than coord_window, which rounds outwards by a pixel.
+__device__ __forceinline__ void span_window(float lo, float hi, int S, int& ilo, int& ihi) {
+  const float a = (lo * (float)S + (float)(S - 1)) * 0.5f;
+  const float b = (hi * (float)S + (float)(S - 1)) * 0.5f;
+  ilo = max(0, (int)ceilf(a - 0.015625f));
+  ihi = min(S - 1, (int)floorf(b + 0.015625f));
+}
+
+// Dilation radius for the spans, or a negative value when the face must keep its full window.
+__device__ __forceinline__ float span_radius(const FaceGeom& g, float sthr) {
+  const float eta = face_noise_eta(g);
+  if (!(eta < LASR_SPAN_MAX_NOISE * sthr)) return -1.f;   // also catches NaN / inf
+  return 1.05f * sthr + 8.f * eta;
+}
+
+// x-interval [lo, hi] of the pixel row at height yp that can lie within R of the triangle: the hull, over the three
+// edges, of (the part of the edge inside the band |y - yp| <= R) widened by R.  false: the row misses the set.
+__device__ __forceinline__ bool row_span(const FaceGeom& g, float yp, float R, float& lo, float& hi) {
+  lo = 3.0e38f; hi = -3.0e38f;
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    const int b = (e + 1) % 3;
+    const float ax = g.x[e], ay = g.y[e], bx = g.x[b], by = g.y[b];
+    if (yp < fminf(ay, by) - R || yp > fmaxf(ay, by) + R) continue;
+    float t0 = 0.f, t1 = 1.f;
+    const float dy = by - ay;
+    if (fabsf(dy) > 1e-12f) {                           // clip the edge to the band (parameters may swap)
+      const float ra = (yp - R - ay) / dy, rb = (yp + R - ay) / dy;
+      t0 = fmaxf(fminf(ra, rb), 0.f); t1 = fminf(fmaxf(ra, rb), 1.f);
+      if (!(t0 <= t1)) continue;
+    }
+    const float xa = ax + t0 * (bx - ax), xb = ax + t1 * (bx - ax);
+    lo = fminf(lo, fminf(xa, xb)); hi = fmaxf(hi, fmaxf(xa, xb));
+  }
+  if (lo > hi) return false;
+  lo -= R; hi += R;
+  return true;
+}
+
 // Sum 16 per-lane values over the warp with 16 shuffles instead of 80 (recursive halving: at each
 // stage a lane keeps half of its values and ships the other half to its partner).  On return lane L
 // holds in v[0] the warp total of value  idx = 8*bit4(L) + 4*bit3(L) + 2*bit2(L) + bit1(L).

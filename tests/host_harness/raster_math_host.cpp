@@ -67,4 +67,32 @@ extern "C" void lasr_host_stats(long long* inside, long long* all_edges, int res
   if (reset) { lasr_host_inside_pairs = 0; lasr_host_all_edges_pairs = 0; }
 }
 
+// Row spans of the dilated triangle for one face: for every row of the face's pixel window, the inclusive pixel-index
+// interval [xa, xb] the span sweep would visit (xa > xb: row skipped).  Returns the window (xlo, xhi, ylo, yhi) in
+// win[4] and 1 if the face uses spans, 0 if it keeps the full window (spans then = the window).  rows: [S][2] ints.
+extern "C" int lasr_host_row_spans(const float* face9, int S, float sigma, float dist_eps, int* win, int* rows) {
+  const float sthr = sqrtf(dist_eps * sigma);
+  FaceGeom g;
+  face_setup(face9, sthr, g);
+  int xlo, xhi, ylo, yhi;
+  coord_window(g.lox, g.hix, S, xlo, xhi);
+  coord_window(g.loy, g.hiy, S, ylo, yhi);
+  win[0] = xlo; win[1] = xhi; win[2] = ylo; win[3] = yhi;
+  if (xlo > xhi || ylo > yhi) return 0;
+  const float R = span_radius(g, sthr);
+  for (int yi = ylo; yi <= yhi; ++yi) {
+    int xa = xlo, xb = xhi;
+    if (R >= 0.f) {
+      float lo, hi;
+      if (row_span(g, pixel_coord(yi, S), R, lo, hi)) {
+        int a, b;
+        span_window(lo, hi, S, a, b);
+        xa = a > xlo ? a : xlo; xb = b < xhi ? b : xhi;
+      } else { xa = 1; xb = 0; }
+    }
+    rows[2 * (yi - ylo)] = xa; rows[2 * (yi - ylo) + 1] = xb;
+  }
+  return R >= 0.f ? 1 : 0;
+}
+
 extern "C" int lasr_host_fast_inside(void) { return LASR_FAST_INSIDE; }

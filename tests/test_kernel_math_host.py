@@ -103,3 +103,53 @@ def test_predicted_edge_is_bit_identical_on_pathological_soups(libs, kind):
     rng = np.random.RandomState(3)
     F, X, Y = _pairs(_soup(rng, 1500, kind), 64, 1e-4, rng)
     _check(libs, F, X, Y, 1e-4, kind)
+
+
+# ---- groundwork for a span-based backward sweep (raster_common.cuh: span_radius / row_span / span_window) ------------
+def _spans_cover_accepted(lib, fv, S, sigma):
+    """For every face: the pixel rows' spans must contain every pixel the exact tests (border box + soft_fragment)
+    accept.  Returns (faces, faces using spans, window pixels, span pixels, accepted pairs, missed pairs)."""
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    coords = ((2 * np.arange(S) + 1 - S) / S).astype(np.float32)
+    sthr = np.float32(np.sqrt(np.float32(DIST_EPS) * np.float32(sigma)))
+    win = np.zeros(4, np.int32); rows = np.zeros((S, 2), np.int32)
+    faces = used = px_win = px_span = n_acc = missed = 0
+    for f in fv:
+        f = np.ascontiguousarray(f, np.float32)
+        u = lib.lasr_host_row_spans(P(f), ctypes.c_int(S), ctypes.c_float(sigma), ctypes.c_float(DIST_EPS), P(win), P(rows))
+        xlo, xhi, ylo, yhi = (int(v) for v in win)
+        if xlo > xhi or ylo > yhi:
+            continue
+        faces += 1; used += u
+        h = yhi - ylo + 1
+        r = rows[:h]
+        px_win += (xhi - xlo + 1) * h
+        px_span += int(np.maximum(r[:, 1] - r[:, 0] + 1, 0).sum())
+        gx, gy = np.meshgrid(np.arange(xlo, xhi + 1), np.arange(ylo, yhi + 1))
+        X = np.ascontiguousarray(coords[gx.ravel()]); Y = np.ascontiguousarray(coords[gy.ravel()])
+        xs, ys = f[[0, 3, 6]], f[[1, 4, 7]]
+        inb = (X <= xs.max() + sthr) & (X >= xs.min() - sthr) & (Y <= ys.max() + sthr) & (Y >= ys.min() - sthr)
+        o, _ = _run(lib, np.ascontiguousarray(np.repeat(f[None], len(X), 0)), X, Y, sigma)
+        acc = (o[:, 0] > 0) & inb
+        n_acc += int(acc.sum())
+        inspan = (gx.ravel() >= r[gy.ravel() - ylo, 0]) & (gx.ravel() <= r[gy.ravel() - ylo, 1])
+        missed += int((acc & ~inspan).sum())
+    return faces, used, px_win, px_span, n_acc, missed
+
+
+@pytest.mark.parametrize("mesh,S,sigma", [("spot", 256, 1e-4), ("spot", 256, 1e-5), ("ico2", 64, 1e-4), ("bumpy2", 96, 1e-5)])
+def test_row_spans_of_the_dilated_triangle_cover_every_accepted_pixel(libs, mesh, S, sigma):
+    fv = cases.lasr_case(mesh, 1, S, sigma=sigma)["face_vertices"].reshape(-1, 9)
+    fv = fv[np.random.RandomState(1).choice(len(fv), min(len(fv), 700), replace=False)]
+    faces, used, px_win, px_span, n_acc, missed = _spans_cover_accepted(libs[1], fv, S, sigma)
+    assert missed == 0 and n_acc > 1000
+    assert used > 0.8 * faces and px_span < 0.85 * px_win        # and they are worth having on real meshes
+
+
+@pytest.mark.parametrize("kind", ["random", "sliver", "needle", "tiny", "degenerate"])
+def test_row_spans_fall_back_to_the_window_on_ill_conditioned_faces(libs, kind):
+    rng = np.random.RandomState(4)
+    faces, used, px_win, px_span, n_acc, missed = _spans_cover_accepted(libs[1], _soup(rng, 250, kind), 96, 1e-4)
+    assert missed == 0
+    if kind in ("sliver", "needle", "degenerate"):
+        assert used == 0 and px_span == px_win                    # noise-dominated faces keep the full window
