@@ -80,6 +80,9 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #ifndef LASR_FTZ_MUFU_BWD           // ... but not in the backward (measured slower)
 #define LASR_FTZ_MUFU_BWD 0
 #endif
+#ifndef LASR_BWD_SPANS              // EXPERIMENTAL (unmeasured): sweep row spans of the dilated triangle in the backward
+#define LASR_BWD_SPANS 0
+#endif
 #ifndef LASR_BWD_INDEX32_MULTI      // ... and in the multi-set backward
 #define LASR_BWD_INDEX32_MULTI 0
 #endif
@@ -487,6 +490,9 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
   constexpr int KL = K - KF;            // live colour sets
   constexpr int NV = 9 + 9 * KL;        // gradient values per face: 9 position + 9 per live colour set
   __shared__ float s_part[8][NV];
+#if LASR_BWD_SPANS
+  __shared__ int s_pre[8][32], s_x0[8][32];   // per warp: span pixels before each row of the window, first x of each row
+#endif
   const int lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   const int S = A.S;
@@ -560,12 +566,58 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
     const index_t SSx = (index_t)S * (index_t)S;
     if (kIdx32) asm volatile("" : "+l"(sc), "+l"(ag), "+l"(gs));
 #define PLANE(k) ((index_t)(k) * SSx + pn)
-    for (int idx = gtid; idx < total; idx += gsize) {
-      int r = (int)(((float)idx + 0.5f) * inv_wdt);  // idx / wdt without an integer divide
-      int col = idx - r * wdt;
-      if (col < 0) { --r; col += wdt; } else if (col >= wdt) { ++r; col -= wdt; }
-      const int xi = xlo + col;
-      const int yi = yhi - r;
+    int sweep_total = total;
+#if LASR_BWD_SPANS
+    // EXPERIMENTAL, off by default, not yet measured on a GPU: sweep the row spans of the
+    // dilated triangle instead of the whole dilated box.  Lane l builds the span of window row l; an inclusive warp
+    // scan of the span lengths gives every row's first sweep index; each 32-pixel step then locates its pixels with
+    // span_locate.  The geometry (span_radius / row_span / span_window / span_locate) is validated on the host
+    // (tests/test_kernel_math_host.py): a superset of what the exact tests below accept.
+    bool use_spans = false;
+    const int swarp = (threadIdx.x >> 5) & 7;
+    if (!kBig && kFast && yhi - ylo < 32) {
+      const float R = span_radius(g, sthr);
+      if (R >= 0.f) {                                  // warp-uniform: g is the warp's face
+        int xa = 1, xb = 0;
+        if (lane <= yhi - ylo) {
+          float lo, hi;
+          if (row_span(g, A.coords[yhi - lane], R, lo, hi)) {
+            int a, b;
+            span_window(lo, hi, S, a, b);
+            xa = max(a, xlo); xb = min(b, xhi);
+          }
+        }
+        const int len = max(xb - xa + 1, 0);
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        s_pre[swarp][lane] = incl - len;
+        s_x0[swarp][lane] = xa;
+        sweep_total = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        use_spans = true;
+      }
+    }
+#endif
+    for (int idx = gtid; idx < sweep_total; idx += gsize) {
+      int xi, yi;
+#if LASR_BWD_SPANS
+      if (use_spans) {
+        const int r = span_locate(s_pre[swarp], idx);
+        xi = s_x0[swarp][r] + idx - s_pre[swarp][r];
+        yi = yhi - r;
+      } else
+#endif
+      {
+        int r = (int)(((float)idx + 0.5f) * inv_wdt);  // idx / wdt without an integer divide
+        int col = idx - r * wdt;
+        if (col < 0) { --r; col += wdt; } else if (col >= wdt) { ++r; col -= wdt; }
+        xi = xlo + col;
+        yi = yhi - r;
+      }
       const float xp = A.coords[xi];
       const float yp = A.coords[yi];
       if (xp > g.hix || xp < g.lox || yp > g.hiy || yp < g.loy) continue;

@@ -546,6 +546,16 @@ __device__ __forceinline__ bool row_span(const FaceGeom& g, float yp, float R, f
   return true;
 }
 
+// Row of the idx-th pixel of a span sweep: pre[r] = number of span pixels in rows < r (32 entries, non-decreasing;
+// empty rows repeat the value).  Returns the largest r with pre[r] <= idx -- never an empty row for idx < total.
+__device__ __forceinline__ int span_locate(const int* pre, int idx) {
+  int r = 0;
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1)
+    if (pre[r + step] <= idx) r += step;       // r + step <= 31
+  return r;
+}
+
 // Sum 16 per-lane values over the warp with 16 shuffles instead of 80 (recursive halving: at each
 // stage a lane keeps half of its values and ships the other half to its partner).  On return lane L
 // holds in v[0] the warp total of value  idx = 8*bit4(L) + 4*bit3(L) + 2*bit2(L) + bit1(L).

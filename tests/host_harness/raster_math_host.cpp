@@ -95,4 +95,21 @@ extern "C" int lasr_host_row_spans(const float* face9, int S, float sigma, float
   return R >= 0.f ? 1 : 0;
 }
 
+// Emulates the span sweep's enumeration for one face: rows[][2] as returned by lasr_host_row_spans (at most 32 rows),
+// visits every idx < total through span_locate and writes the visited (x, y-row) pairs; returns their number.
+extern "C" int lasr_host_span_enumerate(const int* rows, int nrows, int* visited_xy) {
+  int pre[32], x0[32], total = 0;
+  for (int r = 0; r < 32; ++r) {
+    const int len = r < nrows ? (rows[2 * r + 1] - rows[2 * r] + 1 > 0 ? rows[2 * r + 1] - rows[2 * r] + 1 : 0) : 0;
+    pre[r] = total; x0[r] = r < nrows ? rows[2 * r] : 0;
+    total += len;
+  }
+  for (int idx = 0; idx < total; ++idx) {
+    const int r = span_locate(pre, idx);
+    visited_xy[2 * idx] = x0[r] + idx - pre[r];
+    visited_xy[2 * idx + 1] = r;
+  }
+  return total;
+}
+
 extern "C" int lasr_host_fast_inside(void) { return LASR_FAST_INSIDE; }

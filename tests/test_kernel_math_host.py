@@ -153,3 +153,20 @@ def test_row_spans_fall_back_to_the_window_on_ill_conditioned_faces(libs, kind):
     assert missed == 0
     if kind in ("sliver", "needle", "degenerate"):
         assert used == 0 and px_span == px_win                    # noise-dominated faces keep the full window
+
+
+def test_span_enumeration_visits_every_span_pixel_exactly_once(libs):
+    """span_locate (the sweep's index -> row search over the prefix of row lengths), including empty rows in the middle
+    and at both ends."""
+    rng = np.random.RandomState(9)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for trial in range(200):
+        n = int(rng.randint(1, 33))
+        rows = np.zeros((32, 2), np.int32)
+        for r in range(n):
+            a = int(rng.randint(0, 50)); ln = int(rng.choice([0, 0, 1, 2, 7, 13, 40]))
+            rows[r] = (a, a + ln - 1)
+        out = np.zeros((32 * 64, 2), np.int32)
+        total = libs[1].lasr_host_span_enumerate(P(rows), ctypes.c_int(n), P(out))
+        want = [(x, r) for r in range(n) for x in range(rows[r, 0], rows[r, 1] + 1)]
+        assert total == len(want) and [tuple(v) for v in out[:total]] == want
