@@ -1,0 +1,23 @@
+#!/bin/bash
+# First A/B of the next round: the span sweep of the backward.
+#   on the CPU box:   bash profiles/next_trip_spans.sh build
+#   under gpurun:     bash profiles/next_trip_spans.sh run
+# `build` compiles the baseline and -DLASR_BWD_SPANS=1 into lasr_b200/csrc/variants/ (they travel with the snapshot);
+# `run` bit-compares 87 output arrays of the two builds, times them (config A, ico3, K = 1 / 3), runs the rasterizer and
+# hot-path GPU tests on the spans build and takes one ncu capture of its backward.
+set -e
+V=lasr_b200/csrc/variants
+case "$1" in
+build)
+  mkdir -p $V
+  LASR_B200_LIB=$V/base.so python -m lasr_b200._build &
+  LASR_B200_LIB=$V/spans.so python -m lasr_b200._build -DLASR_BWD_SPANS=1 &
+  wait
+  ls -la $V ;;
+run)
+  bash profiles/trip_ab.sh spans base spans
+  LASR_B200_LIB=$V/spans.so python -m pytest tests/test_raster_gpu.py tests/test_hotpath_gpu.py -q -x 2>&1 | tail -3
+  LASR_B200_LIB=$V/spans.so ncu --set full --clock-control none --import-source on -k regex:"raster_backward_kernel" -s 4 -c 1 \
+      -o gpurun_out/spans/backward python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 3 > gpurun_out/spans/ncu.log 2>&1 || true ;;
+*) echo "usage: $0 build|run"; exit 2 ;;
+esac
