@@ -46,8 +46,9 @@ def stage_pairs(frames_bgr, masks, flows, occs, img_size):
 def check_boxes(boxes):
     """The reference raises inside numpy when a mask is empty (``xid.max()`` of an empty array, vidbase.py:98);
     here the condition is detected from the staged pixel counts (one small D2H read)."""
-    if bool((boxes[..., 3] == 0).any()):
-        raise ValueError("stage_pairs: a frame has an empty mask (the reference's crop box is undefined)")
+    if bool(((boxes[..., 3] == 0) | (boxes[..., 2] <= 0)).any()):
+        raise ValueError("stage_pairs: a frame has an empty or one-pixel-wide mask (the reference's crop box is "
+                         "undefined / empty there); its pair was not staged")
 
 
 class DeviceStager:
