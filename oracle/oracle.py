@@ -16,8 +16,9 @@ Two layers:
 
 Parity status: rasterizer pinned against the reference kernels run on a B200
 (tests/golden/softras_ref_*.npz); G1/G2/R2 pinned against the reference's own Python imported
-on CPU (tests/golden/geom_ref.npz); S0 (kornia 0.5.3 quaternion convention, not vendored) and
-L1-L3 (inline code in nnutils/mesh_net.py:372-447, not importable) are **parity unpinned**.
+on CPU (tests/golden/geom_ref.npz); L1-L3 pinned against the reference's own source lines
+(nnutils/mesh_net.py:361-363, 372-447, executed unmodified on CPU tensors by tests/golden/make_losses_golden.py ->
+tests/golden/losses_ref.npz); S0 (kornia 0.5.3 quaternion convention, not vendored) is **parity unpinned**.
 """
 from __future__ import annotations
 

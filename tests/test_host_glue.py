@@ -207,6 +207,42 @@ def test_install_as_soft_renderer_exposes_what_lasr_uses():
                 sys.modules[k] = v
 
 
+def _losses_golden():
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "losses_ref.npz"))
+    for case in ("h1", "h2"):
+        bs, H, S = (int(v) for v in g[f"{case}/meta"])
+        n2 = 2 * bs
+        I = lambda k: g[f"{case}/in/{k}"]
+        args = dict(mask_pred=I("render")[:, 3].reshape(n2, H, S, S), masks=I("masks"), occ=I("occ"),
+                    flow_rd=I("flow_rd").reshape(n2, H, S, S, 2), bgmask=I("bgmask").reshape(n2, H, S, S), flow=I("flow"),
+                    tex=I("render")[:, :3].reshape(n2, H, 3, S, S), imgs=I("imgs"), wt=float(g[f"{case}/l1tex_wt"]))
+        yield case, args, {k: g[f"{case}/out/{k}"] for k in ("mask_loss_sub", "flow_rd_loss_sub", "texture_loss_sub",
+                                                              "mask_loss", "flow_rd_loss", "texture_loss", "total_loss")}
+
+
+def test_image_losses_match_the_reference_source_lines(oracle):
+    """L1-L3 pinned: tests/golden/losses_ref.npz holds what the reference's own lines (nnutils/mesh_net.py:361-363,
+    372-447, executed unmodified on CPU tensors, LPIPS stubbed to zero) compute; the oracle's loop restatement and the
+    product's vectorised host path must both reproduce it."""
+    from lasr_b200 import losses
+    for case, a, want in _losses_golden():
+        lo, subo = oracle.mask_loss(a["mask_pred"], a["masks"], a["occ"])
+        assert np.allclose(subo, want["mask_loss_sub"], rtol=1e-5, atol=1e-7) and abs(lo - float(want["mask_loss"])) < 1e-6
+        lo, subo = oracle.flow_loss(a["flow_rd"], a["bgmask"], a["flow"], a["occ"], a["masks"])
+        assert np.allclose(subo, want["flow_rd_loss_sub"], rtol=2e-5, atol=1e-7) and abs(lo - float(want["flow_rd_loss"])) < 1e-6
+        assert (want["flow_rd_loss_sub"] == 0).any()            # the empty-mask branch (:412) is in the golden
+        lo, subo = oracle.texture_l1_loss(a["tex"], a["mask_pred"], a["imgs"], a["masks"], a["occ"], a["wt"])
+        assert np.allclose(subo, want["texture_loss_sub"], rtol=2e-5, atol=1e-7) and abs(lo - float(want["texture_loss"])) < 1e-6
+        T = torch.from_numpy
+        l1, s1 = losses.mask_loss(T(a["mask_pred"]), T(a["masks"]), T(a["occ"]))
+        l2, s2, _ = losses.flow_loss(T(a["flow_rd"]), T(a["bgmask"]), T(a["flow"]), T(a["occ"]), T(a["masks"]))
+        l3, s3 = losses.texture_l1_loss(T(a["tex"]), T(a["mask_pred"]), T(a["imgs"]), T(a["masks"]), T(a["occ"]), a["wt"])
+        assert np.allclose(s1.numpy(), want["mask_loss_sub"], rtol=1e-5, atol=1e-7)
+        assert np.allclose(s2.numpy(), want["flow_rd_loss_sub"], rtol=2e-5, atol=1e-7)
+        assert np.allclose(s3.numpy(), want["texture_loss_sub"], rtol=2e-5, atol=1e-7)
+        assert abs(float(l1 + l2 + l3) - float(want["total_loss"])) < 2e-6, case
+
+
 class _OracleRasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, fv, tex, settings):
