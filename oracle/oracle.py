@@ -310,7 +310,7 @@ def lasr_render_vertices(verts_px):
     return orthogonal(look_at(v, eye), 1.0)
 
 
-# ---- image losses (nnutils/mesh_net.py:372-447; LPIPS term excluded) -- parity unpinned ----
+# ---- image losses (nnutils/mesh_net.py:372-447; LPIPS term excluded) -- pinned: tests/golden/losses_ref.npz ----
 
 def mask_loss(mask_pred, masks, occ):
     """mesh_net.py:374-390.  mask_pred [N,H,S,S]; masks, occ [N,S,S] -> (scalar, [N,H])."""
