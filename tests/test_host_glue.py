@@ -178,6 +178,39 @@ def test_flow_postprocessing_matches_oracle(oracle):
     assert np.array_equal(bg.numpy(), bgo) and np.allclose(flow.numpy(), fo, atol=1e-6)
 
 
+def test_flow_render_matches_the_reference_source_lines(oracle):
+    """R1 pinned: tests/golden/flow_ref.npz holds what the reference's own render_flow_soft_2 (nnutils/mesh_net.py:75-104,
+    executed unmodified with a stand-in renderer returning a seeded render) hands to the rasterizer and makes of its
+    output; the product's function with the same stand-in, and the oracle's re-projection, must reproduce both."""
+    import types
+    from lasr_b200 import geom_utils as gu
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "flow_ref.npz"))
+    T = torch.from_numpy
+    for case in ("h1", "h2"):
+        I = lambda k: T(g[f"{case}/in/{k}"])
+        seen = {}
+
+        def render_mesh(mesh):
+            seen["vertices"], seen["faces"], seen["textures"] = mesh.vertices, mesh.faces, mesh.textures
+            return I("rendered").clone()
+        renderer = types.SimpleNamespace(
+            transform=types.SimpleNamespace(transformer=types.SimpleNamespace(_eye=[0, 0, -2.732051])), render_mesh=render_mesh)
+        flow, bg, fgm = gu.render_flow_soft_2(renderer, I("verts"), I("faces"), I("pos0"), I("pos1"), I("pp0"), I("pp1"),
+                                              I("f0"), I("f1"))
+        assert np.array_equal(seen["vertices"].numpy(), g[f"{case}/mesh/vertices"])          # eye offset + y flip, exact
+        assert np.array_equal(seen["faces"].numpy(), g[f"{case}/mesh/faces"])
+        assert np.array_equal(seen["textures"].numpy(), g[f"{case}/mesh/textures"])
+        assert np.array_equal(bg.numpy(), g[f"{case}/out/bgmask"]) and bg.any()
+        assert np.array_equal(fgm.numpy(), g[f"{case}/out/fgmask"])
+        np.testing.assert_allclose(flow.numpy(), g[f"{case}/out/flow"], rtol=1e-6, atol=1e-6)
+        n = g[f"{case}/in/verts"].shape[0]
+        r = g[f"{case}/in/rendered"]
+        fo, bgo = oracle.flow_from_rendered_positions(r[:n, :3].transpose(0, 2, 3, 1), r[n:, :3].transpose(0, 2, 3, 1),
+                                                      g[f"{case}/in/pp0"], g[f"{case}/in/pp1"], g[f"{case}/in/f0"], g[f"{case}/in/f1"])
+        assert np.array_equal(bgo, g[f"{case}/out/bgmask"])
+        np.testing.assert_allclose(fo, g[f"{case}/out/flow"], rtol=1e-6, atol=1e-6)
+
+
 def test_install_as_soft_renderer_exposes_what_lasr_uses():
     """nnutils/mesh_net.py:47,132-149,306-316,354-356 and nnutils/geom_utils.py:24 import and poke these."""
     import importlib
@@ -316,3 +349,46 @@ def test_hot_path_region_runs_on_cpu_with_oracle_rasterizer(monkeypatch):
                               out["mask_pred"].detach().view(n2, H, S, S).numpy(), batch["imgs"].numpy(),
                               batch["masks"].numpy(), occ.numpy(), 1.0)
     assert abs(float(out["texture_loss"]) - lo) < 1e-6
+
+
+@pytest.mark.parametrize("case", ["b1", "b4", "b3h2"])
+def test_region_posing_matches_the_reference_source_lines(monkeypatch, case):
+    """The geometry half of the region pinned: tests/golden/region_ref.npz holds what the reference's own lines
+    (nnutils/mesh_net.py:259-311 with its own obj_to_cam / pinhole_cam, executed unmodified on CPU tensors; only
+    kornia's quaternion conversion is a stand-in) compute -- skinning weights, composed bone transforms, posed and
+    projected vertices, the batch-global depth window.  RenderHotPath (three-render structure, CPU tensors, oracle
+    as the rasterizer) must arrive at the same projected vertices and window from the same pose inputs."""
+    from lasr_b200 import geom_utils as gu
+    from lasr_b200 import hotpath, synth
+    import lasr_b200.soft_renderer.rasterizer as rast
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "region_ref.npz"))
+    bs, H, B, V = (int(v) for v in g[f"{case}/meta"])
+    I = lambda k: torch.from_numpy(g[f"{case}/in/{k}"])
+    O_ = lambda k: g[f"{case}/out/{k}"]
+
+    def fake(face_vertices, textures, image_size=256, background_color=[0, 0, 0], near=1, far=100, fill_back=True,
+             eps=1e-3, sigma_val=1e-5, dist_func="euclidean", dist_eps=1e-4, gamma_val=1e-4, aggr_func_rgb="softmax",
+             aggr_func_alpha="prod", texture_type="surface"):
+        return _OracleRasterize.apply(face_vertices, textures, dict(
+            image_size=image_size, background_color=list(background_color), near=near, far=far, fill_back=fill_back,
+            eps=eps, sigma_val=sigma_val, dist_func=dist_func, dist_eps=dist_eps, gamma_val=gamma_val,
+            aggr_func_rgb=aggr_func_rgb, aggr_func_alpha=aggr_func_alpha, texture_type=texture_type))
+
+    monkeypatch.setattr(rast.srf, "soft_rasterize", fake)
+    n2, N, S = 2 * bs, 2 * bs * H, 12
+    bones = None
+    if B > 1:
+        bones = {k: I(k) for k in ("ctl_ts", "ctl_rs", "log_ctl", "rest_ts")}
+        skin = gu.skin_weights(bones["ctl_ts"], bones["ctl_rs"], bones["log_ctl"], I("pred_v").view(n2, H, V, 3)[0], H)
+        np.testing.assert_allclose(skin.numpy(), O_("skin")[:H], rtol=2e-5, atol=1e-7)       # S0 (given the conversion)
+    Rmat = I("quat").view(-1, 3, 3).permute(0, 2, 1).contiguous()            # mesh_net.py:259
+    Tmat = torch.cat([I("trans"), I("depth")], 1)                            # :260
+    rng = np.random.RandomState(0)
+    faces = torch.from_numpy(rng.randint(0, V, (1, 12, 3)).astype(np.int32)).repeat(n2, 1, 1)
+    gt = torch.Generator().manual_seed(1)
+    batch = dict(masks=(torch.rand(n2, S, S, generator=gt) > 0.4).float(), imgs=torch.rand(n2, 3, S, S, generator=gt),
+                 flow=torch.randn(n2, 3, S, S, generator=gt) * 0.05, occ=torch.randn(n2, S, S, generator=gt))
+    m = hotpath.RenderHotPath(hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B))
+    out = m(I("pred_v"), torch.rand(N, V, 3, generator=gt), faces, Rmat, Tmat, I("ppoint"), I("scale"), batch, bones)
+    np.testing.assert_allclose(out["verts_px"].detach().numpy(), O_("verts_fl"), rtol=2e-5, atol=2e-6)
+    assert abs(float(out["near"]) - float(O_("near"))) < 1e-5 and abs(float(out["far"]) - float(O_("far"))) < 1e-5
