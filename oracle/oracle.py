@@ -18,7 +18,9 @@ Parity status: rasterizer pinned against the reference kernels run on a B200
 (tests/golden/softras_ref_*.npz); G1/G2/R2 pinned against the reference's own Python imported
 on CPU (tests/golden/geom_ref.npz); L1-L3 pinned against the reference's own source lines
 (nnutils/mesh_net.py:361-363, 372-447, executed unmodified on CPU tensors by tests/golden/make_losses_golden.py ->
-tests/golden/losses_ref.npz); S0 (kornia 0.5.3 quaternion convention, not vendored) is **parity unpinned**.
+tests/golden/losses_ref.npz); R1's flow re-projection likewise (mesh_net.py:75-104 -> flow_ref.npz) and the region's
+posing G1-G3 + S0's weights (mesh_net.py:259-311 -> region_ref.npz); of S0 only kornia 0.5.3's quaternion conversion
+(not vendored) remains **parity unpinned**.
 """
 from __future__ import annotations
 
