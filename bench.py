@@ -580,6 +580,18 @@ def run_gpu_arm(args, arm_cls):
                                  "section 4); measured DRAM traffic is below the algorithmic bytes because the images the "
                                  "forward just wrote are still L2-resident"},
         }
+        try:   # the binding resource as a fraction: warp instructions of the profiled launch over the LIVE kernel time,
+               # against the issue peak (SMs x 4 schedulers x 1 instruction per clock at the sampled SM clock)
+            br = out["roofline"]["binding_resource"]
+            if br and br.get("warp_instructions") and N == 64 and F == 5856 and S == 256:
+                props = torch.cuda.get_device_properties(device)
+                mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+                peak_issue = props.multi_processor_count * 4 * mhz * 1e6
+                ach_issue = float(br["warp_instructions"]) / (bwd_ms * 1e-3)
+                br.update(achieved_warp_inst_per_s=ach_issue, peak_warp_inst_per_s=peak_issue,
+                          issue_frac=ach_issue / peak_issue)
+        except Exception:
+            pass
         if world == 1 and arm.name == "ours" and args.extras:
             out["extras"] = extras_microbench(device, peak)
         if world == 1 and not args.no_cpu_baseline:
