@@ -392,3 +392,37 @@ def test_region_posing_matches_the_reference_source_lines(monkeypatch, case):
     out = m(I("pred_v"), torch.rand(N, V, 3, generator=gt), faces, Rmat, Tmat, I("ppoint"), I("scale"), batch, bones)
     np.testing.assert_allclose(out["verts_px"].detach().numpy(), O_("verts_fl"), rtol=2e-5, atol=2e-6)
     assert abs(float(out["near"]) - float(O_("near"))) < 1e-5 and abs(float(out["far"]) - float(O_("far"))) < 1e-5
+
+
+@pytest.mark.parametrize("case", ["b1", "b3", "b3h2"])
+def test_whole_region_matches_the_reference_lines_running_on_the_drop_in_package(monkeypatch, case):
+    """tests/golden/region_losses_ref.npz: the reference's own LASR.forward lines (nnutils/mesh_net.py:259-447 and its
+    render_flow_soft_2, :75-104), executed on CPU tensors ON TOP OF lasr_b200.soft_renderer (oracle as the rasterizer
+    backend), give these renders and losses.  RenderHotPath -- the one-call replacement of that region -- must give
+    the same from the same inputs: rendered silhouette and flow, and the three losses."""
+    from lasr_b200 import hotpath
+    import lasr_b200.soft_renderer.rasterizer as rast
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "region_losses_ref.npz"))
+    bs, H, B, S = (int(v) for v in g[f"{case}/meta"])
+    I = lambda k: torch.from_numpy(g[f"{case}/in/{k}"])
+    W = lambda k: g[f"{case}/out/{k}"]
+
+    def fake(face_vertices, textures, image_size=256, background_color=[0, 0, 0], near=1, far=100, fill_back=True,
+             eps=1e-3, sigma_val=1e-5, dist_func="euclidean", dist_eps=1e-4, gamma_val=1e-4, aggr_func_rgb="softmax",
+             aggr_func_alpha="prod", texture_type="surface"):
+        return _OracleRasterize.apply(face_vertices, textures, dict(
+            image_size=image_size, background_color=list(background_color), near=near, far=far, fill_back=fill_back,
+            eps=eps, sigma_val=sigma_val, dist_func=dist_func, dist_eps=dist_eps, gamma_val=gamma_val,
+            aggr_func_rgb=aggr_func_rgb, aggr_func_alpha=aggr_func_alpha, texture_type=texture_type))
+
+    monkeypatch.setattr(rast.srf, "soft_rasterize", fake)
+    bones = {k: I(k) for k in ("ctl_ts", "ctl_rs", "log_ctl", "rest_ts")} if B > 1 else None
+    Rmat = I("quat").view(-1, 3, 3).permute(0, 2, 1).contiguous()            # mesh_net.py:259
+    Tmat = torch.cat([I("trans"), I("depth")], 1)                            # :260
+    batch = dict(masks=I("masks"), imgs=I("imgs"), flow=I("flow"), occ=I("occ"))
+    m = hotpath.RenderHotPath(hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B, l1tex_wt=1.0))
+    out = m(I("pred_v"), I("tex"), I("faces"), Rmat, Tmat, I("ppoint"), I("scale"), batch, bones)
+    np.testing.assert_allclose(out["mask_pred"].detach().numpy(), W("mask_pred"), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(out["flow_rd"].detach().numpy(), W("flow_rd"), rtol=0, atol=5e-6)
+    for ours, ref in (("mask_loss", "mask_loss"), ("flow_loss", "flow_rd_loss"), ("texture_loss", "texture_loss"), ("total", "total_loss")):
+        assert abs(float(out[ours]) - float(W(ref))) < 2e-6, (ours, float(out[ours]), float(W(ref)))
