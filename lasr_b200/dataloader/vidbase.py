@@ -38,8 +38,11 @@ class BaseDataset(Dataset):
             if frames[k].ndim == 2:                       # grey frames are replicated (vidbase.py:61-65)
                 frames[k] = np.repeat(frames[k][:, :, None], 3, axis=2)
             if masks[k].shape[:2] != frames[k].shape[:2]:
-                raise ValueError("mask / frame size mismatch: resize + erode the masks offline "
-                                 "(the reference does it per item, vidbase.py:67-76)")
+                # masks stored at another resolution: nearest-neighbour resize to the frame, then erode -- two
+                # iterations for frame 0, one for its partner, as the reference does (vidbase.py:67-76)
+                from scipy.ndimage import binary_erosion
+                m = cv2.resize(masks[k], frames[k].shape[:2][::-1], interpolation=cv2.INTER_NEAREST)
+                masks[k] = binary_erosion(m, iterations=2 if k == 0 else 1).astype(np.uint8) * 255
         if forward:                                       # vidbase.py:85-90
             flowpath, flowpathn = self.flowfwlist[im0idx], self.flowbwlist[im0idx + self.dframe]
         else:

@@ -36,7 +36,7 @@ def smooth(rng, shape, sigma):
     return cv2.GaussianBlur(rng.normal(size=shape).astype(np.float32), (0, 0), sigma)
 
 
-def synth_video(tmp, n_frames=3, H=96, W=136, seed=0, centre=(52, 40), step=(9, 4), axes=(24.0, 17.0)):
+def synth_video(tmp, n_frames=3, H=96, W=136, seed=0, centre=(52, 40), step=(9, 4), axes=(24.0, 17.0), mask_scale=1):
     import cv2
     rng = np.random.RandomState(seed)
     lists = dict(img=[], mask=[], fw=[], bw=[], cam=[])
@@ -47,6 +47,8 @@ def synth_video(tmp, n_frames=3, H=96, W=136, seed=0, centre=(52, 40), step=(9, 
         mask = ((((xx - cx) / (axes[0] + 2 * t)) ** 2 + ((yy - cy) / (axes[1] + t)) ** 2) < 1).astype(np.uint8) * 255
         p = dict(img=f"{tmp}/img-{t:05d}.png", mask=f"{tmp}/mask-{t:05d}.png", fw=f"{tmp}/flo-fw-{t:05d}.pfm",
                  bw=f"{tmp}/flo-bw-{t:05d}.pfm", cam=f"{tmp}/cam-{t:05d}.txt")
+        if mask_scale != 1:          # masks stored at another resolution: the reference resizes + erodes them per item
+            mask = cv2.resize(mask, (W // mask_scale, H // mask_scale), interpolation=cv2.INTER_NEAREST)
         cv2.imwrite(p["img"], img); cv2.imwrite(p["mask"], mask)
         for d in ("fw", "bw"):
             flow = np.zeros((H, W, 3), np.float32)
@@ -72,8 +74,10 @@ def main():
 
     out = {}
     # video "" : object well inside the frame; video "b_": object at the frame corner, so the square crop reaches
-    # outside the image and cv2.remap's constant border (complement colour / zeros) is exercised
-    videos = {"": dict(seed=0), "b_": dict(seed=1, H=80, W=120, centre=(22, 14), step=(-3, 2), axes=(26.0, 15.0))}
+    # outside the image and cv2.remap's constant border (complement colour / zeros) is exercised; video "m_": masks
+    # stored at half resolution (the reference resizes them to the frame and erodes them, vidbase.py:67-76)
+    videos = {"": dict(seed=0), "b_": dict(seed=1, H=80, W=120, centre=(22, 14), step=(-3, 2), axes=(26.0, 15.0)),
+              "m_": dict(seed=2, H=64, W=96, centre=(44, 30), step=(4, 2), axes=(20.0, 14.0), mask_scale=2)}
     for pre, kw in videos.items():
         with tempfile.TemporaryDirectory() as tmp:
             L = synth_video(tmp, **kw)

@@ -105,6 +105,41 @@ def test_raw_dataset_decodes_what_the_reference_decodes(tmp_path):
     assert tuple(batch["frames_bgr"].shape) == (3, 2) + GOLD["frames_bgr"].shape[1:] and batch["flows"].dtype == torch.float32
 
 
+def test_masks_at_another_resolution_are_resized_and_eroded_like_the_reference(tmp_path):
+    """Video "m_" of the golden file stores its masks at half resolution: the reference resizes them to the frame and
+    erodes them (two iterations for frame 0, one for its partner, dataloader/vidbase.py:67-76) before everything else.
+    The raw dataset must hand over masks from which the oracle reproduces the reference's items."""
+    cv2 = pytest.importorskip("cv2")
+    from lasr_b200.dataloader import BaseDataset
+    pre = "m_"
+    n = len(GOLD[pre + "frames_bgr"])
+    L = dict(img=[], mask=[], fw=[], bw=[])
+    for t in range(n):
+        p = dict(img=str(tmp_path / f"img-{t}.png"), mask=str(tmp_path / f"mask-{t}.png"),
+                 fw=str(tmp_path / f"flo-fw-{t}.pfm"), bw=str(tmp_path / f"flo-bw-{t}.pfm"))
+        cv2.imwrite(p["img"], GOLD[pre + "frames_bgr"][t]); cv2.imwrite(p["mask"], GOLD[pre + "masks"][t])
+        for d in ("fw", "bw"):
+            write_pfm(p[d], GOLD[pre + f"flow_{d}"][t]); write_pfm(p[d].replace("flo-", "occ-"), GOLD[pre + f"occ_{d}"][t])
+        for k in L:
+            L[k].append(p[k])
+    assert GOLD[pre + "masks"].shape[1] * 2 == GOLD[pre + "frames_bgr"].shape[1]
+    ds = BaseDataset(types.SimpleNamespace(img_size=S))
+    ds.imglist, ds.masklist, ds.flowfwlist, ds.flowbwlist = L["img"], L["mask"], L["fw"], L["bw"]
+    ds.baselist, ds.directlist = list(GOLD[pre + "baselist"]), list(GOLD[pre + "directlist"])
+    ds.dframe, ds.can_frame, ds.num_imgs = 1, 0, len(GOLD[pre + "baselist"])
+    for it in GOLD[pre + "items"]:
+        raw = ds[int(it)]
+        assert raw["masks"].shape[1:] == raw["frames_bgr"].shape[1:3] and raw["masks"].dtype == np.uint8
+        r = OD.preprocess_pair(raw["frames_bgr"][0], raw["masks"][0], raw["flows"][0], raw["occs"][0],
+                               raw["frames_bgr"][1], raw["masks"][1], raw["flows"][1], raw["occs"][1], S)
+        for k in KEYS:
+            ref = GOLD[f"{pre}item{it}/{k}"]
+            if k in ("img", "imgn"):
+                np.testing.assert_allclose(r[k], ref, rtol=0, atol=1e-15, err_msg=f"{it}/{k}")
+            else:
+                assert np.array_equal(r[k], ref), (it, k)
+
+
 def test_pair_selection_follows_the_reference():
     from lasr_b200.dataloader import pair_frame_indices
     for pre in VIDEOS:
