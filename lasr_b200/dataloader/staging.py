@@ -15,11 +15,13 @@ import torch
 from .. import _cabi
 
 
-def stage_pairs(frames_bgr, masks, flows, occs, img_size):
+def stage_pairs(frames_bgr, masks, flows, occs, img_size, cam_init=None):
     """frames_bgr [P,2,H,W,3] uint8, masks [P,2,H,W] uint8, flows [P,2,H,W,3] float32, occs [P,2,H,W] float32
     (CUDA, contiguous; slot 0 = frame 0 with the flow 0->n, slot 1 = frame n with the flow n->0).
     Returns the collated batch: img / imgn [P,3,S,S], mask [P,2,S,S], flow / flown [P,3,S,S], occ / occn [P,S,S],
-    cam / camn [P,7], pps [P,2,2] (float32, CUDA) and 'boxes' [P,2,4] int32 (cx, cy, L, mask pixels)."""
+    cam / camn [P,7], pps [P,2,2] (float32, CUDA) and 'boxes' [P,2,4] int32 (cx, cy, L, mask pixels).
+    cam_init [P,2,7] (optional): the rows of the per-frame camera files (``collate_raw``'s 'cam_init'); the staged
+    cameras keep their entries 1..6 and get the focal scale 1/alp in entry 0, as the reference does."""
     if frames_bgr.dim() != 5 or frames_bgr.shape[1] != 2 or frames_bgr.shape[4] != 3:
         raise RuntimeError("stage_pairs: frames_bgr must be [P,2,H,W,3]")
     P, _, H, W, _ = frames_bgr.shape
@@ -37,8 +39,10 @@ def stage_pairs(frames_bgr, masks, flows, occs, img_size):
     _cabi.native_call("stage_pairs", frames_bgr.contiguous(), masks.contiguous(), flows.contiguous().float(),
                       occs.contiguous().float(), img, mask, flow, occ, focal, pps, boxes, ws, ws.numel(), P, H, W, S)
     cam = torch.zeros(P, 2, 7, **f32)              # [1/alp, 0, 0, 1, 0, 0, 0]   (vidbase.py:167-183)
-    cam[:, :, 0] = focal
     cam[:, :, 3] = 1.0
+    if cam_init is not None:                       # per-frame camera files: everything but the focal scale (:174-181)
+        cam[:, :, 1:] = torch.as_tensor(cam_init, dtype=torch.float32).to(dev)[:, :, 1:]
+    cam[:, :, 0] = focal
     return {"img": img[:, 0], "imgn": img[:, 1], "mask": mask, "flow": flow[:, 0], "flown": flow[:, 1],
             "occ": occ[:, 0], "occn": occ[:, 1], "cam": cam[:, 0], "camn": cam[:, 1], "pps": pps, "boxes": boxes}
 
@@ -91,7 +95,7 @@ class DeviceStager:
             ev.record(self._stream)
             self._uploaded[slot] = ev
             self._out = stage_pairs(self._dev["frames_bgr"], self._dev["masks"], self._dev["flows"], self._dev["occs"],
-                                    self.S)
+                                    self.S, cam_init=raw.get("cam_init") if hasattr(raw, "get") else None)
             self._done.record(self._stream)
         return self
 

@@ -7,6 +7,8 @@ Decode needs OpenCV like the reference (``cv2.imread``); the PFM reader is ``pfm
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 from torch.utils.data import Dataset
@@ -49,7 +51,18 @@ class BaseDataset(Dataset):
             flowpath, flowpathn = self.flowbwlist[im0idx], self.flowfwlist[im0idx - self.dframe]
         flows = [np.ascontiguousarray(readPFM(p)[0], np.float32) for p in (flowpath, flowpathn)]
         occs = [np.ascontiguousarray(readPFM(p.replace("flo-", "occ-"))[0], np.float32) for p in (flowpath, flowpathn)]
-        return {"frames_bgr": np.stack(frames), "masks": np.stack(masks), "flows": np.stack(flows),
+        # per-frame camera files [focal, tx, ty, qw, qx, qy, qz, depth] when the dataset has them (vidbase.py:167-183);
+        # the focal entry is replaced by the crop's scale on the device
+        cam_init = np.tile(np.asarray([1., 0., 0., 1., 0., 0., 0.], np.float32), (2, 1))
+        depth = np.zeros(2, np.float32)
+        camlist = getattr(self, "camlist", None)
+        if camlist is not None and os.path.exists(camlist[im0idx]):
+            for k, i in enumerate((im0idx, im1idx)):
+                c = np.loadtxt(camlist[i]).astype(np.float32)
+                cam_init[k] = c[:-1]
+                depth[k] = c[-1]
+        return {"cam_init": cam_init, "depth": depth,
+                "frames_bgr": np.stack(frames), "masks": np.stack(masks), "flows": np.stack(flows),
                 "occs": np.stack(occs), "inds": index, "indsn": index, "id0": im0idx, "id1": im1idx,
                 "is_canonical": self.can_frame == im0idx, "is_canonicaln": self.can_frame == im1idx,
                 "dataid": getattr(self, "dataid", 0), "shape": np.asarray(frames[0].shape[:2][::-1]).copy()}
@@ -57,7 +70,7 @@ class BaseDataset(Dataset):
 
 def collate_raw(items):
     """Stack raw items into the [P,2,...] arrays ``stage_pairs`` / ``DeviceStager.submit`` take."""
-    out = {k: torch.from_numpy(np.stack([it[k] for it in items])) for k in ("frames_bgr", "masks", "flows", "occs", "shape")}
+    out = {k: torch.from_numpy(np.stack([it[k] for it in items])) for k in ("frames_bgr", "masks", "flows", "occs", "shape", "cam_init", "depth")}
     for k in ("inds", "indsn", "id0", "id1", "is_canonical", "is_canonicaln", "dataid"):
         out[k] = torch.as_tensor([it[k] for it in items])
     return out

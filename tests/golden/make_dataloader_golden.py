@@ -36,7 +36,8 @@ def smooth(rng, shape, sigma):
     return cv2.GaussianBlur(rng.normal(size=shape).astype(np.float32), (0, 0), sigma)
 
 
-def synth_video(tmp, n_frames=3, H=96, W=136, seed=0, centre=(52, 40), step=(9, 4), axes=(24.0, 17.0), mask_scale=1):
+def synth_video(tmp, n_frames=3, H=96, W=136, seed=0, centre=(52, 40), step=(9, 4), axes=(24.0, 17.0), mask_scale=1,
+                cam_files=False):
     import cv2
     rng = np.random.RandomState(seed)
     lists = dict(img=[], mask=[], fw=[], bw=[], cam=[])
@@ -50,6 +51,8 @@ def synth_video(tmp, n_frames=3, H=96, W=136, seed=0, centre=(52, 40), step=(9, 
         if mask_scale != 1:          # masks stored at another resolution: the reference resizes + erodes them per item
             mask = cv2.resize(mask, (W // mask_scale, H // mask_scale), interpolation=cv2.INTER_NEAREST)
         cv2.imwrite(p["img"], img); cv2.imwrite(p["mask"], mask)
+        if cam_files:                # per-frame camera file: focal, tx, ty, qw, qx, qy, qz, depth (vidbase.py:174-181)
+            np.savetxt(p["cam"], np.concatenate([[1.0], rng.normal(size=2) * 0.1, rng.normal(size=4), [5 + t]]))
         for d in ("fw", "bw"):
             flow = np.zeros((H, W, 3), np.float32)
             flow[..., :2] = np.round((6 * smooth(rng, (H, W, 2), 5.0) * 5 + (3 if d == "fw" else -3)) * 32) / 32   # 1/32 px: compresses
@@ -75,9 +78,10 @@ def main():
     out = {}
     # video "" : object well inside the frame; video "b_": object at the frame corner, so the square crop reaches
     # outside the image and cv2.remap's constant border (complement colour / zeros) is exercised; video "m_": masks
-    # stored at half resolution (the reference resizes them to the frame and erodes them, vidbase.py:67-76)
+    # stored at half resolution (the reference resizes them to the frame and erodes them, vidbase.py:67-76) and per-frame
+    # camera files (:174-181)
     videos = {"": dict(seed=0), "b_": dict(seed=1, H=80, W=120, centre=(22, 14), step=(-3, 2), axes=(26.0, 15.0)),
-              "m_": dict(seed=2, H=64, W=96, centre=(44, 30), step=(4, 2), axes=(20.0, 14.0), mask_scale=2)}
+              "m_": dict(seed=2, H=64, W=96, centre=(44, 30), step=(4, 2), axes=(20.0, 14.0), mask_scale=2, cam_files=True)}
     for pre, kw in videos.items():
         with tempfile.TemporaryDirectory() as tmp:
             L = synth_video(tmp, **kw)
@@ -93,12 +97,14 @@ def main():
             # decoded inputs, exactly as the reference decodes them
             out[pre + "frames_bgr"] = np.stack([cv2.imread(p) for p in L["img"]])
             out[pre + "masks"] = np.stack([cv2.imread(p, 0) for p in L["mask"]])
+            if os.path.exists(L["cam"][0]):
+                out[pre + "cams"] = np.stack([np.loadtxt(p) for p in L["cam"]])
             for d in ("fw", "bw"):
                 out[pre + f"flow_{d}"] = np.stack([np.ascontiguousarray(readPFM(p)[0]) for p in L[d]])
                 out[pre + f"occ_{d}"] = np.stack([np.ascontiguousarray(readPFM(p.replace("flo-", "occ-"))[0]) for p in L[d]])
             for i in items:
                 elem = ds[i]
-                for k in ("img", "imgn", "mask", "flow", "flown", "occ", "occn", "cam", "camn", "pps", "shape", "id0", "id1"):
+                for k in ("img", "imgn", "mask", "flow", "flown", "occ", "occn", "cam", "camn", "pps", "shape", "id0", "id1", "depth", "depthn"):
                     out[pre + f"item{i}/{k}"] = np.asarray(elem[k])
     path = os.path.join(ROOT, "tests", "golden", "dataloader_ref.npz")
     np.savez_compressed(path, **out)

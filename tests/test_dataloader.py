@@ -123,7 +123,12 @@ def test_masks_at_another_resolution_are_resized_and_eroded_like_the_reference(t
         for k in L:
             L[k].append(p[k])
     assert GOLD[pre + "masks"].shape[1] * 2 == GOLD[pre + "frames_bgr"].shape[1]
+    camlist = []
+    for t in range(n):                   # this video also has per-frame camera files (vidbase.py:174-181)
+        camlist.append(str(tmp_path / f"cam-{t}.txt"))
+        np.savetxt(camlist[-1], GOLD[pre + "cams"][t])
     ds = BaseDataset(types.SimpleNamespace(img_size=S))
+    ds.camlist = camlist
     ds.imglist, ds.masklist, ds.flowfwlist, ds.flowbwlist = L["img"], L["mask"], L["fw"], L["bw"]
     ds.baselist, ds.directlist = list(GOLD[pre + "baselist"]), list(GOLD[pre + "directlist"])
     ds.dframe, ds.can_frame, ds.num_imgs = 1, 0, len(GOLD[pre + "baselist"])
@@ -136,8 +141,23 @@ def test_masks_at_another_resolution_are_resized_and_eroded_like_the_reference(t
             ref = GOLD[f"{pre}item{it}/{k}"]
             if k in ("img", "imgn"):
                 np.testing.assert_allclose(r[k], ref, rtol=0, atol=1e-15, err_msg=f"{it}/{k}")
+            elif k in ("cam", "camn"):      # entries 1..6 come from the camera file, entry 0 is the crop's focal scale
+                slot = 0 if k == "cam" else 1
+                assert r[k][0] == ref[0]
+                np.testing.assert_allclose(raw["cam_init"][slot][1:], ref[1:], rtol=1e-6)
             else:
                 assert np.array_equal(r[k], ref), (it, k)
+        np.testing.assert_allclose(raw["depth"], [float(GOLD[f"{pre}item{it}/depth"][0]), float(GOLD[f"{pre}item{it}/depthn"][0])])
+
+
+def test_cameras_default_to_identity_without_camera_files():
+    from lasr_b200.dataloader import collate_raw
+    item = {"frames_bgr": np.zeros((2, 4, 4, 3), np.uint8), "masks": np.zeros((2, 4, 4), np.uint8),
+            "flows": np.zeros((2, 4, 4, 3), np.float32), "occs": np.zeros((2, 4, 4), np.float32), "shape": np.asarray([4, 4]),
+            "cam_init": np.tile(np.asarray([1., 0, 0, 1, 0, 0, 0], np.float32), (2, 1)), "depth": np.zeros(2, np.float32),
+            "inds": 0, "indsn": 0, "id0": 0, "id1": 1, "is_canonical": True, "is_canonicaln": False, "dataid": 0}
+    b = collate_raw([item, item])
+    assert tuple(b["cam_init"].shape) == (2, 2, 7) and tuple(b["depth"].shape) == (2, 2)
 
 
 def test_pair_selection_follows_the_reference():
