@@ -484,6 +484,78 @@ __device__ __forceinline__ int surface_texel(const float* wc, int R) {
   return ((wc[0] + wc[1]) * R - wx - wy <= 1.f) ? (wy * R + wx) : ((R - 1 - wy) * R + (R - 1 - wx));
 }
 
+// ---- forward: per-pixel state and the evaluation of one (pixel, face) pair ---------------------------------
+// (in this header rather than in raster.cu so that the host harness can run the forward's own code on the CPU:
+// tests/host_harness, tests/test_kernel_math_host.py)
+#ifndef LASR_FTZ_MUFU_FWD           // bare FTZ MUFU reciprocal / ex2 in the forward (faster) ...
+#define LASR_FTZ_MUFU_FWD 1
+#endif
+template <int K>
+struct PixelState {
+  float alpha;             // running product / sum / flag
+  float ssum, smax;        // online softmax state
+  float col[3 * K];        // K colour sets share the geometry work of one pass
+  float depth_min;         // hard rgb
+  int face_min;
+};
+
+struct FwdConsts {
+  float thr, near_, far_, inv_range;
+};
+
+template <bool kFast, int K>
+__device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConsts& C, const float* __restrict__ rec,
+                                             float4 bd, int face, int n, float xp, float yp, PixelState<K>& st) {
+  constexpr int kMode = kFast ? (LASR_FTZ_MUFU_FWD ? 2 : 1) : 0;   // arithmetic mode, see raster_common.cuh
+  // exact border predicate of the reference (.cu:32-38,375)
+  if (xp > bd.y || xp < bd.x || yp > bd.w || yp < bd.z) return;
+  FaceGeom g;
+  float tex9[9 * K];
+  load_record<K>(rec, g, tex9);
+  Fragment fr;
+  if (!soft_fragment<kMode>(A, g, xp, yp, C.thr, fr)) return;
+  const int alpha_f = kFast ? 2 : A.alpha;
+  const int rgb_f = kFast ? 1 : A.rgb;
+  const int sample = kFast ? 1 : A.sample;
+  // alpha aggregation (.cu:408-417)
+  if (alpha_f == 0) { if (fr.frag > 0.5f) st.alpha = 1.f; }
+  else if (alpha_f == 1) st.alpha += fr.frag;
+  else st.alpha *= 1.f - fr.frag;
+  // clipped-barycentric depth (.cu:421-424)
+  float wc[3];
+  const float zp = clip_and_depth<kMode>(g, fr.w, wc);
+  if (zp < C.near_ || zp > C.far_) return;
+  const bool visible = g.front || (kFast ? true : A.double_side != 0);
+  auto sample_tex = [&](int k) -> float {   // k = 3*set + channel
+    if (sample == 1) {
+      const float* t = tex9 + 9 * (k / 3);
+      return wc[0] * t[k % 3] + wc[1] * t[3 + k % 3] + wc[2] * t[6 + k % 3];
+    }
+    const long long base = ((long long)n * A.F + face) * A.T * 3;
+    const long long idx = base + (long long)surface_texel(wc, A.R) * 3 + k;
+    return idx < (long long)A.N * A.F * A.T * 3 ? A.textures[idx] : 0.f;
+  };
+  if (rgb_f == 0) {  // hard z-buffer (.cu:428-435)
+    if (zp < st.depth_min && pixel_inside(fr.w) && visible) {
+      st.depth_min = zp;
+      st.face_min = face;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) st.col[k] = sample_tex(k);
+    }
+  } else if (visible) {  // depth softmax, online (.cu:437-451)
+    const float zn = kFast ? (C.far_ - zp) * C.inv_range : (C.far_ - zp) / (C.far_ - C.near_);
+    float rescale = 1.f;
+    if (zn > st.smax) {
+      rescale = kFast ? fast_exp<kMode>((st.smax - zn) * A.inv_gamma) : expf((st.smax - zn) / A.gamma);
+      st.smax = zn;
+    }
+    const float ez = (kFast ? fast_exp<kMode>((zn - st.smax) * A.inv_gamma) : expf((zn - st.smax) / A.gamma)) * fr.frag;
+    st.ssum = rescale * st.ssum + ez;
+#pragma unroll
+    for (int k = 0; k < 3 * K; ++k) st.col[k] = rescale * st.col[k] + ez * sample_tex(k);
+  }
+}
+
 // ---- row spans of the dilated triangle (backward, LASR_BWD_SPANS; not enabled by default) -----------------
 // A pair can only be accepted if the pixel is inside the face or closer than sqrt(threshold) to it, i.e. inside the
 // triangle dilated by a disc -- a convex set whose intersection with a pixel row is ONE interval, ~30 % smaller in

@@ -112,4 +112,44 @@ extern "C" int lasr_host_span_enumerate(const int* rows, int nrows, int* visited
   return total;
 }
 
+// The forward kernel's own pair code (forward_pair<kFast = true, K = 1>: border test, record load, soft fragment, alpha
+// product, clipped-barycentric depth, online depth softmax, colour blend) run on the host for ONE frame: every pixel
+// visits the faces in ascending order, exactly what a warp lane does after the tile / footprint culls (which only
+// skip faces the border test rejects anyway).  State initialisation and the final division mirror the kernel's
+// init_state / finish.  out_rgba [4,S,S], out_aggr [2,S,S]; textures: vertex colours [F,9].
+extern "C" void lasr_host_forward(const float* faces9, const float* tex9, int F, int S, float near_, float far_, float sigma,
+                                  float gamma, float eps, float dist_eps, const float* bg3, float* out_rgba, float* out_aggr) {
+  RasterArgs A{};
+  A.N = 1; A.F = F; A.S = S; A.T = 3; A.K = 1; A.R = 1;
+  A.dist = 2; A.rgb = 1; A.alpha = 2; A.sample = 1; A.double_side = 1;
+  A.near_ = near_; A.far_ = far_; A.eps = eps; A.sigma = sigma; A.dist_eps = dist_eps; A.gamma = gamma;
+  A.inv_sigma = (float)(1.0 / (double)sigma); A.inv_gamma = (float)(1.0 / (double)gamma);
+  FwdConsts C;
+  C.near_ = near_; C.far_ = far_; C.thr = dist_eps * sigma; C.inv_range = 1.f / (far_ - near_);
+  const float sthr = sqrtf(dist_eps * sigma);
+  float* recs = new float[(size_t)F * rec_words(1)];
+  float4* bds = new float4[F];
+  for (int f = 0; f < F; ++f) {
+    FaceGeom g;
+    face_setup(faces9 + 9 * f, sthr, g);
+    store_record<1>(recs + (size_t)f * rec_words(1), g, tex9 + 9 * f);
+    bds[f] = make_float4(g.lox, g.hix, g.loy, g.hiy);
+  }
+  const size_t SS = (size_t)S * S;
+  for (int py = 0; py < S; ++py)
+    for (int px = 0; px < S; ++px) {
+      const float xp = pixel_coord(px, S), yp = pixel_coord(S - 1 - py, S);      // row 0 is the top
+      PixelState<1> st;
+      st.alpha = 1.f; st.ssum = expf(eps / gamma); st.smax = eps; st.depth_min = 10000000.f; st.face_min = -1;
+      for (int k = 0; k < 3; ++k) st.col[k] = bg3[k] * st.ssum;
+      for (int f = 0; f < F; ++f)
+        forward_pair<true, 1>(A, C, recs + (size_t)f * rec_words(1), bds[f], f, 0, xp, yp, st);
+      const size_t pn = (size_t)py * S + px;
+      for (int k = 0; k < 3; ++k) out_rgba[k * SS + pn] = st.col[k] / st.ssum;
+      out_rgba[3 * SS + pn] = 1.f - st.alpha;
+      out_aggr[pn] = st.ssum; out_aggr[SS + pn] = st.smax;
+    }
+  delete[] recs; delete[] bds;
+}
+
 extern "C" int lasr_host_fast_inside(void) { return LASR_FAST_INSIDE; }

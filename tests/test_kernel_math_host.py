@@ -170,3 +170,29 @@ def test_span_enumeration_visits_every_span_pixel_exactly_once(libs):
         total = libs[1].lasr_host_span_enumerate(P(rows), ctypes.c_int(n), P(out))
         want = [(x, r) for r in range(n) for x in range(rows[r, 0], rows[r, 1] + 1)]
         assert total == len(want) and [tuple(v) for v in out[:total]] == want
+
+
+# ---- the forward kernel's own pair code on the host -------------------------------------------------------------------
+@pytest.mark.parametrize("mesh,S,sigma,bg", [("ico2", 64, 1e-4, (0, 0, 0)), ("bumpy2", 96, 1e-4, (0, 0, 0)),
+                                             ("ico2", 64, 1e-5, (1, 1, 1)), ("spot", 128, 1e-4, (0, 0, 0))])
+def test_forward_pair_code_run_on_the_host_reproduces_the_oracle(libs, mesh, S, sigma, bg):
+    """forward_pair<kFast, K = 1> -- the function the forward kernel inlines: border test, record load, soft fragment,
+    alpha product, clipped-barycentric depth, online depth softmax, colour blend -- compiled for the host and driven
+    pixel by pixel over all faces in ascending order (lasr_host_forward) must give the oracle's image.  A CPU-side
+    regression net for edits to the kernel arithmetic; the GPU tests check the same code as compiled by nvcc."""
+    from oracle import oracle as O
+    c = cases.lasr_case(mesh, 1, S, sigma=sigma, bg=bg)
+    r = O.soft_rasterize_forward(c["face_vertices"], c["textures"], c["settings"], np.float32)
+    fv = np.ascontiguousarray(c["face_vertices"][0].reshape(-1, 9), np.float32)
+    tx = np.ascontiguousarray(c["textures"][0].reshape(-1, 9), np.float32)
+    s = c["settings"]
+    out = np.zeros((4, S, S), np.float32); agg = np.zeros((2, S, S), np.float32)
+    bgv = np.asarray(bg, np.float32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    F32 = ctypes.c_float
+    libs[1].lasr_host_forward(P(fv), P(tx), ctypes.c_int(len(fv)), ctypes.c_int(S), F32(s["near"]), F32(s["far"]), F32(sigma),
+                              F32(s["gamma_val"]), F32(s["eps"]), F32(DIST_EPS), P(bgv), P(out), P(agg))
+    d = np.abs(out - r["soft_colors"][0])
+    assert d.max() < 5e-5 and int((d > 1e-4 * np.maximum(1, np.abs(r["soft_colors"][0]))).sum()) == 0
+    np.testing.assert_allclose(agg[1], r["aggrs_info"][0][1], rtol=1e-5, atol=1e-7)   # running depth maximum
+    np.testing.assert_allclose(agg[0], r["aggrs_info"][0][0], rtol=5e-4)        # softmax sums
