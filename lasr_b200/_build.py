@@ -13,7 +13,7 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.environ.get("LASR_B200_LIB") or os.path.join(CSRC, "liblasr_b200.so")  # override: A/B builds
 SOURCES = ["host_common.cu", "raster.cu", "lbs.cu", "losses.cu", "skin.cu", "meshreg.cu", "chamfer.cu", "texture_io.cu", "staging.cu"]
-HEADERS = ["raster_common.cuh", "host_common.h"]
+HEADERS = ["raster_common.cuh", "raster_backward_pair.inc", "host_common.h"]
 
 
 def _stale() -> bool:

@@ -553,100 +553,7 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
       const float yp = A.coords[yi];
       if (xp > g.hix || xp < g.lox || yp > g.hiy || yp < g.loy) continue;
       const index_t pn = (index_t)(S - 1 - yi) * (index_t)S + (index_t)xi;
-      Fragment fr;
-      if (!soft_fragment<kMode>(A, g, xp, yp, thr, fr)) continue;
-      // alpha term (.cu:582-593); for 'hard' alpha the reference still adds the raw upstream
-      // gradient (nothing resets C_grad_xy_alpha), reproduced here
-      float Cxy = gs[PLANE(P - 1)];
-      if (alpha_f == 1) Cxy /= A.F;
-      else if (alpha_f == 2) Cxy *= div_<kMode>(1.f - sc[PLANE(P - 1)], fmaxf(1.f - fr.frag, 1e-6f));
-      float wc[3];
-      const float zp = clip_and_depth<kMode>(g, fr.w, wc);
-      if (zp < near_ || zp > far_) continue;
-      float gz[3] = {0.f, 0.f, 0.f};
-      if (rgb_f == 0) {  // .cu:602-609
-        if ((float)f == ag[PLANE(1)]) {   // (hard rgb: generic path only)
-          if (sample == 1) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              const float gk = gs[PLANE(k)];
-#pragma unroll
-              for (int j = 0; j < 3; ++j) gt[3 * j + k] += wc[j] * gk;
-            }
-          } else {
-            const int texel = surface_texel(wc, A.R);
-            if (texel < A.T)
-              for (int k = 0; k < 3; ++k) atomicAdd(&gtex_out[3 * texel + k], gs[PLANE(k)]);
-          }
-        }
-      } else if (g.front || (kFast ? true : A.double_side != 0)) {  // .cu:611-640
-        const float ssum = ag[PLANE(0)], smax = ag[PLANE(1)];
-        const float zn = kFast ? (far_ - zp) * inv_range : (far_ - zp) / (far_ - near_);
-        const float wgt = kFast ? fr.frag * fast_exp<kMode>((zn - smax) * A.inv_gamma) * fast_rcp<kMode>(ssum)
-                                : fr.frag * expf((zn - smax) / A.gamma) / ssum;
-        float Crgb = 0.f;
-        int texel = 0;
-        if (sample == 0) texel = surface_texel(wc, A.R);
-#pragma unroll
-        for (int k = 3 * KF; k < 3 * K; ++k) {   // k = 3*set + channel, live sets only
-          const float gk = gs[PLANE(k)];
-          float ck;
-          if (sample == 1) {
-            const float wg_k = wgt * gk;
-            float* gts = gt + 9 * (k / 3 - KF);
-            const float* ts = tex9 + 9 * (k / 3);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) gts[3 * j + k % 3] += wg_k * wc[j];
-            ck = wc[0] * ts[k % 3] + wc[1] * ts[3 + k % 3] + wc[2] * ts[6 + k % 3];
-          } else {
-            if (texel < A.T) atomicAdd(&gtex_out[3 * texel + k], wgt * gk);
-            const long long ti = wg * A.T * 3 + (long long)texel * 3 + k;
-            ck = ti < (long long)A.N * A.F * A.T * 3 ? A.textures[ti] : 0.f;
-          }
-          Crgb += gk * (ck - sc[PLANE(k)]);
-        }
-        Crgb *= wgt;
-        Cxy += div_<kMode>(Crgb, fr.frag);
-        if (kFast) {
-          const float Cz = Crgb * cz_scale * zp * zp;
-          gz[0] = Cz * wc[0] * g.iz[0] * g.iz[0];
-          gz[1] = Cz * wc[1] * g.iz[1] * g.iz[1];
-          gz[2] = Cz * wc[2] * g.iz[2] * g.iz[2];
-        } else {
-          const float Cz = Crgb / A.gamma / (near_ - far_) * zp * zp;
-          gz[0] = Cz * wc[0] / g.z[0] / g.z[0];
-          gz[1] = Cz * wc[1] / g.z[1] / g.z[1];
-          gz[2] = Cz * wc[2] / g.z[2] / g.z[2];
-        }
-      }
-      Cxy *= kFast ? fr.frag * (1.f - fr.frag) * A.inv_sigma : fr.frag * (1.f - fr.frag) / A.sigma;  // .cu:644
-      float gx[3] = {0.f, 0.f, 0.f}, gy[3] = {0.f, 0.f, 0.f};
-      if (dist_f == 1) {  // .cu:161-175
-        const float* w = fr.t;
-        const int p = w[0] > w[1] ? (w[1] > w[2] ? 2 : 1) : (w[0] > w[2] ? 2 : 0);
-        const float sc2 = fr.dis > 0.f ? 2.f * sqrtf(fr.dis) : 2.f * sqrtf(-fr.dis);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          float ax = 0.f, ay = 0.f;
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const float pq = q == 0 ? xp : (q == 1 ? yp : 1.f);
-            ax += -g.inv[3 * p + 0] * g.inv[3 * k + q] * pq;
-            ay += -g.inv[3 * p + 1] * g.inv[3 * k + q] * pq;
-          }
-          gx[k] = ax * Cxy * sc2;
-          gy[k] = ay * Cxy * sc2;
-        }
-      } else if (dist_f == 2) {  // .cu:649-655
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float c = 2.f * fr.sign * Cxy * (fr.t[k] + fr.w[k]);
-          gx[k] = c * fr.dx;
-          gy[k] = c * fr.dy;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { gf[3 * k] += gx[k]; gf[3 * k + 1] += gy[k]; gf[3 * k + 2] += gz[k]; }
+#include "raster_backward_pair.inc"   // one (pixel, face) pair -> gf / gt
     }
   }
   // fixed-order reduction (16 values by recursive halving + 2 butterflies), one write per value

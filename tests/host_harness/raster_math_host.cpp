@@ -20,6 +20,7 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fdividef(float a, float b) { return a / b; }
 #define __expf(x) expf(x)
 static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
+static inline float atomicAdd(float* p, float v) { const float o = *p; *p = o + v; return o; }
 #define LASR_HOST_STATS 1
 static long long lasr_host_inside_pairs = 0, lasr_host_all_edges_pairs = 0;
 template <class T> static inline T __ldg(const T* p) { return *p; }
@@ -150,6 +151,49 @@ extern "C" void lasr_host_forward(const float* faces9, const float* tex9, int F,
       out_aggr[pn] = st.ssum; out_aggr[SS + pn] = st.smax;
     }
   delete[] recs; delete[] bds;
+}
+
+// The backward kernel's own pixel-loop body (raster_backward_pair.inc, included textually exactly as the kernel includes
+// it) run on the host for ONE frame: every face sweeps its pixel window, as a warp does, and sums the pairs'
+// contributions (sequentially here; the kernel sums per lane and reduces in a fixed order).  LASR configuration
+// (kFast), one colour set.  grad_faces [F,9], grad_tex [F,9].
+extern "C" void lasr_host_backward(const float* faces9, const float* textures9, int F, int S, float near_, float far_,
+                                   float sigma, float gamma, float eps, float dist_eps, const float* soft_colors,
+                                   const float* aggrs, const float* grad_soft_colors, float* grad_faces, float* grad_tex) {
+  constexpr bool kFast = true;
+  constexpr int kMode = 1, K = 1, KF = 0, P = 3 * K + 1;
+  RasterArgs A{};
+  A.N = 1; A.F = F; A.S = S; A.T = 3; A.K = 1; A.R = 1;
+  A.dist = 2; A.rgb = 1; A.alpha = 2; A.sample = 1; A.double_side = 1;
+  A.near_ = near_; A.far_ = far_; A.eps = eps; A.sigma = sigma; A.dist_eps = dist_eps; A.gamma = gamma;
+  A.inv_sigma = (float)(1.0 / (double)sigma); A.inv_gamma = (float)(1.0 / (double)gamma);
+  const float thr = dist_eps * sigma, sthr = sqrtf(thr);
+  const float inv_range = 1.f / (far_ - near_), cz_scale = A.inv_gamma / (near_ - far_);
+  const int dist_f = 2, rgb_f = 1, alpha_f = 2, sample = 1;
+  (void)dist_f; (void)rgb_f; (void)alpha_f; (void)sample;
+  const long long SS = (long long)S * S;
+  const float *sc = soft_colors, *ag = aggrs, *gs = grad_soft_colors;
+  for (int f = 0; f < F; ++f) {
+    const long long wg = f;
+    FaceGeom g;
+    face_setup(faces9 + 9 * f, sthr, g);
+    const float* tex9 = textures9 + 9 * f;
+    float* gtex_out = grad_tex + 9 * f;
+    float gf[9] = {0}, gt[9] = {0};
+    int xlo, xhi, ylo, yhi;
+    coord_window(g.lox, g.hix, S, xlo, xhi);
+    coord_window(g.loy, g.hiy, S, ylo, yhi);
+    for (int yi = yhi; yi >= ylo && xlo <= xhi; --yi)
+      for (int xi = xlo; xi <= xhi; ++xi) {
+        const float xp = pixel_coord(xi, S), yp = pixel_coord(yi, S);
+        if (xp > g.hix || xp < g.lox || yp > g.hiy || yp < g.loy) continue;
+        const long long pn = (long long)(S - 1 - yi) * S + xi;
+#define PLANE(k) ((k) * SS + pn)
+#include "raster_backward_pair.inc"
+#undef PLANE
+      }
+    for (int k = 0; k < 9; ++k) { grad_faces[9 * f + k] = gf[k]; grad_tex[9 * f + k] = gt[k]; }
+  }
 }
 
 extern "C" int lasr_host_fast_inside(void) { return LASR_FAST_INSIDE; }

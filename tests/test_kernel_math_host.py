@@ -196,3 +196,29 @@ def test_forward_pair_code_run_on_the_host_reproduces_the_oracle(libs, mesh, S, 
     assert d.max() < 5e-5 and int((d > 1e-4 * np.maximum(1, np.abs(r["soft_colors"][0]))).sum()) == 0
     np.testing.assert_allclose(agg[1], r["aggrs_info"][0][1], rtol=1e-5, atol=1e-7)   # running depth maximum
     np.testing.assert_allclose(agg[0], r["aggrs_info"][0][0], rtol=5e-4)        # softmax sums
+
+
+# ---- the backward kernel's own pixel-loop body on the host ------------------------------------------------------------
+@pytest.mark.parametrize("mesh,S,sigma", [("ico2", 64, 1e-4), ("bumpy2", 96, 1e-4), ("ico2", 64, 1e-5), ("spot", 128, 1e-4)])
+def test_backward_pair_code_run_on_the_host_reproduces_the_oracle_gradients(libs, mesh, S, sigma):
+    """raster_backward_pair.inc -- the body of the backward kernel's pixel loop, textually included by the kernel and by
+    the host harness -- swept over every face's pixel window on the CPU (lasr_host_backward) must give the oracle's
+    vertex and colour gradients (north-star tolerance 1e-3; measured ~3e-5)."""
+    from oracle import oracle as O
+    import parity
+    c = cases.lasr_case(mesh, 1, S, sigma=sigma)
+    r = O.soft_rasterize_forward(c["face_vertices"], c["textures"], c["settings"], np.float32)
+    gf, gt = O.soft_rasterize_backward(r, c["grad_soft_colors"])
+    fv = np.ascontiguousarray(c["face_vertices"][0].reshape(-1, 9), np.float32)
+    tx = np.ascontiguousarray(c["textures"][0].reshape(-1, 9), np.float32)
+    s, n = c["settings"], len(fv)
+    ogf = np.zeros((n, 9), np.float32); ogt = np.zeros((n, 9), np.float32)
+    scol = np.ascontiguousarray(r["soft_colors"][0]); agg = np.ascontiguousarray(r["aggrs_info"][0])
+    gsc = np.ascontiguousarray(c["grad_soft_colors"][0])
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    F32 = ctypes.c_float
+    libs[1].lasr_host_backward(P(fv), P(tx), ctypes.c_int(n), ctypes.c_int(S), F32(s["near"]), F32(s["far"]), F32(sigma),
+                               F32(s["gamma_val"]), F32(s["eps"]), F32(DIST_EPS), P(scol), P(agg), P(gsc), P(ogf), P(ogt))
+    for ours, ref in ((ogf, gf.reshape(n, 9)), (ogt, gt.reshape(n, 9))):
+        rep = parity.grad_report(ours, ref)
+        assert rep["rel_l2"] < 2e-4 and rep["max_over_scale"] < 3e-4 and rep["frac_gt_1e3"] == 0, rep
