@@ -156,10 +156,13 @@ extern "C" void lasr_host_forward(const float* faces9, const float* tex9, int F,
 // The backward kernel's own pixel-loop body (raster_backward_pair.inc, included textually exactly as the kernel includes
 // it) run on the host for ONE frame: every face sweeps its pixel window, as a warp does, and sums the pairs'
 // contributions (sequentially here; the kernel sums per lane and reduces in a fixed order).  LASR configuration
-// (kFast), one colour set.  grad_faces [F,9], grad_tex [F,9].
+// (kFast), one colour set.  grad_faces [F,9], grad_tex [F,9].  use_spans: sweep the row spans of the dilated triangle
+// (the experimental LASR_BWD_SPANS path) instead of the whole window -- the accepted pairs, and so every bit of the
+// sums, must be the same.
 extern "C" void lasr_host_backward(const float* faces9, const float* textures9, int F, int S, float near_, float far_,
                                    float sigma, float gamma, float eps, float dist_eps, const float* soft_colors,
-                                   const float* aggrs, const float* grad_soft_colors, float* grad_faces, float* grad_tex) {
+                                   const float* aggrs, const float* grad_soft_colors, float* grad_faces, float* grad_tex,
+                                   int use_spans) {
   constexpr bool kFast = true;
   constexpr int kMode = 1, K = 1, KF = 0, P = 3 * K + 1;
   RasterArgs A{};
@@ -183,8 +186,17 @@ extern "C" void lasr_host_backward(const float* faces9, const float* textures9, 
     int xlo, xhi, ylo, yhi;
     coord_window(g.lox, g.hix, S, xlo, xhi);
     coord_window(g.loy, g.hiy, S, ylo, yhi);
-    for (int yi = yhi; yi >= ylo && xlo <= xhi; --yi)
-      for (int xi = xlo; xi <= xhi; ++xi) {
+    const float R = use_spans ? span_radius(g, sthr) : -1.f;     // < 0: this face keeps its full window
+    for (int yi = yhi; yi >= ylo && xlo <= xhi; --yi) {
+      int xa = xlo, xb = xhi;
+      if (R >= 0.f) {                                            // the span sweep of LASR_BWD_SPANS: same rows, fewer pixels
+        float lo, hi;
+        if (!row_span(g, pixel_coord(yi, S), R, lo, hi)) continue;
+        int a, b;
+        span_window(lo, hi, S, a, b);
+        xa = a > xlo ? a : xlo; xb = b < xhi ? b : xhi;
+      }
+      for (int xi = xa; xi <= xb; ++xi) {
         const float xp = pixel_coord(xi, S), yp = pixel_coord(yi, S);
         if (xp > g.hix || xp < g.lox || yp > g.hiy || yp < g.loy) continue;
         const long long pn = (long long)(S - 1 - yi) * S + xi;
@@ -192,6 +204,7 @@ extern "C" void lasr_host_backward(const float* faces9, const float* textures9, 
 #include "raster_backward_pair.inc"
 #undef PLANE
       }
+    }
     for (int k = 0; k < 9; ++k) { grad_faces[9 * f + k] = gf[k]; grad_tex[9 * f + k] = gt[k]; }
   }
 }

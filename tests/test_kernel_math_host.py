@@ -218,7 +218,14 @@ def test_backward_pair_code_run_on_the_host_reproduces_the_oracle_gradients(libs
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     F32 = ctypes.c_float
     libs[1].lasr_host_backward(P(fv), P(tx), ctypes.c_int(n), ctypes.c_int(S), F32(s["near"]), F32(s["far"]), F32(sigma),
-                               F32(s["gamma_val"]), F32(s["eps"]), F32(DIST_EPS), P(scol), P(agg), P(gsc), P(ogf), P(ogt))
+                               F32(s["gamma_val"]), F32(s["eps"]), F32(DIST_EPS), P(scol), P(agg), P(gsc), P(ogf), P(ogt),
+                               ctypes.c_int(0))
     for ours, ref in ((ogf, gf.reshape(n, 9)), (ogt, gt.reshape(n, 9))):
         rep = parity.grad_report(ours, ref)
         assert rep["rel_l2"] < 2e-4 and rep["max_over_scale"] < 3e-4 and rep["frac_gt_1e3"] == 0, rep
+    # the span sweep (LASR_BWD_SPANS) visits fewer pixels but the same accepted pairs in the same order: identical bits
+    sgf = np.zeros((n, 9), np.float32); sgt = np.zeros((n, 9), np.float32)
+    libs[1].lasr_host_backward(P(fv), P(tx), ctypes.c_int(n), ctypes.c_int(S), F32(s["near"]), F32(s["far"]), F32(sigma),
+                               F32(s["gamma_val"]), F32(s["eps"]), F32(DIST_EPS), P(scol), P(agg), P(gsc), P(sgf), P(sgt),
+                               ctypes.c_int(1))
+    assert np.array_equal(sgf.view(np.uint32), ogf.view(np.uint32)) and np.array_equal(sgt.view(np.uint32), ogt.view(np.uint32))
