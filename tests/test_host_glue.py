@@ -426,3 +426,16 @@ def test_whole_region_matches_the_reference_lines_running_on_the_drop_in_package
     np.testing.assert_allclose(out["flow_rd"].detach().numpy(), W("flow_rd"), rtol=0, atol=5e-6)
     for ours, ref in (("mask_loss", "mask_loss"), ("flow_loss", "flow_rd_loss"), ("texture_loss", "texture_loss"), ("total", "total_loss")):
         assert abs(float(out[ours]) - float(W(ref))) < 2e-6, (ours, float(out[ours]), float(W(ref)))
+
+
+def test_package_surface_matches_reference_exports():
+    """third_party/softras/soft_renderer/__init__.py:1-15 exports these names; LASR reaches the first three
+    (nnutils/mesh_net.py, lasr/lasr.py), the rest keep `import soft_renderer as sr` code importable."""
+    import lasr_b200.soft_renderer as sr
+    for name in ("Mesh", "SoftRenderer", "Renderer", "Transform", "Projection", "LookAt", "Look", "Lighting",
+                 "AmbientLighting", "DirectionalLighting", "Rasterizer", "SoftRasterizer", "LaplacianLoss",
+                 "FlattenLoss", "functional", "losses"):
+        assert hasattr(sr, name), name
+    assert sr.losses.LaplacianLoss is sr.LaplacianLoss
+    with pytest.raises(NotImplementedError):
+        sr.Renderer()
