@@ -439,3 +439,64 @@ def test_package_surface_matches_reference_exports():
     assert sr.losses.LaplacianLoss is sr.LaplacianLoss
     with pytest.raises(NotImplementedError):
         sr.Renderer()
+
+
+def test_synthetic_workload_is_the_reference_generators(monkeypatch):
+    """tests/golden/render_syn_ref.npz is what the reference's own scripts/render_syn.py (run whole and unmodified on
+    the drop-in package, tests/golden/make_render_syn_golden.py) writes for three frames of Spot: camera files, posed
+    meshes, 512^2 silhouettes and flow files.  bench.py's workload (lasr_b200.synth: Spot fixture, camera orbit,
+    projection) must be that generator's geometry, and the package's flow render -- `render_flow_soft_2`, the trainer's
+    copy of the script's `render_flow` -- must reproduce its silhouettes and flow files from it."""
+    import lasr_b200.soft_renderer as sr
+    import lasr_b200.soft_renderer.rasterizer as rast
+    from lasr_b200 import geom_utils as gu, synth
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "render_syn_ref.npz"))
+    n, S = int(g["nframes"]), int(g["img_size"])
+    v, f = synth.load_spot()
+    R, T, pp, fl = synth.spot_cameras(n)
+    px, cam = synth.project_frames(v, R, T, pp, fl)
+    for i in range(n):
+        c = g[f"cam{i}"]                       # [focal, tx, ty, qw, qx, qy, qz, depth]  (render_syn.py:150-157,193)
+        assert c[0] == fl[i, 0] and c[7] == T[i, 0, 2] and (c[1:3] == T[i, 0, :2]).all()
+        q_conj = torch.tensor([[-c[4], -c[5], -c[6], c[3]]])                     # render_syn.py:162: obj -> cam rotation
+        np.testing.assert_allclose(gu.quaternion_to_rotation_matrix(q_conj)[0].numpy(), R[i], atol=2e-7)
+        np.testing.assert_allclose(cam[i], g[f"mesh{i}"], rtol=0, atol=2e-6)     # posed vertices (the exported meshes)
+        np.testing.assert_allclose(px[i, :, :2], g[f"verts_px{i}"][:, :2], rtol=0, atol=2e-6)   # projected x, y
+
+    def fake(face_vertices, textures, image_size=256, background_color=[0, 0, 0], near=1, far=100, fill_back=True,
+             eps=1e-3, sigma_val=1e-5, dist_func="euclidean", dist_eps=1e-4, gamma_val=1e-4, aggr_func_rgb="softmax",
+             aggr_func_alpha="prod", texture_type="surface"):
+        return _OracleRasterize.apply(face_vertices, textures, dict(
+            image_size=image_size, background_color=list(background_color), near=near, far=far, fill_back=fill_back,
+            eps=eps, sigma_val=sigma_val, dist_func=dist_func, dist_eps=dist_eps, gamma_val=gamma_val,
+            aggr_func_rgb=aggr_func_rgb, aggr_func_alpha=aggr_func_alpha, texture_type=texture_type))
+    monkeypatch.setattr(rast.srf, "soft_rasterize", fake)
+    renderer = sr.SoftRenderer(image_size=S, sigma_val=1e-12, camera_mode="look_at", perspective=False,
+                               aggr_func_rgb="hard", light_mode="vertex", light_intensity_ambient=1.,
+                               light_intensity_directionals=0.)                  # render_syn.py:139-141
+    eye_z = float(renderer.transform.transformer._eye[2])
+    z = cam[:, :, 2]                                                             # render_syn.py:174: z to [-0.5, 0.5]
+    zn = (z - z.min(1, keepdims=True)) / (z.max(1, keepdims=True) - z.min(1, keepdims=True)) - 0.5
+    T_ = torch.from_numpy
+    verts = T_(np.concatenate([px[:, :, :2], zn[:, :, None]], -1).astype(np.float32))
+    np.testing.assert_allclose(verts.numpy(), np.stack([g[f"verts_px{i}"][:, :3] for i in range(n)]), atol=3e-6)
+    verts[:, :, 2] -= 2 * eye_z                    # the script subtracts the eye offset where the trainer adds it (:44 vs mesh_net.py:81)
+    pos = T_(cam)
+    faces = T_(f)[None]
+    zero, foc = torch.zeros(1, 2), torch.full((1, 1), 10.0)
+    for i in range(1, n):
+        for tag, a, b, j in (("FlowFW", i - 1, i, i - 1), ("FlowBW", i, i - 1, i)):   # render_syn.py:203-211
+            flow, bg, fgm = gu.render_flow_soft_2(renderer, verts[a:a + 1], faces, pos[a:a + 1], pos[b:b + 1], zero, zero, foc, foc)
+            out = np.concatenate([(flow / 2 * (S - 1)).numpy()[0], 1 - bg.float().numpy()[0][:, :, None]], -1)
+            ref, ref_sum = g[f"{tag}{j}"], g[f"{tag}{j}_sum"]
+            assert np.array_equal(out[::4, ::4, 2], ref[:, :, 2]) and out[:, :, 2].sum() == ref_sum[2]
+            # flow in pixels: 'hard' colour aggregation takes the nearest face's value, so where synth's pose and the
+            # script's differ by float rounding a pixel on a crease reads the neighbouring face (<= 0.01 px off) and one
+            # on an occlusion edge the other surface (pixels off)
+            d = np.abs(out[::4, ::4, :2] - ref[:, :, :2])
+            assert (d > 1e-4 + 1e-5 * np.abs(ref[:, :, :2])).mean() < 1e-3 and (d > 0.05).sum() <= 4, ((d > 1e-4).sum(), d.max())
+            np.testing.assert_allclose(out.astype(np.float64).sum((0, 1)), ref_sum, rtol=2e-4)
+            mask = np.clip(np.rint(128 * fgm[0].numpy()), 0, 255).astype(np.uint8)               # render_syn.py:191
+            # the silhouette edge is hard (sigma 1e-12) and synth's pose differs from the script's by float rounding
+            # (cv2.Rodrigues -> quaternion -> matrix there): a few edge pixels of 262 144 may flip
+            assert (mask != g[f"mask{a}"]).sum() <= 8, (mask != g[f"mask{a}"]).sum()
