@@ -73,3 +73,23 @@ def test_rasterizer_rejects_bad_enums():
                dict(texture_type="uv")):
         with pytest.raises(ValueError):
             sr.SoftRasterizer(**kw)
+
+
+def test_every_compute_entry_point_refuses_null_arguments_with_a_message():
+    """Argument validation happens before any CUDA call: with null pointers and zero sizes every entry point returns
+    non-zero and leaves a message in lasr_b200_last_error() -- no GPU needed, nothing is launched (the reference
+    printf's CUDA errors and carries on, soft_rasterize_cuda_kernel.cu:710-712)."""
+    from lasr_b200 import _cabi
+    L = _cabi.lib()
+    before = _cabi.launch_count()
+    checked = 0
+    for name in _cabi.EXPORTED_SYMBOLS:
+        fn = getattr(L, name)
+        if fn.argtypes is None or name.endswith("_bytes"):
+            continue
+        args = [0.0 if t is ctypes.c_float else 0 if t in (ctypes.c_int, ctypes.c_size_t) else None for t in fn.argtypes]
+        assert fn(*args) != 0, name
+        msg = L.lasr_b200_last_error().decode()
+        assert msg and msg.split(":")[0].split("_")[0] in name, (name, msg)
+        checked += 1
+    assert checked >= 27 and _cabi.launch_count() == before
