@@ -592,6 +592,16 @@ def run_gpu_arm(args, arm_cls):
                           issue_frac=ach_issue / peak_issue)
         except Exception:
             pass
+        try:   # SURVEY 8d timing protocol: spread of the per-step kernel times (CUDA events of every timed step)
+            def spread(xs):
+                return {"median": float(np.median(xs)), "p10": float(np.percentile(xs, 10)),
+                        "p90": float(np.percentile(xs, 90)), "n": len(xs)}
+            out["step_stats_ms"] = {
+                "forward": spread([e[0].elapsed_time(e[1]) for e in arm.pending]),
+                "backward": spread([e[1].elapsed_time(e[2]) for e in arm.pending]),
+                "forward_plus_backward": spread([e[0].elapsed_time(e[2]) for e in arm.pending])}
+        except Exception:
+            pass
         if world == 1 and arm.name == "ours" and args.extras:
             out["extras"] = extras_microbench(device, peak)
         if world == 1 and not args.no_cpu_baseline:
