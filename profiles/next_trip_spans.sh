@@ -13,9 +13,15 @@ build)
   LASR_B200_LIB=$V/base.so python -m lasr_b200._build &
   LASR_B200_LIB=$V/spans.so python -m lasr_b200._build -DLASR_BWD_SPANS=1 &
   wait
+  # the backward's 21 denormal-guard instructions per sweep (profiles/round1g_instruction_budget.md): bare .ftz MUFUs were
+  # slower on the window sweep (r1f t3); the span sweep changes the loop's register pressure, so measure them together
+  LASR_B200_LIB=$V/spans_ftz.so python -m lasr_b200._build -DLASR_BWD_SPANS=1 -DLASR_FTZ_MUFU_BWD=1 &
+  LASR_B200_LIB=$V/ftz.so python -m lasr_b200._build -DLASR_FTZ_MUFU_BWD=1 &
+  wait
+  for v in base spans spans_ftz ftz; do rm -rf lasr_b200/csrc/build/$v.so.obj; done     # object caches need not travel
   ls -la $V ;;
 run)
-  bash profiles/trip_ab.sh spans base spans
+  bash profiles/trip_ab.sh spans base spans spans_ftz ftz     # (the ftz builds differ from base by <= 3e-5 in the gradients)
   LASR_B200_LIB=$V/spans.so python -m pytest tests/test_raster_gpu.py tests/test_hotpath_gpu.py -q -x 2>&1 | tail -3
   LASR_B200_LIB=$V/spans.so ncu --set full --clock-control none --import-source on -k regex:"raster_backward_kernel" -s 4 -c 1 \
       -o gpurun_out/spans/backward python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 3 > gpurun_out/spans/ncu.log 2>&1 || true ;;
