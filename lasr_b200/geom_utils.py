@@ -207,10 +207,12 @@ def render_flow_soft_3(renderer_soft, verts, verts_target, faces):
     pre = torch.cat([pre[:, :, :1], -pre[:, :, 1:2], pre[:, :, 2:]], dim=-1)
     px = renderer_soft.render_mesh(sr.Mesh(pre, faces, textures=verts_target[:, :, :3],
                                            texture_type="vertex")).clone()
-    fgmask = px[:, -1]
     px = px.permute(0, 2, 3, 1)
     bgmask = px[..., 2] < 1e-9
     px = torch.where(bgmask[..., None], torch.full_like(px, 10.0), px)
+    # the reference's fgmask is a view of the render it then overwrites with 10 on the background (all four channels,
+    # geom_utils.py:82-86), so its foreground mask reads 10 there; kept
+    fgmask = px[..., 3]
     H, W = bgmask.shape[1], bgmask.shape[2]
     gx = torch.arange(W, device=verts.device, dtype=torch.float32) * 2 / (W - 1) - 1
     gy = torch.arange(H, device=verts.device, dtype=torch.float32) * 2 / (H - 1) - 1

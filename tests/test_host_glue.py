@@ -500,3 +500,29 @@ def test_synthetic_workload_is_the_reference_generators(monkeypatch):
             # the silhouette edge is hard (sigma 1e-12) and synth's pose differs from the script's by float rounding
             # (cv2.Rodrigues -> quaternion -> matrix there): a few edge pixels of 262 144 may flip
             assert (mask != g[f"mask{a}"]).sum() <= 8, (mask != g[f"mask{a}"]).sum()
+
+
+def test_flow_render_3_matches_the_reference_source_lines():
+    """`render_flow_soft_3` (nnutils/geom_utils.py:73-95, the evaluation scripts' flow render: rendered target positions
+    against the pixel grid) pinned the same way: tests/golden/flow_ref.npz cases s3a / s3b are the reference's own
+    lines executed with a stand-in renderer."""
+    import types
+    from lasr_b200 import geom_utils as gu
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "flow_ref.npz"))
+    T = torch.from_numpy
+    for case in ("s3a", "s3b"):
+        I = lambda k: T(g[f"{case}/in/{k}"])
+        seen = {}
+
+        def render_mesh(mesh):
+            seen["vertices"], seen["faces"], seen["textures"] = mesh.vertices, mesh.faces, mesh.textures
+            return I("rendered").clone()
+        renderer = types.SimpleNamespace(
+            transform=types.SimpleNamespace(transformer=types.SimpleNamespace(_eye=[0, 0, -2.732051])), render_mesh=render_mesh)
+        flow, bg, fgm = gu.render_flow_soft_3(renderer, I("verts"), I("target"), I("faces"))
+        assert np.array_equal(seen["vertices"].numpy(), g[f"{case}/mesh/vertices"])
+        assert np.array_equal(seen["faces"].numpy(), g[f"{case}/mesh/faces"])
+        assert np.array_equal(seen["textures"].numpy(), g[f"{case}/mesh/textures"])
+        assert np.array_equal(bg.numpy(), g[f"{case}/out/bgmask"]) and bg.any()
+        assert np.array_equal(fgm.numpy(), g[f"{case}/out/fgmask"])
+        np.testing.assert_allclose(flow.numpy(), g[f"{case}/out/flow"], rtol=1e-6, atol=1e-6)
