@@ -526,3 +526,45 @@ def test_flow_render_3_matches_the_reference_source_lines():
         assert np.array_equal(bg.numpy(), g[f"{case}/out/bgmask"]) and bg.any()
         assert np.array_equal(fgm.numpy(), g[f"{case}/out/fgmask"])
         np.testing.assert_allclose(flow.numpy(), g[f"{case}/out/flow"], rtol=1e-6, atol=1e-6)
+
+
+def test_module_layer_matches_the_reference_classes(monkeypatch):
+    """R2 at the module level: tests/golden/modules_ref.npz records what the reference's own SoftRenderer / Lighting /
+    Transform / SoftRasterizer / Mesh classes (loaded unmodified, tests/golden/make_modules_golden.py) hand to the
+    rasterizer and return, for cameras, lights, texture types and setters LASR's one configuration does not exercise.
+    The mirror must hand over the same face vertices, face textures and scalars, and pool the render the same way."""
+    import json
+    import lasr_b200.soft_renderer as sr
+    import lasr_b200.soft_renderer.rasterizer as rast
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "modules_ref.npz"))
+    names = sorted({k.split("/")[0] for k in g.files})
+    assert len(names) == 8
+    arg_names = ("image_size", "background_color", "near", "far", "fill_back", "eps", "sigma_val", "dist_func",
+                 "dist_eps", "gamma_val", "aggr_func_rgb", "aggr_func_alpha", "texture_type")
+    for name in names:
+        meta = json.loads(str(g[f"{name}/meta"]))
+        rec = {}
+
+        def soft_rasterize(face_vertices, textures, *args):
+            rec["face_vertices"], rec["face_textures"], rec["args"] = face_vertices, textures, dict(zip(arg_names, args))
+            return torch.from_numpy(g[f"{name}/rec/render"]).clone()
+        monkeypatch.setattr(rast.srf, "soft_rasterize", soft_rasterize)
+        r = sr.SoftRenderer(**meta["kwargs"])
+        for fn, a in meta["calls"]:
+            a = [torch.tensor(x) if isinstance(x, list) and fn == "set_eyes_from_angles" else x for x in a]
+            (getattr(r, fn) if hasattr(r, fn) else getattr(r.transform, fn))(*a)
+        verts, faces = torch.from_numpy(g[f"{name}/in/verts"]), torch.from_numpy(g[f"{name}/in/faces"])
+        tex = torch.from_numpy(g[f"{name}/in/textures"]) if f"{name}/in/textures" in g.files else None
+        if meta["via_forward"]:
+            img = r(verts, faces, tex, texture_type=meta["texture_type"])
+        else:
+            img = r.render_mesh(sr.Mesh(verts, faces, textures=tex, texture_res=meta["texture_res"],
+                                        texture_type=meta["texture_type"]))
+        np.testing.assert_allclose(rec["face_vertices"].numpy(), g[f"{name}/rec/face_vertices"], rtol=1e-6, atol=1e-6,
+                                   err_msg=name)
+        np.testing.assert_allclose(rec["face_textures"].numpy(), g[f"{name}/rec/face_textures"], rtol=1e-6, atol=1e-7,
+                                   err_msg=name)
+        for k, v in meta["args"].items():
+            got = rec["args"][k]
+            assert (list(got) == list(v)) if isinstance(v, list) else (got == v), (name, k, got, v)
+        np.testing.assert_allclose(img.numpy(), g[f"{name}/out/image"], rtol=1e-6, atol=1e-7, err_msg=name)
