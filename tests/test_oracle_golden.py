@@ -84,3 +84,61 @@ def test_oracle_texture_gradient_matches_finite_differences(oracle):
         m[j] -= 1e-3
         fd = (loss(p) - loss(m)) / 2e-3
         assert abs(fd - gt[j]) <= 1e-8 * max(1.0, abs(gt[j])) + 1e-10, (j, fd, gt[j])
+
+
+def test_reference_driver_sets_up_buffers_like_the_reference_function(monkeypatch):
+    """oracle/ref_gpu.py drives the reference's compiled kernels (golden minting, `bench.py --impl reference`) behind a
+    restatement of the buffer set-up in the reference's SoftRasterizeFunction.  tests/golden/function_glue_ref.npz holds
+    every argument the reference's own Python (functional/soft_rasterize.py, run unmodified with a recording stand-in for
+    the pybind module) hands to forward_/backward_soft_rasterize; the restatement must hand over the same."""
+    import importlib.util
+    import json
+    import torch
+    from oracle import ref_gpu
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_function_glue_golden", os.path.join(here, "golden", "make_function_glue_golden.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    g = np.load(os.path.join(here, "golden", "function_glue_ref.npz"))
+    for name in gen.CASES:
+        s = json.loads(str(g[f"{name}/settings"]))
+        assert s == json.loads(json.dumps(gen.CASES[name]))
+        rec = gen.Recorder(1)
+        monkeypatch.setattr(ref_gpu, "ext", lambda: rec)
+        fv = torch.from_numpy(g[f"{name}/in/face_vertices"]).requires_grad_(True)
+        tex = torch.from_numpy(g[f"{name}/in/textures"]).requires_grad_(True)
+        img = ref_gpu.soft_rasterize(fv, tex, **s)
+        img.backward(torch.from_numpy(g[f"{name}/in/grad"]))
+        for tag, names in (("fwd", gen.FWD_T), ("bwd", gen.BWD_T)):
+            tensors, scalars = rec.calls[tag]
+            for n, t in zip(names, tensors):
+                ref = g[f"{name}/{tag}/{n}"]
+                assert t.dtype == torch.float32 and tuple(t.shape) == ref.shape and t.is_contiguous(), (name, tag, n)
+                assert np.array_equal(t.detach().numpy(), ref), (name, tag, n)
+            want = json.loads(str(g[f"{name}/{tag}/scalars"]))
+            assert len(scalars) == len(want) == len(gen.SCALARS)
+            for k, a, b in zip(gen.SCALARS, scalars, want):
+                assert type(a) is type(b) or not isinstance(b, bool), (name, tag, k)
+                assert float(a) == float(b), (name, tag, k, a, b)
+        assert np.array_equal(img.detach().numpy(), g[f"{name}/out/image"])
+        assert np.array_equal(fv.grad.numpy(), g[f"{name}/out/grad_faces"])
+        assert np.array_equal(tex.grad.numpy(), g[f"{name}/out/grad_textures"])
+
+
+def test_reference_driver_render_chain_matches_the_reference_classes(monkeypatch):
+    """`ref_gpu.render_mesh_lasr` (the `--impl reference` arm's restatement of SoftRenderer.render_mesh with LASR's
+    settings) against what the reference's own classes hand to the rasterizer (tests/golden/modules_ref.npz, case
+    'lasr')."""
+    import torch
+    from oracle import ref_gpu
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "modules_ref.npz"))
+    rec = {}
+
+    def soft_rasterize(face_vertices, textures, **settings):
+        rec.update(fv=face_vertices, tex=textures, settings=settings)
+        return torch.from_numpy(g["lasr/rec/render"])
+    monkeypatch.setattr(ref_gpu, "soft_rasterize", soft_rasterize)
+    eye = torch.tensor([0.0, 0.0, -(1.0 / np.tan(np.radians(30.0)) + 1.0)], dtype=torch.float32)
+    ref_gpu.render_mesh_lasr(torch.from_numpy(g["lasr/in/verts"]), torch.from_numpy(g["lasr/in/faces"]),
+                             torch.from_numpy(g["lasr/in/textures"]), eye, dict(image_size=8))
+    np.testing.assert_allclose(rec["fv"].numpy(), g["lasr/rec/face_vertices"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(rec["tex"].numpy(), g["lasr/rec/face_textures"], rtol=1e-6, atol=1e-7)
