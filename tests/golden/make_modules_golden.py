@@ -137,6 +137,29 @@ def main():
         out[f"{name}/meta"] = np.asarray(json.dumps(dict(kwargs=kw, texture_type=ttype, texture_res=tres, calls=call_log,
                                                          via_forward=via_forward, args=rec["args"])))
         print(name, tuple(rec["face_vertices"].shape), tuple(rec["face_textures"].shape), tuple(img.shape), rec["args"])
+    # Mesh bookkeeping outside the render call: fill_back_ / reset_ and the cached derived tensors (mesh.py:67-146)
+    for ttype in ("surface", "vertex"):
+        verts, faces, tex, g = inputs(100, ttype, "rand", 2)
+        mesh = sr.Mesh(verts.clone(), faces.clone(), textures=tex.clone(), texture_res=2, texture_type=ttype)
+        n0 = mesh.surface_normals.clone()
+        mesh.fill_back_()
+        mesh.fill_back_()                                    # idempotent
+        pre = f"mesh_ops_{ttype}"
+        out[f"{pre}/in/verts"], out[f"{pre}/in/faces"], out[f"{pre}/in/textures"] = verts.numpy(), faces.numpy(), tex.numpy()
+        out[f"{pre}/filled/faces"], out[f"{pre}/filled/textures"] = mesh.faces.numpy(), mesh.textures.numpy()
+        out[f"{pre}/filled/face_vertices"] = mesh.face_vertices.numpy()
+        out[f"{pre}/filled/surface_normals"] = mesh.surface_normals.numpy()
+        out[f"{pre}/filled/vertex_normals"] = mesh.vertex_normals.numpy()
+        if ttype == "surface":
+            out[f"{pre}/filled/face_textures"] = mesh.face_textures.numpy()
+        mesh.vertices = mesh.vertices * 2.0                  # the setter invalidates the caches
+        out[f"{pre}/scaled/face_vertices"] = mesh.face_vertices.numpy()
+        mesh.reset_()
+        out[f"{pre}/reset/faces"], out[f"{pre}/reset/textures"] = mesh.faces.numpy(), mesh.textures.numpy()
+        out[f"{pre}/reset/face_vertices"] = mesh.face_vertices.numpy()
+        out[f"{pre}/meta"] = np.asarray(json.dumps(dict(num_faces=[int(n0.shape[1]), int(out[f"{pre}/filled/faces"].shape[1])],
+                                                         texture_res=int(mesh.texture_res), batch_size=int(mesh.batch_size))))
+        print(pre, out[f"{pre}/filled/faces"].shape, out[f"{pre}/filled/textures"].shape)
     np.savez_compressed(DST, **out)
     print("wrote", DST, os.path.getsize(DST), "bytes")
 

@@ -537,7 +537,7 @@ def test_module_layer_matches_the_reference_classes(monkeypatch):
     import lasr_b200.soft_renderer as sr
     import lasr_b200.soft_renderer.rasterizer as rast
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "modules_ref.npz"))
-    names = sorted({k.split("/")[0] for k in g.files})
+    names = sorted({k.split("/")[0] for k in g.files if not k.startswith("mesh_ops")})
     assert len(names) == 8
     arg_names = ("image_size", "background_color", "near", "far", "fill_back", "eps", "sigma_val", "dist_func",
                  "dist_eps", "gamma_val", "aggr_func_rgb", "aggr_func_alpha", "texture_type")
@@ -568,3 +568,35 @@ def test_module_layer_matches_the_reference_classes(monkeypatch):
             got = rec["args"][k]
             assert (list(got) == list(v)) if isinstance(v, list) else (got == v), (name, k, got, v)
         np.testing.assert_allclose(img.numpy(), g[f"{name}/out/image"], rtol=1e-6, atol=1e-7, err_msg=name)
+
+
+def test_mesh_bookkeeping_matches_the_reference_class():
+    """Mesh.fill_back_ / reset_ / the vertices setter and the cached derived tensors against the reference's own Mesh
+    (mesh.py:67-146; tests/golden/modules_ref.npz, mesh_ops_*) -- including its habit of doubling per-vertex textures
+    along the vertex axis when filling back."""
+    import lasr_b200.soft_renderer as sr
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "modules_ref.npz"))
+    T = torch.from_numpy
+    for ttype in ("surface", "vertex"):
+        pre = f"mesh_ops_{ttype}"
+        mesh = sr.Mesh(T(g[f"{pre}/in/verts"]), T(g[f"{pre}/in/faces"]), textures=T(g[f"{pre}/in/textures"]), texture_res=2,
+                       texture_type=ttype)
+        mesh.surface_normals
+        mesh.fill_back_()
+        mesh.fill_back_()
+        assert np.array_equal(mesh.faces.numpy(), g[f"{pre}/filled/faces"])
+        assert np.array_equal(mesh.textures.numpy(), g[f"{pre}/filled/textures"])
+        assert np.array_equal(mesh.face_vertices.numpy(), g[f"{pre}/filled/face_vertices"])
+        np.testing.assert_allclose(mesh.surface_normals.numpy(), g[f"{pre}/filled/surface_normals"], atol=1e-6)
+        np.testing.assert_allclose(mesh.vertex_normals.numpy(), g[f"{pre}/filled/vertex_normals"], atol=1e-6)
+        if ttype == "surface":
+            assert np.array_equal(mesh.face_textures.numpy(), g[f"{pre}/filled/face_textures"])
+        mesh.vertices = mesh.vertices * 2.0
+        assert np.array_equal(mesh.face_vertices.numpy(), g[f"{pre}/scaled/face_vertices"])
+        mesh.reset_()
+        assert np.array_equal(mesh.faces.numpy(), g[f"{pre}/reset/faces"])
+        assert np.array_equal(mesh.textures.numpy(), g[f"{pre}/reset/textures"])
+        assert np.array_equal(mesh.face_vertices.numpy(), g[f"{pre}/reset/face_vertices"])
+        import json
+        meta = json.loads(str(g[f"{pre}/meta"]))
+        assert mesh.texture_res == meta["texture_res"] and mesh.batch_size == meta["batch_size"]
