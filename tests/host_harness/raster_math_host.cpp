@@ -209,4 +209,96 @@ extern "C" void lasr_host_backward(const float* faces9, const float* textures9, 
   }
 }
 
+// ---- the generic instantiation (kFast = false: every operator mode, the reference's IEEE arithmetic) on the host ------
+// One frame; textures [F,T,3] ('vertex': T = 3 = the three corner colours; 'surface': T = R*R texels).
+static void fill_mode_args(RasterArgs& A, int F, int S, int T, float near_, float far_, float sigma, float gamma, float eps,
+                           float dist_eps, int dist, int rgb, int alpha, int sample, int double_side, const float* textures) {
+  A.N = 1; A.F = F; A.S = S; A.T = T; A.K = 1; A.R = (int)sqrt((double)T);
+  A.dist = dist; A.rgb = rgb; A.alpha = alpha; A.sample = sample; A.double_side = double_side;
+  A.near_ = near_; A.far_ = far_; A.eps = eps; A.sigma = sigma; A.dist_eps = dist_eps; A.gamma = gamma;
+  A.inv_sigma = (float)(1.0 / (double)sigma); A.inv_gamma = (float)(1.0 / (double)gamma);
+  A.textures = textures;
+}
+
+extern "C" void lasr_host_forward_modes(const float* faces9, const float* textures, int F, int S, int T, float near_,
+                                        float far_, float sigma, float gamma, float eps, float dist_eps, int dist, int rgb,
+                                        int alpha, int sample, int double_side, const float* bg3, float* out_rgba,
+                                        float* out_aggr) {
+  RasterArgs A{};
+  fill_mode_args(A, F, S, T, near_, far_, sigma, gamma, eps, dist_eps, dist, rgb, alpha, sample, double_side, textures);
+  FwdConsts C;
+  C.near_ = near_; C.far_ = far_; C.thr = dist_eps * sigma; C.inv_range = 1.f / (far_ - near_);
+  const float sthr = sqrtf(dist_eps * sigma);
+  float* recs = new float[(size_t)F * rec_words(1)];
+  float4* bds = new float4[F];
+  for (int f = 0; f < F; ++f) {
+    FaceGeom g;
+    face_setup(faces9 + 9 * f, sthr, g);
+    store_record<1>(recs + (size_t)f * rec_words(1), g, sample == 1 ? textures + 9 * f : nullptr);
+    bds[f] = make_float4(g.lox, g.hix, g.loy, g.hiy);
+  }
+  const size_t SS = (size_t)S * S;
+  for (int py = 0; py < S; ++py)
+    for (int px = 0; px < S; ++px) {
+      const float xp = pixel_coord(px, S), yp = pixel_coord(S - 1 - py, S);
+      PixelState<1> st;                                        // raster.cu: init_state
+      st.alpha = alpha == 2 ? 1.f : 0.f; st.ssum = expf(eps / gamma); st.smax = eps; st.depth_min = 10000000.f; st.face_min = -1;
+      for (int k = 0; k < 3; ++k) st.col[k] = rgb == 1 ? bg3[k] * st.ssum : bg3[k];
+      for (int f = 0; f < F; ++f)
+        forward_pair<false, 1>(A, C, recs + (size_t)f * rec_words(1), bds[f], f, 0, xp, yp, st);
+      const size_t pn = (size_t)py * S + px;                   // raster.cu: finish
+      out_rgba[3 * SS + pn] = alpha == 0 ? st.alpha : (alpha == 1 ? st.alpha / F : 1.f - st.alpha);
+      if (rgb == 0) {
+        for (int k = 0; k < 3; ++k) out_rgba[k * SS + pn] = st.face_min != -1 ? st.col[k] : bg3[k];
+        out_aggr[pn] = st.depth_min; out_aggr[SS + pn] = (float)st.face_min;
+      } else {
+        for (int k = 0; k < 3; ++k) out_rgba[k * SS + pn] = st.col[k] / st.ssum;
+        out_aggr[pn] = st.ssum; out_aggr[SS + pn] = st.smax;
+      }
+    }
+  delete[] recs; delete[] bds;
+}
+
+#define atomicAdd(p, v) (*(p) += (v))
+extern "C" void lasr_host_backward_modes(const float* faces9, const float* textures, int F, int S, int T, float near_,
+                                         float far_, float sigma, float gamma, float eps, float dist_eps, int dist, int rgb,
+                                         int alpha, int sample_, int double_side, const float* soft_colors,
+                                         const float* aggrs, const float* grad_soft_colors, float* grad_faces,
+                                         float* grad_tex) {
+  constexpr bool kFast = false;
+  constexpr int kMode = 0, K = 1, KF = 0, P = 3 * K + 1;
+  RasterArgs A{};
+  fill_mode_args(A, F, S, T, near_, far_, sigma, gamma, eps, dist_eps, dist, rgb, alpha, sample_, double_side, textures);
+  const float thr = dist_eps * sigma, sthr = sqrtf(thr);
+  const float inv_range = 1.f / (far_ - near_), cz_scale = A.inv_gamma / (near_ - far_);
+  (void)inv_range; (void)cz_scale;
+  const int dist_f = dist, rgb_f = rgb, alpha_f = alpha, sample = sample_;
+  const long long SS = (long long)S * S;
+  const float *sc = soft_colors, *ag = aggrs, *gs = grad_soft_colors;
+  for (int f = 0; f < F; ++f) {
+    const long long wg = f;
+    FaceGeom g;
+    face_setup(faces9 + 9 * f, sthr, g);
+    float tex9[9] = {0};
+    if (sample == 1) for (int k = 0; k < 9; ++k) tex9[k] = textures[9 * f + k];
+    float* gtex_out = grad_tex + (size_t)f * T * 3;
+    float gf[9] = {0}, gt[9] = {0};
+    int xlo, xhi, ylo, yhi;
+    coord_window(g.lox, g.hix, S, xlo, xhi);
+    coord_window(g.loy, g.hiy, S, ylo, yhi);
+    for (int yi = yhi; yi >= ylo && xlo <= xhi; --yi)
+      for (int xi = xlo; xi <= xhi; ++xi) {
+        const float xp = pixel_coord(xi, S), yp = pixel_coord(yi, S);
+        if (xp > g.hix || xp < g.lox || yp > g.hiy || yp < g.loy) continue;
+        const long long pn = (long long)(S - 1 - yi) * S + xi;
+#define PLANE(k) ((k) * SS + pn)
+#include "raster_backward_pair.inc"
+#undef PLANE
+      }
+    for (int k = 0; k < 9; ++k) grad_faces[9 * f + k] = gf[k];
+    if (sample == 1) for (int k = 0; k < 9; ++k) gtex_out[k] = gt[k];     // 'surface': scattered by the loop body itself
+  }
+}
+#undef atomicAdd
+
 extern "C" int lasr_host_fast_inside(void) { return LASR_FAST_INSIDE; }
