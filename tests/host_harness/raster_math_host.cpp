@@ -301,4 +301,104 @@ extern "C" void lasr_host_backward_modes(const float* faces9, const float* textu
 }
 #undef atomicAdd
 
+// ---- several colour sets per geometry pass (K = 2, 3; LASR's configuration only) on the host -------------------------
+// tex [F][9K]: set-major, nine corner-colour floats per set (what the setup kernel gathers into the record).
+template <int K>
+static void host_forward_sets(const float* faces9, const float* tex, int F, int S, float near_, float far_, float sigma,
+                              float gamma, float eps, float dist_eps, const float* bg, float* out, float* out_aggr) {
+  RasterArgs A{};
+  fill_mode_args(A, F, S, 3, near_, far_, sigma, gamma, eps, dist_eps, 2, 1, 2, 1, 1, nullptr);
+  A.K = K;
+  FwdConsts C;
+  C.near_ = near_; C.far_ = far_; C.thr = dist_eps * sigma; C.inv_range = 1.f / (far_ - near_);
+  const float sthr = sqrtf(dist_eps * sigma);
+  constexpr int W = rec_words(K), P = 3 * K + 1;
+  float* recs = new float[(size_t)F * W];
+  float4* bds = new float4[F];
+  for (int f = 0; f < F; ++f) {
+    FaceGeom g;
+    face_setup(faces9 + 9 * f, sthr, g);
+    store_record<K>(recs + (size_t)f * W, g, tex + (size_t)9 * K * f);
+    bds[f] = make_float4(g.lox, g.hix, g.loy, g.hiy);
+  }
+  const size_t SS = (size_t)S * S;
+  for (int py = 0; py < S; ++py)
+    for (int px = 0; px < S; ++px) {
+      const float xp = pixel_coord(px, S), yp = pixel_coord(S - 1 - py, S);
+      PixelState<K> st;
+      st.alpha = 1.f; st.ssum = expf(eps / gamma); st.smax = eps; st.depth_min = 10000000.f; st.face_min = -1;
+      for (int k = 0; k < 3 * K; ++k) st.col[k] = bg[k] * st.ssum;
+      for (int f = 0; f < F; ++f) forward_pair<true, K>(A, C, recs + (size_t)f * W, bds[f], f, 0, xp, yp, st);
+      const size_t pn = (size_t)py * S + px;
+      for (int k = 0; k < 3 * K; ++k) out[k * SS + pn] = st.col[k] / st.ssum;
+      out[(P - 1) * SS + pn] = 1.f - st.alpha;
+      out_aggr[pn] = st.ssum; out_aggr[SS + pn] = st.smax;
+    }
+  delete[] recs; delete[] bds;
+}
+
+extern "C" int lasr_host_forward_sets(const float* faces9, const float* tex, int F, int S, int K, float near_, float far_,
+                                      float sigma, float gamma, float eps, float dist_eps, const float* bg, float* out,
+                                      float* out_aggr) {
+  if (K == 1) host_forward_sets<1>(faces9, tex, F, S, near_, far_, sigma, gamma, eps, dist_eps, bg, out, out_aggr);
+  else if (K == 2) host_forward_sets<2>(faces9, tex, F, S, near_, far_, sigma, gamma, eps, dist_eps, bg, out, out_aggr);
+  else if (K == 3) host_forward_sets<3>(faces9, tex, F, S, near_, far_, sigma, gamma, eps, dist_eps, bg, out, out_aggr);
+  else return 1;
+  return 0;
+}
+
+template <int K, int KF>
+static void host_backward_sets(const float* faces9, const float* tex, int F, int S, float near_, float far_, float sigma,
+                               float gamma, float eps, float dist_eps, const float* soft_colors, const float* aggrs,
+                               const float* grad_soft_colors, float* grad_faces, float* grad_tex) {
+  constexpr bool kFast = true;
+  constexpr int kMode = 1, P = 3 * K + 1;
+  RasterArgs A{};
+  fill_mode_args(A, F, S, 3, near_, far_, sigma, gamma, eps, dist_eps, 2, 1, 2, 1, 1, nullptr);
+  A.K = K;
+  const float thr = dist_eps * sigma, sthr = sqrtf(thr);
+  const float inv_range = 1.f / (far_ - near_), cz_scale = A.inv_gamma / (near_ - far_);
+  const int dist_f = 2, rgb_f = 1, alpha_f = 2, sample = 1;
+  (void)dist_f; (void)rgb_f; (void)alpha_f; (void)sample;
+  const long long SS = (long long)S * S;
+  const float *sc = soft_colors, *ag = aggrs, *gs = grad_soft_colors;
+  for (int f = 0; f < F; ++f) {
+    const long long wg = f;
+    FaceGeom g;
+    face_setup(faces9 + 9 * f, sthr, g);
+    const float* tex9 = tex + (size_t)9 * K * f;
+    float* gtex_out = grad_tex + (size_t)9 * K * f + 9 * KF;
+    float gf[9] = {0}, gt[9 * (K - KF)] = {0};
+    int xlo, xhi, ylo, yhi;
+    coord_window(g.lox, g.hix, S, xlo, xhi);
+    coord_window(g.loy, g.hiy, S, ylo, yhi);
+    for (int yi = yhi; yi >= ylo && xlo <= xhi; --yi)
+      for (int xi = xlo; xi <= xhi; ++xi) {
+        const float xp = pixel_coord(xi, S), yp = pixel_coord(yi, S);
+        if (xp > g.hix || xp < g.lox || yp > g.hiy || yp < g.loy) continue;
+        const long long pn = (long long)(S - 1 - yi) * S + xi;
+#define PLANE(k) ((k) * SS + pn)
+#include "raster_backward_pair.inc"
+#undef PLANE
+      }
+    for (int k = 0; k < 9; ++k) grad_faces[9 * f + k] = gf[k];
+    for (int k = 0; k < 9 * (K - KF); ++k) gtex_out[k] = gt[k];
+  }
+}
+
+extern "C" int lasr_host_backward_sets(const float* faces9, const float* tex, int F, int S, int K, int KF, float near_,
+                                       float far_, float sigma, float gamma, float eps, float dist_eps,
+                                       const float* soft_colors, const float* aggrs, const float* grad_soft_colors,
+                                       float* grad_faces, float* grad_tex) {
+#define LASR_SETS_CASE(k, kf)                                                                                          \
+  if (K == k && KF == kf) {                                                                                            \
+    host_backward_sets<k, kf>(faces9, tex, F, S, near_, far_, sigma, gamma, eps, dist_eps, soft_colors, aggrs,         \
+                              grad_soft_colors, grad_faces, grad_tex);                                                 \
+    return 0;                                                                                                          \
+  }
+  LASR_SETS_CASE(1, 0) LASR_SETS_CASE(2, 0) LASR_SETS_CASE(2, 1) LASR_SETS_CASE(3, 0) LASR_SETS_CASE(3, 1)
+#undef LASR_SETS_CASE
+  return 1;
+}
+
 extern "C" int lasr_host_fast_inside(void) { return LASR_FAST_INSIDE; }

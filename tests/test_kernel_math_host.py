@@ -274,3 +274,57 @@ def test_generic_pair_code_run_on_the_host_reproduces_the_reference_kernels(libs
     if gfr["scale"] > 1e-20:
         assert gfr["rel_l2"] < 1e-3 and gfr["max_over_scale"] < 1e-3, (name, gfr)
     assert gtr["rel_l2"] < 1e-3 and gtr["max_over_scale"] < 1e-3, (name, gtr)
+
+
+# ---- several colour sets riding one geometry pass (K = 2, 3), on the host ---------------------------------------------
+@pytest.mark.parametrize("K", [2, 3])
+def test_colour_set_kernels_on_the_host_equal_separate_passes(libs, K):
+    """forward_pair<true, K> / the backward body with K colour sets (and a detached first set, KF = 1) against K separate
+    single-set passes of the same code: image planes and colour gradients bit-identical per set, the silhouette and the
+    aggregates shared, the vertex gradient the sum over the sets.  The CPU twin of
+    tests/test_raster_gpu.py::test_colour_sets_in_one_pass_equal_separate_renders."""
+    c = cases.lasr_case("bumpy2", 1, 64)
+    s, S = c["settings"], 64
+    fv = np.ascontiguousarray(c["face_vertices"][0].reshape(-1, 9), np.float32)
+    F = len(fv)
+    rng = np.random.RandomState(5)
+    tex = rng.rand(K, F, 9).astype(np.float32)
+    tex[0] = c["textures"][0].reshape(F, 9)
+    bg = rng.rand(3 * K).astype(np.float32)
+    gimg = (rng.randn(3 * K + 1, S, S) * 1e-3).astype(np.float32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    F32, I = ctypes.c_float, ctypes.c_int
+    scal = (F32(s["near"]), F32(s["far"]), F32(s["sigma_val"]), F32(s["gamma_val"]), F32(s["eps"]), F32(DIST_EPS))
+    L = libs[1]
+    texK = np.ascontiguousarray(tex.transpose(1, 0, 2).reshape(F, 9 * K))            # [F][9K], set-major per face
+    img = np.zeros((3 * K + 1, S, S), np.float32); agg = np.zeros((2, S, S), np.float32)
+    assert L.lasr_host_forward_sets(P(fv), P(texK), I(F), I(S), I(K), *scal, P(bg), P(img), P(agg)) == 0
+    singles = []
+    for k in range(K):
+        im1 = np.zeros((4, S, S), np.float32); ag1 = np.zeros((2, S, S), np.float32)
+        t1 = np.ascontiguousarray(tex[k]); b1 = np.ascontiguousarray(bg[3 * k:3 * k + 3])
+        assert L.lasr_host_forward_sets(P(fv), P(t1), I(F), I(S), I(1), *scal, P(b1), P(im1), P(ag1)) == 0
+        assert np.array_equal(im1[:3].view(np.uint32), img[3 * k:3 * k + 3].view(np.uint32)), k
+        assert np.array_equal(im1[3].view(np.uint32), img[3 * K].view(np.uint32))
+        assert np.array_equal(ag1.view(np.uint32), agg.view(np.uint32))
+        singles.append((t1, im1, ag1))
+    for KF in (0, 1):
+        gf = np.zeros((F, 9), np.float32); gt = np.zeros((F, 9 * K), np.float32)
+        assert L.lasr_host_backward_sets(P(fv), P(texK), I(F), I(S), I(K), I(KF), *scal, P(img), P(agg), P(gimg), P(gf), P(gt)) == 0
+        gf_sum = np.zeros((F, 9), np.float64)
+        for k, (t1, im1, ag1) in enumerate(singles):
+            g1 = np.zeros((4, S, S), np.float32)
+            if k >= KF:
+                g1[:3] = gimg[3 * k:3 * k + 3]
+            if k == K - 1:
+                g1[3] = gimg[3 * K]                                   # the silhouette's gradient enters once
+            a = np.zeros((F, 9), np.float32); b = np.zeros((F, 9), np.float32)
+            assert L.lasr_host_backward_sets(P(fv), P(t1), I(F), I(S), I(1), I(0), *scal, P(im1), P(ag1), P(g1), P(a), P(b)) == 0
+            gf_sum += a
+            got = gt[:, 9 * k:9 * k + 9]
+            if k < KF:
+                assert not got.any()                                  # detached set: no colour gradient
+            else:
+                assert np.array_equal(got.view(np.uint32), b.view(np.uint32)), (KF, k)
+        scale = np.abs(gf_sum).max()
+        assert scale > 0 and np.abs(gf - gf_sum).max() < 2e-5 * scale, (KF, np.abs(gf - gf_sum).max(), scale)
