@@ -17,7 +17,12 @@ SPOT_FIXTURE = os.path.join(_REPO, "tests", "golden", "spot_mesh.npz")
 def icosphere(level: int, radius: float = 1.0):
     """Unit icosahedron subdivided ``level`` times (level 3 -> 642 V / 1280 F, 4 -> 2562 / 5120,
     5 -> 10242 / 20480), the mesh family LASR initialises from (``--subdivide``,
-    nnutils/mesh_net.py:63).  Returns (vertices float32 [V,3], faces int32 [F,3])."""
+    nnutils/mesh_net.py:63).  Returns (vertices float32 [V,3], faces int32 [F,3]).
+
+    Same vertex and face counts as the reference's ``meshzoo.iso_sphere(level)`` (third_party/ext_utils/meshzoo.py:229),
+    same level-1 mesh; from level 2 on the vertices sit slightly differently on the sphere -- meshzoo refines the flat
+    icosahedron ``level`` times and projects once, this projects the midpoints at every level.  Benchmark shapes B / D
+    are defined by their counts; the golden cases hash these very vertices, so the construction stays."""
     t = (1.0 + 5.0 ** 0.5) / 2.0
     v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
          (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
