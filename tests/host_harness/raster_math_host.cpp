@@ -401,4 +401,13 @@ extern "C" int lasr_host_backward_sets(const float* faces9, const float* tex, in
   return 1;
 }
 
+// coord_window on n intervals: the inclusive pixel-index windows both kernels cull with (setup kernel -> face_window; the
+// backward sweeps them).  They must contain every pixel whose centre passes the exact float predicate lo <= c <= hi.
+extern "C" void lasr_host_coord_windows(const float* lo, const float* hi, int n, int S, int* out_lo_hi) {
+  for (int i = 0; i < n; ++i) coord_window(lo[i], hi[i], S, out_lo_hi[2 * i], out_lo_hi[2 * i + 1]);
+}
+extern "C" void lasr_host_pixel_coords(int S, float* out) {
+  for (int i = 0; i < S; ++i) out[i] = pixel_coord(i, S);
+}
+
 extern "C" int lasr_host_fast_inside(void) { return LASR_FAST_INSIDE; }

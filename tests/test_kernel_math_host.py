@@ -328,3 +328,34 @@ def test_colour_set_kernels_on_the_host_equal_separate_passes(libs, K):
                 assert np.array_equal(got.view(np.uint32), b.view(np.uint32)), (KF, k)
         scale = np.abs(gf_sum).max()
         assert scale > 0 and np.abs(gf - gf_sum).max() < 2e-5 * scale, (KF, np.abs(gf - gf_sum).max(), scale)
+
+
+@pytest.mark.parametrize("S", [7, 64, 256, 513, 2048, 8192])
+def test_pixel_windows_contain_every_pixel_the_exact_predicate_accepts(libs, S):
+    """coord_window (raster_common.cuh) turns a face's dilated box into the integer pixel window the forward's tile and
+    footprint culls and the backward's sweep use; the exact float predicate of the reference (.cu:32-38) is applied per
+    pixel afterwards, so the window only has to be a superset -- for every image size up to the supported maximum, for
+    boxes on pixel centres, half-open at the image border, far outside, one ulp wide, and for NaN / inf (culled)."""
+    rng = np.random.RandomState(S)
+    coords = np.zeros(S, np.float32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    libs[1].lasr_host_pixel_coords(ctypes.c_int(S), P(coords))
+    assert np.array_equal(coords, ((2.0 * np.arange(S) + 1.0 - S) / S).astype(np.float32))    # .cu:345 in double, rounded once
+    lo = rng.uniform(-1.3, 1.3, 4000).astype(np.float32)
+    hi = (lo + np.abs(rng.standard_cauchy(4000)).astype(np.float32) * 0.02).astype(np.float32)
+    c = rng.choice(coords, 1000)
+    lo = np.concatenate([lo, c, c, np.nextafter(c, np.float32(-9)), c - 3e-8, [-5, 2, -np.inf, np.nan, 0.0, -1.0]]).astype(np.float32)
+    hi = np.concatenate([hi, c, np.nextafter(c, np.float32(9)), c, c + 3e-8, [-4, 3, 0.0, 1.0, np.inf, 1.0]]).astype(np.float32)
+    n = len(lo)
+    out = np.zeros((n, 2), np.int32)
+    libs[1].lasr_host_coord_windows(P(lo), P(hi), ctypes.c_int(n), ctypes.c_int(S), P(out))
+    with np.errstate(invalid="ignore"):
+        accept = (coords[None, :] >= lo[:, None]) & (coords[None, :] <= hi[:, None])           # exact predicate per pixel
+    idx = np.arange(S)[None, :]
+    inside = (idx >= out[:, :1]) & (idx <= out[:, 1:])
+    finite = np.isfinite(lo) & np.isfinite(hi)
+    assert not (accept & ~inside)[finite].any()
+    assert (out[~finite, 0] > out[~finite, 1]).all()                                            # NaN / inf boxes: empty window
+    assert (out[finite, 0] >= 0).all() and (out[finite, 1] <= S - 1).all()
+    width = (out[:, 1] - out[:, 0] + 1).clip(0)[finite]
+    assert (width <= accept.sum(1)[finite] + 4).all()                                           # and not wastefully wide
