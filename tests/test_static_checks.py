@@ -59,16 +59,41 @@ def _header_arities():
     return out
 
 
-def test_ctypes_signatures_have_the_headers_arity():
-    """Every prototype of include/lasr_b200.h against the argtypes lasr_b200/_cabi.py declares for it."""
+def _header_kinds():
+    """name -> parameter kinds ('ptr' | 'int' | 'float' | 'size') of every prototype in include/lasr_b200.h."""
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "lasr_b200.h")).read(), flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+
+    def kind(p):
+        if "*" in p:
+            return "ptr"
+        t = re.sub(r"\b\w+$", "", p.strip()).replace("const", "").strip() or p.strip()
+        return {"int": "int", "int32_t": "int", "float": "float", "size_t": "size", "cudaStream_t": "ptr"}[t]
+    out = {}
+    for m in re.finditer(r"\b(lasr_b200_\w+)\s*\(([^)]*)\)\s*;", src):
+        params = m.group(2).strip()
+        out[m.group(1)] = [] if params in ("", "void") else [kind(p) for p in params.split(",")]
+    return out
+
+
+def test_ctypes_signatures_follow_the_header_parameter_by_parameter():
+    """Every prototype of include/lasr_b200.h against the argtypes lasr_b200/_cabi.py declares for it: same number of
+    parameters, and a pointer / int / float / size_t in the same positions."""
+    import ctypes
     from lasr_b200 import _cabi
     L = _cabi.lib()
-    ar = _header_arities()
-    assert set(ar) == set(_cabi.EXPORTED_SYMBOLS)
-    for name, n in ar.items():
+    assert {k: len(v) for k, v in _header_kinds().items()} == _header_arities()
+
+    def ckind(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or (hasattr(t, "_type_") and not isinstance(t._type_, str)):
+            return "ptr"
+        return {ctypes.c_int: "int", ctypes.c_float: "float", ctypes.c_size_t: "size"}[t]
+    kinds = _header_kinds()
+    assert set(kinds) == set(_cabi.EXPORTED_SYMBOLS)
+    for name, want in kinds.items():
         fn = getattr(L, name)
-        have = len(fn.argtypes) if fn.argtypes is not None else 0
-        assert have == n, (name, "header", n, "ctypes", have)
+        have = [ckind(t) for t in (fn.argtypes or [])]
+        assert have == want, (name, "header", want, "ctypes", have)
 
 
 def test_native_calls_pass_as_many_arguments_as_the_entry_point_takes():
