@@ -93,3 +93,28 @@ def test_every_compute_entry_point_refuses_null_arguments_with_a_message():
         assert msg and msg.split(":")[0].split("_")[0] in name, (name, msg)
         checked += 1
     assert checked >= 27 and _cabi.launch_count() == before
+
+
+def test_a_plain_c_program_binds_the_library(tmp_path, lib):
+    """The boundary is a C ABI: include/lasr_b200.h must be valid C99 (no C++ in the signatures) and a C program linked
+    against liblasr_b200.so must be able to call it -- here the version query and one refused call (null arguments are
+    rejected before the device is touched, so this runs without a GPU)."""
+    import shutil
+    import subprocess
+    from lasr_b200 import _build
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "consumer.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "lasr_b200.h"\n'
+                   "int main(void) {\n"
+                   "  int v = lasr_b200_abi_version();\n"
+                   "  int rc = lasr_b200_chamfer_forward(NULL, NULL, NULL, NULL, NULL, NULL, 1, 4, 4, NULL);\n"
+                   '  printf("%d %d %s\\n", v, rc, lasr_b200_last_error());\n'
+                   "  return (v >= 4 && rc != 0 && strlen(lasr_b200_last_error()) > 0) ? 0 : 1;\n}\n")
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(_build.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-llasr_b200", "-Wl,-rpath," + libdir])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "chamfer_forward" in r.stdout
