@@ -178,6 +178,19 @@ __device__ __forceinline__ float pixel_coord(int i, int S) {
   return (float)((2.0 * (double)i + 1.0 - (double)S) / (double)S);
 }
 
+// EXPERIMENTAL, off by default, not yet run on a GPU (profiles/round1g_instruction_budget.md): a lane fetches the row of
+// `a` and the reciprocal of the edge it selected with four 32-bit loads from the face's record (L1-resident, at most three
+// distinct addresses per warp) instead of the three divergent arms of register moves the compiler builds for
+// "pick edge e's constants" -- 10-15 % of a pair evaluation at a quarter of the lanes.  Same values, same bits.
+#ifndef LASR_EDGE_LOAD
+#define LASR_EDGE_LOAD 0
+#endif
+#ifdef __CUDA_ARCH__
+#define LASR_ASSUME(x) __builtin_assume(x)
+#else
+#define LASR_ASSUME(x) ((void)0)
+#endif
+
 // ---- per-face derived quantities (.cu:245-305 + the border box of :32-38) -------------------
 struct FaceGeom {
   float inv[9];       // inverse of [[x0 x1 x2],[y0 y1 y2],[1 1 1]] (rows give barycentrics)
@@ -190,6 +203,9 @@ struct FaceGeom {
   float kappa;        // edge-prediction trust threshold (see euclid_distance): (s_mid - s_lo)^2 > kappa * s_mid
   int obt;            // index of the (first) obtuse corner, -1 if none
   bool front;
+#if LASR_EDGE_LOAD
+  const float* rec;   // the face's record in memory when the geometry was loaded from one (else nullptr)
+#endif
 };
 
 __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float sthr, FaceGeom& g) {
@@ -244,6 +260,9 @@ __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float s
     const float ke = 2.f * LASR_NOISE_K * eta / det;
     g.kappa = ke * ke;   // inf / NaN for degenerate faces: the prediction is then never trusted
   }
+#if LASR_EDGE_LOAD
+  g.rec = nullptr;
+#endif
   g.hix = __fadd_rn(max3(x0, x1, x2), sthr);
   g.lox = __fsub_rn(min3(x0, x1, x2), sthr);
   g.hiy = __fadd_rn(max3(y0, y1, y2), sthr);
@@ -300,6 +319,9 @@ __device__ __forceinline__ void load_record(const float* __restrict__ r, FaceGeo
     g.z[k] = K == 1 ? v[41 + k] : 0.f;
   }
   g.kappa = v[31];
+#if LASR_EDGE_LOAD
+  g.rec = r;
+#endif
   const int fl = __float_as_int(v[15]);
   g.obt = (fl & 3) - 1;
   g.front = (fl & 4) != 0;
@@ -406,12 +428,30 @@ __device__ __forceinline__ void euclid_distance(const FaceGeom& g, float xp, flo
     }
   }
   // pick the row of `a` for edge e without dynamic register indexing
+#if LASR_EDGE_LOAD
+  float a0, a1, a2, rd, ae, ab;
+  if (kFast != 0 && g.rec != nullptr) {       // record words 19+e (rden) and 22+3e.. (row e of a), see store_record
+    const float* row = g.rec + 22 + 3 * e;
+    a0 = __ldg(row); a1 = __ldg(row + 1); a2 = __ldg(row + 2);
+    rd = __ldg(g.rec + 19 + e);
+    ae = __ldg(g.rec + 22 + 4 * e);                                  // a[e][e]
+    ab = __ldg(g.rec + (e == 0 ? 23 : (e == 1 ? 27 : 28)));          // a[e][(e+1)%3]
+  } else {
+    a0 = e == 0 ? g.a[0][0] : (e == 1 ? g.a[1][0] : g.a[2][0]);
+    a1 = e == 0 ? g.a[0][1] : (e == 1 ? g.a[1][1] : g.a[2][1]);
+    a2 = e == 0 ? g.a[0][2] : (e == 1 ? g.a[1][2] : g.a[2][2]);
+    rd = e == 0 ? g.rden[0] : (e == 1 ? g.rden[1] : g.rden[2]);
+    ae = e == 0 ? a0 : (e == 1 ? a1 : a2);
+    ab = e == 0 ? a1 : (e == 1 ? a2 : a0);
+  }
+#else
   const float a0 = e == 0 ? g.a[0][0] : (e == 1 ? g.a[1][0] : g.a[2][0]);
   const float a1 = e == 0 ? g.a[0][1] : (e == 1 ? g.a[1][1] : g.a[2][1]);
   const float a2 = e == 0 ? g.a[0][2] : (e == 1 ? g.a[1][2] : g.a[2][2]);
   const float ae = e == 0 ? a0 : (e == 1 ? a1 : a2);
   const float ab = e == 0 ? a1 : (e == 1 ? a2 : a0);
   const float rd = e == 0 ? g.rden[0] : (e == 1 ? g.rden[1] : g.rden[2]);
+#endif
   const float num = __fsub_rn(dot3(w0, a0, w1, a1, w2, a2), ab);
   const float den = __fsub_rn(ae, ab);
   const float q = kFast ? div_by_rcp(num, den, rd) : __fdiv_rn(num, den);
@@ -512,6 +552,9 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConst
   FaceGeom g;
   float tex9[9 * K];
   load_record<K>(rec, g, tex9);
+#if LASR_EDGE_LOAD
+  LASR_ASSUME(g.rec != nullptr);
+#endif
   Fragment fr;
   if (!soft_fragment<kMode>(A, g, xp, yp, C.thr, fr)) return;
   const int alpha_f = kFast ? 2 : A.alpha;

@@ -181,6 +181,12 @@ extern "C" void lasr_host_backward(const float* faces9, const float* textures9, 
     FaceGeom g;
     face_setup(faces9 + 9 * f, sthr, g);
     const float* tex9 = textures9 + 9 * f;
+#if LASR_EDGE_LOAD   // as the kernel with setup_done = 1: the geometry comes back from the record (and may read it per lane)
+    alignas(16) float rec_buf[rec_words(1)];
+    float tex_back[9];
+    store_record<1>(rec_buf, g, tex9);
+    load_record<1>(rec_buf, g, tex_back);
+#endif
     float* gtex_out = grad_tex + 9 * f;
     float gf[9] = {0}, gt[9] = {0};
     int xlo, xhi, ylo, yhi;
@@ -411,3 +417,4 @@ extern "C" void lasr_host_pixel_coords(int S, float* out) {
 }
 
 extern "C" int lasr_host_fast_inside(void) { return LASR_FAST_INSIDE; }
+extern "C" int lasr_host_edge_load(void) { return LASR_EDGE_LOAD; }

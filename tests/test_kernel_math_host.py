@@ -359,3 +359,35 @@ def test_pixel_windows_contain_every_pixel_the_exact_predicate_accepts(libs, S):
     assert (out[finite, 0] >= 0).all() and (out[finite, 1] <= S - 1).all()
     width = (out[:, 1] - out[:, 0] + 1).clip(0)[finite]
     assert (width <= accept.sum(1)[finite] + 4).all()                                           # and not wastefully wide
+
+
+def test_edge_load_variant_is_bit_identical_on_the_host(libs, tmp_path):
+    """-DLASR_EDGE_LOAD=1 (experimental, off by default): the selected edge's constants come from per-lane loads of the
+    face record instead of register selects.  Same values, so the forward images, the aggregates and the backward
+    gradients of the kernels' own code must not change by a single bit."""
+    so = str(tmp_path / "raster_math_host_edge.so")
+    subprocess.check_call([os.path.join(ROOT, "tests", "host_harness", "build.sh"), so, "-DLASR_EDGE_LOAD=1"])
+    E = ctypes.CDLL(so)
+    assert E.lasr_host_edge_load() == 1 and libs[1].lasr_host_edge_load() == 0
+    from oracle import oracle as O
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    F32, I = ctypes.c_float, ctypes.c_int
+    for mesh, S, sigma in (("bumpy2", 96, 1e-4), ("spot", 128, 1e-4), ("ico2", 64, 1e-5)):
+        c = cases.lasr_case(mesh, 1, S, sigma=sigma)
+        s = c["settings"]
+        fv = np.ascontiguousarray(c["face_vertices"][0].reshape(-1, 9), np.float32)
+        tx = np.ascontiguousarray(c["textures"][0].reshape(-1, 9), np.float32)
+        n = len(fv)
+        bg = np.zeros(3, np.float32)
+        scal = (F32(s["near"]), F32(s["far"]), F32(sigma), F32(s["gamma_val"]), F32(s["eps"]), F32(DIST_EPS))
+        res = []
+        for L in (libs[1], E):
+            img = np.zeros((4, S, S), np.float32); agg = np.zeros((2, S, S), np.float32)
+            L.lasr_host_forward(P(fv), P(tx), I(n), I(S), *scal, P(bg), P(img), P(agg))
+            gsc = np.ascontiguousarray(c["grad_soft_colors"][0])
+            gf = np.zeros((n, 9), np.float32); gt = np.zeros((n, 9), np.float32)
+            L.lasr_host_backward(P(fv), P(tx), I(n), I(S), *scal, P(img), P(agg), P(gsc), P(gf), P(gt), I(0))
+            res.append((img, agg, gf, gt))
+        for a, b in zip(*res):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (mesh, S)
+        assert res[0][2].any() and res[0][0][3].max() > 0.5
