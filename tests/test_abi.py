@@ -118,3 +118,31 @@ def test_a_plain_c_program_binds_the_library(tmp_path, lib):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, (r.stdout, r.stderr)
     assert "chamfer_forward" in r.stdout
+
+
+def test_module_constructors_refuse_what_the_reference_refuses():
+    """ValueError for unknown light / camera modes and for eye setters on a projection camera (lighting.py:41-42,
+    transform.py:87-99), the texture-mode assertion of SoftRenderer.set_texture_mode (renderer.py:86), and the explicit
+    refusals of what is out of scope here."""
+    import lasr_b200.soft_renderer as sr
+    with pytest.raises(ValueError):
+        sr.Lighting(light_mode="pixel")
+    with pytest.raises(ValueError):
+        sr.Transform(camera_mode="fisheye")
+    with pytest.raises(ValueError):
+        sr.SoftRenderer(camera_mode="look_at", light_mode="pixel")
+    r = sr.SoftRenderer(camera_mode="look_at")
+    with pytest.raises(AssertionError):
+        r.set_texture_mode("uv")
+    with pytest.raises(NotImplementedError):
+        sr.SoftRenderer()                       # camera_mode='projection' (the default) needs srf.projection: out of scope
+    with pytest.raises(NotImplementedError):
+        sr.functional.voxelization(None)
+    t = sr.Transform(camera_mode="look_at")
+    t.set_eyes([0, 0, -3.0])
+    assert t.eyes == [0, 0, -3.0]
+    import torch
+    with pytest.raises(ValueError):
+        sr.functional.look_at(torch.zeros(4, 3), [0, 0, -1])          # vertices must be [N,V,3] (look_at.py:16-17)
+    with pytest.raises(AssertionError):
+        sr.functional.face_vertices(torch.zeros(2, 4, 3), torch.zeros(3, 4, 3, dtype=torch.int32))   # face_vertices.py:10-13 asserts
