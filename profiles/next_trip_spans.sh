@@ -24,10 +24,13 @@ build)
   LASR_B200_LIB=$V/edgeload.so python -m lasr_b200._build -DLASR_EDGE_LOAD=1 &
   LASR_B200_LIB=$V/spans_edgeload.so python -m lasr_b200._build -DLASR_BWD_SPANS=1 -DLASR_EDGE_LOAD=1 &
   wait
-  for v in base spans spans_ftz ftz edgeload spans_edgeload; do rm -rf lasr_b200/csrc/build/$v.so.obj; done     # object caches need not travel
+  # three-set forward (the hot path's): 2 resident CTAs at 118 registers and no stack frame instead of 3 at 80 with 56 B spilled
+  LASR_B200_LIB=$V/fwdm2.so python -m lasr_b200._build -DLASR_FWD_MIN_BLOCKS_MULTI=2 &
+  wait
+  for v in base spans spans_ftz ftz edgeload spans_edgeload fwdm2; do rm -rf lasr_b200/csrc/build/$v.so.obj; done     # object caches need not travel
   ls -la $V ;;
 run)
-  bash profiles/trip_ab.sh spans base spans edgeload spans_edgeload spans_ftz ftz     # (the ftz builds differ from base by <= 3e-5 in the gradients)
+  bash profiles/trip_ab.sh spans base spans edgeload spans_edgeload spans_ftz ftz fwdm2     # (the ftz builds differ from base by <= 3e-5 in the gradients)
   LASR_B200_LIB=$V/spans.so python -m pytest tests/test_raster_gpu.py tests/test_hotpath_gpu.py -q -x 2>&1 | tail -3
   LASR_B200_LIB=$V/spans.so ncu --set full --clock-control none --import-source on -k regex:"raster_backward_kernel" -s 4 -c 1 \
       -o gpurun_out/spans/backward python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 3 > gpurun_out/spans/ncu.log 2>&1 || true ;;
