@@ -391,3 +391,8 @@ def test_edge_load_variant_is_bit_identical_on_the_host(libs, tmp_path):
         for a, b in zip(*res):
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (mesh, S)
         assert res[0][2].any() and res[0][0][3].max() > 0.5
+        # ... and together with the span sweep (the spans_edgeload build of profiles/next_trip_spans.sh)
+        img, agg = res[1][0], res[1][1]
+        gf = np.zeros((n, 9), np.float32); gt = np.zeros((n, 9), np.float32)
+        E.lasr_host_backward(P(fv), P(tx), I(n), I(S), *scal, P(img), P(agg), P(gsc), P(gf), P(gt), I(1))
+        assert np.array_equal(gf.view(np.uint32), res[0][2].view(np.uint32)) and np.array_equal(gt.view(np.uint32), res[0][3].view(np.uint32))
