@@ -38,6 +38,11 @@
 // this is NOT bit-identical to the reference on a GPU; the measured gap is
 // recorded in tests/golden/README.md.
 //
+// min / max: the reference writes `min(max(t, 0.), 1.)` etc. in device code, where min / max on doubles are fmin /
+// fmax -- a NaN operand is dropped.  That matters for exactly degenerate faces (a zero-length edge makes the
+// closest-point parameter 0/0, which the clamp turns into 0 on the GPU); std::min / std::max would propagate the NaN
+// into every pixel of the face's box.  std::fmin / std::fmax are used wherever the reference clamps.
+//
 // Parity status: pinned against outputs of the reference kernels themselves
 // (oracle/_ref, built from the unmodified reference sources) run on a B200 --
 // see tests/golden/ and tests/test_oracle_vs_reference_golden.py.
@@ -109,8 +114,9 @@ inline bool pixel_inside(const T* w) {  // :47-50
 
 template <class T>
 inline void bary_clip(T* w) {  // :53-58  (min/max against double literals)
-  for (int k = 0; k < 3; ++k) w[k] = T(std::max(std::min(double(w[k]), 1.0), 0.0));
-  const T wsum = T(std::max(double(w[0] + w[1] + w[2]), 1e-5));
+  // CUDA's min/max on doubles are fmin/fmax: a NaN operand is dropped, not propagated (std::min/std::max would keep it)
+  for (int k = 0; k < 3; ++k) w[k] = T(std::fmax(std::fmin(double(w[k]), 1.0), 0.0));
+  const T wsum = T(std::fmax(double(w[0] + w[1] + w[2]), 1e-5));
   for (int k = 0; k < 3; ++k) w[k] /= wsum;
 }
 
@@ -179,7 +185,7 @@ inline void euclid_p2f(T& sign, T& dx, T& dy, const T* w, T* t, const T* fv, con
     t[b] = 1 - t[a];
     t[c] = 0;
     for (int k = 0; k < 3; ++k) {
-      t[k] = T(std::min(std::max(double(t[k]), 0.0), 1.0));
+      t[k] = T(std::fmin(std::fmax(double(t[k]), 0.0), 1.0));   // fmax(NaN, 0) = 0: a zero-length edge (0/0) clamps to 0, as on the GPU
       t[k] -= w[k];
     }
     dx = dot3(t[0], fv[0], t[1], fv[3], t[2], fv[6]);
@@ -250,7 +256,7 @@ inline void face_precompute(const T* fv, T* info) {
                     py[2] - py[0], px[0] - px[2], cross2(px[2], py[0], px[0], py[2]),
                     py[0] - py[1], px[1] - px[0], cross2(px[0], py[1], px[1], py[0])};
   T det = dot3(px[2], py[0] - py[1], px[0], py[1] - py[2], px[1], py[2] - py[0]);
-  det = det > 0 ? T(std::max(double(det), 1e-10)) : T(std::min(double(det), -1e-10));
+  det = det > 0 ? T(std::fmax(double(det), 1e-10)) : T(std::fmin(double(det), -1e-10));
   for (int k = 0; k < 9; ++k) inv[k] = adj[k] / det;
   for (int j = 0; j < 3; ++j)
     for (int k = 0; k < 3; ++k) sym[3 * j + k] = dot2(px[j], px[k], py[j], py[k]) + 1;
@@ -479,7 +485,7 @@ void backward_impl(const RasterParams& P, const T* faces, const T* textures, con
         if (P.alpha_func == 1) {
           Ca /= F;
         } else if (P.alpha_func == 2) {
-          Ca = T(double(Ca) * (double(1 - sc[3 * SS]) / std::max(double(1 - frag), 1e-6)));
+          Ca = T(double(Ca) * (double(1 - sc[3 * SS]) / std::fmax(double(1 - frag), 1e-6)));
         }
         Cxy += Ca;
         // depth (:596-599)
