@@ -431,3 +431,45 @@ def test_kernel_code_matches_the_oracle_on_pathological_soups(libs, kind):
         for ours, ref in ((gf, ogf.reshape(n, 9)), (gt, ogt.reshape(n, 9))):
             rep = parity.grad_report(ours, ref)
             assert rep["rel_l2"] < 1e-4 and rep["max_over_scale"] < 2e-4, (kind, sigma, rep)
+
+
+@pytest.mark.parametrize("kind", ["sliver", "degenerate"])
+def test_generic_kernel_code_matches_the_oracle_in_every_mode_combination(libs, kind):
+    """All 72 combinations of distance (hard / barycentric / euclidean), colour aggregation (hard / softmax), alpha
+    aggregation (hard / sum / prod), texture type (surface / vertex) and fill_back, on pathological soups: the generic
+    instantiation of the kernels' forward and backward code (host build) against the oracle."""
+    import itertools
+    from oracle import oracle as O
+    import parity
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    F32, I = ctypes.c_float, ctypes.c_int
+    S, n = 32, 70
+    for dist, rgb, alpha, tt, fb in itertools.product(DIST_ID, RGB_ID, ALPHA_ID, SAMPLE_ID, (True, False)):
+        rng = np.random.RandomState(7)
+        fv = _soup(rng, n, kind).astype(np.float32)
+        Tt = 3 if tt == "vertex" else 4
+        tx = rng.rand(n, Tt, 3).astype(np.float32)
+        if tt == "surface":
+            fv[-1, [0, 3, 6]] += 10          # the last face's out-of-bounds texel read is undefined in the reference (cases.py)
+        sigma = 1e-2 if dist == "barycentric" else 1e-4
+        s = dict(image_size=S, background_color=[0.1, 0.2, 0.3], near=4.0, far=16.0, fill_back=fb, eps=1e-3, sigma_val=sigma,
+                 dist_func=dist, dist_eps=1e-4, gamma_val=1e-4 if rgb == "hard" else 1e-2, aggr_func_rgb=rgb,
+                 aggr_func_alpha=alpha, texture_type=tt)
+        r = O.soft_rasterize_forward(fv.reshape(1, n, 3, 3), tx.reshape(1, n, Tt, 3), s, np.float32)
+        g = (rng.randn(1, 4, S, S) * 1e-3).astype(np.float32)
+        ogf, ogt = O.soft_rasterize_backward(r, g)
+        scal = (F32(s["near"]), F32(s["far"]), F32(sigma), F32(s["gamma_val"]), F32(s["eps"]), F32(DIST_EPS)) + \
+            tuple(I(v) for v in (DIST_ID[dist], RGB_ID[rgb], ALPHA_ID[alpha], SAMPLE_ID[tt], int(fb)))
+        img = np.zeros((4, S, S), np.float32); agg = np.zeros((2, S, S), np.float32)
+        bg = np.asarray(s["background_color"], np.float32)
+        libs[1].lasr_host_forward_modes(P(fv), P(tx), I(n), I(S), I(Tt), *scal, P(bg), P(img), P(agg))
+        gf = np.zeros((n, 9), np.float32); gt = np.zeros((n, Tt, 3), np.float32)
+        sc = np.ascontiguousarray(r["soft_colors"][0]); ag = np.ascontiguousarray(r["aggrs_info"][0])
+        libs[1].lasr_host_backward_modes(P(fv), P(tx), I(n), I(S), I(Tt), *scal, P(sc), P(ag), P(np.ascontiguousarray(g[0])), P(gf), P(gt))
+        tag = (kind, dist, rgb, alpha, tt, fb)
+        assert np.isfinite(img).all() and np.isfinite(gf).all() and np.isfinite(gt).all(), tag
+        ir = parity.image_report(img[None], r["soft_colors"], rel=1e-4)
+        assert ir["n_bad"] == 0, (tag, ir)
+        for ours, ref in ((gf, ogf.reshape(n, 9)), (gt, ogt.reshape(n, Tt, 3))):
+            rep = parity.grad_report(ours, ref)
+            assert rep["scale"] < 1e-20 or (rep["rel_l2"] < 1e-3 and rep["max_over_scale"] < 1e-3), (tag, rep)
