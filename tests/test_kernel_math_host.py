@@ -473,3 +473,64 @@ def test_generic_kernel_code_matches_the_oracle_in_every_mode_combination(libs, 
         for ours, ref in ((gf, ogf.reshape(n, 9)), (gt, ogt.reshape(n, Tt, 3))):
             rep = parity.grad_report(ours, ref)
             assert rep["scale"] < 1e-20 or (rep["rel_l2"] < 1e-3 and rep["max_over_scale"] < 1e-3), (tag, rep)
+
+
+def test_kernel_code_matches_the_oracle_across_depth_ranges_sizes_and_scales(libs):
+    """Random soups with vertices behind the camera and at z = 0 (NaN in the reference's arithmetic: the NaN pixels must
+    be the same ones), far off screen, odd image sizes, very sharp and very wide sigma, empty and inverted depth
+    windows: the kernels' own forward / backward code (host build) against the oracle."""
+    from oracle import oracle as O
+    import parity
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    F32, I = ctypes.c_float, ctypes.c_int
+    rng0 = np.random.RandomState(5)
+    base = _soup(rng0, 300, "random").astype(np.float32)
+    zcols, xycols = [2, 5, 8], [0, 1, 3, 4, 6, 7]
+
+    def variant(tag):
+        f = base.copy()
+        if tag == "behind":
+            f[:, zcols] = rng0.uniform(-2, 20, (300, 3))
+        elif tag == "z0":
+            f[:, zcols] = rng0.uniform(0.5, 3, (300, 3)); f[::7, 2] = 0.0
+        elif tag == "off4":
+            f[:, xycols] *= 4
+        elif tag == "off50":
+            f[:, xycols] *= 50
+        elif tag == "flat":
+            f[:, zcols] = 10.0
+        return f
+    runs = [("behind", 64, 1.0, 15.0, 1e-4), ("z0", 64, 0.1, 5.0, 1e-4), ("off4", 64, 4.0, 16.0, 1e-4),
+            ("off50", 64, 4.0, 16.0, 1e-4), ("base", 37, 4.0, 16.0, 1e-4), ("base", 130, 4.0, 16.0, 1e-6),
+            ("base60", 48, 4.0, 16.0, 1e-2), ("flat", 64, 4.0, 16.0, 1e-4), ("base", 64, 16.0, 4.0, 1e-4),
+            ("base", 64, 10.0, 10.0, 1e-4)]
+    for tag, S, near, far, sigma in runs:
+        fv = variant(tag)[:60] if tag == "base60" else variant(tag)
+        n = len(fv)
+        rng = np.random.RandomState(11)
+        tx = rng.rand(n, 9).astype(np.float32)
+        s = dict(image_size=S, background_color=[0.1, 0.2, 0.3], near=near, far=far, fill_back=True, eps=1e-3, sigma_val=sigma,
+                 dist_func="euclidean", dist_eps=1e-4, gamma_val=1e-2, aggr_func_rgb="softmax", aggr_func_alpha="prod",
+                 texture_type="vertex")
+        r = O.soft_rasterize_forward(fv.reshape(1, n, 3, 3), tx.reshape(1, n, 3, 3), s, np.float32)
+        g = (rng.randn(1, 4, S, S) * 1e-3).astype(np.float32)
+        ogf, ogt = O.soft_rasterize_backward(r, g)
+        img = np.zeros((4, S, S), np.float32); agg = np.zeros((2, S, S), np.float32)
+        bg = np.asarray(s["background_color"], np.float32)
+        scal = (F32(near), F32(far), F32(sigma), F32(s["gamma_val"]), F32(s["eps"]), F32(DIST_EPS))
+        libs[1].lasr_host_forward(P(fv), P(tx), I(n), I(S), *scal, P(bg), P(img), P(agg))
+        gf = np.zeros((n, 9), np.float32); gt = np.zeros((n, 9), np.float32)
+        sc = np.ascontiguousarray(r["soft_colors"][0]); ag = np.ascontiguousarray(r["aggrs_info"][0])
+        libs[1].lasr_host_backward(P(fv), P(tx), I(n), I(S), *scal, P(sc), P(ag), P(np.ascontiguousarray(g[0])), P(gf), P(gt), I(0))
+        what = (tag, S, near, far, sigma)
+        ref_img, rgf, rgt = r["soft_colors"][0], ogf.reshape(n, 9), ogt.reshape(n, 9)
+        assert np.array_equal(np.isnan(img), np.isnan(ref_img)), what
+        assert np.array_equal(np.isnan(gf), np.isnan(rgf)) and np.array_equal(np.isnan(gt), np.isnan(rgt)), what
+        assert (tag == "z0") == bool(np.isnan(ref_img).any()), what
+        ok = ~np.isnan(ref_img)
+        d = np.abs(img - ref_img)[ok]
+        assert d.max() < 5e-5, (what, d.max())
+        for ours, ref in ((gf, rgf), (gt, rgt)):
+            m = ~np.isnan(ref)
+            rep = parity.grad_report(np.where(m, ours, 0), np.where(m, ref, 0))
+            assert rep["scale"] < 1e-20 or (rep["rel_l2"] < 1e-4 and rep["max_over_scale"] < 2e-4), (what, rep)
