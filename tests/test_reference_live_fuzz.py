@@ -1,0 +1,100 @@
+"""Randomised comparison of the host-side mirrors with the reference's own Python, imported live from /root/reference
+(build container only; skipped where the tree is absent).  The golden vectors pin fixed cases that travel; this sweeps
+shapes and arguments the goldens do not: hypothesis / bone / vertex counts, tocam on and off, per-frame eyes, list and
+tensor arguments, big- and little-endian colour and grey PFM files."""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "nnutils", "geom_utils.py")),
+                                reason="reference tree not present (GPU box)")
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _close(tag, a, b, tol=1e-6):
+    d = float((a - b).abs().max())
+    assert d <= tol * max(1.0, float(b.abs().max())), (tag, d)
+
+
+def test_geometry_mirrors_follow_the_reference_on_random_shapes(monkeypatch):
+    import warnings
+    from lasr_b200 import geom_utils as gu
+    import lasr_b200.soft_renderer.functional as srf
+    monkeypatch.setitem(sys.modules, "soft_renderer", types.ModuleType("soft_renderer"))      # nnutils/geom_utils.py:24
+    rg = _load(os.path.join(REF, "nnutils/geom_utils.py"), "ref_geom_live")
+    fdir = os.path.join(REF, "third_party/softras/soft_renderer/functional")
+    R = {n: getattr(_load(os.path.join(fdir, n + ".py"), "ref_live_" + n), n)
+         for n in ("look_at", "orthogonal", "perspective", "face_vertices", "vertex_normals", "ambient_lighting",
+                   "directional_lighting", "get_points_from_angles")}
+    g = torch.Generator().manual_seed(0)
+    ri = lambda lo, hi: int(torch.randint(lo, hi, (1,), generator=g))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                       # the reference calls torch.cross without dim
+        for _ in range(25):
+            bs, H, B, V = ri(1, 4), ri(1, 3), ri(1, 5), ri(5, 40)
+            N = 2 * bs * H
+            verts = torch.randn(N, V, 3, generator=g)
+            Rm = gu.quaternion_to_rotation_matrix(torch.randn(N * B, 4, generator=g))
+            Tm = torch.randn(N * B, 1, 3, generator=g) + torch.tensor([0, 0, 8.0])
+            skin = torch.softmax(torch.randn(N, B - 1, V, 1, generator=g), 1) if B > 1 else None
+            for tocam in (True, False):
+                _close(("obj_to_cam", N, B, V, tocam), gu.obj_to_cam(verts, Rm, Tm, B, H, skin, tocam=tocam),
+                       rg.obj_to_cam(verts, Rm, Tm, B, H, skin, tocam=tocam))
+            v4 = torch.cat([verts + torch.tensor([0, 0, 6.0]), torch.ones(N, V, 1)], -1)
+            pp, fl = torch.randn(2 * bs, 2, generator=g) * 0.1, 8 + torch.rand(2 * bs, H, generator=g)
+            _close("pinhole_cam", gu.pinhole_cam(v4, pp, fl), rg.pinhole_cam(v4.clone(), pp, fl))
+            _close("orthographic_cam", gu.orthographic_cam(v4, pp, fl), rg.orthographic_cam(v4.clone(), pp, fl))
+            nb, nf = ri(1, 6), ri(4, 30)
+            nb, nf = (4 if nb == 3 else nb), (5 if nf == 3 else nf)       # the reference's dim-less torch.cross
+            vv = torch.randn(nb, V, 3, generator=g)
+            ff = torch.randint(0, V, (nb, nf, 3), generator=g, dtype=torch.int32)
+            _close("face_vertices", srf.face_vertices(vv, ff), R["face_vertices"](vv, ff))
+            _close("vertex_normals", srf.vertex_normals(vv, ff), R["vertex_normals"](vv, ff), 1e-5)
+            eye = [float(x) for x in torch.randn(3, generator=g) + torch.tensor([0, 0, -3.0])]
+            _close("look_at (list eye)", srf.look_at(vv, eye), R["look_at"](vv, eye), 1e-5)
+            eyes = torch.randn(nb, 3, generator=g) + torch.tensor([0, 0, -3.0])
+            _close("look_at (per-frame eyes)", srf.look_at(vv, eyes), R["look_at"](vv, eyes), 1e-5)
+            far = vv + torch.tensor([0, 0, 5.0])
+            _close("perspective", srf.perspective(far, angle=37.0), R["perspective"](far, angle=37.0))
+            _close("orthogonal", srf.orthogonal(vv, 1.3), R["orthogonal"](vv, 1.3))
+            light = torch.zeros(nb, V, 3)
+            nrm = torch.nn.functional.normalize(torch.randn(nb, V, 3, generator=g), dim=2)
+            _close("ambient_lighting", srf.ambient_lighting(light.clone(), 0.4, [1, 0.5, 0.2]),
+                   R["ambient_lighting"](light.clone(), 0.4, [1, 0.5, 0.2]))
+            _close("directional_lighting", srf.directional_lighting(light.clone(), nrm, 0.7, [1, 0.5, 0.2], [0.3, 0.8, -0.5]),
+                   R["directional_lighting"](light.clone(), nrm, 0.7, [1, 0.5, 0.2], [0.3, 0.8, -0.5]))
+            d, e, a = torch.rand(nb, generator=g) + 2, torch.rand(nb, generator=g) * 60 - 30, torch.rand(nb, generator=g) * 360
+            _close("get_points_from_angles", srf.get_points_from_angles(d, e, a), R["get_points_from_angles"](d, e, a))
+        assert srf.get_points_from_angles(2.7, 20.0, 40.0) == pytest.approx(R["get_points_from_angles"](2.7, 20.0, 40.0))
+
+
+def test_pfm_reader_follows_the_reference_reader(tmp_path, monkeypatch):
+    from lasr_b200.dataloader.pfm import readPFM
+    monkeypatch.setitem(sys.modules, "png", types.ModuleType("png"))          # pypng: imported by util_flow, unused here
+    uf = _load(os.path.join(REF, "third_party/ext_utils/util_flow.py"), "ref_util_flow_live")
+    rng = np.random.RandomState(0)
+    for i, (shape, little) in enumerate([((7, 9, 3), True), ((7, 9, 3), False), ((5, 4), True), ((5, 4), False),
+                                         ((1, 1, 3), True), ((33, 2), True)]):
+        data = rng.randn(*shape).astype(np.float32)
+        p = str(tmp_path / f"f{i}.pfm")
+        with open(p, "wb") as fh:
+            fh.write(b"PF\n" if data.ndim == 3 else b"Pf\n")
+            fh.write(f"{shape[1]} {shape[0]}\n".encode())
+            fh.write(b"-1.0\n" if little else b"1.0\n")
+            np.flipud(data).astype("<f4" if little else ">f4").tofile(fh)
+        a, sa = readPFM(p)
+        b, sb = uf.readPFM(p)
+        assert np.array_equal(a, b) and sa == sb and a.shape == b.shape, (shape, little)
+        assert np.array_equal(a, data)
