@@ -98,3 +98,48 @@ def test_pfm_reader_follows_the_reference_reader(tmp_path, monkeypatch):
         b, sb = uf.readPFM(p)
         assert np.array_equal(a, b) and sa == sb and a.shape == b.shape, (shape, little)
         assert np.array_equal(a, data)
+
+
+def test_image_losses_follow_the_reference_lines_on_random_inputs(monkeypatch):
+    """nnutils/mesh_net.py:361-363,372-447 executed live (as tests/golden/make_losses_golden.py does for the two stored
+    cases) on random batch sizes, hypothesis counts and image sizes, with the degenerate situations the stored cases only
+    touch once: all-background flow masks, frames whose occlusion map is entirely zero, empty silhouettes."""
+    import textwrap
+    from lasr_b200 import losses
+    with open(os.path.join(REF, "nnutils/mesh_net.py")) as fh:
+        lines = fh.readlines()
+    prep, body = textwrap.dedent("".join(lines[360:363])), textwrap.dedent("".join(lines[371:447]))
+    assert "img_obs = self.imgs" in prep and "# 1) mask loss" in body and "self.total_loss += self.texture_loss" in body
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    g = torch.Generator().manual_seed(3)
+    ri = lambda lo, hi: int(torch.randint(lo, hi, (1,), generator=g))
+    for trial in range(12):
+        bs, H, S = ri(1, 4), ri(1, 4), int([8, 12, 20][ri(0, 3)])
+        n2 = 2 * bs
+        U = lambda *sh: torch.rand(*sh, generator=g)
+        masks = (U(n2, S, S) > 0.45).float()
+        occ = torch.randn(n2, S, S, generator=g)
+        occ[U(n2, S, S) < 0.2] = 0
+        imgs, flow = U(n2, 3, S, S), torch.randn(n2, 3, S, S, generator=g) * 0.05
+        render = U(n2 * H, 4, S, S)
+        flow_rd = torch.randn(n2 * H, S, S, 2, generator=g) * 0.05
+        bgmask = U(n2 * H, S, S) < 0.4
+        if trial % 3 == 0:
+            bgmask[ri(0, n2 * H)] = True                     # a (frame, hypothesis) whose flow mask is empty
+        if trial % 4 == 1:
+            masks[ri(0, n2)] = 0                             # an empty observed silhouette
+        self = types.SimpleNamespace(imgs=imgs, masks=masks, occ=occ, flow=flow, flow_rd=flow_rd, bgmask=bgmask,
+                                     texture_render=render[:, :3], fgmask_tex=render[:, -1], mask_pred=render[:, -1], iters=1,
+                                     ptex_loss=types.SimpleNamespace(forward_pair=lambda a, b: torch.zeros(a.shape[0])))
+        opts = types.SimpleNamespace(n_hypo=H, img_size=S, opt_tex="yes", l1tex_wt=0.7, n_bones=1)
+        ns = dict(self=self, opts=opts, torch=torch, local_batch_size=bs, np=np)
+        exec(prep, ns)
+        exec(body, ns)
+        mp, tex = render[:, 3].reshape(n2, H, S, S), render[:, :3].reshape(n2, H, 3, S, S)
+        l1, s1 = losses.mask_loss(mp, masks, occ)
+        l2, s2, _ = losses.flow_loss(flow_rd.reshape(n2, H, S, S, 2), bgmask.reshape(n2, H, S, S), flow, occ, masks)
+        l3, s3 = losses.texture_l1_loss(tex, mp, imgs, masks, occ, 0.7)
+        what = (trial, bs, H, S)
+        for ours, ref in ((s1, self.mask_loss_sub), (s2, self.flow_rd_loss_sub), (s3, self.texture_loss_sub)):
+            np.testing.assert_allclose(ours.numpy(), ref.detach().numpy(), rtol=3e-5, atol=1e-7, err_msg=str(what))
+        assert abs(float(l1 + l2 + l3) - float(self.total_loss)) < 3e-6, what
