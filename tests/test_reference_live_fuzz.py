@@ -128,6 +128,8 @@ def test_image_losses_follow_the_reference_lines_on_random_inputs(monkeypatch):
             bgmask[ri(0, n2 * H)] = True                     # a (frame, hypothesis) whose flow mask is empty
         if trial % 4 == 1:
             masks[ri(0, n2)] = 0                             # an empty observed silhouette
+        if trial % 5 == 2:
+            occ[ri(0, n2)] = 0                               # no valid pixel at all: the reference's masked mean is NaN
         self = types.SimpleNamespace(imgs=imgs, masks=masks, occ=occ, flow=flow, flow_rd=flow_rd, bgmask=bgmask,
                                      texture_render=render[:, :3], fgmask_tex=render[:, -1], mask_pred=render[:, -1], iters=1,
                                      ptex_loss=types.SimpleNamespace(forward_pair=lambda a, b: torch.zeros(a.shape[0])))
@@ -142,4 +144,6 @@ def test_image_losses_follow_the_reference_lines_on_random_inputs(monkeypatch):
         what = (trial, bs, H, S)
         for ours, ref in ((s1, self.mask_loss_sub), (s2, self.flow_rd_loss_sub), (s3, self.texture_loss_sub)):
             np.testing.assert_allclose(ours.numpy(), ref.detach().numpy(), rtol=3e-5, atol=1e-7, err_msg=str(what))
-        assert abs(float(l1 + l2 + l3) - float(self.total_loss)) < 3e-6, what
+        tot, ref_tot = float(l1 + l2 + l3), float(self.total_loss)
+        assert (np.isnan(tot) and np.isnan(ref_tot)) or abs(tot - ref_tot) < 3e-6, what
+        assert np.isnan(ref_tot) == bool((occ.reshape(n2, -1) == 0).all(1).any()), what
