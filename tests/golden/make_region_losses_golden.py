@@ -43,10 +43,10 @@ def block(lines, first, last, indent):
     return "".join(out)
 
 
-def main():
+def setup():
+    """Load the reference's functions and source lines once; returns the environment run_case needs."""
     import lasr_b200.soft_renderer as sr
     import lasr_b200.soft_renderer.rasterizer as rast
-    from lasr_b200 import synth
     from lasr_b200.geom_utils import quaternion_to_rotation_matrix
     from test_host_glue import _OracleRasterize
 
@@ -72,56 +72,71 @@ def main():
     assert region.count(alias) == 1
     region = region.replace(alias, alias + ".clone()")
     torch.Tensor.cuda = lambda self, *a, **k: self
+    return types.SimpleNamespace(sr=sr, gu=gu, flow_fn=flow_fn, region=region, q2r=quaternion_to_rotation_matrix)
 
+
+def run_case(env, bs, H, B, S, seed):
+    """Execute the reference's region lines for one configuration; returns (inputs, outputs) as dicts of numpy arrays."""
+    from lasr_b200 import synth
+    sr, quaternion_to_rotation_matrix = env.sr, env.q2r
     mk = lambda S: sr.SoftRenderer(image_size=S, sigma_val=1e-4, gamma_val=1e-2, camera_mode="look_at", perspective=False,
                                    aggr_func_rgb="softmax", light_mode="vertex", light_intensity_ambient=1.0,
                                    light_intensity_directionals=0.0)       # nnutils/mesh_net.py:136-145
-    out = {}
     v, f = synth.icosphere(1, 0.4)
     V = len(v)
+    g = torch.Generator().manual_seed(seed)
+    n2, N = 2 * bs, 2 * bs * H
+    q = torch.randn(N * B, 4, generator=g) * 0.1; q[:, 3] = 1
+    quat = quaternion_to_rotation_matrix(q).reshape(N * B, 9)
+    trans = torch.randn(N * B, 2, generator=g) * 0.02
+    depth = torch.randn(N * B, 1, generator=g) * 0.02
+    depth.view(N, B, 1)[:, 0] += 10
+    pred_v = torch.from_numpy(v)[None].repeat(N, 1, 1) + torch.randn(N, V, 3, generator=g) * 0.01
+    tex = torch.sigmoid(torch.randn(N, V, 3, generator=g))
+    faces = torch.from_numpy(f)[None].repeat(n2, 1, 1)
+    ppoint = torch.randn(n2, 2, generator=g) * 0.05
+    scale = 9.5 + torch.rand(n2, H, generator=g)          # [2bs, H]: what the reference's code predictor hands over
+    occ = torch.randn(n2, S, S, generator=g)
+    self = types.SimpleNamespace(
+        renderer_soft=mk(S), renderer_softflf=mk(S), renderer_softflb=mk(S), renderer_softtex=mk(S), optim_idx=0, iters=1,
+        texture_type="vertex", masks=(torch.rand(n2, S, S, generator=g) > 0.4).float(), imgs=torch.rand(n2, 3, S, S, generator=g),
+        flow=torch.randn(n2, 3, S, S, generator=g) * 0.05, occ=occ,
+        ptex_loss=types.SimpleNamespace(forward_pair=lambda a, b: torch.zeros(a.shape[0])))
+    if B > 1:
+        self.ctl_ts = torch.from_numpy(v)[:H * (B - 1)].clone()
+        self.rest_ts = self.ctl_ts + 0.01
+        self.ctl_rs = torch.tensor([[0.0, 0.0, 0.0, 1.0]]).repeat(H * (B - 1), 1)
+        self.log_ctl = 1 + torch.randn(H * (B - 1), 3, generator=g) * 0.3
+    opts = types.SimpleNamespace(n_hypo=H, n_bones=B, sigval=1e-4, opt_tex="yes", img_size=S, l1tex_wt=1.0)
+    ins = dict(quat=quat, trans=trans, depth=depth, pred_v=pred_v, tex=tex, faces=faces, ppoint=ppoint, scale=scale,
+               masks=self.masks, imgs=self.imgs, flow=self.flow, occ=occ)
+    if B > 1:
+        ins.update(ctl_ts=self.ctl_ts, rest_ts=self.rest_ts, ctl_rs=self.ctl_rs, log_ctl=self.log_ctl)
+    ins = {k: t.clone().numpy() for k, t in ins.items()}          # before the lines run: they write into `quat` through a view
+    ns = dict(self=self, opts=opts, torch=torch, np=np, sr=sr, local_batch_size=bs, quat=quat, trans=trans, depth=depth,
+              pred_v=pred_v, tex=tex, faces=faces, ppoint=ppoint, scale=scale, obj_to_cam=env.gu.obj_to_cam,
+              pinhole_cam=env.gu.pinhole_cam, citylabs=[[10 * k, 20, 30] for k in range(64)],
+              kornia=types.SimpleNamespace(quaternion_to_rotation_matrix=quaternion_to_rotation_matrix))
+    exec(env.flow_fn, ns)
+    exec(env.region, ns)
+    outs = {k: np.asarray(getattr(self, k).detach().numpy())
+            for k in ("mask_loss", "flow_rd_loss", "texture_loss", "total_loss", "mask_loss_sub", "flow_rd_loss_sub", "texture_loss_sub")}
+    outs["mask_pred"] = self.mask_pred.detach().numpy()
+    outs["flow_rd"] = self.flow_rd.detach().numpy()
+    return ins, outs
+
+
+def main():
+    env = setup()
+    out = {}
     for case, (bs, H, B, S, seed) in {"b1": (1, 1, 1, 16, 0), "b3": (1, 1, 3, 16, 1), "b3h2": (1, 2, 3, 12, 2)}.items():
-        g = torch.Generator().manual_seed(seed)
-        n2, N = 2 * bs, 2 * bs * H
-        q = torch.randn(N * B, 4, generator=g) * 0.1; q[:, 3] = 1
-        quat = quaternion_to_rotation_matrix(q).reshape(N * B, 9)
-        trans = torch.randn(N * B, 2, generator=g) * 0.02
-        depth = torch.randn(N * B, 1, generator=g) * 0.02
-        depth.view(N, B, 1)[:, 0] += 10
-        pred_v = torch.from_numpy(v)[None].repeat(N, 1, 1) + torch.randn(N, V, 3, generator=g) * 0.01
-        tex = torch.sigmoid(torch.randn(N, V, 3, generator=g))
-        faces = torch.from_numpy(f)[None].repeat(n2, 1, 1)
-        ppoint = torch.randn(n2, 2, generator=g) * 0.05
-        scale = 9.5 + torch.rand(n2, H, generator=g)          # [2bs, H]: what the reference's code predictor hands over
-        occ = torch.randn(n2, S, S, generator=g)
-        self = types.SimpleNamespace(
-            renderer_soft=mk(S), renderer_softflf=mk(S), renderer_softflb=mk(S), renderer_softtex=mk(S), optim_idx=0, iters=1,
-            texture_type="vertex", masks=(torch.rand(n2, S, S, generator=g) > 0.4).float(), imgs=torch.rand(n2, 3, S, S, generator=g),
-            flow=torch.randn(n2, 3, S, S, generator=g) * 0.05, occ=occ,
-            ptex_loss=types.SimpleNamespace(forward_pair=lambda a, b: torch.zeros(a.shape[0])))
-        if B > 1:
-            self.ctl_ts = torch.from_numpy(v)[:H * (B - 1)].clone()
-            self.rest_ts = self.ctl_ts + 0.01
-            self.ctl_rs = torch.tensor([[0.0, 0.0, 0.0, 1.0]]).repeat(H * (B - 1), 1)
-            self.log_ctl = 1 + torch.randn(H * (B - 1), 3, generator=g) * 0.3
-        opts = types.SimpleNamespace(n_hypo=H, n_bones=B, sigval=1e-4, opt_tex="yes", img_size=S, l1tex_wt=1.0)
-        ins = dict(quat=quat, trans=trans, depth=depth, pred_v=pred_v, tex=tex, faces=faces, ppoint=ppoint, scale=scale,
-                   masks=self.masks, imgs=self.imgs, flow=self.flow, occ=occ)
-        if B > 1:
-            ins.update(ctl_ts=self.ctl_ts, rest_ts=self.rest_ts, ctl_rs=self.ctl_rs, log_ctl=self.log_ctl)
-        for k, t in ins.items():                   # before the lines run: they write into `quat` through a view
-            out[f"{case}/in/{k}"] = t.clone().numpy()
+        ins, outs = run_case(env, bs, H, B, S, seed)
+        for k, a in ins.items():
+            out[f"{case}/in/{k}"] = a
         out[f"{case}/meta"] = np.asarray([bs, H, B, S], np.int64)
-        ns = dict(self=self, opts=opts, torch=torch, np=np, sr=sr, local_batch_size=bs, quat=quat, trans=trans, depth=depth,
-                  pred_v=pred_v, tex=tex, faces=faces, ppoint=ppoint, scale=scale, obj_to_cam=gu.obj_to_cam,
-                  pinhole_cam=gu.pinhole_cam, citylabs=[[10 * k, 20, 30] for k in range(64)],
-                  kornia=types.SimpleNamespace(quaternion_to_rotation_matrix=quaternion_to_rotation_matrix))
-        exec(flow_fn, ns)
-        exec(region, ns)
-        for k in ("mask_loss", "flow_rd_loss", "texture_loss", "total_loss", "mask_loss_sub", "flow_rd_loss_sub", "texture_loss_sub"):
-            out[f"{case}/out/{k}"] = np.asarray(getattr(self, k).detach().numpy())
-        out[f"{case}/out/mask_pred"] = self.mask_pred.detach().numpy()
-        out[f"{case}/out/flow_rd"] = self.flow_rd.detach().numpy()
-        print(case, {k: round(float(getattr(self, k)), 6) for k in ("mask_loss", "flow_rd_loss", "texture_loss", "total_loss")})
+        for k, a in outs.items():
+            out[f"{case}/out/{k}"] = a
+        print(case, {k: round(float(outs[k]), 6) for k in ("mask_loss", "flow_rd_loss", "texture_loss", "total_loss")})
     np.savez_compressed(DST, **out)
     print("wrote", DST, os.path.getsize(DST), "bytes")
 

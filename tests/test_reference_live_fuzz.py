@@ -147,3 +147,34 @@ def test_image_losses_follow_the_reference_lines_on_random_inputs(monkeypatch):
         tot, ref_tot = float(l1 + l2 + l3), float(self.total_loss)
         assert (np.isnan(tot) and np.isnan(ref_tot)) or abs(tot - ref_tot) < 3e-6, what
         assert np.isnan(ref_tot) == bool((occ.reshape(n2, -1) == 0).all(1).any()), what
+
+
+@pytest.mark.parametrize("bs,H,B,S,seed", [(2, 1, 1, 12, 10), (2, 2, 3, 10, 11), (3, 1, 2, 10, 12), (2, 1, 4, 12, 13)])
+def test_whole_region_follows_the_reference_lines_for_larger_batches(monkeypatch, bs, H, B, S, seed):
+    """The stored whole-region vectors (region_losses_ref.npz) all have one frame pair per batch.  Here the reference's
+    own LASR.forward lines (nnutils/mesh_net.py:259-447, on top of the drop-in package, oracle as the rasterizer) are
+    executed live for batches of two and three pairs, with and without bones and hypotheses, and RenderHotPath must
+    reproduce their renders and losses."""
+    import importlib.util as iu
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    spec = iu.spec_from_file_location("make_region_losses_golden_live", os.path.join(here, "golden", "make_region_losses_golden.py"))
+    gen = iu.module_from_spec(spec); spec.loader.exec_module(gen)
+    import lasr_b200.soft_renderer.rasterizer as rast
+    from lasr_b200 import hotpath
+    monkeypatch.setattr(torch.Tensor, "cuda", torch.Tensor.cuda)                    # setup() patches these two globally:
+    monkeypatch.setattr(rast.srf, "soft_rasterize", rast.srf.soft_rasterize)        # restored when the test ends
+    monkeypatch.setitem(sys.modules, "soft_renderer", sys.modules.get("soft_renderer", types.ModuleType("soft_renderer")))
+    env = gen.setup()
+    ins, want = gen.run_case(env, bs, H, B, S, seed)
+    I = lambda k: torch.from_numpy(ins[k])
+    bones = {k: I(k) for k in ("ctl_ts", "ctl_rs", "log_ctl", "rest_ts")} if B > 1 else None
+    Rmat = I("quat").view(-1, 3, 3).permute(0, 2, 1).contiguous()                   # mesh_net.py:259
+    Tmat = torch.cat([I("trans"), I("depth")], 1)                                   # :260
+    batch = dict(masks=I("masks"), imgs=I("imgs"), flow=I("flow"), occ=I("occ"))
+    m = hotpath.RenderHotPath(hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B, l1tex_wt=1.0))
+    out = m(I("pred_v"), I("tex"), I("faces"), Rmat, Tmat, I("ppoint"), I("scale"), batch, bones)
+    np.testing.assert_allclose(out["mask_pred"].detach().numpy(), want["mask_pred"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(out["flow_rd"].detach().numpy(), want["flow_rd"], rtol=0, atol=5e-6)
+    for ours, ref in (("mask_loss", "mask_loss"), ("flow_loss", "flow_rd_loss"), ("texture_loss", "texture_loss"), ("total", "total_loss")):
+        assert abs(float(out[ours]) - float(want[ref])) < 2e-6, (ours, float(out[ours]), float(want[ref]))
