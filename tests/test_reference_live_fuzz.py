@@ -178,3 +178,63 @@ def test_whole_region_follows_the_reference_lines_for_larger_batches(monkeypatch
     np.testing.assert_allclose(out["flow_rd"].detach().numpy(), want["flow_rd"], rtol=0, atol=5e-6)
     for ours, ref in (("mask_loss", "mask_loss"), ("flow_loss", "flow_rd_loss"), ("texture_loss", "texture_loss"), ("total", "total_loss")):
         assert abs(float(out[ours]) - float(want[ref])) < 2e-6, (ours, float(out[ours]), float(want[ref]))
+
+
+def test_dataloader_oracle_follows_the_reference_dataset_on_random_videos(tmp_path, monkeypatch):
+    """The reference's own BaseDataset.__getitem__ (dataloader/vidbase.py, imported live) on random synthetic videos --
+    frame sizes that are not multiples of anything, objects of any size anywhere (crops leaving the frame on every
+    side) -- against oracle/dataloader.py on the same decoded inputs: bit for bit at power-of-two img_size, float32
+    rounding at img_size 100 (see the oracle's header)."""
+    cv2 = pytest.importorskip("cv2")
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here))
+    from oracle import dataloader as OD
+    gen = _load(os.path.join(here, "golden", "make_dataloader_golden.py"), "make_dataloader_golden_live")
+    for name in ("absl", "absl.flags", "absl.app", "png"):
+        monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
+    sys.modules["absl"].flags, sys.modules["absl"].app = sys.modules["absl.flags"], sys.modules["absl.app"]
+    monkeypatch.syspath_prepend(os.path.join(REF, "third_party"))
+    monkeypatch.syspath_prepend(REF)
+    for k in [k for k in sys.modules if k == "dataloader" or k.startswith(("dataloader.", "ext_utils"))]:
+        monkeypatch.delitem(sys.modules, k)
+    from ext_utils import image as image_utils
+    monkeypatch.setattr(image_utils, "sample_contour", lambda m: np.zeros((1000, 2)))     # skimage tracer: not on this path
+    from ext_utils.util_flow import readPFM
+    from dataloader import vidbase
+    rng = np.random.RandomState(123)
+    keys = ("img", "imgn", "mask", "flow", "flown", "occ", "occn", "cam", "camn", "pps")
+    checked = 0
+    for trial in range(8):
+        H, W = int(rng.choice([48, 63, 80, 97])), int(rng.choice([64, 91, 128, 150]))
+        S = [32, 64, 100][trial % 3]
+        kw = dict(seed=100 + trial, H=H, W=W, centre=(float(rng.uniform(0, W)), float(rng.uniform(0, H))),
+                  step=(float(rng.uniform(-6, 6)), float(rng.uniform(-4, 4))),
+                  axes=(float(rng.uniform(3, 0.45 * W)), float(rng.uniform(3, 0.45 * H))))
+        d = tmp_path / f"v{trial}"
+        d.mkdir()
+        L = gen.synth_video(str(d), **kw)
+        masks = np.stack([cv2.imread(p, 0) for p in L["mask"]])
+        if not all((m > 0).any() for m in masks):
+            continue                                             # object left the frame: the reference raises on it
+        ds = vidbase.BaseDataset(types.SimpleNamespace(img_size=S))
+        ds.imglist, ds.masklist, ds.flowfwlist, ds.flowbwlist, ds.camlist = L["img"], L["mask"], L["fw"], L["bw"], L["cam"]
+        ds.dframe, ds.can_frame, ds.baselist, ds.directlist, ds.num_imgs = 1, 0, [0, 1, 1, 2], [1, 1, 0, 0], 4
+        gold = {"frames_bgr": np.stack([cv2.imread(p) for p in L["img"]]), "masks": masks,
+                "baselist": np.asarray(ds.baselist), "directlist": np.asarray(ds.directlist)}
+        for dd in ("fw", "bw"):
+            gold[f"flow_{dd}"] = np.stack([np.ascontiguousarray(readPFM(p)[0]) for p in L[dd]])
+            gold[f"occ_{dd}"] = np.stack([np.ascontiguousarray(readPFM(p.replace("flo-", "occ-"))[0]) for p in L[dd]])
+        for it in (0, 1, 3):
+            elem = ds[it]
+            r = OD.preprocess_pair(*OD.pair_inputs(gold, it, ""), S)
+            for k in keys:
+                ref, got = np.asarray(elem[k]), r[k]
+                assert got.shape == ref.shape, (trial, it, k)
+                if S != 100 or k in ("mask", "cam", "camn", "pps"):
+                    tol = 1e-12 if k in ("img", "imgn") else 0.0
+                    assert np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() <= tol, (trial, (H, W, S), it, k)
+                else:
+                    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=5e-6 * max(1.0, float(np.abs(ref).max())),
+                                               err_msg=str((trial, it, k)))
+            checked += 1
+    assert checked >= 15
