@@ -238,3 +238,96 @@ def test_dataloader_oracle_follows_the_reference_dataset_on_random_videos(tmp_pa
                                                err_msg=str((trial, it, k)))
             checked += 1
     assert checked >= 15
+
+
+def test_module_layer_follows_the_reference_classes_on_random_configurations(monkeypatch):
+    """Forty random SoftRenderer configurations -- camera (perspective / orthographic, viewing angle and scale, eyes as
+    lists, numpy arrays, per-frame tensors, from angles), lighting (mode, intensities, colours, direction), rasterizer
+    scalars and modes, anti-aliasing, fill_back, texture type and resolution, default textures -- through the
+    reference's own classes (loaded live, recording rasterizer) and through the mirror: same face vertices, face
+    textures, scalars and pooled output.  tests/golden/modules_ref.npz stores eight fixed ones."""
+    import warnings
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here))
+    gen = _load(os.path.join(here, "golden", "make_modules_golden.py"), "make_modules_golden_live")
+    import lasr_b200.soft_renderer as ours_sr
+    import lasr_b200.soft_renderer.rasterizer as rast
+    from lasr_b200 import synth
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(rast.srf, "soft_rasterize", rast.srf.soft_rasterize)            # restored at teardown
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "soft_renderer" or k.startswith("soft_renderer.")}
+    try:
+        srf = types.ModuleType("soft_renderer.functional")
+        fdir = os.path.join(gen.SR, "functional")
+        for fn in ("look_at", "look", "perspective", "orthogonal", "face_vertices", "vertex_normals", "ambient_lighting",
+                   "directional_lighting", "get_points_from_angles"):
+            setattr(srf, fn, getattr(gen.load(os.path.join(fdir, fn + ".py"), "ref_fn_live_" + fn), fn))
+        sr = types.ModuleType("soft_renderer")
+        sr.functional = srf
+        sys.modules["soft_renderer"], sys.modules["soft_renderer.functional"] = sr, srf
+        for mod, names in (("mesh", ("Mesh",)), ("lighting", ("AmbientLighting", "DirectionalLighting", "Lighting")),
+                           ("transform", ("Projection", "LookAt", "Look", "Transform")), ("rasterizer", ("SoftRasterizer",)),
+                           ("renderer", ("SoftRenderer",))):
+            m = gen.load(os.path.join(gen.SR, mod + ".py"), "soft_renderer." + mod)
+            for n in names:
+                setattr(sr, n, getattr(m, n))
+        rng = np.random.RandomState(0)
+        v, f = synth.icosphere(1, 0.6)
+        U = lambda n: [float(x) for x in rng.rand(n)]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for trial in range(40):
+                N = int(rng.choice([1, 2, 4, 5]))                 # not 3: the reference's dim-less torch.cross
+                g = torch.Generator().manual_seed(trial)
+                ttype, tres = str(rng.choice(["surface", "vertex"])), int(rng.choice([1, 2, 3]))
+                kw = dict(image_size=int(rng.choice([4, 8])), camera_mode="look_at", perspective=bool(rng.rand() < 0.5),
+                          viewing_angle=float(rng.uniform(15, 60)), viewing_scale=float(rng.uniform(0.5, 2)),
+                          light_mode=str(rng.choice(["surface", "vertex"])), light_intensity_ambient=float(rng.uniform(0, 1)),
+                          light_color_ambient=U(3), light_intensity_directionals=float(rng.uniform(0, 1)),
+                          light_color_directionals=U(3), light_directions=[float(x) for x in rng.randn(3)],
+                          anti_aliasing=bool(rng.rand() < 0.3), fill_back=bool(rng.rand() < 0.5), background_color=U(3),
+                          near=float(rng.uniform(0.1, 2)), far=float(rng.uniform(20, 100)),
+                          sigma_val=float(10 ** rng.uniform(-6, -3)), gamma_val=float(10 ** rng.uniform(-4, -1)),
+                          dist_func=str(rng.choice(["hard", "euclidean", "barycentric"])),
+                          aggr_func_rgb=str(rng.choice(["hard", "softmax"])), aggr_func_alpha=str(rng.choice(["hard", "prod", "sum"])))
+                eye_kind = str(rng.choice(["none", "list", "np", "tensorN", "angles_f", "angles_t"]))
+                if eye_kind == "list":
+                    kw["eye"] = [float(x) for x in rng.randn(3) + [0, 0, -3]]
+                verts = torch.from_numpy(v)[None].repeat(N, 1, 1) + torch.randn(N, len(v), 3, generator=g) * 0.03
+                faces = torch.from_numpy(f)[None].repeat(N, 1, 1)
+                tex = None
+                if rng.rand() < 0.8:
+                    tex = torch.rand(N, len(f), tres ** 2, 3, generator=g) if ttype == "surface" else torch.rand(N, len(v), 3, generator=g)
+                recs = []
+                for pkg, target in ((sr, srf), (ours_sr, rast.srf)):
+                    rec = {}
+
+                    def soft_rasterize(face_vertices, textures_, *args, _rec=rec):
+                        _rec["fv"], _rec["ft"], _rec["args"] = face_vertices.clone(), textures_.clone(), args
+                        S = args[0]
+                        n = face_vertices.shape[0]
+                        return torch.arange(n * 4 * S * S, dtype=torch.float32).reshape(n, 4, S, S) / 100
+                    target.soft_rasterize = soft_rasterize
+                    r = pkg.SoftRenderer(**kw)
+                    if eye_kind == "np":
+                        r.transform.set_eyes(np.asarray([0.2, -0.1, -2.5], np.float32))
+                    elif eye_kind == "tensorN":
+                        r.transform.set_eyes(torch.tensor([[0.2, -0.1, -2.5]]).repeat(N, 1) + torch.arange(N)[:, None] * 0.1)
+                    elif eye_kind == "angles_f":
+                        r.transform.set_eyes_from_angles(2.5, 15.0, 70.0)
+                    elif eye_kind == "angles_t":
+                        r.transform.set_eyes_from_angles(torch.full((N,), 2.5), torch.linspace(-20, 20, N), torch.linspace(0, 300, N))
+                    mesh = pkg.Mesh(verts.clone(), faces.clone(), textures=None if tex is None else tex.clone(),
+                                    texture_res=tres, texture_type=ttype)
+                    rec["img"] = r.render_mesh(mesh)
+                    recs.append(rec)
+                a, b = recs
+                what = (trial, eye_kind, N, ttype, kw["light_mode"])
+                assert torch.allclose(a["fv"], b["fv"], atol=1e-5), what
+                assert torch.allclose(a["ft"], b["ft"], atol=1e-6), what
+                assert torch.equal(a["img"], b["img"]) and len(a["args"]) == len(b["args"]) == 13, what
+                assert all(x == y for x, y in zip(a["args"], b["args"])), what
+    finally:
+        for k in [k for k in sys.modules if k == "soft_renderer" or k.startswith("soft_renderer.")]:
+            del sys.modules[k]
+        sys.modules.update({k: m for k, m in saved.items() if m is not None})
