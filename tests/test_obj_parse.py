@@ -143,3 +143,41 @@ def test_writer_produces_the_reference_writers_bytes(tmp_path, monkeypatch):
         ra, rb = open(a).read(), open(b).read()
         assert ra.replace(os.path.basename(a), "X") == rb.replace(os.path.basename(b), "X"), tag
         assert ra.count("\nv ") == 11 and ra.count("\nf ") == 17
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not present (GPU box)")
+def test_random_obj_files_parse_like_the_reference_loader(tmp_path, monkeypatch):
+    """Forty random OBJ files -- polygons of 3 to 6 corners in the four face-token styles (v, v/vt, v//vn, v/vt/vn),
+    optional per-vertex colours, blank lines, comments, doubled separators -- through the reference's own load_obj
+    (live) and through obj_io: vertices, fan-triangulated faces, per-vertex colours and the normalised variant."""
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    ref = _reference_loader([])
+    rng = np.random.RandomState(0)
+    for trial in range(40):
+        nv, nt = rng.randint(4, 12), rng.randint(3, 8)
+        coloured = rng.rand() < 0.4
+        lines = ["# fuzz", ""]
+        for _ in range(nv):
+            lines.append("v %.4f %.4f %.4f" % tuple(rng.randn(3)) + (" %.3f %.3f %.3f" % tuple(rng.rand(3)) if coloured else ""))
+            if rng.rand() < 0.2:
+                lines.append("")
+            if rng.rand() < 0.1:
+                lines.append("# comment")
+        lines += ["vt %.3f %.3f" % tuple(rng.rand(2) * 1.5) for _ in range(nt)] + ["vn 0 0 1"] * 3
+        style = str(rng.choice(["v", "v/vt", "v//vn", "v/vt/vn"]))
+        for _ in range(rng.randint(2, 7)):
+            idx = rng.choice(nv, min(rng.randint(3, 7), nv), replace=False) + 1
+            tok = {"v": lambda j: str(j), "v/vt": lambda j: f"{j}/{rng.randint(1, nt + 1)}", "v//vn": lambda j: f"{j}//1",
+                   "v/vt/vn": lambda j: f"{j}/{rng.randint(1, nt + 1)}/2"}[style]
+            sep = "  " if rng.rand() < 0.3 else " "
+            lines.append("f" + sep + sep.join(tok(j) for j in idx))
+        p = str(tmp_path / f"m{trial}.obj")
+        with open(p, "w") as fh:
+            fh.write("\n".join(lines) + "\n")
+        rv, rf = ref.load_obj(p)
+        v, _, f, _ = obj_io.parse_obj(p)
+        assert np.array_equal(v, rv.numpy()) and np.array_equal(f, rf.numpy()), (trial, style)
+        if coloured:
+            assert torch.equal(obj_io.load_obj(p, load_texture=True, texture_type="vertex")[2],
+                               ref.load_obj(p, load_texture=True, texture_type="vertex")[2]), trial
+        assert torch.allclose(obj_io.load_obj(p, normalization=True)[0], ref.load_obj(p, normalization=True)[0], atol=1e-6), trial
