@@ -8,12 +8,14 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 
 import torch
 
 from . import _build
 
 _lib = None
+_lib_lock = threading.Lock()      # lib() may be reached first from a DataLoader / stager thread
 
 _c = ctypes
 _RASTER_SCALARS = [_c.c_int, _c.c_int, _c.c_int, _c.c_int,      # N, F, S, T
@@ -27,6 +29,14 @@ class NativeLibraryMissing(RuntimeError):
 
 
 def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        return _load_locked()
+
+
+def _load_locked():
     global _lib
     if _lib is None:
         path = _build.LIB_PATH
