@@ -70,6 +70,18 @@ int lasr_b200_raster_forward(const float* faces, const float* textures, float* a
                              int func_id_rgb, int func_id_alpha, int texture_sample_type,
                              int double_side, void* stream);
 
+/* The same call with the background colour as an argument: `background_host` is a HOST array of 3 floats and
+ * `soft_colors` is output only -- no pre-fill pass over the image by the caller (the three fills of
+ * soft_rasterize.py:50-53: 12 S^2 bytes per frame written and read back) and no read of it here.  When the
+ * hard z-buffer ('hard' rgb) leaves a pixel uncovered it writes the background itself. */
+int lasr_b200_raster_forward_bg(const float* faces, const float* textures, float* aggrs_info,
+                                float* soft_colors, void* workspace, size_t workspace_bytes,
+                                int batch_size, int num_faces, int image_size, int texture_size,
+                                float near_, float far_, const float* near_far_dev, float eps,
+                                float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
+                                int func_id_rgb, int func_id_alpha, int texture_sample_type,
+                                int double_side, const float* background_host, void* stream);
+
 /* backward_soft_rasterize(faces, textures, soft_colors, faces_info, aggrs_info, grad_faces,
  *                         grad_textures, grad_soft_colors, <same scalars>)
  *   grad_faces    [N,F,9]    out (overwritten; the reference accumulates into a zeroed buffer)

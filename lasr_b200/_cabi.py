@@ -24,6 +24,9 @@ _RASTER_SCALARS = [_c.c_int, _c.c_int, _c.c_int, _c.c_int,      # N, F, S, T
                    _c.c_int, _c.c_int, _c.c_int, _c.c_int]       # rgb, alpha, sample, double_side
 
 
+EXPECTED_ABI = 5     # include/lasr_b200.h; bumped whenever an entry point's argument list changes
+
+
 class NativeLibraryMissing(RuntimeError):
     pass
 
@@ -46,12 +49,21 @@ def _load_locked():
                 "(lasr_b200 has no CPU/eager fallback for its CUDA kernels)")
         L = ctypes.CDLL(path)
         L.lasr_b200_abi_version.restype = _c.c_int
+        if L.lasr_b200_abi_version() != EXPECTED_ABI:
+            # *.so files are build products (LASR_B200_LIB may point anywhere): a stale library with the same symbols
+            # and an older argument list would be called with shifted arguments
+            raise NativeLibraryMissing(
+                f"{path} has ABI version {L.lasr_b200_abi_version()}, these bindings are written for {EXPECTED_ABI}: "
+                "rebuild it with `python -m lasr_b200._build`")
         L.lasr_b200_last_error.restype = _c.c_char_p
         L.lasr_b200_launch_count.restype = _c.c_uint64
         L.lasr_b200_raster_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_raster_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_raster_forward.restype = _c.c_int
         L.lasr_b200_raster_forward.argtypes = [_c.c_void_p] * 5 + [_c.c_size_t] + _RASTER_SCALARS + [_c.c_void_p]
+        L.lasr_b200_raster_forward_bg.restype = _c.c_int
+        L.lasr_b200_raster_forward_bg.argtypes = ([_c.c_void_p] * 5 + [_c.c_size_t] + _RASTER_SCALARS
+                                                  + [_c.POINTER(_c.c_float), _c.c_void_p])
         L.lasr_b200_raster_backward.restype = _c.c_int
         L.lasr_b200_raster_backward.argtypes = [_c.c_void_p] * 8 + [_c.c_size_t] + _RASTER_SCALARS + [_c.c_int, _c.c_void_p]
         L.lasr_b200_render_workspace_bytes.restype = _c.c_size_t
@@ -123,7 +135,8 @@ def _load_locked():
 
 EXPORTED_SYMBOLS = [
     "lasr_b200_abi_version", "lasr_b200_last_error", "lasr_b200_launch_count",
-    "lasr_b200_raster_workspace_bytes", "lasr_b200_raster_forward", "lasr_b200_raster_backward",
+    "lasr_b200_raster_workspace_bytes", "lasr_b200_raster_forward", "lasr_b200_raster_forward_bg",
+    "lasr_b200_raster_backward",
     "lasr_b200_render_workspace_bytes", "lasr_b200_render_forward", "lasr_b200_render_backward",
     "lasr_b200_losses_workspace_bytes", "lasr_b200_losses_forward", "lasr_b200_losses_backward",
     "lasr_b200_losses_finalize", "lasr_b200_losses_coefficients",
@@ -174,18 +187,24 @@ def raster_workspace(N: int, F: int, S: int, device) -> torch.Tensor:
 
 def raster_forward(faces, textures, aggrs_info, soft_colors, workspace, image_size, near, far, near_far_dev, eps,
                    sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, texture_sample_type,
-                   double_side):
+                   double_side, background=None):
+    """background=None: the reference's contract, soft_colors arrives pre-filled with the background colour
+    (lasr_b200_raster_forward).  background=[r, g, b]: soft_colors is output only (lasr_b200_raster_forward_bg)."""
     for t, nm in ((faces, "faces"), (textures, "textures"), (aggrs_info, "aggrs_info"), (soft_colors, "soft_colors")):
         _require_cuda_f32(t, nm)
     N, F = faces.shape[:2]
     T = textures.shape[2]
-    with torch.cuda.device(faces.device):
-        rc = lib().lasr_b200_raster_forward(
-            faces.data_ptr(), textures.data_ptr(), aggrs_info.data_ptr(), soft_colors.data_ptr(),
+    args = (faces.data_ptr(), textures.data_ptr(), aggrs_info.data_ptr(), soft_colors.data_ptr(),
             workspace.data_ptr(), workspace.numel(), N, F, int(image_size), T, float(near), float(far),
             near_far_dev.data_ptr() if near_far_dev is not None else None, float(eps), float(sigma_val),
             int(func_id_dist), float(dist_eps), float(gamma_val), int(func_id_rgb), int(func_id_alpha),
-            int(texture_sample_type), int(bool(double_side)), _stream_ptr())
+            int(texture_sample_type), int(bool(double_side)))
+    with torch.cuda.device(faces.device):
+        if background is None:
+            rc = lib().lasr_b200_raster_forward(*args, _stream_ptr())
+        else:
+            bg = (_c.c_float * 3)(*[float(x) for x in background])
+            rc = lib().lasr_b200_raster_forward_bg(*args, bg, _stream_ptr())
     _check(rc, "lasr_b200_raster_forward")
 
 

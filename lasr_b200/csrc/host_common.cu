@@ -29,7 +29,7 @@ int lasr_check_launch(const char* what) {
 
 }  // namespace lasr
 
-extern "C" int lasr_b200_abi_version(void) { return 4; }   // 4: + chamfer, texture atlas, staging entry points
+extern "C" int lasr_b200_abi_version(void) { return 5; }   // 5: + lasr_b200_raster_forward_bg (4: + chamfer, texture atlas, staging)
 
 extern "C" const char* lasr_b200_last_error(void) {
   static thread_local std::string copy;

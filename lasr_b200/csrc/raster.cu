@@ -77,8 +77,8 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #ifndef LASR_FTZ_MUFU_BWD           // ... but not in the backward (measured slower)
 #define LASR_FTZ_MUFU_BWD 0
 #endif
-#ifndef LASR_BWD_SPANS              // EXPERIMENTAL (unmeasured): sweep row spans of the dilated triangle in the backward
-#define LASR_BWD_SPANS 0
+#ifndef LASR_EXP_PLANES_L1
+#define LASR_EXP_PLANES_L1 0
 #endif
 #ifndef LASR_BWD_INDEX32_MULTI      // ... and in the multi-set backward
 #define LASR_BWD_INDEX32_MULTI 0
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
     else if (alpha_f == 1) out[(P - 1) * SS] = st.alpha / A.F;
     else out[(P - 1) * SS] = 1.f - st.alpha;
     if (rgb_f == 0) {
-      if (st.face_min != -1) {
+      if (st.face_min != -1 || A.bg_in_args) {   // uncovered pixels keep the caller's pre-fill, or get the background argument
 #pragma unroll
         for (int k = 0; k < 3; ++k) out[k * SS] = st.col[k];
       }
@@ -421,9 +421,6 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
   constexpr int KL = K - KF;            // live colour sets
   constexpr int NV = 9 + 9 * KL;        // gradient values per face: 9 position + 9 per live colour set
   __shared__ float s_part[8][NV];
-#if LASR_BWD_SPANS
-  __shared__ int s_pre[8][32], s_x0[8][32];   // per warp: span pixels before each row of the window, first x of each row
-#endif
   const int lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   const int S = A.S;
@@ -496,52 +493,13 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
     typedef typename PlaneIndex<kIdx32>::type index_t;
     const index_t SSx = (index_t)S * (index_t)S;
     if (kIdx32) asm volatile("" : "+l"(sc), "+l"(ag), "+l"(gs));
+#if LASR_EXP_PLANES_L1   // TIMING-ONLY bound experiment (wrong gradients): every plane load hits one L1-resident line
+#define PLANE(k) ((index_t)(k) * 32u + (index_t)lane)
+#else
 #define PLANE(k) ((index_t)(k) * SSx + pn)
-    int sweep_total = total;
-#if LASR_BWD_SPANS
-    // EXPERIMENTAL, off by default, not yet measured on a GPU: sweep the row spans of the
-    // dilated triangle instead of the whole dilated box.  Lane l builds the span of window row l; an inclusive warp
-    // scan of the span lengths gives every row's first sweep index; each 32-pixel step then locates its pixels with
-    // span_locate.  The geometry (span_radius / row_span / span_window / span_locate) is validated on the host
-    // (tests/test_kernel_math_host.py): a superset of what the exact tests below accept.
-    bool use_spans = false;
-    const int swarp = (threadIdx.x >> 5) & 7;
-    if (!kBig && kFast && yhi - ylo < 32) {
-      const float R = span_radius(g, sthr);
-      if (R >= 0.f) {                                  // warp-uniform: g is the warp's face
-        int xa = 1, xb = 0;
-        if (lane <= yhi - ylo) {
-          float lo, hi;
-          if (row_span(g, A.coords[yhi - lane], R, lo, hi)) {
-            int a, b;
-            span_window(lo, hi, S, a, b);
-            xa = max(a, xlo); xb = min(b, xhi);
-          }
-        }
-        const int len = max(xb - xa + 1, 0);
-        int incl = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += v;
-        }
-        s_pre[swarp][lane] = incl - len;
-        s_x0[swarp][lane] = xa;
-        sweep_total = __shfl_sync(0xffffffffu, incl, 31);
-        __syncwarp();
-        use_spans = true;
-      }
-    }
 #endif
-    for (int idx = gtid; idx < sweep_total; idx += gsize) {
+    for (int idx = gtid; idx < total; idx += gsize) {
       int xi, yi;
-#if LASR_BWD_SPANS
-      if (use_spans) {
-        const int r = span_locate(s_pre[swarp], idx);
-        xi = s_x0[swarp][r] + idx - s_pre[swarp][r];
-        yi = yhi - r;
-      } else
-#endif
       {
         int r = (int)(((float)idx + 0.5f) * inv_wdt);  // idx / wdt without an integer divide
         int col = idx - r * wdt;
@@ -790,18 +748,21 @@ using namespace lasr;
 
 extern "C" size_t lasr_b200_raster_workspace_bytes(int N, int F, int S) { return raster_ws_bytes(N, F, S, 1); }
 
-extern "C" int lasr_b200_raster_forward(const float* faces, const float* textures, float* aggrs_info,
-                                        float* soft_colors, void* workspace, size_t workspace_bytes, int N, int F,
-                                        int S, int T, float near_, float far_, const float* near_far_dev, float eps,
-                                        float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
-                                        int func_id_rgb, int func_id_alpha, int texture_sample_type, int double_side,
-                                        void* stream) {
+static int raster_forward_impl(const float* faces, const float* textures, float* aggrs_info, float* soft_colors,
+                               void* workspace, size_t workspace_bytes, int N, int F, int S, int T, float near_, float far_,
+                               const float* near_far_dev, float eps, float sigma_val, int func_id_dist, float dist_eps,
+                               float gamma_val, int func_id_rgb, int func_id_alpha, int texture_sample_type,
+                               int double_side, const float* background_host, void* stream) {
   RasterArgs A{};
   if (fill_args(A, N, F, S, T, near_, far_, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
                 func_id_rgb, func_id_alpha, texture_sample_type, double_side, workspace, workspace_bytes))
     return 1;
   if (!faces || !textures || !aggrs_info || !soft_colors) return fail("raster_forward: null tensor pointer");
   A.faces = faces; A.textures = textures; A.aggrs_info = aggrs_info; A.soft_colors = soft_colors;
+  if (background_host) {   // no pre-fill pass over the image and no read of it in the forward
+    A.bg_in_args = 1;
+    for (int k = 0; k < 3; ++k) A.bg[k] = background_host[k];
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const long long nf = (long long)N * F;
   const long long nthreads = nf > S ? nf : S;
@@ -811,6 +772,29 @@ extern "C" int lasr_b200_raster_forward(const float* faces, const float* texture
   raster_setup_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(A, 1);
   if (check_launch("raster_setup_kernel")) return 1;
   return launch_forward(A, st);
+}
+
+extern "C" int lasr_b200_raster_forward(const float* faces, const float* textures, float* aggrs_info,
+                                        float* soft_colors, void* workspace, size_t workspace_bytes, int N, int F,
+                                        int S, int T, float near_, float far_, const float* near_far_dev, float eps,
+                                        float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
+                                        int func_id_rgb, int func_id_alpha, int texture_sample_type, int double_side,
+                                        void* stream) {
+  return raster_forward_impl(faces, textures, aggrs_info, soft_colors, workspace, workspace_bytes, N, F, S, T, near_, far_,
+                             near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha,
+                             texture_sample_type, double_side, nullptr, stream);
+}
+
+extern "C" int lasr_b200_raster_forward_bg(const float* faces, const float* textures, float* aggrs_info,
+                                           float* soft_colors, void* workspace, size_t workspace_bytes, int N, int F,
+                                           int S, int T, float near_, float far_, const float* near_far_dev, float eps,
+                                           float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
+                                           int func_id_rgb, int func_id_alpha, int texture_sample_type, int double_side,
+                                           const float* background_host, void* stream) {
+  if (!background_host) return fail("raster_forward_bg: null background");
+  return raster_forward_impl(faces, textures, aggrs_info, soft_colors, workspace, workspace_bytes, N, F, S, T, near_, far_,
+                             near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha,
+                             texture_sample_type, double_side, background_host, stream);
 }
 
 extern "C" int lasr_b200_raster_backward(const float* faces, const float* textures, const float* soft_colors,

@@ -178,19 +178,6 @@ __device__ __forceinline__ float pixel_coord(int i, int S) {
   return (float)((2.0 * (double)i + 1.0 - (double)S) / (double)S);
 }
 
-// EXPERIMENTAL, off by default, not yet run on a GPU (profiles/round1g_instruction_budget.md): a lane fetches the row of
-// `a` and the reciprocal of the edge it selected with four 32-bit loads from the face's record (L1-resident, at most three
-// distinct addresses per warp) instead of the three divergent arms of register moves the compiler builds for
-// "pick edge e's constants" -- 10-15 % of a pair evaluation at a quarter of the lanes.  Same values, same bits.
-#ifndef LASR_EDGE_LOAD
-#define LASR_EDGE_LOAD 0
-#endif
-#ifdef __CUDA_ARCH__
-#define LASR_ASSUME(x) __builtin_assume(x)
-#else
-#define LASR_ASSUME(x) ((void)0)
-#endif
-
 // ---- per-face derived quantities (.cu:245-305 + the border box of :32-38) -------------------
 struct FaceGeom {
   float inv[9];       // inverse of [[x0 x1 x2],[y0 y1 y2],[1 1 1]] (rows give barycentrics)
@@ -203,9 +190,6 @@ struct FaceGeom {
   float kappa;        // edge-prediction trust threshold (see euclid_distance): (s_mid - s_lo)^2 > kappa * s_mid
   int obt;            // index of the (first) obtuse corner, -1 if none
   bool front;
-#if LASR_EDGE_LOAD
-  const float* rec;   // the face's record in memory when the geometry was loaded from one (else nullptr)
-#endif
 };
 
 __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float sthr, FaceGeom& g) {
@@ -260,9 +244,6 @@ __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float s
     const float ke = 2.f * LASR_NOISE_K * eta / det;
     g.kappa = ke * ke;   // inf / NaN for degenerate faces: the prediction is then never trusted
   }
-#if LASR_EDGE_LOAD
-  g.rec = nullptr;
-#endif
   g.hix = __fadd_rn(max3(x0, x1, x2), sthr);
   g.lox = __fsub_rn(min3(x0, x1, x2), sthr);
   g.hiy = __fadd_rn(max3(y0, y1, y2), sthr);
@@ -319,9 +300,6 @@ __device__ __forceinline__ void load_record(const float* __restrict__ r, FaceGeo
     g.z[k] = K == 1 ? v[41 + k] : 0.f;
   }
   g.kappa = v[31];
-#if LASR_EDGE_LOAD
-  g.rec = r;
-#endif
   const int fl = __float_as_int(v[15]);
   g.obt = (fl & 3) - 1;
   g.front = (fl & 4) != 0;
@@ -333,16 +311,32 @@ __device__ __forceinline__ void load_record(const float* __restrict__ r, FaceGeo
   for (int k = 0; k < 9 * K; ++k) tex9[k] = v[32 + k];
 }
 
-// Conservative inclusive pixel-index window of coordinates in [lo, hi] (the exact predicate is
-// still applied per pixel; this only has to be a superset).  Empty windows come back lo > hi.
+// Inclusive pixel-index window of the pixel centres inside [lo, hi] (centre i sits at (2i + 1 - S) / S, so coordinate c
+// has index (c*S + S - 1) / 2).  The exact predicate is still applied per pixel; this only has to be a superset, and it
+// is a tight one: the bounds are widened by 1/64 pixel, which covers the float rounding of this conversion and of the
+// coordinate table for every S <= 8192 (<= 1e-3 pixel; tests/test_kernel_math_host.py sweeps it).  Round 1 rounded
+// outwards by a whole pixel on both sides -- a 12.8-pixel box became a ~14.8-pixel window, and a quarter of the
+// backward's sweep slots and of the forward's tile-list entries fell outside the box (LASR_LOOSE_WINDOWS=1 restores it).
+// Empty windows come back lo > hi.  Boxes reaching beyond the screen -- including +-inf and the huge coordinates a
+// pinhole projection produces for z ~ 0 -- are clamped to it, as the reference's per-pixel test would accept them; only
+// NaN bounds are culled (the reference's behaviour for NaN vertices is undefined: out-of-bounds stack writes in
+// euclidean_p2f_distance when every comparison is false).
+#ifndef LASR_LOOSE_WINDOWS
+#define LASR_LOOSE_WINDOWS 0
+#endif
 __device__ __forceinline__ void coord_window(float lo, float hi, int S, int& ilo, int& ihi) {
-  const float a = (lo * (float)S + (float)(S - 1)) * 0.5f;
-  const float b = (hi * (float)S + (float)(S - 1)) * 0.5f;
-  // NaN / inf vertices: the reference's behaviour is undefined (out-of-bounds stack writes in
-  // euclidean_p2f_distance when every comparison is false); we cull such faces.
-  if (!(a >= -1e9f && b <= 1e9f && a <= b + 1.f)) { ilo = 1; ihi = 0; return; }
+  float a = (lo * (float)S + (float)(S - 1)) * 0.5f;
+  float b = (hi * (float)S + (float)(S - 1)) * 0.5f;
+  if (!(a <= b + 1.f)) { ilo = 1; ihi = 0; return; }          // NaN (or inverted) bounds
+  a = fminf(fmaxf(a, -2.f), (float)S + 1.f);                   // beyond the screen: clamp before the int conversion
+  b = fminf(fmaxf(b, -2.f), (float)S + 1.f);
+#if LASR_LOOSE_WINDOWS
   ilo = max(0, (int)floorf(a - 0.0625f));
   ihi = min(S - 1, (int)ceilf(b + 0.0625f));
+#else
+  ilo = max(0, (int)ceilf(a - 0.015625f));
+  ihi = min(S - 1, (int)floorf(b + 0.015625f));
+#endif
 }
 
 // ---- the soft fragment of one (pixel, face) pair --------------------------------------------
@@ -428,30 +422,12 @@ __device__ __forceinline__ void euclid_distance(const FaceGeom& g, float xp, flo
     }
   }
   // pick the row of `a` for edge e without dynamic register indexing
-#if LASR_EDGE_LOAD
-  float a0, a1, a2, rd, ae, ab;
-  if (kFast != 0 && g.rec != nullptr) {       // record words 19+e (rden) and 22+3e.. (row e of a), see store_record
-    const float* row = g.rec + 22 + 3 * e;
-    a0 = __ldg(row); a1 = __ldg(row + 1); a2 = __ldg(row + 2);
-    rd = __ldg(g.rec + 19 + e);
-    ae = __ldg(g.rec + 22 + 4 * e);                                  // a[e][e]
-    ab = __ldg(g.rec + (e == 0 ? 23 : (e == 1 ? 27 : 28)));          // a[e][(e+1)%3]
-  } else {
-    a0 = e == 0 ? g.a[0][0] : (e == 1 ? g.a[1][0] : g.a[2][0]);
-    a1 = e == 0 ? g.a[0][1] : (e == 1 ? g.a[1][1] : g.a[2][1]);
-    a2 = e == 0 ? g.a[0][2] : (e == 1 ? g.a[1][2] : g.a[2][2]);
-    rd = e == 0 ? g.rden[0] : (e == 1 ? g.rden[1] : g.rden[2]);
-    ae = e == 0 ? a0 : (e == 1 ? a1 : a2);
-    ab = e == 0 ? a1 : (e == 1 ? a2 : a0);
-  }
-#else
   const float a0 = e == 0 ? g.a[0][0] : (e == 1 ? g.a[1][0] : g.a[2][0]);
   const float a1 = e == 0 ? g.a[0][1] : (e == 1 ? g.a[1][1] : g.a[2][1]);
   const float a2 = e == 0 ? g.a[0][2] : (e == 1 ? g.a[1][2] : g.a[2][2]);
   const float ae = e == 0 ? a0 : (e == 1 ? a1 : a2);
   const float ab = e == 0 ? a1 : (e == 1 ? a2 : a0);
   const float rd = e == 0 ? g.rden[0] : (e == 1 ? g.rden[1] : g.rden[2]);
-#endif
   const float num = __fsub_rn(dot3(w0, a0, w1, a1, w2, a2), ab);
   const float den = __fsub_rn(ae, ab);
   const float q = kFast ? div_by_rcp(num, den, rd) : __fdiv_rn(num, den);
@@ -552,9 +528,6 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConst
   FaceGeom g;
   float tex9[9 * K];
   load_record<K>(rec, g, tex9);
-#if LASR_EDGE_LOAD
-  LASR_ASSUME(g.rec != nullptr);
-#endif
   Fragment fr;
   if (!soft_fragment<kMode>(A, g, xp, yp, C.thr, fr)) return;
   const int alpha_f = kFast ? 2 : A.alpha;
@@ -597,78 +570,6 @@ __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConst
 #pragma unroll
     for (int k = 0; k < 3 * K; ++k) st.col[k] = rescale * st.col[k] + ez * sample_tex(k);
   }
-}
-
-// ---- row spans of the dilated triangle (backward, LASR_BWD_SPANS; not enabled by default) -----------------
-// A pair can only be accepted if the pixel is inside the face or closer than sqrt(threshold) to it, i.e. inside the
-// triangle dilated by a disc -- a convex set whose intersection with a pixel row is ONE interval, ~30 % smaller in
-// total than the dilated bounding box the backward sweeps (profiles/analysis_backward_sweeps.py).  Everything here
-// only has to be a SUPERSET of what the exact per-pixel tests accept: the tests themselves stay in the loop.
-//
-// Rounding-noise amplitude (NDC) of the distances the reference's float pipeline computes for this face (the same
-// estimate face_setup turns into kappa): the dilation radius is widened by a few of these, and faces whose noise is
-// not small against the radius -- slivers, degenerate faces, whose "inside" set is noise -- keep the full window.
-__device__ __forceinline__ float face_noise_eta(const FaceGeom& g) {
-  float m = 0.f;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) m = fmaxf(m, fabsf(g.inv[3 * k]) + fabsf(g.inv[3 * k + 1]) + fabsf(g.inv[3 * k + 2]));
-  const float xm = fmaxf(1.f, fmaxf(max3(fabsf(g.x[0]), fabsf(g.x[1]), fabsf(g.x[2])),
-                                    max3(fabsf(g.y[0]), fabsf(g.y[1]), fabsf(g.y[2]))));
-  const float emin2 = min3(g.a[0][0] - g.a[0][1], g.a[1][1] - g.a[1][2], g.a[2][2] - g.a[2][0]);
-  return 5.96e-8f * (LASR_NOISE_C1 * m * xm + LASR_NOISE_C2 * xm * xm * rsqrtf(fmaxf(emin2, 1e-30f)));
-}
-
-#ifndef LASR_SPAN_MAX_NOISE
-#define LASR_SPAN_MAX_NOISE 0.05f
-#endif
-// Inclusive pixel-index interval of the pixel centres inside [lo, hi] (centre i sits at (2i + 1 - S) / S), widened by
-// 1/64 pixel for the float rounding of this conversion -- tighter than coord_window, which rounds outwards by a pixel.
-__device__ __forceinline__ void span_window(float lo, float hi, int S, int& ilo, int& ihi) {
-  const float a = (lo * (float)S + (float)(S - 1)) * 0.5f;
-  const float b = (hi * (float)S + (float)(S - 1)) * 0.5f;
-  ilo = max(0, (int)ceilf(a - 0.015625f));
-  ihi = min(S - 1, (int)floorf(b + 0.015625f));
-}
-
-// Dilation radius for the spans, or a negative value when the face must keep its full window.
-__device__ __forceinline__ float span_radius(const FaceGeom& g, float sthr) {
-  const float eta = face_noise_eta(g);
-  if (!(eta < LASR_SPAN_MAX_NOISE * sthr)) return -1.f;   // also catches NaN / inf
-  return 1.05f * sthr + 8.f * eta;
-}
-
-// x-interval [lo, hi] of the pixel row at height yp that can lie within R of the triangle: the hull, over the three
-// edges, of (the part of the edge inside the band |y - yp| <= R) widened by R.  false: the row misses the set.
-__device__ __forceinline__ bool row_span(const FaceGeom& g, float yp, float R, float& lo, float& hi) {
-  lo = 3.0e38f; hi = -3.0e38f;
-#pragma unroll
-  for (int e = 0; e < 3; ++e) {
-    const int b = (e + 1) % 3;
-    const float ax = g.x[e], ay = g.y[e], bx = g.x[b], by = g.y[b];
-    if (yp < fminf(ay, by) - R || yp > fmaxf(ay, by) + R) continue;
-    float t0 = 0.f, t1 = 1.f;
-    const float dy = by - ay;
-    if (fabsf(dy) > 1e-12f) {                           // clip the edge to the band (parameters may swap)
-      const float ra = (yp - R - ay) / dy, rb = (yp + R - ay) / dy;
-      t0 = fmaxf(fminf(ra, rb), 0.f); t1 = fminf(fmaxf(ra, rb), 1.f);
-      if (!(t0 <= t1)) continue;
-    }
-    const float xa = ax + t0 * (bx - ax), xb = ax + t1 * (bx - ax);
-    lo = fminf(lo, fminf(xa, xb)); hi = fmaxf(hi, fmaxf(xa, xb));
-  }
-  if (lo > hi) return false;
-  lo -= R; hi += R;
-  return true;
-}
-
-// Row of the idx-th pixel of a span sweep: pre[r] = number of span pixels in rows < r (32 entries, non-decreasing;
-// empty rows repeat the value).  Returns the largest r with pre[r] <= idx -- never an empty row for idx < total.
-__device__ __forceinline__ int span_locate(const int* pre, int idx) {
-  int r = 0;
-#pragma unroll
-  for (int step = 16; step > 0; step >>= 1)
-    if (pre[r + step] <= idx) r += step;       // r + step <= 31
-  return r;
 }
 
 // Sum 16 per-lane values over the warp with 16 shuffles instead of 80 (recursive halving: at each

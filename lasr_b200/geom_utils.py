@@ -174,6 +174,10 @@ def render_flow_soft_2(renderer_soft, verts, faces, verts_pos0, verts_pos1, pp0,
     re-project them with each frame's intrinsics to get optical flow (mesh_net.py:75-104).
     Returns (flow_fw [n,S,S,2], bgmask [n,S,S] bool, fgmask [n,S,S])."""
     n_hypo = verts.shape[0] // faces.shape[0]
+    if shared_faces is None and faces.is_cuda:
+        # the one-topology check is cached per tensor OBJECT: ask it of the caller's tensor, not of the fresh
+        # repeat / cat copies built below (those would re-run the synchronising comparison at every call)
+        shared_faces = sr.functional.shared_topology(faces)
     faces = faces[:, None].repeat(1, n_hypo, 1, 1).view(-1, faces.shape[1], 3)
     offset = _eye_offset(renderer_soft, verts.device)
     pre = verts[:, :, :3] + offset

@@ -152,9 +152,11 @@ class RenderHotPath(torch.nn.Module):
         faces_h = faces[:, None].repeat(1, H, 1, 1).view(-1, faces.shape[1], 3)
         r.rasterizer.background_color = [0, 0, 0, 0, 0, 0, 1, 1, 1]
         r.rasterizer.detached_sets = 1          # own positions enter the flow only under .detach() (:102-103)
-        image = r.render_mesh(sr.Mesh(pre, faces_h, textures=sets, texture_type="vertex", shared_faces=shared_faces))
-        r.rasterizer.background_color = [1, 1, 1]
-        r.rasterizer.detached_sets = 0
+        try:
+            image = r.render_mesh(sr.Mesh(pre, faces_h, textures=sets, texture_type="vertex", shared_faces=shared_faces))
+        finally:                                # the renderer is shared state: never leave the K = 3 settings behind
+            r.rasterizer.background_color = [1, 1, 1]
+            r.rasterizer.detached_sets = 0
         pp_own = ppoint[:, None].repeat(1, H, 1).view(nh, 2)
         pp_pair = torch.roll(ppoint, bs, 0)[:, None].repeat(1, H, 1).view(nh, 2)
         f_own = scale.view(n2, H, -1)[:, :, 0].reshape(nh)

@@ -174,3 +174,22 @@ def directional_lighting(light, normals, light_intensity=0.5, light_color=(1, 1,
     cosine = F.relu(torch.sum(normals * direction, dim=2))
     light += light_intensity * (color[:, None, :] * cosine[:, :, None])
     return light
+
+
+def projection(vertices, P, dist_coeffs, orig_size):
+    """Pinhole projection with OpenCV's five-coefficient lens distortion (k1, k2, p1, p2, k3), then normalisation of
+    the pixel coordinates to [-1, 1] by ``orig_size`` (functional/projection.py:4-32).  ``P`` is [N,3,4]; depth is
+    passed through.  The operation order -- radius by sqrt, its even powers by ``**`` -- is the reference's, so the
+    two agree to the last bit on the same device."""
+    hom = torch.cat([vertices, torch.ones_like(vertices[:, :, :1])], dim=-1)
+    cam = torch.bmm(hom, P.transpose(2, 1))
+    depth = cam[:, :, 2]
+    u = cam[:, :, 0] / (depth + 1e-5)
+    v = cam[:, :, 1] / (depth + 1e-5)
+    k1, k2, p1, p2, k3 = (dist_coeffs[:, None, i] for i in range(5))
+    r = torch.sqrt(u ** 2 + v ** 2)
+    radial = 1 + k1 * (r ** 2) + k2 * (r ** 4) + k3 * (r ** 6)
+    ud = u * radial + 2 * p1 * u * v + p2 * (r ** 2 + 2 * u ** 2)
+    vd = v * radial + p1 * (r ** 2 + 2 * v ** 2) + 2 * p2 * u * v
+    to_ndc = lambda t: 2 * (t - orig_size / 2.) / orig_size
+    return torch.stack([to_ndc(ud), to_ndc(vd), depth], dim=-1)

@@ -55,6 +55,11 @@ def vertex_adjacency(tri, num_vertices):
     hit = _cache_get(_csr_cache, tri, (num_vertices,))
     if hit is None:
         flat = tri.reshape(-1).long()
+        # validated once per topology (this path is cached): the kernels fetch vertices through these indices
+        # unchecked, where the reference's gather device-asserts (functional/face_vertices.py:16-22)
+        lo, hi = int(flat.min()), int(flat.max())
+        if lo < 0 or hi >= num_vertices:
+            raise IndexError(f"faces index vertices {lo}..{hi} but the mesh has {num_vertices}")
         order = torch.argsort(flat, stable=True)
         counts = torch.bincount(flat, minlength=num_vertices)
         offsets = torch.zeros(num_vertices + 1, dtype=torch.int32, device=tri.device)

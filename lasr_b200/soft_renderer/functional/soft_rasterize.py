@@ -6,8 +6,9 @@ Differences a caller can observe, all deliberate:
   * ``near`` / ``far`` may be python numbers or 0-dim CUDA tensors; tensors are handed to the
     kernel as a device pointer, so LASR's per-step depth window (nnutils/mesh_net.py:304-311)
     costs no host synchronisation (the reference's pybind ``float`` coercion does);
-  * the scratch tensor the reference calls ``faces_info`` [N,F,27] does not exist; a packed
-    8-byte-per-face window is used instead and is not saved for backward;
+  * the scratch tensor the reference calls ``faces_info`` [N,F,27] is replaced by a workspace of packed
+    per-face windows, border boxes and records, which IS saved for backward (``setup_done=True``), exactly as
+    the reference hands ``faces_info`` from its forward to its backward (soft_rasterize.py:64,71);
   * backward is deterministic (no float atomics).
 """
 from __future__ import annotations
@@ -63,12 +64,13 @@ class SoftRasterizeFunction(Function):
         S = ctx.image_size
         aggrs_info = torch.empty(nb, 2, S, S, dtype=torch.float32, device=device)
         soft_colors = torch.empty(nb, 4, S, S, dtype=torch.float32, device=device)
-        for k in range(3):                            # the kernel reads the background from here
-            soft_colors[:, k].fill_(float(background_color[k]))   # (fills, not an H2D copy: CUDA-graph safe)
+        # the background colour travels as a kernel argument (lasr_b200_raster_forward_bg): the reference's three fills
+        # of soft_colors (:50-53) and the kernel's read of them are 24 S^2 bytes of HBM traffic per frame for a constant
         workspace = _cabi.raster_workspace(nb, nf, S, device)
         _cabi.raster_forward(fv, tex, aggrs_info, soft_colors, workspace, S, ctx.near, ctx.far, ctx.near_far_dev,
                              eps, sigma_val, ctx.func_dist_type, ctx.dist_eps, gamma_val, ctx.func_rgb_type,
-                             ctx.func_alpha_type, ctx.texture_type, ctx.fill_back)
+                             ctx.func_alpha_type, ctx.texture_type, ctx.fill_back,
+                             background=[float(background_color[k]) for k in range(3)])
         ctx.save_for_backward(fv, tex, soft_colors, aggrs_info, workspace)   # workspace plays the reference's faces_info
         return soft_colors
 

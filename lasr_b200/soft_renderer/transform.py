@@ -6,6 +6,8 @@ from __future__ import annotations
 
 import math
 
+import numpy as np
+import torch
 import torch.nn as nn
 
 from . import functional as srf
@@ -16,9 +18,21 @@ def _default_eye(viewing_angle):
 
 
 class Projection(nn.Module):
+    """Calibrated camera: a [N,3,4] projection matrix plus OpenCV distortion coefficients (transform.py:8-26).
+    numpy matrices are moved to the current CUDA device as the reference does; tensors stay where they are."""
+
     def __init__(self, P, dist_coeffs=None, orig_size=512):
         super().__init__()
-        raise NotImplementedError("camera_mode='projection' is outside the LASR hot path (uses srf.projection)")
+        if isinstance(P, np.ndarray):
+            P = torch.from_numpy(P).cuda()
+        if P is None or P.ndimension() != 3 or P.shape[1] != 3 or P.shape[2] != 4:
+            raise ValueError("You need to provide a valid (batch_size)x3x4 projection matrix")
+        if dist_coeffs is None:
+            dist_coeffs = torch.zeros(P.shape[0], 5, dtype=torch.float32, device=P.device)
+        self.P, self.dist_coeffs, self.orig_size = P, dist_coeffs, orig_size
+
+    def forward(self, vertices):
+        return srf.projection(vertices, self.P, self.dist_coeffs, self.orig_size)
 
 
 class LookAt(nn.Module):

@@ -177,3 +177,102 @@ def hot_path_inputs(n_pairs: int, n_bones: int, image_size: int, device, n_hypo:
     leaves = [pred_v, tex, Rmat, Tmat, ppoint, scale] + (list(bones.values()) if bones else [])
     return dict(pred_v=pred_v, tex=tex, faces=faces, Rmat=Rmat, Tmat=Tmat, ppoint=ppoint, scale=scale, batch=batch,
                 bones=bones), leaves
+
+
+def refine_to_faces(verts, faces, target_faces: int):
+    """Refine a closed triangle mesh to exactly ``target_faces`` faces by splitting interior edges at their
+    midpoints, longest first, never two edges of the same triangle (each split turns the edge's two triangles
+    into four: +2 faces, +1 vertex, the mesh stays a valid manifold).  Used for BASELINE config C's "10k-face
+    mesh": Spot (5856 F) + 2072 split edges = 10 000 faces."""
+    v = [p for p in np.asarray(verts, dtype=np.float64)]
+    f = [tuple(int(i) for i in t) for t in np.asarray(faces)]
+    need = target_faces - len(f)
+    if need < 0 or need % 2:
+        raise ValueError("target_faces must exceed the mesh's face count by an even number")
+    while need > 0:
+        edge_tris = {}
+        for ti, (a, b, c) in enumerate(f):
+            for e in ((a, b), (b, c), (c, a)):
+                edge_tris.setdefault((min(e), max(e)), []).append(ti)
+        cand = [(float(np.sum((v[a] - v[b]) ** 2)), (a, b)) for (a, b), ts in edge_tris.items() if len(ts) == 2]
+        cand.sort(key=lambda x: (-x[0], x[1]))
+        used, split = set(), 0
+        out = list(f)
+        for _, (a, b) in cand:
+            if need == 0:
+                break
+            t0, t1 = edge_tris[(a, b)]
+            if t0 in used or t1 in used:
+                continue
+            used.update((t0, t1))
+            m = len(v)
+            v.append(0.5 * (v[a] + v[b]))
+            for ti in (t0, t1):
+                tri = f[ti]
+                k = [i for i in range(3) if tri[i] not in (a, b)][0]      # the corner opposite the edge
+                p, q, r = tri[k], tri[(k + 1) % 3], tri[(k + 2) % 3]      # winding kept: (p,q,r) -> (p,q,m) + (p,m,r)
+                out[ti] = (p, q, m)
+                out.append((p, m, r))
+            need -= 2
+            split += 1
+        f = out
+        if split == 0:
+            raise ValueError("no splittable edge left")
+    return np.asarray(v, dtype=np.float32), np.asarray(f, dtype=np.int32)
+
+
+def mesh_by_name(name: str):
+    """'spot' (2930 V / 5856 F), 'spot10k' (Spot refined to 10 000 faces, BASELINE config C), 'icoK' (icosphere level K,
+    radius 0.5: ico3 642 / 1280 -- what LASR trains at --, ico4 2562 / 5120, ico5 10242 / 20480)."""
+    if name == "spot":
+        return load_spot()
+    if name == "spot10k":
+        v, f = load_spot()
+        return refine_to_faces(v, f, 10000)
+    if name.startswith("ico"):
+        return icosphere(int(name[3:]), 0.5)
+    raise ValueError(f"unknown mesh {name!r}")
+
+
+def quaternion_to_matrix_np(q):
+    """XYZW unit-quaternion matrix (the convention of nnutils/mesh_net.py:118,120), numpy."""
+    q = np.asarray(q, dtype=np.float64)
+    q = q / np.linalg.norm(q, axis=-1, keepdims=True)
+    x, y, z, w = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    m = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                  2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                  2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)
+    return m.reshape(q.shape[:-1] + (3, 3)).astype(np.float32)
+
+
+def region_workload(mesh: str, n_frames: int, n_bones: int, image_size: int, seed: int = 0):
+    """Host-side (numpy) inputs of one batch of the whole render region of LASR.forward (mesh_net.py:255-447) for
+    bench.py: ``n_frames`` = 2*bs frames laid out [first frames; second frames] on the render_syn.py camera orbit,
+    ``n_bones`` bones (1 body + parts with small random articulations, control points at sampled vertices) and random
+    observations in the formats LASR's loader decodes them from (uint8 frames and silhouettes, float flow / occlusion).
+    Shared parameters (mean shape, vertex colours, bone parameters) come separately from per-batch inputs."""
+    if n_frames % 2:
+        raise ValueError("the region works on frame pairs: n_frames must be even")
+    rng = np.random.RandomState(100 + seed)
+    v, f = mesh_by_name(mesh)
+    V, N, B, S = len(v), n_frames, n_bones, image_size
+    Rb, Tb, _, _ = spot_cameras(N, seed)
+    q = rng.randn(N * B, 4) * 0.05
+    q[:, 3] = 1
+    R = quaternion_to_matrix_np(q).reshape(N, B, 3, 3)
+    R[:, 0] = Rb
+    T = (rng.randn(N, B, 3) * 0.01).astype(np.float32)
+    T[:, 0] = Tb[:, 0]
+    params = dict(mean_v=v, tex=vertex_colors(V, 0))
+    if B > 1:
+        idx = np.random.RandomState(7).permutation(V)[:B - 1]      # the shared parameters do not depend on the rank
+        params.update(ctl_ts=v[idx].copy(), rest_ts=v[idx].copy(),
+                      ctl_rs=np.tile(np.array([[0, 0, 0, 1]], np.float32), (B - 1, 1)),
+                      log_ctl=np.ones((B - 1, 3), np.float32))
+    batch = dict(imgs_u8=rng.randint(0, 256, (N, 3, S, S)).astype(np.uint8),
+                 masks_u8=(rng.rand(N, S, S) > 0.5).astype(np.uint8),
+                 flow=(rng.randn(N, 3, S, S) * 0.02).astype(np.float32),
+                 occ=rng.randn(N, S, S).astype(np.float32))
+    pose = dict(Rmat=np.ascontiguousarray(R.reshape(-1, 3, 3)), Tmat=np.ascontiguousarray(T.reshape(-1, 3)),
+                ppoint=np.zeros((N, 2), np.float32), scale=np.full((N, 1), 10.0, np.float32))
+    return dict(faces=f, params=params, pose=pose, batch=batch, V=V, F=len(f), N=N, B=B, S=S)

@@ -260,3 +260,34 @@ def lasr_region_reference(pred_v, tex, faces, Rmat, Tmat, ppoint, scale, batch, 
             tmp[i, j] *= 2 * l1tex_wt
     tex_loss = (0.25 * tmp).mean()
     return mask_loss + flow_loss + tex_loss, mask_loss, flow_loss, tex_loss
+
+
+# ---- the part of the region upstream of obj_to_cam, reference style (mesh_net.py:259-289) ------------------
+def _ref_quat_to_mat(q):
+    """kornia 0.5.3 quaternion_to_rotation_matrix, XYZW (not vendored by the reference; restated)."""
+    q = torch.nn.functional.normalize(q, p=2, dim=-1, eps=1e-12)
+    x, y, z, w = q.unbind(-1)
+    tx, ty, tz = 2 * x, 2 * y, 2 * z
+    one = torch.ones_like(x)
+    m = torch.stack([one - (ty * y + tz * z), ty * x - tz * w, tz * x + ty * w,
+                     ty * x + tz * w, one - (tx * x + tz * z), tz * y - tx * w,
+                     tz * x - ty * w, tz * y + tx * w, one - (tx * x + ty * y)], dim=-1)
+    return m.view(q.shape[:-1] + (3, 3))
+
+
+def ref_skin_and_bones(pred_v, Rmat, Tmat, bones, n2, n_hypo, n_bones):
+    """nnutils/mesh_net.py:261-289 as the reference executes it: the softmax skinning weights in ~6 PyTorch kernels,
+    repeated per frame, and the part transforms composed about their rest positions."""
+    H, B = n_hypo, n_bones
+    dis = bones["ctl_ts"].view(H, -1, 1, 3) - pred_v.view(n2, H, -1, 3)[0].detach().view(H, 1, -1, 3)
+    dis = dis.matmul(_ref_quat_to_mat(bones["ctl_rs"]).view(H, -1, 3, 3))
+    dis = bones["log_ctl"].exp().view(H, -1, 1, 3) * dis.pow(2)
+    skin = (-10 * dis.sum(3)).softmax(1)[:, :, :, None].repeat(n2, 1, 1, 1)
+    rest = bones["rest_ts"][:, None, :, None].repeat(n2, 1, 1, 1).view(-1, B - 1, 3, 1)
+    R4, T4 = Rmat.view(-1, B, 3, 3), Tmat.view(-1, B, 3, 1)
+    Tm = torch.cat([T4[:, :1], -R4[:, 1:].matmul(rest) + T4[:, 1:] + rest], 1).view(-1, 3)
+    Rm = torch.cat([R4[:, :1], R4[:, 1:].permute(0, 1, 3, 2)], 1).view(-1, 3, 3)
+    return skin, Rm, Tm
+
+
+LASR_EYE = (0.0, 0.0, -2.7320508075688776)     # SoftRenderer's default look_at eye: -(1 / tan(30 deg) + 1) (renderer.py:60-63)

@@ -68,51 +68,6 @@ extern "C" void lasr_host_stats(long long* inside, long long* all_edges, int res
   if (reset) { lasr_host_inside_pairs = 0; lasr_host_all_edges_pairs = 0; }
 }
 
-// Row spans of the dilated triangle for one face: for every row of the face's pixel window, the inclusive pixel-index
-// interval [xa, xb] the span sweep would visit (xa > xb: row skipped).  Returns the window (xlo, xhi, ylo, yhi) in
-// win[4] and 1 if the face uses spans, 0 if it keeps the full window (spans then = the window).  rows: [S][2] ints.
-extern "C" int lasr_host_row_spans(const float* face9, int S, float sigma, float dist_eps, int* win, int* rows) {
-  const float sthr = sqrtf(dist_eps * sigma);
-  FaceGeom g;
-  face_setup(face9, sthr, g);
-  int xlo, xhi, ylo, yhi;
-  coord_window(g.lox, g.hix, S, xlo, xhi);
-  coord_window(g.loy, g.hiy, S, ylo, yhi);
-  win[0] = xlo; win[1] = xhi; win[2] = ylo; win[3] = yhi;
-  if (xlo > xhi || ylo > yhi) return 0;
-  const float R = span_radius(g, sthr);
-  for (int yi = ylo; yi <= yhi; ++yi) {
-    int xa = xlo, xb = xhi;
-    if (R >= 0.f) {
-      float lo, hi;
-      if (row_span(g, pixel_coord(yi, S), R, lo, hi)) {
-        int a, b;
-        span_window(lo, hi, S, a, b);
-        xa = a > xlo ? a : xlo; xb = b < xhi ? b : xhi;
-      } else { xa = 1; xb = 0; }
-    }
-    rows[2 * (yi - ylo)] = xa; rows[2 * (yi - ylo) + 1] = xb;
-  }
-  return R >= 0.f ? 1 : 0;
-}
-
-// Emulates the span sweep's enumeration for one face: rows[][2] as returned by lasr_host_row_spans (at most 32 rows),
-// visits every idx < total through span_locate and writes the visited (x, y-row) pairs; returns their number.
-extern "C" int lasr_host_span_enumerate(const int* rows, int nrows, int* visited_xy) {
-  int pre[32], x0[32], total = 0;
-  for (int r = 0; r < 32; ++r) {
-    const int len = r < nrows ? (rows[2 * r + 1] - rows[2 * r] + 1 > 0 ? rows[2 * r + 1] - rows[2 * r] + 1 : 0) : 0;
-    pre[r] = total; x0[r] = r < nrows ? rows[2 * r] : 0;
-    total += len;
-  }
-  for (int idx = 0; idx < total; ++idx) {
-    const int r = span_locate(pre, idx);
-    visited_xy[2 * idx] = x0[r] + idx - pre[r];
-    visited_xy[2 * idx + 1] = r;
-  }
-  return total;
-}
-
 // The forward kernel's own pair code (forward_pair<kFast = true, K = 1>: border test, record load, soft fragment, alpha
 // product, clipped-barycentric depth, online depth softmax, colour blend) run on the host for ONE frame: every pixel
 // visits the faces in ascending order, exactly what a warp lane does after the tile / footprint culls (which only
@@ -156,13 +111,10 @@ extern "C" void lasr_host_forward(const float* faces9, const float* tex9, int F,
 // The backward kernel's own pixel-loop body (raster_backward_pair.inc, included textually exactly as the kernel includes
 // it) run on the host for ONE frame: every face sweeps its pixel window, as a warp does, and sums the pairs'
 // contributions (sequentially here; the kernel sums per lane and reduces in a fixed order).  LASR configuration
-// (kFast), one colour set.  grad_faces [F,9], grad_tex [F,9].  use_spans: sweep the row spans of the dilated triangle
-// (the experimental LASR_BWD_SPANS path) instead of the whole window -- the accepted pairs, and so every bit of the
-// sums, must be the same.
+// (kFast), one colour set.  grad_faces [F,9], grad_tex [F,9].
 extern "C" void lasr_host_backward(const float* faces9, const float* textures9, int F, int S, float near_, float far_,
                                    float sigma, float gamma, float eps, float dist_eps, const float* soft_colors,
-                                   const float* aggrs, const float* grad_soft_colors, float* grad_faces, float* grad_tex,
-                                   int use_spans) {
+                                   const float* aggrs, const float* grad_soft_colors, float* grad_faces, float* grad_tex) {
   constexpr bool kFast = true;
   constexpr int kMode = 1, K = 1, KF = 0, P = 3 * K + 1;
   RasterArgs A{};
@@ -181,27 +133,13 @@ extern "C" void lasr_host_backward(const float* faces9, const float* textures9, 
     FaceGeom g;
     face_setup(faces9 + 9 * f, sthr, g);
     const float* tex9 = textures9 + 9 * f;
-#if LASR_EDGE_LOAD   // as the kernel with setup_done = 1: the geometry comes back from the record (and may read it per lane)
-    alignas(16) float rec_buf[rec_words(1)];
-    float tex_back[9];
-    store_record<1>(rec_buf, g, tex9);
-    load_record<1>(rec_buf, g, tex_back);
-#endif
     float* gtex_out = grad_tex + 9 * f;
     float gf[9] = {0}, gt[9] = {0};
     int xlo, xhi, ylo, yhi;
     coord_window(g.lox, g.hix, S, xlo, xhi);
     coord_window(g.loy, g.hiy, S, ylo, yhi);
-    const float R = use_spans ? span_radius(g, sthr) : -1.f;     // < 0: this face keeps its full window
     for (int yi = yhi; yi >= ylo && xlo <= xhi; --yi) {
-      int xa = xlo, xb = xhi;
-      if (R >= 0.f) {                                            // the span sweep of LASR_BWD_SPANS: same rows, fewer pixels
-        float lo, hi;
-        if (!row_span(g, pixel_coord(yi, S), R, lo, hi)) continue;
-        int a, b;
-        span_window(lo, hi, S, a, b);
-        xa = a > xlo ? a : xlo; xb = b < xhi ? b : xhi;
-      }
+      const int xa = xlo, xb = xhi;
       for (int xi = xa; xi <= xb; ++xi) {
         const float xp = pixel_coord(xi, S), yp = pixel_coord(yi, S);
         if (xp > g.hix || xp < g.lox || yp > g.hiy || yp < g.loy) continue;
@@ -417,4 +355,3 @@ extern "C" void lasr_host_pixel_coords(int S, float* out) {
 }
 
 extern "C" int lasr_host_fast_inside(void) { return LASR_FAST_INSIDE; }
-extern "C" int lasr_host_edge_load(void) { return LASR_EDGE_LOAD; }

@@ -134,8 +134,8 @@ def test_module_constructors_refuse_what_the_reference_refuses():
     r = sr.SoftRenderer(camera_mode="look_at")
     with pytest.raises(AssertionError):
         r.set_texture_mode("uv")
-    with pytest.raises(NotImplementedError):
-        sr.SoftRenderer()                       # camera_mode='projection' (the default) needs srf.projection: out of scope
+    with pytest.raises(ValueError):
+        sr.SoftRenderer()                       # camera_mode='projection' (the default) needs a [N,3,4] matrix (transform.py:18-19)
     with pytest.raises(NotImplementedError):
         sr.functional.voxelization(None)
     t = sr.Transform(camera_mode="look_at")

@@ -300,6 +300,33 @@ def test_backward_with_reused_setup_equals_fresh_setup(srf):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
+def test_background_as_argument_equals_prefilled_image(srf):
+    """lasr_b200_raster_forward_bg (background colour as an argument, soft_colors output only) writes the very bits the
+    reference-contract entry point writes into an image its caller pre-filled (soft_rasterize.py:50-53) -- for the
+    depth-softmax blend and for the hard z-buffer, whose uncovered pixels must come out as the background."""
+    from lasr_b200 import _cabi
+    dev = torch.device("cuda", 0)
+    c = cases.lasr_case("bumpy2", 2, 96)
+    s = c["settings"]
+    N, F = c["face_vertices"].shape[:2]
+    S = s["image_size"]
+    fv = torch.from_numpy(c["face_vertices"]).to(dev).reshape(N, F, 9).contiguous()
+    tex = torch.from_numpy(c["textures"]).to(dev).contiguous()
+    bg = [0.25, 0.5, 0.75]
+    for rgb in (1, 0):
+        scal = (S, s["near"], s["far"], None, s["eps"], s["sigma_val"], 2, float(np.log(1 / s["dist_eps"] - 1)),
+                s["gamma_val"], rgb, 2, 1, True)
+        pre = torch.ones(N, 4, S, S, device=dev)
+        for k in range(3):
+            pre[:, k] = bg[k]
+        agg_a, agg_b = torch.empty(N, 2, S, S, device=dev), torch.empty(N, 2, S, S, device=dev)
+        _cabi.raster_forward(fv, tex, agg_a, pre, _cabi.raster_workspace(N, F, S, dev), *scal)
+        out = torch.full((N, 4, S, S), float("nan"), device=dev)
+        _cabi.raster_forward(fv, tex, agg_b, out, _cabi.raster_workspace(N, F, S, dev), *scal, background=bg)
+        assert torch.equal(pre, out) and torch.equal(agg_a, agg_b), rgb
+        assert float(out[:, 3].min()) < 1e-3 and float((out[:, 0] == bg[0]).float().mean()) > 0.05   # background pixels exist
+
+
 def test_anti_aliasing_and_forward_entry_point(srf, oracle):
     """SoftRasterizer(anti_aliasing=True) renders at 2x and average-pools (rasterizer.py:43,52-53);
     SoftRenderer.forward(vertices, faces, textures) builds the Mesh itself (renderer.py:99-101)."""

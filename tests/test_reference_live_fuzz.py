@@ -32,12 +32,13 @@ def test_geometry_mirrors_follow_the_reference_on_random_shapes(monkeypatch):
     import warnings
     from lasr_b200 import geom_utils as gu
     import lasr_b200.soft_renderer.functional as srf
+    import lasr_b200.soft_renderer as sr_pkg
     monkeypatch.setitem(sys.modules, "soft_renderer", types.ModuleType("soft_renderer"))      # nnutils/geom_utils.py:24
     rg = _load(os.path.join(REF, "nnutils/geom_utils.py"), "ref_geom_live")
     fdir = os.path.join(REF, "third_party/softras/soft_renderer/functional")
     R = {n: getattr(_load(os.path.join(fdir, n + ".py"), "ref_live_" + n), n)
          for n in ("look_at", "orthogonal", "perspective", "face_vertices", "vertex_normals", "ambient_lighting",
-                   "directional_lighting", "get_points_from_angles")}
+                   "directional_lighting", "get_points_from_angles", "projection")}
     g = torch.Generator().manual_seed(0)
     ri = lambda lo, hi: int(torch.randint(lo, hi, (1,), generator=g))
     with warnings.catch_warnings():
@@ -77,6 +78,11 @@ def test_geometry_mirrors_follow_the_reference_on_random_shapes(monkeypatch):
                    R["directional_lighting"](light.clone(), nrm, 0.7, [1, 0.5, 0.2], [0.3, 0.8, -0.5]))
             d, e, a = torch.rand(nb, generator=g) + 2, torch.rand(nb, generator=g) * 60 - 30, torch.rand(nb, generator=g) * 360
             _close("get_points_from_angles", srf.get_points_from_angles(d, e, a), R["get_points_from_angles"](d, e, a))
+            Pm = torch.randn(nb, 3, 4, generator=g) * 0.05 + torch.tensor([[1.0, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 6]])
+            dc = torch.randn(nb, 5, generator=g) * 0.05
+            _close("projection", srf.projection(vv, Pm, dc, 256), R["projection"](vv, Pm, dc, 256), 1e-6)
+            cam = sr_pkg.Transform(camera_mode="projection", P=Pm, dist_coeffs=dc, orig_size=256)
+            _close("Projection module", cam.transformer(vv), R["projection"](vv, Pm, dc, 256), 1e-6)
         assert srf.get_points_from_angles(2.7, 20.0, 40.0) == pytest.approx(R["get_points_from_angles"](2.7, 20.0, 40.0))
 
 
