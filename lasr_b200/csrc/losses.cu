@@ -55,6 +55,31 @@ __device__ __forceinline__ float wsum(float v) {
   return v;
 }
 
+// V consecutive pixels per thread and iteration: V = 4 turns every plane access into one 128-bit load (13 of them in
+// flight per thread before the first use) when S*S is a multiple of 4 -- the kernel is HBM-bound and the scalar form
+// (V = 1, kept for odd image sizes) reached 31 % of the copy bandwidth; all loads are unconditional so that they can be
+// issued together (the masked-out values are simply not accumulated).
+template <int V> struct PixVec;
+template <> struct PixVec<1> {
+  static __device__ __forceinline__ void ld(const float* p, float* o) { o[0] = __ldg(p); }
+  static __device__ __forceinline__ void ldb(const uint8_t* p, unsigned* o) { o[0] = __ldg(p); }
+  static __device__ __forceinline__ void st(float* p, const float* v) { p[0] = v[0]; }
+};
+template <> struct PixVec<4> {
+  static __device__ __forceinline__ void ld(const float* p, float* o) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
+  }
+  static __device__ __forceinline__ void ldb(const uint8_t* p, unsigned* o) {
+    const unsigned q = __ldg(reinterpret_cast<const unsigned*>(p));
+    o[0] = q & 0xffu; o[1] = (q >> 8) & 0xffu; o[2] = (q >> 16) & 0xffu; o[3] = q >> 24;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+template <int V>
 __global__ void __launch_bounds__(kLossThreads) losses_forward_kernel(LossArgs A, float* partial, int nblk) {
   __shared__ float s_w[kLossThreads / 32][kNumSums];
   const int ij = blockIdx.y;            // frame * H + hypothesis
@@ -65,42 +90,59 @@ __global__ void __launch_bounds__(kLossThreads) losses_forward_kernel(LossArgs A
   for (int q = 0; q < kNumSums; ++q) acc[q] = 0.f;
   const int p0 = blockIdx.x * kLossPixPerBlock;
   const int p1 = min(p0 + kLossPixPerBlock, A.SS);
-  for (int p = p0 + threadIdx.x; p < p1; p += kLossThreads) {
-    const float occ = A.occ[i * SS + p];
-    const float m = A.masks[i * SS + p];
-    const bool v = occ != 0.f;
-    const bool fgm = m > 0.f;
-    if (v) {
-      acc[6] += 1.f;
-      const float d = A.mask_pred[ij * SS + p] - m;
-      acc[0] += d * d;
-    }
+  for (int p = p0 + threadIdx.x * V; p < p1; p += kLossThreads * V) {
+    float occ[V], m[V], mp[V], fx[V], fy[V], ox[V], oy[V], fgv[V], img[3][V], tx[3][V];
+    unsigned bgm[V];
+    PixVec<V>::ld(A.occ + i * SS + p, occ);
+    PixVec<V>::ld(A.masks + i * SS + p, m);
+    PixVec<V>::ld(A.mask_pred + ij * SS + p, mp);
     if (A.has_flow) {
-      const bool k = v && fgm && A.bgmask[ij * SS + p] == 0;
-      if (k) {
-        const float2 f = reinterpret_cast<const float2*>(A.flow_rd)[ij * SS + p];
-        const float dx = f.x - A.flow_obs[(i * 3 + 0) * SS + p];
-        const float dy = f.y - A.flow_obs[(i * 3 + 1) * SS + p];
-        const float s = 1.f / (1.f + expf(occ));
-        acc[1] += s * sqrtf(dx * dx + dy * dy);
-        acc[2] += s;
-        acc[3] += 1.f;
-      }
+      PixVec<V>::ldb(A.bgmask + ij * SS + p, bgm);
+      float f2[2 * V];                                    // interleaved (x, y) per pixel
+      PixVec<V>::ld(A.flow_rd + 2 * (ij * SS + p), f2);
+      if constexpr (V == 4) PixVec<V>::ld(A.flow_rd + 2 * (ij * SS + p) + 4, f2 + 4); else f2[1] = __ldg(A.flow_rd + 2 * (ij * SS + p) + 1);
+#pragma unroll
+      for (int k = 0; k < V; ++k) { fx[k] = f2[2 * k]; fy[k] = f2[2 * k + 1]; }
+      PixVec<V>::ld(A.flow_obs + (i * 3 + 0) * SS + p, ox);
+      PixVec<V>::ld(A.flow_obs + (i * 3 + 1) * SS + p, oy);
     }
-    if (A.has_tex && v) {
-      const float fgv = A.fg[ij * SS + p];
-      float a = 0.f, b = 0.f;
+    if (A.has_tex) {
+      PixVec<V>::ld(A.fg + ij * SS + p, fgv);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float img = A.imgs[(i * 3 + c) * SS + p];
-        const float obs = fgm ? img : 0.f;
-        const float white = fgm ? img : 1.f;
-        const float t = A.tex[((long long)ij * 3 + c) * SS + p];
-        a += fabsf(obs - t * fgv);
-        b += fabsf(white - t);
+        PixVec<V>::ld(A.imgs + (i * 3 + c) * SS + p, img[c]);
+        PixVec<V>::ld(A.tex + ((long long)ij * 3 + c) * SS + p, tx[c]);
       }
-      acc[4] += a * (1.f / 3.f);
-      acc[5] += b * (1.f / 3.f);
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const bool v = occ[k] != 0.f;
+      const bool fgm = m[k] > 0.f;
+      if (v) {
+        acc[6] += 1.f;
+        const float d = mp[k] - m[k];
+        acc[0] += d * d;
+      }
+      if (A.has_flow && v && fgm && bgm[k] == 0) {
+        const float dx = fx[k] - ox[k];
+        const float dy = fy[k] - oy[k];
+        const float sg = 1.f / (1.f + expf(occ[k]));
+        acc[1] += sg * sqrtf(dx * dx + dy * dy);
+        acc[2] += sg;
+        acc[3] += 1.f;
+      }
+      if (A.has_tex && v) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float obs = fgm ? img[c][k] : 0.f;
+          const float white = fgm ? img[c][k] : 1.f;
+          a += fabsf(obs - tx[c][k] * fgv[k]);
+          b += fabsf(white - tx[c][k]);
+        }
+        acc[4] += a * (1.f / 3.f);
+        acc[5] += b * (1.f / 3.f);
+      }
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -129,55 +171,84 @@ __global__ void losses_reduce_kernel(const float* partial, int nblk, int NH, flo
 
 // gsums [N,H,7] (gradient of the scalar objective w.r.t. each sum; entry 2,3,6 ignored: those sums
 // do not depend on differentiable inputs) -> per-pixel gradients.
+template <int V>
 __global__ void __launch_bounds__(kLossThreads) losses_backward_kernel(LossArgs A, const float* gsums,
                                                                        float* g_mask_pred, float* g_flow_rd,
                                                                        float* g_tex, float* g_fg) {
   const int ij = blockIdx.y;
   const int i = ij / A.H;
   const long long SS = A.SS;
-  const int p = blockIdx.x * kLossThreads + threadIdx.x;
+  const int p = (blockIdx.x * kLossThreads + threadIdx.x) * V;
   if (p >= A.SS) return;
   const float g0 = gsums[ij * kNumSums + 0], g1 = gsums[ij * kNumSums + 1];
   const float g4 = gsums[ij * kNumSums + 4], g5 = gsums[ij * kNumSums + 5];
-  const float occ = A.occ[i * SS + p];
-  const float m = A.masks[i * SS + p];
-  const bool v = occ != 0.f;
-  const bool fgm = m > 0.f;
-  if (g_mask_pred) g_mask_pred[ij * SS + p] = v ? 2.f * (A.mask_pred[ij * SS + p] - m) * g0 : 0.f;
-  if (A.has_flow && g_flow_rd) {
-    float2 out = make_float2(0.f, 0.f);
-    if (v && fgm && A.bgmask[ij * SS + p] == 0) {
-      const float2 f = reinterpret_cast<const float2*>(A.flow_rd)[ij * SS + p];
-      const float dx = f.x - A.flow_obs[(i * 3 + 0) * SS + p];
-      const float dy = f.y - A.flow_obs[(i * 3 + 1) * SS + p];
+  float occ[V], m[V], mp[V], fx[V], fy[V], ox[V], oy[V], fgv[V], img[3][V], tx[3][V];
+  unsigned bgm[V];
+  PixVec<V>::ld(A.occ + i * SS + p, occ);
+  PixVec<V>::ld(A.masks + i * SS + p, m);
+  if (g_mask_pred) PixVec<V>::ld(A.mask_pred + ij * SS + p, mp);
+  const bool do_flow = A.has_flow && g_flow_rd, do_tex = A.has_tex && g_tex;
+  if (do_flow) {
+    PixVec<V>::ldb(A.bgmask + ij * SS + p, bgm);
+    float f2[2 * V];
+    PixVec<V>::ld(A.flow_rd + 2 * (ij * SS + p), f2);
+    if constexpr (V == 4) PixVec<V>::ld(A.flow_rd + 2 * (ij * SS + p) + 4, f2 + 4); else f2[1] = __ldg(A.flow_rd + 2 * (ij * SS + p) + 1);
+#pragma unroll
+    for (int k = 0; k < V; ++k) { fx[k] = f2[2 * k]; fy[k] = f2[2 * k + 1]; }
+    PixVec<V>::ld(A.flow_obs + (i * 3 + 0) * SS + p, ox);
+    PixVec<V>::ld(A.flow_obs + (i * 3 + 1) * SS + p, oy);
+  }
+  if (do_tex) {
+    PixVec<V>::ld(A.fg + ij * SS + p, fgv);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      PixVec<V>::ld(A.imgs + (i * 3 + c) * SS + p, img[c]);
+      PixVec<V>::ld(A.tex + ((long long)ij * 3 + c) * SS + p, tx[c]);
+    }
+  }
+  float o_mp[V], o_flow[2 * V], o_tex[3][V], o_fg[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const bool v = occ[k] != 0.f;
+    const bool fgm = m[k] > 0.f;
+    o_mp[k] = (g_mask_pred && v) ? 2.f * (mp[k] - m[k]) * g0 : 0.f;
+    o_flow[2 * k] = 0.f; o_flow[2 * k + 1] = 0.f;
+    if (do_flow && v && fgm && bgm[k] == 0) {
+      const float dx = fx[k] - ox[k];
+      const float dy = fy[k] - oy[k];
       const float nrm = sqrtf(dx * dx + dy * dy);
       if (nrm > 0.f) {
-        const float c = g1 / (1.f + expf(occ)) / nrm;
-        out = make_float2(c * dx, c * dy);
+        const float c = g1 / (1.f + expf(occ[k])) / nrm;
+        o_flow[2 * k] = c * dx; o_flow[2 * k + 1] = c * dy;
       }
     }
-    reinterpret_cast<float2*>(g_flow_rd)[ij * SS + p] = out;
-  }
-  if (A.has_tex && g_tex) {
-    const float fgv = A.fg[ij * SS + p];
     float gfg = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float gt = 0.f;
-      if (v) {
-        const float img = A.imgs[(i * 3 + c) * SS + p];
-        const float obs = fgm ? img : 0.f;
-        const float white = fgm ? img : 1.f;
-        const float t = A.tex[((long long)ij * 3 + c) * SS + p];
-        const float ra = obs - t * fgv, rb = white - t;
+      if (do_tex && v) {
+        const float obs = fgm ? img[c][k] : 0.f;
+        const float white = fgm ? img[c][k] : 1.f;
+        const float t = tx[c][k];
+        const float ra = obs - t * fgv[k], rb = white - t;
         const float sa = ra > 0.f ? 1.f : (ra < 0.f ? -1.f : 0.f);   // d|x|/dx, 0 at 0 like torch.abs
         const float sb = rb > 0.f ? 1.f : (rb < 0.f ? -1.f : 0.f);
-        gt = (-sa * fgv * g4 - sb * g5) * (1.f / 3.f);
+        gt = (-sa * fgv[k] * g4 - sb * g5) * (1.f / 3.f);
         gfg += -sa * t * g4 * (1.f / 3.f);
       }
-      g_tex[((long long)ij * 3 + c) * SS + p] = gt;
+      o_tex[c][k] = gt;
     }
-    if (g_fg) g_fg[ij * SS + p] = gfg;
+    o_fg[k] = gfg;
+  }
+  if (g_mask_pred) PixVec<V>::st(g_mask_pred + ij * SS + p, o_mp);
+  if (do_flow) {
+    PixVec<V>::st(g_flow_rd + 2 * (ij * SS + p), o_flow);
+    if constexpr (V == 4) PixVec<V>::st(g_flow_rd + 2 * (ij * SS + p) + 4, o_flow + 4); else g_flow_rd[2 * (ij * SS + p) + 1] = o_flow[1];
+  }
+  if (do_tex) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) PixVec<V>::st(g_tex + ((long long)ij * 3 + c) * SS + p, o_tex[c]);
+    if (g_fg) PixVec<V>::st(g_fg + ij * SS + p, o_fg);
   }
 }
 
@@ -592,7 +663,8 @@ extern "C" int lasr_b200_losses_forward(const float* mask_pred, const float* flo
   const int nblk = (A.SS + kLossPixPerBlock - 1) / kLossPixPerBlock;
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = reinterpret_cast<float*>(workspace);
-  losses_forward_kernel<<<dim3(nblk, N * H), kLossThreads, 0, st>>>(A, partial, nblk);
+  if (A.SS % 4 == 0) losses_forward_kernel<4><<<dim3(nblk, N * H), kLossThreads, 0, st>>>(A, partial, nblk);
+  else losses_forward_kernel<1><<<dim3(nblk, N * H), kLossThreads, 0, st>>>(A, partial, nblk);
   if (lasr_check_launch("losses_forward_kernel")) return 1;
   const int tot = N * H * kNumSums;
   losses_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(partial, nblk, N * H, sums);
@@ -608,8 +680,12 @@ extern "C" int lasr_b200_losses_backward(const float* mask_pred, const float* fl
   if (fill_loss(A, mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs, N, H, S)) return 1;
   if (!grad_sums) return lasr_fail("losses_backward: grad_sums required");
   cudaStream_t st = (cudaStream_t)stream;
-  losses_backward_kernel<<<dim3((A.SS + kLossThreads - 1) / kLossThreads, N * H), kLossThreads, 0, st>>>(
-      A, grad_sums, grad_mask_pred, grad_flow_rd, grad_tex, grad_fg);
+  if (A.SS % 4 == 0)
+    losses_backward_kernel<4><<<dim3((A.SS / 4 + kLossThreads - 1) / kLossThreads, N * H), kLossThreads, 0, st>>>(
+        A, grad_sums, grad_mask_pred, grad_flow_rd, grad_tex, grad_fg);
+  else
+    losses_backward_kernel<1><<<dim3((A.SS + kLossThreads - 1) / kLossThreads, N * H), kLossThreads, 0, st>>>(
+        A, grad_sums, grad_mask_pred, grad_flow_rd, grad_tex, grad_fg);
   return lasr_check_launch("losses_backward_kernel");
 }
 

@@ -77,6 +77,10 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #ifndef LASR_FTZ_MUFU_BWD           // ... but not in the backward (measured slower)
 #define LASR_FTZ_MUFU_BWD 0
 #endif
+#ifndef LASR_BWD_FACES_PER_WARP     // consecutive faces a backward warp works through, single colour set (see raster_backward_kernel)
+#define LASR_BWD_FACES_PER_WARP 4
+#endif
+__host__ __device__ constexpr int bwd_faces_per_warp(int K) { return K == 1 ? LASR_BWD_FACES_PER_WARP : 1; }
 #ifndef LASR_EXP_PLANES_L1
 #define LASR_EXP_PLANES_L1 0
 #endif
@@ -437,10 +441,18 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
   const int alpha_f = kFast ? 2 : A.alpha;
   const int sample = kFast ? 1 : A.sample;
 
-  const int n_items = kBig ? min(A.big_list[0], kBigListCap) : 1;
+  // One-warp-per-face pass: a CTA owns a run of nwarps * LASR_BWD_FACES_PER_WARP CONSECUTIVE faces and its warps take
+  // them interleaved.  Neighbouring faces of a mesh overlap in their pixel windows (a ~5-pixel face has a ~13-pixel
+  // window: every pixel is inside ~7 windows), so keeping them on one SM turns most of the ten plane loads per pixel
+  // into L1 hits; with one face per warp consecutive faces landed on 148 different SMs (CTAs are dealt round-robin).
+  // Measured (profiles/r2/README.md, trip 3): L1 hit rate 69 -> 80 %, single-set backward -3 % at 4 or 8 faces per
+  // warp; the multi-set kernels, whose windows carry 16-22 planes, lose 2 % and keep one face per warp.
+  constexpr int kFPW = bwd_faces_per_warp(K);
+  const int n_items = kBig ? min(A.big_list[0], kBigListCap) : kFPW;
+#pragma unroll 1
   for (int item = kBig ? blockIdx.x : 0; item < n_items; item += kBig ? gridDim.x : 1) {
   const long long wg = kBig ? (long long)A.big_list[1 + item]
-                            : (long long)blockIdx.x * nwarps + (threadIdx.x >> 5);
+                            : ((long long)blockIdx.x * kFPW + item) * nwarps + (threadIdx.x >> 5);
   if (!kBig && wg >= (long long)A.N * A.F) return;
   const int n = (int)(wg / A.F);
   const int f = (int)(wg % A.F);
@@ -469,7 +481,7 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
     slot = __shfl_sync(0xffffffffu, slot, 0);
     if (slot < kBigListCap) {           // deferred: the CTA-per-face pass writes this face's outputs
       if (lane == 0) A.big_list[1 + slot] = (int)wg;
-      return;
+      continue;
     }
   }
   float gf[9], gt[9 * KL];
@@ -679,8 +691,8 @@ static int launch_forward(const RasterArgs& A, cudaStream_t st) {
 // main pass (one warp per face, huge faces deferred) + CTA-per-face pass over the deferred list
 static int launch_backward(const RasterArgs& A, long long nf, cudaStream_t st) {
   if (cudaMemsetAsync(A.big_list, 0, sizeof(int), st) != cudaSuccess) return fail("raster_backward: memset failed");
-  constexpr int kWarpsPerBlock = LASR_BWD_THREADS / 32;
-  const unsigned blocks = (unsigned)((nf + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const int faces_per_block = (LASR_BWD_THREADS / 32) * bwd_faces_per_warp(A.K);
+  const unsigned blocks = (unsigned)((nf + faces_per_block - 1) / faces_per_block);
   const int kf = A.first_live_set;
   if (A.K == 3 && kf == 1) raster_backward_kernel<true, false, 3, 1><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
   else if (A.K == 3) raster_backward_kernel<true, false, 3, 0><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);

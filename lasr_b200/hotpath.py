@@ -57,19 +57,9 @@ class RenderHotPath(torch.nn.Module):
             shared_faces = sr.functional.shared_topology(faces)
         n2 = ppoint.shape[0]          # 2 * bs
         bs = n2 // 2
-        skin = None
-        if B > 1:                      # mesh_net.py:261-281
-            skin = gu.skin_weights(bones["ctl_ts"], bones["ctl_rs"], bones["log_ctl"],
-                                   pred_v.view(n2, H, -1, 3)[0].detach(), H)
-            fused_route = o.fused and pred_v.is_cuda and o.opt_tex
-            if not (fused_route and H == 1):       # the fused LBS kernel reads one shared [1,B-1,V] table
-                skin = skin.repeat(n2, 1, 1, 1)
-            rest_ts = bones["rest_ts"][:, None, :, None].repeat(n2, 1, 1, 1).view(-1, B - 1, 3, 1)
-            R4 = Rmat.view(-1, B, 3, 3)
-            T4 = Tmat.view(-1, B, 3, 1)
-            T_parts = -R4[:, 1:].matmul(rest_ts) + T4[:, 1:] + rest_ts
-            Tmat = torch.cat([T4[:, :1], T_parts], 1).view(-1, 3)
-            Rmat = torch.cat([R4[:, :1], R4[:, 1:].permute(0, 1, 3, 2)], 1).view(-1, 3, 3)
+        fused_route = o.fused and pred_v.is_cuda and o.opt_tex
+        # the fused LBS kernel reads one shared [1,B-1,V] weight table; every other route gets the per-frame repeat
+        skin, Rmat, Tmat = self.bone_transforms(pred_v, Rmat, Tmat, bones, n2, repeat_skin=not (fused_route and H == 1))
         if o.fused and pred_v.is_cuda and o.opt_tex:
             # 1') LBS + camera + projection + depth window in ONE kernel (lasr_b200_lbs_project_forward)
             from . import native_geom
@@ -129,6 +119,24 @@ class RenderHotPath(torch.nn.Module):
         return dict(total=total, mask_loss=mask_loss, flow_loss=flow_loss, texture_loss=texture_loss,
                     mask_pred=mask_pred, texture_render=rgb, flow_rd=flow_rd, bgmask=bgmask, verts_px=verts_px,
                     near=near, far=far)
+
+    def bone_transforms(self, pred_v, Rmat, Tmat, bones, n2, repeat_skin=True):
+        """Skinning weights and the part transforms composed about their rest positions (mesh_net.py:261-281).
+        Returns (skin or None, Rmat [n2*H*B,3,3], Tmat [n2*H*B,3]) ready for ``obj_to_cam``."""
+        H, B = self.opts.n_hypo, self.opts.n_bones
+        if B <= 1:
+            return None, Rmat, Tmat
+        skin = gu.skin_weights(bones["ctl_ts"], bones["ctl_rs"], bones["log_ctl"],
+                               pred_v.view(n2, H, -1, 3)[0].detach(), H)
+        if repeat_skin:
+            skin = skin.repeat(n2, 1, 1, 1)
+        rest_ts = bones["rest_ts"][:, None, :, None].repeat(n2, 1, 1, 1).view(-1, B - 1, 3, 1)
+        R4 = Rmat.view(-1, B, 3, 3)
+        T4 = Tmat.view(-1, B, 3, 1)
+        T_parts = -R4[:, 1:].matmul(rest_ts) + T4[:, 1:] + rest_ts
+        Tmat = torch.cat([T4[:, :1], T_parts], 1).view(-1, 3)
+        Rmat = torch.cat([R4[:, :1], R4[:, 1:].permute(0, 1, 3, 2)], 1).view(-1, 3, 3)
+        return skin, Rmat, Tmat
 
     def _forward_fused(self, cam, verts_px, tex, faces, ppoint, scale, batch, shared_faces, near, far):
         """Steps 2-4 of ``forward`` with the mesh rasterized ONCE per frame.  The reference renders every

@@ -9,10 +9,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 if sys.argv[1] == "--compare":
     a, b = np.load(sys.argv[2]), np.load(sys.argv[3])
     bad = [k for k in a.files if not np.array_equal(a[k], b[k], equal_nan=True)]
+    worst = {"img": 0.0, "gf": 0.0, "gt": 0.0}
     for k in bad:
         d = np.abs(a[k].astype(np.float64) - b[k].astype(np.float64))
-        print("DIFF", k, "max", np.nanmax(d), "count", int((d > 0).sum()))
-    print(f"{len(a.files)} arrays compared, {len(bad)} differ")
+        scale = max(float(np.nanmax(np.abs(a[k]))), 1e-30)
+        worst[k.rsplit("/", 1)[1]] = max(worst[k.rsplit("/", 1)[1]], float(np.nanmax(d)) / scale)
+        print("DIFF", k, "max", np.nanmax(d), "count", int((d > 0).sum()), "max/scale", float(np.nanmax(d)) / scale)
+    print(f"{len(a.files)} arrays compared, {len(bad)} differ; images differing: {sum(k.endswith('/img') for k in bad)}; "
+          f"worst max|d|/max|x|: img {worst['img']:.2e} gf {worst['gf']:.2e} gt {worst['gt']:.2e}")
     sys.exit(1 if bad else 0)
 
 import torch

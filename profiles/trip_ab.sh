@@ -9,7 +9,7 @@ LASR_B200_LIB=$V/$BASE.so python profiles/ab_outputs.py $OUT/ab_$BASE.npz > $OUT
 LASR_B200_LIB=$V/$BASE.so python profiles/ab_timing.py $BASE 2>&1 | grep "^AB" | tee -a $OUT/ab_timing.log
 for v in "$@"; do
   LASR_B200_LIB=$V/$v.so python profiles/ab_outputs.py $OUT/ab_$v.npz > $OUT/ab_$v.log 2>&1
-  python profiles/ab_outputs.py --compare $OUT/ab_$BASE.npz $OUT/ab_$v.npz 2>&1 | tail -4 | tee -a $OUT/ab_compare_$v.log
+  python profiles/ab_outputs.py --compare $OUT/ab_$BASE.npz $OUT/ab_$v.npz > $OUT/ab_compare_$v.log 2>&1; tail -1 $OUT/ab_compare_$v.log
   LASR_B200_LIB=$V/$v.so python profiles/ab_timing.py $v 2>&1 | grep "^AB" | tee -a $OUT/ab_timing.log
 done
 LASR_B200_LIB=$V/$BASE.so python profiles/ab_timing.py $BASE-again 2>&1 | grep "^AB" | tee -a $OUT/ab_timing.log

@@ -600,3 +600,53 @@ def test_mesh_bookkeeping_matches_the_reference_class():
         import json
         meta = json.loads(str(g[f"{pre}/meta"]))
         assert mesh.texture_res == meta["texture_res"] and mesh.batch_size == meta["batch_size"]
+
+
+def _full_region_inputs():
+    """Inputs and golden of tests/golden/region_full_ref.npz (Spot, 26 bones, 256^2, two frame pairs): the inputs are
+    regenerated from the seed by the generator script's own ``inputs()``."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_region_full_golden", os.path.join(here, "golden", "make_region_full_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    g = np.load(os.path.join(here, "golden", "region_full_ref.npz"))
+    bs, H, B, S, seed = (int(v) for v in g["meta"])
+    return gen.inputs(seed, bs, H, B, S), g, (bs, H, B, S)
+
+
+def test_full_size_region_on_cpu_matches_the_reference_lines_with_gradients(monkeypatch):
+    """tests/golden/region_full_ref.npz: the reference's own LASR.forward lines, with autograd, at LASR's articulated
+    shape (Spot, 26 bones, 256^2).  RenderHotPath on CPU tensors (three renders, oracle as the rasterizer) must give
+    the same losses, silhouette and -- through its own autograd -- the same gradient for every input."""
+    from lasr_b200 import hotpath
+    import lasr_b200.soft_renderer.rasterizer as rast
+    x, g, (bs, H, B, S) = _full_region_inputs()
+
+    def fake(face_vertices, textures, image_size=256, background_color=[0, 0, 0], near=1, far=100, fill_back=True,
+             eps=1e-3, sigma_val=1e-5, dist_func="euclidean", dist_eps=1e-4, gamma_val=1e-4, aggr_func_rgb="softmax",
+             aggr_func_alpha="prod", texture_type="surface"):
+        return _OracleRasterize.apply(face_vertices, textures, dict(
+            image_size=image_size, background_color=list(background_color), near=near, far=far, fill_back=fill_back,
+            eps=eps, sigma_val=sigma_val, dist_func=dist_func, dist_eps=dist_eps, gamma_val=gamma_val,
+            aggr_func_rgb=aggr_func_rgb, aggr_func_alpha=aggr_func_alpha, texture_type=texture_type))
+
+    monkeypatch.setattr(rast.srf, "soft_rasterize", fake)
+    L = {k: x[k].clone().requires_grad_(True) for k in ("quat", "trans", "depth", "pred_v", "tex", "ppoint", "scale",
+                                                        "ctl_ts", "rest_ts", "ctl_rs", "log_ctl")}
+    Rmat = L["quat"].view(-1, 3, 3).permute(0, 2, 1).contiguous()            # mesh_net.py:259
+    Tmat = torch.cat([L["trans"], L["depth"]], 1)                            # :260
+    batch = dict(masks=x["masks"], imgs=x["imgs"], flow=x["flow"], occ=x["occ"])
+    bones = {k: L[k] for k in ("ctl_ts", "ctl_rs", "log_ctl", "rest_ts")}
+    m = hotpath.RenderHotPath(hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B, l1tex_wt=1.0))
+    out = m(L["pred_v"], L["tex"], x["faces"], Rmat, Tmat, L["ppoint"], L["scale"], batch, bones)
+    out["total"].backward()
+    for ours, ref in (("mask_loss", "mask_loss"), ("flow_loss", "flow_rd_loss"), ("texture_loss", "texture_loss"), ("total", "total_loss")):
+        assert abs(float(out[ours]) - float(g[f"out/{ref}"])) < 5e-6, (ours, float(out[ours]), float(g[f"out/{ref}"]))
+    sil = g["out/mask_pred_u16"].astype(np.float32) / 65535.0
+    d = np.abs(out["mask_pred"].detach().numpy() - sil)
+    assert (d > 1e-3).mean() < 1e-4, float((d > 1e-3).mean())            # isolated flips at edge-on faces only
+    for k, t in L.items():
+        ref = torch.from_numpy(g[f"grad/{k}"])
+        err = float((t.grad - ref).norm() / ref.norm())
+        assert err < 1e-3, (k, err)

@@ -164,6 +164,19 @@ def test_full_size_properties(srf):
     assert np.abs(gt).max() > 0 and np.abs(gf).max() > 0
 
 
+def test_headline_launch_matches_oracle_on_sampled_frames(srf, oracle):
+    """BASELINE.json configs[1] exactly as bench.py launches it -- Spot, 256x256, N = 64 frames in ONE launch, heaviest-first
+    tile dispatch and the four-faces-per-warp backward on -- against the oracle on four sampled frames (frames are
+    independent, test_full_size_properties: a permuted batch is bit-identical, so four stand for the batch)."""
+    c = cases.lasr_case("spot", 64, 256)
+    img, gf, gt = run_ours(srf, c)
+    pick = [0, 21, 42, 63]
+    sub = dict(c, face_vertices=c["face_vertices"][pick], textures=c["textures"][pick],
+               grad_soft_colors=c["grad_soft_colors"][pick])
+    ref = run_oracle(oracle, sub)
+    assert_parity("headline N=64", (img[pick], gf[pick], gt[pick]), ref)
+
+
 def test_texture_gradient_matches_finite_differences_of_own_forward(srf):
     """The image is linear in the vertex colours: the texture gradient equals central differences of
     our own forward (the vertex gradient of SoftRas is approximate by design, see test_oracle_golden)."""
