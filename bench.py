@@ -403,7 +403,10 @@ class RegionArmBase:
         self.h_in = None
         order = ["imgs_u8", "masks_u8", "flow", "occ"]
         self.in_names = order + ["Rmat", "Tmat", "ppoint", "scale"]
-        self.host_arrays = [rw["batch"][k] for k in order] + [rw["pose"][k] for k in ("Rmat", "Tmat", "ppoint", "scale")]
+        # only the two flow channels the losses read cross PCIe (mesh_net.py:400 uses flow[:, :2]; the third is the
+        # loader's validity channel, dataloader/vidbase.py:151)
+        host = dict(rw["batch"], flow=np.ascontiguousarray(rw["batch"]["flow"][:, :2]))
+        self.host_arrays = [host[k] for k in order] + [rw["pose"][k] for k in ("Rmat", "Tmat", "ppoint", "scale")]
         self.resident = [dv(a) for a in self.host_arrays]
         self.pending = []
         self.eye = torch.tensor(EYE, dtype=torch.float32, device=device)
@@ -424,7 +427,9 @@ class RegionArmBase:
     def step(self, imgs_u8, masks_u8, flow, occ, Rmat, Tmat, ppoint, scale):
         """One forward + backward of the region from device buffers.  Returns (4 losses, *shared-parameter grads)."""
         torch = self.torch
-        batch = dict(imgs=imgs_u8.float().mul_(1.0 / 255.0), masks=masks_u8.float(), flow=flow, occ=occ)
+        flow3 = torch.zeros(flow.shape[0], 3, flow.shape[2], flow.shape[3], device=flow.device)
+        flow3[:, :2] = flow
+        batch = dict(imgs=imgs_u8.float().mul_(1.0 / 255.0), masks=masks_u8.float(), flow=flow3, occ=occ)
         P = {k: v.detach().requires_grad_(True) for k, v in self.params.items()}
         pose = [t.detach().requires_grad_(True) for t in (Rmat, Tmat, ppoint, scale)]
         losses = self.region(P, pose, batch)

@@ -148,6 +148,18 @@ int lasr_b200_render_backward(const float* verts, const int32_t* tri, const floa
                               int func_id_alpha, int double_side, int num_sets, int detached_sets,
                               int setup_done, void* stream);
 
+/* lasr_b200_render_backward fed by lasr_b200_head_backward_packed: `packed_grad` replaces soft_colors, aggrs_info and
+ * grad_soft_colors (num_sets must be 3 and detached_sets 1).  Same outputs. */
+int lasr_b200_render_backward_packed(const float* verts, const int32_t* tri, const float* vcolors,
+                                     const float* packed_grad, const int32_t* csr_offsets,
+                                     const int32_t* csr_entries, float* grad_verts, float* grad_vcolors,
+                                     void* workspace, size_t workspace_bytes, int batch_size,
+                                     int num_vertices, int num_faces, int image_size, float near_,
+                                     float far_, const float* near_far_dev, float eps, float sigma_val,
+                                     int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
+                                     int func_id_alpha, int double_side, int num_sets, int detached_sets,
+                                     int setup_done, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused linear-blend skinning + body transform + pinhole projection + batch depth window
  * (SURVEY 8a rows G1, G2, G3).  Replaces, for CUDA tensors,
@@ -263,6 +275,19 @@ int lasr_b200_head_backward(const float* image, const float* pp_own, const float
                             const float* grad_sums, float* grad_image, float* grad_pp_pair,
                             float* grad_f_pair, void* workspace, size_t workspace_bytes, int N, int H,
                             int image_size, void* stream);
+
+/* The same backward with the image gradient in PACKED per-pixel form for lasr_b200_render_backward_packed (K = 3 colour
+ * sets, set 0 detached -- LASR's hot path): packed_grad [N*H][3][S*S] float4 =
+ *   { g_alpha * (1 - alpha), sum_k g_k * image_k (six live colour planes), 1 / softmax sum, softmax max },
+ *   { g3, g4, g5, g6 }, { g7, g8, 0, 0 }
+ * aggrs_info [N*H,2,S,S] is the rasterizer forward's.  The ten planar gradient planes are never written, and a
+ * (pixel, face) pair of the rasterizer's backward reads three coalesced 128-bit words instead of sixteen scalars. */
+int lasr_b200_head_backward_packed(const float* image, const float* pp_own, const float* pp_pair,
+                                   const float* f_own, const float* f_pair, const float* imgs,
+                                   const float* masks, const float* occ, const float* flow_obs,
+                                   const float* grad_sums, const float* aggrs_info, float* packed_grad,
+                                   float* grad_pp_pair, float* grad_f_pair, void* workspace,
+                                   size_t workspace_bytes, int N, int H, int image_size, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Skinning weights, nnutils/mesh_net.py:264-267:

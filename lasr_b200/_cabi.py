@@ -24,7 +24,7 @@ _RASTER_SCALARS = [_c.c_int, _c.c_int, _c.c_int, _c.c_int,      # N, F, S, T
                    _c.c_int, _c.c_int, _c.c_int, _c.c_int]       # rgb, alpha, sample, double_side
 
 
-EXPECTED_ABI = 5     # include/lasr_b200.h; bumped whenever an entry point's argument list changes
+EXPECTED_ABI = 6     # include/lasr_b200.h; bumped whenever an entry point's argument list changes
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -76,6 +76,9 @@ def _load_locked():
         L.lasr_b200_render_backward.restype = _c.c_int
         L.lasr_b200_render_backward.argtypes = ([_c.c_void_p] * 11 + [_c.c_size_t] + _render_scalars
                                                 + [_c.c_int, _c.c_int, _c.c_void_p])
+        L.lasr_b200_render_backward_packed.restype = _c.c_int
+        L.lasr_b200_render_backward_packed.argtypes = ([_c.c_void_p] * 9 + [_c.c_size_t] + _render_scalars
+                                                       + [_c.c_int, _c.c_int, _c.c_void_p])
         L.lasr_b200_meshreg_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_meshreg_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         vp, ci = _c.c_void_p, _c.c_int
@@ -107,6 +110,8 @@ def _load_locked():
         L.lasr_b200_head_forward.argtypes = [_c.c_void_p] * 13 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
         L.lasr_b200_head_backward.restype = _c.c_int
         L.lasr_b200_head_backward.argtypes = [_c.c_void_p] * 14 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
+        L.lasr_b200_head_backward_packed.restype = _c.c_int
+        L.lasr_b200_head_backward_packed.argtypes = [_c.c_void_p] * 15 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
         L.lasr_b200_losses_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_losses_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_losses_forward.restype = _c.c_int
@@ -138,6 +143,7 @@ EXPORTED_SYMBOLS = [
     "lasr_b200_raster_workspace_bytes", "lasr_b200_raster_forward", "lasr_b200_raster_forward_bg",
     "lasr_b200_raster_backward",
     "lasr_b200_render_workspace_bytes", "lasr_b200_render_forward", "lasr_b200_render_backward",
+    "lasr_b200_render_backward_packed", "lasr_b200_head_backward_packed",
     "lasr_b200_losses_workspace_bytes", "lasr_b200_losses_forward", "lasr_b200_losses_backward",
     "lasr_b200_losses_finalize", "lasr_b200_losses_coefficients",
     "lasr_b200_flow_epilogue_workspace_bytes", "lasr_b200_flow_epilogue_forward", "lasr_b200_flow_epilogue_backward",
@@ -335,6 +341,26 @@ def render_backward(verts, tri, vcolors, soft_colors, aggrs_info, grad_soft_colo
     _check(rc, "lasr_b200_render_backward")
 
 
+def render_backward_packed(verts, tri, vcolors, packed_grad, csr_offsets, csr_entries, grad_verts, grad_vcolors,
+                           workspace, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
+                           func_id_rgb, func_id_alpha, double_side, setup_done=False, detached_sets=1):
+    for t in (verts, vcolors, packed_grad, grad_verts, grad_vcolors):
+        _require_cuda_f32(t, "render tensor")
+    N, V = verts.shape[:2]
+    F = tri.shape[0]
+    K = _num_sets(verts, vcolors)
+    if grad_vcolors.shape != vcolors.shape or packed_grad.numel() != N * 3 * int(S) * int(S) * 4:
+        raise RuntimeError("render_backward_packed: gradient shapes must match vcolors / [N,3,S*S,4]")
+    with torch.cuda.device(verts.device):
+        rc = lib().lasr_b200_render_backward_packed(
+            _p(verts), _p(tri), _p(vcolors), _p(packed_grad), _p(csr_offsets), _p(csr_entries), _p(grad_verts),
+            _p(grad_vcolors), _p(workspace), workspace.numel(),
+            *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
+                                 gamma_val, func_id_rgb, func_id_alpha, double_side, K), int(detached_sets),
+            int(bool(setup_done)), _stream_ptr())
+    _check(rc, "lasr_b200_render_backward_packed")
+
+
 def losses_forward(mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs, sums, N, H, S):
     ws = torch.empty(int(lib().lasr_b200_losses_workspace_bytes(N, H, S)), dtype=torch.uint8, device=mask_pred.device)
     with torch.cuda.device(mask_pred.device):
@@ -436,6 +462,19 @@ def head_backward(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_
                                            _p(grad_pp_pair), _p(grad_f_pair), _p(ws), ws.numel(), N, H, S,
                                            _stream_ptr())
     _check(rc, "lasr_b200_head_backward")
+
+
+def head_backward_packed(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, grad_sums, aggrs_info,
+                         packed_grad, grad_pp_pair, grad_f_pair, N, H, S):
+    for t in (image, grad_sums, aggrs_info, packed_grad, grad_pp_pair, grad_f_pair):
+        _require_cuda_f32(t, "head tensor")
+    ws = torch.empty(int(lib().lasr_b200_head_workspace_bytes(N, H, S)), dtype=torch.uint8, device=image.device)
+    with torch.cuda.device(image.device):
+        rc = lib().lasr_b200_head_backward_packed(_p(image), _p(pp_own), _p(pp_pair), _p(f_own), _p(f_pair), _p(imgs),
+                                                  _p(masks), _p(occ), _p(flow_obs), _p(grad_sums), _p(aggrs_info),
+                                                  _p(packed_grad), _p(grad_pp_pair), _p(grad_f_pair), _p(ws), ws.numel(),
+                                                  N, H, S, _stream_ptr())
+    _check(rc, "lasr_b200_head_backward_packed")
 
 
 def flow_epilogue_forward(px, pp0, pp1, f0, f1, flow, bgmask, n, S):

@@ -543,8 +543,16 @@ __global__ void __launch_bounds__(kLossThreads) head_forward_kernel(HeadArgs A, 
 
 // gsums [N,H,7] -> grad_image [N*H,10,S,S] (every plane written) + per-block partials of the pair
 // intrinsics' gradients: partial [N*H][nblk][3] = (d pp_pair.x, d pp_pair.y, d f_pair)
+// kPacked: instead of the ten planar gradient planes, write what the rasterizer's backward needs from a pixel in packed
+// form -- three float4 per pixel, planes [N*H][3][S*S]:
+//   q0 = { g_alpha * (1 - alpha),  sum_k g_k * image_k over the six live colour planes,  1 / softmax sum,  softmax max }
+//   q1 = { g3, g4, g5, g6 }     q2 = { g7, g8, 0, 0 }          (planes 0-2, the frame's own positions, are detached)
+// so that a (pixel, face) pair costs it three coalesced 128-bit loads instead of sixteen scalar plane loads
+// (raster_backward_pair.inc, kPacked).  `aggrs` is the forward's [N*H,2,S,S] (softmax sum, max).
+template <bool kPacked>
 __global__ void __launch_bounds__(256) head_backward_kernel(HeadArgs A, const float* gsums, float* gimage,
-                                                            float* partial, int nblk) {
+                                                            float* partial, int nblk, const float* aggrs = nullptr,
+                                                            float4* packed = nullptr) {
   __shared__ float s_w[8][3];
   const int ij = blockIdx.y;
   const int i = ij / A.H;
@@ -553,7 +561,7 @@ __global__ void __launch_bounds__(256) head_backward_kernel(HeadArgs A, const fl
   float acc[3] = {0.f, 0.f, 0.f};
   if (p < A.SS) {
     const float* img = A.image + (long long)ij * kHeadPlanes * SS;
-    float* go = gimage + (long long)ij * kHeadPlanes * SS + p;
+    float* go = kPacked ? nullptr : gimage + (long long)ij * kHeadPlanes * SS + p;
     const float g0 = gsums[ij * kNumSums + 0], g1 = gsums[ij * kNumSums + 1];
     const float g4 = gsums[ij * kNumSums + 4], g5 = gsums[ij * kNumSums + 5];
     const float occ = A.occ[i * SS + p];
@@ -580,9 +588,11 @@ __global__ void __launch_bounds__(256) head_backward_kernel(HeadArgs A, const fl
         }
       }
     }
-    go[0] = 0.f; go[SS] = 0.f; go[2 * SS] = 0.f;
-    go[3 * SS] = gx; go[4 * SS] = gy; go[5 * SS] = gz;
-    float gfg = 0.f;
+    if (!kPacked) {
+      go[0] = 0.f; go[SS] = 0.f; go[2 * SS] = 0.f;
+      go[3 * SS] = gx; go[4 * SS] = gy; go[5 * SS] = gz;
+    }
+    float gfg = 0.f, gtex[3], tsum = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float gt = 0.f;
@@ -596,10 +606,22 @@ __global__ void __launch_bounds__(256) head_backward_kernel(HeadArgs A, const fl
         const float sb = rb > 0.f ? 1.f : (rb < 0.f ? -1.f : 0.f);
         gt = (-sa * alpha * g4 - sb * g5) * (1.f / 3.f);
         gfg += -sa * t * g4 * (1.f / 3.f);
+        tsum += gt * t;
       }
-      go[(6 + c) * SS] = gt;
+      gtex[c] = gt;
+      if (!kPacked) go[(6 + c) * SS] = gt;
     }
-    go[9 * SS] = galpha + gfg;
+    if (!kPacked) {
+      go[9 * SS] = galpha + gfg;
+    } else {
+      if (gx != 0.f || gy != 0.f || gz != 0.f)       // the pair-frame positions rendered at this pixel (planes 3-5)
+        tsum += gx * img[3 * SS + p] + gy * img[4 * SS + p] + gz * img[5 * SS + p];
+      const float* ag = aggrs + (long long)ij * 2 * SS + p;
+      float4* pk = packed + (long long)ij * 3 * SS + p;
+      pk[0] = make_float4((galpha + gfg) * (1.f - alpha), tsum, __fdividef(1.f, ag[0]), ag[SS]);
+      pk[SS] = make_float4(gx, gy, gz, gtex[0]);
+      pk[2 * SS] = make_float4(gtex[1], gtex[2], 0.f, 0.f);
+    }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -687,6 +709,28 @@ extern "C" int lasr_b200_losses_backward(const float* mask_pred, const float* fl
     losses_backward_kernel<1><<<dim3((A.SS + kLossThreads - 1) / kLossThreads, N * H), kLossThreads, 0, st>>>(
         A, grad_sums, grad_mask_pred, grad_flow_rd, grad_tex, grad_fg);
   return lasr_check_launch("losses_backward_kernel");
+}
+
+extern "C" int lasr_b200_head_backward_packed(const float* image, const float* pp_own, const float* pp_pair,
+                                              const float* f_own, const float* f_pair, const float* imgs,
+                                              const float* masks, const float* occ, const float* flow_obs,
+                                              const float* grad_sums, const float* aggrs_info, float* packed_grad,
+                                              float* grad_pp_pair, float* grad_f_pair, void* workspace,
+                                              size_t workspace_bytes, int N, int H, int S, void* stream) {
+  HeadArgs A{};
+  if (fill_head(A, image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, N, H, S)) return 1;
+  if (!grad_sums || !aggrs_info || !packed_grad || !grad_pp_pair || !grad_f_pair)
+    return lasr_fail("head_backward_packed: null pointer");
+  if (!workspace || workspace_bytes < lasr_b200_head_workspace_bytes(N, H, S))
+    return lasr_fail("head_backward_packed: workspace too small");
+  const int nblk = (A.SS + 255) / 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = reinterpret_cast<float*>(workspace);
+  head_backward_kernel<true><<<dim3(nblk, N * H), 256, 0, st>>>(A, grad_sums, nullptr, partial, nblk, aggrs_info,
+                                                                  reinterpret_cast<float4*>(packed_grad));
+  if (lasr_check_launch("head_backward_kernel<packed>")) return 1;
+  flow_epilogue_reduce_kernel<<<(N * H * 3 + 127) / 128, 128, 0, st>>>(partial, N * H, nblk, grad_pp_pair, grad_f_pair);
+  return lasr_check_launch("flow_epilogue_reduce_kernel");
 }
 
 extern "C" int lasr_b200_losses_finalize(const float* sums, float* sub, float* out3, int N, int H, float l1tex_wt,
@@ -780,7 +824,7 @@ extern "C" int lasr_b200_head_backward(const float* image, const float* pp_own, 
   const int nblk = (A.SS + 255) / 256;
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = reinterpret_cast<float*>(workspace);
-  head_backward_kernel<<<dim3(nblk, N * H), 256, 0, st>>>(A, grad_sums, grad_image, partial, nblk);
+  head_backward_kernel<false><<<dim3(nblk, N * H), 256, 0, st>>>(A, grad_sums, grad_image, partial, nblk);
   if (lasr_check_launch("head_backward_kernel")) return 1;
   flow_epilogue_reduce_kernel<<<(N * H * 3 + 127) / 128, 128, 0, st>>>(partial, N * H, nblk, grad_pp_pair, grad_f_pair);
   return lasr_check_launch("flow_epilogue_reduce_kernel");

@@ -77,6 +77,9 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #ifndef LASR_FTZ_MUFU_BWD           // ... but not in the backward (measured slower)
 #define LASR_FTZ_MUFU_BWD 0
 #endif
+#ifndef LASR_FWD_BULK                // forward: stage the tile's face records + boxes in shared memory with cp.async.bulk + mbarrier
+#define LASR_FWD_BULK 0
+#endif
 #ifndef LASR_BWD_FACES_PER_WARP     // consecutive faces a backward warp works through, single colour set (see raster_backward_kernel)
 #define LASR_BWD_FACES_PER_WARP 4
 #endif
@@ -203,6 +206,36 @@ __global__ void __launch_bounds__(1024) raster_order_kernel(const int* __restric
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+// Blackwell / Hopper async-proxy primitives for the bulk-staged forward (LASR_FWD_BULK): mbarrier objects in shared
+// memory, 1-D bulk copies global -> shared that complete on them (the TMA unit moves the bytes, no registers, no
+// per-lane load instructions), parity waits.
+constexpr int kStageSlots = 64;                 // face records per staging buffer (two cull steps of a warp)
+constexpr int kStageBufs = 2;
+__host__ __device__ constexpr int stage_bytes(int K) { return kStageSlots * (rec_words(K) * 4 + 16); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const uint32_t a = smem_u32(bar);
+  unsigned done = 0, spins = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();     // a protocol bug must fail the launch, not hang the GPU
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 #ifndef LASR_FWD_CENTRE_OUT
 #define LASR_FWD_CENTRE_OUT 1
 #endif
@@ -221,9 +254,19 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
   constexpr int P = 3 * K + 1;      // image planes per frame: K colour sets, then alpha
   constexpr int kTW = kTileW, kTH = kTileH;
   constexpr int kFpX = kTW / 8;
-  extern __shared__ int s_list[];   // [chunk] face indices, 8 per-warp segments of chunk/8
+  extern __shared__ __align__(16) int s_list[];   // [chunk] face indices, 8 per-warp segments of chunk/8 (+ staging buffers)
   __shared__ int s_cnt[kFwdWarps];
   const int wseg = chunk / kFwdWarps;
+  constexpr bool kBulk = kFast && LASR_FWD_BULK != 0;
+  __shared__ uint64_t s_full[kStageBufs], s_empty[kStageBufs];
+  if (kBulk) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int b = 0; b < kStageBufs; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], kFwdWarps); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
 
   const int S = A.S;
   const int tiles_x = (S + kTW - 1) / kTW, tiles_y = (S + kTH - 1) / kTH;
@@ -368,6 +411,74 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
       }
     }
   };
+  // (2') LASR_FWD_BULK: the same walk over records and boxes STAGED IN SHARED MEMORY by the TMA unit.  The tile's list is
+  //      consumed in rounds of kStageSlots faces through a two-deep ring: warp 0 issues, per face, one bulk copy of the
+  //      record and one of the box (cp.async.bulk ... mbarrier::complete_tx) into the free buffer and arms its `full`
+  //      barrier with the byte count; every warp waits on `full`, culls and evaluates from LDS broadcasts, and arrives on
+  //      the buffer's `empty` barrier; warp 0 refills a buffer once all eight warps have released it.  No __syncthreads
+  //      in the loop, no global loads in the walk, round r + 1 in flight while round r is evaluated.
+  unsigned stage_it = 0;                       // staging rounds issued so far by this CTA (uniform): buffer = it & 1
+  auto walk_bulk = [&](const Footprint& q, PixelState<K>& st) {
+    constexpr unsigned kRecBytes = kRecWords * 4;
+    const uint32_t stage0 = smem_u32(s_list) + (uint32_t)chunk * 4u;
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < kFwdWarps; ++w) total += s_cnt[w];
+    const int rounds = (total + kStageSlots - 1) / kStageSlots;
+    auto produce = [&](int r) {                // warp 0: fill buffer (stage_it + r) & 1 with round r of the list
+      const unsigned it = stage_it + (unsigned)r, b = it & 1u, u = it >> 1;
+      if (u >= 1) mbar_wait(&s_empty[b], (u - 1) & 1u);
+      const int n_r = min(kStageSlots, total - r * kStageSlots);
+      if (lane == 0) mbar_expect_tx(&s_full[b], (unsigned)n_r * (kRecBytes + 16u));
+      __syncwarp();
+      const uint32_t sbox = stage0 + b * (uint32_t)stage_bytes(K), srec = sbox + kStageSlots * 16u;
+      for (int j = lane; j < n_r; j += 32) {
+        const int flat = r * kStageSlots + j;
+        int seg = 0, seg_first = 0, run = 0;      // which scanning warp's segment holds flat entry `flat`
+#pragma unroll
+        for (int w = 0; w < kFwdWarps - 1; ++w) {
+          run += s_cnt[w];
+          if (flat >= run) { seg = w + 1; seg_first = run; }
+        }
+        const int f = s_list[seg * wseg + flat - seg_first];
+        bulk_g2s(srec + (uint32_t)j * kRecBytes, records + (long long)f * kRecWords, kRecBytes, &s_full[b]);
+        bulk_g2s(sbox + (uint32_t)j * 16u, border + f, 16u, &s_full[b]);
+      }
+    };
+    if (warp == 0 && rounds > 0) produce(0);
+#pragma unroll 1
+    for (int r = 0; r < rounds; ++r) {
+      if (warp == 0 && r + 1 < rounds) produce(r + 1);
+      const unsigned it = stage_it + (unsigned)r, b = it & 1u, u = it >> 1;
+      mbar_wait(&s_full[b], u & 1u);
+      const int n_r = min(kStageSlots, total - r * kStageSlots);
+      const uint32_t sbox = stage0 + b * (uint32_t)stage_bytes(K), srec = sbox + kStageSlots * 16u;
+#pragma unroll 1
+      for (int c = 0; c < n_r; c += 32) {
+        const int j = c + lane;
+        float4 bd = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool pass = false;
+        if (j < n_r) {
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bd.x), "=f"(bd.y), "=f"(bd.z), "=f"(bd.w) : "r"(sbox + (uint32_t)j * 16u));
+          pass = !(q.fx0 > bd.y || q.fx1 < bd.x || q.fy0 > bd.w || q.fy1 < bd.z);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, pass);
+        while (m) {
+          const int bsel = __ffs(m) - 1;
+          m &= m - 1;
+          float4 bb;
+          bb.x = __shfl_sync(0xffffffffu, bd.x, bsel);
+          bb.y = __shfl_sync(0xffffffffu, bd.y, bsel);
+          bb.z = __shfl_sync(0xffffffffu, bd.z, bsel);
+          bb.w = __shfl_sync(0xffffffffu, bd.w, bsel);
+          if (q.valid) forward_pair<kFast, K>(A, C, nullptr, bb, 0, n, q.xp, q.yp, st, srec + (uint32_t)(c + bsel) * kRecBytes);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[b]);
+    }
+    stage_it += (unsigned)rounds;
+  };
   // finalize (.cu:457-482)
   auto finish = [&](const Footprint& q, const PixelState<K>& st) {
     if (!q.valid) return;
@@ -397,7 +508,7 @@ __global__ void __launch_bounds__(kFwdThreads, K == 1 ? LASR_FWD_MIN_BLOCKS : LA
   for (int base = 0; tile_live && base < A.F; base += chunk) {
     scan(base);
     __syncthreads();
-    walk(q, st);
+    if (kBulk) walk_bulk(q, st); else walk(q, st);
     if (base + chunk < A.F) __syncthreads();  // the list is reused by the next round
   }
   finish(q, st);
@@ -417,7 +528,7 @@ constexpr int kBigListCap = 16384;     // deferred faces the workspace can list 
 template <bool k32> struct PlaneIndex { typedef long long type; };
 template <> struct PlaneIndex<true> { typedef unsigned type; };
 
-template <bool kFast, bool kBig, int K, int KF>
+template <bool kFast, bool kBig, int K, int KF, bool kPacked = false>
 __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K == 1 ? LASR_BWD_MIN_BLOCKS : (K - KF >= 3 ? LASR_BWD_MIN_BLOCKS_MULTI : LASR_BWD_MIN_BLOCKS_LIVE2))) raster_backward_kernel(RasterArgs A) {
   constexpr int kMode = kFast ? (LASR_FTZ_MUFU_BWD ? 2 : 1) : 0;   // arithmetic mode, see raster_common.cuh
   constexpr int kRecWords = rec_words(K);
@@ -497,6 +608,7 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
     const float* sc = A.soft_colors + (long long)n * P * SS;
     const float* ag = A.aggrs_info + (long long)n * 2 * SS;
     const float* gs = A.grad_soft_colors + (long long)n * P * SS;
+    const float4* pk = kPacked ? A.packed + (long long)n * (1 + (3 * KL + 3) / 4) * SS : nullptr;
     // Single colour set: per-frame plane offsets as 32-bit values (fill_args bounds P*S*S) on opaque 64-bit
     // bases -> one IMAD.WIDE per load instead of an IADD3/IADD3.X/LEA/LEA.HI.X chain (the ten plane loads of
     // a pixel were ~40 integer instructions per sweep; backward 1.208 -> 1.168 ms on config A).  With several
@@ -504,7 +616,7 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
     constexpr bool kIdx32 = K == 1 ? LASR_BWD_INDEX32 != 0 : LASR_BWD_INDEX32_MULTI != 0;
     typedef typename PlaneIndex<kIdx32>::type index_t;
     const index_t SSx = (index_t)S * (index_t)S;
-    if (kIdx32) asm volatile("" : "+l"(sc), "+l"(ag), "+l"(gs));
+    if (kIdx32) asm volatile("" : "+l"(sc), "+l"(ag), "+l"(gs), "+l"(pk));
 #if LASR_EXP_PLANES_L1   // TIMING-ONLY bound experiment (wrong gradients): every plane load hits one L1-resident line
 #define PLANE(k) ((index_t)(k) * 32u + (index_t)lane)
 #else
@@ -678,8 +790,19 @@ static int launch_forward(const RasterArgs& A, cudaStream_t st) {
     if (check_launch("raster_order_kernel")) return 1;
   }
   int chunk = ((F + kFwdThreads - 1) / kFwdThreads) * kFwdThreads;   // a multiple of 32 faces per warp
-  if (chunk > kMaxScanChunk) chunk = (kMaxScanChunk / kFwdThreads) * kFwdThreads;
-  const size_t smem = (size_t)chunk * sizeof(int);
+  const bool bulk = LASR_FWD_BULK != 0 && (A.K > 1 || is_fast(A));
+  // with the staging ring the list is capped so that four CTAs (three with several colour sets) still fit an SM
+  const int max_chunk = bulk ? (A.K == 1 ? 7936 : 9984) : kMaxScanChunk;
+  if (chunk > max_chunk) chunk = (max_chunk / kFwdThreads) * kFwdThreads;
+  const size_t smem = (size_t)chunk * sizeof(int) + (bulk ? (size_t)kStageBufs * stage_bytes(A.K) : 0);
+  if (bulk) {
+    static std::once_flag once;
+    std::call_once(once, [] {
+      cudaFuncSetAttribute(raster_forward_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(raster_forward_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(raster_forward_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    });
+  }
   const unsigned grid = (unsigned)((long long)tiles * N);
   if (A.K == 3) raster_forward_kernel<true, 3><<<grid, kFwdThreads, smem, st>>>(A, chunk);
   else if (A.K == 2) raster_forward_kernel<true, 2><<<grid, kFwdThreads, smem, st>>>(A, chunk);
@@ -694,6 +817,12 @@ static int launch_backward(const RasterArgs& A, long long nf, cudaStream_t st) {
   const int faces_per_block = (LASR_BWD_THREADS / 32) * bwd_faces_per_warp(A.K);
   const unsigned blocks = (unsigned)((nf + faces_per_block - 1) / faces_per_block);
   const int kf = A.first_live_set;
+  if (A.packed) {   // the fused region's packed per-pixel gradients (lasr_b200_render_backward_packed: K = 3, set 0 detached)
+    raster_backward_kernel<true, false, 3, 1, true><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+    if (check_launch("raster_backward_kernel<packed>")) return 1;
+    raster_backward_kernel<true, true, 3, 1, true><<<592, 256, 0, st>>>(A);
+    return check_launch("raster_backward_kernel<packed, big>");
+  }
   if (A.K == 3 && kf == 1) raster_backward_kernel<true, false, 3, 1><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
   else if (A.K == 3) raster_backward_kernel<true, false, 3, 0><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
   else if (A.K == 2 && kf == 1) raster_backward_kernel<true, false, 2, 1><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
@@ -889,15 +1018,14 @@ extern "C" int lasr_b200_render_forward(const float* verts, const int32_t* tri, 
   return launch_forward(A, st);
 }
 
-extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri, const float* vcolors,
-                                         const float* soft_colors, const float* aggrs_info,
-                                         const float* grad_soft_colors, const int32_t* csr_offsets,
-                                         const int32_t* csr_entries, float* grad_verts, float* grad_vcolors,
-                                         void* workspace, size_t workspace_bytes, int N, int V, int F, int S,
-                                         float near_, float far_, const float* near_far_dev, float eps,
-                                         float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
-                                         int func_id_rgb, int func_id_alpha, int double_side, int num_sets,
-                                         int detached_sets, int setup_done, void* stream) {
+static int render_backward_impl(const float* verts, const int32_t* tri, const float* vcolors,
+                                const float* soft_colors, const float* aggrs_info, const float* grad_soft_colors,
+                                const float* packed_grad, const int32_t* csr_offsets, const int32_t* csr_entries,
+                                float* grad_verts, float* grad_vcolors, void* workspace, size_t workspace_bytes, int N,
+                                int V, int F, int S, float near_, float far_, const float* near_far_dev, float eps,
+                                float sigma_val, int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
+                                int func_id_alpha, int double_side, int num_sets, int detached_sets, int setup_done,
+                                void* stream) {
   RasterArgs A{};
   if (num_sets < 1 || num_sets > kMaxSets) return fail("render: num_sets must be 1, 2 or 3");
   if (detached_sets < 0 || detached_sets > 1 || detached_sets >= num_sets)
@@ -909,8 +1037,13 @@ extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri,
   A.records_valid = setup_done;
   A.first_live_set = detached_sets;
   if (fill_indexed(A, verts, tri, vcolors, V)) return 1;
-  if (!soft_colors || !aggrs_info || !grad_soft_colors || !csr_offsets || !csr_entries || !grad_verts || !grad_vcolors)
+  if (!csr_offsets || !csr_entries || !grad_verts || !grad_vcolors) return fail("render_backward: null tensor pointer");
+  if (packed_grad) {
+    if (!(num_sets == 3 && detached_sets == 1)) return fail("render_backward_packed: needs three colour sets with the first detached");
+    A.packed = reinterpret_cast<const float4*>(packed_grad);
+  } else if (!soft_colors || !aggrs_info || !grad_soft_colors) {
     return fail("render_backward: null tensor pointer");
+  }
   A.aggrs_info = const_cast<float*>(aggrs_info);
   A.soft_colors = const_cast<float*>(soft_colors);
   A.grad_soft_colors = grad_soft_colors;
@@ -931,4 +1064,35 @@ extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri,
                                                                       csr_entries, grad_verts, grad_vcolors, N, V, F,
                                                                       num_sets, detached_sets);
   return check_launch("vertex_gather_kernel");
+}
+
+
+extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri, const float* vcolors,
+                                         const float* soft_colors, const float* aggrs_info,
+                                         const float* grad_soft_colors, const int32_t* csr_offsets,
+                                         const int32_t* csr_entries, float* grad_verts, float* grad_vcolors,
+                                         void* workspace, size_t workspace_bytes, int N, int V, int F, int S,
+                                         float near_, float far_, const float* near_far_dev, float eps,
+                                         float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
+                                         int func_id_rgb, int func_id_alpha, int double_side, int num_sets,
+                                         int detached_sets, int setup_done, void* stream) {
+  return render_backward_impl(verts, tri, vcolors, soft_colors, aggrs_info, grad_soft_colors, nullptr, csr_offsets,
+                              csr_entries, grad_verts, grad_vcolors, workspace, workspace_bytes, N, V, F, S, near_, far_,
+                              near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha,
+                              double_side, num_sets, detached_sets, setup_done, stream);
+}
+
+extern "C" int lasr_b200_render_backward_packed(const float* verts, const int32_t* tri, const float* vcolors,
+                                                const float* packed_grad, const int32_t* csr_offsets,
+                                                const int32_t* csr_entries, float* grad_verts, float* grad_vcolors,
+                                                void* workspace, size_t workspace_bytes, int N, int V, int F, int S,
+                                                float near_, float far_, const float* near_far_dev, float eps,
+                                                float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
+                                                int func_id_rgb, int func_id_alpha, int double_side, int num_sets,
+                                                int detached_sets, int setup_done, void* stream) {
+  if (!packed_grad) return fail("render_backward_packed: null packed gradient");
+  return render_backward_impl(verts, tri, vcolors, nullptr, nullptr, nullptr, packed_grad, csr_offsets, csr_entries,
+                              grad_verts, grad_vcolors, workspace, workspace_bytes, N, V, F, S, near_, far_, near_far_dev,
+                              eps, sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side,
+                              num_sets, detached_sets, setup_done, stream);
 }

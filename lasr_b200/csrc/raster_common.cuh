@@ -45,6 +45,7 @@ struct RasterArgs {
   float* aggrs_info;         // [N,2,S,S]
   float* soft_colors;        // [N,4,S,S]
   const float* grad_soft_colors;  // [N,4,S,S]   (backward)
+  const float4* packed;           // [N][1 + ceil(3*live/4)][S*S] packed per-pixel gradients (backward of the fused region)
   float* grad_faces;         // [N,F,9]          (backward)
   float* grad_textures;      // [N,F,T,3]        (backward)
   // workspace carve-up
@@ -311,6 +312,37 @@ __device__ __forceinline__ void load_record(const float* __restrict__ r, FaceGeo
   for (int k = 0; k < 9 * K; ++k) tex9[k] = v[32 + k];
 }
 
+// The same from a record staged in shared memory (the bulk-copy forward, raster.cu): 32-bit shared-space address, explicit
+// ld.shared.v4 -- every lane reads the same address, a broadcast, one wavefront per load.
+#ifdef __CUDACC__
+template <int K>
+__device__ __forceinline__ void load_record_shared(uint32_t saddr, FaceGeom& g, float* tex9) {
+  constexpr int kRecWords = rec_words(K);
+  float v[kRecWords];
+#pragma unroll
+  for (int k = 0; k < kRecWords / 4; ++k)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[4 * k]), "=f"(v[4 * k + 1]), "=f"(v[4 * k + 2]), "=f"(v[4 * k + 3]) : "r"(saddr + 16u * k));
+#pragma unroll
+  for (int k = 0; k < 9; ++k) g.inv[k] = v[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    g.x[k] = v[9 + k]; g.y[k] = v[12 + k]; g.iz[k] = v[16 + k]; g.rden[k] = v[19 + k];
+    g.z[k] = K == 1 ? v[41 + k] : 0.f;
+  }
+  g.kappa = v[31];
+  const int fl = __float_as_int(v[15]);
+  g.obt = (fl & 3) - 1;
+  g.front = (fl & 4) != 0;
+#pragma unroll
+  for (int e = 0; e < 3; ++e)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) g.a[e][j] = v[22 + 3 * e + j];
+#pragma unroll
+  for (int k = 0; k < 9 * K; ++k) tex9[k] = v[32 + k];
+}
+#endif
+
 // Inclusive pixel-index window of the pixel centres inside [lo, hi] (centre i sits at (2i + 1 - S) / S, so coordinate c
 // has index (c*S + S - 1) / 2).  The exact predicate is still applied per pixel; this only has to be a superset, and it
 // is a tight one: the bounds are widened by 1/64 pixel, which covers the float rounding of this conversion and of the
@@ -519,14 +551,20 @@ struct FwdConsts {
   float thr, near_, far_, inv_range;
 };
 
+// rec: the face's record in global memory, or -- rec == nullptr -- staged in shared memory at shared-space address srec
 template <bool kFast, int K>
 __device__ __forceinline__ void forward_pair(const RasterArgs& A, const FwdConsts& C, const float* __restrict__ rec,
-                                             float4 bd, int face, int n, float xp, float yp, PixelState<K>& st) {
+                                             float4 bd, int face, int n, float xp, float yp, PixelState<K>& st,
+                                             uint32_t srec = 0) {
   constexpr int kMode = kFast ? (LASR_FTZ_MUFU_FWD ? 2 : 1) : 0;   // arithmetic mode, see raster_common.cuh
   // exact border predicate of the reference (.cu:32-38,375)
   if (xp > bd.y || xp < bd.x || yp > bd.w || yp < bd.z) return;
   FaceGeom g;
   float tex9[9 * K];
+#ifdef __CUDACC__
+  if (rec == nullptr) load_record_shared<K>(srec, g, tex9);
+  else
+#endif
   load_record<K>(rec, g, tex9);
   Fragment fr;
   if (!soft_fragment<kMode>(A, g, xp, yp, C.thr, fr)) return;

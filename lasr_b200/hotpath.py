@@ -29,6 +29,8 @@ class HotPathOptions:
     opt_tex: bool = True
     fused: bool = True          # CUDA only: one three-set render + fused image head instead of three renders
     report_flow: bool = True    # fused path: also materialise flow_rd / bgmask (reporting; costs one write)
+    packed_grad: bool = True    # fused path: the image gradient travels packed per pixel between the head's and the
+                                # rasterizer's backward kernels; the rendered image is then a reporting output only
 
 
 class RenderHotPath(torch.nn.Module):
@@ -158,21 +160,25 @@ class RenderHotPath(torch.nn.Module):
         pair = torch.roll(own.view(n2, H, -1, 3), bs, 0).reshape(nh, -1, 3)     # frame i <-> i +- bs
         sets = torch.stack([own, pair, tex.reshape(nh, -1, 3).to(own.dtype)], 0)
         faces_h = faces[:, None].repeat(1, H, 1, 1).view(-1, faces.shape[1], 3)
+        link = sr.functional.PackedGradLink() if (o.packed_grad and torch.is_grad_enabled()) else None
         r.rasterizer.background_color = [0, 0, 0, 0, 0, 0, 1, 1, 1]
         r.rasterizer.detached_sets = 1          # own positions enter the flow only under .detach() (:102-103)
+        r.rasterizer.grad_link = link
         try:
             image = r.render_mesh(sr.Mesh(pre, faces_h, textures=sets, texture_type="vertex", shared_faces=shared_faces))
         finally:                                # the renderer is shared state: never leave the K = 3 settings behind
             r.rasterizer.background_color = [1, 1, 1]
             r.rasterizer.detached_sets = 0
+            r.rasterizer.grad_link = None
         pp_own = ppoint[:, None].repeat(1, H, 1).view(nh, 2)
         pp_pair = torch.roll(ppoint, bs, 0)[:, None].repeat(1, H, 1).view(nh, 2)
         f_own = scale.view(n2, H, -1)[:, :, 0].reshape(nh)
         f_pair = torch.roll(scale.view(n2, H, -1)[:, :, 0], bs, 0).reshape(nh)
         mask_loss, flow_loss, texture_loss, sub, flow_rd, bgmask = L.fused_head(
             image, pp_own, pp_pair, f_own, f_pair, batch["imgs"], batch["masks"], batch["occ"], batch["flow"], n2, H,
-            o.l1tex_wt, want_flow=o.report_flow)
+            o.l1tex_wt, want_flow=o.report_flow, grad_link=link)
         total = mask_loss + flow_loss + texture_loss
+        shown = image.detach() if link is not None else image     # packed gradients: the image is for reporting only
         return dict(total=total, mask_loss=mask_loss, flow_loss=flow_loss, texture_loss=texture_loss,
-                    mask_pred=image[:, 9], texture_render=image[:, 6:9], flow_rd=flow_rd, bgmask=bgmask,
+                    mask_pred=shown[:, 9], texture_render=shown[:, 6:9], flow_rd=flow_rd, bgmask=bgmask,
                     verts_px=verts_px, near=near, far=far)

@@ -94,7 +94,8 @@ class _FusedHead(Function):
     writes the image gradient in one pass."""
 
     @staticmethod
-    def forward(ctx, image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, l1tex_wt, N, H, want_flow):
+    def forward(ctx, image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, l1tex_wt, N, H, want_flow,
+                grad_link=None):
         from . import _cabi
         S = image.shape[-1]
         dev = image.device
@@ -115,6 +116,7 @@ class _FusedHead(Function):
         ctx.save_for_backward(img, po, pq, fo, fq, im, mk, oc, fl, sums)
         ctx.dims = (N, H, S, float(l1tex_wt))
         ctx.shapes = (pp_pair.shape, f_pair.shape)
+        ctx.grad_link = grad_link
         if want_flow:
             bgb = bg.bool()
             ctx.mark_non_differentiable(flow_rd, bgb)
@@ -131,21 +133,29 @@ class _FusedHead(Function):
         gsub = None if g_sub is None else g_sub.float().contiguous()
         gsums = torch.empty_like(sums)
         _cabi.losses_coefficients(sums, g3, gsub, gsums, N, H, wt)
-        gimg = torch.empty_like(img)
         gpp = torch.empty(N * H, 2, dtype=torch.float32, device=dev)
         gf = torch.empty(N * H, dtype=torch.float32, device=dev)
-        _cabi.head_backward(img, po, pq, fo, fq, im, mk, oc, fl, gsums, gimg, gpp, gf, N, H, S)
+        link = ctx.grad_link
+        if link is not None:
+            # packed per-pixel gradient for the rasterizer's backward; autograd carries a zero-stride placeholder
+            link.packed = torch.empty(N * H, 3, S * S, 4, dtype=torch.float32, device=dev)
+            _cabi.head_backward_packed(img, po, pq, fo, fq, im, mk, oc, fl, gsums, link.aggrs, link.packed, gpp, gf,
+                                       N, H, S)
+            gimg = link.make_placeholder(img)
+        else:
+            gimg = torch.empty_like(img)
+            _cabi.head_backward(img, po, pq, fo, fq, im, mk, oc, fl, gsums, gimg, gpp, gf, N, H, S)
         return (gimg, None, gpp.reshape(ctx.shapes[0]), None, gf.reshape(ctx.shapes[1]), None, None, None, None,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 def fused_head(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, n_frames, n_hypo, l1tex_wt=1.0,
-               want_flow=True):
+               want_flow=True, grad_link=None):
     """image [N*H,10,S,S] from the three-set render -> (mask_loss, flow_loss, texture_loss, per-pair dict,
     flow_rd [N*H,S,S,2] | None, bgmask [N*H,S,S] bool | None).  The flow outputs are for reporting only
     (not differentiable: their gradient path is inside the losses)."""
     out3, sub, flow_rd, bg = _FusedHead.apply(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs,
-                                              l1tex_wt, n_frames, n_hypo, want_flow)
+                                              l1tex_wt, n_frames, n_hypo, want_flow, grad_link)
     return out3[0], out3[1], out3[2], dict(mask=sub[0], flow=sub[1], texture=sub[2]), flow_rd, bg
 
 

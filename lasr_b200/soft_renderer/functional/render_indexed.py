@@ -68,11 +68,32 @@ def vertex_adjacency(tri, num_vertices):
     return hit
 
 
+class PackedGradLink:
+    """Side channel between the two ends of the fused region's backward (lasr_b200.losses.fused_head ->
+    render_indexed): the head's backward writes the image gradient in the packed per-pixel form the rasterizer's backward
+    reads (lasr_b200_head_backward_packed / lasr_b200_render_backward_packed) and hands autograd a zero-stride
+    placeholder instead of ten planar gradient planes.  Valid only when the rendered image feeds the head and nothing
+    else differentiable -- the rasterizer's backward checks that it received the placeholder and raises otherwise."""
+
+    def __init__(self):
+        self.aggrs = None        # the forward's [N,2,S,S] softmax (sum, max), set by render_indexed
+        self.packed = None       # [N,3,S*S,4] set by the head's backward
+        self.placeholder = None
+
+    def make_placeholder(self, like):
+        self.placeholder = torch.zeros((), dtype=like.dtype, device=like.device).expand(like.shape)
+        return self.placeholder
+
+    def is_placeholder(self, grad):
+        p = self.placeholder
+        return p is not None and grad.data_ptr() == p.data_ptr() and all(st == 0 for st in grad.stride())
+
+
 class RenderIndexedFunction(Function):
 
     @staticmethod
     def forward(ctx, vertices, vcolors, tri, image_size, background_color, near, far, fill_back, eps, sigma_val,
-                dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha, detached_sets=0):
+                dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha, detached_sets=0, grad_link=None):
         if not vertices.is_cuda:
             raise _cabi.CudaTensorRequired("Rasterize module supports only cuda Tensors")
         dev = vertices.device
@@ -101,6 +122,11 @@ class RenderIndexedFunction(Function):
         offsets, entries = vertex_adjacency(tri, V)
         ctx.save_for_backward(v, c, tri, img, aggrs, ws, offsets, entries)
         ctx.shapes = (vertices.shape, vcolors.shape)
+        ctx.grad_link = grad_link
+        if grad_link is not None:
+            if not (K == 3 and ctx.detached == 1):
+                raise ValueError("grad_link needs three colour sets with the first detached (the fused region)")
+            grad_link.aggrs = aggrs
         return img
 
     @staticmethod
@@ -108,20 +134,31 @@ class RenderIndexedFunction(Function):
         v, c, tri, img, aggrs, ws, offsets, entries = ctx.saved_tensors
         N, V = v.shape[:2]
         gv, gc = torch.empty_like(v), torch.empty_like(c)
-        _cabi.render_backward(v, tri, c, img, aggrs, grad.float().contiguous(), offsets, entries, gv, gc, ws, ctx.S,
-                              ctx.near, ctx.far, ctx.nf, *ctx.scal, setup_done=True, detached_sets=ctx.detached)
+        link = ctx.grad_link
+        if link is not None and link.packed is not None:
+            if not link.is_placeholder(grad):
+                raise RuntimeError("render_indexed(grad_link=...): the rendered image received gradient from something "
+                                   "other than the fused head; render without grad_link for that")
+            packed, link.packed, link.placeholder = link.packed, None, None
+            _cabi.render_backward_packed(v, tri, c, packed, offsets, entries, gv, gc, ws, ctx.S, ctx.near, ctx.far,
+                                         ctx.nf, *ctx.scal, setup_done=True, detached_sets=ctx.detached)
+        else:
+            _cabi.render_backward(v, tri, c, img, aggrs, grad.float().contiguous(), offsets, entries, gv, gc, ws, ctx.S,
+                                  ctx.near, ctx.far, ctx.nf, *ctx.scal, setup_done=True, detached_sets=ctx.detached)
         vshape, cshape = ctx.shapes
-        return (gv.reshape(vshape), gc.reshape(cshape)) + (None,) * 14
+        return (gv.reshape(vshape), gc.reshape(cshape)) + (None,) * 15
 
 
 def render_indexed(vertices, vcolors, tri, image_size=256, background_color=[0, 0, 0], near=1, far=100,
                    fill_back=True, eps=1e-3, sigma_val=1e-5, dist_func="euclidean", dist_eps=1e-4, gamma_val=1e-4,
-                   aggr_func_rgb="softmax", aggr_func_alpha="prod", detached_sets=0):
+                   aggr_func_rgb="softmax", aggr_func_alpha="prod", detached_sets=0, grad_link=None):
     """vcolors [N,V,3] -> image [N,4,S,S] (RGBA, the reference's layout).  vcolors [K,N,V,3] with
     K = 2 or 3 renders K colour sets over ONE geometry pass -> image [N,3K+1,S,S] (set s in planes
     3s..3s+2, alpha last); background_color then holds K rgb triples.  Per set the result equals a
     separate render of that set; the vertex gradient is the sum over the sets.  detached_sets=1 declares
-    set 0 an output for reading only (as if its planes were ``.detach()``ed): the backward skips it."""
+    set 0 an output for reading only (as if its planes were ``.detach()``ed): the backward skips it.
+    grad_link (a PackedGradLink shared with ``lasr_b200.losses.fused_head``): the image gradient travels in packed
+    per-pixel form between the two backward kernels instead of as ten planar planes."""
     return RenderIndexedFunction.apply(vertices, vcolors, tri, image_size, background_color, near, far, fill_back,
                                        eps, sigma_val, dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha,
-                                       detached_sets)
+                                       detached_sets, grad_link)

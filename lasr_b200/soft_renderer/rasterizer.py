@@ -35,6 +35,7 @@ class SoftRasterizer(nn.Module):
         self.aggr_func_alpha = aggr_func_alpha
         self.texture_type = texture_type
         self.detached_sets = 0   # extension (stacked colour sets): set 0 rendered for reading only
+        self.grad_link = None    # extension: PackedGradLink shared with losses.fused_head (the fused region)
 
     def forward(self, mesh, mode=None):
         image_size = self.image_size * (2 if self.anti_aliasing else 1)
@@ -48,7 +49,8 @@ class SoftRasterizer(nn.Module):
             images = srf.render_indexed(mesh.vertices, mesh.textures, tri, image_size, self.background_color,
                                         self.near, self.far, self.fill_back, self.eps, self.sigma_val,
                                         self.dist_func, self.dist_eps, self.gamma_val, self.aggr_func_rgb,
-                                        self.aggr_func_alpha, self.detached_sets if mesh.textures.dim() == 4 else 0)
+                                        self.aggr_func_alpha, self.detached_sets if mesh.textures.dim() == 4 else 0,
+                                        self.grad_link if mesh.textures.dim() == 4 else None)
             if self.anti_aliasing:
                 images = F.avg_pool2d(images, kernel_size=2, stride=2)
             return images

@@ -117,6 +117,7 @@ extern "C" void lasr_host_backward(const float* faces9, const float* textures9, 
                                    const float* aggrs, const float* grad_soft_colors, float* grad_faces, float* grad_tex) {
   constexpr bool kFast = true;
   constexpr int kMode = 1, K = 1, KF = 0, P = 3 * K + 1;
+  constexpr bool kPacked = false; const float4* pk = nullptr; (void)pk;
   RasterArgs A{};
   A.N = 1; A.F = F; A.S = S; A.T = 3; A.K = 1; A.R = 1;
   A.dist = 2; A.rgb = 1; A.alpha = 2; A.sample = 1; A.double_side = 1;
@@ -211,6 +212,7 @@ extern "C" void lasr_host_backward_modes(const float* faces9, const float* textu
                                          float* grad_tex) {
   constexpr bool kFast = false;
   constexpr int kMode = 0, K = 1, KF = 0, P = 3 * K + 1;
+  constexpr bool kPacked = false; const float4* pk = nullptr; (void)pk;
   RasterArgs A{};
   fill_mode_args(A, F, S, T, near_, far_, sigma, gamma, eps, dist_eps, dist, rgb, alpha, sample_, double_side, textures);
   const float thr = dist_eps * sigma, sthr = sqrtf(thr);
@@ -297,6 +299,7 @@ static void host_backward_sets(const float* faces9, const float* tex, int F, int
                                const float* grad_soft_colors, float* grad_faces, float* grad_tex) {
   constexpr bool kFast = true;
   constexpr int kMode = 1, P = 3 * K + 1;
+  constexpr bool kPacked = false; const float4* pk = nullptr; (void)pk;
   RasterArgs A{};
   fill_mode_args(A, F, S, 3, near_, far_, sigma, gamma, eps, dist_eps, 2, 1, 2, 1, 1, nullptr);
   A.K = K;

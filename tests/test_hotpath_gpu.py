@@ -304,3 +304,63 @@ def test_full_size_region_end_to_end_sits_on_the_reference_noise_floor(fused):
     assert max(rep["loss_err"].values()) < 1e-3, rep
     assert rep["flip_frac"] <= 2e-2, rep
     assert max(rep["grad_err"].values()) < 0.2, rep
+
+
+def test_packed_image_gradient_equals_the_planar_one():
+    """HotPathOptions.packed_grad: the head's backward hands the rasterizer's backward three float4 per pixel
+    (lasr_b200_head_backward_packed -> lasr_b200_render_backward_packed) instead of ten planar gradient planes.  Same
+    losses bit for bit (the forward is untouched) and the same gradients up to the re-association of
+    sum_k g_k (c_k - image_k) as sum_k g_k c_k - sum_k g_k image_k."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from lasr_b200 import hotpath
+    H, B, S = 1, 3, 64
+    pred_v, tex, faces, Rmat, Tmat, ppoint, scale, batch, bones = scenario(H, B, S, seed=5)
+    dev = torch.device("cuda", 0)
+
+    def run(packed):
+        t = lambda x: x.clone().to(dev)
+        leaves = dict(pred_v=t(pred_v), tex=t(tex), Rmat=t(Rmat), Tmat=t(Tmat), ppoint=t(ppoint), scale=t(scale))
+        bn = {k: t(v) for k, v in bones.items()}
+        leaves.update({f"bone_{k}": bn[k] for k in bn})
+        for x in leaves.values():
+            x.requires_grad_(True)
+        m = hotpath.RenderHotPath(hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B, fused=True, packed_grad=packed))
+        out = m(leaves["pred_v"], leaves["tex"], t(faces), leaves["Rmat"], leaves["Tmat"], leaves["ppoint"],
+                leaves["scale"], {k: t(v) for k, v in batch.items()}, bn)
+        out["total"].backward()
+        return out, {k: x.grad.detach().cpu() for k, x in leaves.items()}
+
+    a_out, a = run(True)
+    b_out, b = run(False)
+    assert not a_out["mask_pred"].requires_grad and b_out["mask_pred"].requires_grad      # reporting output vs live image
+    for k in ("total", "mask_loss", "flow_loss", "texture_loss"):
+        assert float(a_out[k]) == float(b_out[k]), k
+    for k in b:
+        err = float((a[k] - b[k]).norm() / b[k].norm())
+        assert err < 2e-5, (k, err)
+
+
+def test_packed_gradient_link_refuses_a_second_consumer_of_the_image():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import lasr_b200.soft_renderer as sr
+    from lasr_b200 import losses as L, synth
+    dev = torch.device("cuda", 0)
+    v, f = synth.icosphere(1, 0.5)
+    N, S = 2, 32
+    px, cam, near, far = synth.render_inputs(v, f, N)
+    verts = torch.from_numpy(px).to(dev).requires_grad_(True)
+    sets = torch.rand(3, N, len(v), 3, device=dev).requires_grad_(True)
+    sets.data[:2, :, :, 2] += 8
+    tri = torch.from_numpy(f).int().to(dev)
+    link = sr.functional.PackedGradLink()
+    img = sr.functional.render_indexed(verts, sets, tri, image_size=S, background_color=[0] * 6 + [1] * 3, near=near, far=far,
+                                       sigma_val=1e-4, gamma_val=1e-2, detached_sets=1, grad_link=link)
+    z = torch.zeros(N, device=dev)
+    obs = dict(imgs=torch.rand(N, 3, S, S, device=dev), masks=(torch.rand(N, S, S, device=dev) > 0.5).float(),
+               occ=torch.randn(N, S, S, device=dev), flow=torch.randn(N, 3, S, S, device=dev) * 0.05)
+    ml, fl, tl, _, _, _ = L.fused_head(img, torch.zeros(N, 2, device=dev), torch.zeros(N, 2, device=dev), z + 10, z + 10,
+                                       obs["imgs"], obs["masks"], obs["occ"], obs["flow"], N, 1, grad_link=link)
+    with pytest.raises(RuntimeError, match="other than the fused head"):
+        (ml + fl + tl + img.sum()).backward()
