@@ -78,7 +78,7 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #define LASR_FTZ_MUFU_BWD 0
 #endif
 #ifndef LASR_FWD_BULK                // forward: stage the tile's face records + boxes in shared memory with cp.async.bulk + mbarrier
-#define LASR_FWD_BULK 0
+#define LASR_FWD_BULK 1
 #endif
 #ifndef LASR_BWD_FACES_PER_WARP     // consecutive faces a backward warp works through, single colour set (see raster_backward_kernel)
 #define LASR_BWD_FACES_PER_WARP 4

@@ -10,6 +10,7 @@ pairs as [first frames; second frames] (2*bs items), each with ``H`` hypotheses 
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -29,7 +30,7 @@ class HotPathOptions:
     opt_tex: bool = True
     fused: bool = True          # CUDA only: one three-set render + fused image head instead of three renders
     report_flow: bool = True    # fused path: also materialise flow_rd / bgmask (reporting; costs one write)
-    packed_grad: bool = True    # fused path: the image gradient travels packed per pixel between the head's and the
+    packed_grad: bool = os.environ.get("LASR_B200_PACKED_GRAD", "1") != "0"   # fused path: the image gradient travels packed per pixel between the head's and the
                                 # rasterizer's backward kernels; the rendered image is then a reporting output only
 
 

@@ -50,3 +50,20 @@ def test_library_is_sm_100a_only(usage):
     txt, _ = usage
     archs = set(re.findall(r"arch = (sm_\w+)", txt))
     assert archs == {"sm_100a"}, archs
+
+
+def test_forward_kernel_stages_its_records_with_the_tma_unit():
+    """The LASR-configuration forward kernels stage a tile's face records and boxes in shared memory with 1-D bulk
+    copies completing on mbarriers (cp.async.bulk ... mbarrier::complete_tx -> UBLKCP, mbarrier arrive / try_wait ->
+    SYNCS): the async-proxy path of Hopper / Blackwell, visible in the SASS of the product library."""
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    lib = _build.build_library()
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    per_kernel = re.split(r"\n\s*Function : ", sass)
+    fwd = [k for k in per_kernel if k.startswith("_ZN4lasr21raster_forward_kernelILb1E")]
+    assert len(fwd) == 3                                            # K = 1, 2, 3
+    for k in fwd:
+        assert "UBLKCP" in k and "SYNCS.ARRIVE.TRANS64" in k and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in k, k[:80]
+    generic = [k for k in per_kernel if k.startswith("_ZN4lasr21raster_forward_kernelILb0E")]
+    assert generic and "UBLKCP" not in generic[0]                   # the reference-faithful generic modes keep plain loads
