@@ -326,10 +326,11 @@ class OursArm(RasterArmBase):
     def device_step(self, timed):
         torch = self.torch
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timed else None
-        self.img[:, :3] = 0.0  # background pre-fill the kernel reads (soft_rasterize.py:50-53)
         if timed:
             e[0].record()
-        self.cabi.raster_forward(self.fv, self.tex, self.aggrs, self.img, self.ws, *self.scal)
+        # the background colour travels as an argument (lasr_b200_raster_forward_bg): no pre-fill pass over the image --
+        # the reference arm performs the fills its Python performs (soft_rasterize.py:50-53)
+        self.cabi.raster_forward(self.fv, self.tex, self.aggrs, self.img, self.ws, *self.scal, background=[0.0, 0.0, 0.0])
         if timed:
             e[1].record()
         self.cabi.raster_backward(self.fv, self.tex, self.img, self.aggrs, self.gf, self.gt, self.grad, self.ws,
@@ -540,10 +541,27 @@ def extras_microbench(device, peak_gbs, iters=20):
     fl = torch.full((N,), 10.0, device=device, requires_grad=True)
 
     def timeit(fn):
+        """Device time of fn: replayed as a CUDA graph (these calls are tens of microseconds of GPU work behind ~100 us
+        of eager-mode Python -- timed launch by launch the loop measures the host); eager if the call cannot be captured."""
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
-        return timed_loop(torch, fn, iters)
+        try:
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream(device).wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fn()
+            graph.replay()
+            torch.cuda.synchronize()
+            return timed_loop(torch, graph.replay, iters)
+        except Exception:
+            torch.cuda.synchronize()
+            return timed_loop(torch, fn, iters)
 
     with torch.no_grad():
         t_f = timeit(lambda: native_geom.skin_project(verts, R, T, B, skin, pp, fl, depth_window=True))

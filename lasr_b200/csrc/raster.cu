@@ -94,28 +94,79 @@ __host__ __device__ constexpr int bwd_faces_per_warp(int K) { return K == 1 ? LA
 #define LASR_BWD_INDEX32 1
 #endif
 
+// Blackwell / Hopper async-proxy primitives for the bulk-staged forward (LASR_FWD_BULK): mbarrier objects in shared
+// memory, 1-D bulk copies global -> shared that complete on them (the TMA unit moves the bytes, no registers, no
+// per-lane load instructions), parity waits.
+constexpr int kStageSlots = 64;                 // face records per staging buffer (two cull steps of a warp)
+constexpr int kStageBufs = 2;
+__host__ __device__ constexpr int stage_bytes(int K) { return kStageSlots * (rec_words(K) * 4 + 16); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const uint32_t a = smem_u32(bar);
+  unsigned done = 0, spins = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();     // a protocol bug must fail the launch, not hang the GPU
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global bulk store of `bytes` (16-byte granular) by ONE thread; the caller orders its generic-proxy writes to
+// the source with fence.proxy.async first and must not leave before the read of shared memory has completed
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // setup: one thread per face -> packed pixel window, dilated border box, full face record;
 // the first S threads also fill the pixel-centre coordinate table.
 // ---------------------------------------------------------------------------------------------
+#ifndef LASR_SETUP_BULK_STORE        // records leave the setup kernel as one bulk store per warp (else 11-15 strided 16-byte stores per thread)
+#define LASR_SETUP_BULK_STORE 1
+#endif
 __global__ void __launch_bounds__(128) raster_setup_kernel(RasterArgs A, int with_records) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nf = (long long)A.N * A.F;
   if (i < A.S) A.coords[i] = pixel_coord((int)i, A.S);
-  if (i >= (long long)A.N * A.F) return;
+  // A thread's record is 176 - 240 contiguous bytes, so a warp's 32 records are one contiguous 5.5 - 7.5 KB run of the
+  // workspace: they are laid down in shared memory and ONE lane hands the run to the TMA unit (cp.async.bulk
+  // shared -> global).  Written per thread, every 16-byte store of a warp instruction lands in a different 176-byte
+  // stride (32 half-used sectors per instruction).  Lanes past the last face of the last warp stay for the warp-level
+  // steps but write nothing.
+  const bool staged = LASR_SETUP_BULK_STORE != 0 && with_records != 0;
+  __shared__ __align__(16) float s_rec[LASR_SETUP_BULK_STORE ? 4 : 1][LASR_SETUP_BULK_STORE ? 32 * rec_words(kMaxSets) : 4];
+  const long long warp_first = i - (threadIdx.x & 31);
+  if (staged ? warp_first >= nf : i >= nf) return;
+  const bool live_thread = i < nf;
+  const long long fi = live_thread ? i : nf - 1;
   const bool vertex_tex = A.sample == 1;
   float fv[9], tex9[9 * kMaxSets];
-  fetch_face(A, (int)(i / A.F), (int)(i % A.F), fv, tex9, vertex_tex && with_records);
+  fetch_face(A, (int)(fi / A.F), (int)(fi % A.F), fv, tex9, vertex_tex && with_records);
   const float sthr = sqrtf(A.dist_eps * A.sigma);
   FaceGeom g;
   face_setup(fv, sthr, g);
   int xlo, xhi, ylo, yhi;
   coord_window(g.lox, g.hix, A.S, xlo, xhi);
   coord_window(g.loy, g.hiy, A.S, ylo, yhi);
-  if (xlo > xhi || ylo > yhi) { xlo = 1; xhi = 0; ylo = 1; yhi = 0; }
-  A.face_window[i] = make_uint2((uint32_t)xlo | ((uint32_t)xhi << 16), (uint32_t)ylo | ((uint32_t)yhi << 16));
+  if (xlo > xhi || ylo > yhi || !live_thread) { xlo = 1; xhi = 0; ylo = 1; yhi = 0; }
+  if (live_thread) A.face_window[i] = make_uint2((uint32_t)xlo | ((uint32_t)xhi << 16), (uint32_t)ylo | ((uint32_t)yhi << 16));
   if (!with_records) return;
   {  // union of the frame's face windows (lets empty tiles skip their scan): one atomic per warp, not per face
-    const int frame = (int)(i / A.F);
+    const int frame = (int)(fi / A.F);
     const bool live = xlo <= xhi;
     const unsigned act = __activemask();
     const int f0 = __shfl_sync(act, frame, __ffs(act) - 1);
@@ -134,16 +185,28 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RasterArgs A, int wit
   }
   if (A.tile_count && xlo <= xhi) {   // work estimate per forward tile: faces whose window reaches it
     const int tiles_x = (A.S + kTileW - 1) / kTileW, tiles_y = (A.S + kTileH - 1) / kTileH;
-    int* tc = A.tile_count + (long long)(i / A.F) * tiles_x * tiles_y;
+    int* tc = A.tile_count + (long long)(fi / A.F) * tiles_x * tiles_y;
     const int tx0 = xlo / kTileW, tx1 = xhi / kTileW;
     const int ty0 = (A.S - 1 - yhi) / kTileH, ty1 = (A.S - 1 - ylo) / kTileH;   // rows from the top
     for (int ty = ty0; ty <= ty1; ++ty)
       for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(tc + ty * tiles_x + tx, 1);
   }
-  A.face_border[i] = make_float4(g.lox, g.hix, g.loy, g.hiy);
-  if (A.K == 1) store_record<1>(A.face_record + i * rec_words(1), g, vertex_tex ? tex9 : nullptr);
-  else if (A.K == 2) store_record<2>(A.face_record + i * rec_words(2), g, tex9);
-  else store_record<3>(A.face_record + i * rec_words(3), g, tex9);
+  if (live_thread) A.face_border[i] = make_float4(g.lox, g.hix, g.loy, g.hiy);
+  const int words = rec_words(A.K);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* dst = staged ? s_rec[warp] + lane * words : A.face_record + fi * words;
+  if (A.K == 1) store_record<1>(dst, g, vertex_tex ? tex9 : nullptr);
+  else if (A.K == 2) store_record<2>(dst, g, tex9);
+  else store_record<3>(dst, g, tex9);
+  if (staged) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the async proxy
+    __syncwarp();
+    if (lane == 0) {
+      const long long left = nf - warp_first;
+      const unsigned cnt = (unsigned)(left < 32 ? left : 32);
+      bulk_s2g(A.face_record + warp_first * words, smem_u32(s_rec[warp]), cnt * (unsigned)words * 4u);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -206,36 +269,6 @@ __global__ void __launch_bounds__(1024) raster_order_kernel(const int* __restric
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-// Blackwell / Hopper async-proxy primitives for the bulk-staged forward (LASR_FWD_BULK): mbarrier objects in shared
-// memory, 1-D bulk copies global -> shared that complete on them (the TMA unit moves the bytes, no registers, no
-// per-lane load instructions), parity waits.
-constexpr int kStageSlots = 64;                 // face records per staging buffer (two cull steps of a warp)
-constexpr int kStageBufs = 2;
-__host__ __device__ constexpr int stage_bytes(int K) { return kStageSlots * (rec_words(K) * 4 + 16); }
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  const uint32_t a = smem_u32(bar);
-  unsigned done = 0, spins = 0;
-  while (!done) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
-    if (!done && ++spins > (1u << 24)) __trap();     // a protocol bug must fail the launch, not hang the GPU
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 #ifndef LASR_FWD_CENTRE_OUT
 #define LASR_FWD_CENTRE_OUT 1
 #endif

@@ -82,8 +82,10 @@ def look_at(vertices, eye, at=[0, 0, 0], up=[0, 1, 0]):
         key = (tuple(map(float, eye)), tuple(map(float, at)), tuple(map(float, up)), bs, str(device))
         hit = _look_at_cache.get(key)
         if hit is not None:
-            eye_b, rt = hit
-            return torch.matmul(vertices - eye_b, rt)
+            eye_b, rt, identity = hit
+            # LASR's camera sits on the -z axis looking at the origin (mesh_net.py:132-149): the basis is exactly the
+            # identity, and x*1 + y*0 + z*0 is x bit for bit -- skip the batched 3x3 matmul and its backward
+            return vertices - eye_b if identity else torch.matmul(vertices - eye_b, rt)
     eye, at, up = _as_batch(eye, bs, device), _as_batch(at, bs, device), _as_batch(up, bs, device)
     z_axis = F.normalize(at - eye, eps=1e-5)
     x_axis = F.normalize(torch.cross(up, z_axis, dim=1), eps=1e-5)
@@ -94,7 +96,9 @@ def look_at(vertices, eye, at=[0, 0, 0], up=[0, 1, 0]):
     if key is not None and not (vertices.is_cuda and torch.cuda.is_current_stream_capturing()):
         if len(_look_at_cache) > 32:
             _look_at_cache.clear()
-        _look_at_cache[key] = (eye.contiguous(), r.transpose(1, 2).contiguous())
+        rt = r.transpose(1, 2).contiguous()
+        identity = bool((rt == torch.eye(3, dtype=rt.dtype, device=rt.device)).all())     # one sync, once per camera
+        _look_at_cache[key] = (eye.contiguous(), rt, identity)
     return torch.matmul(vertices - eye, r.transpose(1, 2))
 
 
