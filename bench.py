@@ -849,6 +849,13 @@ def run_gpu_arm(args, impl):
             cb = cpu_baseline(cw, S, min(args.cpu_budget, 6.0))
             cb["sample"] = "ONE of the region's three rasterize passes only (the CPU port covers the rasterizer): " + cb["sample"]
             out["cpu_baseline"] = cb
+        if impl == "reference":
+            # the reference arm must not have touched this repository's native code: checked on the process's own map
+            try:
+                mapped = open("/proc/self/maps").read()
+                out["native_code_of_this_repo_loaded"] = "liblasr_b200" in mapped or "lasr_b200._cabi" in sys.modules
+            except OSError:
+                pass
         print(json.dumps(out), flush=True)
     if dist is not None:
         dist.barrier()
