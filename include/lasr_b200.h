@@ -49,7 +49,9 @@ uint64_t lasr_b200_launch_count(void);
 
 /* Scratch needed by one forward or backward call.  Replaces the reference's `faces_info`
  * [N,F,27] buffer (soft_rasterize.py:47): per face a packed pixel window (8 B), the dilated border
- * box (16 B) and a 176-byte record of derived constants, plus an S-entry pixel-coordinate table. */
+ * box (16 B) and a 176-byte record of derived constants, plus an S-entry pixel-coordinate table.
+ * The workspace pointer must be 256-byte aligned (cudaMalloc and framework allocators are): the records are moved
+ * by 16-byte-granular bulk copies. */
 size_t lasr_b200_raster_workspace_bytes(int batch_size, int num_faces, int image_size);
 
 /* forward_soft_rasterize(faces, textures, faces_info, aggrs_info, soft_colors, image_size, near,

@@ -786,6 +786,8 @@ static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, flo
   if (sample == 1 && T != 3) return fail("raster: 'vertex' textures must be [N,F,3,3]");
   if (K < 1 || K > kMaxSets) return fail("render: num_sets must be 1, 2 or 3");
   if (!workspace || workspace_bytes < raster_ws_bytes(N, F, S, K)) return fail("raster: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0)   // bulk copies and 128-bit loads of the records need 16-byte alignment
+    return fail("raster: workspace must be 256-byte aligned (cudaMalloc / torch allocations are)");
   if (K > 1 && !(dist == 2 && rgb == 1 && alpha == 2 && sample == 1 && double_side != 0))
     return fail("render: several colour sets need euclidean / softmax / prod / vertex / fill_back (LASR's configuration)");
   A.N = N; A.F = F; A.S = S; A.T = T; A.K = K;
@@ -828,13 +830,19 @@ static int launch_forward(const RasterArgs& A, cudaStream_t st) {
   const int max_chunk = bulk ? (A.K == 1 ? 7936 : 9984) : kMaxScanChunk;
   if (chunk > max_chunk) chunk = (max_chunk / kFwdThreads) * kFwdThreads;
   const size_t smem = (size_t)chunk * sizeof(int) + (bulk ? (size_t)kStageBufs * stage_bytes(A.K) : 0);
-  if (bulk) {
-    static std::once_flag once;
-    std::call_once(once, [] {
-      cudaFuncSetAttribute(raster_forward_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(raster_forward_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      cudaFuncSetAttribute(raster_forward_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    });
+  if (bulk) {   // more than 48 KB of dynamic shared memory is an opt-in per kernel AND per device
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && !done[dev]) {
+      if (cudaFuncSetAttribute(raster_forward_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
+          cudaFuncSetAttribute(raster_forward_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
+          cudaFuncSetAttribute(raster_forward_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+        return fail("raster_forward: cannot opt in to the staging ring's shared memory");
+      done[dev] = true;
+    }
   }
   const unsigned grid = (unsigned)((long long)tiles * N);
   if (A.K == 3) raster_forward_kernel<true, 3><<<grid, kFwdThreads, smem, st>>>(A, chunk);
