@@ -567,7 +567,10 @@ def extras_microbench(device, peak_gbs, iters=20):
         t_f = timeit(lambda: native_geom.skin_project(verts, R, T, B, skin, pp, fl, depth_window=True))
     cam, px, _ = native_geom.skin_project(verts, R, T, B, skin, pp, fl, depth_window=True)
     gc, gp = torch.randn_like(cam), torch.randn_like(px)
-    t_fb = timeit(lambda: torch.autograd.grad([cam, px], [verts, R, T, skin, pp, fl], [gc, gp], retain_graph=True))
+    for _ in range(3):
+        torch.autograd.grad([cam, px], [verts, R, T, skin, pp, fl], [gc, gp], retain_graph=True)
+    torch.cuda.synchronize()      # eager: six freshly allocated gradients per call do not replay well from a graph
+    t_fb = timed_loop(torch, lambda: torch.autograd.grad([cam, px], [verts, R, T, skin, pp, fl], [gc, gp], retain_graph=True), iters)
     lbs_fwd_bytes = V * 12 + (B - 1) * V * 4 + N * (B * 48 + 12) + N * V * 28       # shared mesh+skin in, cam+px out
     lbs_bwd_bytes = V * 12 + (B - 1) * V * 4 + N * B * 48 + N * V * 28 + N * V * 12 + N * (B - 1) * V * 4
     out["lbs_project"] = {"shape": f"N={N} V={V} B={B} (shared mesh + weights)", "forward_ms": t_f, "backward_ms": t_fb,

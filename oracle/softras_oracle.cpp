@@ -273,8 +273,12 @@ inline void face_precompute(const T* fv, T* info) {
 // conservative pixel-index window [lo, hi] of coordinates c with  cmin-thr <= c <= cmax+thr,
 // padded by 2 px so that the exact float predicate (outside_border) stays the only decider.
 inline void conservative_window(double cmin, double cmax, double thr, int S, int& lo, int& hi) {
-  const double a = ((cmin - thr) * S + S - 1.0) * 0.5;
-  const double b = ((cmax + thr) * S + S - 1.0) * 0.5;
+  double a = ((cmin - thr) * S + S - 1.0) * 0.5;
+  double b = ((cmax + thr) * S + S - 1.0) * 0.5;
+  // boxes reaching far beyond the screen (|pixel coordinate| past the int range: out-of-range float -> int conversion is
+  // undefined and used to come back as an empty window): clamp first, as the kernels' coord_window does
+  a = std::min(std::max(a, -4.0), double(S) + 4.0);
+  b = std::min(std::max(b, -4.0), double(S) + 4.0);
   lo = std::max(0, int(std::floor(a)) - 2);
   hi = std::min(S - 1, int(std::ceil(b)) + 2);
   if (!(a == a) || !(b == b)) {  // NaN vertices: let the exact predicate decide everywhere

@@ -129,7 +129,8 @@ def test_edge_cases_match_oracle(srf, oracle, name):
 def test_boxes_beyond_the_int_range_are_clamped_not_culled(srf, oracle):
     """A face whose vertices sit 1e10 NDC units away (|pixel coordinate| > 2^31) used to be culled by the window
     conversion; it is now clamped to the screen and evaluated like any other face -- with the reference's own float
-    arithmetic, which at that magnitude makes the face vanish by itself (the oracle agrees), and without NaN or a crash."""
+    arithmetic (at that magnitude its geometry is rounding noise, but it does cover most of the screen), and without NaN or
+    a crash.  (The test also caught the same int-overflow cull in the ORACLE's accelerated scan, fixed with it.)"""
     c = cases.lasr_case("ico1", 1, 64)
     z = float(c["face_vertices"][..., 2].mean())
     far = np.array([[[-4e9, -4e9, z + 0.3], [4e9, -4e9, z + 0.35], [0.0, 4e9, z + 0.4]],
@@ -138,7 +139,12 @@ def test_boxes_beyond_the_int_range_are_clamped_not_culled(srf, oracle):
     c["textures"] = np.concatenate([c["textures"], c["textures"][:, :2]], 1)
     ours = run_ours(srf, c)
     assert all(np.isfinite(a).all() for a in ours)
-    assert_parity("beyond int range", ours, run_oracle(oracle, c))
+    ref = run_oracle(oracle, c)
+    base = run_oracle(oracle, dict(c, face_vertices=c["face_vertices"][:, :-2], textures=c["textures"][:, :-2]))
+    assert ref[0][0, 3].mean() > base[0][0, 3].mean() + 0.2          # the reference does render the far face ...
+    assert abs(ours[0][0, 3].mean() - ref[0][0, 3].mean()) < 0.02     # ... and so do we (it used to be culled)
+    ir = parity.image_report(ours[0], ref[0], rel=1e-4)               # at 4e9 the float geometry is noise: a few
+    assert ir["n_bad"] <= 0.01 * ir["n"], ir                           # pixels may decide differently, not more
 
 
 def test_near_far_as_device_tensors(srf):
