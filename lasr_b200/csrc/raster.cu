@@ -80,6 +80,9 @@ constexpr int kMaxScanChunk = 12032;  // faces scanned per round (47 KB of indic
 #ifndef LASR_FWD_BULK                // forward: stage the tile's face records + boxes in shared memory with cp.async.bulk + mbarrier
 #define LASR_FWD_BULK 1
 #endif
+#ifndef LASR_BWD_PACK_K1             // single-set backward (LASR configuration): pack the per-pixel gradients first (raster_pack_kernel)
+#define LASR_BWD_PACK_K1 1
+#endif
 #ifndef LASR_BWD_FACES_PER_WARP     // consecutive faces a backward warp works through, single colour set (see raster_backward_kernel)
 #define LASR_BWD_FACES_PER_WARP 4
 #endif
@@ -747,6 +750,51 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
 }
 
 // ---------------------------------------------------------------------------------------------
+// Per-pixel pre-pass of the single-set backward (LASR configuration).  Everything a (pixel, face) pair reads from the
+// pixel -- image (4 planes), its gradient (4), the softmax sum / max (2): ten scalar gathers per pair -- is independent of
+// the face, and every pixel is inside ~25 face windows.  One coalesced pass packs it into two float4 per pixel
+//   { g_alpha * (1 - alpha),  sum_k g_k * colour_k,  1 / softmax sum,  softmax max },  { g0, g1, g2, 0 }
+// (planes [N][2][S*S], the layout lasr_b200_head_backward_packed writes for three sets), and the pair costs two
+// coalesced 128-bit loads, no `1 - alpha`, one MUFU.RCP less and three subtractions less.  4 pixels per thread.
+// ---------------------------------------------------------------------------------------------
+template <int vec>
+__global__ void __launch_bounds__(256) raster_pack_kernel(const float* __restrict__ sc, const float* __restrict__ gs,
+                                                          const float* __restrict__ ag, float4* __restrict__ pk,
+                                                          long long SS) {
+  const int n = blockIdx.y;
+  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * vec;
+  if (p >= SS) return;
+  const float* s0 = sc + (long long)n * 4 * SS + p;
+  const float* g0 = gs + (long long)n * 4 * SS + p;
+  const float* a0 = ag + (long long)n * 2 * SS + p;
+  float4* o = pk + (long long)n * 2 * SS + p;
+  float c[4][vec], g[4][vec], a[2][vec];
+  if constexpr (vec == 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(s0 + k * SS)), y = __ldg(reinterpret_cast<const float4*>(g0 + k * SS));
+      c[k][0] = x.x; c[k][1] = x.y; c[k][2] = x.z; c[k][3] = x.w;
+      g[k][0] = y.x; g[k][1] = y.y; g[k][2] = y.z; g[k][3] = y.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(a0 + k * SS));
+      a[k][0] = x.x; a[k][1] = x.y; a[k][2] = x.z; a[k][3] = x.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { c[k][0] = s0[k * SS]; g[k][0] = g0[k * SS]; }
+    a[0][0] = a0[0]; a[1][0] = a0[SS];
+  }
+#pragma unroll
+  for (int e = 0; e < vec; ++e) {
+    const float T = g[0][e] * c[0][e] + g[1][e] * c[1][e] + g[2][e] * c[2][e];
+    o[e] = make_float4(g[3][e] * (1.f - c[3][e]), T, fast_rcp<LASR_FTZ_MUFU_BWD ? 2 : 1>(a[0][e]), a[1][e]);
+    o[SS + e] = make_float4(g[0][e], g[1][e], g[2][e], 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 static int fail(const std::string& msg) { return lasr_fail(msg); }
@@ -766,6 +814,23 @@ static bool use_lpt(int N, int F) {
 
 static size_t num_tiles(int S) { return (size_t)((S + kTileW - 1) / kTileW) * (size_t)((S + kTileH - 1) / kTileH); }
 
+// The packing pre-pass of the single-set backward (raster_pack_kernel) costs one pass over the images (72 B per pixel) and
+// saves eight scalar gathers per (pixel, face) pair: it pays when a pixel sits inside many face windows.  Estimate of that
+// number from what the host knows -- F faces of ~0.8 S^2 / F pixels each (an object over ~40 % of the image, two layers),
+// dilated by the blur radius r on every side: F (w + 2r)^2 / S^2.  Measured (profiles/r2/README.md, trip 12): config D
+// (estimate 28) backward -6.6 %, config A (10) +-0, ico3 (4) +5 % -- the pass is taken from 16 up.  The workspace reserves
+// room for it by the same estimate at LASR's sigma = 1e-4 (its size may depend on N, F, S only).
+static float est_windows_per_pixel(int F, int S, float sthr_ndc) {
+  const float r = sthr_ndc * 0.5f * (float)S;
+  const float w = sqrtf(0.8f * (float)S * (float)S / (float)F);
+  return (float)F * (w + 2.f * r) * (w + 2.f * r) / ((float)S * (float)S);
+}
+static bool pack_room(int F, int S, int K) {
+  static const int forced = [] { const char* e = getenv("LASR_B200_BWD_PACK"); return e ? atoi(e) : -1; }();
+  if (!LASR_BWD_PACK_K1 || K != 1 || forced == 0) return false;
+  return forced == 1 || est_windows_per_pixel(F, S, 0.030349f) >= 16.f;     // sqrt(ln(9999) * 1e-4)
+}
+
 static size_t raster_ws_bytes(int N, int F, int S, int K) {
   if (N <= 0 || F <= 0 || S <= 0 || K < 1 || K > kMaxSets) return 0;
   const size_t nf = (size_t)N * (size_t)F;
@@ -773,7 +838,8 @@ static size_t raster_ws_bytes(int N, int F, int S, int K) {
          align256((size_t)(kBigListCap + 1) * sizeof(int)) +
          (LASR_FWD_LPT ? 2 * align256((size_t)N * num_tiles(S) * sizeof(int)) : 0) +
          align256(nf * sizeof(float4)) +
-         align256(nf * rec_words(K) * sizeof(float));
+         align256(nf * rec_words(K) * sizeof(float)) +
+         (pack_room(F, S, K) ? align256((size_t)N * 2 * (size_t)S * S * sizeof(float4)) : 0);   // packed per-pixel gradients
 }
 
 static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, float far_, const float* nf_dev,
@@ -810,7 +876,8 @@ static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, flo
     if (use_lpt(N, F)) { A.tile_count = tc; A.tile_order = to; }
   }
   A.face_border = reinterpret_cast<float4*>(p);  p += align256(nf * sizeof(float4));
-  A.face_record = reinterpret_cast<float*>(p);
+  A.face_record = reinterpret_cast<float*>(p);   p += align256(nf * rec_words(K) * sizeof(float));
+  A.pack_area = pack_room(F, S, K) ? reinterpret_cast<float4*>(p) : nullptr;
   return 0;
 }
 
@@ -858,6 +925,22 @@ static int launch_backward(const RasterArgs& A, long long nf, cudaStream_t st) {
   const int faces_per_block = (LASR_BWD_THREADS / 32) * bwd_faces_per_warp(A.K);
   const unsigned blocks = (unsigned)((nf + faces_per_block - 1) / faces_per_block);
   const int kf = A.first_live_set;
+  static const int pack_forced = [] { const char* e = getenv("LASR_B200_BWD_PACK"); return e ? atoi(e) : -1; }();
+  if (!A.packed && A.pack_area && A.K == 1 && is_fast(A) &&
+      (pack_forced == 1 || est_windows_per_pixel(A.F, A.S, sqrtf(A.dist_eps * A.sigma)) >= 16.f)) {   // pack per pixel first
+    const long long SS = (long long)A.S * A.S;
+    const int vec = SS % 4 == 0 ? 4 : 1;
+    const unsigned gx = (unsigned)((SS / vec + 255) / 256);
+    if (vec == 4) raster_pack_kernel<4><<<dim3(gx, A.N), 256, 0, st>>>(A.soft_colors, A.grad_soft_colors, A.aggrs_info, A.pack_area, SS);
+    else raster_pack_kernel<1><<<dim3(gx, A.N), 256, 0, st>>>(A.soft_colors, A.grad_soft_colors, A.aggrs_info, A.pack_area, SS);
+    if (check_launch("raster_pack_kernel")) return 1;
+    RasterArgs P = A;
+    P.packed = A.pack_area;
+    raster_backward_kernel<true, false, 1, 0, true><<<blocks, LASR_BWD_THREADS, 0, st>>>(P);
+    if (check_launch("raster_backward_kernel<packed>")) return 1;
+    raster_backward_kernel<true, true, 1, 0, true><<<592, 256, 0, st>>>(P);
+    return check_launch("raster_backward_kernel<packed, big>");
+  }
   if (A.packed) {   // the fused region's packed per-pixel gradients (lasr_b200_render_backward_packed: K = 3, set 0 detached)
     raster_backward_kernel<true, false, 3, 1, true><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
     if (check_launch("raster_backward_kernel<packed>")) return 1;

@@ -46,6 +46,7 @@ struct RasterArgs {
   float* soft_colors;        // [N,4,S,S]
   const float* grad_soft_colors;  // [N,4,S,S]   (backward)
   const float4* packed;           // [N][1 + ceil(3*live/4)][S*S] packed per-pixel gradients (backward of the fused region)
+  float4* pack_area;              // workspace room for the single-set backward's own packing pass (raster_pack_kernel)
   float* grad_faces;         // [N,F,9]          (backward)
   float* grad_textures;      // [N,F,T,3]        (backward)
   // workspace carve-up
