@@ -7,23 +7,26 @@
 // (pixel,face) pair (.cu:620-622,657-666).  Here:
 //
 //   setup     one thread per face: derived per-face constants (a 176-byte record), the dilated
-//             bounding box and its packed pixel window (8 B), written once to the workspace; for
-//             large launches also a per-tile face count, from which a one-CTA counting sort lists
-//             the (frame, tile) items heaviest first -- the order the forward's CTAs start in;
+//             bounding box and its packed pixel window (8 B), written once to the workspace -- the records as ONE bulk
+//             store per warp (shared -> global through the TMA unit); for large launches also a per-tile face count,
+//             from which a one-CTA counting sort lists the (frame, tile) items heaviest first -- the order the
+//             forward's CTAs start in;
 //   forward   one CTA per 16x16 pixel tile: (1) the CTA scans the packed windows and compacts the
-//             indices of overlapping faces, in ascending order, into shared memory; (2) each warp
-//             (an 8x4 pixel footprint) then walks that list on its own, culls 32 faces at a time
-//             against its footprint with one ballot and evaluates only the survivors, reading
-//             the face record with warp-uniform 128-bit loads (L1/L2 resident).  Faces are
-//             visited in ascending index, the order the reference's per-pixel loop uses, so the
-//             online depth-softmax and the hard z-test see the same sequence;
-//   backward  one warp per face: the warp sweeps the face's own pixel window, every lane owns a
-//             pixel, the 18 partial derivatives are reduced with a fixed-order warp butterfly and
-//             written once.  No atomics, deterministic, ~2/3 of the lanes do useful work.
+//             indices of overlapping faces, in ascending order, into shared memory; (2) the list is consumed in rounds
+//             of 64 faces through a two-deep shared-memory ring filled by cp.async.bulk copies of the faces' records and
+//             boxes that complete on mbarriers (LASR configuration); (3) each warp (an 8x4 pixel footprint) walks the
+//             staged round on its own, culls 32 faces at a time against its footprint with one ballot and evaluates
+//             only the survivors from LDS broadcasts.  Faces are visited in ascending index, the order the reference's
+//             per-pixel loop uses, so the online depth-softmax and the hard z-test see the same sequence;
+//   backward  one warp per face, a CTA owning a run of consecutive faces: the warp sweeps the face's own (tight) pixel
+//             window, every lane owns a pixel, the 18 partial derivatives are reduced with a fixed-order warp
+//             butterfly and written once.  No atomics, deterministic.  What a pair needs from its pixel arrives either
+//             as ten plane gathers or, packed per pixel by the fused head / raster_pack_kernel, as two or three
+//             coalesced 128-bit loads.
 //
 // Nothing here is GEMM-shaped: no tensor cores.  The kernels are FP32-issue/MUFU bound after
 // binning; HBM traffic is the compulsory 72F+24S^2 / 144F+40S^2 bytes per frame
-// plus the 8F-byte window scratch.
+// plus the per-face scratch, which stays in L2.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
