@@ -410,6 +410,7 @@ class RegionArmBase:
         self.host_arrays = [host[k] for k in order] + [rw["pose"][k] for k in ("Rmat", "Tmat", "ppoint", "scale")]
         self.resident = [dv(a) for a in self.host_arrays]
         self.pending = []
+        self.flow3 = None
         self.eye = torch.tensor(EYE, dtype=torch.float32, device=device)
 
     def launch_count(self):
@@ -428,9 +429,10 @@ class RegionArmBase:
     def step(self, imgs_u8, masks_u8, flow, occ, Rmat, Tmat, ppoint, scale):
         """One forward + backward of the region from device buffers.  Returns (4 losses, *shared-parameter grads)."""
         torch = self.torch
-        flow3 = torch.zeros(flow.shape[0], 3, flow.shape[2], flow.shape[3], device=flow.device)
-        flow3[:, :2] = flow
-        batch = dict(imgs=imgs_u8.float().mul_(1.0 / 255.0), masks=masks_u8.float(), flow=flow3, occ=occ)
+        if self.flow3 is None:        # [N,3,S,S] as the loader lays it out; the validity channel stays zero (never read)
+            self.flow3 = torch.zeros(flow.shape[0], 3, flow.shape[2], flow.shape[3], device=flow.device)
+        self.flow3[:, :2] = flow
+        batch = dict(imgs=torch.mul(imgs_u8, 1.0 / 255.0), masks=masks_u8.float(), flow=self.flow3, occ=occ)
         P = {k: v.detach().requires_grad_(True) for k, v in self.params.items()}
         pose = [t.detach().requires_grad_(True) for t in (Rmat, Tmat, ppoint, scale)]
         losses = self.region(P, pose, batch)

@@ -66,7 +66,7 @@ class RenderHotPath(torch.nn.Module):
         if o.fused and pred_v.is_cuda and o.opt_tex:
             # 1') LBS + camera + projection + depth window in ONE kernel (lasr_b200_lbs_project_forward)
             from . import native_geom
-            pp_rep = ppoint[:, None].repeat(1, H, 1).view(n2 * H, 2)
+            pp_rep = ppoint if H == 1 else ppoint[:, None].repeat(1, H, 1).view(n2 * H, 2)
             cam, px3, (near, far) = native_geom.skin_project(pred_v, Rmat, Tmat, B, skin, pp_rep, scale.view(-1),
                                                              tocam=True, depth_window=True)
             self.renderer_softtex.rasterizer.near, self.renderer_softtex.rasterizer.far = near, far
@@ -160,7 +160,7 @@ class RenderHotPath(torch.nn.Module):
         own = cam                                            # camera-space positions [n2*H,V,3]
         pair = torch.roll(own.view(n2, H, -1, 3), bs, 0).reshape(nh, -1, 3)     # frame i <-> i +- bs
         sets = torch.stack([own, pair, tex.reshape(nh, -1, 3).to(own.dtype)], 0)
-        faces_h = faces[:, None].repeat(1, H, 1, 1).view(-1, faces.shape[1], 3)
+        faces_h = faces if H == 1 else faces[:, None].repeat(1, H, 1, 1).view(-1, faces.shape[1], 3)
         link = sr.functional.PackedGradLink() if (o.packed_grad and torch.is_grad_enabled()) else None
         r.rasterizer.background_color = [0, 0, 0, 0, 0, 0, 1, 1, 1]
         r.rasterizer.detached_sets = 1          # own positions enter the flow only under .detach() (:102-103)
@@ -171,8 +171,9 @@ class RenderHotPath(torch.nn.Module):
             r.rasterizer.background_color = [1, 1, 1]
             r.rasterizer.detached_sets = 0
             r.rasterizer.grad_link = None
-        pp_own = ppoint[:, None].repeat(1, H, 1).view(nh, 2)
-        pp_pair = torch.roll(ppoint, bs, 0)[:, None].repeat(1, H, 1).view(nh, 2)
+        rep = (lambda t: t) if H == 1 else (lambda t: t[:, None].repeat(1, H, 1).view(nh, 2))   # one hypothesis: no copies
+        pp_own = rep(ppoint)
+        pp_pair = rep(torch.roll(ppoint, bs, 0))
         f_own = scale.view(n2, H, -1)[:, :, 0].reshape(nh)
         f_pair = torch.roll(scale.view(n2, H, -1)[:, :, 0], bs, 0).reshape(nh)
         mask_loss, flow_loss, texture_loss, sub, flow_rd, bgmask = L.fused_head(
