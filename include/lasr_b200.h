@@ -88,8 +88,9 @@ int lasr_b200_raster_forward_bg(const float* faces, const float* textures, float
  *                         grad_textures, grad_soft_colors, <same scalars>)
  *   grad_faces    [N,F,9]    out (overwritten; the reference accumulates into a zeroed buffer)
  *   grad_textures [N,F,T,3]  out (overwritten)
- * Deterministic: every face's gradient is a private, fixed-order sum (no float atomics, unlike
- * .cu:606,622,657-666). */
+ * Deterministic for 'vertex' textures (LASR's mode): every face's gradient is a private, fixed-order sum (no
+ * float atomics, unlike .cu:606,622,657-666).  'surface' texel gradients are still scattered with atomicAdd
+ * (several faces' pixels never share a texel, but several pixels of one face do). */
 int lasr_b200_raster_backward(const float* faces, const float* textures, const float* soft_colors,
                               const float* aggrs_info, float* grad_faces, float* grad_textures,
                               const float* grad_soft_colors, void* workspace,
