@@ -8,12 +8,14 @@ frame shares one topology, which is how LASR calls it (faces repeated per frame,
 nnutils/mesh_net.py:77,357)."""
 from __future__ import annotations
 
+import sys
+
 import numpy as np
 import torch
 from torch.autograd import Function
 
 from ... import _cabi
-from .soft_rasterize import ALPHA_FUNCS, DIST_FUNCS, RGB_FUNCS, _near_far
+from .soft_rasterize import ALPHA_FUNCS, DIST_FUNCS, RGB_FUNCS, SoftRasterizeFunction, _near_far
 
 import weakref
 
@@ -120,7 +122,12 @@ class RenderIndexedFunction(Function):
         # the adjacency is looked up here, where `tri` is the caller's (cached) tensor object; the backward
         # only sees re-wrapped saved tensors
         offsets, entries = vertex_adjacency(tri, V)
-        ctx.save_for_backward(v, c, tri, img, aggrs, ws, offsets, entries)
+        # (the package re-exports the FUNCTION soft_rasterize under the module's name: fetch the module itself)
+        ctx.keep_ws = bool(sys.modules[SoftRasterizeFunction.__module__].KEEP_WORKSPACE)
+        if ctx.keep_ws:
+            ctx.save_for_backward(v, c, tri, img, aggrs, ws, offsets, entries)
+        else:
+            ctx.save_for_backward(v, c, tri, img, aggrs, offsets, entries)
         ctx.shapes = (vertices.shape, vcolors.shape)
         ctx.grad_link = grad_link
         if grad_link is not None:
@@ -131,7 +138,11 @@ class RenderIndexedFunction(Function):
 
     @staticmethod
     def backward(ctx, grad):
-        v, c, tri, img, aggrs, ws, offsets, entries = ctx.saved_tensors
+        if ctx.keep_ws:
+            v, c, tri, img, aggrs, ws, offsets, entries = ctx.saved_tensors
+        else:
+            v, c, tri, img, aggrs, offsets, entries = ctx.saved_tensors
+            ws = _cabi.render_workspace(v.shape[0], tri.shape[0], ctx.S, v.device, 1 if c.dim() == 3 else int(c.shape[0]))
         N, V = v.shape[:2]
         gv, gc = torch.empty_like(v), torch.empty_like(c)
         link = ctx.grad_link
@@ -141,10 +152,10 @@ class RenderIndexedFunction(Function):
                                    "other than the fused head; render without grad_link for that")
             packed, link.packed, link.placeholder = link.packed, None, None
             _cabi.render_backward_packed(v, tri, c, packed, offsets, entries, gv, gc, ws, ctx.S, ctx.near, ctx.far,
-                                         ctx.nf, *ctx.scal, setup_done=True, detached_sets=ctx.detached)
+                                         ctx.nf, *ctx.scal, setup_done=ctx.keep_ws, detached_sets=ctx.detached)
         else:
             _cabi.render_backward(v, tri, c, img, aggrs, grad.float().contiguous(), offsets, entries, gv, gc, ws, ctx.S,
-                                  ctx.near, ctx.far, ctx.nf, *ctx.scal, setup_done=True, detached_sets=ctx.detached)
+                                  ctx.near, ctx.far, ctx.nf, *ctx.scal, setup_done=ctx.keep_ws, detached_sets=ctx.detached)
         vshape, cshape = ctx.shapes
         return (gv.reshape(vshape), gc.reshape(cshape)) + (None,) * 15
 

@@ -13,11 +13,19 @@ Differences a caller can observe, all deliberate:
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 from torch.autograd import Function
 
 from ... import _cabi
+
+# Keep the forward's per-face scratch (200 B per face: windows, boxes, records) alive for the backward, as the reference
+# keeps its `faces_info` (108 B per face, soft_rasterize.py:64,71).  False: nothing but the op's own inputs and outputs is
+# saved and the backward recomputes the records (`setup_done=0`): 0 B per face kept, a few per cent slower backward
+# (profiles/r2/README.md).  Read at forward time; LASR_B200_KEEP_WORKSPACE=0 in the environment sets the default.
+KEEP_WORKSPACE = os.environ.get("LASR_B200_KEEP_WORKSPACE", "1") != "0"
 
 DIST_FUNCS = {"hard": 0, "barycentric": 1, "euclidean": 2}
 RGB_FUNCS = {"hard": 0, "softmax": 1}
@@ -71,12 +79,20 @@ class SoftRasterizeFunction(Function):
                              eps, sigma_val, ctx.func_dist_type, ctx.dist_eps, gamma_val, ctx.func_rgb_type,
                              ctx.func_alpha_type, ctx.texture_type, ctx.fill_back,
                              background=[float(background_color[k]) for k in range(3)])
-        ctx.save_for_backward(fv, tex, soft_colors, aggrs_info, workspace)   # workspace plays the reference's faces_info
+        ctx.keep_ws = bool(KEEP_WORKSPACE)
+        if ctx.keep_ws:
+            ctx.save_for_backward(fv, tex, soft_colors, aggrs_info, workspace)   # workspace plays the reference's faces_info
+        else:
+            ctx.save_for_backward(fv, tex, soft_colors, aggrs_info)
         return soft_colors
 
     @staticmethod
     def backward(ctx, grad_soft_colors):
-        fv, tex, soft_colors, aggrs_info, workspace = ctx.saved_tensors
+        if ctx.keep_ws:
+            fv, tex, soft_colors, aggrs_info, workspace = ctx.saved_tensors
+        else:
+            fv, tex, soft_colors, aggrs_info = ctx.saved_tensors
+            workspace = _cabi.raster_workspace(fv.shape[0], fv.shape[1], ctx.image_size, fv.device)
         nb, nf = fv.shape[:2]
         S = ctx.image_size
         grad_faces = torch.empty_like(fv)
@@ -85,7 +101,7 @@ class SoftRasterizeFunction(Function):
         _cabi.raster_backward(fv, tex, soft_colors, aggrs_info, grad_faces, grad_textures, g, workspace, S,
                               ctx.near, ctx.far, ctx.near_far_dev, ctx.eps, ctx.sigma_val, ctx.func_dist_type,
                               ctx.dist_eps, ctx.gamma_val, ctx.func_rgb_type, ctx.func_alpha_type, ctx.texture_type,
-                              ctx.fill_back, setup_done=True)
+                              ctx.fill_back, setup_done=ctx.keep_ws)
         fshape, tshape = ctx.in_shapes
         return (grad_faces.reshape(fshape), grad_textures.reshape(tshape)) + (None,) * 13
 

@@ -367,6 +367,34 @@ def test_background_as_argument_equals_prefilled_image(srf):
         assert float(out[:, 3].min()) < 1e-3 and float((out[:, 0] == bg[0]).float().mean()) > 0.05   # background pixels exist
 
 
+def test_dropping_the_saved_workspace_changes_no_gradient(srf, monkeypatch):
+    """functional.soft_rasterize.KEEP_WORKSPACE = False: nothing but the op's inputs and outputs is kept from forward to
+    backward (0 B per face instead of 200; the reference keeps 108), the backward recomputes the per-face records --
+    the same arithmetic, so the same bits, through both Functions."""
+    mod = sys.modules[srf.SoftRasterizeFunction.__module__]      # the module (the package re-exports the function under its name)
+    from lasr_b200 import synth
+    c = cases.lasr_case("bumpy2", 2, 96)
+    kept = run_ours(srf, c)
+    dev = torch.device("cuda", 0)
+    v, f = synth.bumpy_sphere(2, 0.5)
+    px, cam, near, far = synth.render_inputs(v, f, 2)
+    tri = torch.from_numpy(f).int().to(dev)
+
+    def indexed():
+        verts = torch.from_numpy(px).to(dev).requires_grad_(True)
+        cols = torch.from_numpy(np.repeat(synth.vertex_colors(len(v))[None], 2, 0)).to(dev).requires_grad_(True)
+        img = srf.render_indexed(verts, cols, tri, image_size=96, near=near, far=far, sigma_val=1e-4, gamma_val=1e-2)
+        img.backward(torch.ones_like(img) * 1e-3)
+        return img.detach(), verts.grad, cols.grad
+
+    kept_idx = indexed()
+    monkeypatch.setattr(mod, "KEEP_WORKSPACE", False)
+    dropped = run_ours(srf, c)
+    dropped_idx = indexed()
+    assert all(np.array_equal(a, b) for a, b in zip(kept, dropped))
+    assert all(torch.equal(a, b) for a, b in zip(kept_idx, dropped_idx))
+
+
 def test_anti_aliasing_and_forward_entry_point(srf, oracle):
     """SoftRasterizer(anti_aliasing=True) renders at 2x and average-pools (rasterizer.py:43,52-53);
     SoftRenderer.forward(vertices, faces, textures) builds the Mesh itself (renderer.py:99-101)."""
