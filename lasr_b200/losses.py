@@ -137,6 +137,9 @@ class _FusedHead(Function):
         gf = torch.empty(N * H, dtype=torch.float32, device=dev)
         link = ctx.grad_link
         if link is not None:
+            if link.aggrs is None:
+                raise RuntimeError("fused_head(grad_link=...): the link was not attached to the render that produced this "
+                                   "image (pass the same PackedGradLink to render_indexed)")
             # packed per-pixel gradient for the rasterizer's backward; autograd carries a zero-stride placeholder
             link.packed = torch.empty(N * H, 3, S * S, 4, dtype=torch.float32, device=dev)
             _cabi.head_backward_packed(img, po, pq, fo, fq, im, mk, oc, fl, gsums, link.aggrs, link.packed, gpp, gf,
