@@ -293,13 +293,35 @@ extern "C" int lasr_host_forward_sets(const float* faces9, const float* tex, int
   return 0;
 }
 
-template <int K, int KF>
+// kPacked: what a pair reads from its pixel is first packed per pixel the way raster_pack_kernel (one colour set) and
+// head_backward_kernel<packed> (three sets, the first detached) lay it out on the GPU -- planes [1 + ceil(3 live / 4)][S*S]
+// of float4: { g_alpha (1 - alpha), sum over live colour planes of g_k image_k, 1 / softmax sum, softmax max }, then the
+// live g_k -- and the pair code runs its packed branch.
+template <int K, int KF, bool kPacked = false>
 static void host_backward_sets(const float* faces9, const float* tex, int F, int S, float near_, float far_, float sigma,
                                float gamma, float eps, float dist_eps, const float* soft_colors, const float* aggrs,
                                const float* grad_soft_colors, float* grad_faces, float* grad_tex) {
   constexpr bool kFast = true;
   constexpr int kMode = 1, P = 3 * K + 1;
-  constexpr bool kPacked = false; const float4* pk = nullptr; (void)pk;
+  constexpr int kPlanes = 1 + (3 * (K - KF) + 3) / 4;
+  float4* pk_buf = nullptr;
+  if (kPacked) {
+    const size_t SSz = (size_t)S * S;
+    pk_buf = new float4[(size_t)kPlanes * SSz];
+    for (size_t p = 0; p < SSz; ++p) {
+      float gk[4 * (kPlanes - 1)] = {0};
+      float T = 0.f;
+      for (int k = 3 * KF; k < 3 * K; ++k) {
+        gk[k - 3 * KF] = grad_soft_colors[k * SSz + p];
+        T += gk[k - 3 * KF] * soft_colors[k * SSz + p];
+      }
+      pk_buf[p] = make_float4(grad_soft_colors[(P - 1) * SSz + p] * (1.f - soft_colors[(P - 1) * SSz + p]), T,
+                              fast_rcp<kMode>(aggrs[p]), aggrs[SSz + p]);
+      for (int j = 0; j < kPlanes - 1; ++j)
+        pk_buf[(1 + j) * SSz + p] = make_float4(gk[4 * j], gk[4 * j + 1], gk[4 * j + 2], gk[4 * j + 3]);
+    }
+  }
+  const float4* pk = pk_buf; (void)pk;
   RasterArgs A{};
   fill_mode_args(A, F, S, 3, near_, far_, sigma, gamma, eps, dist_eps, 2, 1, 2, 1, 1, nullptr);
   A.K = K;
@@ -331,6 +353,24 @@ static void host_backward_sets(const float* faces9, const float* tex, int F, int
     for (int k = 0; k < 9; ++k) grad_faces[9 * f + k] = gf[k];
     for (int k = 0; k < 9 * (K - KF); ++k) gtex_out[k] = gt[k];
   }
+  delete[] pk_buf;
+}
+
+// the packed branch of the pair code for the two instantiations the library launches it with: K = 1 (raster_pack_kernel
+// feeding the single-set backward) and K = 3 with the first set detached (the fused region)
+extern "C" int lasr_host_backward_packed(const float* faces9, const float* tex, int F, int S, int K, int KF, float near_,
+                                         float far_, float sigma, float gamma, float eps, float dist_eps,
+                                         const float* soft_colors, const float* aggrs, const float* grad_soft_colors,
+                                         float* grad_faces, float* grad_tex) {
+  if (K == 1 && KF == 0)
+    host_backward_sets<1, 0, true>(faces9, tex, F, S, near_, far_, sigma, gamma, eps, dist_eps, soft_colors, aggrs,
+                                   grad_soft_colors, grad_faces, grad_tex);
+  else if (K == 3 && KF == 1)
+    host_backward_sets<3, 1, true>(faces9, tex, F, S, near_, far_, sigma, gamma, eps, dist_eps, soft_colors, aggrs,
+                                   grad_soft_colors, grad_faces, grad_tex);
+  else
+    return 1;
+  return 0;
 }
 
 extern "C" int lasr_host_backward_sets(const float* faces9, const float* tex, int F, int S, int K, int KF, float near_,

@@ -203,7 +203,7 @@ def test_generic_pair_code_run_on_the_host_reproduces_the_reference_kernels(libs
 
 
 # ---- several colour sets riding one geometry pass (K = 2, 3), on the host ---------------------------------------------
-@pytest.mark.parametrize("K", [2, 3])
+@pytest.mark.parametrize("K", [1, 2, 3])
 def test_colour_set_kernels_on_the_host_equal_separate_passes(libs, K):
     """forward_pair<true, K> / the backward body with K colour sets (and a detached first set, KF = 1) against K separate
     single-set passes of the same code: image planes and colour gradients bit-identical per set, the silhouette and the
@@ -234,7 +234,7 @@ def test_colour_set_kernels_on_the_host_equal_separate_passes(libs, K):
         assert np.array_equal(im1[3].view(np.uint32), img[3 * K].view(np.uint32))
         assert np.array_equal(ag1.view(np.uint32), agg.view(np.uint32))
         singles.append((t1, im1, ag1))
-    for KF in (0, 1):
+    for KF in ((0,) if K == 1 else (0, 1)):
         gf = np.zeros((F, 9), np.float32); gt = np.zeros((F, 9 * K), np.float32)
         assert L.lasr_host_backward_sets(P(fv), P(texK), I(F), I(S), I(K), I(KF), *scal, P(img), P(agg), P(gimg), P(gf), P(gt)) == 0
         gf_sum = np.zeros((F, 9), np.float64)
@@ -254,6 +254,15 @@ def test_colour_set_kernels_on_the_host_equal_separate_passes(libs, K):
                 assert np.array_equal(got.view(np.uint32), b.view(np.uint32)), (KF, k)
         scale = np.abs(gf_sum).max()
         assert scale > 0 and np.abs(gf - gf_sum).max() < 2e-5 * scale, (KF, np.abs(gf - gf_sum).max(), scale)
+        # the PACKED branch of the pair code (per-pixel float4s as raster_pack_kernel / head_backward_kernel<packed> write
+        # them) in the two instantiations the library launches: same colour gradients bit for bit (they do not depend
+        # on the re-associated sum), vertex gradients up to sum_k g_k (c_k - image_k) = sum_k g_k c_k - T
+        if (K, KF) in ((1, 0), (3, 1)):
+            pf = np.zeros((F, 9), np.float32); pt = np.zeros((F, 9 * K), np.float32)
+            assert L.lasr_host_backward_packed(P(fv), P(texK), I(F), I(S), I(K), I(KF), *scal, P(img), P(agg), P(gimg), P(pf), P(pt)) == 0
+            assert np.array_equal(pt.view(np.uint32), gt.view(np.uint32)), (K, KF)
+            assert np.abs(pf - gf).max() < 2e-5 * np.abs(gf).max(), (K, KF, np.abs(pf - gf).max(), np.abs(gf).max())
+            assert L.lasr_host_backward_packed(P(fv), P(texK), I(F), I(S), I(2), I(0), *scal, P(img), P(agg), P(gimg), P(pf), P(pt)) == 1
 
 
 @pytest.mark.parametrize("S", [7, 64, 256, 513, 2048, 8192])
