@@ -198,6 +198,27 @@ int lasr_b200_lbs_project_backward(const float* verts, const float* Rmat, const 
                                    int num_frames, int num_vertices, int num_bones,
                                    int verts_shared, int skin_shared, int tocam, void* stream);
 
+/* The same two calls with the part transforms COMPOSED ABOUT THEIR REST POSITIONS inside the kernels
+ * (nnutils/mesh_net.py:278-281: Tmat[:,1:] = -Rmat[:,1:] rest + Tmat[:,1:] + rest; Rmat[:,1:] transposed), which the
+ * reference does with ~8 small PyTorch kernels forward and ~20 backward per step:
+ *   rest_ts   [n_hypo*(B-1), 3]  joint centres, shared by the frames (frame n uses hypothesis n % n_hypo)
+ *   Rmat/Tmat the RAW network outputs (mesh_net.py:259-260), bone 0 the body transform, used as given
+ *   grad_R / grad_T are gradients w.r.t. those raw inputs; grad_rest [N, B-1, 3] is per frame (the caller sums the
+ *   frames of a hypothesis). */
+int lasr_b200_lbs_pose_forward(const float* verts, const float* Rmat, const float* Tmat,
+                               const float* rest_ts, const float* skin, const float* pp, const float* fl,
+                               float* cam, float* px, float* near_far_dev, void* workspace,
+                               size_t workspace_bytes, int N, int V, int B, int n_hypo, int verts_shared,
+                               int skin_shared, int tocam, void* stream);
+
+int lasr_b200_lbs_pose_backward(const float* verts, const float* Rmat, const float* Tmat,
+                                const float* rest_ts, const float* skin, const float* pp, const float* fl,
+                                const float* grad_cam, const float* grad_px, float* grad_verts,
+                                float* grad_R, float* grad_T, float* grad_rest, float* grad_skin,
+                                float* grad_pp, float* grad_fl, void* workspace, size_t workspace_bytes,
+                                int N, int V, int B, int n_hypo, int verts_shared, int skin_shared,
+                                int tocam, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Image losses: one fused masked-reduction pass.  Replaces the Python double
  * loops of nnutils/mesh_net.py:372-447 (silhouette :374-390, flow :393-416, texture L1 :420-441;

@@ -24,7 +24,7 @@ _RASTER_SCALARS = [_c.c_int, _c.c_int, _c.c_int, _c.c_int,      # N, F, S, T
                    _c.c_int, _c.c_int, _c.c_int, _c.c_int]       # rgb, alpha, sample, double_side
 
 
-EXPECTED_ABI = 6     # include/lasr_b200.h; bumped whenever an entry point's argument list changes
+EXPECTED_ABI = 7     # include/lasr_b200.h; bumped whenever an entry point's argument list changes
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -132,6 +132,10 @@ def _load_locked():
         L.lasr_b200_lbs_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_lbs_project_forward.restype = _c.c_int
         L.lasr_b200_lbs_project_forward.argtypes = [_c.c_void_p] * 10 + [_c.c_size_t] + [_c.c_int] * 6 + [_c.c_void_p]
+        L.lasr_b200_lbs_pose_forward.restype = _c.c_int
+        L.lasr_b200_lbs_pose_forward.argtypes = [_c.c_void_p] * 11 + [_c.c_size_t] + [_c.c_int] * 7 + [_c.c_void_p]
+        L.lasr_b200_lbs_pose_backward.restype = _c.c_int
+        L.lasr_b200_lbs_pose_backward.argtypes = [_c.c_void_p] * 17 + [_c.c_size_t] + [_c.c_int] * 7 + [_c.c_void_p]
         L.lasr_b200_lbs_project_backward.restype = _c.c_int
         L.lasr_b200_lbs_project_backward.argtypes = [_c.c_void_p] * 15 + [_c.c_size_t] + [_c.c_int] * 6 + [_c.c_void_p]
         _lib = L
@@ -148,6 +152,7 @@ EXPORTED_SYMBOLS = [
     "lasr_b200_losses_finalize", "lasr_b200_losses_coefficients",
     "lasr_b200_flow_epilogue_workspace_bytes", "lasr_b200_flow_epilogue_forward", "lasr_b200_flow_epilogue_backward",
     "lasr_b200_lbs_workspace_bytes", "lasr_b200_lbs_project_forward", "lasr_b200_lbs_project_backward",
+    "lasr_b200_lbs_pose_forward", "lasr_b200_lbs_pose_backward",
     "lasr_b200_head_workspace_bytes", "lasr_b200_head_forward", "lasr_b200_head_backward",
     "lasr_b200_skin_workspace_bytes", "lasr_b200_skin_weights_forward", "lasr_b200_skin_weights_backward",
     "lasr_b200_meshreg_workspace_bytes", "lasr_b200_laplacian_forward", "lasr_b200_laplacian_backward",
@@ -270,6 +275,36 @@ def lbs_project_backward(verts, Rmat, Tmat, skin, pp, fl, grad_cam, grad_px, gra
                                                   workspace.numel(), N, V, B, int(verts_shared), int(skin_shared),
                                                   int(tocam), _stream_ptr())
     _check(rc, "lasr_b200_lbs_project_backward")
+
+
+def lbs_pose_forward(verts, Rmat, Tmat, rest_ts, skin, pp, fl, cam, px, near_far, workspace, N, V, B, n_hypo,
+                     verts_shared, skin_shared, tocam):
+    for t, nm in ((verts, "verts"), (Rmat, "Rmat"), (Tmat, "Tmat"), (rest_ts, "rest_ts"), (skin, "skin"), (cam, "cam")):
+        _require_cuda_f32(t, nm)
+    for t, nm in ((pp, "pp"), (fl, "fl"), (px, "px"), (near_far, "near_far")):
+        if t is not None:
+            _require_cuda_f32(t, nm)
+    with torch.cuda.device(verts.device):
+        rc = lib().lasr_b200_lbs_pose_forward(_p(verts), _p(Rmat), _p(Tmat), _p(rest_ts), _p(skin), _p(pp), _p(fl),
+                                              _p(cam), _p(px), _p(near_far), _p(workspace), workspace.numel(), N, V, B,
+                                              int(n_hypo), int(verts_shared), int(skin_shared), int(tocam), _stream_ptr())
+    _check(rc, "lasr_b200_lbs_pose_forward")
+
+
+def lbs_pose_backward(verts, Rmat, Tmat, rest_ts, skin, pp, fl, grad_cam, grad_px, grad_verts, grad_R, grad_T, grad_rest,
+                      grad_skin, grad_pp, grad_fl, workspace, N, V, B, n_hypo, verts_shared, skin_shared, tocam):
+    for t in (verts, Rmat, Tmat, rest_ts, skin, grad_verts, grad_R, grad_T, grad_rest):
+        _require_cuda_f32(t, "lbs tensor")
+    for t in (pp, fl, grad_cam, grad_px, grad_skin, grad_pp, grad_fl):
+        if t is not None:
+            _require_cuda_f32(t, "lbs tensor")
+    with torch.cuda.device(verts.device):
+        rc = lib().lasr_b200_lbs_pose_backward(_p(verts), _p(Rmat), _p(Tmat), _p(rest_ts), _p(skin), _p(pp), _p(fl),
+                                               _p(grad_cam), _p(grad_px), _p(grad_verts), _p(grad_R), _p(grad_T),
+                                               _p(grad_rest), _p(grad_skin), _p(grad_pp), _p(grad_fl), _p(workspace),
+                                               workspace.numel(), N, V, B, int(n_hypo), int(verts_shared),
+                                               int(skin_shared), int(tocam), _stream_ptr())
+    _check(rc, "lasr_b200_lbs_pose_backward")
 
 
 def render_workspace(N: int, F: int, S: int, device, num_sets: int = 1) -> torch.Tensor:

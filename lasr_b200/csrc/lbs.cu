@@ -39,7 +39,34 @@ struct LbsArgs {
   unsigned* zminmax;    // [2] order-preserving encodings of min / max z (null: skip)
   int N, V, B;
   int verts_shared, skin_shared, tocam;
+  // Optional composition of the part transforms about their rest positions (nnutils/mesh_net.py:278-281), done while the
+  // frame's bones are staged in shared memory instead of by ~30 small PyTorch kernels per step:
+  //   R'_k = R_k^T,   T'_k = -R_k rest_k + T_k + rest_k      (k >= 1; the body transform k = 0 is used as given)
+  const float* rest;    // [n_hypo*(B-1), 3] joint centres, shared by the frames; null: Rmat / Tmat are used as given
+  int n_hypo;           // frames are laid out [.., n_hypo]: frame n uses the bones of hypothesis n % n_hypo
 };
+
+// the frame's B transforms -> shared memory, [B][12]: R (9, row-major) then T (3)
+__device__ __forceinline__ void stage_bones(const LbsArgs& A, int n, float* s_rt, int nthreads) {
+  for (int i = threadIdx.x; i < A.B * 12; i += nthreads) {
+    const int k = i / 12, j = i % 12;
+    const float* R = A.Rmat + ((long long)n * A.B + k) * 9;
+    const float* T = A.Tmat + ((long long)n * A.B + k) * 3;
+    float val;
+    if (A.rest == nullptr || k == 0) {
+      val = j < 9 ? R[j] : T[j - 9];
+    } else {
+      const float* q = A.rest + ((long long)(n % A.n_hypo) * (A.B - 1) + (k - 1)) * 3;
+      if (j < 9) {
+        val = R[(j % 3) * 3 + j / 3];
+      } else {
+        const int c = j - 9;
+        val = (-(R[3 * c] * q[0] + R[3 * c + 1] * q[1] + R[3 * c + 2] * q[2]) + T[c]) + q[c];
+      }
+    }
+    s_rt[i] = val;
+  }
+}
 
 // order-preserving float <-> uint encoding for atomicMin/atomicMax
 __device__ __forceinline__ unsigned enc(float f) {
@@ -67,10 +94,7 @@ __global__ void __launch_bounds__(kLbsThreads) lbs_forward_kernel(LbsArgs A) {
   extern __shared__ float s_rt[];  // [B][12]: R (9, row-major) then T (3)
   const int n = blockIdx.y;
   const int v = blockIdx.x * kLbsThreads + threadIdx.x;
-  for (int i = threadIdx.x; i < A.B * 12; i += kLbsThreads) {
-    const int k = i / 12, j = i % 12;
-    s_rt[i] = j < 9 ? A.Rmat[((long long)n * A.B + k) * 9 + j] : A.Tmat[((long long)n * A.B + k) * 3 + (j - 9)];
-  }
+  stage_bones(A, n, s_rt, kLbsThreads);
   __syncthreads();
   float z = 0.f;
   const bool active = v < A.V;
@@ -162,10 +186,7 @@ __global__ void __launch_bounds__(kLbsThreads) lbs_backward_kernel(LbsBwdArgs G)
   const LbsArgs& A = G.f;
   const int n = blockIdx.y;
   const int v = blockIdx.x * kLbsThreads + threadIdx.x;
-  for (int i = threadIdx.x; i < A.B * 12; i += kLbsThreads) {
-    const int k = i / 12, j = i % 12;
-    s_rt[i] = j < 9 ? A.Rmat[((long long)n * A.B + k) * 9 + j] : A.Tmat[((long long)n * A.B + k) * 3 + (j - 9)];
-  }
+  stage_bones(A, n, s_rt, kLbsThreads);
   __syncthreads();
   const bool active = v < A.V;
   float x0 = 0.f, y0 = 0.f, z0 = 0.f;
@@ -270,19 +291,41 @@ __global__ void __launch_bounds__(kLbsThreads) lbs_backward_kernel(LbsBwdArgs G)
   }
 }
 
-// sum the block partials in block order -> grad_R [N,B,9], grad_T [N,B,3], grad_pp [N,2], grad_fl [N]
+// sum the block partials in block order -> grad_R [N,B,9], grad_T [N,B,3], grad_pp [N,2], grad_fl [N].
+// With composed part transforms (rest != null) the sums are gradients of (R', T') and are carried to the raw inputs here:
+//   g_R_k[b][a] = g_R'_k[a][b] - g_T'_k[b] rest_k[a],   g_T_k = g_T'_k,   g_rest_k[c] = g_T'_k[c] - sum_i R_k[i][c] g_T'_k[i]
+// (g_rest per frame, [N,B-1,3]; the caller sums the frames of a hypothesis).
 __global__ void lbs_reduce_partials_kernel(const float* partial, int nblk, int N, int B, float* grad_R, float* grad_T,
-                                           float* grad_pp, float* grad_fl) {
+                                           float* grad_pp, float* grad_fl, const float* Rmat, const float* rest,
+                                           int n_hypo, float* grad_rest) {
   const int per = B * 12 + 3;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * per) return;
   const int n = (int)(i / per), j = (int)(i % per);
-  float t = 0.f;
-  for (int b = 0; b < nblk; ++b) t += partial[((long long)n * nblk + b) * per + j];
+  auto total = [&](int elem) {
+    float t = 0.f;
+    for (int b = 0; b < nblk; ++b) t += partial[((long long)n * nblk + b) * per + elem];
+    return t;
+  };
+  const float t = total(j);
   if (j < B * 12) {
     const int k = j / 12, e = j % 12;
-    if (e < 9) grad_R[((long long)n * B + k) * 9 + e] = t;
-    else grad_T[((long long)n * B + k) * 3 + (e - 9)] = t;
+    if (rest == nullptr || k == 0) {
+      if (e < 9) grad_R[((long long)n * B + k) * 9 + e] = t;
+      else grad_T[((long long)n * B + k) * 3 + (e - 9)] = t;
+    } else {
+      const float* q = rest + ((long long)(n % n_hypo) * (B - 1) + (k - 1)) * 3;
+      if (e < 9) {
+        const int a = e / 3, b = e % 3;
+        grad_R[((long long)n * B + k) * 9 + 3 * b + a] = t - total(k * 12 + 9 + b) * q[a];
+      } else {
+        const int c = e - 9;
+        grad_T[((long long)n * B + k) * 3 + c] = t;
+        const float* R = Rmat + ((long long)n * B + k) * 9;
+        const float g0 = total(k * 12 + 9), g1 = total(k * 12 + 10), g2 = total(k * 12 + 11);
+        grad_rest[((long long)n * (B - 1) + (k - 1)) * 3 + c] = t - (R[c] * g0 + R[3 + c] * g1 + R[6 + c] * g2);
+      }
+    }
   } else if (j - B * 12 < 2) {
     if (grad_pp) grad_pp[2 * n + (j - B * 12)] = t;
   } else if (grad_fl) {
@@ -301,6 +344,7 @@ static int fill_lbs(LbsArgs& A, const float* verts, const float* Rmat, const flo
   A.verts = verts; A.Rmat = Rmat; A.Tmat = Tmat; A.skin = skin; A.pp = pp; A.fl = fl;
   A.N = N; A.V = V; A.B = B;
   A.verts_shared = verts_shared; A.skin_shared = skin_shared; A.tocam = tocam;
+  A.rest = nullptr; A.n_hypo = 1;
   return 0;
 }
 
@@ -314,13 +358,16 @@ extern "C" size_t lasr_b200_lbs_workspace_bytes(int N, int V, int B) {
   return 256 + (size_t)N * nblk * ((size_t)B * 12 + 3) * sizeof(float);
 }
 
-extern "C" int lasr_b200_lbs_project_forward(const float* verts, const float* Rmat, const float* Tmat,
-                                             const float* skin, const float* pp, const float* fl, float* cam,
-                                             float* px, float* near_far_dev, void* workspace,
-                                             size_t workspace_bytes, int N, int V, int B, int verts_shared,
-                                             int skin_shared, int tocam, void* stream) {
+static int lbs_forward_impl(const float* verts, const float* Rmat, const float* Tmat, const float* rest, int n_hypo,
+                            const float* skin, const float* pp, const float* fl, float* cam, float* px,
+                            float* near_far_dev, void* workspace, size_t workspace_bytes, int N, int V, int B,
+                            int verts_shared, int skin_shared, int tocam, void* stream) {
   LbsArgs A{};
   if (fill_lbs(A, verts, Rmat, Tmat, skin, pp, fl, N, V, B, verts_shared, skin_shared, tocam)) return 1;
+  if (rest) {
+    if (n_hypo <= 0 || N % n_hypo != 0) return lasr_fail("lbs_pose: n_hypo must divide the frame count");
+    A.rest = rest; A.n_hypo = n_hypo;
+  }
   if (!cam) return lasr_fail("lbs_project_forward: cam output required");
   if (pp && !px) return lasr_fail("lbs_project_forward: px output required when projecting");
   A.cam = cam; A.px = pp ? px : nullptr;
@@ -341,15 +388,36 @@ extern "C" int lasr_b200_lbs_project_forward(const float* verts, const float* Rm
   return 0;
 }
 
-extern "C" int lasr_b200_lbs_project_backward(const float* verts, const float* Rmat, const float* Tmat,
-                                              const float* skin, const float* pp, const float* fl,
-                                              const float* grad_cam, const float* grad_px, float* grad_verts,
-                                              float* grad_R, float* grad_T, float* grad_skin, float* grad_pp,
-                                              float* grad_fl, void* workspace, size_t workspace_bytes, int N,
-                                              int V, int B, int verts_shared, int skin_shared, int tocam,
-                                              void* stream) {
+extern "C" int lasr_b200_lbs_project_forward(const float* verts, const float* Rmat, const float* Tmat,
+                                             const float* skin, const float* pp, const float* fl, float* cam,
+                                             float* px, float* near_far_dev, void* workspace,
+                                             size_t workspace_bytes, int N, int V, int B, int verts_shared,
+                                             int skin_shared, int tocam, void* stream) {
+  return lbs_forward_impl(verts, Rmat, Tmat, nullptr, 1, skin, pp, fl, cam, px, near_far_dev, workspace, workspace_bytes, N,
+                          V, B, verts_shared, skin_shared, tocam, stream);
+}
+
+extern "C" int lasr_b200_lbs_pose_forward(const float* verts, const float* Rmat, const float* Tmat, const float* rest_ts,
+                                          const float* skin, const float* pp, const float* fl, float* cam, float* px,
+                                          float* near_far_dev, void* workspace, size_t workspace_bytes, int N, int V,
+                                          int B, int n_hypo, int verts_shared, int skin_shared, int tocam, void* stream) {
+  if (!rest_ts || B < 2) return lasr_fail("lbs_pose_forward: rest_ts and at least one part are required");
+  return lbs_forward_impl(verts, Rmat, Tmat, rest_ts, n_hypo, skin, pp, fl, cam, px, near_far_dev, workspace,
+                          workspace_bytes, N, V, B, verts_shared, skin_shared, tocam, stream);
+}
+
+static int lbs_backward_impl(const float* verts, const float* Rmat, const float* Tmat, const float* rest, int n_hypo,
+                             const float* skin, const float* pp, const float* fl, const float* grad_cam,
+                             const float* grad_px, float* grad_verts, float* grad_R, float* grad_T, float* grad_rest,
+                             float* grad_skin, float* grad_pp, float* grad_fl, void* workspace, size_t workspace_bytes,
+                             int N, int V, int B, int verts_shared, int skin_shared, int tocam, void* stream) {
   LbsBwdArgs G{};
   if (fill_lbs(G.f, verts, Rmat, Tmat, skin, pp, fl, N, V, B, verts_shared, skin_shared, tocam)) return 1;
+  if (rest) {
+    if (n_hypo <= 0 || N % n_hypo != 0) return lasr_fail("lbs_pose: n_hypo must divide the frame count");
+    if (!grad_rest) return lasr_fail("lbs_pose_backward: grad_rest output required");
+    G.f.rest = rest; G.f.n_hypo = n_hypo;
+  }
   if (!grad_verts || !grad_R || !grad_T) return lasr_fail("lbs_project_backward: null gradient output");
   if (!grad_cam && !grad_px) return lasr_fail("lbs_project_backward: no upstream gradient");
   if (grad_px && !pp) return lasr_fail("lbs_project_backward: grad_px without a projection");
@@ -364,6 +432,31 @@ extern "C" int lasr_b200_lbs_project_backward(const float* verts, const float* R
   if (lasr_check_launch("lbs_backward_kernel")) return 1;
   const long long tot = (long long)N * (B * 12 + 3);
   lbs_reduce_partials_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(G.partial, G.nblk, N, B, grad_R, grad_T,
-                                                                            grad_pp, grad_fl);
+                                                                            grad_pp, grad_fl, Rmat, rest, n_hypo, grad_rest);
   return lasr_check_launch("lbs_reduce_partials_kernel");
+}
+
+extern "C" int lasr_b200_lbs_project_backward(const float* verts, const float* Rmat, const float* Tmat,
+                                              const float* skin, const float* pp, const float* fl,
+                                              const float* grad_cam, const float* grad_px, float* grad_verts,
+                                              float* grad_R, float* grad_T, float* grad_skin, float* grad_pp,
+                                              float* grad_fl, void* workspace, size_t workspace_bytes, int N,
+                                              int V, int B, int verts_shared, int skin_shared, int tocam,
+                                              void* stream) {
+  return lbs_backward_impl(verts, Rmat, Tmat, nullptr, 1, skin, pp, fl, grad_cam, grad_px, grad_verts, grad_R, grad_T,
+                           nullptr, grad_skin, grad_pp, grad_fl, workspace, workspace_bytes, N, V, B, verts_shared,
+                           skin_shared, tocam, stream);
+}
+
+extern "C" int lasr_b200_lbs_pose_backward(const float* verts, const float* Rmat, const float* Tmat,
+                                           const float* rest_ts, const float* skin, const float* pp, const float* fl,
+                                           const float* grad_cam, const float* grad_px, float* grad_verts,
+                                           float* grad_R, float* grad_T, float* grad_rest, float* grad_skin,
+                                           float* grad_pp, float* grad_fl, void* workspace, size_t workspace_bytes,
+                                           int N, int V, int B, int n_hypo, int verts_shared, int skin_shared,
+                                           int tocam, void* stream) {
+  if (!rest_ts || B < 2) return lasr_fail("lbs_pose_backward: rest_ts and at least one part are required");
+  return lbs_backward_impl(verts, Rmat, Tmat, rest_ts, n_hypo, skin, pp, fl, grad_cam, grad_px, grad_verts, grad_R,
+                           grad_T, grad_rest, grad_skin, grad_pp, grad_fl, workspace, workspace_bytes, N, V, B,
+                           verts_shared, skin_shared, tocam, stream);
 }

@@ -61,17 +61,24 @@ class RenderHotPath(torch.nn.Module):
         n2 = ppoint.shape[0]          # 2 * bs
         bs = n2 // 2
         fused_route = o.fused and pred_v.is_cuda and o.opt_tex
-        # the fused LBS kernel reads one shared [1,B-1,V] weight table; every other route gets the per-frame repeat
-        skin, Rmat, Tmat = self.bone_transforms(pred_v, Rmat, Tmat, bones, n2, repeat_skin=not (fused_route and H == 1))
-        if o.fused and pred_v.is_cuda and o.opt_tex:
-            # 1') LBS + camera + projection + depth window in ONE kernel (lasr_b200_lbs_project_forward)
+        if fused_route:
+            # 1') bone composition + LBS + camera + projection + depth window in ONE kernel (lasr_b200_lbs_pose_forward /
+            #     lasr_b200_lbs_project_forward): the raw part transforms go in, the joint centres ride along
             from . import native_geom
+            skin = rest = None
+            if B > 1:
+                skin = gu.skin_weights(bones["ctl_ts"], bones["ctl_rs"], bones["log_ctl"],
+                                       pred_v.view(n2, H, -1, 3)[0].detach(), H)
+                if H > 1:                      # the kernel reads one shared [1,B-1,V] table only when there is one hypothesis
+                    skin = skin.repeat(n2, 1, 1, 1)
+                rest = bones["rest_ts"]
             pp_rep = ppoint if H == 1 else ppoint[:, None].repeat(1, H, 1).view(n2 * H, 2)
             cam, px3, (near, far) = native_geom.skin_project(pred_v, Rmat, Tmat, B, skin, pp_rep, scale.view(-1),
-                                                             tocam=True, depth_window=True)
+                                                             tocam=True, depth_window=True, rest_ts=rest, n_hypo=H)
             self.renderer_softtex.rasterizer.near, self.renderer_softtex.rasterizer.far = near, far
             self.renderer_softtex.rasterizer.sigma_val = o.sigval
             return self._forward_fused(cam, px3, tex, faces, ppoint, scale, batch, shared_faces, near, far)
+        skin, Rmat, Tmat = self.bone_transforms(pred_v, Rmat, Tmat, bones, n2)
         # 1) LBS + camera (mesh_net.py:298-311)
         cam = gu.obj_to_cam(pred_v, Rmat, Tmat[:, None, :], B, H, skin)
         verts_fl = torch.cat([cam, torch.ones_like(cam[:, :, :1])], dim=-1)

@@ -181,3 +181,49 @@ def test_native_skin_weights_match_the_reference_expression(H, Bp, V):
     # deterministic
     s2, g2 = run(torch.device("cuda", 0), torch.float32)
     assert torch.equal(s2, s_gpu) and all(torch.equal(x, y) for x, y in zip(g2, g_gpu))
+
+
+@pytest.mark.parametrize("H,B,V", [(1, 4, 300), (2, 3, 77), (1, 26, 2930)])
+def test_bone_composition_inside_the_lbs_kernel_equals_the_pytorch_composition(dev, H, B, V):
+    """lasr_b200_lbs_pose_forward / backward (skin_project(rest_ts=...)): the part transforms are composed about their rest
+    positions while the frame's bones are staged in shared memory (mesh_net.py:278-281: T' = -R rest + T + rest, R' = R^T).
+    Against the same kernels fed the composition done in PyTorch (RenderHotPath.bone_transforms): positions, depth window
+    and the gradient of every input, the joint centres included."""
+    from lasr_b200 import hotpath, native_geom
+    from lasr_b200.geom_utils import quaternion_to_rotation_matrix
+    g = torch.Generator().manual_seed(B * 7 + H)
+    n2 = 4
+    N = n2 * H
+    leaves = dict(
+        verts=torch.randn(N, V, 3, generator=g) * 0.3,
+        R=quaternion_to_rotation_matrix(torch.randn(N * B, 4, generator=g)),
+        T=torch.randn(N * B, 3, generator=g) * 0.05,
+        rest=torch.randn(H * (B - 1), 3, generator=g) * 0.3,
+        skin=torch.softmax(torch.randn(N, B - 1, V, 1, generator=g), 1),
+        pp=torch.randn(N, 2, generator=g) * 0.05, fl=9.5 + torch.rand(N, generator=g))
+    leaves["T"].view(N, B, 3)[:, 0, 2] += 8.0
+    gc, gp = torch.randn(N, V, 3, generator=g).to(dev), torch.randn(N, V, 4, generator=g).to(dev)
+
+    def run(in_kernel):
+        L = {k: v.clone().to(dev).requires_grad_(True) for k, v in leaves.items()}
+        if in_kernel:
+            cam, px, (near, far) = native_geom.skin_project(L["verts"], L["R"], L["T"], B, L["skin"], L["pp"], L["fl"],
+                                                            depth_window=True, rest_ts=L["rest"], n_hypo=H)
+        else:
+            m = hotpath.RenderHotPath(hotpath.HotPathOptions(n_hypo=H, n_bones=B))
+            bones = dict(rest_ts=L["rest"])
+            rest = bones["rest_ts"][:, None, :, None].repeat(n2, 1, 1, 1).view(-1, B - 1, 3, 1)
+            R4, T4 = L["R"].view(-1, B, 3, 3), L["T"].view(-1, B, 3, 1)
+            Tm = torch.cat([T4[:, :1], -R4[:, 1:].matmul(rest) + T4[:, 1:] + rest], 1).view(-1, 3)
+            Rm = torch.cat([R4[:, :1], R4[:, 1:].permute(0, 1, 3, 2)], 1).reshape(-1, 3, 3)
+            cam, px, (near, far) = native_geom.skin_project(L["verts"], Rm, Tm, B, L["skin"], L["pp"], L["fl"],
+                                                            depth_window=True)
+        torch.autograd.backward([cam, px], [gc, gp])
+        return cam.detach(), px.detach(), float(near), float(far), {k: v.grad for k, v in L.items()}
+
+    a, b = run(True), run(False)
+    assert float((a[0] - b[0]).abs().max()) < 2e-6 and float((a[1] - b[1]).abs().max()) < 2e-5
+    assert abs(a[2] - b[2]) < 1e-5 and abs(a[3] - b[3]) < 1e-5
+    for k in leaves:
+        err = float((a[4][k] - b[4][k]).norm() / b[4][k].norm())
+        assert err < 2e-5, (k, err)
