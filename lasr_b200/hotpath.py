@@ -61,9 +61,10 @@ class RenderHotPath(torch.nn.Module):
         n2 = ppoint.shape[0]          # 2 * bs
         bs = n2 // 2
         fused_route = o.fused and pred_v.is_cuda and o.opt_tex
-        if fused_route:
+        if pred_v.is_cuda:
             # 1') bone composition + LBS + camera + projection + depth window in ONE kernel (lasr_b200_lbs_pose_forward /
-            #     lasr_b200_lbs_project_forward): the raw part transforms go in, the joint centres ride along
+            #     lasr_b200_lbs_project_forward): the raw part transforms go in, the joint centres ride along.  Both CUDA
+            #     routes pose the mesh this way, so they rasterize bit-identical vertices.
             from . import native_geom
             skin = rest = None
             if B > 1:
@@ -73,19 +74,22 @@ class RenderHotPath(torch.nn.Module):
                     skin = skin.repeat(n2, 1, 1, 1)
                 rest = bones["rest_ts"]
             pp_rep = ppoint if H == 1 else ppoint[:, None].repeat(1, H, 1).view(n2 * H, 2)
-            cam, px3, (near, far) = native_geom.skin_project(pred_v, Rmat, Tmat, B, skin, pp_rep, scale.view(-1),
-                                                             tocam=True, depth_window=True, rest_ts=rest, n_hypo=H)
-            self.renderer_softtex.rasterizer.near, self.renderer_softtex.rasterizer.far = near, far
-            self.renderer_softtex.rasterizer.sigma_val = o.sigval
-            return self._forward_fused(cam, px3, tex, faces, ppoint, scale, batch, shared_faces, near, far)
-        skin, Rmat, Tmat = self.bone_transforms(pred_v, Rmat, Tmat, bones, n2)
-        # 1) LBS + camera (mesh_net.py:298-311)
-        cam = gu.obj_to_cam(pred_v, Rmat, Tmat[:, None, :], B, H, skin)
-        verts_fl = torch.cat([cam, torch.ones_like(cam[:, :, :1])], dim=-1)
+            cam, verts_px, (near, far) = native_geom.skin_project(pred_v, Rmat, Tmat, B, skin, pp_rep, scale.view(-1),
+                                                                  tocam=True, depth_window=True, rest_ts=rest, n_hypo=H)
+            if fused_route:
+                self.renderer_softtex.rasterizer.near, self.renderer_softtex.rasterizer.far = near, far
+                self.renderer_softtex.rasterizer.sigma_val = o.sigval
+                return self._forward_fused(cam, verts_px, tex, faces, ppoint, scale, batch, shared_faces, near, far)
+            verts_fl = torch.cat([cam, torch.ones_like(cam[:, :, :1])], dim=-1)
+        else:
+            skin, Rmat, Tmat = self.bone_transforms(pred_v, Rmat, Tmat, bones, n2)
+            # 1) LBS + camera (mesh_net.py:298-311)
+            cam = gu.obj_to_cam(pred_v, Rmat, Tmat[:, None, :], B, H, skin)
+            verts_fl = torch.cat([cam, torch.ones_like(cam[:, :, :1])], dim=-1)
+            verts_px = gu.pinhole_cam(verts_fl, ppoint, scale)
+            near, far = gu.depth_window(verts_px[:, :, 2])
         verts_pos0 = verts_fl.view(n2, H, -1, 4)[:bs].reshape(bs * H, -1, 4)
         verts_pos1 = verts_fl.view(n2, H, -1, 4)[bs:].reshape(bs * H, -1, 4)
-        verts_px = gu.pinhole_cam(verts_fl, ppoint, scale)
-        near, far = gu.depth_window(verts_px[:, :, 2])
         for r in (self.renderer_softflf, self.renderer_softflb, self.renderer_softtex):
             r.rasterizer.near, r.rasterizer.far = near, far
             r.rasterizer.sigma_val = o.sigval
