@@ -198,26 +198,31 @@ int lasr_b200_lbs_project_backward(const float* verts, const float* Rmat, const 
                                    int num_frames, int num_vertices, int num_bones,
                                    int verts_shared, int skin_shared, int tocam, void* stream);
 
-/* The same two calls with the part transforms COMPOSED ABOUT THEIR REST POSITIONS inside the kernels
- * (nnutils/mesh_net.py:278-281: Tmat[:,1:] = -Rmat[:,1:] rest + Tmat[:,1:] + rest; Rmat[:,1:] transposed), which the
- * reference does with ~8 small PyTorch kernels forward and ~20 backward per step:
- *   rest_ts   [n_hypo*(B-1), 3]  joint centres, shared by the frames (frame n uses hypothesis n % n_hypo)
- *   Rmat/Tmat the RAW network outputs (mesh_net.py:259-260), bone 0 the body transform, used as given
- *   grad_R / grad_T are gradients w.r.t. those raw inputs; grad_rest [N, B-1, 3] is per frame (the caller sums the
- *   frames of a hypothesis). */
+/* The general pose entry points: lasr_b200_lbs_project_* plus two optional pieces of LASR's per-step glue done inside
+ * the kernels.
+ * (1) rest_ts != NULL: the part transforms are COMPOSED ABOUT THEIR REST POSITIONS (nnutils/mesh_net.py:278-281:
+ *     Tmat[:,1:] = -Rmat[:,1:] rest + Tmat[:,1:] + rest; Rmat[:,1:] transposed), which the reference does with ~8 small
+ *     PyTorch kernels forward and ~20 backward per step:
+ *       rest_ts   [n_hypo*(B-1), 3]  joint centres, shared by the frames (frame n uses hypothesis n % n_hypo)
+ *       Rmat/Tmat the RAW network outputs (mesh_net.py:259-260), bone 0 the body transform, used as given
+ *       grad_R / grad_T are gradients w.r.t. those raw inputs; grad_rest [N, B-1, 3] is per frame (the caller sums the
+ *       frames of a hypothesis).
+ * (2) view != NULL: a third output [N,V,3], the projected vertex as LASR hands it to the rasterizer -- + eye offset,
+ *     y flip, then SoftRenderer's look_at(eye) with the eye at (0, 0, eye_z) and orthographic scale 1
+ *     (mesh_net.py:81-83,354-357; transform.py:41-48): (x, -y, (z + eye_z) - eye_z); grad_view is its upstream gradient. */
 int lasr_b200_lbs_pose_forward(const float* verts, const float* Rmat, const float* Tmat,
                                const float* rest_ts, const float* skin, const float* pp, const float* fl,
-                               float* cam, float* px, float* near_far_dev, void* workspace,
-                               size_t workspace_bytes, int N, int V, int B, int n_hypo, int verts_shared,
-                               int skin_shared, int tocam, void* stream);
+                               float* cam, float* px, float* view, float eye_z, float* near_far_dev,
+                               void* workspace, size_t workspace_bytes, int N, int V, int B, int n_hypo,
+                               int verts_shared, int skin_shared, int tocam, void* stream);
 
 int lasr_b200_lbs_pose_backward(const float* verts, const float* Rmat, const float* Tmat,
                                 const float* rest_ts, const float* skin, const float* pp, const float* fl,
-                                const float* grad_cam, const float* grad_px, float* grad_verts,
-                                float* grad_R, float* grad_T, float* grad_rest, float* grad_skin,
-                                float* grad_pp, float* grad_fl, void* workspace, size_t workspace_bytes,
-                                int N, int V, int B, int n_hypo, int verts_shared, int skin_shared,
-                                int tocam, void* stream);
+                                const float* grad_cam, const float* grad_px, const float* grad_view,
+                                float* grad_verts, float* grad_R, float* grad_T, float* grad_rest,
+                                float* grad_skin, float* grad_pp, float* grad_fl, void* workspace,
+                                size_t workspace_bytes, int N, int V, int B, int n_hypo, int verts_shared,
+                                int skin_shared, int tocam, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Image losses: one fused masked-reduction pass.  Replaces the Python double

@@ -133,9 +133,10 @@ def _load_locked():
         L.lasr_b200_lbs_project_forward.restype = _c.c_int
         L.lasr_b200_lbs_project_forward.argtypes = [_c.c_void_p] * 10 + [_c.c_size_t] + [_c.c_int] * 6 + [_c.c_void_p]
         L.lasr_b200_lbs_pose_forward.restype = _c.c_int
-        L.lasr_b200_lbs_pose_forward.argtypes = [_c.c_void_p] * 11 + [_c.c_size_t] + [_c.c_int] * 7 + [_c.c_void_p]
+        L.lasr_b200_lbs_pose_forward.argtypes = ([_c.c_void_p] * 10 + [_c.c_float, _c.c_void_p, _c.c_void_p, _c.c_size_t]
+                                                 + [_c.c_int] * 7 + [_c.c_void_p])
         L.lasr_b200_lbs_pose_backward.restype = _c.c_int
-        L.lasr_b200_lbs_pose_backward.argtypes = [_c.c_void_p] * 17 + [_c.c_size_t] + [_c.c_int] * 7 + [_c.c_void_p]
+        L.lasr_b200_lbs_pose_backward.argtypes = [_c.c_void_p] * 18 + [_c.c_size_t] + [_c.c_int] * 7 + [_c.c_void_p]
         L.lasr_b200_lbs_project_backward.restype = _c.c_int
         L.lasr_b200_lbs_project_backward.argtypes = [_c.c_void_p] * 15 + [_c.c_size_t] + [_c.c_int] * 6 + [_c.c_void_p]
         _lib = L
@@ -277,33 +278,35 @@ def lbs_project_backward(verts, Rmat, Tmat, skin, pp, fl, grad_cam, grad_px, gra
     _check(rc, "lasr_b200_lbs_project_backward")
 
 
-def lbs_pose_forward(verts, Rmat, Tmat, rest_ts, skin, pp, fl, cam, px, near_far, workspace, N, V, B, n_hypo,
+def lbs_pose_forward(verts, Rmat, Tmat, rest_ts, skin, pp, fl, cam, px, view, eye_z, near_far, workspace, N, V, B, n_hypo,
                      verts_shared, skin_shared, tocam):
-    for t, nm in ((verts, "verts"), (Rmat, "Rmat"), (Tmat, "Tmat"), (rest_ts, "rest_ts"), (skin, "skin"), (cam, "cam")):
+    for t, nm in ((verts, "verts"), (Rmat, "Rmat"), (Tmat, "Tmat"), (cam, "cam")):
         _require_cuda_f32(t, nm)
-    for t, nm in ((pp, "pp"), (fl, "fl"), (px, "px"), (near_far, "near_far")):
+    for t, nm in ((rest_ts, "rest_ts"), (skin, "skin"), (pp, "pp"), (fl, "fl"), (px, "px"), (view, "view"),
+                  (near_far, "near_far")):
         if t is not None:
             _require_cuda_f32(t, nm)
     with torch.cuda.device(verts.device):
         rc = lib().lasr_b200_lbs_pose_forward(_p(verts), _p(Rmat), _p(Tmat), _p(rest_ts), _p(skin), _p(pp), _p(fl),
-                                              _p(cam), _p(px), _p(near_far), _p(workspace), workspace.numel(), N, V, B,
-                                              int(n_hypo), int(verts_shared), int(skin_shared), int(tocam), _stream_ptr())
+                                              _p(cam), _p(px), _p(view), float(eye_z), _p(near_far), _p(workspace),
+                                              workspace.numel(), N, V, B, int(n_hypo), int(verts_shared),
+                                              int(skin_shared), int(tocam), _stream_ptr())
     _check(rc, "lasr_b200_lbs_pose_forward")
 
 
-def lbs_pose_backward(verts, Rmat, Tmat, rest_ts, skin, pp, fl, grad_cam, grad_px, grad_verts, grad_R, grad_T, grad_rest,
-                      grad_skin, grad_pp, grad_fl, workspace, N, V, B, n_hypo, verts_shared, skin_shared, tocam):
-    for t in (verts, Rmat, Tmat, rest_ts, skin, grad_verts, grad_R, grad_T, grad_rest):
+def lbs_pose_backward(verts, Rmat, Tmat, rest_ts, skin, pp, fl, grad_cam, grad_px, grad_view, grad_verts, grad_R, grad_T,
+                      grad_rest, grad_skin, grad_pp, grad_fl, workspace, N, V, B, n_hypo, verts_shared, skin_shared, tocam):
+    for t in (verts, Rmat, Tmat, grad_verts, grad_R, grad_T):
         _require_cuda_f32(t, "lbs tensor")
-    for t in (pp, fl, grad_cam, grad_px, grad_skin, grad_pp, grad_fl):
+    for t in (rest_ts, skin, pp, fl, grad_cam, grad_px, grad_view, grad_rest, grad_skin, grad_pp, grad_fl):
         if t is not None:
             _require_cuda_f32(t, "lbs tensor")
     with torch.cuda.device(verts.device):
         rc = lib().lasr_b200_lbs_pose_backward(_p(verts), _p(Rmat), _p(Tmat), _p(rest_ts), _p(skin), _p(pp), _p(fl),
-                                               _p(grad_cam), _p(grad_px), _p(grad_verts), _p(grad_R), _p(grad_T),
-                                               _p(grad_rest), _p(grad_skin), _p(grad_pp), _p(grad_fl), _p(workspace),
-                                               workspace.numel(), N, V, B, int(n_hypo), int(verts_shared),
-                                               int(skin_shared), int(tocam), _stream_ptr())
+                                               _p(grad_cam), _p(grad_px), _p(grad_view), _p(grad_verts), _p(grad_R),
+                                               _p(grad_T), _p(grad_rest), _p(grad_skin), _p(grad_pp), _p(grad_fl),
+                                               _p(workspace), workspace.numel(), N, V, B, int(n_hypo),
+                                               int(verts_shared), int(skin_shared), int(tocam), _stream_ptr())
     _check(rc, "lasr_b200_lbs_pose_backward")
 
 

@@ -44,6 +44,11 @@ struct LbsArgs {
   //   R'_k = R_k^T,   T'_k = -R_k rest_k + T_k + rest_k      (k >= 1; the body transform k = 0 is used as given)
   const float* rest;    // [n_hypo*(B-1), 3] joint centres, shared by the frames; null: Rmat / Tmat are used as given
   int n_hypo;           // frames are laid out [.., n_hypo]: frame n uses the bones of hypothesis n % n_hypo
+  // Optional third output: the projected vertex as LASR hands it to the rasterizer -- + eye offset, y flip, then the
+  // renderer's look_at(eye) with the eye on the z axis (mesh_net.py:81-83, 354-357; transform.py:41-48): (x, -y, (z + e) - e),
+  // the float additions kept so that the values are the PyTorch chain's bit for bit (three small kernels forward, four back).
+  float* view;          // [N, V, 3] or null
+  float eye_z;
 };
 
 // the frame's B transforms -> shared memory, [B][12]: R (9, row-major) then T (3)
@@ -126,8 +131,12 @@ __global__ void __launch_bounds__(kLbsThreads) lbs_forward_kernel(LbsArgs A) {
     z = cz;
     if (A.px) {
       const float f = A.fl[n];   // same operation order as the reference: pp + (x * f) / z  (geom_utils.py:32-33)
-      reinterpret_cast<float4*>(A.px)[(long long)n * A.V + v] =
-          make_float4(A.pp[2 * n] + __fdiv_rn(cx * f, cz), A.pp[2 * n + 1] + __fdiv_rn(cy * f, cz), cz, 1.f);
+      const float ux = A.pp[2 * n] + __fdiv_rn(cx * f, cz), uy = A.pp[2 * n + 1] + __fdiv_rn(cy * f, cz);
+      reinterpret_cast<float4*>(A.px)[(long long)n * A.V + v] = make_float4(ux, uy, cz, 1.f);
+      if (A.view) {
+        float* vo = A.view + ((long long)n * A.V + v) * 3;
+        vo[0] = ux; vo[1] = -uy; vo[2] = __fsub_rn(__fadd_rn(cz, A.eye_z), A.eye_z);
+      }
     }
   }
   if (A.zminmax) {
@@ -148,6 +157,7 @@ struct LbsBwdArgs {
   LbsArgs f;
   const float* grad_cam;  // [N,V,3] or null
   const float* grad_px;   // [N,V,4] or null
+  const float* grad_view; // [N,V,3] or null: gradient of the render-space output (f.view)
   float* grad_verts;      // [N,V,3]  (per frame; the caller sums frames for a shared mesh)
   float* grad_skin;       // [N,B-1,V] (per frame) or null
   float* partial;         // [N][nblk][B*12 + 3]  block partials of (R,T) per bone and (pp_x, pp_y, f)
@@ -213,7 +223,7 @@ __global__ void __launch_bounds__(kLbsThreads) lbs_backward_kernel(LbsBwdArgs G)
       const float* g = G.grad_cam + ((long long)n * A.V + v) * 3;
       gcx = g[0]; gcy = g[1]; gcz = g[2];
     }
-    if (G.grad_px) {
+    if (G.grad_px || G.grad_view) {
       const float* r = s_rt;
       float cx = sx, cy = sy, cz = sz;
       if (A.tocam) {
@@ -221,7 +231,12 @@ __global__ void __launch_bounds__(kLbsThreads) lbs_backward_kernel(LbsBwdArgs G)
         cy = sx * r[1] + sy * r[4] + sz * r[7] + r[10];
         cz = sx * r[2] + sy * r[5] + sz * r[8] + r[11];
       }
-      const float4 g = reinterpret_cast<const float4*>(G.grad_px)[(long long)n * A.V + v];
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (G.grad_px) g = reinterpret_cast<const float4*>(G.grad_px)[(long long)n * A.V + v];
+      if (G.grad_view) {                                   // view = (x, -y, (z + e) - e)
+        const float* gv = G.grad_view + ((long long)n * A.V + v) * 3;
+        g.x += gv[0]; g.y -= gv[1]; g.z += gv[2];
+      }
       const float f = A.fl[n];
       const float iz = 1.f / cz;
       const float s = (g.x * cx + g.y * cy) * iz;   // (g_x X + g_y Y) / Z
@@ -344,7 +359,7 @@ static int fill_lbs(LbsArgs& A, const float* verts, const float* Rmat, const flo
   A.verts = verts; A.Rmat = Rmat; A.Tmat = Tmat; A.skin = skin; A.pp = pp; A.fl = fl;
   A.N = N; A.V = V; A.B = B;
   A.verts_shared = verts_shared; A.skin_shared = skin_shared; A.tocam = tocam;
-  A.rest = nullptr; A.n_hypo = 1;
+  A.rest = nullptr; A.n_hypo = 1; A.view = nullptr; A.eye_z = 0.f;
   return 0;
 }
 
@@ -359,9 +374,9 @@ extern "C" size_t lasr_b200_lbs_workspace_bytes(int N, int V, int B) {
 }
 
 static int lbs_forward_impl(const float* verts, const float* Rmat, const float* Tmat, const float* rest, int n_hypo,
-                            const float* skin, const float* pp, const float* fl, float* cam, float* px,
-                            float* near_far_dev, void* workspace, size_t workspace_bytes, int N, int V, int B,
-                            int verts_shared, int skin_shared, int tocam, void* stream) {
+                            const float* skin, const float* pp, const float* fl, float* cam, float* px, float* view,
+                            float eye_z, float* near_far_dev, void* workspace, size_t workspace_bytes, int N, int V,
+                            int B, int verts_shared, int skin_shared, int tocam, void* stream) {
   LbsArgs A{};
   if (fill_lbs(A, verts, Rmat, Tmat, skin, pp, fl, N, V, B, verts_shared, skin_shared, tocam)) return 1;
   if (rest) {
@@ -371,6 +386,10 @@ static int lbs_forward_impl(const float* verts, const float* Rmat, const float* 
   if (!cam) return lasr_fail("lbs_project_forward: cam output required");
   if (pp && !px) return lasr_fail("lbs_project_forward: px output required when projecting");
   A.cam = cam; A.px = pp ? px : nullptr;
+  if (view) {
+    if (!pp) return lasr_fail("lbs_pose_forward: the render-space output needs a projection");
+    A.view = view; A.eye_z = eye_z;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (near_far_dev) {
     if (!workspace || workspace_bytes < 256) return lasr_fail("lbs_project_forward: workspace too small");
@@ -393,22 +412,24 @@ extern "C" int lasr_b200_lbs_project_forward(const float* verts, const float* Rm
                                              float* px, float* near_far_dev, void* workspace,
                                              size_t workspace_bytes, int N, int V, int B, int verts_shared,
                                              int skin_shared, int tocam, void* stream) {
-  return lbs_forward_impl(verts, Rmat, Tmat, nullptr, 1, skin, pp, fl, cam, px, near_far_dev, workspace, workspace_bytes, N,
-                          V, B, verts_shared, skin_shared, tocam, stream);
+  return lbs_forward_impl(verts, Rmat, Tmat, nullptr, 1, skin, pp, fl, cam, px, nullptr, 0.f, near_far_dev, workspace,
+                          workspace_bytes, N, V, B, verts_shared, skin_shared, tocam, stream);
 }
 
 extern "C" int lasr_b200_lbs_pose_forward(const float* verts, const float* Rmat, const float* Tmat, const float* rest_ts,
                                           const float* skin, const float* pp, const float* fl, float* cam, float* px,
-                                          float* near_far_dev, void* workspace, size_t workspace_bytes, int N, int V,
-                                          int B, int n_hypo, int verts_shared, int skin_shared, int tocam, void* stream) {
-  if (!rest_ts || B < 2) return lasr_fail("lbs_pose_forward: rest_ts and at least one part are required");
-  return lbs_forward_impl(verts, Rmat, Tmat, rest_ts, n_hypo, skin, pp, fl, cam, px, near_far_dev, workspace,
+                                          float* view, float eye_z, float* near_far_dev, void* workspace,
+                                          size_t workspace_bytes, int N, int V, int B, int n_hypo, int verts_shared,
+                                          int skin_shared, int tocam, void* stream) {
+  if (rest_ts && B < 2) return lasr_fail("lbs_pose_forward: rest_ts needs at least one part");
+  return lbs_forward_impl(verts, Rmat, Tmat, rest_ts, n_hypo, skin, pp, fl, cam, px, view, eye_z, near_far_dev, workspace,
                           workspace_bytes, N, V, B, verts_shared, skin_shared, tocam, stream);
 }
 
 static int lbs_backward_impl(const float* verts, const float* Rmat, const float* Tmat, const float* rest, int n_hypo,
                              const float* skin, const float* pp, const float* fl, const float* grad_cam,
-                             const float* grad_px, float* grad_verts, float* grad_R, float* grad_T, float* grad_rest,
+                             const float* grad_px, const float* grad_view, float* grad_verts, float* grad_R,
+                             float* grad_T, float* grad_rest,
                              float* grad_skin, float* grad_pp, float* grad_fl, void* workspace, size_t workspace_bytes,
                              int N, int V, int B, int verts_shared, int skin_shared, int tocam, void* stream) {
   LbsBwdArgs G{};
@@ -419,11 +440,12 @@ static int lbs_backward_impl(const float* verts, const float* Rmat, const float*
     G.f.rest = rest; G.f.n_hypo = n_hypo;
   }
   if (!grad_verts || !grad_R || !grad_T) return lasr_fail("lbs_project_backward: null gradient output");
-  if (!grad_cam && !grad_px) return lasr_fail("lbs_project_backward: no upstream gradient");
-  if (grad_px && !pp) return lasr_fail("lbs_project_backward: grad_px without a projection");
+  if (!grad_cam && !grad_px && !grad_view) return lasr_fail("lbs_project_backward: no upstream gradient");
+  if ((grad_px || grad_view) && !pp) return lasr_fail("lbs_project_backward: grad_px without a projection");
   if (!workspace || workspace_bytes < lasr_b200_lbs_workspace_bytes(N, V, B))
     return lasr_fail("lbs_project_backward: workspace too small");
-  G.grad_cam = grad_cam; G.grad_px = grad_px; G.grad_verts = grad_verts; G.grad_skin = B > 1 ? grad_skin : nullptr;
+  G.grad_cam = grad_cam; G.grad_px = grad_px; G.grad_view = grad_view; G.grad_verts = grad_verts;
+  G.grad_skin = B > 1 ? grad_skin : nullptr;
   G.nblk = (V + kLbsThreads - 1) / kLbsThreads;
   G.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
   cudaStream_t st = (cudaStream_t)stream;
@@ -443,20 +465,20 @@ extern "C" int lasr_b200_lbs_project_backward(const float* verts, const float* R
                                               float* grad_fl, void* workspace, size_t workspace_bytes, int N,
                                               int V, int B, int verts_shared, int skin_shared, int tocam,
                                               void* stream) {
-  return lbs_backward_impl(verts, Rmat, Tmat, nullptr, 1, skin, pp, fl, grad_cam, grad_px, grad_verts, grad_R, grad_T,
-                           nullptr, grad_skin, grad_pp, grad_fl, workspace, workspace_bytes, N, V, B, verts_shared,
+  return lbs_backward_impl(verts, Rmat, Tmat, nullptr, 1, skin, pp, fl, grad_cam, grad_px, nullptr, grad_verts, grad_R,
+                           grad_T, nullptr, grad_skin, grad_pp, grad_fl, workspace, workspace_bytes, N, V, B, verts_shared,
                            skin_shared, tocam, stream);
 }
 
 extern "C" int lasr_b200_lbs_pose_backward(const float* verts, const float* Rmat, const float* Tmat,
                                            const float* rest_ts, const float* skin, const float* pp, const float* fl,
-                                           const float* grad_cam, const float* grad_px, float* grad_verts,
-                                           float* grad_R, float* grad_T, float* grad_rest, float* grad_skin,
-                                           float* grad_pp, float* grad_fl, void* workspace, size_t workspace_bytes,
-                                           int N, int V, int B, int n_hypo, int verts_shared, int skin_shared,
-                                           int tocam, void* stream) {
-  if (!rest_ts || B < 2) return lasr_fail("lbs_pose_backward: rest_ts and at least one part are required");
-  return lbs_backward_impl(verts, Rmat, Tmat, rest_ts, n_hypo, skin, pp, fl, grad_cam, grad_px, grad_verts, grad_R,
-                           grad_T, grad_rest, grad_skin, grad_pp, grad_fl, workspace, workspace_bytes, N, V, B,
+                                           const float* grad_cam, const float* grad_px, const float* grad_view,
+                                           float* grad_verts, float* grad_R, float* grad_T, float* grad_rest,
+                                           float* grad_skin, float* grad_pp, float* grad_fl, void* workspace,
+                                           size_t workspace_bytes, int N, int V, int B, int n_hypo, int verts_shared,
+                                           int skin_shared, int tocam, void* stream) {
+  if (rest_ts && B < 2) return lasr_fail("lbs_pose_backward: rest_ts needs at least one part");
+  return lbs_backward_impl(verts, Rmat, Tmat, rest_ts, n_hypo, skin, pp, fl, grad_cam, grad_px, grad_view, grad_verts,
+                           grad_R, grad_T, grad_rest, grad_skin, grad_pp, grad_fl, workspace, workspace_bytes, N, V, B,
                            verts_shared, skin_shared, tocam, stream);
 }

@@ -74,12 +74,15 @@ class RenderHotPath(torch.nn.Module):
                     skin = skin.repeat(n2, 1, 1, 1)
                 rest = bones["rest_ts"]
             pp_rep = ppoint if H == 1 else ppoint[:, None].repeat(1, H, 1).view(n2 * H, 2)
-            cam, verts_px, (near, far) = native_geom.skin_project(pred_v, Rmat, Tmat, B, skin, pp_rep, scale.view(-1),
-                                                                  tocam=True, depth_window=True, rest_ts=rest, n_hypo=H)
+            eye_z = self._plain_view_eye_z(self.renderer_softtex) if fused_route else None
+            posed = native_geom.skin_project(pred_v, Rmat, Tmat, B, skin, pp_rep, scale.view(-1), tocam=True,
+                                             depth_window=True, rest_ts=rest, n_hypo=H, view_eye_z=eye_z)
+            cam, verts_px, (near, far) = posed[:3]
             if fused_route:
                 self.renderer_softtex.rasterizer.near, self.renderer_softtex.rasterizer.far = near, far
                 self.renderer_softtex.rasterizer.sigma_val = o.sigval
-                return self._forward_fused(cam, verts_px, tex, faces, ppoint, scale, batch, shared_faces, near, far)
+                return self._forward_fused(cam, verts_px, tex, faces, ppoint, scale, batch, shared_faces, near, far,
+                                           view=posed[3] if eye_z is not None else None)
             verts_fl = torch.cat([cam, torch.ones_like(cam[:, :, :1])], dim=-1)
         else:
             skin, Rmat, Tmat = self.bone_transforms(pred_v, Rmat, Tmat, bones, n2)
@@ -152,7 +155,20 @@ class RenderHotPath(torch.nn.Module):
         Rmat = torch.cat([R4[:, :1], R4[:, 1:].permute(0, 1, 3, 2)], 1).view(-1, 3, 3)
         return skin, Rmat, Tmat
 
-    def _forward_fused(self, cam, verts_px, tex, faces, ppoint, scale, batch, shared_faces, near, far):
+    @staticmethod
+    def _plain_view_eye_z(r):
+        """eye_z when LASR's renderer settings make lighting and camera a fixed map of the projected vertices -- ambient
+        light 1 / directional 0 (textures x 1), look_at from an eye ON the negative z axis, orthographic, scale 1 (mesh_net.py:132-149):
+        +eye, y flip, look_at(eye) is then (x, -y, (z + e) - e), which the LBS kernel writes itself; None otherwise."""
+        t = r.transform.transformer
+        eye = getattr(t, "_eye", None)
+        ok = (r.lighting.is_identity() and r.transform.camera_mode == "look_at" and not t.perspective
+              and t.viewing_scale == 1 and isinstance(eye, (list, tuple)) and len(eye) == 3
+              and float(eye[0]) == 0.0 and float(eye[1]) == 0.0 and float(eye[2]) < 0.0      # (+z eyes mirror x)
+              and not r.rasterizer.anti_aliasing)
+        return float(eye[2]) if ok else None
+
+    def _forward_fused(self, cam, verts_px, tex, faces, ppoint, scale, batch, shared_faces, near, far, view=None):
         """Steps 2-4 of ``forward`` with the mesh rasterized ONCE per frame.  The reference renders every
         posed frame three times with the same geometry and renderer settings but different vertex
         attributes -- flow (own + paired camera-space positions, mesh_net.py:77-87, 318-335) and texture
@@ -165,9 +181,11 @@ class RenderHotPath(torch.nn.Module):
         bs = n2 // 2
         nh = n2 * H
         r = self.renderer_softtex
-        from .soft_renderer.functional.geometry import _const
-        offset = gu._eye_offset(r, verts_px.device)
-        pre = (verts_px[:, :, :3] + offset) * _const([1.0, -1.0, 1.0], verts_px.device)   # y flip (:83), exact
+        pre = None
+        if view is None:
+            from .soft_renderer.functional.geometry import _const
+            offset = gu._eye_offset(r, verts_px.device)
+            pre = (verts_px[:, :, :3] + offset) * _const([1.0, -1.0, 1.0], verts_px.device)   # y flip (:83), exact
         own = cam                                            # camera-space positions [n2*H,V,3]
         pair = torch.roll(own.view(n2, H, -1, 3), bs, 0).reshape(nh, -1, 3)     # frame i <-> i +- bs
         sets = torch.stack([own, pair, tex.reshape(nh, -1, 3).to(own.dtype)], 0)
@@ -177,7 +195,10 @@ class RenderHotPath(torch.nn.Module):
         r.rasterizer.detached_sets = 1          # own positions enter the flow only under .detach() (:102-103)
         r.rasterizer.grad_link = link
         try:
-            image = r.render_mesh(sr.Mesh(pre, faces_h, textures=sets, texture_type="vertex", shared_faces=shared_faces))
+            if view is not None:     # the LBS kernel already wrote what lighting (x 1) and the camera make of the mesh
+                image = r.rasterizer(sr.Mesh(view, faces_h, textures=sets, texture_type="vertex", shared_faces=shared_faces))
+            else:
+                image = r.render_mesh(sr.Mesh(pre, faces_h, textures=sets, texture_type="vertex", shared_faces=shared_faces))
         finally:                                # the renderer is shared state: never leave the K = 3 settings behind
             r.rasterizer.background_color = [1, 1, 1]
             r.rasterizer.detached_sets = 0

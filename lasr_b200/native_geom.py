@@ -21,7 +21,8 @@ class SkinProjectFunction(Function):
     """(verts, Rmat, Tmat, skin, pp, fl) -> (cam [N,V,3], px [N,V,4] or None, near_far [2] or None)."""
 
     @staticmethod
-    def forward(ctx, verts, Rmat, Tmat, skin, pp, fl, nmesh, tocam, want_depth_window, rest_ts=None, n_hypo=1):
+    def forward(ctx, verts, Rmat, Tmat, skin, pp, fl, nmesh, tocam, want_depth_window, rest_ts=None, n_hypo=1,
+                view_eye_z=None):
         N = Rmat.shape[0] // nmesh
         V = verts.shape[1]
         dev = verts.device
@@ -39,32 +40,43 @@ class SkinProjectFunction(Function):
         nf = torch.empty(2, dtype=torch.float32, device=dev) if want_depth_window else None
         ws = _cabi.lbs_workspace(N, V, nmesh, dev)
         vs, ss = _batch_shared(verts_c, N), (sk is not None and _batch_shared(sk, N))
-        rest = None
-        if rest_ts is not None:       # raw part transforms, composed about their rest positions inside the kernel
-            rest = rest_ts.detach().float().reshape(int(n_hypo) * (nmesh - 1), 3).contiguous()
-            _cabi.lbs_pose_forward(verts_c, R, T, rest, sk, ppc, flc, cam, px, nf, ws, N, V, nmesh, n_hypo, vs, ss, tocam)
+        rest = view = None
+        if rest_ts is not None or view_eye_z is not None:
+            # raw part transforms composed about their rest positions inside the kernel, and / or the render-space vertices
+            # (x, -y, (z + eye_z) - eye_z) as a third output
+            if rest_ts is not None:
+                rest = rest_ts.detach().float().reshape(int(n_hypo) * (nmesh - 1), 3).contiguous()
+            if view_eye_z is not None:
+                view = torch.empty(N, V, 3, dtype=torch.float32, device=dev)
+            _cabi.lbs_pose_forward(verts_c, R, T, rest, sk, ppc, flc, cam, px, view, view_eye_z or 0.0, nf, ws, N, V, nmesh,
+                                   n_hypo, vs, ss, tocam)
         else:
             _cabi.lbs_project_forward(verts_c, R, T, sk, ppc, flc, cam, px, nf, ws, N, V, nmesh, vs, ss, tocam)
         ctx.save_for_backward(verts_c, R, T, sk, ppc, flc, rest)
+        ctx.has_view = view is not None
         ctx.meta = (N, V, nmesh, vs, ss, bool(tocam), verts.shape, Rmat.shape, Tmat.shape,
                     None if skin is None else skin.shape, None if pp is None else pp.shape,
                     None if fl is None else fl.shape, int(n_hypo), None if rest_ts is None else rest_ts.shape)
-        outs = [cam, px if project else cam.new_empty(0), nf if want_depth_window else cam.new_empty(0)]
+        outs = [cam, px if project else cam.new_empty(0), nf if want_depth_window else cam.new_empty(0),
+                view if view is not None else cam.new_empty(0)]
         ctx.mark_non_differentiable(outs[2])
         if not project:
             ctx.mark_non_differentiable(outs[1])
+        if view is None:
+            ctx.mark_non_differentiable(outs[3])
         return tuple(outs)
 
     @staticmethod
-    def backward(ctx, g_cam, g_px, _g_nf):
+    def backward(ctx, g_cam, g_px, _g_nf, g_view):
         verts, R, T, sk, pp, fl, rest = ctx.saved_tensors
         N, V, B, vs, ss, tocam, vshape, rshape, tshape, sshape, ppshape, flshape, n_hypo, restshape = ctx.meta
         dev = verts.device
         project = pp is not None
         g_cam = g_cam.float().contiguous() if g_cam is not None else None
         g_px = g_px.float().contiguous() if (project and g_px is not None and g_px.numel()) else None
-        if g_cam is None and g_px is None:
-            return (None,) * 11
+        g_view = g_view.float().contiguous() if (ctx.has_view and g_view is not None and g_view.numel()) else None
+        if g_cam is None and g_px is None and g_view is None:
+            return (None,) * 12
         gv = torch.empty(N, V, 3, dtype=torch.float32, device=dev)
         gR = torch.empty(N * B, 3, 3, dtype=torch.float32, device=dev)
         gT = torch.empty(N * B, 3, dtype=torch.float32, device=dev)
@@ -73,11 +85,12 @@ class SkinProjectFunction(Function):
         gfl = torch.empty(N, dtype=torch.float32, device=dev) if project else None
         ws = _cabi.lbs_workspace(N, V, B, dev)
         g_rest = None
-        if rest is not None:
-            g_rest_f = torch.empty(N, B - 1, 3, dtype=torch.float32, device=dev)
-            _cabi.lbs_pose_backward(verts, R, T, rest, sk, pp, fl, g_cam, g_px, gv, gR, gT, g_rest_f, gs, gpp, gfl, ws,
-                                    N, V, B, n_hypo, vs, ss, tocam)
-            g_rest = g_rest_f.view(N // n_hypo, n_hypo * (B - 1), 3).sum(0).reshape(restshape)   # frames of a hypothesis
+        if rest is not None or g_view is not None:
+            g_rest_f = torch.empty(N, B - 1, 3, dtype=torch.float32, device=dev) if rest is not None else None
+            _cabi.lbs_pose_backward(verts, R, T, rest, sk, pp, fl, g_cam, g_px, g_view, gv, gR, gT, g_rest_f, gs, gpp, gfl,
+                                    ws, N, V, B, n_hypo, vs, ss, tocam)
+            if rest is not None:
+                g_rest = g_rest_f.view(N // n_hypo, n_hypo * (B - 1), 3).sum(0).reshape(restshape)   # frames of a hypothesis
         else:
             _cabi.lbs_project_backward(verts, R, T, sk, pp, fl, g_cam, g_px, gv, gR, gT, gs, gpp, gfl, ws, N, V, B, vs,
                                        ss, tocam)
@@ -88,7 +101,7 @@ class SkinProjectFunction(Function):
         return (gv.reshape(vshape), gR.reshape(rshape), gT.reshape(tshape),
                 gs.reshape(sshape) if gs is not None else None,
                 gpp.reshape(ppshape) if project else None, gfl.reshape(flshape) if project else None,
-                None, None, None, g_rest, None)
+                None, None, None, g_rest, None, None)
 
 
 class SkinWeightsFunction(Function):
@@ -119,14 +132,18 @@ class SkinWeightsFunction(Function):
 
 
 def skin_project(verts, Rmat, Tmat, nmesh, skin=None, pp=None, fl=None, tocam=True, depth_window=False, rest_ts=None,
-                 n_hypo=1):
+                 n_hypo=1, view_eye_z=None):
     """Fused G1+G2+G3.  verts [N or 1,V,3]; Rmat [N*nmesh,3,3]; Tmat [N*nmesh,(1,)3];
     skin [N or 1,nmesh-1,V(,1)]; pp [N,2] and fl [N(,1)] per FRAME (already repeated over hypotheses).
     rest_ts [n_hypo*(nmesh-1),3]: Rmat / Tmat are the RAW part transforms and are composed about these joint centres
     inside the kernel (mesh_net.py:278-281) -- frames laid out [.., n_hypo].
-    Returns (cam [N,V,3], px [N,V,4] or None, (near, far) 0-dim device tensors or None)."""
-    cam, px, nf = SkinProjectFunction.apply(verts, Rmat, Tmat, skin, pp, fl, nmesh, tocam, depth_window, rest_ts, n_hypo)
-    return cam, (px if pp is not None else None), ((nf[0], nf[1]) if depth_window else None)
+    view_eye_z (a float): also return the render-space vertices LASR hands the rasterizer, (x, -y, (z + e) - e) [N,V,3]
+    (eye offset, y flip, look_at of an eye on the z axis: mesh_net.py:81-83, transform.py:41-48) as a fourth value.
+    Returns (cam [N,V,3], px [N,V,4] or None, (near, far) 0-dim device tensors or None[, view])."""
+    cam, px, nf, view = SkinProjectFunction.apply(verts, Rmat, Tmat, skin, pp, fl, nmesh, tocam, depth_window, rest_ts,
+                                                  n_hypo, view_eye_z)
+    out = (cam, (px if pp is not None else None), ((nf[0], nf[1]) if depth_window else None))
+    return out + (view,) if view_eye_z is not None else out
 
 
 def obj_to_cam(verts, Rmat, Tmat, nmesh, skin, tocam=True):

@@ -364,3 +364,41 @@ def test_packed_gradient_link_refuses_a_second_consumer_of_the_image():
                                        obs["imgs"], obs["masks"], obs["occ"], obs["flow"], N, 1, grad_link=link)
     with pytest.raises(RuntimeError, match="other than the fused head"):
         (ml + fl + tl + img.sum()).backward()
+
+
+def test_kernel_written_render_space_vertices_equal_the_pytorch_chain(monkeypatch):
+    """With LASR's renderer settings the chain `+ eye, y flip, look_at(eye)` is the fixed map (x, -y, (z + e) - e); the
+    LBS kernel writes it as a third output and the fused region hands it straight to the rasterizer
+    (RenderHotPath._plain_view_eye_z).  Same losses bit for bit and the same gradients as the PyTorch chain."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from lasr_b200 import hotpath
+    H, B, S = 1, 3, 64
+    pred_v, tex, faces, Rmat, Tmat, ppoint, scale, batch, bones = scenario(H, B, S, seed=7)
+    dev = torch.device("cuda", 0)
+
+    def run():
+        t = lambda x: x.clone().to(dev)
+        leaves = dict(pred_v=t(pred_v), tex=t(tex), Rmat=t(Rmat), Tmat=t(Tmat), ppoint=t(ppoint), scale=t(scale))
+        bn = {k: t(v) for k, v in bones.items()}
+        leaves.update({f"bone_{k}": bn[k] for k in bn})
+        for x in leaves.values():
+            x.requires_grad_(True)
+        m = hotpath.RenderHotPath(hotpath.HotPathOptions(img_size=S, n_hypo=H, n_bones=B, fused=True))
+        assert (hotpath.RenderHotPath._plain_view_eye_z(m.renderer_softtex) is None) == forced_off[0]
+        out = m(leaves["pred_v"], leaves["tex"], t(faces), leaves["Rmat"], leaves["Tmat"], leaves["ppoint"],
+                leaves["scale"], {k: t(v) for k, v in batch.items()}, bn)
+        out["total"].backward()
+        return out, {k: x.grad.detach().cpu() for k, x in leaves.items()}
+
+    forced_off = [False]
+    a_out, a = run()
+    forced_off[0] = True
+    monkeypatch.setattr(hotpath.RenderHotPath, "_plain_view_eye_z", staticmethod(lambda r: None))
+    b_out, b = run()
+    for k in ("total", "mask_loss", "flow_loss", "texture_loss"):
+        assert float(a_out[k]) == float(b_out[k]), k
+    assert torch.equal(a_out["mask_pred"], b_out["mask_pred"])
+    for k in b:
+        err = float((a[k] - b[k]).norm() / b[k].norm())
+        assert err < 1e-6, (k, err)
