@@ -196,6 +196,7 @@ class RenderHotPath(torch.nn.Module):
         r.rasterizer.grad_link = link
         try:
             if view is not None:     # the LBS kernel already wrote what lighting (x 1) and the camera make of the mesh
+                r.set_texture_mode("vertex")
                 image = r.rasterizer(sr.Mesh(view, faces_h, textures=sets, texture_type="vertex", shared_faces=shared_faces))
             else:
                 image = r.render_mesh(sr.Mesh(pre, faces_h, textures=sets, texture_type="vertex", shared_faces=shared_faces))
