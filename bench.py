@@ -597,7 +597,7 @@ def extras_microbench(device, peak_gbs, iters=20):
                            "forward_GBps": loss_fwd_bytes / t_lf / 1e6, "backward_GBps": loss_bwd_bytes / t_lb / 1e6,
                            "forward_frac_of_hbm_peak": loss_fwd_bytes / t_lf / 1e6 / peak_gbs,
                            "backward_frac_of_hbm_peak": loss_bwd_bytes / t_lb / 1e6 / peak_gbs,
-                           "note": "sums + reduce + finalize kernels forward; coefficient + per-pixel kernels backward"}
+                           "note": "two kernels forward (per-pixel sums; reduce + finalize), two backward (coefficients; per-pixel gradients)"}
     # dataloader -> device staging: 16 pairs of 480x854 frames -> 256^2, inputs resident
     from lasr_b200.dataloader.staging import stage_pairs
     P, Hh, Ww = 16, 480, 854

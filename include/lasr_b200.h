@@ -246,6 +246,14 @@ int lasr_b200_losses_forward(const float* mask_pred, const float* flow_rd, const
                              size_t workspace_bytes, int num_frames, int num_hypotheses, int image_size,
                              void* stream);
 
+/* The same plus the scalar step of lasr_b200_losses_finalize in the launch that sums the block partials: sums [N,H,7],
+ * sub [3][N*H] and out3 [3] out (sub and out3 both given or both NULL).  Same bits as the two calls. */
+int lasr_b200_losses_forward_total(const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
+                                   const float* tex, const float* fg, const float* imgs, const float* masks,
+                                   const float* occ, const float* flow_obs, float* sums, float* sub, float* out3,
+                                   float l1tex_wt, void* workspace, size_t workspace_bytes, int num_frames,
+                                   int num_hypotheses, int image_size, void* stream);
+
 int lasr_b200_losses_backward(const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
                               const float* tex, const float* fg, const float* imgs, const float* masks,
                               const float* occ, const float* flow_obs, const float* grad_sums,
@@ -297,6 +305,13 @@ int lasr_b200_head_forward(const float* image, const float* pp_own, const float*
                            const float* masks, const float* occ, const float* flow_obs, float* sums,
                            float* flow_rd, uint8_t* bgmask, void* workspace, size_t workspace_bytes,
                            int N, int H, int image_size, void* stream);
+
+/* head_forward + lasr_b200_losses_finalize, the scalar step riding the partial-sum launch (sub [3][N*H], out3 [3]). */
+int lasr_b200_head_forward_total(const float* image, const float* pp_own, const float* pp_pair,
+                                 const float* f_own, const float* f_pair, const float* imgs,
+                                 const float* masks, const float* occ, const float* flow_obs, float* sums,
+                                 float* sub, float* out3, float l1tex_wt, float* flow_rd, uint8_t* bgmask,
+                                 void* workspace, size_t workspace_bytes, int N, int H, int image_size, void* stream);
 
 int lasr_b200_head_backward(const float* image, const float* pp_own, const float* pp_pair,
                             const float* f_own, const float* f_pair, const float* imgs,

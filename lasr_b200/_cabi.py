@@ -24,7 +24,7 @@ _RASTER_SCALARS = [_c.c_int, _c.c_int, _c.c_int, _c.c_int,      # N, F, S, T
                    _c.c_int, _c.c_int, _c.c_int, _c.c_int]       # rgb, alpha, sample, double_side
 
 
-EXPECTED_ABI = 7     # include/lasr_b200.h; bumped whenever an entry point's argument list changes
+EXPECTED_ABI = 8     # include/lasr_b200.h; bumped whenever an entry point's argument list changes
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -108,6 +108,9 @@ def _load_locked():
         L.lasr_b200_head_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_head_forward.restype = _c.c_int
         L.lasr_b200_head_forward.argtypes = [_c.c_void_p] * 13 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
+        L.lasr_b200_head_forward_total.restype = _c.c_int
+        L.lasr_b200_head_forward_total.argtypes = ([_c.c_void_p] * 12 + [_c.c_float] + [_c.c_void_p] * 3 +
+                                                   [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p])
         L.lasr_b200_head_backward.restype = _c.c_int
         L.lasr_b200_head_backward.argtypes = [_c.c_void_p] * 14 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
         L.lasr_b200_head_backward_packed.restype = _c.c_int
@@ -116,6 +119,9 @@ def _load_locked():
         L.lasr_b200_losses_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         L.lasr_b200_losses_forward.restype = _c.c_int
         L.lasr_b200_losses_forward.argtypes = [_c.c_void_p] * 11 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
+        L.lasr_b200_losses_forward_total.restype = _c.c_int
+        L.lasr_b200_losses_forward_total.argtypes = ([_c.c_void_p] * 12 + [_c.c_float, _c.c_void_p, _c.c_size_t, _c.c_int,
+                                                                            _c.c_int, _c.c_int, _c.c_void_p])
         L.lasr_b200_losses_backward.restype = _c.c_int
         L.lasr_b200_losses_backward.argtypes = [_c.c_void_p] * 14 + [_c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
         L.lasr_b200_losses_finalize.restype = _c.c_int
@@ -149,12 +155,13 @@ EXPORTED_SYMBOLS = [
     "lasr_b200_raster_backward",
     "lasr_b200_render_workspace_bytes", "lasr_b200_render_forward", "lasr_b200_render_backward",
     "lasr_b200_render_backward_packed", "lasr_b200_head_backward_packed",
-    "lasr_b200_losses_workspace_bytes", "lasr_b200_losses_forward", "lasr_b200_losses_backward",
+    "lasr_b200_losses_workspace_bytes", "lasr_b200_losses_forward", "lasr_b200_losses_forward_total",
+    "lasr_b200_losses_backward",
     "lasr_b200_losses_finalize", "lasr_b200_losses_coefficients",
     "lasr_b200_flow_epilogue_workspace_bytes", "lasr_b200_flow_epilogue_forward", "lasr_b200_flow_epilogue_backward",
     "lasr_b200_lbs_workspace_bytes", "lasr_b200_lbs_project_forward", "lasr_b200_lbs_project_backward",
     "lasr_b200_lbs_pose_forward", "lasr_b200_lbs_pose_backward",
-    "lasr_b200_head_workspace_bytes", "lasr_b200_head_forward", "lasr_b200_head_backward",
+    "lasr_b200_head_workspace_bytes", "lasr_b200_head_forward", "lasr_b200_head_forward_total", "lasr_b200_head_backward",
     "lasr_b200_skin_workspace_bytes", "lasr_b200_skin_weights_forward", "lasr_b200_skin_weights_backward",
     "lasr_b200_meshreg_workspace_bytes", "lasr_b200_laplacian_forward", "lasr_b200_laplacian_backward",
     "lasr_b200_arap_forward", "lasr_b200_arap_backward", "lasr_b200_flatten_forward", "lasr_b200_flatten_backward",
@@ -399,13 +406,15 @@ def render_backward_packed(verts, tri, vcolors, packed_grad, csr_offsets, csr_en
     _check(rc, "lasr_b200_render_backward_packed")
 
 
-def losses_forward(mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs, sums, N, H, S):
+def losses_forward(mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs, sums, N, H, S, sub=None, out3=None,
+                   l1tex_wt=0.0):
+    """sums [N,H,7]; with `sub` [3,N,H] and `out3` [3] also the per-pair losses and their means, in the same launches."""
     ws = torch.empty(int(lib().lasr_b200_losses_workspace_bytes(N, H, S)), dtype=torch.uint8, device=mask_pred.device)
     with torch.cuda.device(mask_pred.device):
-        rc = lib().lasr_b200_losses_forward(_p(mask_pred), _p(flow_rd), _p(bgmask), _p(tex), _p(fg), _p(imgs),
-                                            _p(masks), _p(occ), _p(flow_obs), _p(sums), _p(ws), ws.numel(), N, H, S,
-                                            _stream_ptr())
-    _check(rc, "lasr_b200_losses_forward")
+        rc = lib().lasr_b200_losses_forward_total(_p(mask_pred), _p(flow_rd), _p(bgmask), _p(tex), _p(fg), _p(imgs),
+                                                  _p(masks), _p(occ), _p(flow_obs), _p(sums), _p(sub), _p(out3),
+                                                  float(l1tex_wt), _p(ws), ws.numel(), N, H, S, _stream_ptr())
+    _check(rc, "lasr_b200_losses_forward_total")
 
 
 def losses_backward(mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs, grad_sums, g_mask_pred,
@@ -476,17 +485,19 @@ def skin_weights_backward(ctl_ts, ctl_rs, log_ctl, verts, skin, grad_skin, g_ts,
     _check(rc, "lasr_b200_skin_weights_backward")
 
 
-def head_forward(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, sums, flow_rd, bgmask, N, H, S):
+def head_forward(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, sums, flow_rd, bgmask, N, H, S,
+                 sub=None, out3=None, l1tex_wt=0.0):
     for t in (image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, sums):
         _require_cuda_f32(t, "head tensor")
     if tuple(image.shape) != (N * H, 10, S, S):
         raise RuntimeError("head: image must be [N*H,10,S,S] (three colour sets + silhouette)")
     ws = torch.empty(int(lib().lasr_b200_head_workspace_bytes(N, H, S)), dtype=torch.uint8, device=image.device)
     with torch.cuda.device(image.device):
-        rc = lib().lasr_b200_head_forward(_p(image), _p(pp_own), _p(pp_pair), _p(f_own), _p(f_pair), _p(imgs),
-                                          _p(masks), _p(occ), _p(flow_obs), _p(sums), _p(flow_rd), _p(bgmask), _p(ws),
-                                          ws.numel(), N, H, S, _stream_ptr())
-    _check(rc, "lasr_b200_head_forward")
+        rc = lib().lasr_b200_head_forward_total(_p(image), _p(pp_own), _p(pp_pair), _p(f_own), _p(f_pair), _p(imgs),
+                                                _p(masks), _p(occ), _p(flow_obs), _p(sums), _p(sub), _p(out3),
+                                                float(l1tex_wt), _p(flow_rd), _p(bgmask), _p(ws), ws.numel(), N, H, S,
+                                                _stream_ptr())
+    _check(rc, "lasr_b200_head_forward_total")
 
 
 def head_backward(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, grad_sums, grad_image,

@@ -29,7 +29,7 @@ int lasr_check_launch(const char* what) {
 
 }  // namespace lasr
 
-extern "C" int lasr_b200_abi_version(void) { return 7; }   // 7: + lbs_pose_forward / backward; 6: + head_backward_packed / render_backward_packed; 5: + lasr_b200_raster_forward_bg (4: + chamfer, texture atlas, staging)
+extern "C" int lasr_b200_abi_version(void) { return 8; }   // 8: + losses_forward_total / head_forward_total; 7: + lbs_pose_forward / backward; 6: + head_backward_packed / render_backward_packed; 5: + lasr_b200_raster_forward_bg (4: + chamfer, texture atlas, staging)
 
 extern "C" const char* lasr_b200_last_error(void) {
   static thread_local std::string copy;

@@ -254,12 +254,12 @@ __global__ void __launch_bounds__(kLossThreads) losses_backward_kernel(LossArgs 
 
 // sums [N,H,7] -> per-(frame,hypothesis) losses sub[3][N*H] (mask, flow, texture) and their means
 // out3[3], following nnutils/mesh_net.py:388-390, 404-416, 440-445.  One block; fixed-order reduction.
-__global__ void __launch_bounds__(256) losses_finalize_kernel(const float* sums, int N, int H, float l1tex_wt,
-                                                              float* sub, float* out3) {
+__device__ __forceinline__ void losses_finalize_block(const float* sums, int N, int H, float l1tex_wt, float* sub,
+                                                      float* out3) {   // the first 256 threads of the block work
   __shared__ float s_red[3][256 / 32];
   const int NH = N * H;
   float acc[3] = {0.f, 0.f, 0.f};
-  for (int t = threadIdx.x; t < NH; t += blockDim.x) {
+  for (int t = threadIdx.x; t < NH && threadIdx.x < 256; t += 256) {
     const int i = t / H;
     const float* q = sums + (long long)t * kNumSums;
     const float V = q[6];
@@ -276,14 +276,38 @@ __global__ void __launch_bounds__(256) losses_finalize_kernel(const float* sums,
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const float w = wsum(acc[k]);
-    if (lane == 0) s_red[k][warp] = w;
+    if (lane == 0 && warp < 256 / 32) s_red[k][warp] = w;
   }
   __syncthreads();
   if (threadIdx.x < 3) {
     float t = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[threadIdx.x][w];
+    for (int w = 0; w < 256 / 32; ++w) t += s_red[threadIdx.x][w];
     out3[threadIdx.x] = t / (float)NH;
   }
+}
+
+__global__ void __launch_bounds__(256) losses_finalize_kernel(const float* sums, int N, int H, float l1tex_wt,
+                                                              float* sub, float* out3) {
+  losses_finalize_block(sums, N, H, l1tex_wt, sub, out3);
+}
+
+// Block partials -> sums [N,H,7] -> per-pair losses and the three means, in ONE block (the two steps used to be two
+// launches behind the pixel pass; at LASR's batch sizes the whole head is launch-latency bound).  Same summation orders as
+// losses_reduce_kernel and losses_finalize_kernel: same bits.
+__global__ void __launch_bounds__(512) losses_reduce_finalize_kernel(const float* __restrict__ partial, int nblk, int N,
+                                                                     int H, float l1tex_wt, float* sums, float* sub,
+                                                                     float* out3) {
+  const int tot = N * H * kNumSums;
+  for (int t = threadIdx.x; t < tot; t += blockDim.x) {
+    const int ij = t / kNumSums, q = t % kNumSums;
+    const float* src = partial + (long long)ij * nblk * kNumSums + q;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int b = 0; b < nblk; ++b) acc += __ldg(src + (long long)b * kNumSums);
+    sums[t] = acc;
+  }
+  __syncthreads();                       // this block's own global writes are visible to it after the barrier
+  losses_finalize_block(sums, N, H, l1tex_wt, sub, out3);
 }
 
 // upstream gradients of the three means (g3[3]) and of the per-pair losses (gsub[3][N*H], may be null)
@@ -674,10 +698,24 @@ extern "C" size_t lasr_b200_losses_workspace_bytes(int N, int H, int S) {
   return (size_t)N * H * nblk * kNumSums * sizeof(float) + 256;
 }
 
-extern "C" int lasr_b200_losses_forward(const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
-                                        const float* tex, const float* fg, const float* imgs, const float* masks,
-                                        const float* occ, const float* flow_obs, float* sums, void* workspace,
-                                        size_t workspace_bytes, int N, int H, int S, void* stream) {
+// partials -> sums (and, when `sub`/`out3` are given, the per-pair losses and their means in the same launch)
+static int reduce_tail(const float* partial, int nblk, int N, int H, float* sums, float* sub, float* out3, float l1tex_wt,
+                       cudaStream_t st) {
+  if ((sub == nullptr) != (out3 == nullptr)) return lasr_fail("losses: sub and out3 go together");
+  if (sub) {
+    losses_reduce_finalize_kernel<<<1, 512, 0, st>>>(partial, nblk, N, H, l1tex_wt, sums, sub, out3);
+    return lasr_check_launch("losses_reduce_finalize_kernel");
+  }
+  const int tot = N * H * kNumSums;
+  losses_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(partial, nblk, N * H, sums);
+  return lasr_check_launch("losses_reduce_kernel");
+}
+
+extern "C" int lasr_b200_losses_forward_total(const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
+                                              const float* tex, const float* fg, const float* imgs, const float* masks,
+                                              const float* occ, const float* flow_obs, float* sums, float* sub,
+                                              float* out3, float l1tex_wt, void* workspace, size_t workspace_bytes,
+                                              int N, int H, int S, void* stream) {
   LossArgs A{};
   if (fill_loss(A, mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs, N, H, S)) return 1;
   if (!sums || !workspace || workspace_bytes < lasr_b200_losses_workspace_bytes(N, H, S))
@@ -688,9 +726,15 @@ extern "C" int lasr_b200_losses_forward(const float* mask_pred, const float* flo
   if (A.SS % 4 == 0) losses_forward_kernel<4><<<dim3(nblk, N * H), kLossThreads, 0, st>>>(A, partial, nblk);
   else losses_forward_kernel<1><<<dim3(nblk, N * H), kLossThreads, 0, st>>>(A, partial, nblk);
   if (lasr_check_launch("losses_forward_kernel")) return 1;
-  const int tot = N * H * kNumSums;
-  losses_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(partial, nblk, N * H, sums);
-  return lasr_check_launch("losses_reduce_kernel");
+  return reduce_tail(partial, nblk, N, H, sums, sub, out3, l1tex_wt, st);
+}
+
+extern "C" int lasr_b200_losses_forward(const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
+                                        const float* tex, const float* fg, const float* imgs, const float* masks,
+                                        const float* occ, const float* flow_obs, float* sums, void* workspace,
+                                        size_t workspace_bytes, int N, int H, int S, void* stream) {
+  return lasr_b200_losses_forward_total(mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs, sums, nullptr,
+                                        nullptr, 0.f, workspace, workspace_bytes, N, H, S, stream);
 }
 
 extern "C" int lasr_b200_losses_backward(const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
@@ -789,11 +833,12 @@ extern "C" size_t lasr_b200_head_workspace_bytes(int N, int H, int S) {
   return (a > b ? a : b) + 256;
 }
 
-extern "C" int lasr_b200_head_forward(const float* image, const float* pp_own, const float* pp_pair,
-                                      const float* f_own, const float* f_pair, const float* imgs,
-                                      const float* masks, const float* occ, const float* flow_obs, float* sums,
-                                      float* flow_rd, uint8_t* bgmask, void* workspace, size_t workspace_bytes, int N,
-                                      int H, int S, void* stream) {
+extern "C" int lasr_b200_head_forward_total(const float* image, const float* pp_own, const float* pp_pair,
+                                            const float* f_own, const float* f_pair, const float* imgs,
+                                            const float* masks, const float* occ, const float* flow_obs, float* sums,
+                                            float* sub, float* out3, float l1tex_wt, float* flow_rd, uint8_t* bgmask,
+                                            void* workspace, size_t workspace_bytes, int N, int H, int S,
+                                            void* stream) {
   HeadArgs A{};
   if (fill_head(A, image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, N, H, S)) return 1;
   if (!sums || !workspace || workspace_bytes < lasr_b200_head_workspace_bytes(N, H, S))
@@ -805,9 +850,16 @@ extern "C" int lasr_b200_head_forward(const float* image, const float* pp_own, c
   if (A.SS % 4 == 0) head_forward_kernel<4><<<dim3(nblk, N * H), kLossThreads, 0, st>>>(A, partial, nblk, flow_rd, bgmask);
   else head_forward_kernel<1><<<dim3(nblk, N * H), kLossThreads, 0, st>>>(A, partial, nblk, flow_rd, bgmask);
   if (lasr_check_launch("head_forward_kernel")) return 1;
-  const int tot = N * H * kNumSums;
-  losses_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(partial, nblk, N * H, sums);
-  return lasr_check_launch("losses_reduce_kernel");
+  return reduce_tail(partial, nblk, N, H, sums, sub, out3, l1tex_wt, st);
+}
+
+extern "C" int lasr_b200_head_forward(const float* image, const float* pp_own, const float* pp_pair,
+                                      const float* f_own, const float* f_pair, const float* imgs,
+                                      const float* masks, const float* occ, const float* flow_obs, float* sums,
+                                      float* flow_rd, uint8_t* bgmask, void* workspace, size_t workspace_bytes, int N,
+                                      int H, int S, void* stream) {
+  return lasr_b200_head_forward_total(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, sums, nullptr,
+                                      nullptr, 0.f, flow_rd, bgmask, workspace, workspace_bytes, N, H, S, stream);
 }
 
 extern "C" int lasr_b200_head_backward(const float* image, const float* pp_own, const float* pp_pair,

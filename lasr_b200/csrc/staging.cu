@@ -132,6 +132,15 @@ __device__ __forceinline__ float lerp2(float p00, float p01, float p10, float p1
   return top * (1.f - wy) + bot * wy;                 // vertical pass
 }
 
+// Per-frame constants of the resample pass.  They are float64 expressions of the frame's statistics (numpy evaluates
+// them in double, vidbase.py:78,141-149); thread 0 of every block evaluates them once and the block reads them from
+// shared memory -- round 1 had every one of the S*S threads of a frame run the same eight double divisions.
+struct ResampleFrame {
+  double scale, alp, alpn, shift_x, shift_y;
+  float color[3], a_other;
+  int src, ox, oy, ok;
+};
+
 __global__ void __launch_bounds__(256) stage_resample_kernel(const uint8_t* __restrict__ frames,
                                                              const uint8_t* __restrict__ masks,
                                                              const float* __restrict__ flows,
@@ -140,30 +149,46 @@ __global__ void __launch_bounds__(256) stage_resample_kernel(const uint8_t* __re
                                                              float* __restrict__ mask_out, float* __restrict__ flow_out,
                                                              float* __restrict__ occ_out, float* cam_focal, float* pps,
                                                              int32_t* boxes, int H, int W, int S) {
+  __shared__ ResampleFrame s_c;
   const int slot = blockIdx.y, pair = blockIdx.z;
   const int f = pair * 2 + slot, fo = pair * 2 + (1 - slot);
-  const FrameStats s_own = st[f], s_oth = st[fo];
-  const Box b = crop_box(s_own), bo = crop_box(s_oth);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) {
-    boxes[4 * f] = b.cx; boxes[4 * f + 1] = b.cy; boxes[4 * f + 2] = b.L;
-    boxes[4 * f + 3] = (int)min(s_own.count, (unsigned long long)INT_MAX);
+  if (threadIdx.x == 0) {
+    const FrameStats s_own = st[f], s_oth = st[fo];
+    const Box b = crop_box(s_own), bo = crop_box(s_oth);
+    ResampleFrame c;
+    c.ok = !(s_own.count == 0 || s_oth.count == 0 || b.L <= 0 || bo.L <= 0);       // host raises (empty mask)
+    c.src = 2 * b.L;
+    c.alp = (double)c.src / (double)S;                                            // :141 (orisize[0] / maxw)
+    c.alpn = (double)(2 * bo.L) / (double)S;
+    c.scale = 1.0 / ((double)S / (double)c.src);     // cv2: inv_scale = dst/src; scale = 1/inv_scale
+    c.ox = b.cx - b.L; c.oy = b.cy - b.L;            // crop origin in the frame
+    c.shift_x = (double)(c.ox - (bo.cx - bo.L));
+    c.shift_y = (double)(c.oy - (bo.cy - bo.L));
+    c.a_other = (float)c.alpn;
+    const unsigned long long sums[3] = {s_own.sum_r, s_own.sum_g, s_own.sum_b};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      c.color[k] = c.ok ? (float)(1.0 - ((double)sums[k] / 255.0) / (double)s_own.count) : 0.f;   // :78
+    s_c = c;
+    if (i == 0) {
+      boxes[4 * f] = b.cx; boxes[4 * f + 1] = b.cy; boxes[4 * f + 2] = b.L;
+      boxes[4 * f + 3] = (int)min(s_own.count, (unsigned long long)INT_MAX);
+      if (c.ok) {
+        cam_focal[f] = (float)(1.0 / c.alp);                                       // :182
+        pps[2 * f] = (float)c.ox; pps[2 * f + 1] = (float)c.oy;                   // :172
+      }
+    }
   }
-  if (s_own.count == 0 || s_oth.count == 0 || b.L <= 0 || bo.L <= 0) return;   // host raises (empty mask)
-  const int src = 2 * b.L;
-  const double alp = (double)src / (double)S, alpn = (double)(2 * bo.L) / (double)S;   // :141 (orisize[0] / maxw)
-  if (i == 0) {
-    cam_focal[f] = (float)(1.0 / alp);                                                   // :182
-    pps[2 * f] = (float)(b.cx - b.L); pps[2 * f + 1] = (float)(b.cy - b.L);             // :172
-  }
-  if (i >= S * S) return;
+  __syncthreads();
+  if (!s_c.ok || i >= S * S) return;
+  const int src = s_c.src, ox = s_c.ox, oy = s_c.oy;
+  const double scale = s_c.scale;
   const int dy = i / S, dx = i - dy * S;
-  const double scale = 1.0 / ((double)S / (double)src);     // cv2: inv_scale = dst/src; scale = 1/inv_scale
   int x0, x1, y0, y1;
   float wx, wy;
   linear_tap(dx, scale, src, x0, x1, wx);
   linear_tap(dy, scale, src, y0, y1, wy);
-  const int ox = b.cx - b.L, oy = b.cy - b.L;               // crop origin in the frame
   const int X0 = x0 + ox, X1 = x1 + ox, Y0 = y0 + oy, Y1 = y1 + oy;
   const bool vx0 = X0 >= 0 && X0 < W, vx1 = X1 >= 0 && X1 < W, vy0 = Y0 >= 0 && Y0 < H, vy1 = Y1 >= 0 && Y1 < H;
   const long long HW = (long long)H * W;
@@ -172,45 +197,52 @@ __global__ void __launch_bounds__(256) stage_resample_kernel(const uint8_t* __re
   const float* fl = flows + f * HW * 3;
   const float* oc = occs + f * HW;
   const long long SS = (long long)S * S;
-  const long long q00 = (long long)Y0 * W + X0, q01 = (long long)Y0 * W + X1, q10 = (long long)Y1 * W + X0,
-                  q11 = (long long)Y1 * W + X1;
-  const bool v00 = vy0 && vx0, v01 = vy0 && vx1, v10 = vy1 && vx0, v11 = vy1 && vx1;
-
+  const bool v[4] = {vy0 && vx0, vy0 && vx1, vy1 && vx0, vy1 && vx1};
+  // taps outside the frame read element 0 (always there) and are discarded: every load below is unconditional, so the
+  // 4 mask + 12 colour + 4 occlusion + 12 flow reads of a pixel are in flight together instead of mask -> colour chains
+  const long long q[4] = {v[0] ? (long long)Y0 * W + X0 : 0, v[1] ? (long long)Y0 * W + X1 : 0,
+                          v[2] ? (long long)Y1 * W + X0 : 0, v[3] ? (long long)Y1 * W + X1 : 0};
+  // mask: nearest neighbour, zero border
+  const int nx = min((int)floor((double)dx * scale), src - 1) + ox, ny = min((int)floor((double)dy * scale), src - 1) + oy;
+  const bool vn = nx >= 0 && nx < W && ny >= 0 && ny < H;
+  const unsigned mnn = __ldg(mk + (vn ? (long long)ny * W + nx : 0));
+  unsigned mq[4], cq[4][3];
+  float oq[4], fq[4][3];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    mq[t] = __ldg(mk + q[t]);
+    oq[t] = __ldg(oc + q[t]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { cq[t][c] = __ldg(fr + 3 * q[t] + c); fq[t][c] = __ldg(fl + 3 * q[t] + c); }
+  }
   // image: RGB / 255 where the mask is set, the complement of the masked mean colour elsewhere and outside
-  const bool m00 = v00 && mk[q00] > 0, m01 = v01 && mk[q01] > 0, m10 = v10 && mk[q10] > 0, m11 = v11 && mk[q11] > 0;
-  const unsigned long long sums[3] = {s_own.sum_r, s_own.sum_g, s_own.sum_b};
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float color = (float)(1.0 - ((double)sums[c] / 255.0) / (double)s_own.count);   // :78
+    const float color = s_c.color[c];
     const int ch = 2 - c;                                                                 // BGR -> RGB (:56)
-    const float p00 = m00 ? (float)fr[3 * q00 + ch] / 255.f : color;
-    const float p01 = m01 ? (float)fr[3 * q01 + ch] / 255.f : color;
-    const float p10 = m10 ? (float)fr[3 * q10 + ch] / 255.f : color;
-    const float p11 = m11 ? (float)fr[3 * q11 + ch] / 255.f : color;
-    img[((long long)f * 3 + c) * SS + i] = lerp2(p00, p01, p10, p11, wx, wy);
+    float p[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) p[t] = (v[t] && mq[t] > 0) ? (float)cq[t][ch] / 255.f : color;
+    img[((long long)f * 3 + c) * SS + i] = lerp2(p[0], p[1], p[2], p[3], wx, wy);
   }
   // occlusion map and flow: bilinear, zero border
-  const float occ = lerp2(v00 ? oc[q00] : 0.f, v01 ? oc[q01] : 0.f, v10 ? oc[q10] : 0.f, v11 ? oc[q11] : 0.f, wx, wy);
+  const float occ = lerp2(v[0] ? oq[0] : 0.f, v[1] ? oq[1] : 0.f, v[2] ? oq[2] : 0.f, v[3] ? oq[3] : 0.f, wx, wy);
   occ_out[(long long)f * SS + i] = occ;
   float fv[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c)
-    fv[c] = lerp2(v00 ? fl[3 * q00 + c] : 0.f, v01 ? fl[3 * q01 + c] : 0.f, v10 ? fl[3 * q10 + c] : 0.f,
-                  v11 ? fl[3 * q11 + c] : 0.f, wx, wy);
+    fv[c] = lerp2(v[0] ? fq[0][c] : 0.f, v[1] ? fq[1][c] : 0.f, v[2] ? fq[2][c] : 0.f, v[3] ? fq[3][c] : 0.f, wx, wy);
   // :141-149 -- the shift between the two crops and the scale change are added in float64, as numpy does
-  const double dxs = (double)(ox - (bo.cx - bo.L)) + (double)dx * (alp - alpn);
-  const double dys = (double)(oy - (bo.cy - bo.L)) + (double)dy * (alp - alpn);
-  const float a_other = (float)alpn;
-  float u = (float)((double)fv[0] + dxs), v = (float)((double)fv[1] + dys);
-  u = __fdiv_rn(u, a_other); v = __fdiv_rn(v, a_other);
-  u = 2.f * __fdiv_rn(u, (float)S); v = 2.f * __fdiv_rn(v, (float)S);
+  const double dxs = s_c.shift_x + (double)dx * (s_c.alp - s_c.alpn);
+  const double dys = s_c.shift_y + (double)dy * (s_c.alp - s_c.alpn);
+  const float a_other = s_c.a_other;
+  float u = (float)((double)fv[0] + dxs), w = (float)((double)fv[1] + dys);
+  u = __fdiv_rn(u, a_other); w = __fdiv_rn(w, a_other);
+  u = 2.f * __fdiv_rn(u, (float)S); w = 2.f * __fdiv_rn(w, (float)S);
   float* fo_ = flow_out + (long long)f * 3 * SS + i;
-  fo_[0] = u; fo_[SS] = v;
+  fo_[0] = u; fo_[SS] = w;
   fo_[2 * SS] = (__fdiv_rn(fv[2], a_other) != 0.f && occ < 10.f) ? 1.f : 0.f;            // :151
-  // mask: nearest neighbour, zero border
-  const int nx = min((int)floor((double)dx * scale), src - 1) + ox, ny = min((int)floor((double)dy * scale), src - 1) + oy;
-  const bool vn = nx >= 0 && nx < W && ny >= 0 && ny < H;
-  mask_out[(long long)f * SS + i] = (vn && mk[(long long)ny * W + nx] > 0) ? 1.f : 0.f;
+  mask_out[(long long)f * SS + i] = (vn && mnn > 0) ? 1.f : 0.f;
 }
 
 }  // namespace lasr

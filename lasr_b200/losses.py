@@ -48,7 +48,7 @@ class _LossSums(Function):
 
 
 class _FusedImageLosses(Function):
-    """All three losses in four launches forward (sums, reduce, finalize) and three backward
+    """All three losses in two launches forward (sums; reduce + finalize) and three backward
     (coefficients, per-pixel gradients): no [N,H]-sized PyTorch arithmetic, no autograd graph of tiny ops."""
 
     @staticmethod
@@ -60,10 +60,9 @@ class _FusedImageLosses(Function):
         bg = bgmask.detach().to(torch.uint8).contiguous()
         dev = mask_pred.device
         sums = torch.empty(N, H, 7, dtype=torch.float32, device=dev)
-        _cabi.losses_forward(mp, fr, bg, tx, fgc, im, mk, oc, fo, sums, N, H, S)
         sub = torch.empty(3, N, H, dtype=torch.float32, device=dev)
         out3 = torch.empty(3, dtype=torch.float32, device=dev)
-        _cabi.losses_finalize(sums, sub, out3, N, H, l1tex_wt)
+        _cabi.losses_forward(mp, fr, bg, tx, fgc, im, mk, oc, fo, sums, N, H, S, sub, out3, l1tex_wt)
         ctx.save_for_backward(mp, fr, bg, tx, fgc, im, mk, oc, fo, sums)
         ctx.dims = (N, H, S, float(l1tex_wt))
         return out3, sub
@@ -109,10 +108,9 @@ class _FusedHead(Function):
         if want_flow:
             flow_rd = torch.empty(N * H, S, S, 2, dtype=torch.float32, device=dev)
             bg = torch.empty(N * H, S, S, dtype=torch.uint8, device=dev)
-        _cabi.head_forward(img, po, pq, fo, fq, im, mk, oc, fl, sums, flow_rd, bg, N, H, S)
         sub = torch.empty(3, N, H, dtype=torch.float32, device=dev)
         out3 = torch.empty(3, dtype=torch.float32, device=dev)
-        _cabi.losses_finalize(sums, sub, out3, N, H, l1tex_wt)
+        _cabi.head_forward(img, po, pq, fo, fq, im, mk, oc, fl, sums, flow_rd, bg, N, H, S, sub, out3, l1tex_wt)
         ctx.save_for_backward(img, po, pq, fo, fq, im, mk, oc, fl, sums)
         ctx.dims = (N, H, S, float(l1tex_wt))
         ctx.shapes = (pp_pair.shape, f_pair.shape)

@@ -147,6 +147,16 @@ def test_fused_image_losses_match_cpu_expressions(dev):
     lm, lf, lt, _ = losses.image_losses(t(mask_pred), t(masks), t(occ), t(flow_rd), t(bg), t(flow_obs), t(tex), t(fg),
                                         t(imgs), 0.7)
     assert torch.allclose(torch.stack([lm, lf, lt]).cpu(), torch.stack(a[:3]), rtol=2e-4)
+    # the scalar step riding the partial-sum launch (lasr_b200_losses_forward_total) == the two separate calls, bit for bit
+    from lasr_b200 import _cabi
+    c = lambda x: t(x).float().contiguous()
+    args = (c(mask_pred), c(flow_rd), t(bg).to(torch.uint8).contiguous(), c(tex), c(fg), c(imgs), c(masks), c(occ), c(flow_obs))
+    e = lambda *sh: torch.full(sh, float("nan"), device=dev)
+    s1, s2, sub1, sub2, o1, o2 = e(N, H, 7), e(N, H, 7), e(3, N, H), e(3, N, H), e(3), e(3)
+    _cabi.losses_forward(*args, s1, N, H, S)
+    _cabi.losses_finalize(s1, sub1, o1, N, H, 0.7)
+    _cabi.losses_forward(*args, s2, N, H, S, sub2, o2, 0.7)
+    assert torch.equal(s1, s2) and torch.equal(sub1, sub2) and torch.equal(o1, o2) and bool(torch.isfinite(o2).all())
 
 
 @pytest.mark.parametrize("H,Bp,V", [(1, 25, 2930), (2, 7, 642), (1, 1, 100)])
