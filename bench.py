@@ -525,7 +525,20 @@ class ReferenceRegionArm(RegionArmBase):
 # ----------------------------------------------------------------------------------------------
 def extras_microbench(device, peak_gbs, iters=20):
     """The HBM-bound helper kernels of the path, timed alone with CUDA events (config E shape for the
-    LBS: Spot, 64 frames, 26 bones; config A shape for the losses) against their algorithmic bytes."""
+    LBS: Spot, 64 frames, 26 bones; config A shape for the losses) against their algorithmic bytes.  Everything runs on
+    ONE side stream: autograd replays a backward on the stream its forward ran on, so a backward is captured into a
+    CUDA graph only if the forward ran on the capturing stream."""
+    import torch
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        out = _extras_microbench_on(side, device, peak_gbs, iters)
+    torch.cuda.current_stream(device).wait_stream(side)
+    torch.cuda.synchronize()
+    return out
+
+
+def _extras_microbench_on(side, device, peak_gbs, iters):
     import torch
     from lasr_b200 import native_geom, losses, synth
     from lasr_b200.geom_utils import quaternion_to_rotation_matrix
@@ -549,18 +562,15 @@ def extras_microbench(device, peak_gbs, iters=20):
             fn()
         torch.cuda.synchronize()
         try:
-            side = torch.cuda.Stream(device=device)
-            side.wait_stream(torch.cuda.current_stream(device))
-            with torch.cuda.stream(side):
-                fn()
-            torch.cuda.current_stream(device).wait_stream(side)
-            torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=side):
                 fn()
             graph.replay()
             torch.cuda.synchronize()
-            return timed_loop(torch, graph.replay, iters)
+            t = timed_loop(torch, graph.replay, iters)
+            if t < 1e-3:          # an empty graph (nothing was captured) replays in no time: not a measurement
+                raise RuntimeError("empty graph")
+            return t
         except Exception:
             torch.cuda.synchronize()
             return timed_loop(torch, fn, iters)

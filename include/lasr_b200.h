@@ -163,6 +163,31 @@ int lasr_b200_render_backward_packed(const float* verts, const int32_t* tri, con
                                      int func_id_alpha, int double_side, int num_sets, int detached_sets,
                                      int setup_done, void* stream);
 
+/* The colour sets as SEPARATE tensors with a frame shift each, instead of one stacked [K][N,V,3] tensor:
+ *   set_ptrs  HOST array of num_sets device pointers, each [N,V,3]
+ *   set_shifts HOST array of num_sets ints in [0, N) (NULL = all 0): frame n renders frame (n + shift) mod N of the set
+ * LASR's flow render colours every frame with its own camera-space vertices AND with its pair's -- frame i and frame
+ * i +- bs of the SAME tensor (nnutils/mesh_net.py:84-87, 318-335).  Stacked, that is a roll and a concatenation per step
+ * (and their adjoints); here both sets point at the one tensor, the second with shift bs.  The backward writes set s's
+ * gradient [N,V,3] through grad_set_ptrs[s] (HOST array; NULL entries allowed for detached sets) in the frame order of
+ * the set's own tensor, i.e. already shifted back. */
+int lasr_b200_render_forward_sets(const float* verts, const int32_t* tri, const float* const* set_ptrs,
+                                  const int* set_shifts, float* aggrs_info, float* soft_colors, void* workspace,
+                                  size_t workspace_bytes, int batch_size, int num_vertices, int num_faces,
+                                  int image_size, float near_, float far_, const float* near_far_dev, float eps,
+                                  float sigma_val, int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
+                                  int func_id_alpha, int double_side, int num_sets, const float* background,
+                                  void* stream);
+int lasr_b200_render_backward_sets_packed(const float* verts, const int32_t* tri, const float* const* set_ptrs,
+                                          const int* set_shifts, const float* packed_grad,
+                                          const int32_t* csr_offsets, const int32_t* csr_entries, float* grad_verts,
+                                          float* const* grad_set_ptrs, void* workspace, size_t workspace_bytes,
+                                          int batch_size, int num_vertices, int num_faces, int image_size, float near_,
+                                          float far_, const float* near_far_dev, float eps, float sigma_val,
+                                          int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
+                                          int func_id_alpha, int double_side, int num_sets, int detached_sets,
+                                          int setup_done, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused linear-blend skinning + body transform + pinhole projection + batch depth window
  * (SURVEY 8a rows G1, G2, G3).  Replaces, for CUDA tensors,
@@ -247,10 +272,11 @@ int lasr_b200_losses_forward(const float* mask_pred, const float* flow_rd, const
                              void* stream);
 
 /* The same plus the scalar step of lasr_b200_losses_finalize in the launch that sums the block partials: sums [N,H,7],
- * sub [3][N*H] and out3 [3] out (sub and out3 both given or both NULL).  Same bits as the two calls. */
+ * sub [3][N*H] and out4 [4] out (both given or both NULL): out4 = the three means of lasr_b200_losses_finalize (same
+ * bits as the two calls) and their sum (mask + flow) + texture, the objective LASR forms of them. */
 int lasr_b200_losses_forward_total(const float* mask_pred, const float* flow_rd, const uint8_t* bgmask,
                                    const float* tex, const float* fg, const float* imgs, const float* masks,
-                                   const float* occ, const float* flow_obs, float* sums, float* sub, float* out3,
+                                   const float* occ, const float* flow_obs, float* sums, float* sub, float* out4,
                                    float l1tex_wt, void* workspace, size_t workspace_bytes, int num_frames,
                                    int num_hypotheses, int image_size, void* stream);
 
@@ -268,6 +294,10 @@ int lasr_b200_losses_finalize(const float* sums, float* sub, float* out3, int nu
 int lasr_b200_losses_coefficients(const float* sums, const float* grad_out3, const float* grad_sub,
                                   float* grad_sums, int num_frames, int num_hypotheses, float l1tex_wt,
                                   void* stream);
+/* ... for the four-entry output of the *_total calls: grad_out4 [4], the last entry being the gradient of the sum. */
+int lasr_b200_losses_coefficients_total(const float* sums, const float* grad_out4, const float* grad_sub,
+                                        float* grad_sums, int num_frames, int num_hypotheses, float l1tex_wt,
+                                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Flow epilogue: the post-processing of render_flow_soft_2,
@@ -306,12 +336,16 @@ int lasr_b200_head_forward(const float* image, const float* pp_own, const float*
                            float* flow_rd, uint8_t* bgmask, void* workspace, size_t workspace_bytes,
                            int N, int H, int image_size, void* stream);
 
-/* head_forward + lasr_b200_losses_finalize, the scalar step riding the partial-sum launch (sub [3][N*H], out3 [3]). */
+/* head_forward + lasr_b200_losses_finalize, the scalar step riding the partial-sum launch (sub [3][N*H]; out4 [4] as in
+ * lasr_b200_losses_forward_total).  pair_shift in [0, N*H): frame ij takes entry (ij + pair_shift) mod N*H of pp_pair /
+ * f_pair -- LASR pairs frame i with frame i +- bs, so the caller passes the OWN arrays again with pair_shift = bs*H
+ * instead of rolled copies (0: pp_pair / f_pair are indexed like pp_own / f_own). */
 int lasr_b200_head_forward_total(const float* image, const float* pp_own, const float* pp_pair,
                                  const float* f_own, const float* f_pair, const float* imgs,
                                  const float* masks, const float* occ, const float* flow_obs, float* sums,
-                                 float* sub, float* out3, float l1tex_wt, float* flow_rd, uint8_t* bgmask,
-                                 void* workspace, size_t workspace_bytes, int N, int H, int image_size, void* stream);
+                                 float* sub, float* out4, float l1tex_wt, float* flow_rd, uint8_t* bgmask,
+                                 void* workspace, size_t workspace_bytes, int N, int H, int image_size,
+                                 int pair_shift, void* stream);
 
 int lasr_b200_head_backward(const float* image, const float* pp_own, const float* pp_pair,
                             const float* f_own, const float* f_pair, const float* imgs,
@@ -332,6 +366,15 @@ int lasr_b200_head_backward_packed(const float* image, const float* pp_own, cons
                                    const float* grad_sums, const float* aggrs_info, float* packed_grad,
                                    float* grad_pp_pair, float* grad_f_pair, void* workspace,
                                    size_t workspace_bytes, int N, int H, int image_size, void* stream);
+/* ... with the pair_shift of lasr_b200_head_forward_total: entry (ij + pair_shift) mod N*H of grad_pp_pair / grad_f_pair
+ * receives frame ij's gradient, i.e. the gradients come out in the order of the arrays that were read. */
+int lasr_b200_head_backward_packed_shift(const float* image, const float* pp_own, const float* pp_pair,
+                                         const float* f_own, const float* f_pair, const float* imgs,
+                                         const float* masks, const float* occ, const float* flow_obs,
+                                         const float* grad_sums, const float* aggrs_info, float* packed_grad,
+                                         float* grad_pp_pair, float* grad_f_pair, void* workspace,
+                                         size_t workspace_bytes, int N, int H, int image_size, int pair_shift,
+                                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Skinning weights, nnutils/mesh_net.py:264-267:

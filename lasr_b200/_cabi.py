@@ -79,6 +79,15 @@ def _load_locked():
         L.lasr_b200_render_backward_packed.restype = _c.c_int
         L.lasr_b200_render_backward_packed.argtypes = ([_c.c_void_p] * 9 + [_c.c_size_t] + _render_scalars
                                                        + [_c.c_int, _c.c_int, _c.c_void_p])
+        L.lasr_b200_render_forward_sets.restype = _c.c_int
+        L.lasr_b200_render_forward_sets.argtypes = ([_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_int),
+                                                     _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t] + _render_scalars
+                                                    + [_c.POINTER(_c.c_float), _c.c_void_p])
+        L.lasr_b200_render_backward_sets_packed.restype = _c.c_int
+        L.lasr_b200_render_backward_sets_packed.argtypes = ([_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p),
+                                                             _c.POINTER(_c.c_int), _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                                             _c.c_void_p, _c.POINTER(_c.c_void_p), _c.c_void_p, _c.c_size_t]
+                                                            + _render_scalars + [_c.c_int, _c.c_int, _c.c_void_p])
         L.lasr_b200_meshreg_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_meshreg_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         vp, ci = _c.c_void_p, _c.c_int
@@ -110,7 +119,10 @@ def _load_locked():
         L.lasr_b200_head_forward.argtypes = [_c.c_void_p] * 13 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
         L.lasr_b200_head_forward_total.restype = _c.c_int
         L.lasr_b200_head_forward_total.argtypes = ([_c.c_void_p] * 12 + [_c.c_float] + [_c.c_void_p] * 3 +
-                                                   [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p])
+                                                   [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p])
+        L.lasr_b200_head_backward_packed_shift.restype = _c.c_int
+        L.lasr_b200_head_backward_packed_shift.argtypes = ([_c.c_void_p] * 15 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int,
+                                                                                  _c.c_int, _c.c_void_p])
         L.lasr_b200_head_backward.restype = _c.c_int
         L.lasr_b200_head_backward.argtypes = [_c.c_void_p] * 14 + [_c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
         L.lasr_b200_head_backward_packed.restype = _c.c_int
@@ -128,6 +140,8 @@ def _load_locked():
         L.lasr_b200_losses_finalize.argtypes = [_c.c_void_p] * 3 + [_c.c_int, _c.c_int, _c.c_float, _c.c_void_p]
         L.lasr_b200_losses_coefficients.restype = _c.c_int
         L.lasr_b200_losses_coefficients.argtypes = [_c.c_void_p] * 4 + [_c.c_int, _c.c_int, _c.c_float, _c.c_void_p]
+        L.lasr_b200_losses_coefficients_total.restype = _c.c_int
+        L.lasr_b200_losses_coefficients_total.argtypes = [_c.c_void_p] * 4 + [_c.c_int, _c.c_int, _c.c_float, _c.c_void_p]
         L.lasr_b200_flow_epilogue_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_flow_epilogue_workspace_bytes.argtypes = [_c.c_int, _c.c_int]
         L.lasr_b200_flow_epilogue_forward.restype = _c.c_int
@@ -154,10 +168,10 @@ EXPORTED_SYMBOLS = [
     "lasr_b200_raster_workspace_bytes", "lasr_b200_raster_forward", "lasr_b200_raster_forward_bg",
     "lasr_b200_raster_backward",
     "lasr_b200_render_workspace_bytes", "lasr_b200_render_forward", "lasr_b200_render_backward",
-    "lasr_b200_render_backward_packed", "lasr_b200_head_backward_packed",
+    "lasr_b200_render_backward_packed", "lasr_b200_render_forward_sets", "lasr_b200_render_backward_sets_packed", "lasr_b200_head_backward_packed", "lasr_b200_head_backward_packed_shift",
     "lasr_b200_losses_workspace_bytes", "lasr_b200_losses_forward", "lasr_b200_losses_forward_total",
     "lasr_b200_losses_backward",
-    "lasr_b200_losses_finalize", "lasr_b200_losses_coefficients",
+    "lasr_b200_losses_finalize", "lasr_b200_losses_coefficients", "lasr_b200_losses_coefficients_total",
     "lasr_b200_flow_epilogue_workspace_bytes", "lasr_b200_flow_epilogue_forward", "lasr_b200_flow_epilogue_backward",
     "lasr_b200_lbs_workspace_bytes", "lasr_b200_lbs_project_forward", "lasr_b200_lbs_project_backward",
     "lasr_b200_lbs_pose_forward", "lasr_b200_lbs_pose_backward",
@@ -386,6 +400,66 @@ def render_backward(verts, tri, vcolors, soft_colors, aggrs_info, grad_soft_colo
     _check(rc, "lasr_b200_render_backward")
 
 
+def _set_arrays(sets, shifts, N, V, what):
+    K = len(sets)
+    if K < 1 or K > 3 or len(shifts) != K:
+        raise RuntimeError(f"{what}: one to three colour sets, one frame shift each")
+    for t, sh in zip(sets, shifts):
+        if t is not None:
+            _require_cuda_f32(t, "colour set")
+            if tuple(t.shape) != (N, V, 3):
+                raise RuntimeError(f"{what}: every colour set is [N,V,3]")
+        if not 0 <= int(sh) < N:
+            raise RuntimeError(f"{what}: frame shifts lie in [0, N)")
+    return (_c.c_void_p * K)(*[_p(t) for t in sets]), (_c.c_int * K)(*[int(x) for x in shifts])
+
+
+def render_forward_sets(verts, tri, sets, shifts, aggrs_info, soft_colors, workspace, S, near, far, near_far_dev, eps,
+                        sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side,
+                        background):
+    """lasr_b200_render_forward_sets: `sets` K tensors [N,V,3], frame n of the image reads frame (n + shifts[s]) mod N."""
+    for t, nm in ((verts, "verts"), (aggrs_info, "aggrs_info"), (soft_colors, "soft_colors")):
+        _require_cuda_f32(t, nm)
+    if tri.dtype != torch.int32 or not tri.is_cuda or not tri.is_contiguous():
+        raise RuntimeError("tri must be a contiguous CUDA int32 tensor [F,3]")
+    N, V = verts.shape[:2]
+    F, K = tri.shape[0], len(sets)
+    if any(t is None for t in sets):
+        raise RuntimeError("render_forward_sets: null colour set")
+    ptrs, sh = _set_arrays(sets, shifts, N, V, "render_forward_sets")
+    if tuple(soft_colors.shape[:2]) != (N, 3 * K + 1) or len(background) != 3 * K:
+        raise RuntimeError("soft_colors must be [N,3K+1,S,S] and background 3 floats per colour set")
+    bg_arr = (_c.c_float * (3 * K))(*[float(x) for x in background])
+    with torch.cuda.device(verts.device):
+        rc = lib().lasr_b200_render_forward_sets(
+            _p(verts), _p(tri), ptrs, sh, _p(aggrs_info), _p(soft_colors), _p(workspace), workspace.numel(),
+            *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
+                                 gamma_val, func_id_rgb, func_id_alpha, double_side, K), bg_arr, _stream_ptr())
+    _check(rc, "lasr_b200_render_forward_sets")
+
+
+def render_backward_sets_packed(verts, tri, sets, shifts, packed_grad, csr_offsets, csr_entries, grad_verts, grad_sets,
+                                workspace, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
+                                func_id_rgb, func_id_alpha, double_side, setup_done=False, detached_sets=1):
+    """grad_sets: K tensors [N,V,3] or None (detached sets), written in each set's own frame order."""
+    for t in (verts, packed_grad, grad_verts):
+        _require_cuda_f32(t, "render tensor")
+    N, V = verts.shape[:2]
+    F, K = tri.shape[0], len(sets)
+    ptrs, sh = _set_arrays(sets, shifts, N, V, "render_backward_sets_packed")
+    gptrs, _ = _set_arrays(grad_sets, shifts, N, V, "render_backward_sets_packed")
+    if packed_grad.numel() != N * 3 * int(S) * int(S) * 4:
+        raise RuntimeError("render_backward_sets_packed: packed_grad is [N,3,S*S,4]")
+    with torch.cuda.device(verts.device):
+        rc = lib().lasr_b200_render_backward_sets_packed(
+            _p(verts), _p(tri), ptrs, sh, _p(packed_grad), _p(csr_offsets), _p(csr_entries), _p(grad_verts), gptrs,
+            _p(workspace), workspace.numel(),
+            *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
+                                 gamma_val, func_id_rgb, func_id_alpha, double_side, K), int(detached_sets),
+            int(bool(setup_done)), _stream_ptr())
+    _check(rc, "lasr_b200_render_backward_sets_packed")
+
+
 def render_backward_packed(verts, tri, vcolors, packed_grad, csr_offsets, csr_entries, grad_verts, grad_vcolors,
                            workspace, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
                            func_id_rgb, func_id_alpha, double_side, setup_done=False, detached_sets=1):
@@ -408,7 +482,10 @@ def render_backward_packed(verts, tri, vcolors, packed_grad, csr_offsets, csr_en
 
 def losses_forward(mask_pred, flow_rd, bgmask, tex, fg, imgs, masks, occ, flow_obs, sums, N, H, S, sub=None, out3=None,
                    l1tex_wt=0.0):
-    """sums [N,H,7]; with `sub` [3,N,H] and `out3` [3] also the per-pair losses and their means, in the same launches."""
+    """sums [N,H,7]; with `sub` [3,N,H] and `out3` -- FOUR entries: the three means and their sum -- also the per-pair
+    losses, their means and the objective, in the same launches."""
+    if out3 is not None and out3.numel() != 4:
+        raise RuntimeError("losses_forward: out3 takes four entries (mask, flow, texture means and their sum)")
     ws = torch.empty(int(lib().lasr_b200_losses_workspace_bytes(N, H, S)), dtype=torch.uint8, device=mask_pred.device)
     with torch.cuda.device(mask_pred.device):
         rc = lib().lasr_b200_losses_forward_total(_p(mask_pred), _p(flow_rd), _p(bgmask), _p(tex), _p(fg), _p(imgs),
@@ -433,9 +510,13 @@ def losses_finalize(sums, sub, out3, N, H, l1tex_wt):
 
 
 def losses_coefficients(sums, g3, gsub, gsums, N, H, l1tex_wt):
+    """g3 [3] -> gsums; g3 with FOUR entries (the output of the *_total forward calls: three means and their sum) takes
+    the gradient of the sum from the last one."""
+    if g3.numel() not in (3, 4):
+        raise RuntimeError("losses_coefficients: the upstream gradient has 3 entries (or 4 with the sum)")
+    fn = lib().lasr_b200_losses_coefficients_total if g3.numel() == 4 else lib().lasr_b200_losses_coefficients
     with torch.cuda.device(sums.device):
-        rc = lib().lasr_b200_losses_coefficients(_p(sums), _p(g3), _p(gsub), _p(gsums), N, H, float(l1tex_wt),
-                                                 _stream_ptr())
+        rc = fn(_p(sums), _p(g3), _p(gsub), _p(gsums), N, H, float(l1tex_wt), _stream_ptr())
     _check(rc, "lasr_b200_losses_coefficients")
 
 
@@ -486,17 +567,19 @@ def skin_weights_backward(ctl_ts, ctl_rs, log_ctl, verts, skin, grad_skin, g_ts,
 
 
 def head_forward(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, sums, flow_rd, bgmask, N, H, S,
-                 sub=None, out3=None, l1tex_wt=0.0):
+                 sub=None, out3=None, l1tex_wt=0.0, pair_shift=0):
     for t in (image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, sums):
         _require_cuda_f32(t, "head tensor")
     if tuple(image.shape) != (N * H, 10, S, S):
         raise RuntimeError("head: image must be [N*H,10,S,S] (three colour sets + silhouette)")
+    if out3 is not None and out3.numel() != 4:
+        raise RuntimeError("head_forward: out3 takes four entries (mask, flow, texture means and their sum)")
     ws = torch.empty(int(lib().lasr_b200_head_workspace_bytes(N, H, S)), dtype=torch.uint8, device=image.device)
     with torch.cuda.device(image.device):
         rc = lib().lasr_b200_head_forward_total(_p(image), _p(pp_own), _p(pp_pair), _p(f_own), _p(f_pair), _p(imgs),
                                                 _p(masks), _p(occ), _p(flow_obs), _p(sums), _p(sub), _p(out3),
                                                 float(l1tex_wt), _p(flow_rd), _p(bgmask), _p(ws), ws.numel(), N, H, S,
-                                                _stream_ptr())
+                                                int(pair_shift), _stream_ptr())
     _check(rc, "lasr_b200_head_forward_total")
 
 
@@ -514,16 +597,16 @@ def head_backward(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_
 
 
 def head_backward_packed(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, grad_sums, aggrs_info,
-                         packed_grad, grad_pp_pair, grad_f_pair, N, H, S):
+                         packed_grad, grad_pp_pair, grad_f_pair, N, H, S, pair_shift=0):
     for t in (image, grad_sums, aggrs_info, packed_grad, grad_pp_pair, grad_f_pair):
         _require_cuda_f32(t, "head tensor")
     ws = torch.empty(int(lib().lasr_b200_head_workspace_bytes(N, H, S)), dtype=torch.uint8, device=image.device)
     with torch.cuda.device(image.device):
-        rc = lib().lasr_b200_head_backward_packed(_p(image), _p(pp_own), _p(pp_pair), _p(f_own), _p(f_pair), _p(imgs),
-                                                  _p(masks), _p(occ), _p(flow_obs), _p(grad_sums), _p(aggrs_info),
-                                                  _p(packed_grad), _p(grad_pp_pair), _p(grad_f_pair), _p(ws), ws.numel(),
-                                                  N, H, S, _stream_ptr())
-    _check(rc, "lasr_b200_head_backward_packed")
+        rc = lib().lasr_b200_head_backward_packed_shift(
+            _p(image), _p(pp_own), _p(pp_pair), _p(f_own), _p(f_pair), _p(imgs), _p(masks), _p(occ), _p(flow_obs),
+            _p(grad_sums), _p(aggrs_info), _p(packed_grad), _p(grad_pp_pair), _p(grad_f_pair), _p(ws), ws.numel(), N, H, S,
+            int(pair_shift), _stream_ptr())
+    _check(rc, "lasr_b200_head_backward_packed_shift")
 
 
 def flow_epilogue_forward(px, pp0, pp1, f0, f1, flow, bgmask, n, S):

@@ -255,8 +255,9 @@ __global__ void __launch_bounds__(kLossThreads) losses_backward_kernel(LossArgs 
 // sums [N,H,7] -> per-(frame,hypothesis) losses sub[3][N*H] (mask, flow, texture) and their means
 // out3[3], following nnutils/mesh_net.py:388-390, 404-416, 440-445.  One block; fixed-order reduction.
 __device__ __forceinline__ void losses_finalize_block(const float* sums, int N, int H, float l1tex_wt, float* sub,
-                                                      float* out3) {   // the first 256 threads of the block work
+                                                      float* out3, bool with_total) {   // the first 256 threads work
   __shared__ float s_red[3][256 / 32];
+  __shared__ float s_out[3];
   const int NH = N * H;
   float acc[3] = {0.f, 0.f, 0.f};
   for (int t = threadIdx.x; t < NH && threadIdx.x < 256; t += 256) {
@@ -282,13 +283,17 @@ __device__ __forceinline__ void losses_finalize_block(const float* sums, int N, 
   if (threadIdx.x < 3) {
     float t = 0.f;
     for (int w = 0; w < 256 / 32; ++w) t += s_red[threadIdx.x][w];
-    out3[threadIdx.x] = t / (float)NH;
+    out3[threadIdx.x] = s_out[threadIdx.x] = t / (float)NH;
+  }
+  if (with_total) {        // out3 has a fourth entry: (mask + flow) + texture, the sum LASR forms of them (mesh_net.py:448)
+    __syncthreads();
+    if (threadIdx.x == 0) out3[3] = __fadd_rn(__fadd_rn(s_out[0], s_out[1]), s_out[2]);
   }
 }
 
 __global__ void __launch_bounds__(256) losses_finalize_kernel(const float* sums, int N, int H, float l1tex_wt,
                                                               float* sub, float* out3) {
-  losses_finalize_block(sums, N, H, l1tex_wt, sub, out3);
+  losses_finalize_block(sums, N, H, l1tex_wt, sub, out3, false);
 }
 
 // Block partials -> sums [N,H,7] -> per-pair losses and the three means, in ONE block (the two steps used to be two
@@ -307,13 +312,13 @@ __global__ void __launch_bounds__(512) losses_reduce_finalize_kernel(const float
     sums[t] = acc;
   }
   __syncthreads();                       // this block's own global writes are visible to it after the barrier
-  losses_finalize_block(sums, N, H, l1tex_wt, sub, out3);
+  losses_finalize_block(sums, N, H, l1tex_wt, sub, out3, true);
 }
 
 // upstream gradients of the three means (g3[3]) and of the per-pair losses (gsub[3][N*H], may be null)
 // -> gradient of every sum (only sums 0, 1, 4, 5 carry gradient to the images)
 __global__ void losses_coef_kernel(const float* sums, const float* g3, const float* gsub, int N, int H,
-                                   float l1tex_wt, float* gsums) {
+                                   float l1tex_wt, float* gsums, int with_total) {
   const int NH = N * H;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= NH) return;
@@ -323,9 +328,10 @@ __global__ void losses_coef_kernel(const float* sums, const float* g3, const flo
   float Bs = 0.f, Cs = 0.f;
   for (int j = 0; j < H; ++j) { Bs += sums[((long long)i * H + j) * kNumSums + 2]; Cs += sums[((long long)i * H + j) * kNumSums + 3]; }
   const float inv = 1.f / (float)NH;
-  const float gm = g3[0] * inv + (gsub ? gsub[t] : 0.f);
-  const float gf = g3[1] * inv + (gsub ? gsub[NH + t] : 0.f);
-  const float gx = g3[2] * inv + (gsub ? gsub[2 * NH + t] : 0.f);
+  const float gt = with_total ? g3[3] : 0.f;          // gradient of the fourth entry, the sum of the three
+  const float gm = (g3[0] + gt) * inv + (gsub ? gsub[t] : 0.f);
+  const float gf = (g3[1] + gt) * inv + (gsub ? gsub[NH + t] : 0.f);
+  const float gx = (g3[2] + gt) * inv + (gsub ? gsub[2 * NH + t] : 0.f);
   float* o = gsums + (long long)t * kNumSums;
   o[0] = gm * 0.5f / V;
   o[1] = q[3] == 0.f ? 0.f : gf * 0.5f / (Bs / Cs) / q[3];
@@ -405,13 +411,23 @@ __global__ void __launch_bounds__(256) flow_epilogue_backward_kernel(const float
   }
 }
 
-__global__ void flow_epilogue_reduce_kernel(const float* partial, int n, int nblk, float* gpp1, float* gf1) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per output (frame, component): lane l adds blocks l, l + 32, ... in order, then a butterfly over the lanes --
+// a fixed order, so the result is deterministic.  (One thread per output walked the nblk partials one dependent load
+// after another: 12 us for 24 outputs of 256 blocks, as long as the head's backward pass itself at LASR's batch size.)
+__global__ void __launch_bounds__(128) flow_epilogue_reduce_kernel(const float* __restrict__ partial, int n, int nblk,
+                                                                   float* gpp1, float* gf1, int shift = 0) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= n * 3) return;
   const int i = t / 3, k = t % 3;
+  const float* src = partial + (long long)i * nblk * 3 + k;
   float acc = 0.f;
-  for (int b = 0; b < nblk; ++b) acc += partial[((long long)i * nblk + b) * 3 + k];
-  if (k < 2) gpp1[2 * i + k] = acc; else gf1[i] = acc;
+#pragma unroll 4
+  for (int b = lane; b < nblk; b += 32) acc += __ldg(src + (long long)b * 3);
+  acc = wsum(acc);
+  if (lane == 0) {
+    const int o = i + shift >= n ? i + shift - n : i + shift;     // the head's pair_shift: the entry frame i read
+    if (k < 2) gpp1[2 * o + k] = acc; else gf1[o] = acc;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -437,7 +453,13 @@ struct HeadArgs {
   const float* occ;        // [N,S,S]
   const float* flow_obs;   // [N,3,S,S]
   int N, H, SS;
+  int pair_shift;          // frame ij reads (and its gradient is written to) entry (ij + pair_shift) mod N*H of the PAIR arrays
 };
+
+__device__ __forceinline__ int head_pair_index(const HeadArgs& A, int ij) {
+  const int j = ij + A.pair_shift;
+  return j >= A.N * A.H ? j - A.N * A.H : j;
+}
 
 struct HeadFlow { float fx, fy, x1, y1, z1; bool bg; };
 
@@ -448,9 +470,9 @@ __device__ __forceinline__ HeadFlow head_flow(const HeadArgs& A, const float* im
   HeadFlow r;
   r.bg = z0 < 1e-9f || z1 < 1e-9f;
   if (r.bg) { x0 = y0 = z0 = 10.f; x1 = y1 = z1 = 10.f; }
-  const float f0 = A.f_own[ij], f1 = A.f_pair[ij];
+  const float f0 = A.f_own[ij], f1 = A.f_pair[head_pair_index(A, ij)];
   const float u0 = A.pp_own[2 * ij] + x0 * f0 / z0, v0 = A.pp_own[2 * ij + 1] + y0 * f0 / z0;
-  const float u1 = A.pp_pair[2 * ij] + x1 * f1 / z1, v1 = A.pp_pair[2 * ij + 1] + y1 * f1 / z1;
+  const float u1 = A.pp_pair[2 * head_pair_index(A, ij)] + x1 * f1 / z1, v1 = A.pp_pair[2 * head_pair_index(A, ij) + 1] + y1 * f1 / z1;
   r.fx = u1 - u0; r.fy = v1 - v0; r.x1 = x1; r.y1 = y1; r.z1 = z1;
   return r;
 }
@@ -471,9 +493,9 @@ __device__ __forceinline__ void head_pixel(const HeadArgs& A, int ij, const floa
     float x0 = x[0], y0 = x[1], z0 = x[2], x1 = x[3], y1 = x[4], z1 = x[5];
     const bool bg = z0 < 1e-9f || z1 < 1e-9f;
     if (bg) { x0 = y0 = z0 = 10.f; x1 = y1 = z1 = 10.f; }
-    const float f0 = A.f_own[ij], f1 = A.f_pair[ij];
+    const float f0 = A.f_own[ij], f1 = A.f_pair[head_pair_index(A, ij)];
     const float u0 = A.pp_own[2 * ij] + x0 * f0 / z0, v0 = A.pp_own[2 * ij + 1] + y0 * f0 / z0;
-    const float u1 = A.pp_pair[2 * ij] + x1 * f1 / z1, v1 = A.pp_pair[2 * ij + 1] + y1 * f1 / z1;
+    const float u1 = A.pp_pair[2 * head_pair_index(A, ij)] + x1 * f1 / z1, v1 = A.pp_pair[2 * head_pair_index(A, ij) + 1] + y1 * f1 / z1;
     const float fx = u1 - u0, fy = v1 - v0;
     if (want_flow) { *flow = make_float2(fx, fy); *bgo = bg ? 1 : 0; }
     if (v && fgm && !bg) {
@@ -604,7 +626,7 @@ __global__ void __launch_bounds__(256) head_backward_kernel(HeadArgs A, const fl
         if (nrm > 0.f) {
           const float c = g1 / (1.f + expf(occ)) / nrm;
           const float ox = c * dx, oy = c * dy;
-          const float f = A.f_pair[ij], iz = 1.f / fl.z1;
+          const float f = A.f_pair[head_pair_index(A, ij)], iz = 1.f / fl.z1;
           gx = ox * f * iz;
           gy = oy * f * iz;
           gz = -(ox * fl.x1 + oy * fl.y1) * f * iz * iz;
@@ -663,8 +685,10 @@ __global__ void __launch_bounds__(256) head_backward_kernel(HeadArgs A, const fl
 
 static int fill_head(HeadArgs& A, const float* image, const float* pp_own, const float* pp_pair, const float* f_own,
                      const float* f_pair, const float* imgs, const float* masks, const float* occ,
-                     const float* flow_obs, int N, int H, int S) {
+                     const float* flow_obs, int N, int H, int S, int pair_shift = 0) {
   if (N <= 0 || H <= 0 || S <= 0) return lasr_fail("head: N, H, S must be positive");
+  if (pair_shift < 0 || pair_shift >= N * H) return lasr_fail("head: pair_shift must lie in [0, N*H)");
+  A.pair_shift = pair_shift;
   if (!image || !pp_own || !pp_pair || !f_own || !f_pair || !imgs || !masks || !occ || !flow_obs)
     return lasr_fail("head: null tensor pointer");
   A.image = image; A.pp_own = pp_own; A.pp_pair = pp_pair; A.f_own = f_own; A.f_pair = f_pair;
@@ -755,14 +779,15 @@ extern "C" int lasr_b200_losses_backward(const float* mask_pred, const float* fl
   return lasr_check_launch("losses_backward_kernel");
 }
 
-extern "C" int lasr_b200_head_backward_packed(const float* image, const float* pp_own, const float* pp_pair,
-                                              const float* f_own, const float* f_pair, const float* imgs,
-                                              const float* masks, const float* occ, const float* flow_obs,
-                                              const float* grad_sums, const float* aggrs_info, float* packed_grad,
-                                              float* grad_pp_pair, float* grad_f_pair, void* workspace,
-                                              size_t workspace_bytes, int N, int H, int S, void* stream) {
+extern "C" int lasr_b200_head_backward_packed_shift(const float* image, const float* pp_own, const float* pp_pair,
+                                                    const float* f_own, const float* f_pair, const float* imgs,
+                                                    const float* masks, const float* occ, const float* flow_obs,
+                                                    const float* grad_sums, const float* aggrs_info, float* packed_grad,
+                                                    float* grad_pp_pair, float* grad_f_pair, void* workspace,
+                                                    size_t workspace_bytes, int N, int H, int S, int pair_shift,
+                                                    void* stream) {
   HeadArgs A{};
-  if (fill_head(A, image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, N, H, S)) return 1;
+  if (fill_head(A, image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, N, H, S, pair_shift)) return 1;
   if (!grad_sums || !aggrs_info || !packed_grad || !grad_pp_pair || !grad_f_pair)
     return lasr_fail("head_backward_packed: null pointer");
   if (!workspace || workspace_bytes < lasr_b200_head_workspace_bytes(N, H, S))
@@ -773,8 +798,20 @@ extern "C" int lasr_b200_head_backward_packed(const float* image, const float* p
   head_backward_kernel<true><<<dim3(nblk, N * H), 256, 0, st>>>(A, grad_sums, nullptr, partial, nblk, aggrs_info,
                                                                   reinterpret_cast<float4*>(packed_grad));
   if (lasr_check_launch("head_backward_kernel<packed>")) return 1;
-  flow_epilogue_reduce_kernel<<<(N * H * 3 + 127) / 128, 128, 0, st>>>(partial, N * H, nblk, grad_pp_pair, grad_f_pair);
+  flow_epilogue_reduce_kernel<<<(N * H * 3 + 3) / 4, 128, 0, st>>>(partial, N * H, nblk, grad_pp_pair, grad_f_pair,
+                                                                   pair_shift);
   return lasr_check_launch("flow_epilogue_reduce_kernel");
+}
+
+extern "C" int lasr_b200_head_backward_packed(const float* image, const float* pp_own, const float* pp_pair,
+                                              const float* f_own, const float* f_pair, const float* imgs,
+                                              const float* masks, const float* occ, const float* flow_obs,
+                                              const float* grad_sums, const float* aggrs_info, float* packed_grad,
+                                              float* grad_pp_pair, float* grad_f_pair, void* workspace,
+                                              size_t workspace_bytes, int N, int H, int S, void* stream) {
+  return lasr_b200_head_backward_packed_shift(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, grad_sums,
+                                              aggrs_info, packed_grad, grad_pp_pair, grad_f_pair, workspace,
+                                              workspace_bytes, N, H, S, 0, stream);
 }
 
 extern "C" int lasr_b200_losses_finalize(const float* sums, float* sub, float* out3, int N, int H, float l1tex_wt,
@@ -784,13 +821,23 @@ extern "C" int lasr_b200_losses_finalize(const float* sums, float* sub, float* o
   return lasr_check_launch("losses_finalize_kernel");
 }
 
+static int coefficients_impl(const float* sums, const float* grad_out, const float* grad_sub, float* grad_sums, int N,
+                             int H, float l1tex_wt, int with_total, void* stream) {
+  if (!sums || !grad_out || !grad_sums || N <= 0 || H <= 0) return lasr_fail("losses_coefficients: bad arguments");
+  const int NH = N * H;
+  losses_coef_kernel<<<(NH + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, grad_out, grad_sub, N, H, l1tex_wt,
+                                                                         grad_sums, with_total);
+  return lasr_check_launch("losses_coef_kernel");
+}
+
 extern "C" int lasr_b200_losses_coefficients(const float* sums, const float* grad_out3, const float* grad_sub,
                                              float* grad_sums, int N, int H, float l1tex_wt, void* stream) {
-  if (!sums || !grad_out3 || !grad_sums || N <= 0 || H <= 0) return lasr_fail("losses_coefficients: bad arguments");
-  const int NH = N * H;
-  losses_coef_kernel<<<(NH + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, grad_out3, grad_sub, N, H, l1tex_wt,
-                                                                         grad_sums);
-  return lasr_check_launch("losses_coef_kernel");
+  return coefficients_impl(sums, grad_out3, grad_sub, grad_sums, N, H, l1tex_wt, 0, stream);
+}
+
+extern "C" int lasr_b200_losses_coefficients_total(const float* sums, const float* grad_out4, const float* grad_sub,
+                                                   float* grad_sums, int N, int H, float l1tex_wt, void* stream) {
+  return coefficients_impl(sums, grad_out4, grad_sub, grad_sums, N, H, l1tex_wt, 1, stream);
 }
 
 extern "C" size_t lasr_b200_flow_epilogue_workspace_bytes(int n, int S) {
@@ -821,7 +868,7 @@ extern "C" int lasr_b200_flow_epilogue_backward(const float* px, const float* f1
   cudaStream_t st = (cudaStream_t)stream;
   flow_epilogue_backward_kernel<<<dim3(nblk, n), 256, 0, st>>>(px, f1, grad_flow, grad_px, partial, n, SS, nblk);
   if (lasr_check_launch("flow_epilogue_backward_kernel")) return 1;
-  flow_epilogue_reduce_kernel<<<(n * 3 + 127) / 128, 128, 0, st>>>(partial, n, nblk, grad_pp1, grad_f1);
+  flow_epilogue_reduce_kernel<<<(n * 3 + 3) / 4, 128, 0, st>>>(partial, n, nblk, grad_pp1, grad_f1);
   return lasr_check_launch("flow_epilogue_reduce_kernel");
 }
 
@@ -838,9 +885,9 @@ extern "C" int lasr_b200_head_forward_total(const float* image, const float* pp_
                                             const float* masks, const float* occ, const float* flow_obs, float* sums,
                                             float* sub, float* out3, float l1tex_wt, float* flow_rd, uint8_t* bgmask,
                                             void* workspace, size_t workspace_bytes, int N, int H, int S,
-                                            void* stream) {
+                                            int pair_shift, void* stream) {
   HeadArgs A{};
-  if (fill_head(A, image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, N, H, S)) return 1;
+  if (fill_head(A, image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, N, H, S, pair_shift)) return 1;
   if (!sums || !workspace || workspace_bytes < lasr_b200_head_workspace_bytes(N, H, S))
     return lasr_fail("head_forward: null output or workspace too small");
   if ((flow_rd == nullptr) != (bgmask == nullptr)) return lasr_fail("head_forward: flow_rd and bgmask go together");
@@ -859,7 +906,7 @@ extern "C" int lasr_b200_head_forward(const float* image, const float* pp_own, c
                                       float* flow_rd, uint8_t* bgmask, void* workspace, size_t workspace_bytes, int N,
                                       int H, int S, void* stream) {
   return lasr_b200_head_forward_total(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, sums, nullptr,
-                                      nullptr, 0.f, flow_rd, bgmask, workspace, workspace_bytes, N, H, S, stream);
+                                      nullptr, 0.f, flow_rd, bgmask, workspace, workspace_bytes, N, H, S, 0, stream);
 }
 
 extern "C" int lasr_b200_head_backward(const float* image, const float* pp_own, const float* pp_pair,
@@ -878,6 +925,6 @@ extern "C" int lasr_b200_head_backward(const float* image, const float* pp_own, 
   float* partial = reinterpret_cast<float*>(workspace);
   head_backward_kernel<false><<<dim3(nblk, N * H), 256, 0, st>>>(A, grad_sums, grad_image, partial, nblk);
   if (lasr_check_launch("head_backward_kernel")) return 1;
-  flow_epilogue_reduce_kernel<<<(N * H * 3 + 127) / 128, 128, 0, st>>>(partial, N * H, nblk, grad_pp_pair, grad_f_pair);
+  flow_epilogue_reduce_kernel<<<(N * H * 3 + 3) / 4, 128, 0, st>>>(partial, N * H, nblk, grad_pp_pair, grad_f_pair);
   return lasr_check_launch("flow_epilogue_reduce_kernel");
 }

@@ -977,11 +977,13 @@ static bool is_fast(const RasterArgs& A) {
 // indexed mode: per-face gradients -> per-vertex gradients through the vertex->corner adjacency
 // (CSR, ascending face order => fixed summation order, no atomics)
 // ---------------------------------------------------------------------------------------------
+struct SetGrads { float* p[kMaxSets]; int shift[kMaxSets]; };   // per colour set: [N,V,3] output (null: not wanted), frame shift
+
 __global__ void __launch_bounds__(256) vertex_gather_kernel(const float* __restrict__ grad_faces,
                                                             const float* __restrict__ grad_textures,
                                                             const int* __restrict__ csr_offsets,
                                                             const int* __restrict__ csr_entries, float* grad_verts,
-                                                            float* grad_vcolors, int N, int V, int F, int K,
+                                                            SetGrads out, int N, int V, int F, int K,
                                                             int first_live) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * V) return;
@@ -1004,8 +1006,10 @@ __global__ void __launch_bounds__(256) vertex_gather_kernel(const float* __restr
   grad_verts[i * 3] = a0; grad_verts[i * 3 + 1] = a1; grad_verts[i * 3 + 2] = a2;
 #pragma unroll
   for (int s = 0; s < kMaxSets; ++s)
-    if (s < K) {
-      float* o = grad_vcolors + ((long long)s * N * V + i) * 3;
+    if (s < K && out.p[s]) {            // the gradient lands in the frame the colours were read from
+      int m = n + out.shift[s];
+      if (m >= N) m -= N;
+      float* o = out.p[s] + ((long long)m * V + v) * 3;
       o[0] = c[3 * s]; o[1] = c[3 * s + 1]; o[2] = c[3 * s + 2];
     }
 }
@@ -1108,26 +1112,41 @@ extern "C" size_t lasr_b200_render_workspace_bytes(int N, int F, int S, int num_
          align256((size_t)N * F * 9 * num_sets * sizeof(float));
 }
 
-static int fill_indexed(RasterArgs& A, const float* verts, const int* tri, const float* vcolors, int V) {
-  if (!verts || !tri || !vcolors || V <= 0) return fail("render: null vertex / topology / colour pointer");
+// colour sets of an indexed render: one stacked tensor [K][N,V,3], or K separate [N,V,3] tensors each read with a frame
+// shift (frame n takes frame (n + shift) mod N: LASR pairs frame i with i +- bs, mesh_net.py:318-335)
+struct ColourSets { const float* p[kMaxSets]; int shift[kMaxSets]; };
+
+static ColourSets stacked_sets(const float* vcolors, int N, int V, int K) {
+  ColourSets c{};
+  for (int s = 0; s < K && s < kMaxSets; ++s) c.p[s] = vcolors ? vcolors + (size_t)s * N * V * 3 : nullptr;
+  return c;
+}
+
+static int fill_indexed(RasterArgs& A, const float* verts, const int* tri, const ColourSets& sets, int V) {
+  if (!verts || !tri || V <= 0) return fail("render: null vertex / topology pointer");
   if (A.sample != 1) return fail("render: the indexed path takes 'vertex' textures");
-  A.verts = verts; A.tri = tri; A.vcolors = vcolors; A.V = V;
+  for (int s = 0; s < A.K; ++s) {
+    if (!sets.p[s]) return fail("render: null colour pointer");
+    if (sets.shift[s] < 0 || sets.shift[s] >= A.N) return fail("render: a colour set's frame shift must lie in [0, N)");
+    A.set_ptr[s] = sets.p[s]; A.set_shift[s] = sets.shift[s];
+  }
+  A.verts = verts; A.tri = tri; A.V = V;
   return 0;
 }
 
-extern "C" int lasr_b200_render_forward(const float* verts, const int32_t* tri, const float* vcolors,
-                                        float* aggrs_info, float* soft_colors, void* workspace,
-                                        size_t workspace_bytes, int N, int V, int F, int S, float near_, float far_,
-                                        const float* near_far_dev, float eps, float sigma_val, int func_id_dist,
-                                        float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
-                                        int double_side, int num_sets, const float* background, void* stream) {
+static int render_forward_impl(const float* verts, const int32_t* tri, const ColourSets& sets,
+                               float* aggrs_info, float* soft_colors, void* workspace,
+                               size_t workspace_bytes, int N, int V, int F, int S, float near_, float far_,
+                               const float* near_far_dev, float eps, float sigma_val, int func_id_dist,
+                               float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
+                               int double_side, int num_sets, const float* background, void* stream) {
   RasterArgs A{};
   if (num_sets < 1 || num_sets > kMaxSets) return fail("render: num_sets must be 1, 2 or 3");
   if (workspace_bytes < lasr_b200_render_workspace_bytes(N, F, S, num_sets)) return fail("render: workspace too small");
   if (fill_args(A, N, F, S, 3, near_, far_, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
                 func_id_rgb, func_id_alpha, 1, double_side, workspace, workspace_bytes, num_sets))
     return 1;
-  if (fill_indexed(A, verts, tri, vcolors, V)) return 1;
+  if (fill_indexed(A, verts, tri, sets, V)) return 1;
   if (!aggrs_info || !soft_colors) return fail("render_forward: null tensor pointer");
   A.aggrs_info = aggrs_info; A.soft_colors = soft_colors;
   if (background) {   // host array of 3*num_sets floats: no pre-fill pass over the image, no read of it here
@@ -1145,10 +1164,49 @@ extern "C" int lasr_b200_render_forward(const float* verts, const int32_t* tri, 
   return launch_forward(A, st);
 }
 
-static int render_backward_impl(const float* verts, const int32_t* tri, const float* vcolors,
+extern "C" int lasr_b200_render_forward(const float* verts, const int32_t* tri, const float* vcolors,
+                                        float* aggrs_info, float* soft_colors, void* workspace,
+                                        size_t workspace_bytes, int N, int V, int F, int S, float near_, float far_,
+                                        const float* near_far_dev, float eps, float sigma_val, int func_id_dist,
+                                        float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
+                                        int double_side, int num_sets, const float* background, void* stream) {
+  if (!vcolors || num_sets < 1 || num_sets > kMaxSets || N <= 0 || V <= 0)
+    return fail("render_forward: null colour pointer or bad num_sets");
+  return render_forward_impl(verts, tri, stacked_sets(vcolors, N, V, num_sets), aggrs_info, soft_colors, workspace,
+                             workspace_bytes, N, V, F, S, near_, far_, near_far_dev, eps, sigma_val, func_id_dist,
+                             dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side, num_sets, background, stream);
+}
+
+static ColourSets separate_sets(const float* const* set_ptrs, const int* set_shifts, int K) {
+  ColourSets c{};
+  for (int s = 0; s < K && s < kMaxSets; ++s) { c.p[s] = set_ptrs ? set_ptrs[s] : nullptr; c.shift[s] = set_shifts ? set_shifts[s] : 0; }
+  return c;
+}
+
+extern "C" int lasr_b200_render_forward_sets(const float* verts, const int32_t* tri, const float* const* set_ptrs,
+                                             const int* set_shifts, float* aggrs_info, float* soft_colors,
+                                             void* workspace, size_t workspace_bytes, int N, int V, int F, int S,
+                                             float near_, float far_, const float* near_far_dev, float eps,
+                                             float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
+                                             int func_id_rgb, int func_id_alpha, int double_side, int num_sets,
+                                             const float* background, void* stream) {
+  if (!set_ptrs || num_sets < 1 || num_sets > kMaxSets) return fail("render_forward_sets: null set array or bad num_sets");
+  return render_forward_impl(verts, tri, separate_sets(set_ptrs, set_shifts, num_sets), aggrs_info, soft_colors,
+                             workspace, workspace_bytes, N, V, F, S, near_, far_, near_far_dev, eps, sigma_val,
+                             func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side, num_sets,
+                             background, stream);
+}
+
+static SetGrads stacked_grads(float* grad_vcolors, int N, int V, int K) {
+  SetGrads g{};
+  for (int s = 0; s < K && s < kMaxSets; ++s) g.p[s] = grad_vcolors ? grad_vcolors + (size_t)s * N * V * 3 : nullptr;
+  return g;
+}
+
+static int render_backward_impl(const float* verts, const int32_t* tri, const ColourSets& sets,
                                 const float* soft_colors, const float* aggrs_info, const float* grad_soft_colors,
                                 const float* packed_grad, const int32_t* csr_offsets, const int32_t* csr_entries,
-                                float* grad_verts, float* grad_vcolors, void* workspace, size_t workspace_bytes, int N,
+                                float* grad_verts, const SetGrads& grad_sets, void* workspace, size_t workspace_bytes, int N,
                                 int V, int F, int S, float near_, float far_, const float* near_far_dev, float eps,
                                 float sigma_val, int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
                                 int func_id_alpha, int double_side, int num_sets, int detached_sets, int setup_done,
@@ -1163,8 +1221,10 @@ static int render_backward_impl(const float* verts, const int32_t* tri, const fl
     return 1;
   A.records_valid = setup_done;
   A.first_live_set = detached_sets;
-  if (fill_indexed(A, verts, tri, vcolors, V)) return 1;
-  if (!csr_offsets || !csr_entries || !grad_verts || !grad_vcolors) return fail("render_backward: null tensor pointer");
+  if (fill_indexed(A, verts, tri, sets, V)) return 1;
+  if (!csr_offsets || !csr_entries || !grad_verts) return fail("render_backward: null tensor pointer");
+  for (int s = detached_sets; s < num_sets; ++s)
+    if (!grad_sets.p[s]) return fail("render_backward: null colour-gradient pointer of a live set");
   if (packed_grad) {
     if (!(num_sets == 3 && detached_sets == 1)) return fail("render_backward_packed: needs three colour sets with the first detached");
     A.packed = reinterpret_cast<const float4*>(packed_grad);
@@ -1188,7 +1248,7 @@ static int render_backward_impl(const float* verts, const int32_t* tri, const fl
   if (launch_backward(A, nf, st)) return 1;
   const long long nv = (long long)N * V;
   vertex_gather_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(A.grad_faces, A.grad_textures, csr_offsets,
-                                                                      csr_entries, grad_verts, grad_vcolors, N, V, F,
+                                                                      csr_entries, grad_verts, grad_sets, N, V, F,
                                                                       num_sets, detached_sets);
   return check_launch("vertex_gather_kernel");
 }
@@ -1203,8 +1263,11 @@ extern "C" int lasr_b200_render_backward(const float* verts, const int32_t* tri,
                                          float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
                                          int func_id_rgb, int func_id_alpha, int double_side, int num_sets,
                                          int detached_sets, int setup_done, void* stream) {
-  return render_backward_impl(verts, tri, vcolors, soft_colors, aggrs_info, grad_soft_colors, nullptr, csr_offsets,
-                              csr_entries, grad_verts, grad_vcolors, workspace, workspace_bytes, N, V, F, S, near_, far_,
+  if (!vcolors || !grad_vcolors || num_sets < 1 || num_sets > kMaxSets || N <= 0 || V <= 0)
+    return fail("render_backward: null colour pointer or bad num_sets");
+  return render_backward_impl(verts, tri, stacked_sets(vcolors, N, V, num_sets), soft_colors, aggrs_info, grad_soft_colors,
+                              nullptr, csr_offsets, csr_entries, grad_verts, stacked_grads(grad_vcolors, N, V, num_sets),
+                              workspace, workspace_bytes, N, V, F, S, near_, far_,
                               near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha,
                               double_side, num_sets, detached_sets, setup_done, stream);
 }
@@ -1218,8 +1281,32 @@ extern "C" int lasr_b200_render_backward_packed(const float* verts, const int32_
                                                 int func_id_rgb, int func_id_alpha, int double_side, int num_sets,
                                                 int detached_sets, int setup_done, void* stream) {
   if (!packed_grad) return fail("render_backward_packed: null packed gradient");
-  return render_backward_impl(verts, tri, vcolors, nullptr, nullptr, nullptr, packed_grad, csr_offsets, csr_entries,
-                              grad_verts, grad_vcolors, workspace, workspace_bytes, N, V, F, S, near_, far_, near_far_dev,
+  if (!vcolors || !grad_vcolors || num_sets < 1 || num_sets > kMaxSets || N <= 0 || V <= 0)
+    return fail("render_backward_packed: null colour pointer or bad num_sets");
+  return render_backward_impl(verts, tri, stacked_sets(vcolors, N, V, num_sets), nullptr, nullptr, nullptr, packed_grad,
+                              csr_offsets, csr_entries, grad_verts, stacked_grads(grad_vcolors, N, V, num_sets),
+                              workspace, workspace_bytes, N, V, F, S, near_, far_, near_far_dev,
                               eps, sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side,
+                              num_sets, detached_sets, setup_done, stream);
+}
+
+extern "C" int lasr_b200_render_backward_sets_packed(const float* verts, const int32_t* tri, const float* const* set_ptrs,
+                                                     const int* set_shifts, const float* packed_grad,
+                                                     const int32_t* csr_offsets, const int32_t* csr_entries,
+                                                     float* grad_verts, float* const* grad_set_ptrs, void* workspace,
+                                                     size_t workspace_bytes, int N, int V, int F, int S, float near_,
+                                                     float far_, const float* near_far_dev, float eps, float sigma_val,
+                                                     int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
+                                                     int func_id_alpha, int double_side, int num_sets, int detached_sets,
+                                                     int setup_done, void* stream) {
+  if (!packed_grad) return fail("render_backward_sets_packed: null packed gradient");
+  if (!set_ptrs || !grad_set_ptrs || num_sets < 1 || num_sets > kMaxSets)
+    return fail("render_backward_sets_packed: null set array or bad num_sets");
+  const ColourSets sets = separate_sets(set_ptrs, set_shifts, num_sets);
+  SetGrads g{};
+  for (int s = 0; s < num_sets; ++s) { g.p[s] = grad_set_ptrs[s]; g.shift[s] = sets.shift[s]; }
+  return render_backward_impl(verts, tri, sets, nullptr, nullptr, nullptr, packed_grad, csr_offsets, csr_entries,
+                              grad_verts, g, workspace, workspace_bytes, N, V, F, S, near_, far_, near_far_dev, eps,
+                              sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side,
                               num_sets, detached_sets, setup_done, stream);
 }

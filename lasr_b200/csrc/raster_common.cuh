@@ -62,7 +62,8 @@ struct RasterArgs {
   const float* near_far_dev; // optional {near, far} on device
   // indexed ("fused") input mode: faces/textures are gathered on the fly from per-vertex arrays
   const float* verts;        // [N,V,3] clip-space vertices   (null: direct mode, use `faces`)
-  const float* vcolors;      // [K][N,V,3] vertex colours, K colour sets sharing one geometry pass
+  const float* set_ptr[kMaxSets];  // colour set s: [N,V,3] vertex colours; frame n reads frame (n + set_shift[s]) mod N of it
+  int set_shift[kMaxSets];         //   (one stacked [K][N,V,3] tensor is the special case ptr + s*N*V*3, shift 0)
   int K;                     // number of colour sets (1 on the reference-signature paths); images have 3K+1 planes
   int first_live_set;        // backward: colour sets below this index are detached (no gradient read / written)
   int bg_in_args;            // forward: background colours come from bg[] instead of a pre-filled soft_colors
@@ -88,7 +89,9 @@ __device__ __forceinline__ void fetch_face(const RasterArgs& A, int n, int f, fl
 #pragma unroll
       for (int s = 0; s < kMaxSets; ++s) {
         if (s < A.K) {
-          const float* cb = A.vcolors + ((long long)s * A.N + n) * A.V * 3;
+          int m = n + A.set_shift[s];
+          if (m >= A.N) m -= A.N;
+          const float* cb = A.set_ptr[s] + (long long)m * A.V * 3;
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             tex9[9 * s + k] = cb[3 * i0 + k]; tex9[9 * s + 3 + k] = cb[3 * i1 + k]; tex9[9 * s + 6 + k] = cb[3 * i2 + k];

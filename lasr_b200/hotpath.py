@@ -127,12 +127,13 @@ class RenderHotPath(torch.nn.Module):
         if mp.is_cuda and o.opt_tex:
             mask_loss, flow_loss, texture_loss, sub = L.image_losses(mp, batch["masks"], batch["occ"], fr, bgm,
                                                                      batch["flow"], tr, mp, batch["imgs"], o.l1tex_wt)
+            total = sub["total"]          # (mask + flow) + texture, out of the loss kernels' own launch
         else:
             mask_loss, _ = L.mask_loss(mp, batch["masks"], batch["occ"])
             flow_loss, _, _ = L.flow_loss(fr, bgm, batch["flow"], batch["occ"], batch["masks"])
             texture_loss = (L.texture_l1_loss(tr, mp, batch["imgs"], batch["masks"], batch["occ"], o.l1tex_wt)[0]
                             if o.opt_tex else mask_loss * 0)
-        total = mask_loss + flow_loss + (texture_loss if o.opt_tex else 0)
+            total = mask_loss + flow_loss + (texture_loss if o.opt_tex else 0)
         return dict(total=total, mask_loss=mask_loss, flow_loss=flow_loss, texture_loss=texture_loss,
                     mask_pred=mask_pred, texture_render=rgb, flow_rd=flow_rd, bgmask=bgmask, verts_px=verts_px,
                     near=near, far=far)
@@ -187,32 +188,47 @@ class RenderHotPath(torch.nn.Module):
             offset = gu._eye_offset(r, verts_px.device)
             pre = (verts_px[:, :, :3] + offset) * _const([1.0, -1.0, 1.0], verts_px.device)   # y flip (:83), exact
         own = cam                                            # camera-space positions [n2*H,V,3]
-        pair = torch.roll(own.view(n2, H, -1, 3), bs, 0).reshape(nh, -1, 3)     # frame i <-> i +- bs
-        sets = torch.stack([own, pair, tex.reshape(nh, -1, 3).to(own.dtype)], 0)
+        texc = tex.reshape(nh, -1, 3).to(own.dtype)
         faces_h = faces if H == 1 else faces[:, None].repeat(1, H, 1, 1).view(-1, faces.shape[1], 3)
         link = sr.functional.PackedGradLink() if (o.packed_grad and torch.is_grad_enabled()) else None
-        r.rasterizer.background_color = [0, 0, 0, 0, 0, 0, 1, 1, 1]
-        r.rasterizer.detached_sets = 1          # own positions enter the flow only under .detach() (:102-103)
-        r.rasterizer.grad_link = link
-        try:
-            if view is not None:     # the LBS kernel already wrote what lighting (x 1) and the camera make of the mesh
-                r.set_texture_mode("vertex")
-                image = r.rasterizer(sr.Mesh(view, faces_h, textures=sets, texture_type="vertex", shared_faces=shared_faces))
-            else:
-                image = r.render_mesh(sr.Mesh(pre, faces_h, textures=sets, texture_type="vertex", shared_faces=shared_faces))
-        finally:                                # the renderer is shared state: never leave the K = 3 settings behind
-            r.rasterizer.background_color = [1, 1, 1]
-            r.rasterizer.detached_sets = 0
-            r.rasterizer.grad_link = None
+        bg9 = [0, 0, 0, 0, 0, 0, 1, 1, 1]
         rep = (lambda t: t) if H == 1 else (lambda t: t[:, None].repeat(1, H, 1).view(nh, 2))   # one hypothesis: no copies
         pp_own = rep(ppoint)
-        pp_pair = rep(torch.roll(ppoint, bs, 0))
         f_own = scale.view(n2, H, -1)[:, :, 0].reshape(nh)
-        f_pair = torch.roll(scale.view(n2, H, -1)[:, :, 0], bs, 0).reshape(nh)
+        # frame i pairs with frame i +- bs (mesh_net.py:318-335): entry (n + bs*H) mod n2*H of the same tensors
+        shifted = view is not None and (link is not None or not torch.is_grad_enabled())
+        if shifted:
+            # the LBS kernel already wrote what lighting (x 1) and the camera make of the mesh, and the pair's positions
+            # and intrinsics are the own ones read half a batch further on: no rolled copies, no stacked colour tensor
+            rz = r.rasterizer
+            tri = shared_faces if shared_faces is not None else sr.functional.shared_topology(faces_h)
+            image = sr.functional.render_sets(view, (own, own, texc), (0, bs * H, 0), tri, rz.image_size, bg9, near, far,
+                                              rz.fill_back, rz.eps, rz.sigma_val, rz.dist_func, rz.dist_eps, rz.gamma_val,
+                                              rz.aggr_func_rgb, rz.aggr_func_alpha, grad_link=link)
+            pp_pair, f_pair, pair_shift = pp_own, f_own, bs * H
+        else:
+            pair = torch.roll(own.view(n2, H, -1, 3), bs, 0).reshape(nh, -1, 3)
+            sets = torch.stack([own, pair, texc], 0)
+            r.rasterizer.background_color = bg9
+            r.rasterizer.detached_sets = 1          # own positions enter the flow only under .detach() (:102-103)
+            r.rasterizer.grad_link = link
+            try:
+                if view is not None:
+                    r.set_texture_mode("vertex")
+                    image = r.rasterizer(sr.Mesh(view, faces_h, textures=sets, texture_type="vertex", shared_faces=shared_faces))
+                else:
+                    image = r.render_mesh(sr.Mesh(pre, faces_h, textures=sets, texture_type="vertex", shared_faces=shared_faces))
+            finally:                                # the renderer is shared state: never leave the K = 3 settings behind
+                r.rasterizer.background_color = [1, 1, 1]
+                r.rasterizer.detached_sets = 0
+                r.rasterizer.grad_link = None
+            pp_pair = rep(torch.roll(ppoint, bs, 0))
+            f_pair = torch.roll(scale.view(n2, H, -1)[:, :, 0], bs, 0).reshape(nh)
+            pair_shift = 0
         mask_loss, flow_loss, texture_loss, sub, flow_rd, bgmask = L.fused_head(
             image, pp_own, pp_pair, f_own, f_pair, batch["imgs"], batch["masks"], batch["occ"], batch["flow"], n2, H,
-            o.l1tex_wt, want_flow=o.report_flow, grad_link=link)
-        total = mask_loss + flow_loss + texture_loss
+            o.l1tex_wt, want_flow=o.report_flow, grad_link=link, pair_shift=pair_shift)
+        total = sub.pop("total")            # (mask + flow) + texture, out of the head's own launch
         shown = image.detach() if link is not None else image     # packed gradients: the image is for reporting only
         return dict(total=total, mask_loss=mask_loss, flow_loss=flow_loss, texture_loss=texture_loss,
                     mask_pred=shown[:, 9], texture_render=shown[:, 6:9], flow_rd=flow_rd, bgmask=bgmask,

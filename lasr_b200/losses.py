@@ -13,6 +13,15 @@ import torch
 from torch.autograd import Function
 
 
+def _as_u8(mask):
+    """A boolean mask as the kernels read it (one byte per pixel, non-zero = set): a bool tensor is reinterpreted in
+    place (same storage, no conversion kernel); anything else is converted."""
+    m = mask.detach()
+    if m.dtype == torch.bool:
+        return m.contiguous().view(torch.uint8)
+    return m.to(torch.uint8).contiguous()
+
+
 class _LossSums(Function):
     """[N,H,7] masked sums of lasr_b200/csrc/losses.cu (see the layout there); differentiable w.r.t.
     mask_pred, flow_rd, texture_render and fgmask."""
@@ -23,7 +32,7 @@ class _LossSums(Function):
         N, H, S = mask_pred.shape[0], mask_pred.shape[1], mask_pred.shape[-1]
         c = lambda t: None if t is None else t.detach().float().contiguous()
         mp, fr, tx, fgc, im, mk, oc, fo = (c(t) for t in (mask_pred, flow_rd, tex, fg, imgs, masks, occ, flow_obs))
-        bg = None if bgmask is None else bgmask.detach().to(torch.uint8).contiguous()
+        bg = None if bgmask is None else _as_u8(bgmask)
         sums = torch.empty(N, H, 7, dtype=torch.float32, device=mask_pred.device)
         _cabi.losses_forward(mp, fr, bg, tx, fgc, im, mk, oc, fo, sums, N, H, S)
         ctx.save_for_backward(*[t for t in (mp, fr, bg, tx, fgc, im, mk, oc, fo) if t is not None])
@@ -57,14 +66,15 @@ class _FusedImageLosses(Function):
         N, H, S = mask_pred.shape[0], mask_pred.shape[1], mask_pred.shape[-1]
         c = lambda t: t.detach().float().contiguous()
         mp, fr, tx, fgc, im, mk, oc, fo = (c(t) for t in (mask_pred, flow_rd, tex, fg, imgs, masks, occ, flow_obs))
-        bg = bgmask.detach().to(torch.uint8).contiguous()
+        bg = _as_u8(bgmask)
         dev = mask_pred.device
         sums = torch.empty(N, H, 7, dtype=torch.float32, device=dev)
         sub = torch.empty(3, N, H, dtype=torch.float32, device=dev)
-        out3 = torch.empty(3, dtype=torch.float32, device=dev)
+        out3 = torch.empty(4, dtype=torch.float32, device=dev)     # three means and their sum
         _cabi.losses_forward(mp, fr, bg, tx, fgc, im, mk, oc, fo, sums, N, H, S, sub, out3, l1tex_wt)
         ctx.save_for_backward(mp, fr, bg, tx, fgc, im, mk, oc, fo, sums)
         ctx.dims = (N, H, S, float(l1tex_wt))
+        ctx.set_materialize_grads(False)        # an unused output (the per-pair losses) costs no zero-fill in the backward
         return out3, sub
 
     @staticmethod
@@ -73,7 +83,7 @@ class _FusedImageLosses(Function):
         mp, fr, bg, tx, fgc, im, mk, oc, fo, sums = ctx.saved_tensors
         N, H, S, wt = ctx.dims
         dev = mp.device
-        g3 = torch.zeros(3, device=dev) if g_out3 is None else g_out3.float().contiguous()
+        g3 = torch.zeros(4, device=dev) if g_out3 is None else g_out3.float().contiguous()
         gsub = None if g_sub is None else g_sub.float().contiguous()
         gsums = torch.empty_like(sums)
         _cabi.losses_coefficients(sums, g3, gsub, gsums, N, H, wt)
@@ -94,7 +104,7 @@ class _FusedHead(Function):
 
     @staticmethod
     def forward(ctx, image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, l1tex_wt, N, H, want_flow,
-                grad_link=None):
+                grad_link=None, pair_shift=0):
         from . import _cabi
         S = image.shape[-1]
         dev = image.device
@@ -109,14 +119,19 @@ class _FusedHead(Function):
             flow_rd = torch.empty(N * H, S, S, 2, dtype=torch.float32, device=dev)
             bg = torch.empty(N * H, S, S, dtype=torch.uint8, device=dev)
         sub = torch.empty(3, N, H, dtype=torch.float32, device=dev)
-        out3 = torch.empty(3, dtype=torch.float32, device=dev)
-        _cabi.head_forward(img, po, pq, fo, fq, im, mk, oc, fl, sums, flow_rd, bg, N, H, S, sub, out3, l1tex_wt)
+        out3 = torch.empty(4, dtype=torch.float32, device=dev)     # three means and their sum
+        if pair_shift and grad_link is None and torch.is_grad_enabled():
+            raise ValueError("fused_head(pair_shift=...) differentiates through the packed gradient only: pass grad_link")
+        _cabi.head_forward(img, po, pq, fo, fq, im, mk, oc, fl, sums, flow_rd, bg, N, H, S, sub, out3, l1tex_wt,
+                           pair_shift)
+        ctx.pair_shift = int(pair_shift)
         ctx.save_for_backward(img, po, pq, fo, fq, im, mk, oc, fl, sums)
         ctx.dims = (N, H, S, float(l1tex_wt))
         ctx.shapes = (pp_pair.shape, f_pair.shape)
         ctx.grad_link = grad_link
+        ctx.set_materialize_grads(False)
         if want_flow:
-            bgb = bg.bool()
+            bgb = bg.view(torch.bool)          # the kernel wrote 0 / 1
             ctx.mark_non_differentiable(flow_rd, bgb)
             return out3, sub, flow_rd, bgb
         return out3, sub, None, None
@@ -127,7 +142,7 @@ class _FusedHead(Function):
         img, po, pq, fo, fq, im, mk, oc, fl, sums = ctx.saved_tensors
         N, H, S, wt = ctx.dims
         dev = img.device
-        g3 = torch.zeros(3, device=dev) if g_out3 is None else g_out3.float().contiguous()
+        g3 = torch.zeros(4, device=dev) if g_out3 is None else g_out3.float().contiguous()
         gsub = None if g_sub is None else g_sub.float().contiguous()
         gsums = torch.empty_like(sums)
         _cabi.losses_coefficients(sums, g3, gsub, gsums, N, H, wt)
@@ -141,23 +156,27 @@ class _FusedHead(Function):
             # packed per-pixel gradient for the rasterizer's backward; autograd carries a zero-stride placeholder
             link.packed = torch.empty(N * H, 3, S * S, 4, dtype=torch.float32, device=dev)
             _cabi.head_backward_packed(img, po, pq, fo, fq, im, mk, oc, fl, gsums, link.aggrs, link.packed, gpp, gf,
-                                       N, H, S)
+                                       N, H, S, ctx.pair_shift)
             gimg = link.make_placeholder(img)
         else:
+            if ctx.pair_shift:
+                raise RuntimeError("fused_head(pair_shift=...): the planar backward has no shifted form")
             gimg = torch.empty_like(img)
             _cabi.head_backward(img, po, pq, fo, fq, im, mk, oc, fl, gsums, gimg, gpp, gf, N, H, S)
         return (gimg, None, gpp.reshape(ctx.shapes[0]), None, gf.reshape(ctx.shapes[1]), None, None, None, None,
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 def fused_head(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs, n_frames, n_hypo, l1tex_wt=1.0,
-               want_flow=True, grad_link=None):
-    """image [N*H,10,S,S] from the three-set render -> (mask_loss, flow_loss, texture_loss, per-pair dict,
-    flow_rd [N*H,S,S,2] | None, bgmask [N*H,S,S] bool | None).  The flow outputs are for reporting only
-    (not differentiable: their gradient path is inside the losses)."""
+               want_flow=True, grad_link=None, pair_shift=0):
+    """image [N*H,10,S,S] from the three-set render -> (mask_loss, flow_loss, texture_loss, per-pair dict (+ "total":
+    (mask + flow) + texture, formed in the kernel), flow_rd [N*H,S,S,2] | None, bgmask [N*H,S,S] bool | None).  The flow outputs are for reporting only
+    (not differentiable: their gradient path is inside the losses).
+    pair_shift: frame ij takes entry (ij + pair_shift) mod N*H of pp_pair / f_pair (pass the own tensors again and
+    bs * n_hypo instead of rolled copies; needs grad_link when differentiated)."""
     out3, sub, flow_rd, bg = _FusedHead.apply(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs,
-                                              l1tex_wt, n_frames, n_hypo, want_flow, grad_link)
-    return out3[0], out3[1], out3[2], dict(mask=sub[0], flow=sub[1], texture=sub[2]), flow_rd, bg
+                                              l1tex_wt, n_frames, n_hypo, want_flow, grad_link, pair_shift)
+    return out3[0], out3[1], out3[2], dict(mask=sub[0], flow=sub[1], texture=sub[2], total=out3[3]), flow_rd, bg
 
 
 def _native(t):
@@ -236,4 +255,4 @@ def image_losses(mask_pred, masks, occ, flow_rd, bgmask, flow_obs, texture_rende
     mesh_net.py:358-359) their gradients are summed by autograd as usual."""
     out3, sub = _FusedImageLosses.apply(mask_pred, flow_rd, bgmask, texture_render, fgmask, imgs, masks, occ,
                                         flow_obs, l1tex_wt)
-    return out3[0], out3[1], out3[2], dict(mask=sub[0], flow=sub[1], texture=sub[2])
+    return out3[0], out3[1], out3[2], dict(mask=sub[0], flow=sub[1], texture=sub[2], total=out3[3])

@@ -60,6 +60,7 @@ class SkinProjectFunction(Function):
         outs = [cam, px if project else cam.new_empty(0), nf if want_depth_window else cam.new_empty(0),
                 view if view is not None else cam.new_empty(0)]
         ctx.mark_non_differentiable(outs[2])
+        ctx.set_materialize_grads(False)         # an output nobody differentiates (px on the fused route) costs no zero-fill
         if not project:
             ctx.mark_non_differentiable(outs[1])
         if view is None:

@@ -1,7 +1,8 @@
 from .geometry import (ambient_lighting, directional_lighting, face_vertices, get_points_from_angles, look, look_at,
                        orthogonal, perspective, projection, vertex_normals)
 from .obj_io import create_texture_image, load_mtl, load_obj, load_textures, save_obj
-from .render_indexed import PackedGradLink, RenderIndexedFunction, render_indexed, shared_topology, vertex_adjacency
+from .render_indexed import (PackedGradLink, RenderIndexedFunction, RenderSetsFunction, render_indexed, render_sets,
+                             shared_topology, vertex_adjacency)
 from .soft_rasterize import SoftRasterizeFunction, soft_rasterize
 
 

@@ -82,13 +82,20 @@ class PackedGradLink:
         self.packed = None       # [N,3,S*S,4] set by the head's backward
         self.placeholder = None
 
+    _zero = {}                   # (device, dtype) -> 0-dim zero, made once: a placeholder costs no fill kernel per step
+
     def make_placeholder(self, like):
-        self.placeholder = torch.zeros((), dtype=like.dtype, device=like.device).expand(like.shape)
+        key = (like.device, like.dtype)
+        z = PackedGradLink._zero.get(key)
+        if z is None:
+            z = PackedGradLink._zero[key] = torch.zeros((), dtype=like.dtype, device=like.device)
+        self.placeholder = z.expand(like.shape)
         return self.placeholder
 
     def is_placeholder(self, grad):
         p = self.placeholder
-        return p is not None and grad.data_ptr() == p.data_ptr() and all(st == 0 for st in grad.stride())
+        return (p is not None and self.packed is not None and grad.data_ptr() == p.data_ptr()
+                and all(st == 0 for st in grad.stride()))
 
 
 class RenderIndexedFunction(Function):
@@ -158,6 +165,76 @@ class RenderIndexedFunction(Function):
                                   ctx.near, ctx.far, ctx.nf, *ctx.scal, setup_done=ctx.keep_ws, detached_sets=ctx.detached)
         vshape, cshape = ctx.shapes
         return (gv.reshape(vshape), gc.reshape(cshape)) + (None,) * 15
+
+
+class RenderSetsFunction(Function):
+    """Three colour sets given as SEPARATE [N,V,3] tensors, each read with a frame shift (lasr_b200_render_forward_sets /
+    lasr_b200_render_backward_sets_packed): the fused region's form of render_indexed -- set 0 (detached) and set 1 are
+    the same camera-space vertices, set 1 shifted by half the batch, so no rolled copy and no stacked tensor exist and
+    the colour gradients come back per tensor.  Differentiated through a PackedGradLink only."""
+
+    @staticmethod
+    def forward(ctx, vertices, set0, set1, set2, shifts, tri, image_size, background_color, near, far, fill_back, eps,
+                sigma_val, dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha, grad_link=None):
+        if not vertices.is_cuda:
+            raise _cabi.CudaTensorRequired("Rasterize module supports only cuda Tensors")
+        dev = vertices.device
+        N, V = vertices.shape[:2]
+        S = int(image_size)
+        v = vertices.detach().float().contiguous()
+        sets = [t.detach().float().reshape(N, V, 3).contiguous() for t in (set0, set1, set2)]
+        ctx.shifts = tuple(int(x) for x in shifts)
+        ctx.scal = (eps, sigma_val, DIST_FUNCS[dist_func], float(np.log(1.0 / dist_eps - 1.0)), gamma_val,
+                    RGB_FUNCS[aggr_func_rgb], ALPHA_FUNCS[aggr_func_alpha], bool(fill_back))
+        ctx.near, ctx.far, ctx.nf = _near_far(near, far, dev)
+        ctx.S = S
+        bg = [float(x) for x in np.asarray(background_color, dtype=np.float64).reshape(-1)]
+        if len(bg) != 9:
+            raise ValueError("background_color needs 3 values per colour set")
+        aggrs = torch.empty(N, 2, S, S, dtype=torch.float32, device=dev)
+        img = torch.empty(N, 10, S, S, dtype=torch.float32, device=dev)
+        ws = _cabi.render_workspace(N, tri.shape[0], S, dev, 3)
+        _cabi.render_forward_sets(v, tri, sets, ctx.shifts, aggrs, img, ws, S, ctx.near, ctx.far, ctx.nf, *ctx.scal,
+                                  background=bg)
+        offsets, entries = vertex_adjacency(tri, V)
+        ctx.keep_ws = bool(sys.modules[SoftRasterizeFunction.__module__].KEEP_WORKSPACE)
+        ctx.save_for_backward(v, tri, offsets, entries, *sets, *([ws] if ctx.keep_ws else []))
+        ctx.shapes = (vertices.shape, set1.shape, set2.shape)
+        ctx.grad_link = grad_link
+        if grad_link is not None:
+            grad_link.aggrs = aggrs
+        return img
+
+    @staticmethod
+    def backward(ctx, grad):
+        v, tri, offsets, entries, s0, s1, s2 = ctx.saved_tensors[:7]
+        N, V = v.shape[:2]
+        ws = ctx.saved_tensors[7] if ctx.keep_ws else _cabi.render_workspace(N, tri.shape[0], ctx.S, v.device, 3)
+        link = ctx.grad_link
+        if link is None or link.packed is None:
+            raise RuntimeError("render_sets: the backward takes the packed gradient of lasr_b200.losses.fused_head "
+                               "(pass the same PackedGradLink to both)")
+        if not link.is_placeholder(grad):
+            raise RuntimeError("render_sets(grad_link=...): the rendered image received gradient from something other "
+                               "than the fused head")
+        packed, link.packed, link.placeholder = link.packed, None, None
+        gv, g1, g2 = torch.empty_like(v), torch.empty_like(s1), torch.empty_like(s2)
+        _cabi.render_backward_sets_packed(v, tri, (s0, s1, s2), ctx.shifts, packed, offsets, entries, gv, (None, g1, g2),
+                                          ws, ctx.S, ctx.near, ctx.far, ctx.nf, *ctx.scal, setup_done=ctx.keep_ws,
+                                          detached_sets=1)
+        vshape, s1shape, s2shape = ctx.shapes
+        return (gv.reshape(vshape), None, g1.reshape(s1shape), g2.reshape(s2shape)) + (None,) * 15
+
+
+def render_sets(vertices, sets, shifts, tri, image_size=256, background_color=(0,) * 9, near=1, far=100, fill_back=True,
+                eps=1e-3, sigma_val=1e-5, dist_func="euclidean", dist_eps=1e-4, gamma_val=1e-4, aggr_func_rgb="softmax",
+                aggr_func_alpha="prod", grad_link=None):
+    """sets: three [N,V,3] tensors (the first rendered for reading only), shifts: three ints in [0, N) -- frame n of
+    the image [N,10,S,S] shows frame (n + shift) mod N of each set.  Same image as render_indexed of the stacked,
+    rolled sets with detached_sets=1."""
+    return RenderSetsFunction.apply(vertices, sets[0], sets[1], sets[2], tuple(shifts), tri, image_size, background_color,
+                                    near, far, fill_back, eps, sigma_val, dist_func, dist_eps, gamma_val, aggr_func_rgb,
+                                    aggr_func_alpha, grad_link)
 
 
 def render_indexed(vertices, vcolors, tri, image_size=256, background_color=[0, 0, 0], near=1, far=100,

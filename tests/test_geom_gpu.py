@@ -152,11 +152,17 @@ def test_fused_image_losses_match_cpu_expressions(dev):
     c = lambda x: t(x).float().contiguous()
     args = (c(mask_pred), c(flow_rd), t(bg).to(torch.uint8).contiguous(), c(tex), c(fg), c(imgs), c(masks), c(occ), c(flow_obs))
     e = lambda *sh: torch.full(sh, float("nan"), device=dev)
-    s1, s2, sub1, sub2, o1, o2 = e(N, H, 7), e(N, H, 7), e(3, N, H), e(3, N, H), e(3), e(3)
+    s1, s2, sub1, sub2, o1, o2 = e(N, H, 7), e(N, H, 7), e(3, N, H), e(3, N, H), e(3), e(4)
     _cabi.losses_forward(*args, s1, N, H, S)
     _cabi.losses_finalize(s1, sub1, o1, N, H, 0.7)
-    _cabi.losses_forward(*args, s2, N, H, S, sub2, o2, 0.7)
-    assert torch.equal(s1, s2) and torch.equal(sub1, sub2) and torch.equal(o1, o2) and bool(torch.isfinite(o2).all())
+    _cabi.losses_forward(*args, s2, N, H, S, sub2, o2, 0.7)       # + a fourth entry: the sum of the three
+    assert torch.equal(s1, s2) and torch.equal(sub1, sub2) and torch.equal(o1, o2[:3]) and bool(torch.isfinite(o2).all())
+    assert float(o2[3]) == float((o1[0] + o1[1]) + o1[2])
+    # and its adjoint: the gradient of the sum reaches every sum exactly as the same gradient on the three means does
+    g1, g2 = e(N, H, 7), e(N, H, 7)
+    _cabi.losses_coefficients(s1, torch.tensor([1.5, 1.5, 1.5], device=dev), None, g1, N, H, 0.7)
+    _cabi.losses_coefficients(s1, torch.tensor([0.0, 0.0, 0.0, 1.5], device=dev), None, g2, N, H, 0.7)
+    assert torch.equal(g1, g2)
 
 
 @pytest.mark.parametrize("H,Bp,V", [(1, 25, 2930), (2, 7, 642), (1, 1, 100)])

@@ -402,3 +402,58 @@ def test_kernel_written_render_space_vertices_equal_the_pytorch_chain(monkeypatc
     for k in b:
         err = float((a[k] - b[k]).norm() / b[k].norm())
         assert err < 1e-6, (k, err)
+
+
+def test_separate_colour_sets_with_a_frame_shift_equal_the_stacked_rolled_render():
+    """lasr_b200_render_forward_sets / _backward_sets_packed and the head's pair_shift: the pair's positions and
+    intrinsics are the own tensors read half a batch further on.  Same image bit for bit as the stacked [3,N,V,3] render
+    of (own, roll(own), tex); same losses; the gradients of the ONE position tensor, of the texture, of the vertices and
+    of the ONE intrinsics tensor equal what autograd forms through the roll."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import lasr_b200.soft_renderer as sr
+    from lasr_b200 import losses as L, synth
+    dev = torch.device("cuda", 0)
+    v, f = synth.icosphere(2, 0.5)
+    N, S, bs = 6, 48, 3
+    px, cam, near, far = synth.render_inputs(v, f, N)
+    tri = torch.from_numpy(f).int().to(dev)
+    g = torch.Generator().manual_seed(3)
+    own0 = torch.from_numpy(cam).float() + torch.randn(N, len(v), 3, generator=g) * 0.01
+    tex0 = torch.rand(N, len(v), 3, generator=g)
+    pp0, f0 = torch.randn(N, 2, generator=g) * 0.02, 10 + torch.rand(N, generator=g)
+    obs = dict(imgs=torch.rand(N, 3, S, S, generator=g), masks=(torch.rand(N, S, S, generator=g) > 0.5).float(),
+               occ=torch.randn(N, S, S, generator=g), flow=torch.randn(N, 3, S, S, generator=g) * 0.05)
+    obs = {k: x.to(dev) for k, x in obs.items()}
+    kw = dict(image_size=S, near=near, far=far, sigma_val=1e-4, gamma_val=1e-2)
+    bg9 = [0] * 6 + [1] * 3
+
+    def run(shifted):
+        verts = torch.from_numpy(px).to(dev).requires_grad_(True)
+        own, tex = own0.clone().to(dev).requires_grad_(True), tex0.clone().to(dev).requires_grad_(True)
+        pp, fl = pp0.clone().to(dev).requires_grad_(True), f0.clone().to(dev).requires_grad_(True)
+        link = sr.functional.PackedGradLink()
+        if shifted:
+            img = sr.functional.render_sets(verts, (own, own, tex), (0, bs, 0), tri, background_color=bg9, grad_link=link, **kw)
+            out = L.fused_head(img, pp, pp, fl, fl, obs["imgs"], obs["masks"], obs["occ"], obs["flow"], N, 1, 0.7,
+                               grad_link=link, pair_shift=bs)
+        else:
+            sets = torch.stack([own, torch.roll(own, bs, 0), tex], 0)
+            img = sr.functional.render_indexed(verts, sets, tri, background_color=bg9, detached_sets=1, grad_link=link, **kw)
+            out = L.fused_head(img, pp, torch.roll(pp, bs, 0), fl, torch.roll(fl, bs, 0), obs["imgs"], obs["masks"],
+                               obs["occ"], obs["flow"], N, 1, 0.7, grad_link=link)
+        out[3]["total"].backward()
+        return img.detach(), [float(x) for x in out[:3]] + [float(out[3]["total"])], out[4], \
+            [x.grad.clone() for x in (verts, own, tex, pp, fl)]
+
+    img_a, loss_a, flow_a, grads_a = run(True)
+    img_b, loss_b, flow_b, grads_b = run(False)
+    assert torch.equal(img_a, img_b) and torch.equal(flow_a, flow_b)
+    assert loss_a == loss_b
+    for nm, x, y in zip(("verts", "own", "tex", "pp", "f"), grads_a, grads_b):
+        assert float(y.abs().max()) > 0, nm
+        assert torch.allclose(x, y, rtol=1e-5, atol=1e-9 + 1e-6 * float(y.abs().max())), (nm, float((x - y).abs().max()))
+    # differentiating the shifted head without the packed link is refused, not silently wrong
+    with pytest.raises(ValueError, match="pair_shift"):
+        L.fused_head(img_a.requires_grad_(True), pp0.to(dev), pp0.to(dev), f0.to(dev), f0.to(dev), obs["imgs"], obs["masks"],
+                     obs["occ"], obs["flow"], N, 1, 0.7, pair_shift=bs)
