@@ -22,6 +22,7 @@
 
 #include "host_common.h"
 #include "lasr_b200.h"
+#include "raster_common.cuh"   // warp_sum16
 
 namespace lasr {
 
@@ -170,29 +171,15 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   return v;
 }
 
-// Block-reduce K values per thread into out[0..K) in a fixed order: warp butterflies, then thread j
-// adds the 8 warp sums of value j in warp order.  Must be called by every thread of the block.
-template <int K>
-__device__ __forceinline__ void block_sum_store(const float (&val)[K], float* s_warp, float* out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();   // s_warp may still be read by the previous call
-#pragma unroll
-  for (int j = 0; j < K; ++j) {
-    const float w = warp_sum_f(val[j]);
-    if (lane == 0) s_warp[warp * 12 + j] = w;
-  }
-  __syncthreads();
-  if (threadIdx.x < K) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < kLbsThreads / 32; ++i) t += s_warp[i * 12 + threadIdx.x];
-    out[threadIdx.x] = t;
-  }
-}
-
+// Two phases.  (A) one thread per vertex: skinned position, gradient of the skinned position gs, per-bone skin-weight
+// gradients (written), vertex gradient (written); the vertex, gs, the skinned position and the camera-space gradient are
+// left in shared memory.  (B) one WARP per bone: g_(R_k, T_k) = sum_v w_kv (v, 1)^T gs_v is a 12-value reduction over the
+// block's 256 vertices -- lanes stride over the vertices, one butterfly per bone.  Round 1 block-reduced bone after bone
+// with two __syncthreads and a skin-weight load in front of each (27 dependent rounds: 26 us for 8 frames of 642
+// vertices, as long as a third of the rasterizer's backward at LASR's batch size).  Fixed summation order: deterministic.
 __global__ void __launch_bounds__(kLbsThreads) lbs_backward_kernel(LbsBwdArgs G) {
   extern __shared__ float s_rt[];  // [B][12]
-  __shared__ float s_warp[(kLbsThreads / 32) * 12];
+  __shared__ float s_st[15][kLbsThreads];   // 0-2 vertex, 3-5 gs, 6-8 skinned position, 9-11 g_cam, 12-14 (g_pp.x, g_pp.y, g_f)
   const LbsArgs& A = G.f;
   const int n = blockIdx.y;
   const int v = blockIdx.x * kLbsThreads + threadIdx.x;
@@ -203,14 +190,15 @@ __global__ void __launch_bounds__(kLbsThreads) lbs_backward_kernel(LbsBwdArgs G)
   float sx = 0.f, sy = 0.f, sz = 0.f;        // skinned (pre-body) position
   float gcx = 0.f, gcy = 0.f, gcz = 0.f;     // gradient w.r.t. the camera-space position
   float gppx = 0.f, gppy = 0.f, gfl = 0.f;
-  const float* sk = nullptr;
+  float gsx = 0.f, gsy = 0.f, gsz = 0.f;
+  const float* skb = A.B > 1 ? A.skin + (long long)(A.skin_shared ? 0 : n) * (A.B - 1) * A.V : nullptr;
   if (active) {
     const float* vp = A.verts + ((long long)(A.verts_shared ? 0 : n) * A.V + v) * 3;
     x0 = vp[0]; y0 = vp[1]; z0 = vp[2];
     sx = x0; sy = y0; sz = z0;
+    const float* sk = skb ? skb + v : nullptr;
     if (A.B > 1) {
       sx = sy = sz = 0.f;
-      sk = A.skin + (long long)(A.skin_shared ? 0 : n) * (A.B - 1) * A.V + v;
       for (int k = 1; k < A.B; ++k) {
         const float* r = s_rt + k * 12;
         const float w = sk[(long long)(k - 1) * A.V];
@@ -246,63 +234,94 @@ __global__ void __launch_bounds__(kLbsThreads) lbs_backward_kernel(LbsBwdArgs G)
       gfl = s;
       gppx = g.x; gppy = g.y;
     }
-  }
-  float* part = G.partial + ((long long)n * G.nblk + blockIdx.x) * (A.B * 12 + 3);
-  // body transform: cam = vs R0 + T0
-  float gsx = gcx, gsy = gcy, gsz = gcz;
-  if (A.tocam) {
-    const float* r = s_rt;
-    gsx = gcx * r[0] + gcy * r[1] + gcz * r[2];   // g_vs = g_cam R0^T
-    gsy = gcx * r[3] + gcy * r[4] + gcz * r[5];
-    gsz = gcx * r[6] + gcy * r[7] + gcz * r[8];
-    const float vs[3] = {sx, sy, sz}, gc[3] = {gcx, gcy, gcz};
-    float acc[12];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) acc[3 * i + j] = active ? vs[i] * gc[j] : 0.f;   // g_R0 = vs^T g_cam
-#pragma unroll
-    for (int j = 0; j < 3; ++j) acc[9 + j] = active ? gc[j] : 0.f;                  // g_T0
-    block_sum_store(acc, s_warp, part);
-  } else if (threadIdx.x < 12) {
-    part[threadIdx.x] = 0.f;
-  }
-  float gvx = gsx, gvy = gsy, gvz = gsz;   // B == 1: vs = v
-  if (A.B > 1) {
-    gvx = gvy = gvz = 0.f;
-    for (int k = 1; k < A.B; ++k) {
-      const float* r = s_rt + k * 12;
-      float w = 0.f, gw = 0.f;
-      if (active) {
-        w = sk[(long long)(k - 1) * A.V];
-        const float pxk = x0 * r[0] + y0 * r[3] + z0 * r[6] + r[9];
-        const float pyk = x0 * r[1] + y0 * r[4] + z0 * r[7] + r[10];
-        const float pzk = x0 * r[2] + y0 * r[5] + z0 * r[8] + r[11];
-        gw = pxk * gsx + pyk * gsy + pzk * gsz;
-        if (G.grad_skin) G.grad_skin[((long long)n * (A.B - 1) + (k - 1)) * A.V + v] = gw;
-      }
-      const float gp[3] = {w * gsx, w * gsy, w * gsz};   // g_p_k
-      gvx += gp[0] * r[0] + gp[1] * r[1] + gp[2] * r[2];  // g_v += g_p_k R_k^T
-      gvy += gp[0] * r[3] + gp[1] * r[4] + gp[2] * r[5];
-      gvz += gp[0] * r[6] + gp[1] * r[7] + gp[2] * r[8];
-      const float vv[3] = {x0, y0, z0};
-      float acc[12];
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) acc[3 * i + j] = vv[i] * gp[j];   // g_R_k = v^T g_p_k  (gp is 0 when inactive)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) acc[9 + j] = gp[j];                   // g_T_k
-      block_sum_store(acc, s_warp, part + k * 12);
+    // body transform: cam = vs R0 + T0  ->  g_vs = g_cam R0^T
+    gsx = gcx; gsy = gcy; gsz = gcz;
+    if (A.tocam) {
+      const float* r = s_rt;
+      gsx = gcx * r[0] + gcy * r[1] + gcz * r[2];
+      gsy = gcx * r[3] + gcy * r[4] + gcz * r[5];
+      gsz = gcx * r[6] + gcy * r[7] + gcz * r[8];
     }
-  }
-  {
-    const float acc[3] = {gppx, gppy, gfl};
-    block_sum_store(acc, s_warp, part + A.B * 12);
-  }
-  if (active) {
+    float gvx = gsx, gvy = gsy, gvz = gsz;   // B == 1: vs = v
+    if (A.B > 1) {
+      gvx = gvy = gvz = 0.f;
+      for (int k = 1; k < A.B; ++k) {
+        const float* r = s_rt + k * 12;
+        const float w = sk[(long long)(k - 1) * A.V];
+        if (G.grad_skin) {
+          const float pxk = x0 * r[0] + y0 * r[3] + z0 * r[6] + r[9];
+          const float pyk = x0 * r[1] + y0 * r[4] + z0 * r[7] + r[10];
+          const float pzk = x0 * r[2] + y0 * r[5] + z0 * r[8] + r[11];
+          G.grad_skin[((long long)n * (A.B - 1) + (k - 1)) * A.V + v] = pxk * gsx + pyk * gsy + pzk * gsz;
+        }
+        const float gp0 = w * gsx, gp1 = w * gsy, gp2 = w * gsz;   // g_p_k
+        gvx += gp0 * r[0] + gp1 * r[1] + gp2 * r[2];               // g_v += g_p_k R_k^T
+        gvy += gp0 * r[3] + gp1 * r[4] + gp2 * r[5];
+        gvz += gp0 * r[6] + gp1 * r[7] + gp2 * r[8];
+      }
+    }
     float* go = G.grad_verts + ((long long)n * A.V + v) * 3;
     go[0] = gvx; go[1] = gvy; go[2] = gvz;
+  }
+  {
+    const int t = threadIdx.x;     // inactive threads stage zeros: they add nothing below
+    s_st[0][t] = x0; s_st[1][t] = y0; s_st[2][t] = z0;
+    s_st[3][t] = gsx; s_st[4][t] = gsy; s_st[5][t] = gsz;
+    s_st[6][t] = sx; s_st[7][t] = sy; s_st[8][t] = sz;
+    s_st[9][t] = gcx; s_st[10][t] = gcy; s_st[11][t] = gcz;
+    s_st[12][t] = gppx; s_st[13][t] = gppy; s_st[14][t] = gfl;
+  }
+  __syncthreads();
+  // (B) item 0: body transform (g_R0 = vs^T g_cam, g_T0 = sum g_cam); items 1..B-1: bones; item B: (g_pp, g_f)
+  float* part = G.partial + ((long long)n * G.nblk + blockIdx.x) * (A.B * 12 + 3);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v_blk = blockIdx.x * kLbsThreads;
+  const int vidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+  for (int item = warp; item <= A.B; item += kLbsThreads / 32) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    if (item == A.B) {
+#pragma unroll
+      for (int i = 0; i < kLbsThreads / 32; ++i) {
+        const int t = lane + 32 * i;
+        acc[0] += s_st[12][t]; acc[1] += s_st[13][t]; acc[2] += s_st[14][t];
+      }
+    } else if (item == 0) {
+      if (A.tocam) {
+#pragma unroll
+        for (int i = 0; i < kLbsThreads / 32; ++i) {
+          const int t = lane + 32 * i;
+          const float a[3] = {s_st[6][t], s_st[7][t], s_st[8][t]}, g[3] = {s_st[9][t], s_st[10][t], s_st[11][t]};
+#pragma unroll
+          for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) acc[3 * p + q] += a[p] * g[q];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) acc[9 + q] += g[q];
+        }
+      }
+    } else {
+      const float* wk = skb + (long long)(item - 1) * A.V + v_blk;
+      float w[kLbsThreads / 32];
+#pragma unroll
+      for (int i = 0; i < kLbsThreads / 32; ++i) w[i] = (v_blk + lane + 32 * i < A.V) ? __ldg(wk + lane + 32 * i) : 0.f;
+#pragma unroll
+      for (int i = 0; i < kLbsThreads / 32; ++i) {
+        const int t = lane + 32 * i;
+        const float a[3] = {s_st[0][t], s_st[1][t], s_st[2][t]};
+        const float g[3] = {w[i] * s_st[3][t], w[i] * s_st[4][t], w[i] * s_st[5][t]};   // g_p_k
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) acc[3 * p + q] += a[p] * g[q];                    // g_R_k = v^T g_p_k
+#pragma unroll
+        for (int q = 0; q < 3; ++q) acc[9 + q] += g[q];                                  // g_T_k
+      }
+    }
+    const int nval = item == A.B ? 3 : 12;
+    warp_sum16(acc, lane);     // recursive halving: every even lane ends with the warp total of value vidx
+    if ((lane & 1) == 0 && vidx < nval) part[item * 12 + vidx] = acc[0];
   }
 }
 

@@ -160,13 +160,23 @@ __global__ void __launch_bounds__(kLossThreads) losses_forward_kernel(LossArgs A
   }
 }
 
-__global__ void losses_reduce_kernel(const float* partial, int nblk, int NH, float* sums) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= NH * kNumSums) return;
+// Sum of the nblk block partials of output t = (frame*H + hypothesis, q), by one warp: lane l adds blocks l, l + 32, ...
+// in order, then a butterfly -- a fixed order (deterministic), and one or two rounds of memory latency instead of nblk.
+__device__ __forceinline__ float reduce_partials_warp(const float* __restrict__ partial, int nblk, int t, int lane) {
   const int ij = t / kNumSums, q = t % kNumSums;
+  const float* src = partial + (long long)ij * nblk * kNumSums + q;
   float acc = 0.f;
-  for (int b = 0; b < nblk; ++b) acc += partial[((long long)ij * nblk + b) * kNumSums + q];
-  sums[t] = acc;
+#pragma unroll 4
+  for (int b = lane; b < nblk; b += 32) acc += __ldg(src + (long long)b * kNumSums);
+  return wsum(acc);
+}
+
+__global__ void __launch_bounds__(256) losses_reduce_kernel(const float* __restrict__ partial, int nblk, int NH,
+                                                            float* sums) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= NH * kNumSums) return;
+  const float acc = reduce_partials_warp(partial, nblk, t, lane);
+  if (lane == 0) sums[t] = acc;
 }
 
 // gsums [N,H,7] (gradient of the scalar objective w.r.t. each sum; entry 2,3,6 ignored: those sums
@@ -299,17 +309,14 @@ __global__ void __launch_bounds__(256) losses_finalize_kernel(const float* sums,
 // Block partials -> sums [N,H,7] -> per-pair losses and the three means, in ONE block (the two steps used to be two
 // launches behind the pixel pass; at LASR's batch sizes the whole head is launch-latency bound).  Same summation orders as
 // losses_reduce_kernel and losses_finalize_kernel: same bits.
-__global__ void __launch_bounds__(512) losses_reduce_finalize_kernel(const float* __restrict__ partial, int nblk, int N,
+__global__ void __launch_bounds__(1024) losses_reduce_finalize_kernel(const float* __restrict__ partial, int nblk, int N,
                                                                      int H, float l1tex_wt, float* sums, float* sub,
                                                                      float* out3) {
   const int tot = N * H * kNumSums;
-  for (int t = threadIdx.x; t < tot; t += blockDim.x) {
-    const int ij = t / kNumSums, q = t % kNumSums;
-    const float* src = partial + (long long)ij * nblk * kNumSums + q;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int b = 0; b < nblk; ++b) acc += __ldg(src + (long long)b * kNumSums);
-    sums[t] = acc;
+  const int lane = threadIdx.x & 31;
+  for (int t = threadIdx.x >> 5; t < tot; t += blockDim.x >> 5) {
+    const float acc = reduce_partials_warp(partial, nblk, t, lane);
+    if (lane == 0) sums[t] = acc;
   }
   __syncthreads();                       // this block's own global writes are visible to it after the barrier
   losses_finalize_block(sums, N, H, l1tex_wt, sub, out3, true);
@@ -727,11 +734,11 @@ static int reduce_tail(const float* partial, int nblk, int N, int H, float* sums
                        cudaStream_t st) {
   if ((sub == nullptr) != (out3 == nullptr)) return lasr_fail("losses: sub and out3 go together");
   if (sub) {
-    losses_reduce_finalize_kernel<<<1, 512, 0, st>>>(partial, nblk, N, H, l1tex_wt, sums, sub, out3);
+    losses_reduce_finalize_kernel<<<1, 1024, 0, st>>>(partial, nblk, N, H, l1tex_wt, sums, sub, out3);
     return lasr_check_launch("losses_reduce_finalize_kernel");
   }
   const int tot = N * H * kNumSums;
-  losses_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(partial, nblk, N * H, sums);
+  losses_reduce_kernel<<<(tot + 7) / 8, 256, 0, st>>>(partial, nblk, N * H, sums);
   return lasr_check_launch("losses_reduce_kernel");
 }
 

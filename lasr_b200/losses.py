@@ -120,8 +120,6 @@ class _FusedHead(Function):
             bg = torch.empty(N * H, S, S, dtype=torch.uint8, device=dev)
         sub = torch.empty(3, N, H, dtype=torch.float32, device=dev)
         out3 = torch.empty(4, dtype=torch.float32, device=dev)     # three means and their sum
-        if pair_shift and grad_link is None and torch.is_grad_enabled():
-            raise ValueError("fused_head(pair_shift=...) differentiates through the packed gradient only: pass grad_link")
         _cabi.head_forward(img, po, pq, fo, fq, im, mk, oc, fl, sums, flow_rd, bg, N, H, S, sub, out3, l1tex_wt,
                            pair_shift)
         ctx.pair_shift = int(pair_shift)
@@ -174,6 +172,9 @@ def fused_head(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs
     (not differentiable: their gradient path is inside the losses).
     pair_shift: frame ij takes entry (ij + pair_shift) mod N*H of pp_pair / f_pair (pass the own tensors again and
     bs * n_hypo instead of rolled copies; needs grad_link when differentiated)."""
+    if (pair_shift and grad_link is None and torch.is_grad_enabled()
+            and any(t.requires_grad for t in (image, pp_pair, f_pair))):
+        raise ValueError("fused_head(pair_shift=...) differentiates through the packed gradient only: pass grad_link")
     out3, sub, flow_rd, bg = _FusedHead.apply(image, pp_own, pp_pair, f_own, f_pair, imgs, masks, occ, flow_obs,
                                               l1tex_wt, n_frames, n_hypo, want_flow, grad_link, pair_shift)
     return out3[0], out3[1], out3[2], dict(mask=sub[0], flow=sub[1], texture=sub[2], total=out3[3]), flow_rd, bg
