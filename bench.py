@@ -310,6 +310,11 @@ class OursArm(RasterArmBase):
         import lasr_b200.soft_renderer as sr
         self.cabi, self.sr = _cabi, sr
         self.ws = _cabi.raster_workspace(self.N, self.F, S, device)
+        # LASR_B200_KEEP_WORKSPACE=compact: 80 B per face kept between the two calls instead of the workspace (an A/B switch)
+        from lasr_b200.soft_renderer.functional import SoftRasterizeFunction
+        self.compact = sys.modules[SoftRasterizeFunction.__module__].keep_mode() == "compact"
+        self.saved = _cabi.saved_buffer(self.N, self.F, S, device) if self.compact else None
+        self.bwd_ws = _cabi.raster_backward_scratch(self.N, self.F, S, device) if self.compact else self.ws
         s = wl["settings"]
         self.scal = (S, s["near"], s["far"], None, s["eps"], s["sigma_val"], 2, float(np.log(1.0 / s["dist_eps"] - 1.0)),
                      s["gamma_val"], 1, 2, 1, True)
@@ -330,11 +335,12 @@ class OursArm(RasterArmBase):
             e[0].record()
         # the background colour travels as an argument (lasr_b200_raster_forward_bg): no pre-fill pass over the image --
         # the reference arm performs the fills its Python performs (soft_rasterize.py:50-53)
-        self.cabi.raster_forward(self.fv, self.tex, self.aggrs, self.img, self.ws, *self.scal, background=[0.0, 0.0, 0.0])
+        self.cabi.raster_forward(self.fv, self.tex, self.aggrs, self.img, self.ws, *self.scal, background=[0.0, 0.0, 0.0],
+                                 saved=self.saved)
         if timed:
             e[1].record()
-        self.cabi.raster_backward(self.fv, self.tex, self.img, self.aggrs, self.gf, self.gt, self.grad, self.ws,
-                                  *self.scal, setup_done=True)
+        self.cabi.raster_backward(self.fv, self.tex, self.img, self.aggrs, self.gf, self.gt, self.grad, self.bwd_ws,
+                                  *self.scal, setup_done=True, saved=self.saved)
         if timed:
             e[2].record()
             self.pending.append(e)

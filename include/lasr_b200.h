@@ -189,6 +189,55 @@ int lasr_b200_render_backward_sets_packed(const float* verts, const int32_t* tri
                                           int setup_done, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Compact mode: 80 bytes per face kept from forward to backward instead of the workspace.
+ * The workspace of the calls above holds, per face, the full record the forward's inner loop reads (176 - 240 bytes),
+ * the dilated box and the pixel window: 200 - 264 bytes per face that a caller who reuses it in the backward
+ * (`setup_done = 1`) keeps alive in between -- the reference keeps 108 (`faces_info`, soft_rasterize_cuda.cpp:59-76).
+ * The *_compact calls write, next to it, a SAVED buffer (lasr_b200_raster_saved_bytes: 80 bytes per face + the S-entry
+ * coordinate table; 256-byte aligned) holding only what costs a division to rebuild (inverse matrix, 1/z, 1/edge^2, the
+ * edge-prediction threshold, flags); the workspace is then scratch that may be freed when the forward call returns, and
+ * the backward takes the saved buffer plus a small scratch of its own (lasr_b200_raster_backward_scratch_bytes /
+ * lasr_b200_render_backward_scratch_bytes), reads the vertices and colours from the op's inputs and re-derives the edge
+ * rows and the box with the forward's own expressions: same gradients bit for bit.
+ * ------------------------------------------------------------------------------------------- */
+size_t lasr_b200_raster_saved_bytes(int batch_size, int num_faces, int image_size);
+size_t lasr_b200_raster_backward_scratch_bytes(int batch_size, int num_faces, int image_size);
+size_t lasr_b200_render_backward_scratch_bytes(int batch_size, int num_faces, int image_size, int num_sets);
+
+int lasr_b200_raster_forward_compact(const float* faces, const float* textures, float* aggrs_info,
+                                     float* soft_colors, void* saved, size_t saved_bytes, void* workspace,
+                                     size_t workspace_bytes, int batch_size, int num_faces, int image_size,
+                                     int texture_size, float near_, float far_, const float* near_far_dev, float eps,
+                                     float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
+                                     int func_id_rgb, int func_id_alpha, int texture_sample_type, int double_side,
+                                     const float* background_host, void* stream);
+int lasr_b200_raster_backward_compact(const float* faces, const float* textures, const float* soft_colors,
+                                      const float* aggrs_info, float* grad_faces, float* grad_textures,
+                                      const float* grad_soft_colors, const void* saved, size_t saved_bytes,
+                                      void* workspace, size_t workspace_bytes, int batch_size, int num_faces,
+                                      int image_size, int texture_size, float near_, float far_,
+                                      const float* near_far_dev, float eps, float sigma_val, int func_id_dist,
+                                      float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
+                                      int texture_sample_type, int double_side, void* stream);
+int lasr_b200_render_forward_sets_compact(const float* verts, const int32_t* tri, const float* const* set_ptrs,
+                                          const int* set_shifts, float* aggrs_info, float* soft_colors, void* saved,
+                                          size_t saved_bytes, void* workspace, size_t workspace_bytes, int batch_size,
+                                          int num_vertices, int num_faces, int image_size, float near_, float far_,
+                                          const float* near_far_dev, float eps, float sigma_val, int func_id_dist,
+                                          float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
+                                          int double_side, int num_sets, const float* background, void* stream);
+int lasr_b200_render_backward_sets_packed_compact(const float* verts, const int32_t* tri, const float* const* set_ptrs,
+                                                  const int* set_shifts, const float* packed_grad,
+                                                  const int32_t* csr_offsets, const int32_t* csr_entries,
+                                                  float* grad_verts, float* const* grad_set_ptrs, const void* saved,
+                                                  size_t saved_bytes, void* workspace, size_t workspace_bytes,
+                                                  int batch_size, int num_vertices, int num_faces, int image_size,
+                                                  float near_, float far_, const float* near_far_dev, float eps,
+                                                  float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
+                                                  int func_id_rgb, int func_id_alpha, int double_side, int num_sets,
+                                                  int detached_sets, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused linear-blend skinning + body transform + pinhole projection + batch depth window
  * (SURVEY 8a rows G1, G2, G3).  Replaces, for CUDA tensors,
  *   obj_to_cam   nnutils/geom_utils.py:45-71     cam = (sum_k w_k (v R_k + T_k)) R_0 + T_0

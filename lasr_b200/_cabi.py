@@ -66,6 +66,17 @@ def _load_locked():
                                                   + [_c.POINTER(_c.c_float), _c.c_void_p])
         L.lasr_b200_raster_backward.restype = _c.c_int
         L.lasr_b200_raster_backward.argtypes = [_c.c_void_p] * 8 + [_c.c_size_t] + _RASTER_SCALARS + [_c.c_int, _c.c_void_p]
+        for nm in ("lasr_b200_raster_saved_bytes", "lasr_b200_raster_backward_scratch_bytes"):
+            getattr(L, nm).restype = _c.c_size_t
+            getattr(L, nm).argtypes = [_c.c_int, _c.c_int, _c.c_int]
+        L.lasr_b200_render_backward_scratch_bytes.restype = _c.c_size_t
+        L.lasr_b200_render_backward_scratch_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int, _c.c_int]
+        L.lasr_b200_raster_forward_compact.restype = _c.c_int
+        L.lasr_b200_raster_forward_compact.argtypes = ([_c.c_void_p] * 5 + [_c.c_size_t, _c.c_void_p, _c.c_size_t]
+                                                       + _RASTER_SCALARS + [_c.POINTER(_c.c_float), _c.c_void_p])
+        L.lasr_b200_raster_backward_compact.restype = _c.c_int
+        L.lasr_b200_raster_backward_compact.argtypes = ([_c.c_void_p] * 8 + [_c.c_size_t, _c.c_void_p, _c.c_size_t]
+                                                        + _RASTER_SCALARS + [_c.c_void_p])
         L.lasr_b200_render_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_render_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int, _c.c_int]
         _render_scalars = [_c.c_int] * 4 + [_c.c_float, _c.c_float, _c.c_void_p, _c.c_float, _c.c_float, _c.c_int,
@@ -88,6 +99,15 @@ def _load_locked():
                                                              _c.POINTER(_c.c_int), _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                                              _c.c_void_p, _c.POINTER(_c.c_void_p), _c.c_void_p, _c.c_size_t]
                                                             + _render_scalars + [_c.c_int, _c.c_int, _c.c_void_p])
+        L.lasr_b200_render_forward_sets_compact.restype = _c.c_int
+        L.lasr_b200_render_forward_sets_compact.argtypes = (
+            [_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_int), _c.c_void_p, _c.c_void_p, _c.c_void_p,
+             _c.c_size_t, _c.c_void_p, _c.c_size_t] + _render_scalars + [_c.POINTER(_c.c_float), _c.c_void_p])
+        L.lasr_b200_render_backward_sets_packed_compact.restype = _c.c_int
+        L.lasr_b200_render_backward_sets_packed_compact.argtypes = (
+            [_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_int), _c.c_void_p, _c.c_void_p, _c.c_void_p,
+             _c.c_void_p, _c.POINTER(_c.c_void_p), _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_size_t] + _render_scalars
+            + [_c.c_int, _c.c_void_p])
         L.lasr_b200_meshreg_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_meshreg_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int]
         vp, ci = _c.c_void_p, _c.c_int
@@ -168,7 +188,10 @@ EXPORTED_SYMBOLS = [
     "lasr_b200_raster_workspace_bytes", "lasr_b200_raster_forward", "lasr_b200_raster_forward_bg",
     "lasr_b200_raster_backward",
     "lasr_b200_render_workspace_bytes", "lasr_b200_render_forward", "lasr_b200_render_backward",
-    "lasr_b200_render_backward_packed", "lasr_b200_render_forward_sets", "lasr_b200_render_backward_sets_packed", "lasr_b200_head_backward_packed", "lasr_b200_head_backward_packed_shift",
+    "lasr_b200_render_backward_packed", "lasr_b200_render_forward_sets", "lasr_b200_render_backward_sets_packed",
+    "lasr_b200_raster_saved_bytes", "lasr_b200_raster_backward_scratch_bytes", "lasr_b200_render_backward_scratch_bytes",
+    "lasr_b200_raster_forward_compact", "lasr_b200_raster_backward_compact", "lasr_b200_render_forward_sets_compact",
+    "lasr_b200_render_backward_sets_packed_compact", "lasr_b200_head_backward_packed", "lasr_b200_head_backward_packed_shift",
     "lasr_b200_losses_workspace_bytes", "lasr_b200_losses_forward", "lasr_b200_losses_forward_total",
     "lasr_b200_losses_backward",
     "lasr_b200_losses_finalize", "lasr_b200_losses_coefficients", "lasr_b200_losses_coefficients_total",
@@ -220,13 +243,28 @@ def raster_workspace(N: int, F: int, S: int, device) -> torch.Tensor:
 
 def raster_forward(faces, textures, aggrs_info, soft_colors, workspace, image_size, near, far, near_far_dev, eps,
                    sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, texture_sample_type,
-                   double_side, background=None):
+                   double_side, background=None, saved=None):
     """background=None: the reference's contract, soft_colors arrives pre-filled with the background colour
-    (lasr_b200_raster_forward).  background=[r, g, b]: soft_colors is output only (lasr_b200_raster_forward_bg)."""
+    (lasr_b200_raster_forward).  background=[r, g, b]: soft_colors is output only (lasr_b200_raster_forward_bg).
+    saved (a `saved_buffer`, with background): compact mode -- the 80 bytes per face the backward needs go there and the
+    workspace is scratch from the moment this call returns (lasr_b200_raster_forward_compact)."""
     for t, nm in ((faces, "faces"), (textures, "textures"), (aggrs_info, "aggrs_info"), (soft_colors, "soft_colors")):
         _require_cuda_f32(t, nm)
     N, F = faces.shape[:2]
     T = textures.shape[2]
+    if saved is not None:
+        if background is None:
+            raise RuntimeError("raster_forward(saved=...): compact mode takes the background as an argument")
+        bg = (_c.c_float * 3)(*[float(x) for x in background])
+        with torch.cuda.device(faces.device):
+            rc = lib().lasr_b200_raster_forward_compact(
+                faces.data_ptr(), textures.data_ptr(), aggrs_info.data_ptr(), soft_colors.data_ptr(), saved.data_ptr(),
+                saved.numel(), workspace.data_ptr(), workspace.numel(), N, F, int(image_size), T, float(near), float(far),
+                near_far_dev.data_ptr() if near_far_dev is not None else None, float(eps), float(sigma_val),
+                int(func_id_dist), float(dist_eps), float(gamma_val), int(func_id_rgb), int(func_id_alpha),
+                int(texture_sample_type), int(bool(double_side)), bg, _stream_ptr())
+        _check(rc, "lasr_b200_raster_forward_compact")
+        return
     args = (faces.data_ptr(), textures.data_ptr(), aggrs_info.data_ptr(), soft_colors.data_ptr(),
             workspace.data_ptr(), workspace.numel(), N, F, int(image_size), T, float(near), float(far),
             near_far_dev.data_ptr() if near_far_dev is not None else None, float(eps), float(sigma_val),
@@ -243,13 +281,25 @@ def raster_forward(faces, textures, aggrs_info, soft_colors, workspace, image_si
 
 def raster_backward(faces, textures, soft_colors, aggrs_info, grad_faces, grad_textures, grad_soft_colors, workspace,
                     image_size, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
-                    func_id_rgb, func_id_alpha, texture_sample_type, double_side, setup_done=False):
+                    func_id_rgb, func_id_alpha, texture_sample_type, double_side, setup_done=False, saved=None):
+    """saved: the forward's `saved_buffer` (compact mode); `workspace` is then a `raster_backward_scratch`."""
     for t, nm in ((faces, "faces"), (textures, "textures"), (soft_colors, "soft_colors"), (aggrs_info, "aggrs_info"),
                   (grad_faces, "grad_faces"), (grad_textures, "grad_textures"),
                   (grad_soft_colors, "grad_soft_colors")):
         _require_cuda_f32(t, nm)
     N, F = faces.shape[:2]
     T = textures.shape[2]
+    if saved is not None:
+        with torch.cuda.device(faces.device):
+            rc = lib().lasr_b200_raster_backward_compact(
+                faces.data_ptr(), textures.data_ptr(), soft_colors.data_ptr(), aggrs_info.data_ptr(),
+                grad_faces.data_ptr(), grad_textures.data_ptr(), grad_soft_colors.data_ptr(), saved.data_ptr(),
+                saved.numel(), workspace.data_ptr(), workspace.numel(), N, F, int(image_size), T, float(near), float(far),
+                near_far_dev.data_ptr() if near_far_dev is not None else None, float(eps), float(sigma_val),
+                int(func_id_dist), float(dist_eps), float(gamma_val), int(func_id_rgb), int(func_id_alpha),
+                int(texture_sample_type), int(bool(double_side)), _stream_ptr())
+        _check(rc, "lasr_b200_raster_backward_compact")
+        return
     with torch.cuda.device(faces.device):
         rc = lib().lasr_b200_raster_backward(
             faces.data_ptr(), textures.data_ptr(), soft_colors.data_ptr(), aggrs_info.data_ptr(),
@@ -263,6 +313,20 @@ def raster_backward(faces, textures, soft_colors, aggrs_info, grad_faces, grad_t
 
 def _p(t):
     return t.data_ptr() if t is not None else None
+
+
+def saved_buffer(N: int, F: int, S: int, device) -> torch.Tensor:
+    """What compact mode keeps from forward to backward: 80 bytes per face + the coordinate table."""
+    return torch.empty(int(lib().lasr_b200_raster_saved_bytes(N, F, int(S))), dtype=torch.uint8, device=device)
+
+
+def raster_backward_scratch(N: int, F: int, S: int, device) -> torch.Tensor:
+    return torch.empty(int(lib().lasr_b200_raster_backward_scratch_bytes(N, F, int(S))), dtype=torch.uint8, device=device)
+
+
+def render_backward_scratch(N: int, F: int, S: int, device, num_sets: int) -> torch.Tensor:
+    return torch.empty(int(lib().lasr_b200_render_backward_scratch_bytes(N, F, int(S), int(num_sets))), dtype=torch.uint8,
+                       device=device)
 
 
 def lbs_workspace(N: int, V: int, B: int, device) -> torch.Tensor:
@@ -416,8 +480,9 @@ def _set_arrays(sets, shifts, N, V, what):
 
 def render_forward_sets(verts, tri, sets, shifts, aggrs_info, soft_colors, workspace, S, near, far, near_far_dev, eps,
                         sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side,
-                        background):
-    """lasr_b200_render_forward_sets: `sets` K tensors [N,V,3], frame n of the image reads frame (n + shifts[s]) mod N."""
+                        background, saved=None):
+    """lasr_b200_render_forward_sets: `sets` K tensors [N,V,3], frame n of the image reads frame (n + shifts[s]) mod N.
+    saved (a `saved_buffer`): compact mode, the workspace is scratch once the call returns."""
     for t, nm in ((verts, "verts"), (aggrs_info, "aggrs_info"), (soft_colors, "soft_colors")):
         _require_cuda_f32(t, nm)
     if tri.dtype != torch.int32 or not tri.is_cuda or not tri.is_contiguous():
@@ -431,17 +496,25 @@ def render_forward_sets(verts, tri, sets, shifts, aggrs_info, soft_colors, works
         raise RuntimeError("soft_colors must be [N,3K+1,S,S] and background 3 floats per colour set")
     bg_arr = (_c.c_float * (3 * K))(*[float(x) for x in background])
     with torch.cuda.device(verts.device):
-        rc = lib().lasr_b200_render_forward_sets(
-            _p(verts), _p(tri), ptrs, sh, _p(aggrs_info), _p(soft_colors), _p(workspace), workspace.numel(),
-            *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
-                                 gamma_val, func_id_rgb, func_id_alpha, double_side, K), bg_arr, _stream_ptr())
+        if saved is not None:
+            rc = lib().lasr_b200_render_forward_sets_compact(
+                _p(verts), _p(tri), ptrs, sh, _p(aggrs_info), _p(soft_colors), _p(saved), saved.numel(), _p(workspace),
+                workspace.numel(),
+                *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
+                                     gamma_val, func_id_rgb, func_id_alpha, double_side, K), bg_arr, _stream_ptr())
+        else:
+            rc = lib().lasr_b200_render_forward_sets(
+                _p(verts), _p(tri), ptrs, sh, _p(aggrs_info), _p(soft_colors), _p(workspace), workspace.numel(),
+                *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
+                                     gamma_val, func_id_rgb, func_id_alpha, double_side, K), bg_arr, _stream_ptr())
     _check(rc, "lasr_b200_render_forward_sets")
 
 
 def render_backward_sets_packed(verts, tri, sets, shifts, packed_grad, csr_offsets, csr_entries, grad_verts, grad_sets,
                                 workspace, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
-                                func_id_rgb, func_id_alpha, double_side, setup_done=False, detached_sets=1):
-    """grad_sets: K tensors [N,V,3] or None (detached sets), written in each set's own frame order."""
+                                func_id_rgb, func_id_alpha, double_side, setup_done=False, detached_sets=1, saved=None):
+    """grad_sets: K tensors [N,V,3] or None (detached sets), written in each set's own frame order.
+    saved: the forward's `saved_buffer` (compact mode); `workspace` is then a `render_backward_scratch`."""
     for t in (verts, packed_grad, grad_verts):
         _require_cuda_f32(t, "render tensor")
     N, V = verts.shape[:2]
@@ -450,6 +523,16 @@ def render_backward_sets_packed(verts, tri, sets, shifts, packed_grad, csr_offse
     gptrs, _ = _set_arrays(grad_sets, shifts, N, V, "render_backward_sets_packed")
     if packed_grad.numel() != N * 3 * int(S) * int(S) * 4:
         raise RuntimeError("render_backward_sets_packed: packed_grad is [N,3,S*S,4]")
+    if saved is not None:
+        with torch.cuda.device(verts.device):
+            rc = lib().lasr_b200_render_backward_sets_packed_compact(
+                _p(verts), _p(tri), ptrs, sh, _p(packed_grad), _p(csr_offsets), _p(csr_entries), _p(grad_verts), gptrs,
+                _p(saved), saved.numel(), _p(workspace), workspace.numel(),
+                *_render_scalar_args(N, V, F, S, near, far, near_far_dev, eps, sigma_val, func_id_dist, dist_eps,
+                                     gamma_val, func_id_rgb, func_id_alpha, double_side, K), int(detached_sets),
+                _stream_ptr())
+        _check(rc, "lasr_b200_render_backward_sets_packed_compact")
+        return
     with torch.cuda.device(verts.device):
         rc = lib().lasr_b200_render_backward_sets_packed(
             _p(verts), _p(tri), ptrs, sh, _p(packed_grad), _p(csr_offsets), _p(csr_entries), _p(grad_verts), gptrs,

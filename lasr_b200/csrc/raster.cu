@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(RasterArgs A, int wit
       for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(tc + ty * tiles_x + tx, 1);
   }
   if (live_thread) A.face_border[i] = make_float4(g.lox, g.hix, g.loy, g.hiy);
+  if (A.compact_record && live_thread) store_compact(A.compact_record + i * kCompactWords, g);   // what the backward keeps
   const int words = rec_words(A.K);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* dst = staged ? s_rec[warp] + lane * words : A.face_record + fi * words;
@@ -611,10 +612,14 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
 
   float tex9[9 * K];
   FaceGeom g;
-  if (A.records_valid) {   // the forward's per-face record (the reference hands faces_info to its backward too)
+  if (A.records_valid == 1) {   // the forward's per-face record (the reference hands faces_info to its backward too)
     load_record<K>(A.face_record + wg * kRecWords, g, tex9);
     const float4 bd = __ldg(A.face_border + wg);
     g.lox = bd.x; g.hix = bd.y; g.loy = bd.z; g.hiy = bd.w;
+  } else if (A.records_valid == 2) {   // the forward's COMPACT record (80 bytes per face) + the op's own inputs
+    float fv[9];
+    fetch_face(A, n, f, fv, tex9, sample == 1);
+    face_from_compact(fv, sthr, A.compact_record + wg * kCompactWords, g);
   } else {
     float fv[9];
     fetch_face(A, n, f, fv, tex9, sample == 1);
@@ -847,15 +852,15 @@ static size_t raster_ws_bytes(int N, int F, int S, int K) {
 
 static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, float far_, const float* nf_dev,
                      float eps, float sigma, int dist, float dist_eps, float gamma, int rgb, int alpha, int sample,
-                     int double_side, void* workspace, size_t workspace_bytes, int K = 1) {
+                     int double_side, void* workspace, size_t workspace_bytes, int K = 1, bool carve = true) {
   if (N <= 0 || F <= 0 || S <= 0 || T <= 0) return fail("raster: batch_size, num_faces, image_size, texture_size must be positive");
   if (S > 8192) return fail("raster: image_size > 8192 unsupported (per-frame plane offsets are 32-bit)");
   if (dist < 0 || dist > 2 || rgb < 0 || rgb > 1 || alpha < 0 || alpha > 2 || sample < 0 || sample > 1)
     return fail("raster: bad func id");
   if (sample == 1 && T != 3) return fail("raster: 'vertex' textures must be [N,F,3,3]");
   if (K < 1 || K > kMaxSets) return fail("render: num_sets must be 1, 2 or 3");
-  if (!workspace || workspace_bytes < raster_ws_bytes(N, F, S, K)) return fail("raster: workspace too small");
-  if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0)   // bulk copies and 128-bit loads of the records need 16-byte alignment
+  if (carve && (!workspace || workspace_bytes < raster_ws_bytes(N, F, S, K))) return fail("raster: workspace too small");
+  if (!workspace || reinterpret_cast<uintptr_t>(workspace) % 256 != 0)   // bulk copies and 128-bit loads of the records need 16-byte alignment
     return fail("raster: workspace must be 256-byte aligned (cudaMalloc / torch allocations are)");
   if (K > 1 && !(dist == 2 && rgb == 1 && alpha == 2 && sample == 1 && double_side != 0))
     return fail("render: several colour sets need euclidean / softmax / prod / vertex / fill_back (LASR's configuration)");
@@ -866,6 +871,7 @@ static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, flo
   A.dist = dist; A.rgb = rgb; A.alpha = alpha; A.sample = sample; A.double_side = double_side;
   A.inv_sigma = (float)(1.0 / (double)sigma);
   A.inv_gamma = (float)(1.0 / (double)gamma);
+  if (!carve) return 0;        // the compact backward lays out its own (much smaller) scratch
   // workspace carve-up (all 256-byte aligned)
   char* p = reinterpret_cast<char*>(workspace);
   const size_t nf = (size_t)N * F;
@@ -885,6 +891,43 @@ static int fill_args(RasterArgs& A, int N, int F, int S, int T, float near_, flo
 }
 
 static bool is_fast(const RasterArgs& A);
+
+// ---- compact mode: what is kept from forward to backward is a separate caller-owned buffer of 80 bytes per face (+ the
+// S-entry coordinate table) instead of the whole workspace (200 - 264 bytes per face); the workspace becomes scratch the
+// caller may free as soon as the forward call returns, and the backward takes a scratch of its own.
+static size_t raster_saved_bytes(int N, int F, int S) {
+  if (N <= 0 || F <= 0 || S <= 0) return 0;
+  return align256((size_t)S * sizeof(float)) + align256((size_t)N * F * kCompactWords * sizeof(float));
+}
+static size_t backward_scratch_bytes(int N, int F, int S, int K) {
+  if (N <= 0 || F <= 0 || S <= 0) return 0;
+  return align256((size_t)(kBigListCap + 1) * sizeof(int)) +
+         (pack_room(F, S, K) ? align256((size_t)N * 2 * (size_t)S * S * sizeof(float4)) : 0);
+}
+static int attach_saved(RasterArgs& A, void* saved, size_t saved_bytes) {
+  if (!saved || saved_bytes < raster_saved_bytes(A.N, A.F, A.S)) return fail("raster: saved buffer too small");
+  if (reinterpret_cast<uintptr_t>(saved) % 256 != 0) return fail("raster: saved buffer must be 256-byte aligned");
+  char* p = reinterpret_cast<char*>(saved);
+  A.coords = reinterpret_cast<float*>(p);  p += align256((size_t)A.S * sizeof(float));
+  A.compact_record = reinterpret_cast<float*>(p);
+  return 0;
+}
+// backward scratch in compact mode: big-face list, packing area of the single-set pre-pass, then `extra` bytes for the
+// caller (per-face gradients of the indexed path); returns the start of the extra region or null
+static char* carve_backward_scratch(RasterArgs& A, void* workspace, size_t workspace_bytes, size_t extra) {
+  if (!workspace || workspace_bytes < backward_scratch_bytes(A.N, A.F, A.S, A.K) + extra) {
+    fail("raster_backward: scratch too small");
+    return nullptr;
+  }
+  char* p = reinterpret_cast<char*>(workspace);
+  A.big_list = reinterpret_cast<int*>(p);  p += align256((size_t)(kBigListCap + 1) * sizeof(int));
+  A.pack_area = nullptr;
+  if (pack_room(A.F, A.S, A.K)) {
+    A.pack_area = reinterpret_cast<float4*>(p);
+    p += align256((size_t)A.N * 2 * (size_t)A.S * A.S * sizeof(float4));
+  }
+  return p;
+}
 
 // forward launch: dispatch order first (if this launch uses it), then one CTA per (frame, tile)
 static int launch_forward(const RasterArgs& A, cudaStream_t st) {
@@ -1024,11 +1067,13 @@ static int raster_forward_impl(const float* faces, const float* textures, float*
                                void* workspace, size_t workspace_bytes, int N, int F, int S, int T, float near_, float far_,
                                const float* near_far_dev, float eps, float sigma_val, int func_id_dist, float dist_eps,
                                float gamma_val, int func_id_rgb, int func_id_alpha, int texture_sample_type,
-                               int double_side, const float* background_host, void* stream) {
+                               int double_side, const float* background_host, void* stream, void* saved = nullptr,
+                               size_t saved_bytes = 0, bool compact = false) {
   RasterArgs A{};
   if (fill_args(A, N, F, S, T, near_, far_, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
                 func_id_rgb, func_id_alpha, texture_sample_type, double_side, workspace, workspace_bytes))
     return 1;
+  if (compact && attach_saved(A, saved, saved_bytes)) return 1;
   if (!faces || !textures || !aggrs_info || !soft_colors) return fail("raster_forward: null tensor pointer");
   A.faces = faces; A.textures = textures; A.aggrs_info = aggrs_info; A.soft_colors = soft_colors;
   if (background_host) {   // no pre-fill pass over the image and no read of it in the forward
@@ -1069,18 +1114,24 @@ extern "C" int lasr_b200_raster_forward_bg(const float* faces, const float* text
                              texture_sample_type, double_side, background_host, stream);
 }
 
-extern "C" int lasr_b200_raster_backward(const float* faces, const float* textures, const float* soft_colors,
-                                         const float* aggrs_info, float* grad_faces, float* grad_textures,
-                                         const float* grad_soft_colors, void* workspace, size_t workspace_bytes,
-                                         int N, int F, int S, int T, float near_, float far_,
-                                         const float* near_far_dev, float eps, float sigma_val, int func_id_dist,
-                                         float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
-                                         int texture_sample_type, int double_side, int setup_done, void* stream) {
+static int raster_backward_impl(const float* faces, const float* textures, const float* soft_colors,
+                                const float* aggrs_info, float* grad_faces, float* grad_textures,
+                                const float* grad_soft_colors, void* workspace, size_t workspace_bytes,
+                                int N, int F, int S, int T, float near_, float far_,
+                                const float* near_far_dev, float eps, float sigma_val, int func_id_dist,
+                                float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
+                                int texture_sample_type, int double_side, int setup_done, void* stream,
+                                void* saved = nullptr, size_t saved_bytes = 0, bool compact = false) {
   RasterArgs A{};
   if (fill_args(A, N, F, S, T, near_, far_, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
-                func_id_rgb, func_id_alpha, texture_sample_type, double_side, workspace, workspace_bytes))
+                func_id_rgb, func_id_alpha, texture_sample_type, double_side, workspace, workspace_bytes, 1, !compact))
     return 1;
   A.records_valid = setup_done;
+  if (compact) {      // the forward's compact records + coordinate table; the workspace is this call's own scratch
+    if (attach_saved(A, saved, saved_bytes) || !carve_backward_scratch(A, workspace, workspace_bytes, 0)) return 1;
+    A.records_valid = 2;
+    setup_done = 1;
+  }
   if (!faces || !textures || !aggrs_info || !soft_colors || !grad_faces || !grad_textures || !grad_soft_colors)
     return fail("raster_backward: null tensor pointer");
   A.faces = faces; A.textures = textures;
@@ -1100,6 +1151,48 @@ extern "C" int lasr_b200_raster_backward(const float* faces, const float* textur
     if (check_launch("raster_setup_kernel")) return 1;
   }
   return launch_backward(A, nf, st);
+}
+
+extern "C" int lasr_b200_raster_backward(const float* faces, const float* textures, const float* soft_colors,
+                                         const float* aggrs_info, float* grad_faces, float* grad_textures,
+                                         const float* grad_soft_colors, void* workspace, size_t workspace_bytes,
+                                         int N, int F, int S, int T, float near_, float far_,
+                                         const float* near_far_dev, float eps, float sigma_val, int func_id_dist,
+                                         float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
+                                         int texture_sample_type, int double_side, int setup_done, void* stream) {
+  return raster_backward_impl(faces, textures, soft_colors, aggrs_info, grad_faces, grad_textures, grad_soft_colors,
+                              workspace, workspace_bytes, N, F, S, T, near_, far_, near_far_dev, eps, sigma_val,
+                              func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, texture_sample_type,
+                              double_side, setup_done, stream);
+}
+
+extern "C" size_t lasr_b200_raster_saved_bytes(int N, int F, int S) { return raster_saved_bytes(N, F, S); }
+extern "C" size_t lasr_b200_raster_backward_scratch_bytes(int N, int F, int S) { return backward_scratch_bytes(N, F, S, 1); }
+
+extern "C" int lasr_b200_raster_forward_compact(const float* faces, const float* textures, float* aggrs_info,
+                                                float* soft_colors, void* saved, size_t saved_bytes, void* workspace,
+                                                size_t workspace_bytes, int N, int F, int S, int T, float near_,
+                                                float far_, const float* near_far_dev, float eps, float sigma_val,
+                                                int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
+                                                int func_id_alpha, int texture_sample_type, int double_side,
+                                                const float* background_host, void* stream) {
+  return raster_forward_impl(faces, textures, aggrs_info, soft_colors, workspace, workspace_bytes, N, F, S, T, near_, far_,
+                             near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha,
+                             texture_sample_type, double_side, background_host, stream, saved, saved_bytes, true);
+}
+
+extern "C" int lasr_b200_raster_backward_compact(const float* faces, const float* textures, const float* soft_colors,
+                                                 const float* aggrs_info, float* grad_faces, float* grad_textures,
+                                                 const float* grad_soft_colors, const void* saved, size_t saved_bytes,
+                                                 void* workspace, size_t workspace_bytes, int N, int F, int S, int T,
+                                                 float near_, float far_, const float* near_far_dev, float eps,
+                                                 float sigma_val, int func_id_dist, float dist_eps, float gamma_val,
+                                                 int func_id_rgb, int func_id_alpha, int texture_sample_type,
+                                                 int double_side, void* stream) {
+  return raster_backward_impl(faces, textures, soft_colors, aggrs_info, grad_faces, grad_textures, grad_soft_colors,
+                              workspace, workspace_bytes, N, F, S, T, near_, far_, near_far_dev, eps, sigma_val,
+                              func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, texture_sample_type,
+                              double_side, 1, stream, const_cast<void*>(saved), saved_bytes, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1139,14 +1232,17 @@ static int render_forward_impl(const float* verts, const int32_t* tri, const Col
                                size_t workspace_bytes, int N, int V, int F, int S, float near_, float far_,
                                const float* near_far_dev, float eps, float sigma_val, int func_id_dist,
                                float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
-                               int double_side, int num_sets, const float* background, void* stream) {
+                               int double_side, int num_sets, const float* background, void* stream,
+                               void* saved = nullptr, size_t saved_bytes = 0, bool compact = false) {
   RasterArgs A{};
   if (num_sets < 1 || num_sets > kMaxSets) return fail("render: num_sets must be 1, 2 or 3");
-  if (workspace_bytes < lasr_b200_render_workspace_bytes(N, F, S, num_sets)) return fail("render: workspace too small");
+  if (workspace_bytes < (compact ? raster_ws_bytes(N, F, S, num_sets) : lasr_b200_render_workspace_bytes(N, F, S, num_sets)))
+    return fail("render: workspace too small");   // (compact: no room for the backward's per-face gradients needed)
   if (fill_args(A, N, F, S, 3, near_, far_, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
                 func_id_rgb, func_id_alpha, 1, double_side, workspace, workspace_bytes, num_sets))
     return 1;
   if (fill_indexed(A, verts, tri, sets, V)) return 1;
+  if (compact && attach_saved(A, saved, saved_bytes)) return 1;
   if (!aggrs_info || !soft_colors) return fail("render_forward: null tensor pointer");
   A.aggrs_info = aggrs_info; A.soft_colors = soft_colors;
   if (background) {   // host array of 3*num_sets floats: no pre-fill pass over the image, no read of it here
@@ -1210,16 +1306,27 @@ static int render_backward_impl(const float* verts, const int32_t* tri, const Co
                                 int V, int F, int S, float near_, float far_, const float* near_far_dev, float eps,
                                 float sigma_val, int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
                                 int func_id_alpha, int double_side, int num_sets, int detached_sets, int setup_done,
-                                void* stream) {
+                                void* stream, void* saved = nullptr, size_t saved_bytes = 0, bool compact = false) {
   RasterArgs A{};
   if (num_sets < 1 || num_sets > kMaxSets) return fail("render: num_sets must be 1, 2 or 3");
   if (detached_sets < 0 || detached_sets > 1 || detached_sets >= num_sets)
     return fail("render_backward: detached_sets must be 0, or 1 with num_sets >= 2");
-  if (workspace_bytes < lasr_b200_render_workspace_bytes(N, F, S, num_sets)) return fail("render: workspace too small");
+  if (!compact && workspace_bytes < lasr_b200_render_workspace_bytes(N, F, S, num_sets)) return fail("render: workspace too small");
   if (fill_args(A, N, F, S, 3, near_, far_, near_far_dev, eps, sigma_val, func_id_dist, dist_eps, gamma_val,
-                func_id_rgb, func_id_alpha, 1, double_side, workspace, workspace_bytes, num_sets))
+                func_id_rgb, func_id_alpha, 1, double_side, workspace, workspace_bytes, num_sets, !compact))
     return 1;
   A.records_valid = setup_done;
+  const size_t grad_bytes = align256((size_t)N * F * 9 * sizeof(float)) + align256((size_t)N * F * 9 * num_sets * sizeof(float));
+  char* scratch = nullptr;
+  if (compact) {      // the forward's compact records + coordinate table; the workspace is this call's own scratch
+    if (attach_saved(A, saved, saved_bytes)) return 1;
+    scratch = carve_backward_scratch(A, workspace, workspace_bytes, grad_bytes);
+    if (!scratch) return 1;
+    A.records_valid = 2;
+    setup_done = 1;
+  } else {
+    scratch = reinterpret_cast<char*>(workspace) + raster_ws_bytes(N, F, S, num_sets);
+  }
   A.first_live_set = detached_sets;
   if (fill_indexed(A, verts, tri, sets, V)) return 1;
   if (!csr_offsets || !csr_entries || !grad_verts) return fail("render_backward: null tensor pointer");
@@ -1234,7 +1341,6 @@ static int render_backward_impl(const float* verts, const int32_t* tri, const Co
   A.aggrs_info = const_cast<float*>(aggrs_info);
   A.soft_colors = const_cast<float*>(soft_colors);
   A.grad_soft_colors = grad_soft_colors;
-  char* scratch = reinterpret_cast<char*>(workspace) + raster_ws_bytes(N, F, S, num_sets);
   const long long nf = (long long)N * F;
   A.grad_faces = reinterpret_cast<float*>(scratch);
   A.grad_textures = reinterpret_cast<float*>(scratch + align256((size_t)nf * 9 * sizeof(float)));
@@ -1309,4 +1415,48 @@ extern "C" int lasr_b200_render_backward_sets_packed(const float* verts, const i
                               grad_verts, g, workspace, workspace_bytes, N, V, F, S, near_, far_, near_far_dev, eps,
                               sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side,
                               num_sets, detached_sets, setup_done, stream);
+}
+
+extern "C" size_t lasr_b200_render_backward_scratch_bytes(int N, int F, int S, int num_sets) {
+  if (N <= 0 || F <= 0 || S <= 0 || num_sets < 1 || num_sets > kMaxSets) return 0;
+  return backward_scratch_bytes(N, F, S, num_sets) + align256((size_t)N * F * 9 * sizeof(float)) +
+         align256((size_t)N * F * 9 * num_sets * sizeof(float));
+}
+
+extern "C" int lasr_b200_render_forward_sets_compact(const float* verts, const int32_t* tri, const float* const* set_ptrs,
+                                                     const int* set_shifts, float* aggrs_info, float* soft_colors,
+                                                     void* saved, size_t saved_bytes, void* workspace,
+                                                     size_t workspace_bytes, int N, int V, int F, int S, float near_,
+                                                     float far_, const float* near_far_dev, float eps, float sigma_val,
+                                                     int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
+                                                     int func_id_alpha, int double_side, int num_sets,
+                                                     const float* background, void* stream) {
+  if (!set_ptrs || num_sets < 1 || num_sets > kMaxSets) return fail("render_forward_sets_compact: null set array or bad num_sets");
+  return render_forward_impl(verts, tri, separate_sets(set_ptrs, set_shifts, num_sets), aggrs_info, soft_colors,
+                             workspace, workspace_bytes, N, V, F, S, near_, far_, near_far_dev, eps, sigma_val,
+                             func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side, num_sets,
+                             background, stream, saved, saved_bytes, true);
+}
+
+extern "C" int lasr_b200_render_backward_sets_packed_compact(const float* verts, const int32_t* tri,
+                                                             const float* const* set_ptrs, const int* set_shifts,
+                                                             const float* packed_grad, const int32_t* csr_offsets,
+                                                             const int32_t* csr_entries, float* grad_verts,
+                                                             float* const* grad_set_ptrs, const void* saved,
+                                                             size_t saved_bytes, void* workspace, size_t workspace_bytes,
+                                                             int N, int V, int F, int S, float near_, float far_,
+                                                             const float* near_far_dev, float eps, float sigma_val,
+                                                             int func_id_dist, float dist_eps, float gamma_val,
+                                                             int func_id_rgb, int func_id_alpha, int double_side,
+                                                             int num_sets, int detached_sets, void* stream) {
+  if (!packed_grad) return fail("render_backward_sets_packed_compact: null packed gradient");
+  if (!set_ptrs || !grad_set_ptrs || num_sets < 1 || num_sets > kMaxSets)
+    return fail("render_backward_sets_packed_compact: null set array or bad num_sets");
+  const ColourSets sets = separate_sets(set_ptrs, set_shifts, num_sets);
+  SetGrads g{};
+  for (int s = 0; s < num_sets; ++s) { g.p[s] = grad_set_ptrs[s]; g.shift[s] = sets.shift[s]; }
+  return render_backward_impl(verts, tri, sets, nullptr, nullptr, nullptr, packed_grad, csr_offsets, csr_entries,
+                              grad_verts, g, workspace, workspace_bytes, N, V, F, S, near_, far_, near_far_dev, eps,
+                              sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, double_side,
+                              num_sets, detached_sets, 1, stream, const_cast<void*>(saved), saved_bytes, true);
 }

@@ -38,6 +38,7 @@ constexpr int kMaxSets = 3;    // colour sets interpolated in one geometry pass 
 // floats per face record: 32 of geometry, then 9 per colour set (+ z for the reference-faithful
 // generic path, which is single-set), rounded to float4s: 44 / 52 / 60 for 1 / 2 / 3 sets
 __host__ __device__ constexpr int rec_words(int K) { return K == 1 ? 44 : ((32 + 9 * K + 3) / 4) * 4; }
+constexpr int kCompactWords = 20;   // inverse 9 | 1/z 3 | 1/edge^2 3 | flags | kappa | 3 spare  (80 bytes, 16-byte aligned)
 
 struct RasterArgs {
   const float* faces;        // [N,F,9]
@@ -53,6 +54,8 @@ struct RasterArgs {
   uint2* face_window;        // [N*F] packed pixel windows
   float4* face_border;       // [N*F] dilated bounding boxes (lox, hix, loy, hiy)
   float* face_record;        // [N*F][rec_words(K)]
+  float* compact_record;     // [N*F][kCompactWords] or null: the division results of the record only -- what the backward
+                             //   keeps of a face when the caller saves 80 bytes per face instead of the whole workspace
   float* coords;             // [S] pixel-centre coordinates
   int records_valid;         // backward: workspace already holds the forward's setup of the same inputs
   int* big_list;             // [1 + cap]: count, then flat (frame*F + face) ids of faces deferred to the CTA-per-face pass
@@ -197,6 +200,27 @@ struct FaceGeom {
   bool front;
 };
 
+// a[e][j] from the vertices: sym = F F^T with z -> 1 (.cu:288-294); only row differences are ever used (:81-83,132-134)
+__device__ __forceinline__ void face_edge_rows(FaceGeom& g) {
+  float sym[3][3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sym[j][k] = __fadd_rn(dot2(g.x[j], g.x[k], g.y[j], g.y[k]), 1.0f);
+#pragma unroll
+  for (int e = 0; e < 3; ++e)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) g.a[e][j] = __fsub_rn(sym[e][j], sym[(e + 1) % 3][j]);
+}
+
+// bounding box dilated by sqrt(threshold) (.cu:32-38)
+__device__ __forceinline__ void face_box(FaceGeom& g, float sthr) {
+  g.hix = __fadd_rn(max3(g.x[0], g.x[1], g.x[2]), sthr);
+  g.lox = __fsub_rn(min3(g.x[0], g.x[1], g.x[2]), sthr);
+  g.hiy = __fadd_rn(max3(g.y[0], g.y[1], g.y[2]), sthr);
+  g.loy = __fsub_rn(min3(g.y[0], g.y[1], g.y[2]), sthr);
+}
+
 __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float sthr, FaceGeom& g) {
   const float x0 = fv[0], y0 = fv[1], x1 = fv[3], y1 = fv[4], x2 = fv[6], y2 = fv[7];
   g.x[0] = x0; g.x[1] = x1; g.x[2] = x2;
@@ -212,18 +236,9 @@ __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float s
                         __fsub_rn(y0, y1), __fsub_rn(x1, x0), cross2(x0, y1, x1, y0)};
 #pragma unroll
   for (int k = 0; k < 9; ++k) g.inv[k] = __fdiv_rn(adj[k], det);  // :284-286 (IEEE division)
-  // sym = F F^T with z -> 1 (:288-294); only row differences are ever used (:81-83,132-134)
-  float sym[3][3];
+  face_edge_rows(g);
 #pragma unroll
-  for (int j = 0; j < 3; ++j)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) sym[j][k] = __fadd_rn(dot2(g.x[j], g.x[k], g.y[j], g.y[k]), 1.0f);
-#pragma unroll
-  for (int e = 0; e < 3; ++e) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) g.a[e][j] = __fsub_rn(sym[e][j], sym[(e + 1) % 3][j]);
-    g.rden[e] = __fdiv_rn(1.f, __fsub_rn(g.a[e][e], g.a[e][(e + 1) % 3]));
-  }
+  for (int e = 0; e < 3; ++e) g.rden[e] = __fdiv_rn(1.f, __fsub_rn(g.a[e][e], g.a[e][(e + 1) % 3]));
   // first obtuse corner (:296-304)
   g.obt = -1;
 #pragma unroll
@@ -249,10 +264,50 @@ __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float s
     const float ke = 2.f * LASR_NOISE_K * eta / det;
     g.kappa = ke * ke;   // inf / NaN for degenerate faces: the prediction is then never trusted
   }
-  g.hix = __fadd_rn(max3(x0, x1, x2), sthr);
-  g.lox = __fsub_rn(min3(x0, x1, x2), sthr);
-  g.hiy = __fadd_rn(max3(y0, y1, y2), sthr);
-  g.loy = __fsub_rn(min3(y0, y1, y2), sthr);
+  face_box(g, sthr);
+}
+
+// The face as the backward needs it from the vertices plus the COMPACT record (store_compact): everything that costs a
+// division comes from the record, the rest -- the edge rows and the box: sums, differences, min / max -- is re-derived
+// by the same expressions face_setup uses, so every field has the bits the forward worked with.
+__device__ __forceinline__ void face_from_compact(const float* __restrict__ fv, float sthr, const float* __restrict__ r,
+                                                  FaceGeom& g) {
+  g.x[0] = fv[0]; g.x[1] = fv[3]; g.x[2] = fv[6];
+  g.y[0] = fv[1]; g.y[1] = fv[4]; g.y[2] = fv[7];
+  g.z[0] = fv[2]; g.z[1] = fv[5]; g.z[2] = fv[8];
+  const float4* r4 = reinterpret_cast<const float4*>(r);
+  float v[kCompactWords];
+#pragma unroll
+  for (int k = 0; k < kCompactWords / 4; ++k) {
+    const float4 q = __ldg(r4 + k);
+    v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) g.inv[k] = v[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { g.iz[k] = v[9 + k]; g.rden[k] = v[12 + k]; }
+  const int fl = __float_as_int(v[15]);
+  g.obt = (fl & 3) - 1;
+  g.front = (fl & 4) != 0;
+  g.kappa = v[16];
+  g.det = 0.f;       // used by face_setup only
+  face_edge_rows(g);
+  face_box(g, sthr);
+}
+
+__device__ __forceinline__ void store_compact(float* __restrict__ r, const FaceGeom& g) {
+  float v[kCompactWords];
+#pragma unroll
+  for (int k = 0; k < kCompactWords; ++k) v[k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) v[k] = g.inv[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { v[9 + k] = g.iz[k]; v[12 + k] = g.rden[k]; }
+  v[15] = __int_as_float((g.obt + 1) | (g.front ? 4 : 0));
+  v[16] = g.kappa;
+  float4* r4 = reinterpret_cast<float4*>(r);
+#pragma unroll
+  for (int k = 0; k < kCompactWords / 4; ++k) r4[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
 }
 
 // record layout (float index):

@@ -130,7 +130,8 @@ class RenderIndexedFunction(Function):
         # only sees re-wrapped saved tensors
         offsets, entries = vertex_adjacency(tri, V)
         # (the package re-exports the FUNCTION soft_rasterize under the module's name: fetch the module itself)
-        ctx.keep_ws = bool(sys.modules[SoftRasterizeFunction.__module__].KEEP_WORKSPACE)
+        # ("compact" exists for the reference-signature op and for render_sets; the stacked form keeps the workspace)
+        ctx.keep_ws = sys.modules[SoftRasterizeFunction.__module__].keep_mode() != "none"
         if ctx.keep_ws:
             ctx.save_for_backward(v, c, tri, img, aggrs, ws, offsets, entries)
         else:
@@ -194,11 +195,13 @@ class RenderSetsFunction(Function):
         aggrs = torch.empty(N, 2, S, S, dtype=torch.float32, device=dev)
         img = torch.empty(N, 10, S, S, dtype=torch.float32, device=dev)
         ws = _cabi.render_workspace(N, tri.shape[0], S, dev, 3)
+        ctx.keep = sys.modules[SoftRasterizeFunction.__module__].keep_mode()
+        saved = _cabi.saved_buffer(N, tri.shape[0], S, dev) if ctx.keep == "compact" else None
         _cabi.render_forward_sets(v, tri, sets, ctx.shifts, aggrs, img, ws, S, ctx.near, ctx.far, ctx.nf, *ctx.scal,
-                                  background=bg)
+                                  background=bg, saved=saved)
         offsets, entries = vertex_adjacency(tri, V)
-        ctx.keep_ws = bool(sys.modules[SoftRasterizeFunction.__module__].KEEP_WORKSPACE)
-        ctx.save_for_backward(v, tri, offsets, entries, *sets, *([ws] if ctx.keep_ws else []))
+        kept = [ws] if ctx.keep == "full" else ([saved] if ctx.keep == "compact" else [])   # compact: 80 B per face
+        ctx.save_for_backward(v, tri, offsets, entries, *sets, *kept)
         ctx.shapes = (vertices.shape, set1.shape, set2.shape)
         ctx.grad_link = grad_link
         if grad_link is not None:
@@ -209,7 +212,14 @@ class RenderSetsFunction(Function):
     def backward(ctx, grad):
         v, tri, offsets, entries, s0, s1, s2 = ctx.saved_tensors[:7]
         N, V = v.shape[:2]
-        ws = ctx.saved_tensors[7] if ctx.keep_ws else _cabi.render_workspace(N, tri.shape[0], ctx.S, v.device, 3)
+        saved = None
+        if ctx.keep == "full":
+            ws = ctx.saved_tensors[7]
+        elif ctx.keep == "compact":
+            saved = ctx.saved_tensors[7]
+            ws = _cabi.render_backward_scratch(N, tri.shape[0], ctx.S, v.device, 3)
+        else:
+            ws = _cabi.render_workspace(N, tri.shape[0], ctx.S, v.device, 3)
         link = ctx.grad_link
         if link is None or link.packed is None:
             raise RuntimeError("render_sets: the backward takes the packed gradient of lasr_b200.losses.fused_head "
@@ -220,8 +230,8 @@ class RenderSetsFunction(Function):
         packed, link.packed, link.placeholder = link.packed, None, None
         gv, g1, g2 = torch.empty_like(v), torch.empty_like(s1), torch.empty_like(s2)
         _cabi.render_backward_sets_packed(v, tri, (s0, s1, s2), ctx.shifts, packed, offsets, entries, gv, (None, g1, g2),
-                                          ws, ctx.S, ctx.near, ctx.far, ctx.nf, *ctx.scal, setup_done=ctx.keep_ws,
-                                          detached_sets=1)
+                                          ws, ctx.S, ctx.near, ctx.far, ctx.nf, *ctx.scal, setup_done=ctx.keep == "full",
+                                          detached_sets=1, saved=saved)
         vshape, s1shape, s2shape = ctx.shapes
         return (gv.reshape(vshape), None, g1.reshape(s1shape), g2.reshape(s2shape)) + (None,) * 15
 

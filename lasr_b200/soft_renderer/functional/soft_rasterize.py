@@ -24,8 +24,22 @@ from ... import _cabi
 # Keep the forward's per-face scratch (200 B per face: windows, boxes, records) alive for the backward, as the reference
 # keeps its `faces_info` (108 B per face, soft_rasterize.py:64,71).  False: nothing but the op's own inputs and outputs is
 # saved and the backward recomputes the records (`setup_done=0`): 0 B per face kept, a few per cent slower backward
-# (profiles/r2/README.md).  Read at forward time; LASR_B200_KEEP_WORKSPACE=0 in the environment sets the default.
-KEEP_WORKSPACE = os.environ.get("LASR_B200_KEEP_WORKSPACE", "1") != "0"
+# (profiles/r2/README.md).  "compact": 80 B per face kept -- the record's division results in a separate buffer, the
+# workspace itself freed when the forward returns; the backward re-derives the rest from the op's inputs, same bits
+# (lasr_b200_raster_forward_compact / _backward_compact; the colour-set route of the fused region likewise).
+# Read at forward time; LASR_B200_KEEP_WORKSPACE=0 / =compact in the environment set the default.
+_env_keep = os.environ.get("LASR_B200_KEEP_WORKSPACE", "1")
+KEEP_WORKSPACE = "compact" if _env_keep == "compact" else _env_keep != "0"
+
+
+def keep_mode():
+    """-> "full" | "compact" | "none" from the module switch (read at forward time)."""
+    k = KEEP_WORKSPACE
+    if isinstance(k, str):
+        if k != "compact":
+            raise ValueError("KEEP_WORKSPACE is True, False or 'compact'")
+        return "compact"
+    return "full" if k else "none"
 
 DIST_FUNCS = {"hard": 0, "barycentric": 1, "euclidean": 2}
 RGB_FUNCS = {"hard": 0, "softmax": 1}
@@ -75,21 +89,28 @@ class SoftRasterizeFunction(Function):
         # the background colour travels as a kernel argument (lasr_b200_raster_forward_bg): the reference's three fills
         # of soft_colors (:50-53) and the kernel's read of them are 24 S^2 bytes of HBM traffic per frame for a constant
         workspace = _cabi.raster_workspace(nb, nf, S, device)
+        ctx.keep = keep_mode()
+        saved = _cabi.saved_buffer(nb, nf, S, device) if ctx.keep == "compact" else None
         _cabi.raster_forward(fv, tex, aggrs_info, soft_colors, workspace, S, ctx.near, ctx.far, ctx.near_far_dev,
                              eps, sigma_val, ctx.func_dist_type, ctx.dist_eps, gamma_val, ctx.func_rgb_type,
                              ctx.func_alpha_type, ctx.texture_type, ctx.fill_back,
-                             background=[float(background_color[k]) for k in range(3)])
-        ctx.keep_ws = bool(KEEP_WORKSPACE)
-        if ctx.keep_ws:
+                             background=[float(background_color[k]) for k in range(3)], saved=saved)
+        if ctx.keep == "full":
             ctx.save_for_backward(fv, tex, soft_colors, aggrs_info, workspace)   # workspace plays the reference's faces_info
+        elif ctx.keep == "compact":
+            ctx.save_for_backward(fv, tex, soft_colors, aggrs_info, saved)       # 80 B per face; the workspace dies here
         else:
             ctx.save_for_backward(fv, tex, soft_colors, aggrs_info)
         return soft_colors
 
     @staticmethod
     def backward(ctx, grad_soft_colors):
-        if ctx.keep_ws:
+        saved = None
+        if ctx.keep == "full":
             fv, tex, soft_colors, aggrs_info, workspace = ctx.saved_tensors
+        elif ctx.keep == "compact":
+            fv, tex, soft_colors, aggrs_info, saved = ctx.saved_tensors
+            workspace = _cabi.raster_backward_scratch(fv.shape[0], fv.shape[1], ctx.image_size, fv.device)
         else:
             fv, tex, soft_colors, aggrs_info = ctx.saved_tensors
             workspace = _cabi.raster_workspace(fv.shape[0], fv.shape[1], ctx.image_size, fv.device)
@@ -101,7 +122,7 @@ class SoftRasterizeFunction(Function):
         _cabi.raster_backward(fv, tex, soft_colors, aggrs_info, grad_faces, grad_textures, g, workspace, S,
                               ctx.near, ctx.far, ctx.near_far_dev, ctx.eps, ctx.sigma_val, ctx.func_dist_type,
                               ctx.dist_eps, ctx.gamma_val, ctx.func_rgb_type, ctx.func_alpha_type, ctx.texture_type,
-                              ctx.fill_back, setup_done=ctx.keep_ws)
+                              ctx.fill_back, setup_done=ctx.keep == "full", saved=saved)
         fshape, tshape = ctx.in_shapes
         return (grad_faces.reshape(fshape), grad_textures.reshape(tshape)) + (None,) * 13
 

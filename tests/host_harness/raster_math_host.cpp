@@ -398,3 +398,26 @@ extern "C" void lasr_host_pixel_coords(int S, float* out) {
 }
 
 extern "C" int lasr_host_fast_inside(void) { return LASR_FAST_INSIDE; }
+
+// Compact record round trip: face_setup -> store_compact -> face_from_compact must give back the FaceGeom the forward
+// worked with, field for field and bit for bit (det excepted: only face_setup uses it).  Returns the number of faces
+// with any differing field.
+extern "C" int lasr_host_compact_roundtrip(const float* faces9, int F, float sthr) {
+  int bad = 0;
+  for (int f = 0; f < F; ++f) {
+    FaceGeom a, b;
+    face_setup(faces9 + 9 * f, sthr, a);
+    alignas(16) float rec[kCompactWords];
+    store_compact(rec, a);
+    face_from_compact(faces9 + 9 * f, sthr, rec, b);
+    bool same = a.obt == b.obt && a.front == b.front;
+    same = same && memcmp(a.inv, b.inv, sizeof a.inv) == 0 && memcmp(a.x, b.x, sizeof a.x) == 0 &&
+           memcmp(a.y, b.y, sizeof a.y) == 0 && memcmp(a.z, b.z, sizeof a.z) == 0 && memcmp(a.iz, b.iz, sizeof a.iz) == 0 &&
+           memcmp(a.a, b.a, sizeof a.a) == 0 && memcmp(a.rden, b.rden, sizeof a.rden) == 0 &&
+           memcmp(&a.lox, &b.lox, sizeof(float)) == 0 && memcmp(&a.hix, &b.hix, sizeof(float)) == 0 &&
+           memcmp(&a.loy, &b.loy, sizeof(float)) == 0 && memcmp(&a.hiy, &b.hiy, sizeof(float)) == 0 &&
+           memcmp(&a.kappa, &b.kappa, sizeof(float)) == 0;
+    bad += same ? 0 : 1;
+  }
+  return bad;
+}

@@ -404,7 +404,7 @@ def test_kernel_written_render_space_vertices_equal_the_pytorch_chain(monkeypatc
         assert err < 1e-6, (k, err)
 
 
-def test_separate_colour_sets_with_a_frame_shift_equal_the_stacked_rolled_render():
+def test_separate_colour_sets_with_a_frame_shift_equal_the_stacked_rolled_render(monkeypatch):
     """lasr_b200_render_forward_sets / _backward_sets_packed and the head's pair_shift: the pair's positions and
     intrinsics are the own tensors read half a batch further on.  Same image bit for bit as the stacked [3,N,V,3] render
     of (own, roll(own), tex); same losses; the gradients of the ONE position tensor, of the texture, of the vertices and
@@ -453,6 +453,19 @@ def test_separate_colour_sets_with_a_frame_shift_equal_the_stacked_rolled_render
     for nm, x, y in zip(("verts", "own", "tex", "pp", "f"), grads_a, grads_b):
         assert float(y.abs().max()) > 0, nm
         assert torch.allclose(x, y, rtol=1e-5, atol=1e-9 + 1e-6 * float(y.abs().max())), (nm, float((x - y).abs().max()))
+    # not keeping the forward's per-face scratch: the backward re-derives the records from the shifted sets -- same bits
+    import sys
+    mod = sys.modules[sr.functional.SoftRasterizeFunction.__module__]
+    monkeypatch.setattr(mod, "KEEP_WORKSPACE", False)
+    img_c, loss_c, _, grads_c = run(True)
+    assert torch.equal(img_a, img_c) and loss_a == loss_c
+    assert all(torch.equal(x, y) for x, y in zip(grads_a, grads_c))
+    # ... and keeping 80 bytes per face of it (compact mode): same bits again
+    monkeypatch.setattr(mod, "KEEP_WORKSPACE", "compact")
+    img_d, loss_d, _, grads_d = run(True)
+    monkeypatch.setattr(mod, "KEEP_WORKSPACE", True)
+    assert torch.equal(img_a, img_d) and loss_a == loss_d
+    assert all(torch.equal(x, y) for x, y in zip(grads_a, grads_d))
     # differentiating the shifted head without the packed link is refused, not silently wrong
     with pytest.raises(ValueError, match="pair_shift"):
         L.fused_head(img_a.requires_grad_(True), pp0.to(dev), pp0.to(dev), f0.to(dev), f0.to(dev), obs["imgs"], obs["masks"],

@@ -434,3 +434,20 @@ def test_kernel_code_matches_the_oracle_across_depth_ranges_sizes_and_scales(lib
             m = ~np.isnan(ref)
             rep = parity.grad_report(np.where(m, ours, 0), np.where(m, ref, 0))
             assert rep["scale"] < 1e-20 or (rep["rel_l2"] < 1e-4 and rep["max_over_scale"] < 2e-4), (what, rep)
+
+
+@pytest.mark.parametrize("kind", ["random", "sliver", "needle", "tiny", "degenerate", "iso"])
+def test_compact_record_gives_the_backward_the_forwards_own_face(libs, kind):
+    """Compact mode keeps 80 bytes per face -- the division results of the record -- and the backward re-derives the
+    edge rows and the dilated box from the op's inputs (face_from_compact, raster_common.cuh): every field of the face
+    must have the bits the forward's record had, on meshes and on pathological soups (NaN fields of degenerate faces
+    included: compared as bit patterns)."""
+    rng = np.random.RandomState(len(kind))
+    fv = np.ascontiguousarray(_soup(rng, 20000, kind), np.float32)
+    if kind == "random":          # + faces reaching far beyond the screen and huge coordinates
+        fv[:2000, [0, 1, 3, 4, 6, 7]] *= np.float32(50.0)
+        fv[2000:2100, 0] = np.float32(1e30)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for sigma in (1e-4, 1e-5):
+        sthr = np.float32(np.sqrt(np.float32(np.log(1.0 / 1e-4 - 1.0)) * np.float32(sigma)))
+        assert libs[1].lasr_host_compact_roundtrip(P(fv), ctypes.c_int(len(fv)), ctypes.c_float(float(sthr))) == 0

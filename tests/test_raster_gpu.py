@@ -393,6 +393,29 @@ def test_dropping_the_saved_workspace_changes_no_gradient(srf, monkeypatch):
     dropped_idx = indexed()
     assert all(np.array_equal(a, b) for a, b in zip(kept, dropped))
     assert all(torch.equal(a, b) for a, b in zip(kept_idx, dropped_idx))
+    # "compact": 80 B per face kept (the record's division results), the workspace freed after the forward; the backward
+    # re-derives the edge rows and the box from the op's inputs with the forward's own expressions -- same bits, in LASR's
+    # configuration and in the generic operator modes (surface textures, barycentric / hard distances, hard aggregation)
+    monkeypatch.setattr(mod, "KEEP_WORKSPACE", "compact")
+    assert mod.keep_mode() == "compact"
+    compact = run_ours(srf, c)
+    assert all(np.array_equal(a, b) for a, b in zip(kept, compact))
+    assert all(torch.equal(a, b) for a, b in zip(kept_idx, indexed()))      # (the stacked indexed form keeps the workspace)
+    for mode in (("euclidean", "softmax", "prod", "surface"), ("barycentric", "softmax", "sum", "vertex"),
+                 ("hard", "hard", "hard", "surface"), ("euclidean", "hard", "prod", "vertex")):
+        cm = cases.mode_case(*mode)
+        monkeypatch.setattr(mod, "KEEP_WORKSPACE", True)
+        full = run_ours(srf, cm)
+        monkeypatch.setattr(mod, "KEEP_WORKSPACE", "compact")
+        comp = run_ours(srf, cm)
+        assert np.array_equal(full[0], comp[0]) and np.array_equal(full[1], comp[1]), mode
+        if mode[3] == "vertex":
+            assert np.array_equal(full[2], comp[2]), mode
+        else:        # 'surface' texel gradients are scattered with float atomics: equal up to summation order
+            assert np.allclose(full[2], comp[2], rtol=1e-5, atol=1e-7), mode
+    from lasr_b200 import _cabi
+    per_face = (int(_cabi.lib().lasr_b200_raster_saved_bytes(64, 5856, 256)) - 1024) / (64 * 5856)
+    assert per_face <= 108            # the reference's faces_info is 108 B per face
 
 
 def test_anti_aliasing_and_forward_entry_point(srf, oracle):
