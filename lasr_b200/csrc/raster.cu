@@ -568,7 +568,10 @@ constexpr int kBigListCap = 16384;     // deferred faces the workspace can list 
 template <bool k32> struct PlaneIndex { typedef long long type; };
 template <> struct PlaneIndex<true> { typedef unsigned type; };
 
-template <bool kFast, bool kBig, int K, int KF, bool kPacked = false>
+// kCompact: the face comes from the COMPACT record + the op's inputs (compact mode); a separate instantiation, so the
+// default kernels are the code they were before the mode existed (folded into one kernel behind a run-time test, the
+// single-set backward measured 13 % slower in the DEFAULT mode: profiles/r2/README.md, trip 21).
+template <bool kFast, bool kBig, int K, int KF, bool kPacked = false, bool kCompact = false>
 __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K == 1 ? LASR_BWD_MIN_BLOCKS : (K - KF >= 3 ? LASR_BWD_MIN_BLOCKS_MULTI : LASR_BWD_MIN_BLOCKS_LIVE2))) raster_backward_kernel(RasterArgs A) {
   constexpr int kMode = kFast ? (LASR_FTZ_MUFU_BWD ? 2 : 1) : 0;   // arithmetic mode, see raster_common.cuh
   constexpr int kRecWords = rec_words(K);
@@ -612,14 +615,14 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
 
   float tex9[9 * K];
   FaceGeom g;
-  if (A.records_valid == 1) {   // the forward's per-face record (the reference hands faces_info to its backward too)
-    load_record<K>(A.face_record + wg * kRecWords, g, tex9);
-    const float4 bd = __ldg(A.face_border + wg);
-    g.lox = bd.x; g.hix = bd.y; g.loy = bd.z; g.hiy = bd.w;
-  } else if (A.records_valid == 2) {   // the forward's COMPACT record (80 bytes per face) + the op's own inputs
+  if (kCompact) {                // the forward's COMPACT record (80 bytes per face) + the op's own inputs
     float fv[9];
     fetch_face(A, n, f, fv, tex9, sample == 1);
     face_from_compact(fv, sthr, A.compact_record + wg * kCompactWords, g);
+  } else if (A.records_valid) {   // the forward's per-face record (the reference hands faces_info to its backward too)
+    load_record<K>(A.face_record + wg * kRecWords, g, tex9);
+    const float4 bd = __ldg(A.face_border + wg);
+    g.lox = bd.x; g.hix = bd.y; g.loy = bd.z; g.hiy = bd.w;
   } else {
     float fv[9];
     fetch_face(A, n, f, fv, tex9, sample == 1);
@@ -965,6 +968,37 @@ static int launch_forward(const RasterArgs& A, cudaStream_t st) {
   return check_launch("raster_forward_kernel");
 }
 
+// compact mode (records_valid == 2): the single-set op of the reference signature and the fused region's three packed sets
+static int launch_backward_compact(const RasterArgs& A, unsigned blocks, bool pack_first, cudaStream_t st) {
+  if (A.K == 1 && pack_first) {
+    RasterArgs P = A;
+    P.packed = A.pack_area;
+    raster_backward_kernel<true, false, 1, 0, true, true><<<blocks, LASR_BWD_THREADS, 0, st>>>(P);
+    if (check_launch("raster_backward_kernel<packed, compact>")) return 1;
+    raster_backward_kernel<true, true, 1, 0, true, true><<<592, 256, 0, st>>>(P);
+    return check_launch("raster_backward_kernel<packed, big, compact>");
+  }
+  if (A.K == 1 && !A.packed) {
+    if (is_fast(A)) {
+      raster_backward_kernel<true, false, 1, 0, false, true><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+      if (check_launch("raster_backward_kernel<compact>")) return 1;
+      raster_backward_kernel<true, true, 1, 0, false, true><<<592, 256, 0, st>>>(A);
+    } else {
+      raster_backward_kernel<false, false, 1, 0, false, true><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+      if (check_launch("raster_backward_kernel<compact>")) return 1;
+      raster_backward_kernel<false, true, 1, 0, false, true><<<592, 256, 0, st>>>(A);
+    }
+    return check_launch("raster_backward_kernel<big, compact>");
+  }
+  if (A.K == 3 && A.packed && A.first_live_set == 1) {
+    raster_backward_kernel<true, false, 3, 1, true, true><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
+    if (check_launch("raster_backward_kernel<packed, compact>")) return 1;
+    raster_backward_kernel<true, true, 3, 1, true, true><<<592, 256, 0, st>>>(A);
+    return check_launch("raster_backward_kernel<packed, big, compact>");
+  }
+  return fail("raster_backward: compact mode serves one colour set, or three packed sets with the first detached");
+}
+
 // main pass (one warp per face, huge faces deferred) + CTA-per-face pass over the deferred list
 static int launch_backward(const RasterArgs& A, long long nf, cudaStream_t st) {
   if (cudaMemsetAsync(A.big_list, 0, sizeof(int), st) != cudaSuccess) return fail("raster_backward: memset failed");
@@ -980,6 +1014,7 @@ static int launch_backward(const RasterArgs& A, long long nf, cudaStream_t st) {
     if (vec == 4) raster_pack_kernel<4><<<dim3(gx, A.N), 256, 0, st>>>(A.soft_colors, A.grad_soft_colors, A.aggrs_info, A.pack_area, SS);
     else raster_pack_kernel<1><<<dim3(gx, A.N), 256, 0, st>>>(A.soft_colors, A.grad_soft_colors, A.aggrs_info, A.pack_area, SS);
     if (check_launch("raster_pack_kernel")) return 1;
+    if (A.records_valid == 2) return launch_backward_compact(A, blocks, true, st);
     RasterArgs P = A;
     P.packed = A.pack_area;
     raster_backward_kernel<true, false, 1, 0, true><<<blocks, LASR_BWD_THREADS, 0, st>>>(P);
@@ -987,6 +1022,7 @@ static int launch_backward(const RasterArgs& A, long long nf, cudaStream_t st) {
     raster_backward_kernel<true, true, 1, 0, true><<<592, 256, 0, st>>>(P);
     return check_launch("raster_backward_kernel<packed, big>");
   }
+  if (A.records_valid == 2) return launch_backward_compact(A, blocks, false, st);
   if (A.packed) {   // the fused region's packed per-pixel gradients (lasr_b200_render_backward_packed: K = 3, set 0 detached)
     raster_backward_kernel<true, false, 3, 1, true><<<blocks, LASR_BWD_THREADS, 0, st>>>(A);
     if (check_launch("raster_backward_kernel<packed>")) return 1;
