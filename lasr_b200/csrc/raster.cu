@@ -616,9 +616,11 @@ __global__ void __launch_bounds__(kBig ? 256 : LASR_BWD_THREADS, kBig ? 2 : (K =
   float tex9[9 * K];
   FaceGeom g;
   if (kCompact) {                // the forward's COMPACT record (80 bytes per face) + the op's own inputs
+    float cr[kCompactWords];
+    load_compact(A.compact_record + wg * kCompactWords, cr);     // issued first: one memory round trip with the vertices
     float fv[9];
     fetch_face(A, n, f, fv, tex9, sample == 1);
-    face_from_compact(fv, sthr, A.compact_record + wg * kCompactWords, g);
+    face_from_compact(fv, sthr, cr, g);
   } else if (A.records_valid) {   // the forward's per-face record (the reference hands faces_info to its backward too)
     load_record<K>(A.face_record + wg * kRecWords, g, tex9);
     const float4 bd = __ldg(A.face_border + wg);

@@ -270,18 +270,23 @@ __device__ __forceinline__ void face_setup(const float* __restrict__ fv, float s
 // The face as the backward needs it from the vertices plus the COMPACT record (store_compact): everything that costs a
 // division comes from the record, the rest -- the edge rows and the box: sums, differences, min / max -- is re-derived
 // by the same expressions face_setup uses, so every field has the bits the forward worked with.
-__device__ __forceinline__ void face_from_compact(const float* __restrict__ fv, float sthr, const float* __restrict__ r,
-                                                  FaceGeom& g) {
-  g.x[0] = fv[0]; g.x[1] = fv[3]; g.x[2] = fv[6];
-  g.y[0] = fv[1]; g.y[1] = fv[4]; g.y[2] = fv[7];
-  g.z[0] = fv[2]; g.z[1] = fv[5]; g.z[2] = fv[8];
+// (the record is loaded by its own call so that the kernel can issue these loads BEFORE it fetches the vertices: placed
+// after them, the compiler scheduled the box computation -- a wait for the vertices -- ahead of the record's loads, two
+// memory round trips in a row per face: trip 23's ncu capture)
+__device__ __forceinline__ void load_compact(const float* __restrict__ r, float (&v)[kCompactWords]) {
   const float4* r4 = reinterpret_cast<const float4*>(r);
-  float v[kCompactWords];
 #pragma unroll
   for (int k = 0; k < kCompactWords / 4; ++k) {
     const float4 q = __ldg(r4 + k);
     v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
   }
+}
+
+__device__ __forceinline__ void face_from_compact(const float* __restrict__ fv, float sthr, const float (&v)[kCompactWords],
+                                                  FaceGeom& g) {
+  g.x[0] = fv[0]; g.x[1] = fv[3]; g.x[2] = fv[6];
+  g.y[0] = fv[1]; g.y[1] = fv[4]; g.y[2] = fv[7];
+  g.z[0] = fv[2]; g.z[1] = fv[5]; g.z[2] = fv[8];
 #pragma unroll
   for (int k = 0; k < 9; ++k) g.inv[k] = v[k];
 #pragma unroll

@@ -409,7 +409,9 @@ extern "C" int lasr_host_compact_roundtrip(const float* faces9, int F, float sth
     face_setup(faces9 + 9 * f, sthr, a);
     alignas(16) float rec[kCompactWords];
     store_compact(rec, a);
-    face_from_compact(faces9 + 9 * f, sthr, rec, b);
+    float cr[kCompactWords];
+    load_compact(rec, cr);
+    face_from_compact(faces9 + 9 * f, sthr, cr, b);
     bool same = a.obt == b.obt && a.front == b.front;
     same = same && memcmp(a.inv, b.inv, sizeof a.inv) == 0 && memcmp(a.x, b.x, sizeof a.x) == 0 &&
            memcmp(a.y, b.y, sizeof a.y) == 0 && memcmp(a.z, b.z, sizeof a.z) == 0 && memcmp(a.iz, b.iz, sizeof a.iz) == 0 &&
