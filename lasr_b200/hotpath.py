@@ -60,7 +60,9 @@ class RenderHotPath(torch.nn.Module):
             shared_faces = sr.functional.shared_topology(faces)
         n2 = ppoint.shape[0]          # 2 * bs
         bs = n2 // 2
-        fused_route = o.fused and pred_v.is_cuda and o.opt_tex
+        # (the fused route renders through the indexed kernels: one topology for every frame -- LASR's case; a batch of
+        #  different meshes takes the three-render route, which gathers faces per frame as the reference does)
+        fused_route = o.fused and pred_v.is_cuda and o.opt_tex and shared_faces is not None
         if pred_v.is_cuda:
             # 1') bone composition + LBS + camera + projection + depth window in ONE kernel (lasr_b200_lbs_pose_forward /
             #     lasr_b200_lbs_project_forward): the raw part transforms go in, the joint centres ride along.  Both CUDA
@@ -196,13 +198,14 @@ class RenderHotPath(torch.nn.Module):
         pp_own = rep(ppoint)
         f_own = scale.view(n2, H, -1)[:, :, 0].reshape(nh)
         # frame i pairs with frame i +- bs (mesh_net.py:318-335): entry (n + bs*H) mod n2*H of the same tensors
-        shifted = view is not None and (link is not None or not torch.is_grad_enabled())
+        # (needs the one shared topology `forward` looked up; meshes that differ per frame take the gathered path below)
+        shifted = (view is not None and shared_faces is not None
+                   and (link is not None or not torch.is_grad_enabled()))
         if shifted:
             # the LBS kernel already wrote what lighting (x 1) and the camera make of the mesh, and the pair's positions
             # and intrinsics are the own ones read half a batch further on: no rolled copies, no stacked colour tensor
             rz = r.rasterizer
-            tri = shared_faces if shared_faces is not None else sr.functional.shared_topology(faces_h)
-            image = sr.functional.render_sets(view, (own, own, texc), (0, bs * H, 0), tri, rz.image_size, bg9, near, far,
+            image = sr.functional.render_sets(view, (own, own, texc), (0, bs * H, 0), shared_faces, rz.image_size, bg9, near, far,
                                               rz.fill_back, rz.eps, rz.sigma_val, rz.dist_func, rz.dist_eps, rz.gamma_val,
                                               rz.aggr_func_rgb, rz.aggr_func_alpha, grad_link=link)
             pp_pair, f_pair, pair_shift = pp_own, f_own, bs * H

@@ -146,3 +146,39 @@ def test_module_constructors_refuse_what_the_reference_refuses():
         sr.functional.look_at(torch.zeros(4, 3), [0, 0, -1])          # vertices must be [N,V,3] (look_at.py:16-17)
     with pytest.raises(AssertionError):
         sr.functional.face_vertices(torch.zeros(2, 4, 3), torch.zeros(3, 4, 3, dtype=torch.int32))   # face_vertices.py:10-13 asserts
+
+
+def test_keep_workspace_switch_has_three_settings(monkeypatch):
+    """functional.soft_rasterize.KEEP_WORKSPACE: True (the workspace, 200 B per face), "compact" (80 B per face),
+    False (nothing); anything else is refused when a forward reads it.  The compact buffer is smaller than the
+    reference's faces_info [N,F,27] at every shape LASR uses, so a maintainer can pass that tensor as `saved`."""
+    import sys
+    import lasr_b200.soft_renderer as sr
+    from lasr_b200 import _cabi
+    mod = sys.modules[sr.functional.SoftRasterizeFunction.__module__]
+    for value, mode in ((True, "full"), (False, "none"), ("compact", "compact"), (1, "full"), (0, "none")):
+        monkeypatch.setattr(mod, "KEEP_WORKSPACE", value)
+        assert mod.keep_mode() == mode
+    monkeypatch.setattr(mod, "KEEP_WORKSPACE", "small")
+    with pytest.raises(ValueError):
+        mod.keep_mode()
+    L = _cabi.lib()
+    for N, F, S in ((64, 5856, 256), (8, 1280, 256), (1, 1280, 256), (32, 20480, 512), (80, 10000, 512)):
+        saved = L.lasr_b200_raster_saved_bytes(N, F, S)
+        assert saved <= N * F * 27 * 4 and saved >= N * F * 80
+        assert L.lasr_b200_raster_backward_scratch_bytes(N, F, S) < L.lasr_b200_raster_workspace_bytes(N, F, S)
+    assert L.lasr_b200_raster_saved_bytes(0, 10, 10) == 0
+
+
+def test_boolean_masks_are_reinterpreted_not_converted():
+    """losses._as_u8: a bool mask reaches the kernels as the same bytes (no conversion kernel per step); other dtypes are
+    converted."""
+    import torch
+    from lasr_b200 import losses
+    m = torch.rand(3, 5, 7) > 0.5
+    u = losses._as_u8(m)
+    assert u.dtype == torch.uint8 and u.data_ptr() == m.data_ptr() and torch.equal(u.bool(), m)
+    f = (torch.rand(3, 5) > 0.5).float()
+    assert losses._as_u8(f).dtype == torch.uint8 and torch.equal(losses._as_u8(f).bool(), f.bool())
+    nc = (torch.rand(4, 6) > 0.5).t()
+    assert torch.equal(losses._as_u8(nc).bool(), nc)
