@@ -88,7 +88,9 @@ class PackedGradLink:
         key = (like.device, like.dtype)
         z = PackedGradLink._zero.get(key)
         if z is None:
-            z = PackedGradLink._zero[key] = torch.zeros((), dtype=like.dtype, device=like.device)
+            z = torch.zeros((), dtype=like.dtype, device=like.device)
+            if not (like.is_cuda and torch.cuda.is_current_stream_capturing()):
+                PackedGradLink._zero[key] = z      # (a tensor born inside a graph capture belongs to that graph's pool)
         self.placeholder = z.expand(like.shape)
         return self.placeholder
 
