@@ -298,6 +298,14 @@ int lasr_b200_lbs_pose_backward(const float* verts, const float* Rmat, const flo
                                 size_t workspace_bytes, int N, int V, int B, int n_hypo, int verts_shared,
                                 int skin_shared, int tocam, void* stream);
 
+/* Sums over frames of the per-frame gradients of parameters shared by every frame (lasr_b200_lbs_*_backward writes
+ * grad_verts [N,V,3], grad_skin [N,B-1,V] and grad_rest [N,B-1,3] per frame), one launch for the three:
+ *   sum_verts [V,3], sum_skin [B-1,V], sum_rest [n_hypo,B-1,3] (frames laid out [.., n_hypo]: frame n belongs to
+ *   hypothesis n % n_hypo).  Any input may be NULL together with its output.  Frames are added in order: deterministic. */
+int lasr_b200_lbs_sum_frames(const float* grad_verts, const float* grad_skin, const float* grad_rest,
+                             float* sum_verts, float* sum_skin, float* sum_rest, int num_frames, int num_vertices,
+                             int num_bones, int n_hypo, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Image losses: one fused masked-reduction pass.  Replaces the Python double
  * loops of nnutils/mesh_net.py:372-447 (silhouette :374-390, flow :393-416, texture L1 :420-441;

@@ -77,6 +77,8 @@ def _load_locked():
         L.lasr_b200_raster_backward_compact.restype = _c.c_int
         L.lasr_b200_raster_backward_compact.argtypes = ([_c.c_void_p] * 8 + [_c.c_size_t, _c.c_void_p, _c.c_size_t]
                                                         + _RASTER_SCALARS + [_c.c_void_p])
+        L.lasr_b200_lbs_sum_frames.restype = _c.c_int
+        L.lasr_b200_lbs_sum_frames.argtypes = [_c.c_void_p] * 6 + [_c.c_int] * 4 + [_c.c_void_p]
         L.lasr_b200_render_workspace_bytes.restype = _c.c_size_t
         L.lasr_b200_render_workspace_bytes.argtypes = [_c.c_int, _c.c_int, _c.c_int, _c.c_int]
         _render_scalars = [_c.c_int] * 4 + [_c.c_float, _c.c_float, _c.c_void_p, _c.c_float, _c.c_float, _c.c_int,
@@ -189,6 +191,7 @@ EXPORTED_SYMBOLS = [
     "lasr_b200_raster_backward",
     "lasr_b200_render_workspace_bytes", "lasr_b200_render_forward", "lasr_b200_render_backward",
     "lasr_b200_render_backward_packed", "lasr_b200_render_forward_sets", "lasr_b200_render_backward_sets_packed",
+    "lasr_b200_lbs_sum_frames",
     "lasr_b200_raster_saved_bytes", "lasr_b200_raster_backward_scratch_bytes", "lasr_b200_render_backward_scratch_bytes",
     "lasr_b200_raster_forward_compact", "lasr_b200_raster_backward_compact", "lasr_b200_render_forward_sets_compact",
     "lasr_b200_render_backward_sets_packed_compact", "lasr_b200_head_backward_packed", "lasr_b200_head_backward_packed_shift",
@@ -393,6 +396,22 @@ def lbs_pose_backward(verts, Rmat, Tmat, rest_ts, skin, pp, fl, grad_cam, grad_p
                                                _p(workspace), workspace.numel(), N, V, B, int(n_hypo),
                                                int(verts_shared), int(skin_shared), int(tocam), _stream_ptr())
     _check(rc, "lasr_b200_lbs_pose_backward")
+
+
+def lbs_sum_frames(grad_verts, grad_skin, grad_rest, N, V, B, n_hypo):
+    """Per-frame gradients of shared parameters summed over frames in one launch: -> (sum_verts [V,3] | None,
+    sum_skin [B-1,V] | None, sum_rest [n_hypo,B-1,3] | None), one per non-None input."""
+    ref = next(t for t in (grad_verts, grad_skin, grad_rest) if t is not None)
+    for t in (grad_verts, grad_skin, grad_rest):
+        if t is not None:
+            _require_cuda_f32(t, "lbs gradient")
+    mk = lambda t, *sh: None if t is None else torch.empty(*sh, dtype=torch.float32, device=ref.device)
+    sv, ss, sr = mk(grad_verts, V, 3), mk(grad_skin, max(B - 1, 0), V), mk(grad_rest, int(n_hypo), max(B - 1, 0), 3)
+    with torch.cuda.device(ref.device):
+        rc = lib().lasr_b200_lbs_sum_frames(_p(grad_verts), _p(grad_skin), _p(grad_rest), _p(sv), _p(ss), _p(sr), N, V, B,
+                                            int(n_hypo), _stream_ptr())
+    _check(rc, "lasr_b200_lbs_sum_frames")
+    return sv, ss, sr
 
 
 def render_workspace(N: int, F: int, S: int, device, num_sets: int = 1) -> torch.Tensor:

@@ -477,6 +477,49 @@ static int lbs_backward_impl(const float* verts, const float* Rmat, const float*
   return lasr_check_launch("lbs_reduce_partials_kernel");
 }
 
+namespace lasr {
+// Sums over frames of the per-frame gradients of SHARED parameters, one launch for the three of them (they were three
+// PyTorch reductions per step): out_v [V,3] = sum_n gv[n], out_s [B-1,V] = sum_n gs[n], and -- the frames of a hypothesis,
+// frames laid out [.., n_hypo] -- out_rest [n_hypo,B-1,3] = sum_m grest[m * n_hypo + h].  One thread per output element,
+// frames added in order: deterministic, coalesced across threads.
+__global__ void __launch_bounds__(256) lbs_sum_frames_kernel(const float* __restrict__ gv, const float* __restrict__ gs,
+                                                             const float* __restrict__ grest, float* out_v, float* out_s,
+                                                             float* out_rest, int N, int V, int B, int n_hypo) {
+  const long long nv = gv ? 3LL * V : 0, ns = gs ? (long long)(B - 1) * V : 0;
+  const long long nr = grest ? (long long)n_hypo * (B - 1) * 3 : 0;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float* src;
+  float* dst;
+  long long stride;
+  int count;
+  if (t < nv) { src = gv + t; dst = out_v + t; stride = nv; count = N; }
+  else if (t < nv + ns) { src = gs + (t - nv); dst = out_s + (t - nv); stride = ns; count = N; }
+  else if (t < nv + ns + nr) { src = grest + (t - nv - ns); dst = out_rest + (t - nv - ns); stride = nr; count = N / n_hypo; }
+  else return;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int n = 0; n < count; ++n) acc += __ldg(src + (long long)n * stride);
+  *dst = acc;
+}
+
+}  // namespace lasr
+
+extern "C" int lasr_b200_lbs_sum_frames(const float* grad_verts, const float* grad_skin, const float* grad_rest,
+                                        float* sum_verts, float* sum_skin, float* sum_rest, int N, int V, int B,
+                                        int n_hypo, void* stream) {
+  if (N <= 0 || V <= 0 || B < 1 || n_hypo < 1 || N % n_hypo != 0) return lasr_fail("lbs_sum_frames: bad sizes");
+  if ((grad_verts == nullptr) != (sum_verts == nullptr) || (grad_skin == nullptr) != (sum_skin == nullptr) ||
+      (grad_rest == nullptr) != (sum_rest == nullptr))
+    return lasr_fail("lbs_sum_frames: every input needs its output and vice versa");
+  if ((grad_skin || grad_rest) && B < 2) return lasr_fail("lbs_sum_frames: skin / rest gradients need at least one part");
+  const long long tot = (grad_verts ? 3LL * V : 0) + (grad_skin ? (long long)(B - 1) * V : 0) +
+                        (grad_rest ? (long long)n_hypo * (B - 1) * 3 : 0);
+  if (tot == 0) return lasr_fail("lbs_sum_frames: nothing to sum");
+  lbs_sum_frames_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      grad_verts, grad_skin, grad_rest, sum_verts, sum_skin, sum_rest, N, V, B, n_hypo);
+  return lasr_check_launch("lbs_sum_frames_kernel");
+}
+
 extern "C" int lasr_b200_lbs_project_backward(const float* verts, const float* Rmat, const float* Tmat,
                                               const float* skin, const float* pp, const float* fl,
                                               const float* grad_cam, const float* grad_px, float* grad_verts,

@@ -85,20 +85,26 @@ class SkinProjectFunction(Function):
         gpp = torch.empty(N, 2, dtype=torch.float32, device=dev) if project else None
         gfl = torch.empty(N, dtype=torch.float32, device=dev) if project else None
         ws = _cabi.lbs_workspace(N, V, B, dev)
-        g_rest = None
+        g_rest = g_rest_f = None
         if rest is not None or g_view is not None:
             g_rest_f = torch.empty(N, B - 1, 3, dtype=torch.float32, device=dev) if rest is not None else None
             _cabi.lbs_pose_backward(verts, R, T, rest, sk, pp, fl, g_cam, g_px, g_view, gv, gR, gT, g_rest_f, gs, gpp, gfl,
                                     ws, N, V, B, n_hypo, vs, ss, tocam)
-            if rest is not None:
-                g_rest = g_rest_f.view(N // n_hypo, n_hypo * (B - 1), 3).sum(0).reshape(restshape)   # frames of a hypothesis
         else:
             _cabi.lbs_project_backward(verts, R, T, sk, pp, fl, g_cam, g_px, gv, gR, gT, gs, gpp, gfl, ws, N, V, B, vs,
                                        ss, tocam)
-        if vs:
-            gv = gv.sum(0, keepdim=True)
-        if gs is not None and ss:
-            gs = gs.sum(0, keepdim=True)
+        # gradients of parameters every frame shares: summed over frames (and g_rest over the frames of a hypothesis) in
+        # ONE launch -- they were three PyTorch reductions per step
+        g_rest_f = g_rest_f if rest is not None else None
+        want_v, want_s = bool(vs), bool(gs is not None and ss)
+        if want_v or want_s or g_rest_f is not None:
+            sv, ssum, srest = _cabi.lbs_sum_frames(gv if want_v else None, gs if want_s else None, g_rest_f, N, V, B, n_hypo)
+            if want_v:
+                gv = sv[None]
+            if want_s:
+                gs = ssum[None]
+            if srest is not None:
+                g_rest = srest.reshape(restshape)
         return (gv.reshape(vshape), gR.reshape(rshape), gT.reshape(tshape),
                 gs.reshape(sshape) if gs is not None else None,
                 gpp.reshape(ppshape) if project else None, gfl.reshape(flshape) if project else None,

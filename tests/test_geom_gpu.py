@@ -243,3 +243,26 @@ def test_bone_composition_inside_the_lbs_kernel_equals_the_pytorch_composition(d
     for k in leaves:
         err = float((a[4][k] - b[4][k]).norm() / b[4][k].norm())
         assert err < 2e-5, (k, err)
+
+
+def test_frame_sums_of_shared_parameter_gradients_in_one_launch():
+    """lasr_b200_lbs_sum_frames: per-frame gradients of the shared mesh, the shared skinning weights and the joint centres
+    (frames of one hypothesis) summed in one launch == the three PyTorch reductions it replaces."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from lasr_b200 import _cabi
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(5)
+    for N, V, B, H in ((8, 642, 26, 1), (6, 100, 4, 2), (64, 2930, 26, 1), (3, 7, 2, 3)):
+        gv = torch.randn(N, V, 3, generator=g).to(dev)
+        gs = torch.randn(N, B - 1, V, generator=g).to(dev)
+        gr = torch.randn(N, B - 1, 3, generator=g).to(dev)
+        sv, ss, sr = _cabi.lbs_sum_frames(gv, gs, gr, N, V, B, H)
+        tol = dict(rtol=1e-5, atol=1e-5)
+        assert torch.allclose(sv, gv.double().sum(0).float(), **tol)
+        assert torch.allclose(ss, gs.double().sum(0).float(), **tol)
+        assert torch.allclose(sr.reshape(H * (B - 1), 3), gr.double().view(N // H, H * (B - 1), 3).sum(0).float(), **tol)
+        only_v = _cabi.lbs_sum_frames(gv, None, None, N, V, B, H)
+        assert only_v[1] is None and only_v[2] is None and torch.equal(only_v[0], sv)
+        only_r = _cabi.lbs_sum_frames(None, None, gr, N, V, B, H)
+        assert only_r[0] is None and torch.equal(only_r[2], sr)
